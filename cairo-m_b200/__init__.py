@@ -1,0 +1,177 @@
+"""cairo-m_b200 — B200-native proving hot path of cairo-m (Stwo Backend ops on sm_100a).
+
+Python is only the test/bench harness here: it binds the C ABI of ``libcm31.so`` (declared in
+``include/cm31.h``) with ctypes and hands it device pointers of torch tensors.  The library must
+exist; there is no CPU fallback (``RuntimeError`` if it is missing or fails to load).
+
+Import with ``importlib.import_module("cairo-m_b200")`` (the directory name is not an identifier).
+"""
+from __future__ import annotations
+
+import ctypes
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libcm31.so"
+
+P = (1 << 31) - 1
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded C-ABI library; raises loudly when the CUDA extension is missing."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python cairo-m_b200/build.py` "
+                "(there is no CPU fallback for the product path)")
+        _lib = ctypes.CDLL(str(LIB_PATH), mode=ctypes.RTLD_GLOBAL)
+        _lib.cm31_last_error.restype = C.c_char_p
+    return _lib
+
+
+class Cm31Error(RuntimeError):
+    pass
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise Cm31Error(lib().cm31_last_error().decode() or f"cm31 status {status}")
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if hasattr(t, "data_ptr") else int(t)
+    return arr
+
+
+def _u32_array(values):
+    arr = (C.c_uint32 * len(values))()
+    for i, v in enumerate(values):
+        arr[i] = int(v)
+    return arr
+
+
+def _qm(v):
+    return _u32_array(list(v))
+
+
+class Twiddles:
+    """PolyOps::precompute_twiddles for CanonicCoset(log_size).half_coset()."""
+
+    def __init__(self, log_size: int):
+        self.log_size = log_size
+        self.handle = C.c_void_p()
+        check(lib().cm31_twiddles_create(C.c_uint32(log_size), C.byref(self.handle)))
+
+    def buffers(self):
+        import torch
+        tw, itw, ls = C.c_void_p(), C.c_void_p(), C.c_uint32()
+        check(lib().cm31_twiddles_buffers(self.handle, C.byref(tw), C.byref(itw), C.byref(ls)))
+        n = 1 << (ls.value - 1)
+        host_tw = (C.c_uint32 * n)()
+        host_itw = (C.c_uint32 * n)()
+        check(lib().cm31_d2h(host_tw, tw, C.c_size_t(4 * n)))
+        check(lib().cm31_d2h(host_itw, itw, C.c_size_t(4 * n)))
+        return list(host_tw), list(host_itw)
+
+    def close(self):
+        if self.handle:
+            lib().cm31_twiddles_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sync():
+    check(lib().cm31_sync())
+
+
+def interpolate_batch(cols, log_size: int, tw: Twiddles) -> None:
+    """In place: evaluations (bit-reversed canonic circle domain) -> FFT-basis coefficients."""
+    check(lib().cm31_interpolate_batch(_ptr_array(cols), C.c_size_t(len(cols)), C.c_uint32(log_size), tw.handle))
+
+
+def evaluate_batch(coeffs, out, log_size: int, log_eval_size: int, tw: Twiddles) -> None:
+    check(lib().cm31_evaluate_batch(_ptr_array(coeffs), _ptr_array(out), C.c_size_t(len(coeffs)),
+                                    C.c_uint32(log_size), C.c_uint32(log_eval_size), tw.handle))
+
+
+def eval_at_point_batch(coeffs, log_sizes, points, point_idx):
+    """points: list of 8-tuples (x QM31, y QM31); returns list of 4-tuples."""
+    n = len(coeffs)
+    flat_pts = [w for p in points for w in p]
+    out = (C.c_uint32 * (4 * n))()
+    check(lib().cm31_eval_at_point_batch(_ptr_array(coeffs), _u32_array(log_sizes), C.c_size_t(n),
+                                         _u32_array(flat_pts), C.c_size_t(len(points)), _u32_array(point_idx), out))
+    return [tuple(out[4 * i:4 * i + 4]) for i in range(n)]
+
+
+def bit_reverse(col, log_size: int) -> None:
+    check(lib().cm31_bit_reverse(C.c_void_p(col.data_ptr()), C.c_uint32(log_size)))
+
+
+def blake2s_commit_layer(log_size: int, prev_layer, cols, out_layer) -> None:
+    prev = C.c_void_p(prev_layer.data_ptr()) if prev_layer is not None else C.c_void_p()
+    check(lib().cm31_blake2s_commit_layer(C.c_uint32(log_size), prev, _ptr_array(cols), C.c_size_t(len(cols)),
+                                          C.c_void_p(out_layer.data_ptr())))
+
+
+def fold_line(src4, log_size: int, alpha, tw: Twiddles, dst4) -> None:
+    check(lib().cm31_fold_line(_ptr_array(src4), C.c_uint32(log_size), _qm(alpha), tw.handle, _ptr_array(dst4)))
+
+
+def fold_circle_into_line(dst4, src4, log_size: int, alpha, tw: Twiddles) -> None:
+    check(lib().cm31_fold_circle_into_line(_ptr_array(dst4), _ptr_array(src4), C.c_uint32(log_size), _qm(alpha),
+                                           tw.handle))
+
+
+def decompose(src4, log_size: int, dst4):
+    lam = (C.c_uint32 * 4)()
+    check(lib().cm31_decompose(_ptr_array(src4), C.c_uint32(log_size), _ptr_array(dst4), lam))
+    return tuple(lam)
+
+
+def accumulate(dst4, src4, n: int) -> None:
+    check(lib().cm31_accumulate(_ptr_array(dst4), _ptr_array(src4), C.c_size_t(n)))
+
+
+def secure_powers(felt, n: int):
+    out = (C.c_uint32 * (4 * n))()
+    check(lib().cm31_secure_powers(_qm(felt), C.c_size_t(n), out))
+    return [tuple(out[4 * i:4 * i + 4]) for i in range(n)]
+
+
+def accumulate_quotients(log_size: int, cols, random_coeff, batches, out4) -> None:
+    """batches: list of (point 8-tuple, [(col_idx, value 4-tuple), ...])."""
+    pts, starts, idx, vals = [], [0], [], []
+    for point, cvs in batches:
+        pts.extend(point)
+        for ci, v in cvs:
+            idx.append(ci)
+            vals.extend(v)
+        starts.append(len(idx))
+    check(lib().cm31_accumulate_quotients(C.c_uint32(log_size), _ptr_array(cols), C.c_size_t(len(cols)),
+                                          _qm(random_coeff), C.c_size_t(len(batches)), _u32_array(pts),
+                                          _u32_array(starts), _u32_array(idx), _u32_array(vals), _ptr_array(out4)))
+
+
+def grind_blake2s(digest: bytes, pow_bits: int) -> int:
+    nonce = C.c_uint64()
+    buf = (C.c_uint8 * 32).from_buffer_copy(digest)
+    check(lib().cm31_grind_blake2s(buf, C.c_uint32(pow_bits), C.byref(nonce)))
+    return nonce.value
+
+
+def gather_u32(cols, idx):
+    out = (C.c_uint32 * (len(cols) * len(idx)))()
+    check(lib().cm31_gather_u32(_ptr_array(cols), C.c_size_t(len(cols)), _u32_array(idx), C.c_size_t(len(idx)), out))
+    return [list(out[c * len(idx):(c + 1) * len(idx)]) for c in range(len(cols))]

@@ -1,0 +1,53 @@
+// Shared runtime pieces of libcm31: error reporting, stream, device scratch for pointer tables.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/cm31.h"
+#include "field.cuh"
+
+namespace cm31 {
+
+void set_error(const std::string& msg);
+cudaStream_t stream();
+
+#define CM_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            cm31::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+            return (int)_e;                                                                    \
+        }                                                                                      \
+    } while (0)
+
+#define CM_REQUIRE(cond, msg)                                    \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            cm31::set_error(std::string("cm31: ") + (msg));      \
+            return -1;                                           \
+        }                                                        \
+    } while (0)
+
+#define CM_LAUNCH_CHECK() CM_CUDA(cudaGetLastError())
+
+// Uploads a small host table (pointer arrays, programs, constants) into a per-call device
+// allocation from a stream-ordered pool. Freed with release() (stream ordered).
+struct DeviceTable {
+    void* d = nullptr;
+    int upload(const void* host, size_t bytes);
+    void release();
+    ~DeviceTable() { release(); }
+};
+
+struct cm31_twiddles_impl {
+    uint32_t log_size;  // max circle-domain log size served
+    uint32_t* tw;       // 2^(log_size-1) words
+    uint32_t* itw;
+};
+
+}  // namespace cm31
+
+struct cm31_twiddles : cm31::cm31_twiddles_impl {};

@@ -1,0 +1,329 @@
+// FriOps, AccumulationOps and QuotientOps on sm_100a.
+//
+// Replaces external/stwo/crates/prover/src/core/backend/simd/fri.rs:24-165,
+// simd/accumulation.rs:11-39, simd/quotients.rs:33-265; defined by core/fri.rs:1132-1189,
+// cpu/fri.rs:29-85, cpu/accumulation.rs:8-25, cpu/quotients.rs:18-146.
+// All kernels are one-thread-per-output-row streaming kernels over SoA QM31 columns.
+#include "circle.hpp"
+#include "common.cuh"
+
+namespace cm31 {
+
+struct Ptr4 {
+    u32* p[4];
+};
+struct CPtr4 {
+    const u32* p[4];
+};
+__device__ __forceinline__ QM31 ld4(const CPtr4& c, size_t i) {
+    return qm_make(__ldg(c.p[0] + i), __ldg(c.p[1] + i), __ldg(c.p[2] + i), __ldg(c.p[3] + i));
+}
+__device__ __forceinline__ QM31 ld4(const Ptr4& c, size_t i) { return qm_make(c.p[0][i], c.p[1][i], c.p[2][i], c.p[3][i]); }
+__device__ __forceinline__ void st4(const Ptr4& c, size_t i, QM31 v) {
+    c.p[0][i] = v.a;
+    c.p[1][i] = v.b;
+    c.p[2][i] = v.c;
+    c.p[3][i] = v.d;
+}
+
+// fold_line (fri.rs:1132-1157): pair (2i, 2i+1), twiddle = 1/x of domain.at(bit_reverse(2i)).
+// itw_layer = inverse twiddles of the tree level whose coset is the line domain's coset.
+__global__ void fold_line_kernel(CPtr4 src, Ptr4 dst, size_t n_out, QM31 alpha, const u32* __restrict__ itw_layer) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    QM31 f0 = ld4(src, 2 * i), f1 = ld4(src, 2 * i + 1);
+    u32 it = __ldg(itw_layer + i);
+    QM31 s = qm_add(f0, f1);
+    QM31 d = qm_mul_m31(qm_sub(f0, f1), it);
+    st4(dst, i, qm_add(s, qm_mul(alpha, d)));
+}
+
+// fold_circle_into_line (fri.rs:1159-1189): twiddle = 1/y of domain.at(bit_reverse(2i)), derived
+// from the first line layer pairs [x, y] -> [y, -y, -x, x]  (cpu/circle.rs:209-229).
+__global__ void fold_circle_kernel(Ptr4 dst, CPtr4 src, size_t n_out, QM31 alpha, QM31 alpha_sq,
+                                   const u32* __restrict__ itw_line0) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    QM31 f0 = ld4(src, 2 * i), f1 = ld4(src, 2 * i + 1);
+    u32 x = __ldg(itw_line0 + 2 * (i >> 2)), y = __ldg(itw_line0 + 2 * (i >> 2) + 1);
+    u32 sel = (u32)i & 3;
+    u32 v = sel < 2 ? y : x;
+    u32 it = (sel == 1 || sel == 2) ? m31_neg(v) : v;
+    QM31 s = qm_add(f0, f1);
+    QM31 d = qm_mul_m31(qm_sub(f0, f1), it);
+    QM31 fp = qm_add(qm_mul(alpha, d), s);
+    st4(dst, i, qm_add(qm_mul(ld4(dst, i), alpha_sq), fp));
+}
+
+// circle domains of log size <= 2 have no [x,y] twiddle pair in the tree: explicit 1/y values.
+__global__ void fold_circle_small_kernel(Ptr4 dst, CPtr4 src, u32 n_out, QM31 alpha, QM31 alpha_sq, u32 iy0, u32 iy1) {
+    u32 i = threadIdx.x;
+    if (i >= n_out) return;
+    QM31 f0 = ld4(src, 2 * i), f1 = ld4(src, 2 * i + 1);
+    u32 it = i == 0 ? iy0 : iy1;
+    QM31 s = qm_add(f0, f1);
+    QM31 d = qm_mul_m31(qm_sub(f0, f1), it);
+    QM31 fp = qm_add(qm_mul(alpha, d), s);
+    st4(dst, i, qm_add(qm_mul(ld4(dst, i), alpha_sq), fp));
+}
+
+__global__ void accumulate_kernel(Ptr4 dst, CPtr4 src, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int k = 0; k < 4; k++) dst.p[k][i] = m31_add(dst.p[k][i], __ldg(src.p[k] + i));
+}
+
+// decompose (cpu/fri.rs:29-85): lambda = (sum first half - sum second half) / n; g = f -/+ lambda.
+__global__ void decompose_sum_kernel(CPtr4 src, size_t n, unsigned long long* sums /* 8: lo[4], hi[4] */) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool hi = i >= n / 2;
+#pragma unroll
+    for (int k = 0; k < 4; k++) atomicAdd(&sums[(hi ? 4 : 0) + k], (unsigned long long)__ldg(src.p[k] + i));
+}
+__global__ void decompose_apply_kernel(CPtr4 src, Ptr4 dst, size_t n, QM31 lambda) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    QM31 v = ld4(src, i);
+    st4(dst, i, i < n / 2 ? qm_sub(v, lambda) : qm_add(v, lambda));
+}
+
+// ------------------------------------------------------------------ DEEP quotients
+struct QuotBatch {
+    u32 prx[2], pry[2], pix[2], piy[2];  // point = (prx + u*pix, pry + u*piy), each CM31
+    u32 batch_coeff[4];                  // alpha^(#columns in batch)
+    u32 sum_a[4], sum_b[4];              // sum_i alpha^i a_i, sum_i alpha^i b_i
+    u32 start, end;                      // range into the (col_idx, c) tables
+};
+
+__device__ __forceinline__ CirclePointM31 domain_point_bitrev(u32 row, u32 log_size, u32 half_initial, u32 half_step,
+                                                               const CirclePointM31* __restrict__ gen_pow) {
+    // CircleDomain::at(bit_reverse(row))  (poly/circle/domain.rs:57-63)
+    u32 d = bit_reverse(row, log_size);
+    u32 half = 1u << (log_size - 1);
+    bool conj = d >= half;
+    u32 dd = conj ? d - half : d;
+    u32 idx = (u32)((half_initial + (u64)half_step * dd) & 0x7fffffffu);
+    if (conj) idx = (u32)(((1ull << 31) - idx) & 0x7fffffffu);
+    CirclePointM31 res = {1, 0};
+#pragma unroll 1
+    for (u32 bit = 0; bit < 31; bit++) {
+        if (idx & (1u << bit)) res = cp_add(res, gen_pow[bit]);
+    }
+    return res;
+}
+
+// accumulate_row_quotients (cpu/quotients.rs:45-78) with the per-batch sums of the line
+// coefficients a_i, b_i hoisted out of the column loop:
+//   num = sum_i c_i * f_i(row)  -  (A * y + B),   row = row*alpha^n_b + num / den.
+__global__ void __launch_bounds__(256) quotients_kernel(u32 log_size, const u32* const* __restrict__ cols,
+                                                        const QuotBatch* __restrict__ batches, u32 n_batches,
+                                                        const u32* __restrict__ col_idx, const u32* __restrict__ coef_c,
+                                                        u32 half_initial, u32 half_step,
+                                                        const CirclePointM31* __restrict__ gen_pow, Ptr4 out) {
+    size_t row = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (row >= ((size_t)1 << log_size)) return;
+    CirclePointM31 p = domain_point_bitrev((u32)row, log_size, half_initial, half_step, gen_pow);
+    QM31 acc = qm_zero();
+    for (u32 b = 0; b < n_batches; b++) {
+        const QuotBatch qb = batches[b];
+        QM31 num = qm_zero();
+        for (u32 k = qb.start; k < qb.end; k++) {
+            u32 f = __ldg(cols[__ldg(col_idx + k)] + row);
+            const u32* c = coef_c + (size_t)k * 4;
+            num = qm_add(num, qm_mul_m31(qm_make(__ldg(c), __ldg(c + 1), __ldg(c + 2), __ldg(c + 3)), f));
+        }
+        QM31 A = qm_make(qb.sum_a[0], qb.sum_a[1], qb.sum_a[2], qb.sum_a[3]);
+        QM31 B = qm_make(qb.sum_b[0], qb.sum_b[1], qb.sum_b[2], qb.sum_b[3]);
+        num = qm_sub(num, qm_add(qm_mul_m31(A, p.y), B));
+        // den = (prx - x) * piy - (pry - y) * pix      (cpu/quotients.rs:127-139)
+        CM31 prx = cm_make(qb.prx[0], qb.prx[1]), pry = cm_make(qb.pry[0], qb.pry[1]);
+        CM31 pix = cm_make(qb.pix[0], qb.pix[1]), piy = cm_make(qb.piy[0], qb.piy[1]);
+        CM31 den = cm_sub(cm_mul(cm_make(m31_sub(prx.a, p.x), prx.b), piy),
+                          cm_mul(cm_make(m31_sub(pry.a, p.y), pry.b), pix));
+        CM31 di = cm_inv(den);
+        QM31 bc = qm_make(qb.batch_coeff[0], qb.batch_coeff[1], qb.batch_coeff[2], qb.batch_coeff[3]);
+        acc = qm_add(qm_mul(acc, bc), qm_mul_cm31(num, di));
+    }
+    st4(out, row, acc);
+}
+
+static const u32* tree_level_for_line_coset(const cm31_twiddles* tw, bool inverse, u32 coset_log_size) {
+    // level whose coset is half_odds(coset_log_size): offset 2^(M-1) - 2^coset_log_size
+    const u32* base = inverse ? tw->itw : tw->tw;
+    return base + (((size_t)1 << (tw->log_size - 1)) - ((size_t)1 << coset_log_size));
+}
+
+}  // namespace cm31
+
+using namespace cm31;
+
+static inline QM31 qm_from_arr(const uint32_t v[4]) { return qm_make(v[0], v[1], v[2], v[3]); }
+
+extern "C" {
+
+int cm31_fold_line(const uint32_t* const src4[4], uint32_t log_size, const uint32_t alpha[4], const cm31_twiddles* tw,
+                   uint32_t* const dst4[4]) {
+    CM_REQUIRE(log_size >= 1, "fold_line: evaluation too small");
+    CM_REQUIRE(tw && log_size + 1 <= tw->log_size, "fold_line: twiddle tree too small");
+    CPtr4 s;
+    Ptr4 d;
+    for (int k = 0; k < 4; k++) {
+        s.p[k] = src4[k];
+        d.p[k] = dst4[k];
+    }
+    size_t n_out = (size_t)1 << (log_size - 1);
+    const u32* itw = tree_level_for_line_coset(tw, true, log_size);
+    fold_line_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, stream()>>>(s, d, n_out, qm_from_arr(alpha), itw);
+    CM_LAUNCH_CHECK();
+    return 0;
+}
+
+int cm31_fold_circle_into_line(uint32_t* const dst4[4], const uint32_t* const src4[4], uint32_t log_size,
+                               const uint32_t alpha[4], const cm31_twiddles* tw) {
+    CM_REQUIRE(log_size >= 1, "fold_circle_into_line: evaluation too small");
+    CPtr4 s;
+    Ptr4 d;
+    for (int k = 0; k < 4; k++) {
+        s.p[k] = src4[k];
+        d.p[k] = dst4[k];
+    }
+    size_t n_out = (size_t)1 << (log_size - 1);
+    QM31 a = qm_from_arr(alpha);
+    QM31 a2 = qm_sqr(a);
+    if (log_size <= 2) {
+        CircleDomain dom = CanonicCoset(log_size).circle_domain();
+        u32 iy0 = m31_inv(dom.at(bit_reverse(0, log_size)).y);
+        u32 iy1 = log_size == 2 ? m31_inv(dom.at(bit_reverse(2, log_size)).y) : 0;
+        fold_circle_small_kernel<<<1, 32, 0, stream()>>>(d, s, (u32)n_out, a, a2, iy0, iy1);
+    } else {
+        CM_REQUIRE(tw && log_size <= tw->log_size, "fold_circle_into_line: twiddle tree too small");
+        const u32* itw0 = tree_level_for_line_coset(tw, true, log_size - 1);
+        fold_circle_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, stream()>>>(d, s, n_out, a, a2, itw0);
+    }
+    CM_LAUNCH_CHECK();
+    return 0;
+}
+
+int cm31_accumulate(uint32_t* const dst4[4], const uint32_t* const src4[4], size_t n) {
+    CPtr4 s;
+    Ptr4 d;
+    for (int k = 0; k < 4; k++) {
+        s.p[k] = src4[k];
+        d.p[k] = dst4[k];
+    }
+    if (n == 0) return 0;
+    accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(d, s, n);
+    CM_LAUNCH_CHECK();
+    return 0;
+}
+
+int cm31_secure_powers(const uint32_t felt[4], size_t n_powers, uint32_t* out_host) {
+    // sequential by definition (cpu/accumulation.rs:17-25); n is the constraint count (hundreds)
+    QM31 f = qm_from_arr(felt), acc = qm_one();
+    for (size_t i = 0; i < n_powers; i++) {
+        out_host[4 * i] = acc.a;
+        out_host[4 * i + 1] = acc.b;
+        out_host[4 * i + 2] = acc.c;
+        out_host[4 * i + 3] = acc.d;
+        acc = qm_mul(acc, f);
+    }
+    return 0;
+}
+
+int cm31_decompose(const uint32_t* const src4[4], uint32_t log_size, uint32_t* const dst4[4], uint32_t lambda_out[4]) {
+    CM_REQUIRE(log_size >= 1, "decompose: evaluation too small");
+    CPtr4 s;
+    Ptr4 d;
+    for (int k = 0; k < 4; k++) {
+        s.p[k] = src4[k];
+        d.p[k] = dst4[k];
+    }
+    size_t n = (size_t)1 << log_size;
+    unsigned long long* dsums = nullptr;
+    CM_CUDA(cudaMallocAsync(&dsums, 64, stream()));
+    CM_CUDA(cudaMemsetAsync(dsums, 0, 64, stream()));
+    decompose_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(s, n, dsums);
+    CM_LAUNCH_CHECK();
+    unsigned long long h[8];
+    CM_CUDA(cudaMemcpyAsync(h, dsums, 64, cudaMemcpyDeviceToHost, stream()));
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    CM_CUDA(cudaFreeAsync(dsums, stream()));
+    u32 lo[4], hi[4];
+    for (int k = 0; k < 4; k++) {
+        lo[k] = m31_reduce64(h[k]);
+        hi[k] = m31_reduce64(h[4 + k]);
+    }
+    u32 n_inv = m31_inv((u32)(n % P));
+    QM31 lam = qm_mul_m31(qm_sub(qm_make(lo[0], lo[1], lo[2], lo[3]), qm_make(hi[0], hi[1], hi[2], hi[3])), n_inv);
+    lambda_out[0] = lam.a;
+    lambda_out[1] = lam.b;
+    lambda_out[2] = lam.c;
+    lambda_out[3] = lam.d;
+    decompose_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(s, d, n, lam);
+    CM_LAUNCH_CHECK();
+    return 0;
+}
+
+int cm31_accumulate_quotients(uint32_t log_size, const uint32_t* const* cols, size_t n_cols,
+                              const uint32_t random_coeff[4], size_t n_batches, const uint32_t* batch_points_host,
+                              const uint32_t* batch_start_host, const uint32_t* col_idx_host,
+                              const uint32_t* values_host, uint32_t* const out4[4]) {
+    CM_REQUIRE(log_size >= 1 && log_size <= 30, "accumulate_quotients: bad log_size");
+    QM31 alpha = qm_from_arr(random_coeff);
+    size_t n_entries = batch_start_host[n_batches];
+    std::vector<QuotBatch> qb(n_batches);
+    std::vector<u32> coef_c(n_entries * 4 + 4);
+    for (size_t b = 0; b < n_batches; b++) {
+        const u32* pt = batch_points_host + b * 8;
+        QM31 px = qm_make(pt[0], pt[1], pt[2], pt[3]), py = qm_make(pt[4], pt[5], pt[6], pt[7]);
+        CM_REQUIRE(!(py.c == 0 && py.d == 0), "accumulate_quotients: sample point on the conjugate line");
+        QuotBatch& q = qb[b];
+        q.prx[0] = px.a; q.prx[1] = px.b; q.pix[0] = px.c; q.pix[1] = px.d;
+        q.pry[0] = py.a; q.pry[1] = py.b; q.piy[0] = py.c; q.piy[1] = py.d;
+        q.start = batch_start_host[b];
+        q.end = batch_start_host[b + 1];
+        // column_line_coeffs (cpu/quotients.rs:84-108) + complex_conjugate_line_coeffs (constraints.rs:98-113)
+        QM31 al = qm_one(), sa = qm_zero(), sb = qm_zero();
+        QM31 c = qm_sub(qm_conj(py), py);
+        for (u32 k = q.start; k < q.end; k++) {
+            CM_REQUIRE(col_idx_host[k] < n_cols, "accumulate_quotients: column index out of range");
+            al = qm_mul(al, alpha);
+            QM31 v = qm_from_arr(values_host + (size_t)k * 4);
+            QM31 a = qm_sub(qm_conj(v), v);
+            QM31 bq = qm_sub(qm_mul(v, c), qm_mul(a, py));
+            sa = qm_add(sa, qm_mul(al, a));
+            sb = qm_add(sb, qm_mul(al, bq));
+            QM31 ac = qm_mul(al, c);
+            coef_c[k * 4] = ac.a; coef_c[k * 4 + 1] = ac.b; coef_c[k * 4 + 2] = ac.c; coef_c[k * 4 + 3] = ac.d;
+        }
+        QM31 bc = qm_pow(alpha, q.end - q.start);
+        q.batch_coeff[0] = bc.a; q.batch_coeff[1] = bc.b; q.batch_coeff[2] = bc.c; q.batch_coeff[3] = bc.d;
+        q.sum_a[0] = sa.a; q.sum_a[1] = sa.b; q.sum_a[2] = sa.c; q.sum_a[3] = sa.d;
+        q.sum_b[0] = sb.a; q.sum_b[1] = sb.b; q.sum_b[2] = sb.c; q.sum_b[3] = sb.d;
+    }
+    std::vector<CirclePointM31> gen_pow(31);
+    CirclePointM31 g = {M31_CIRCLE_GEN_X, M31_CIRCLE_GEN_Y};
+    for (int i = 0; i < 31; i++) {
+        gen_pow[i] = g;
+        g = cp_double(g);
+    }
+    DeviceTable dcols, dqb, didx, dc, dgen;
+    if (int e = dcols.upload(cols, n_cols * sizeof(void*))) return e;
+    if (int e = dqb.upload(qb.data(), qb.size() * sizeof(QuotBatch))) return e;
+    if (int e = didx.upload(col_idx_host, n_entries * 4)) return e;
+    if (int e = dc.upload(coef_c.data(), coef_c.size() * 4)) return e;
+    if (int e = dgen.upload(gen_pow.data(), gen_pow.size() * sizeof(CirclePointM31))) return e;
+    Ptr4 o;
+    for (int k = 0; k < 4; k++) o.p[k] = out4[k];
+    Coset half = CanonicCoset(log_size).half_coset();
+    size_t n = (size_t)1 << log_size;
+    quotients_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(
+        log_size, (const u32* const*)dcols.d, (const QuotBatch*)dqb.d, (u32)n_batches, (const u32*)didx.d,
+        (const u32*)dc.d, half.initial_index, half.step_size, (const CirclePointM31*)dgen.d, o);
+    CM_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

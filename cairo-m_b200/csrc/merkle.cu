@@ -1,0 +1,117 @@
+// MerkleOps<Blake2sMerkleHasher>::commit_on_layer and GrindOps on sm_100a.
+//
+// Replaces external/stwo/crates/prover/src/core/backend/simd/blake2s.rs:60-142 (commit_on_layer),
+// simd/grind.rs:21-71; defined by cpu/blake2s.rs:9-23 + vcs/blake2_merkle.rs:14-30 and
+// cpu/grind.rs:5-16.
+//
+// One thread per Merkle node: consecutive threads read consecutive words of every column
+// (coalesced 128 B per warp per column) and write 32 contiguous bytes each.  The message block
+// lives in 16 registers and is refilled 16 columns at a time.
+#include "blake2s.cuh"
+#include "common.cuh"
+
+namespace cm31 {
+
+__global__ void __launch_bounds__(256) merkle_layer_kernel(u32 log_size, const u32* __restrict__ prev,
+                                                           const u32* const* __restrict__ cols, u32 n_cols,
+                                                           u32* __restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= ((size_t)1 << log_size)) return;
+    Blake2sState st;
+    blake2s_init(st);
+    u32 m[16];
+    const u64 total = (prev ? 64ull : 0ull) + 4ull * n_cols;
+    u64 done = 0;
+    if (prev) {
+        const uint4* p4 = reinterpret_cast<const uint4*>(prev + i * 16);
+        uint4 a = __ldg(p4), b = __ldg(p4 + 1), c = __ldg(p4 + 2), d = __ldg(p4 + 3);
+        m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
+        m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+        m[8] = c.x; m[9] = c.y; m[10] = c.z; m[11] = c.w;
+        m[12] = d.x; m[13] = d.y; m[14] = d.z; m[15] = d.w;
+        done = 64;
+        blake2s_compress(st, m, done, done == total);
+    }
+    for (u32 c0 = 0; c0 < n_cols || (total == 0 && c0 == 0); c0 += 16) {
+        u32 nb = min(16u, n_cols - c0);
+#pragma unroll
+        for (u32 k = 0; k < 16; k++) m[k] = (k < nb) ? __ldg(cols[c0 + k] + i) : 0u;
+        done += 4ull * nb;
+        blake2s_compress(st, m, done, done == total);
+        if (total == 0) break;
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(out + i * 8);
+    o4[0] = make_uint4(st.h[0], st.h[1], st.h[2], st.h[3]);
+    o4[1] = make_uint4(st.h[4], st.h[5], st.h[6], st.h[7]);
+}
+
+// grind: thread t tests nonce = base + t; result = atomicMin over matching nonces.
+__global__ void grind_kernel(const u32* __restrict__ digest, u32 pow_bits, u64 base, unsigned long long* best) {
+    u64 nonce = base + blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    Blake2sState st;
+    blake2s_init(st);
+    u32 m[16];
+#pragma unroll
+    for (int k = 0; k < 8; k++) m[k] = digest[k];
+    m[8] = (u32)nonce;
+    m[9] = (u32)(nonce >> 32);
+#pragma unroll
+    for (int k = 10; k < 16; k++) m[k] = 0;
+    blake2s_compress(st, m, 40, true);
+    // trailing zeros of the digest read as a little-endian u128 (channel/blake2s.rs:57-59)
+    u32 tz = 0;
+    if (st.h[0]) tz = __ffs(st.h[0]) - 1;
+    else if (st.h[1]) tz = 32 + __ffs(st.h[1]) - 1;
+    else if (st.h[2]) tz = 64 + __ffs(st.h[2]) - 1;
+    else if (st.h[3]) tz = 96 + __ffs(st.h[3]) - 1;
+    else tz = 128;
+    if (tz >= pow_bits) atomicMin(best, (unsigned long long)nonce);
+}
+
+}  // namespace cm31
+
+using namespace cm31;
+
+extern "C" {
+
+int cm31_blake2s_commit_layer(uint32_t log_size, const uint32_t* prev_layer, const uint32_t* const* cols,
+                              size_t n_cols, uint32_t* out_layer) {
+    CM_REQUIRE(out_layer != nullptr, "commit_layer: null output");
+    CM_REQUIRE(log_size <= 30, "commit_layer: layer too large");
+    DeviceTable dcols;
+    if (int e = dcols.upload(cols, n_cols * sizeof(void*))) return e;
+    size_t n = (size_t)1 << log_size;
+    unsigned threads = n < 256 ? (unsigned)((n + 31) / 32 * 32) : 256;
+    merkle_layer_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream()>>>(
+        log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, out_layer);
+    CM_LAUNCH_CHECK();
+    return 0;
+}
+
+int cm31_grind_blake2s(const uint8_t digest[32], uint32_t pow_bits, uint64_t* nonce_out) {
+    CM_REQUIRE(nonce_out != nullptr, "grind: null output");
+    CM_REQUIRE(pow_bits <= 64, "grind: pow_bits too large");
+    DeviceTable dd;
+    if (int e = dd.upload(digest, 32)) return e;
+    unsigned long long* dbest = nullptr;
+    CM_CUDA(cudaMallocAsync(&dbest, 8, stream()));
+    const unsigned long long none = ~0ull;
+    // batches of nonces in ascending order; the first batch with a hit contains the minimum.
+    u64 batch = 1ull << (pow_bits + 2 < 16 ? 16 : (pow_bits + 2 > 26 ? 26 : pow_bits + 2));
+    for (u64 base = 0;; base += batch) {
+        CM_CUDA(cudaMemcpyAsync(dbest, &none, 8, cudaMemcpyHostToDevice, stream()));
+        grind_kernel<<<(unsigned)(batch / 256), 256, 0, stream()>>>((const u32*)dd.d, pow_bits, base, dbest);
+        CM_LAUNCH_CHECK();
+        unsigned long long got = none;
+        CM_CUDA(cudaMemcpyAsync(&got, dbest, 8, cudaMemcpyDeviceToHost, stream()));
+        CM_CUDA(cudaStreamSynchronize(stream()));
+        if (got != none) {
+            *nonce_out = got;
+            break;
+        }
+    }
+    CM_CUDA(cudaFreeAsync(dbest, stream()));
+    return 0;
+}
+
+}  // extern "C"

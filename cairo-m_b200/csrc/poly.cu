@@ -1,0 +1,607 @@
+// PolyOps on sm_100a: twiddle tree, batched circle (I)FFT, LDE, bit reversal, eval_at_point.
+//
+// Replaces the SimdBackend kernels
+//   external/stwo/crates/prover/src/core/backend/simd/fft/ifft.rs:33-57, rfft.rs:35-60,
+//   simd/circle.rs:132-297,303-341, simd/bit_reverse.rs:48-147
+// and is defined by (bit-exact against) the CpuBackend
+//   external/stwo/crates/prover/src/core/backend/cpu/circle.rs:18-229, poly/utils.rs:44-99.
+//
+// Layout: one column = 2^L packed u32 M31 words, contiguous (column-major trace).  The FFT is
+// radix-2 over layers 0 (circle layer) .. L-1; a "pass" loads a tile into shared memory,
+// performs up to 12 layers (radix-8 register rounds) and stores it back, so a 2^22 column is
+// transformed with two HBM round trips.  Twiddles use the reference CPU tree layout.
+#include "circle.hpp"
+#include "common.cuh"
+
+namespace cm31 {
+
+// --------------------------------------------------------------------------- twiddles
+// tree[level j][i] = x( C_j.at(bit_reverse(i, k-1-j)) ),  C_j = root.repeated_double(j),
+// root = half_odds(k), level j at offset 2^k - 2^(k-j)   (cpu/circle.rs:171-188)
+__device__ __forceinline__ CirclePointM31 dev_point_from_index(u32 index) {
+    CirclePointM31 res = {1, 0};
+    CirclePointM31 cur = {M31_CIRCLE_GEN_X, M31_CIRCLE_GEN_Y};
+    index &= 0x7fffffffu;
+    while (index) {
+        if (index & 1) res = cp_add(res, cur);
+        cur = cp_double(cur);
+        index >>= 1;
+    }
+    return res;
+}
+
+__global__ void twiddle_kernel(u32* tw, u32* itw, u32 k, u32 root_initial, u32 root_step) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t total = (size_t)1 << k;
+    if (t >= total) return;
+    if (t == total - 1) {  // pad element (cpu/circle.rs:185-187)
+        tw[t] = 1;
+        itw[t] = 1;
+        return;
+    }
+    // find level j: offset_j = 2^k - 2^(k-j) <= t
+    u32 rem = (u32)(total - t);           // in (1, 2^k]
+    u32 j = k - (32 - __clz(rem - 1));    // 2^(k-j-1) < rem <= 2^(k-j)
+    u32 level_off = (u32)(total - ((size_t)1 << (k - j)));
+    u32 i = (u32)t - level_off;           // < 2^(k-1-j)
+    u32 nat = bit_reverse(i, k - 1 - j);
+    u32 initial = (u32)(((u64)root_initial << j) & 0x7fffffffu);
+    u32 step = (u32)(((u64)root_step << j) & 0x7fffffffu);
+    u32 idx = (u32)((initial + (u64)step * nat) & 0x7fffffffu);
+    u32 x = dev_point_from_index(idx).x;
+    tw[t] = x;
+    itw[t] = m31_inv(x);
+}
+
+// --------------------------------------------------------------------------- FFT passes
+__device__ __forceinline__ u32 pad_idx(u32 s) { return s + ((s >> 6) << 3); }
+
+// Twiddle for FFT layer `layer` (0 = circle layer) and butterfly group h, domain log size L,
+// tree log size M (tree holds 2^(M-1) words).
+__device__ __forceinline__ u32 load_twiddle(const u32* __restrict__ tree, u32 M, u32 L, u32 layer, u32 h) {
+    u32 end = 1u << (M - 1);
+    if (layer == 0) {
+        const u32* line0 = tree + (end - (1u << (L - 1)));
+        u32 x = __ldg(line0 + 2 * (h >> 2));
+        u32 y = __ldg(line0 + 2 * (h >> 2) + 1);
+        u32 sel = h & 3;  // [y, -y, -x, x]   (cpu/circle.rs:209-229)
+        u32 v = (sel < 2) ? y : x;
+        return (sel == 1 || sel == 2) ? m31_neg(v) : v;
+    }
+    return __ldg(tree + (end - (1u << (L - layer))) + h);
+}
+
+template <bool INV>
+__device__ __forceinline__ void bfly(u32& v0, u32& v1, u32 t) {
+    if (INV) {  // ibutterfly (core/fft.rs:14-21)
+        u32 tmp = v0;
+        v0 = m31_add(tmp, v1);
+        v1 = m31_mul(m31_sub(tmp, v1), t);
+    } else {  // butterfly (core/fft.rs:5-12)
+        u32 tmp = m31_mul(v1, t);
+        v1 = m31_sub(v0, tmp);
+        v0 = m31_add(v0, tmp);
+    }
+}
+
+// One pass over layers [lo, lo+nl).  Tile = 2^nl strided rows x 2^b contiguous words.
+// grid.x = tile * n_cols + column.
+template <bool INV>
+__global__ void __launch_bounds__(1024) fft_pass_kernel(const u32* const* __restrict__ src_cols,
+                                                        u32* const* __restrict__ dst_cols, u32 L, u32 log_in,
+                                                        u32 lo, u32 nl, u32 b, const u32* __restrict__ tree,
+                                                        u32 M, u32 scale, u32 n_cols) {
+    extern __shared__ u32 smem[];
+    const u32 tile_log = nl + b;
+    const u32 tile = 1u << tile_log;
+    // 1-D grid, column fastest: CTAs that run together work on the same tile of different
+    // columns and share its twiddles through L2.
+    const u32 col = blockIdx.x % n_cols;
+    const u32 tile_id = blockIdx.x / n_cols;
+    const u32* __restrict__ src = src_cols[col];
+    u32* __restrict__ dst = dst_cols[col];
+    const u32 lo_hi = tile_id & ((1u << (lo - b)) - 1);
+    const u32 hi = tile_id >> (lo - b);
+    const u32 n_in = 1u << log_in;
+    const u32 bmask = (1u << b) - 1;
+    const size_t gbase = ((size_t)hi << (lo + nl)) | ((size_t)lo_hi << b);
+
+    // ---- load
+    if (b == 0 && log_in >= 2) {
+        // contiguous tile: 128-bit loads
+        const uint4* s4 = reinterpret_cast<const uint4*>(src + gbase);
+        for (u32 s = threadIdx.x * 4; s < tile; s += blockDim.x * 4) {
+            uint4 v;
+            if (gbase + s < n_in) v = __ldg(s4 + (s >> 2));
+            else v = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(&smem[pad_idx(s)]) = v;
+        }
+    } else {
+        for (u32 s = threadIdx.x; s < tile; s += blockDim.x) {
+            size_t g = gbase | ((size_t)(s >> b) << lo) | (s & bmask);
+            smem[pad_idx(s)] = g < n_in ? __ldg(src + g) : 0u;
+        }
+    }
+    __syncthreads();
+
+    // ---- radix-8 rounds over groups of <=3 layers
+    const u32 n_rounds = (nl + 2) / 3;
+    for (u32 rr = 0; rr < n_rounds; rr++) {
+        const u32 r = INV ? rr : (n_rounds - 1 - rr);
+        const u32 p = b + 3 * r;
+        const u32 k = min(3u, nl - 3 * r);
+        const u32 groups = tile >> k;
+        const u32 hshift = nl - 3 * r - k;
+        for (u32 q = threadIdx.x; q < groups; q += blockDim.x) {
+            const u32 low = q & ((1u << p) - 1);
+            const u32 high = q >> p;
+            const u32 base = (high << (p + k)) | low;
+            const u32 H = (hi << hshift) | high;
+            const u32 layer0 = lo + 3 * r;
+            if (k == 3) {
+                u32 v[8];
+                if (p == 0) {
+                    uint4 a = *reinterpret_cast<uint4*>(&smem[pad_idx(base)]);
+                    uint4 c = *reinterpret_cast<uint4*>(&smem[pad_idx(base) + 4]);
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                    v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+                } else {
+#pragma unroll
+                    for (u32 j = 0; j < 8; j++) v[j] = smem[pad_idx(base + (j << p))];
+                }
+                if (INV) {
+#pragma unroll
+                    for (u32 jj = 0; jj < 4; jj++) {
+                        u32 t = load_twiddle(tree, M, L, layer0, 4 * H + jj);
+                        bfly<true>(v[2 * jj], v[2 * jj + 1], t);
+                    }
+#pragma unroll
+                    for (u32 jj = 0; jj < 2; jj++) {
+                        u32 t = load_twiddle(tree, M, L, layer0 + 1, 2 * H + jj);
+                        bfly<true>(v[4 * jj], v[4 * jj + 2], t);
+                        bfly<true>(v[4 * jj + 1], v[4 * jj + 3], t);
+                    }
+                    {
+                        u32 t = load_twiddle(tree, M, L, layer0 + 2, H);
+#pragma unroll
+                        for (u32 jj = 0; jj < 4; jj++) bfly<true>(v[jj], v[jj + 4], t);
+                    }
+                } else {
+                    {
+                        u32 t = load_twiddle(tree, M, L, layer0 + 2, H);
+#pragma unroll
+                        for (u32 jj = 0; jj < 4; jj++) bfly<false>(v[jj], v[jj + 4], t);
+                    }
+#pragma unroll
+                    for (u32 jj = 0; jj < 2; jj++) {
+                        u32 t = load_twiddle(tree, M, L, layer0 + 1, 2 * H + jj);
+                        bfly<false>(v[4 * jj], v[4 * jj + 2], t);
+                        bfly<false>(v[4 * jj + 1], v[4 * jj + 3], t);
+                    }
+#pragma unroll
+                    for (u32 jj = 0; jj < 4; jj++) {
+                        u32 t = load_twiddle(tree, M, L, layer0, 4 * H + jj);
+                        bfly<false>(v[2 * jj], v[2 * jj + 1], t);
+                    }
+                }
+                if (p == 0) {
+                    *reinterpret_cast<uint4*>(&smem[pad_idx(base)]) = make_uint4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<uint4*>(&smem[pad_idx(base) + 4]) = make_uint4(v[4], v[5], v[6], v[7]);
+                } else {
+#pragma unroll
+                    for (u32 j = 0; j < 8; j++) smem[pad_idx(base + (j << p))] = v[j];
+                }
+            } else if (k == 2) {
+                u32 v[4];
+#pragma unroll
+                for (u32 j = 0; j < 4; j++) v[j] = smem[pad_idx(base + (j << p))];
+                if (INV) {
+#pragma unroll
+                    for (u32 jj = 0; jj < 2; jj++) {
+                        u32 t = load_twiddle(tree, M, L, layer0, 2 * H + jj);
+                        bfly<true>(v[2 * jj], v[2 * jj + 1], t);
+                    }
+                    u32 t = load_twiddle(tree, M, L, layer0 + 1, H);
+                    bfly<true>(v[0], v[2], t);
+                    bfly<true>(v[1], v[3], t);
+                } else {
+                    u32 t = load_twiddle(tree, M, L, layer0 + 1, H);
+                    bfly<false>(v[0], v[2], t);
+                    bfly<false>(v[1], v[3], t);
+#pragma unroll
+                    for (u32 jj = 0; jj < 2; jj++) {
+                        u32 t2 = load_twiddle(tree, M, L, layer0, 2 * H + jj);
+                        bfly<false>(v[2 * jj], v[2 * jj + 1], t2);
+                    }
+                }
+#pragma unroll
+                for (u32 j = 0; j < 4; j++) smem[pad_idx(base + (j << p))] = v[j];
+            } else {
+                u32 v0 = smem[pad_idx(base)], v1 = smem[pad_idx(base + (1u << p))];
+                u32 t = load_twiddle(tree, M, L, layer0, H);
+                bfly<INV>(v0, v1, t);
+                smem[pad_idx(base)] = v0;
+                smem[pad_idx(base + (1u << p))] = v1;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- store
+    if (b == 0) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + gbase);
+        for (u32 s = threadIdx.x * 4; s < tile; s += blockDim.x * 4) {
+            uint4 v = *reinterpret_cast<uint4*>(&smem[pad_idx(s)]);
+            if (scale != 1) {
+                v.x = m31_mul(v.x, scale); v.y = m31_mul(v.y, scale);
+                v.z = m31_mul(v.z, scale); v.w = m31_mul(v.w, scale);
+            }
+            d4[s >> 2] = v;
+        }
+    } else {
+        for (u32 s = threadIdx.x; s < tile; s += blockDim.x) {
+            size_t g = gbase | ((size_t)(s >> b) << lo) | (s & bmask);
+            u32 v = smem[pad_idx(s)];
+            if (scale != 1) v = m31_mul(v, scale);
+            dst[g] = v;
+        }
+    }
+}
+
+// Domains of log size 1 and 2 (cpu/circle.rs:26-50, 107-124): one thread per column.
+template <bool INV>
+__global__ void fft_small_kernel(const u32* const* src_cols, u32* const* dst_cols, u32 n_cols, u32 L, u32 log_in,
+                                 u32 px, u32 py) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    const u32* src = src_cols[c];
+    u32* dst = dst_cols[c];
+    u32 n = 1u << L, n_in = 1u << log_in;
+    u32 v[4];
+    for (u32 i = 0; i < n; i++) v[i] = i < n_in ? src[i] : 0u;
+    if (L == 1) {
+        if (INV) {
+            u32 y_inv = m31_inv(py);
+            bfly<true>(v[0], v[1], y_inv);
+            u32 n_inv = m31_inv(2);
+            v[0] = m31_mul(v[0], n_inv);
+            v[1] = m31_mul(v[1], n_inv);
+        } else {
+            bfly<false>(v[0], v[1], py);
+        }
+    } else {
+        if (INV) {
+            u32 x_inv = m31_inv(px), y_inv = m31_inv(py);
+            bfly<true>(v[0], v[1], y_inv);
+            bfly<true>(v[2], v[3], m31_neg(y_inv));
+            bfly<true>(v[0], v[2], x_inv);
+            bfly<true>(v[1], v[3], x_inv);
+            u32 n_inv = m31_inv(4);
+            for (u32 i = 0; i < 4; i++) v[i] = m31_mul(v[i], n_inv);
+        } else {
+            bfly<false>(v[0], v[2], px);
+            bfly<false>(v[1], v[3], px);
+            bfly<false>(v[0], v[1], py);
+            bfly<false>(v[2], v[3], m31_neg(py));
+        }
+    }
+    for (u32 i = 0; i < n; i++) dst[i] = v[i];
+}
+
+__global__ void bit_reverse_kernel(u32* col, u32 log_size) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= ((size_t)1 << log_size)) return;
+    u32 j = bit_reverse((u32)i, log_size);
+    if (i < j) {
+        u32 a = col[i], c = col[j];
+        col[i] = c;
+        col[j] = a;
+    }
+}
+
+// --------------------------------------------------------------------------- eval_at_point
+// f(P) = fold(coeffs, [pi^{L-2}(x), ..., pi(x), x, y])  (cpu/circle.rs:73-87, poly/utils.rs:44-55):
+// coefficient j weighs prod over set bits i of j of factor_i, factor_0 = y, factor_1 = x,
+// factor_i = pi^{i-1}(x).  Stage 1: each CTA folds a chunk of 2^CH coefficients to one QM31;
+// stage 2: one CTA per polynomial folds the partials with the remaining factors.
+constexpr u32 EAP_CHUNK_LOG = 11;  // 256 threads x 8 coefficients
+constexpr u32 EAP_MAX_LEVELS = 32;
+
+struct EapJob {
+    const u32* coeffs;
+    u32 log_size;
+    u32 point;        // index into the factor table
+    u32 partial_off;  // offset (in QM31s) of this poly's partials
+    u32 first_chunk;  // index of this poly's first chunk in the flattened chunk list
+};
+
+__device__ __forceinline__ QM31 ld_qm(const u32* p) { return qm_make(p[0], p[1], p[2], p[3]); }
+
+__global__ void __launch_bounds__(256) eap_stage1_kernel(const EapJob* __restrict__ jobs, const u32* __restrict__ chunk_job,
+                                                          const u32* __restrict__ factors, u32* __restrict__ partials) {
+    __shared__ QM31 sh[256];
+    const u32 chunk = blockIdx.x;
+    const EapJob job = jobs[chunk_job[chunk]];
+    const u32 local_chunk = chunk - job.first_chunk;
+    const u32 ch_log = min(job.log_size, EAP_CHUNK_LOG);
+    const u32 n = 1u << ch_log;
+    const u32* c = job.coeffs + ((size_t)local_chunk << ch_log);
+    const u32* f = factors + (size_t)job.point * EAP_MAX_LEVELS * 4;
+    // each thread folds 8 consecutive coefficients (levels 0..2)
+    const u32 per = 8;
+    u32 t = threadIdx.x;
+    QM31 acc = qm_zero();
+    bool active = t * per < n;
+    if (active) {
+        u32 m = min(per, n);  // n may be < 8 for tiny polys
+        u32 v[8];
+        for (u32 i = 0; i < 8; i++) v[i] = i < m ? __ldg(c + t * per + i) : 0u;
+        QM31 f0 = ld_qm(f), f1 = ld_qm(f + 4), f2 = ld_qm(f + 8);
+        // level 0: c0 + c1*y
+        QM31 a0 = qm_add_m31(qm_mul_m31(f0, v[1]), v[0]);
+        QM31 a1 = qm_add_m31(qm_mul_m31(f0, v[3]), v[2]);
+        QM31 a2 = qm_add_m31(qm_mul_m31(f0, v[5]), v[4]);
+        QM31 a3 = qm_add_m31(qm_mul_m31(f0, v[7]), v[6]);
+        if (m == 1) a0 = qm_from_m31(v[0]);
+        QM31 b0 = a0, b1 = a2;
+        if (m > 2) {
+            b0 = qm_add(a0, qm_mul(a1, f1));
+            b1 = qm_add(a2, qm_mul(a3, f1));
+        }
+        acc = b0;
+        if (m > 4) acc = qm_add(b0, qm_mul(b1, f2));
+    }
+    sh[t] = acc;
+    __syncthreads();
+    // tree over threads: level 3.. ch_log-1
+    u32 nthr = n > per ? n / per : 1;
+    u32 level = 3;
+    for (u32 stride = 1; stride < nthr; stride <<= 1, level++) {
+        if ((t & (2 * stride - 1)) == 0 && t + stride < nthr) {
+            QM31 fl = ld_qm(f + level * 4);
+            sh[t] = qm_add(sh[t], qm_mul(sh[t + stride], fl));
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        u32* o = partials + ((size_t)job.partial_off + local_chunk) * 4;
+        QM31 r = sh[0];
+        o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d;
+    }
+}
+
+__global__ void __launch_bounds__(256) eap_stage2_kernel(const EapJob* __restrict__ jobs, const u32* __restrict__ factors,
+                                                          const u32* __restrict__ partials, u32* __restrict__ out) {
+    __shared__ QM31 sh[256];
+    const EapJob job = jobs[blockIdx.x];
+    const u32 ch_log = min(job.log_size, EAP_CHUNK_LOG);
+    const u32 n_part = 1u << (job.log_size - ch_log);
+    const u32* f = factors + (size_t)job.point * EAP_MAX_LEVELS * 4;
+    const u32* p = partials + (size_t)job.partial_off * 4;
+    u32 t = threadIdx.x;
+    // n_part can exceed 256: each thread first folds a contiguous run of 2^e partials serially.
+    u32 e = 0;
+    while ((n_part >> e) > 256) e++;
+    u32 run = 1u << e;
+    QM31 acc = qm_zero();
+    u32 nthr = n_part >> e;
+    if (t < nthr) {
+        // serial fold of `run` consecutive partials with levels ch_log .. ch_log+e-1 (Horner-free,
+        // done as an in-register binary tree by recursion depth via explicit stack of size e+1)
+        QM31 stack[24];
+        u32 sp = 0;
+        for (u32 i = 0; i < run; i++) {
+            QM31 v = ld_qm(p + ((size_t)t * run + i) * 4);
+            u32 lvl = 0, idx = i;
+            while (idx & 1) {  // merge with the left sibling waiting on the stack
+                QM31 fl = ld_qm(f + (ch_log + lvl) * 4);
+                v = qm_add(stack[--sp], qm_mul(v, fl));
+                idx >>= 1;
+                lvl++;
+            }
+            stack[sp++] = v;
+        }
+        acc = stack[0];
+    }
+    sh[t] = acc;
+    __syncthreads();
+    u32 level = ch_log + e;
+    for (u32 stride = 1; stride < nthr; stride <<= 1, level++) {
+        if ((t & (2 * stride - 1)) == 0 && t + stride < nthr) {
+            QM31 fl = ld_qm(f + level * 4);
+            sh[t] = qm_add(sh[t], qm_mul(sh[t + stride], fl));
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        QM31 r = sh[0];
+        u32* o = out + (size_t)blockIdx.x * 4;
+        o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d;
+    }
+}
+
+// --------------------------------------------------------------------------- host planning
+struct Pass {
+    u32 lo, nl, b;
+};
+static void plan_passes(u32 L, std::vector<Pass>& out) {
+    // first pass: contiguous tile of up to 2^12 words; the rest: strided passes of <= 12 layers
+    // with 64-byte (b=4) or 32-byte (b=3, 12 layers) contiguous runs.
+    const u32 FIRST_MAX = 12, REST_MAX = 12;
+    out.clear();
+    if (L <= FIRST_MAX) {
+        out.push_back({0, L, 0});
+        return;
+    }
+    u32 n_rest = (L - FIRST_MAX + REST_MAX - 1) / REST_MAX;
+    u32 rest_total = L - FIRST_MAX;
+    if (n_rest == 1 && rest_total < 6) rest_total = 6 < L / 2 ? 6 : L / 2;
+    u32 first = L - rest_total;
+    out.push_back({0, first, 0});
+    u32 lo = first;
+    u32 base = rest_total / n_rest, extra = rest_total % n_rest;
+    for (u32 i = 0; i < n_rest; i++) {
+        u32 nl = base + (i < extra ? 1 : 0);
+        out.push_back({lo, nl, nl >= 12 ? 3u : 4u});
+        lo += nl;
+    }
+}
+
+template <bool INV>
+static int run_fft(const u32* const* src_host, u32* const* dst_host, size_t n_cols, u32 L, u32 log_in,
+                   const cm31_twiddles* tw) {
+    if (n_cols == 0) return 0;
+    CM_REQUIRE(tw != nullptr, "fft: null twiddles");
+    CM_REQUIRE(L >= 1 && L <= tw->log_size, "fft: domain larger than the twiddle tree");
+    CM_REQUIRE(log_in <= L, "fft: more coefficients than domain points");
+    DeviceTable dsrc, ddst;
+    if (int e = dsrc.upload(src_host, n_cols * sizeof(void*))) return e;
+    if (int e = ddst.upload(dst_host, n_cols * sizeof(void*))) return e;
+    const u32* const* src = (const u32* const*)dsrc.d;
+    u32* const* dst = (u32* const*)ddst.d;
+    if (L <= 2) {
+        CirclePointM31 p = CanonicCoset(L).half_coset().initial();
+        fft_small_kernel<INV><<<(unsigned)((n_cols + 127) / 128), 128, 0, stream()>>>(src, dst, (u32)n_cols, L, log_in,
+                                                                                     p.x, p.y);
+        CM_LAUNCH_CHECK();
+        return 0;
+    }
+    std::vector<Pass> passes;
+    plan_passes(L, passes);
+    const u32* tree = INV ? tw->itw : tw->tw;
+    u32 scale_last = 1;
+    if (INV) scale_last = m31_inv((u32)(((u64)1 << L) % P));
+    size_t np = passes.size();
+    for (size_t i = 0; i < np; i++) {
+        const Pass& ps = INV ? passes[i] : passes[np - 1 - i];
+        bool first = (i == 0), last = (i == np - 1);
+        u32 tile_log = ps.nl + ps.b;
+        u32 tile = 1u << tile_log;
+        u32 threads = tile / 8;
+        if (threads < 32) threads = 32;
+        if (threads > 1024) threads = 1024;
+        size_t smem = (size_t)(tile + ((tile >> 6) << 3) + 8) * 4;
+        auto kern = fft_pass_kernel<INV>;
+        if (smem > 48 * 1024) CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        size_t n_blocks = n_cols * (((size_t)1 << L) >> tile_log);
+        CM_REQUIRE(n_blocks < (1ull << 31), "fft: batch too large for one launch");
+        kern<<<(unsigned)n_blocks, threads, smem, stream()>>>(first ? src : (const u32* const*)dst, dst, L,
+                                                              first ? log_in : L, ps.lo, ps.nl, ps.b, tree,
+                                                              tw->log_size, (INV && last) ? scale_last : 1u,
+                                                              (u32)n_cols);
+        CM_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace cm31
+
+using namespace cm31;
+
+extern "C" {
+
+int cm31_twiddles_create(uint32_t log_size, cm31_twiddles** out) {
+    CM_REQUIRE(out != nullptr, "twiddles_create: null out");
+    CM_REQUIRE(log_size >= 3 && log_size <= 30, "twiddles_create: log_size must be in [3,30]");
+    cm31_twiddles* tw = new cm31_twiddles();
+    tw->log_size = log_size;
+    u32 k = log_size - 1;
+    size_t n = (size_t)1 << k;
+    if (int e = cm31_malloc((void**)&tw->tw, n * 4)) return e;
+    if (int e = cm31_malloc((void**)&tw->itw, n * 4)) return e;
+    Coset root = CanonicCoset(log_size).half_coset();
+    twiddle_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(tw->tw, tw->itw, k, root.initial_index,
+                                                                     root.step_size);
+    CM_LAUNCH_CHECK();
+    *out = tw;
+    return 0;
+}
+
+int cm31_twiddles_destroy(cm31_twiddles* tw) {
+    if (!tw) return 0;
+    cm31_free(tw->tw);
+    cm31_free(tw->itw);
+    delete tw;
+    return 0;
+}
+
+int cm31_twiddles_buffers(const cm31_twiddles* tw, const uint32_t** twiddles, const uint32_t** itwiddles,
+                          uint32_t* log_size) {
+    CM_REQUIRE(tw != nullptr, "twiddles_buffers: null handle");
+    if (twiddles) *twiddles = tw->tw;
+    if (itwiddles) *itwiddles = tw->itw;
+    if (log_size) *log_size = tw->log_size;
+    return 0;
+}
+
+int cm31_interpolate_batch(uint32_t* const* cols, size_t n_cols, uint32_t log_size, const cm31_twiddles* tw) {
+    return run_fft<true>((const u32* const*)cols, cols, n_cols, log_size, log_size, tw);
+}
+
+int cm31_evaluate_batch(const uint32_t* const* coeffs, uint32_t* const* out, size_t n_cols, uint32_t log_size,
+                        uint32_t log_eval_size, const cm31_twiddles* tw) {
+    CM_REQUIRE(log_eval_size >= log_size, "evaluate: domain smaller than the polynomial");
+    return run_fft<false>(coeffs, out, n_cols, log_eval_size, log_size, tw);
+}
+
+int cm31_bit_reverse(uint32_t* col, uint32_t log_size) {
+    size_t n = (size_t)1 << log_size;
+    bit_reverse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(col, log_size);
+    CM_LAUNCH_CHECK();
+    return 0;
+}
+
+int cm31_eval_at_point_batch(const uint32_t* const* coeffs, const uint32_t* log_sizes_host, size_t n_polys,
+                             const uint32_t* points_host, size_t n_points, const uint32_t* point_idx_host,
+                             uint32_t* out_host) {
+    if (n_polys == 0) return 0;
+    // factor table: per point, factor_0 = y, factor_1 = x, factor_i = pi^{i-1}(x)
+    std::vector<u32> factors(n_points * EAP_MAX_LEVELS * 4, 0);
+    for (size_t k = 0; k < n_points; k++) {
+        const u32* pt = points_host + k * 8;
+        QM31 x = qm_make(pt[0], pt[1], pt[2], pt[3]);
+        QM31 y = qm_make(pt[4], pt[5], pt[6], pt[7]);
+        u32* f = &factors[k * EAP_MAX_LEVELS * 4];
+        f[0] = y.a; f[1] = y.b; f[2] = y.c; f[3] = y.d;
+        for (u32 i = 1; i < EAP_MAX_LEVELS; i++) {
+            f[i * 4 + 0] = x.a; f[i * 4 + 1] = x.b; f[i * 4 + 2] = x.c; f[i * 4 + 3] = x.d;
+            x = qm_double_x(x);
+        }
+    }
+    std::vector<EapJob> jobs(n_polys);
+    std::vector<u32> chunk_job;
+    u32 part_off = 0;
+    for (size_t i = 0; i < n_polys; i++) {
+        u32 L = log_sizes_host[i];
+        CM_REQUIRE(L < EAP_MAX_LEVELS, "eval_at_point: polynomial too large");
+        CM_REQUIRE(point_idx_host[i] < n_points, "eval_at_point: point index out of range");
+        u32 ch_log = L < EAP_CHUNK_LOG ? L : EAP_CHUNK_LOG;
+        u32 n_chunks = 1u << (L - ch_log);
+        jobs[i].coeffs = coeffs[i];
+        jobs[i].log_size = L;
+        jobs[i].point = point_idx_host[i];
+        jobs[i].partial_off = part_off;
+        jobs[i].first_chunk = (u32)chunk_job.size();
+        for (u32 c = 0; c < n_chunks; c++) chunk_job.push_back((u32)i);
+        part_off += n_chunks;
+    }
+    DeviceTable djobs, dchunk, dfac;
+    if (int e = djobs.upload(jobs.data(), jobs.size() * sizeof(EapJob))) return e;
+    if (int e = dchunk.upload(chunk_job.data(), chunk_job.size() * 4)) return e;
+    if (int e = dfac.upload(factors.data(), factors.size() * 4)) return e;
+    u32 *dpart = nullptr, *dout = nullptr;
+    CM_CUDA(cudaMallocAsync(&dpart, (size_t)part_off * 16, stream()));
+    CM_CUDA(cudaMallocAsync(&dout, n_polys * 16, stream()));
+    eap_stage1_kernel<<<(unsigned)chunk_job.size(), 256, 0, stream()>>>((const EapJob*)djobs.d, (const u32*)dchunk.d,
+                                                                       (const u32*)dfac.d, dpart);
+    CM_LAUNCH_CHECK();
+    eap_stage2_kernel<<<(unsigned)n_polys, 256, 0, stream()>>>((const EapJob*)djobs.d, (const u32*)dfac.d, dpart, dout);
+    CM_LAUNCH_CHECK();
+    CM_CUDA(cudaMemcpyAsync(out_host, dout, n_polys * 16, cudaMemcpyDeviceToHost, stream()));
+    CM_CUDA(cudaFreeAsync(dpart, stream()));
+    CM_CUDA(cudaFreeAsync(dout, stream()));
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// libcm31 runtime: errors, stream, stream-ordered device memory, gathers.
+// Replaces Column<T> storage management of the reference backends
+// (external/stwo/crates/prover/src/core/backend/mod.rs:46-65).
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace cm31 {
+
+static thread_local std::string g_err;
+static cudaStream_t g_stream = 0;
+static bool g_pool_ready[64] = {false};
+
+void set_error(const std::string& msg) { g_err = msg; }
+cudaStream_t stream() { return g_stream; }
+
+static int ensure_pool() {
+    int dev = 0;
+    CM_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !g_pool_ready[dev]) {
+        cudaMemPool_t pool;
+        CM_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t thresh = UINT64_MAX;  // keep freed blocks cached: proving reuses the same sizes
+        CM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+        g_pool_ready[dev] = true;
+    }
+    return 0;
+}
+
+int DeviceTable::upload(const void* host, size_t bytes) {
+    release();
+    if (bytes == 0) bytes = 4;
+    if (int e = ensure_pool()) return e;
+    CM_CUDA(cudaMallocAsync(&d, bytes, stream()));
+    // pageable source: the runtime stages the bytes before returning, so `host` may be reused.
+    CM_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, stream()));
+    return 0;
+}
+void DeviceTable::release() {
+    if (d) {
+        cudaFreeAsync(d, stream());
+        d = nullptr;
+    }
+}
+
+__global__ void gather_u32_kernel(const u32* const* cols, size_t n_cols, const u32* idx, size_t n_idx, u32* out) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= n_cols * n_idx) return;
+    size_t c = t / n_idx, q = t % n_idx;
+    out[t] = cols[c][idx[q]];
+}
+__global__ void gather_hash_kernel(const u32* layer, const u32* idx, size_t n_idx, u32* out) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= n_idx * 8) return;
+    out[t] = layer[(size_t)idx[t >> 3] * 8 + (t & 7)];
+}
+
+}  // namespace cm31
+
+using namespace cm31;
+
+extern "C" {
+
+const char* cm31_last_error(void) { return g_err.c_str(); }
+
+int cm31_device_count(int* out) {
+    CM_CUDA(cudaGetDeviceCount(out));
+    return 0;
+}
+int cm31_set_device(int ordinal) {
+    CM_CUDA(cudaSetDevice(ordinal));
+    return 0;
+}
+int cm31_set_stream(void* s) {
+    g_stream = (cudaStream_t)s;
+    return 0;
+}
+int cm31_sync(void) {
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    return 0;
+}
+int cm31_malloc(void** out, size_t bytes) {
+    CM_REQUIRE(out != nullptr, "malloc: null out");
+    if (int e = ensure_pool()) return e;
+    if (bytes == 0) bytes = 4;
+    CM_CUDA(cudaMallocAsync(out, bytes, stream()));
+    return 0;
+}
+int cm31_free(void* p) {
+    if (p) CM_CUDA(cudaFreeAsync(p, stream()));
+    return 0;
+}
+int cm31_memset0(void* p, size_t bytes) {
+    CM_CUDA(cudaMemsetAsync(p, 0, bytes, stream()));
+    return 0;
+}
+int cm31_h2d(void* dst, const void* src, size_t bytes) {
+    CM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream()));
+    return 0;
+}
+int cm31_d2h(void* dst, const void* src, size_t bytes) {
+    CM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream()));
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    return 0;
+}
+int cm31_d2d(void* dst, const void* src, size_t bytes) {
+    CM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream()));
+    return 0;
+}
+
+int cm31_gather_u32(const uint32_t* const* cols, size_t n_cols, const uint32_t* idx_host, size_t n_idx,
+                    uint32_t* out_host) {
+    if (n_cols == 0 || n_idx == 0) return 0;
+    DeviceTable dcols, didx;
+    if (int e = dcols.upload(cols, n_cols * sizeof(void*))) return e;
+    if (int e = didx.upload(idx_host, n_idx * 4)) return e;
+    u32* dout = nullptr;
+    size_t total = n_cols * n_idx;
+    CM_CUDA(cudaMallocAsync(&dout, total * 4, stream()));
+    gather_u32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream()>>>((const u32* const*)dcols.d, n_cols,
+                                                                            (const u32*)didx.d, n_idx, dout);
+    CM_LAUNCH_CHECK();
+    CM_CUDA(cudaMemcpyAsync(out_host, dout, total * 4, cudaMemcpyDeviceToHost, stream()));
+    CM_CUDA(cudaFreeAsync(dout, stream()));
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    return 0;
+}
+
+int cm31_gather_hash(const uint32_t* layer, const uint32_t* idx_host, size_t n_idx, uint32_t* out_host) {
+    if (n_idx == 0) return 0;
+    DeviceTable didx;
+    if (int e = didx.upload(idx_host, n_idx * 4)) return e;
+    u32* dout = nullptr;
+    CM_CUDA(cudaMallocAsync(&dout, n_idx * 32, stream()));
+    gather_hash_kernel<<<(unsigned)((n_idx * 8 + 255) / 256), 256, 0, stream()>>>(layer, (const u32*)didx.d, n_idx,
+                                                                                 dout);
+    CM_LAUNCH_CHECK();
+    CM_CUDA(cudaMemcpyAsync(out_host, dout, n_idx * 32, cudaMemcpyDeviceToHost, stream()));
+    CM_CUDA(cudaFreeAsync(dout, stream()));
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+/*
+ * cm31.h — C ABI of the B200-native cairo-m proving hot path (libcm31.so).
+ *
+ * This is the boundary a Rust `CudaBackend` shim binds with `extern "C"` to implement the Stwo
+ * backend traits in place of `SimdBackend` (INTEGRATION.md shows the shim).  Every entry point
+ * names the reference interface it replaces (paths relative to the reference checkout:
+ * S/ = external/stwo/crates, P/ = crates/prover).
+ *
+ * Conventions
+ *  - All field data are u32 words holding CANONICAL M31 values in [0, 2^31-1).
+ *  - A "column" is a contiguous device array of 2^log_size u32 (the reference `BaseColumn`,
+ *    S/prover/src/core/backend/simd/column.rs:26-30).  Secure (QM31) columns are 4 base columns
+ *    (S/prover/src/core/secure_column.rs:11-13).
+ *  - `const uint32_t* const* cols` arguments are HOST arrays of DEVICE pointers.
+ *  - QM31 scalars cross the boundary as uint32_t[4] = (a, b, c, d) of (a+bi)+(c+di)u.
+ *  - Hash columns are device arrays of 8 u32 (32 bytes) per node (reference `Blake2sHash`,
+ *    S/prover/src/core/vcs/blake2_hash.rs:8-10).
+ *  - Every function returns 0 on success; non-zero = error, text via cm31_last_error().  Contract
+ *    violations the reference `assert!`s on are reported as errors, never silently ignored.
+ *  - Calls are issued from one host thread and are ordered on one CUDA stream (cm31_set_stream);
+ *    functions that return host-readable values synchronise that stream before returning.
+ */
+#ifndef CM31_H
+#define CM31_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ runtime / buffers */
+const char* cm31_last_error(void);
+int cm31_device_count(int* out);
+int cm31_set_device(int ordinal);
+int cm31_set_stream(void* cuda_stream); /* cudaStream_t; NULL = legacy default stream */
+int cm31_sync(void);
+/* Column<T>::zeros / uninitialized / to_cpu / from_iter  (S/prover/src/core/backend/mod.rs:46-65) */
+int cm31_malloc(void** out, size_t bytes);
+int cm31_free(void* dptr);
+int cm31_memset0(void* dptr, size_t bytes);
+int cm31_h2d(void* dst, const void* src_host, size_t bytes);
+int cm31_d2h(void* dst_host, const void* src, size_t bytes);
+int cm31_d2d(void* dst, const void* src, size_t bytes);
+/* Column::at for many (column,row) pairs at once (decommit):
+ * out_host[c * n_idx + q] = cols[c][idx_host[q]]   (S/prover/src/core/vcs/prover.rs:125-140) */
+int cm31_gather_u32(const uint32_t* const* cols, size_t n_cols, const uint32_t* idx_host, size_t n_idx,
+                    uint32_t* out_host);
+/* same for hash columns: out_host[q*8..] = layer[idx[q]] */
+int cm31_gather_hash(const uint32_t* layer, const uint32_t* idx_host, size_t n_idx, uint32_t* out_host);
+
+/* ------------------------------------------------------------------ PolyOps
+ * S/prover/src/core/poly/circle/ops.rs:13-69, CPU definition S/prover/src/core/backend/cpu/circle.rs */
+typedef struct cm31_twiddles cm31_twiddles;
+/* PolyOps::precompute_twiddles(CanonicCoset(log_size).half_coset())  (cpu/circle.rs:137-188):
+ * twiddle tree able to serve every canonic circle domain of log size <= log_size. */
+int cm31_twiddles_create(uint32_t log_size, cm31_twiddles** out);
+int cm31_twiddles_destroy(cm31_twiddles* tw);
+/* device pointers to the (x) and (1/x) tree buffers, 2^(log_size-1) words each, stwo CPU layout */
+int cm31_twiddles_buffers(const cm31_twiddles* tw, const uint32_t** twiddles, const uint32_t** itwiddles,
+                          uint32_t* log_size);
+/* PolyOps::interpolate / interpolate_columns (ops.rs:19-33, cpu/circle.rs:18-71): in place,
+ * evaluations on CanonicCoset(log_size).circle_domain() in bit-reversed order -> FFT-basis coeffs. */
+int cm31_interpolate_batch(uint32_t* const* cols, size_t n_cols, uint32_t log_size, const cm31_twiddles* tw);
+/* PolyOps::evaluate / evaluate_polynomials (ops.rs:43-65, cpu/circle.rs:97-135): coefficient
+ * vectors of 2^log_size words -> evaluations on CanonicCoset(log_eval_size).circle_domain(),
+ * bit-reversed order, out columns of 2^log_eval_size words (log_eval_size >= log_size). */
+int cm31_evaluate_batch(const uint32_t* const* coeffs, uint32_t* const* out, size_t n_cols, uint32_t log_size,
+                        uint32_t log_eval_size, const cm31_twiddles* tw);
+/* PolyOps::eval_at_point (ops.rs:36, cpu/circle.rs:73-87) for many (poly, point) pairs:
+ * points_host[k*8..] = (x.a,x.b,x.c,x.d,y.a,..,y.d); point_idx_host[i] selects the point of poly i;
+ * out_host[i*4..] = poly_i(point).  Synchronises. */
+int cm31_eval_at_point_batch(const uint32_t* const* coeffs, const uint32_t* log_sizes_host, size_t n_polys,
+                             const uint32_t* points_host, size_t n_points, const uint32_t* point_idx_host,
+                             uint32_t* out_host);
+/* ColumnOps::bit_reverse_column (S/prover/src/core/backend/cpu/mod.rs:36-46), in place */
+int cm31_bit_reverse(uint32_t* col, uint32_t log_size);
+
+/* ------------------------------------------------------------------ MerkleOps<Blake2sMerkleHasher>
+ * S/prover/src/core/vcs/ops.rs:41-45, CPU def cpu/blake2s.rs:9-23, hasher vcs/blake2_merkle.rs:14-30:
+ * out[i] = Blake2s( prev[2i] || prev[2i+1] || le32(cols[0][i]) || ... ), i < 2^log_size.
+ * prev_layer may be NULL (leaf layer). */
+int cm31_blake2s_commit_layer(uint32_t log_size, const uint32_t* prev_layer, const uint32_t* const* cols,
+                              size_t n_cols, uint32_t* out_layer);
+
+/* ------------------------------------------------------------------ AccumulationOps
+ * S/prover/src/core/air/accumulation.rs:156-162 */
+int cm31_accumulate(uint32_t* const dst4[4], const uint32_t* const src4[4], size_t n);
+int cm31_secure_powers(const uint32_t felt[4], size_t n_powers, uint32_t* out_host /* 4*n */);
+
+/* ------------------------------------------------------------------ QuotientOps
+ * S/prover/src/core/pcs/quotients.rs:22-35, CPU def cpu/quotients.rs:18-146.
+ * One call per distinct column log size.  Sample batches in flattened form:
+ *   batch b: point = batch_points_host[b*8..], columns col_idx_host[batch_start_host[b] ..
+ *   batch_start_host[b+1]) with sampled values values_host[k*4..].
+ * out4 = 4 coordinate columns of 2^log_size words. */
+int cm31_accumulate_quotients(uint32_t log_size, const uint32_t* const* cols, size_t n_cols,
+                              const uint32_t random_coeff[4], size_t n_batches, const uint32_t* batch_points_host,
+                              const uint32_t* batch_start_host, const uint32_t* col_idx_host,
+                              const uint32_t* values_host, uint32_t* const out4[4]);
+
+/* ------------------------------------------------------------------ FriOps
+ * S/prover/src/core/fri.rs:92-139; definitions fri.rs:1132-1189, cpu/fri.rs:29-85 */
+/* LineEvaluation of 2^log_size values on LineDomain(half_odds(log_size)) -> 2^(log_size-1) */
+int cm31_fold_line(const uint32_t* const src4[4], uint32_t log_size, const uint32_t alpha[4],
+                   const cm31_twiddles* tw, uint32_t* const dst4[4]);
+/* SecureEvaluation of 2^log_size on CanonicCoset(log_size).circle_domain():
+ * dst[i] = dst[i]*alpha^2 + fold(src)[i], dst has 2^(log_size-1) values */
+int cm31_fold_circle_into_line(uint32_t* const dst4[4], const uint32_t* const src4[4], uint32_t log_size,
+                               const uint32_t alpha[4], const cm31_twiddles* tw);
+int cm31_decompose(const uint32_t* const src4[4], uint32_t log_size, uint32_t* const dst4[4],
+                   uint32_t lambda_out[4]);
+
+/* ------------------------------------------------------------------ GrindOps<Blake2sChannel>
+ * S/prover/src/core/proof_of_work.rs:3-7, cpu/grind.rs:5-16: the MINIMUM nonce such that
+ * blake2s(digest || le32(nonce_lo) || le32(nonce_hi)) has >= pow_bits trailing zero bits
+ * (read as a little-endian u128). */
+int cm31_grind_blake2s(const uint8_t digest[32], uint32_t pow_bits, uint64_t* nonce_out);
+
+/* ------------------------------------------------------------------ ComponentProver (constraint eval)
+ * S/constraint_framework/src/component.rs:283-424.  The AIR is passed as a register bytecode
+ * captured from the component's `evaluate` (see cairo-m_b200/csrc/air_bytecode.hpp).
+ *   cols            : host array of device column pointers, each 2^eval_log_size words
+ *                     (trace/interaction/preprocessed LDE columns, in program column order)
+ *   code            : host array of n_instr 64-bit instructions
+ *   consts          : host array of n_consts QM31 constants (4 words each): AIR constants,
+ *                     relation elements, random-coefficient powers, cumsum shift
+ *   denom_inv_host  : 2^(eval_log_size - trace_log_size) M31 values (already bit-reversed)
+ *   acc4            : 4 accumulator columns, RMW:  acc[row] += row_res * denom_inv[row >> trace_log_size]
+ */
+int cm31_constraint_eval(const uint32_t* const* cols, size_t n_cols, uint32_t trace_log_size,
+                         uint32_t eval_log_size, const uint64_t* code, size_t n_instr, uint32_t n_regs,
+                         const uint32_t* consts, size_t n_consts, const uint32_t* denom_inv_host,
+                         uint32_t* const acc4[4]);
+
+/* ------------------------------------------------------------------ witness generation helpers
+ * LogupTraceGenerator (S/constraint_framework/src/logup.rs:123-320) driven by the same bytecode:
+ * the program writes, for every logup batch k, numerator/denominator QM31 pairs; the kernel
+ * forms col_k = col_{k-1} + num_k/den_k on the 2^log_size trace rows. out columns: 4 per batch. */
+int cm31_logup_columns(const uint32_t* const* cols, size_t n_cols, uint32_t log_size, const uint64_t* code,
+                       size_t n_instr, uint32_t n_regs, const uint32_t* consts, size_t n_consts,
+                       uint32_t n_batches, uint32_t* const* out_cols /* 4*n_batches */);
+/* finalize_last (logup.rs:211-251): claimed_sum = sum(last col); last col -= claimed_sum/n;
+ * inclusive prefix sum in coset order (simd/prefix_sum.rs:19, index map core/utils.rs:121-143). */
+int cm31_logup_finalize_last(uint32_t* const last4[4], uint32_t log_size, uint32_t claimed_sum_out[4]);
+/* multiplicity histograms (P/src/preprocessed/range_check/range_check_macro.rs:72-84) */
+int cm31_histogram(const uint32_t* values, size_t n, uint32_t* bins, uint32_t log_bins);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CM31_H */

@@ -1,0 +1,181 @@
+// ORACLE (test infrastructure, not product): C entry points over oracle/cpu_backend.hpp so the
+// Python tests can diff libcm31 against the CPU restatement op by op.  Same flattened argument
+// conventions as include/cm31.h, but every pointer is a HOST pointer.
+#include <cstdio>
+
+#include "cpu_backend.hpp"
+
+using namespace orc;
+
+static std::vector<M31> to_m31(const u32* p, size_t n) {
+    std::vector<M31> v(n);
+    for (size_t i = 0; i < n; i++) v[i] = M31((u64)p[i]);
+    return v;
+}
+static QM31 qm(const u32* p) { return QM31::from_u32(p[0], p[1], p[2], p[3]); }
+static QPoint qpt(const u32* p) { return QPoint{qm(p), qm(p + 4)}; }
+
+extern "C" {
+
+u32 orc_m31_add(u32 a, u32 b) { return (M31((u64)a) + M31((u64)b)).v; }
+u32 orc_m31_sub(u32 a, u32 b) { return (M31((u64)a) - M31((u64)b)).v; }
+u32 orc_m31_mul(u32 a, u32 b) { return (M31((u64)a) * M31((u64)b)).v; }
+u32 orc_m31_inv(u32 a) { return M31((u64)a).inverse().v; }
+void orc_qm31_mul(const u32* a, const u32* b, u32* out) { (qm(a) * qm(b)).to_u32(out); }
+void orc_qm31_inv(const u32* a, u32* out) { qm(a).inverse().to_u32(out); }
+void orc_point_from_index(u32 index, u32* out) {
+    Point p = point_from_index(index);
+    out[0] = p.x.v;
+    out[1] = p.y.v;
+}
+void orc_domain_at(u32 log_size, u32 i, u32* out) {
+    Point p = ODomain::canonic(log_size).at(i);
+    out[0] = p.x.v;
+    out[1] = p.y.v;
+}
+
+void orc_blake2s(const uint8_t* data, size_t len, uint8_t* out) {
+    OBlake2s h;
+    h.update(data, len);
+    h.finalize(out);
+}
+
+void orc_twiddles(u32 log_size, u32* tw_out, u32* itw_out) {
+    OTwiddles t = precompute_twiddles(log_size);
+    for (size_t i = 0; i < t.tw.size(); i++) {
+        tw_out[i] = t.tw[i].v;
+        itw_out[i] = t.itw[i].v;
+    }
+}
+
+// in place: values (2^log_size) -> coefficients
+void orc_interpolate(u32* values, u32 log_size, u32 n_cols) {
+    OTwiddles t = precompute_twiddles(log_size < 3 ? 3 : log_size);
+    size_t n = (size_t)1 << log_size;
+#pragma omp parallel for schedule(dynamic)
+    for (u32 c = 0; c < n_cols; c++) {
+        std::vector<M31> v = to_m31(values + c * n, n);
+        interpolate(v, t);
+        for (size_t i = 0; i < n; i++) values[c * n + i] = v[i].v;
+    }
+}
+void orc_evaluate(const u32* coeffs, u32 log_size, u32 log_eval, u32 n_cols, u32* out) {
+    OTwiddles t = precompute_twiddles(log_eval < 3 ? 3 : log_eval);
+    size_t n = (size_t)1 << log_size, m = (size_t)1 << log_eval;
+#pragma omp parallel for schedule(dynamic)
+    for (u32 c = 0; c < n_cols; c++) {
+        std::vector<M31> v = evaluate(to_m31(coeffs + c * n, n), log_eval, t);
+        for (size_t i = 0; i < m; i++) out[c * m + i] = v[i].v;
+    }
+}
+void orc_eval_at_point(const u32* coeffs, u32 log_size, const u32* point, u32* out) {
+    eval_at_point(to_m31(coeffs, (size_t)1 << log_size), qpt(point)).to_u32(out);
+}
+
+// cols: n_cols contiguous columns of 2^log_size; prev: 2^(log_size+1) hashes or NULL
+void orc_commit_on_layer(u32 log_size, const uint8_t* prev, const u32* cols, u32 n_cols, uint8_t* out) {
+    size_t n = (size_t)1 << log_size;
+    std::vector<std::vector<M31>> cv(n_cols);
+    std::vector<const std::vector<M31>*> cp;
+    for (u32 c = 0; c < n_cols; c++) {
+        cv[c] = to_m31(cols + c * n, n);
+        cp.push_back(&cv[c]);
+    }
+    std::vector<Hash> pv;
+    if (prev) {
+        pv.resize(2 * n);
+        memcpy(pv.data(), prev, 64 * n);
+    }
+    std::vector<Hash> o = commit_on_layer(log_size, prev ? &pv : nullptr, cp);
+    memcpy(out, o.data(), 32 * n);
+}
+
+static SecureColumn sc_from(const u32* src4, size_t n) {  // 4 contiguous coordinate columns
+    SecureColumn s(n);
+    for (int k = 0; k < 4; k++)
+        for (size_t i = 0; i < n; i++) s.c[k][i] = M31((u64)src4[k * n + i]);
+    return s;
+}
+static void sc_to(const SecureColumn& s, u32* dst4) {
+    size_t n = s.size();
+    for (int k = 0; k < 4; k++)
+        for (size_t i = 0; i < n; i++) dst4[k * n + i] = s.c[k][i].v;
+}
+void orc_fold_line(const u32* src4, u32 log_size, const u32* alpha, u32* dst4) {
+    sc_to(fold_line(sc_from(src4, (size_t)1 << log_size), qm(alpha)), dst4);
+}
+void orc_fold_circle_into_line(u32* dst4, const u32* src4, u32 log_size, const u32* alpha) {
+    size_t n = (size_t)1 << log_size;
+    SecureColumn d = sc_from(dst4, n / 2);
+    fold_circle_into_line(d, sc_from(src4, n), qm(alpha));
+    sc_to(d, dst4);
+}
+void orc_decompose(const u32* src4, u32 log_size, u32* dst4, u32* lambda_out) {
+    QM31 lam;
+    sc_to(decompose(sc_from(src4, (size_t)1 << log_size), &lam), dst4);
+    lam.to_u32(lambda_out);
+}
+void orc_accumulate_quotients(u32 log_size, const u32* cols, u32 n_cols, const u32* random_coeff, u32 n_batches,
+                              const u32* batch_points, const u32* batch_start, const u32* col_idx, const u32* values,
+                              u32* out4) {
+    size_t n = (size_t)1 << log_size;
+    std::vector<std::vector<M31>> cv(n_cols);
+    std::vector<const std::vector<M31>*> cp;
+    for (u32 c = 0; c < n_cols; c++) {
+        cv[c] = to_m31(cols + c * n, n);
+        cp.push_back(&cv[c]);
+    }
+    std::vector<SampleBatch> batches(n_batches);
+    for (u32 b = 0; b < n_batches; b++) {
+        batches[b].point = qpt(batch_points + 8 * b);
+        for (u32 k = batch_start[b]; k < batch_start[b + 1]; k++)
+            batches[b].columns_and_values.push_back({col_idx[k], qm(values + 4 * k)});
+    }
+    sc_to(accumulate_quotients(log_size, cp, qm(random_coeff), batches), out4);
+}
+u64 orc_grind(const uint8_t* digest, u32 pow_bits) {
+    OChannel ch;
+    memcpy(ch.digest.b, digest, 32);
+    return grind(ch, pow_bits);
+}
+void orc_prefix_sum(u32* col, u32 log_size) {
+    size_t n = (size_t)1 << log_size;
+    std::vector<M31> r = inclusive_prefix_sum(to_m31(col, n));
+    for (size_t i = 0; i < n; i++) col[i] = r[i].v;
+}
+
+// channel: state = 32 digest bytes + u32 n_sent (36 bytes, caller-owned)
+static OChannel ch_load(const uint8_t* st) {
+    OChannel c;
+    memcpy(c.digest.b, st, 32);
+    memcpy(&c.n_sent, st + 32, 4);
+    return c;
+}
+static void ch_store(const OChannel& c, uint8_t* st) {
+    memcpy(st, c.digest.b, 32);
+    memcpy(st + 32, &c.n_sent, 4);
+}
+void orc_channel_mix_u32s(uint8_t* st, const u32* data, size_t n) {
+    OChannel c = ch_load(st);
+    c.mix_u32s(data, n);
+    ch_store(c, st);
+}
+void orc_channel_mix_u64(uint8_t* st, u64 v) {
+    OChannel c = ch_load(st);
+    c.mix_u64(v);
+    ch_store(c, st);
+}
+void orc_channel_draw_secure_felts(uint8_t* st, size_t n, u32* out) {
+    OChannel c = ch_load(st);
+    auto f = c.draw_secure_felts(n);
+    for (size_t i = 0; i < n; i++) f[i].to_u32(out + 4 * i);
+    ch_store(c, st);
+}
+void orc_channel_draw_random_bytes(uint8_t* st, uint8_t* out) {
+    OChannel c = ch_load(st);
+    Hash h = c.draw_random_bytes();
+    memcpy(out, h.b, 32);
+    ch_store(c, st);
+}
+
+}  // extern "C"
