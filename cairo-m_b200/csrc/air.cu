@@ -1,0 +1,322 @@
+// AIR program kernel: constraint/quotient evaluation on the LDE, logup column generation and
+// lookup-multiplicity histograms, all driven by the register bytecode of host/air_expr.hpp.
+//
+// Replaces the per-row loops of
+//   external/stwo/crates/constraint_framework/src/component.rs:376-423 (SimdDomainEvaluator loop),
+//   constraint_framework/src/logup.rs:123-320 (LogupTraceGenerator),
+//   crates/prover/src/preprocessed/range_check/range_check_macro.rs:72-84 (multiplicity counts).
+// One thread per row; every column access is a coalesced 4-byte-per-lane load; the program and
+// its constants are warp-uniform reads.  The register file lives in per-thread local memory
+// (hardware-interleaved, L1 resident), sized by the program's register allocation.
+#include "common.cuh"
+#include "host/air_expr.hpp"
+
+namespace cm31 {
+
+__device__ __forceinline__ u32 dev_offset_row(u32 row, u32 trace_log, u32 eval_log, int off) {
+    // core/utils.rs:74-90 offset_bit_reversed_circle_domain_index
+    u32 idx = bit_reverse(row, eval_log);
+    u32 half = 1u << (eval_log - 1);
+    int step = off * (int)(1u << (eval_log - trace_log - 1));
+    u32 mask = half - 1;
+    if (idx < half) idx = (u32)((int)idx + step) & mask;
+    else idx = ((u32)((int)(idx - half) - step) & mask) + half;
+    return bit_reverse(idx, eval_log);
+}
+
+__device__ __forceinline__ QM31 rd4(const u32* r, u32 i) { return qm_make(r[i], r[i + 1], r[i + 2], r[i + 3]); }
+__device__ __forceinline__ void wr4(u32* r, u32 i, QM31 v) {
+    r[i] = v.a;
+    r[i + 1] = v.b;
+    r[i + 2] = v.c;
+    r[i + 3] = v.d;
+}
+
+template <int NREGS>
+__global__ void __launch_bounds__(128) air_program_kernel(const u32* const* __restrict__ in_cols, u32* const* __restrict__ out_cols,
+                                                          u32 row_log, u32 trace_log, const uint64_t* __restrict__ code, u32 n_instr,
+                                                          const u32* __restrict__ consts, const u32* __restrict__ denom_inv,
+                                                          u32* acc0, u32* acc1, u32* acc2, u32* acc3) {
+    const u32 row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= (1u << row_log)) return;
+    u32 regs[NREGS];
+    QM31 acc = qm_zero();
+    for (u32 pc = 0; pc < n_instr; pc++) {
+        const uint64_t ins = __ldg(code + pc);
+        const u32 op = (u32)(ins & 0xff);
+        const u32 dst = (u32)((ins >> 8) & 0xffff);
+        const u32 a = (u32)((ins >> 24) & 0xfffff);
+        const u32 b = (u32)((ins >> 44) & 0xfffff);
+        switch (op) {
+            case OP_LOAD: {
+                u32 r = row;
+                if (b != 0) {
+                    int off = (int)(b << 12) >> 12;  // sign-extend 20 bits
+                    r = dev_offset_row(row, trace_log, row_log, off);
+                }
+                regs[dst] = __ldg(in_cols[a] + r);
+                break;
+            }
+            case OP_CONSTF: regs[dst] = __ldg(consts + a); break;
+            case OP_CONSTE:
+                regs[dst] = __ldg(consts + a);
+                regs[dst + 1] = __ldg(consts + a + 1);
+                regs[dst + 2] = __ldg(consts + a + 2);
+                regs[dst + 3] = __ldg(consts + a + 3);
+                break;
+            case OP_ADD: regs[dst] = m31_add(regs[a], regs[b]); break;
+            case OP_SUB: regs[dst] = m31_sub(regs[a], regs[b]); break;
+            case OP_MUL: regs[dst] = m31_mul(regs[a], regs[b]); break;
+            case OP_NEG: regs[dst] = m31_neg(regs[a]); break;
+            case OP_EADD: wr4(regs, dst, qm_add(rd4(regs, a), rd4(regs, b))); break;
+            case OP_ESUB: wr4(regs, dst, qm_sub(rd4(regs, a), rd4(regs, b))); break;
+            case OP_EMUL: wr4(regs, dst, qm_mul(rd4(regs, a), rd4(regs, b))); break;
+            case OP_ENEG: wr4(regs, dst, qm_neg(rd4(regs, a))); break;
+            case OP_EMULF: wr4(regs, dst, qm_mul_m31(rd4(regs, a), regs[b])); break;
+            case OP_EADDF: wr4(regs, dst, qm_add_m31(rd4(regs, a), regs[b])); break;
+            case OP_ESUBF: wr4(regs, dst, qm_sub_m31(rd4(regs, a), regs[b])); break;
+            case OP_F2E: wr4(regs, dst, qm_from_m31(regs[a])); break;
+            case OP_MOV: regs[dst] = regs[a]; break;
+            case OP_EINV: wr4(regs, dst, qm_inv(rd4(regs, a))); break;
+            case OP_CONSTRAINT_E:
+                acc = qm_add(acc, qm_mul(qm_make(__ldg(consts + b), __ldg(consts + b + 1), __ldg(consts + b + 2), __ldg(consts + b + 3)),
+                                         rd4(regs, a)));
+                break;
+            case OP_CONSTRAINT_F:
+                acc = qm_add(acc, qm_mul_m31(qm_make(__ldg(consts + b), __ldg(consts + b + 1), __ldg(consts + b + 2), __ldg(consts + b + 3)),
+                                             regs[a]));
+                break;
+            case OP_STORE_E:
+                out_cols[b][row] = regs[a];
+                out_cols[b + 1][row] = regs[a + 1];
+                out_cols[b + 2][row] = regs[a + 2];
+                out_cols[b + 3][row] = regs[a + 3];
+                break;
+            case OP_STORE_F: out_cols[b][row] = regs[a]; break;
+            case OP_HIST: atomicAdd(out_cols[b] + regs[a], 1u); break;
+            case OP_INV: regs[dst] = m31_inv(regs[a]); break;
+            case OP_SHR: regs[dst] = regs[a] >> b; break;
+            case OP_AND: regs[dst] = regs[a] & b; break;
+            case OP_ROWLT: regs[dst] = row < __ldg(consts + a) ? 1u : 0u; break;
+            default: break;
+        }
+    }
+    if (acc0 != nullptr) {
+        // component.rs:413-421: col[row] += row_res * denom_inv[row >> trace_log]
+        u32 di = __ldg(denom_inv + (row >> trace_log));
+        QM31 v = qm_mul_m31(acc, di);
+        acc0[row] = m31_add(acc0[row], v.a);
+        acc1[row] = m31_add(acc1[row], v.b);
+        acc2[row] = m31_add(acc2[row], v.c);
+        acc3[row] = m31_add(acc3[row], v.d);
+    }
+}
+
+static int run_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* const* out_cols, size_t n_out, u32 row_log,
+                       u32 trace_log, const uint64_t* code, size_t n_instr, u32 n_regs, const u32* consts, size_t n_consts,
+                       const u32* denom_inv_host, size_t n_denom, uint32_t* const* acc4) {
+    CM_REQUIRE(row_log <= 30, "air: too many rows");
+    CM_REQUIRE(n_regs <= 2048, "air: program needs more than 2048 registers");
+    CM_REQUIRE(trace_log <= row_log, "air: trace domain larger than the evaluation domain");
+    DeviceTable din, dout, dcode, dconsts, ddenom;
+    if (int e = din.upload(in_cols, n_in * sizeof(void*))) return e;
+    if (int e = dout.upload(out_cols, n_out * sizeof(void*))) return e;
+    if (int e = dcode.upload(code, n_instr * 8)) return e;
+    if (int e = dconsts.upload(consts, n_consts * 4)) return e;
+    if (acc4) {
+        CM_REQUIRE(n_denom == ((size_t)1 << (row_log - trace_log)), "air: wrong number of denominator inverses");
+        if (int e = ddenom.upload(denom_inv_host, n_denom * 4)) return e;
+    }
+    size_t n = (size_t)1 << row_log;
+    unsigned threads = 128, blocks = (unsigned)((n + threads - 1) / threads);
+    u32 *a0 = acc4 ? acc4[0] : nullptr, *a1 = acc4 ? acc4[1] : nullptr, *a2 = acc4 ? acc4[2] : nullptr,
+        *a3 = acc4 ? acc4[3] : nullptr;
+#define CM_AIR_LAUNCH(NR)                                                                                              \
+    air_program_kernel<NR><<<blocks, threads, 0, stream()>>>((const u32* const*)din.d, (u32* const*)dout.d, row_log,   \
+                                                             trace_log, (const uint64_t*)dcode.d, (u32)n_instr,        \
+                                                             (const u32*)dconsts.d, (const u32*)ddenom.d, a0, a1, a2, a3)
+    if (n_regs <= 64) CM_AIR_LAUNCH(64);
+    else if (n_regs <= 128) CM_AIR_LAUNCH(128);
+    else if (n_regs <= 256) CM_AIR_LAUNCH(256);
+    else if (n_regs <= 512) CM_AIR_LAUNCH(512);
+    else if (n_regs <= 1024) CM_AIR_LAUNCH(1024);
+    else CM_AIR_LAUNCH(2048);
+#undef CM_AIR_LAUNCH
+    CM_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ logup finalize_last
+// (logup.rs:211-251): claimed_sum = Σ rows of the last cumulative column; subtract
+// claimed_sum/n from every row; inclusive prefix sum in COSET order of the bit-reversed
+// circle-domain column (simd/prefix_sum.rs:19-112, index maps core/utils.rs:92-143).
+__device__ __forceinline__ u32 coset_pos_to_row(u32 j, u32 L) {
+    // coset index j -> circle-domain index -> bit-reversed storage row
+    u32 cd = (j & 1) ? (u32)((((u64)2 << L) - j) >> 1) : (j >> 1);
+    return bit_reverse(cd, L);
+}
+
+constexpr u32 SCAN_CHUNK = 1024;  // elements per CTA in the chunked scan
+
+__global__ void __launch_bounds__(256) sum4_kernel(const u32* c0, const u32* c1, const u32* c2, const u32* c3, size_t n,
+                                                   unsigned long long* sums) {
+    __shared__ unsigned long long sh[4][256];
+    unsigned long long s[4] = {0, 0, 0, 0};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        s[0] += c0[i];
+        s[1] += c1[i];
+        s[2] += c2[i];
+        s[3] += c3[i];
+    }
+    for (int k = 0; k < 4; k++) sh[k][threadIdx.x] = s[k];
+    __syncthreads();
+    for (u32 st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st)
+            for (int k = 0; k < 4; k++) sh[k][threadIdx.x] += sh[k][threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        for (int k = 0; k < 4; k++) atomicAdd(&sums[k], sh[k][0] % P);
+}
+
+// pass 1: per-chunk totals of (value - shift) in coset order
+__global__ void __launch_bounds__(256) scan_chunk_sums_kernel(const u32* col, u32 L, u32 shift, u32* chunk_sums) {
+    __shared__ u32 sh[256];
+    u32 chunk = blockIdx.x;
+    size_t n = (size_t)1 << L;
+    u32 acc = 0;
+    for (u32 k = threadIdx.x; k < SCAN_CHUNK; k += 256) {
+        size_t j = (size_t)chunk * SCAN_CHUNK + k;
+        if (j < n) acc = m31_add(acc, m31_sub(col[coset_pos_to_row((u32)j, L)], shift));
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (u32 st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st) sh[threadIdx.x] = m31_add(sh[threadIdx.x], sh[threadIdx.x + st]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) chunk_sums[chunk] = sh[0];
+}
+// pass 2: exclusive scan of the chunk totals (single CTA, sequential over <= 2^20 chunks in tiles)
+__global__ void __launch_bounds__(1024) scan_chunk_offsets_kernel(u32* chunk_sums, u32 n_chunks) {
+    __shared__ u32 sh[1024];
+    __shared__ u32 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (u32 base = 0; base < n_chunks; base += 1024) {
+        u32 i = base + threadIdx.x;
+        u32 v = i < n_chunks ? chunk_sums[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (u32 st = 1; st < 1024; st <<= 1) {
+            u32 t = threadIdx.x >= st ? sh[threadIdx.x - st] : 0;
+            __syncthreads();
+            sh[threadIdx.x] = m31_add(sh[threadIdx.x], t);
+            __syncthreads();
+        }
+        u32 incl = sh[threadIdx.x];
+        if (i < n_chunks) chunk_sums[i] = m31_add(carry, m31_sub(incl, v));  // exclusive
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = m31_add(carry, incl);
+        __syncthreads();
+    }
+}
+// pass 3: in-chunk inclusive scan + chunk offset, written back in place
+__global__ void __launch_bounds__(256) scan_apply_kernel(u32* col, u32 L, u32 shift, const u32* chunk_offsets) {
+    __shared__ u32 sh[256];
+    u32 chunk = blockIdx.x;
+    size_t n = (size_t)1 << L;
+    const u32 per = SCAN_CHUNK / 256;  // 4 consecutive coset positions per thread
+    u32 v[per];
+    u32 rows[per];
+    u32 acc = 0;
+    for (u32 k = 0; k < per; k++) {
+        size_t j = (size_t)chunk * SCAN_CHUNK + threadIdx.x * per + k;
+        rows[k] = j < n ? coset_pos_to_row((u32)j, L) : 0xffffffffu;
+        u32 x = j < n ? m31_sub(col[rows[k]], shift) : 0;
+        acc = m31_add(acc, x);
+        v[k] = acc;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (u32 st = 1; st < 256; st <<= 1) {
+        u32 t = threadIdx.x >= st ? sh[threadIdx.x - st] : 0;
+        __syncthreads();
+        sh[threadIdx.x] = m31_add(sh[threadIdx.x], t);
+        __syncthreads();
+    }
+    u32 excl = m31_sub(sh[threadIdx.x], acc);
+    u32 base = m31_add(chunk_offsets[chunk], excl);
+    for (u32 k = 0; k < per; k++)
+        if (rows[k] != 0xffffffffu) col[rows[k]] = m31_add(base, v[k]);
+}
+
+__global__ void histogram_kernel(const u32* values, size_t n, u32* bins, u32 n_bins) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 v = values[i];
+    if (v < n_bins) atomicAdd(bins + v, 1u);
+}
+
+}  // namespace cm31
+
+using namespace cm31;
+
+extern "C" {
+
+int cm31_constraint_eval(const uint32_t* const* cols, size_t n_cols, uint32_t trace_log_size, uint32_t eval_log_size,
+                         const uint64_t* code, size_t n_instr, uint32_t n_regs, const uint32_t* consts, size_t n_consts,
+                         const uint32_t* denom_inv_host, uint32_t* const acc4[4]) {
+    CM_REQUIRE(acc4 != nullptr && denom_inv_host != nullptr, "constraint_eval: null accumulator");
+    return run_program(cols, n_cols, nullptr, 0, eval_log_size, trace_log_size, code, n_instr, n_regs, consts, n_consts,
+                       denom_inv_host, (size_t)1 << (eval_log_size - trace_log_size), acc4);
+}
+
+int cm31_air_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* const* out_cols, size_t n_out,
+                     uint32_t log_size, const uint64_t* code, size_t n_instr, uint32_t n_regs, const uint32_t* consts,
+                     size_t n_consts) {
+    return run_program(in_cols, n_in, out_cols, n_out, log_size, log_size, code, n_instr, n_regs, consts, n_consts,
+                       nullptr, 0, nullptr);
+}
+
+int cm31_logup_finalize_last(uint32_t* const last4[4], uint32_t log_size, uint32_t claimed_sum_out[4]) {
+    CM_REQUIRE(log_size >= 1 && log_size <= 30, "logup_finalize_last: bad log_size");
+    size_t n = (size_t)1 << log_size;
+    unsigned long long* dsums = nullptr;
+    CM_CUDA(cudaMallocAsync(&dsums, 32, stream()));
+    CM_CUDA(cudaMemsetAsync(dsums, 0, 32, stream()));
+    unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 1024);
+    sum4_kernel<<<blocks, 256, 0, stream()>>>(last4[0], last4[1], last4[2], last4[3], n, dsums);
+    CM_LAUNCH_CHECK();
+    unsigned long long h[4];
+    CM_CUDA(cudaMemcpyAsync(h, dsums, 32, cudaMemcpyDeviceToHost, stream()));
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    CM_CUDA(cudaFreeAsync(dsums, stream()));
+    QM31 claimed = qm_make(m31_reduce64(h[0]), m31_reduce64(h[1]), m31_reduce64(h[2]), m31_reduce64(h[3]));
+    claimed_sum_out[0] = claimed.a;
+    claimed_sum_out[1] = claimed.b;
+    claimed_sum_out[2] = claimed.c;
+    claimed_sum_out[3] = claimed.d;
+    QM31 shift = qm_mul_m31(claimed, m31_inv((u32)(n % P)));
+    u32 sh[4] = {shift.a, shift.b, shift.c, shift.d};
+    u32 n_chunks = (u32)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    u32* dchunks = nullptr;
+    CM_CUDA(cudaMallocAsync(&dchunks, (size_t)n_chunks * 4, stream()));
+    for (int k = 0; k < 4; k++) {
+        scan_chunk_sums_kernel<<<n_chunks, 256, 0, stream()>>>(last4[k], log_size, sh[k], dchunks);
+        scan_chunk_offsets_kernel<<<1, 1024, 0, stream()>>>(dchunks, n_chunks);
+        scan_apply_kernel<<<n_chunks, 256, 0, stream()>>>(last4[k], log_size, sh[k], dchunks);
+    }
+    CM_LAUNCH_CHECK();
+    CM_CUDA(cudaFreeAsync(dchunks, stream()));
+    return 0;
+}
+
+int cm31_histogram(const uint32_t* values, size_t n, uint32_t* bins, uint32_t log_bins) {
+    if (n == 0) return 0;
+    histogram_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(values, n, bins, 1u << log_bins);
+    CM_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -80,7 +80,6 @@ CM_HD void blake2s_compress(Blake2sState& s, const u32 m[16], u64 t, bool last) 
     s.h[7] ^= v7 ^ v15;
 }
 
-#if !defined(__CUDA_ARCH__)
 // Host convenience: hash `len` bytes (little-endian word packing), out = 32 bytes.
 inline void blake2s_hash_bytes(const uint8_t* data, size_t len, uint8_t out[32]) {
     Blake2sState s;
@@ -99,6 +98,5 @@ inline void blake2s_hash_bytes(const uint8_t* data, size_t len, uint8_t out[32])
     blake2s_compress(s, m, len, true);
     memcpy(out, s.h, 32);
 }
-#endif
 
 }  // namespace cm31

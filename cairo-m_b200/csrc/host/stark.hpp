@@ -1,0 +1,881 @@
+// Backend-generic Circle-STARK prover core: Merkle commitment, PCS, FRI, prove().
+//
+// Host-side mirror (C++; no Rust toolchain in this image) of the generic-over-`B: Backend` layer
+// of Stwo that drives the Backend ops:
+//   MerkleProver            external/stwo/crates/prover/src/core/vcs/prover.rs:14-173
+//   CommitmentSchemeProver  core/pcs/prover.rs:25-249, quotient batching core/pcs/quotients.rs:39-102
+//   FriProver               core/fri.rs:142-368, layer provers fri.rs:877-1062
+//   prove                   core/prover/mod.rs:28-85, ComponentProvers core/air/components.rs:16-138,
+//   DomainEvaluationAccumulator core/air/accumulation.rs:49-154
+// `B` supplies the ops (CudaBackend calls libcm31's C ABI; the test oracle supplies a scalar
+// CpuBackend) — the order of channel mixes/draws below is part of the proof contract
+// (SURVEY.md Appendix A).
+#pragma once
+#include <algorithm>
+#include <array>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <set>
+#include <stdexcept>
+#include <vector>
+
+#include "channel.hpp"
+#include "qm_ops.hpp"
+
+namespace cm31 {
+
+struct FriConfig {
+    u32 log_blowup_factor = 1;
+    u32 log_last_layer_degree_bound = 0;
+    size_t n_queries = 80;
+    size_t last_layer_domain_size() const { return (size_t)1 << (log_last_layer_degree_bound + log_blowup_factor); }
+    void mix_into(Blake2sChannel& ch) const {  // fri.rs:80-89
+        ch.mix_u64(log_blowup_factor);
+        ch.mix_u64(n_queries);
+        ch.mix_u64(log_last_layer_degree_bound);
+    }
+};
+struct PcsConfig {
+    u32 pow_bits = 16;
+    FriConfig fri_config;
+    void mix_into(Blake2sChannel& ch) const {  // pcs/mod.rs:42-49
+        ch.mix_u64(pow_bits);
+        fri_config.mix_into(ch);
+    }
+    // crates/prover/src/prover_config.rs:13-20 REGULAR_96_BITS
+    static PcsConfig regular_96_bits() {
+        PcsConfig c;
+        c.pow_bits = 16;
+        c.fri_config.log_blowup_factor = 1;
+        c.fri_config.log_last_layer_degree_bound = 0;
+        c.fri_config.n_queries = 80;
+        return c;
+    }
+};
+
+struct MerkleDecommitment {
+    std::vector<Hash32> hash_witness;
+    std::vector<u32> column_witness;
+};
+struct FriLayerProof {
+    std::vector<QM31> fri_witness;
+    MerkleDecommitment decommitment;
+    Hash32 commitment;
+};
+struct FriProof {
+    FriLayerProof first_layer;
+    std::vector<FriLayerProof> inner_layers;
+    std::vector<QM31> last_layer_poly;  // LinePoly coefficients (bit-reversed storage order)
+};
+struct CommitmentSchemeProof {
+    PcsConfig config;
+    std::vector<Hash32> commitments;
+    std::vector<std::vector<std::vector<QM31>>> sampled_values;  // [tree][column][sample]
+    std::vector<MerkleDecommitment> decommitments;
+    std::vector<std::vector<u32>> queried_values;
+    u64 proof_of_work = 0;
+    FriProof fri_proof;
+};
+typedef CommitmentSchemeProof StarkProof;
+
+struct ConstraintsNotSatisfied : std::runtime_error {
+    ConstraintsNotSatisfied() : std::runtime_error("Constraints not satisfied.") {}
+};
+
+// Canonical byte serialisation (used for bit-exact proof comparison and as the proof blob
+// handed back across the C ABI; the reference's serde/JSON wire format is out of scope).
+class ProofWriter {
+   public:
+    std::vector<uint8_t> bytes;
+    void u32v(u32 v) {
+        for (int i = 0; i < 4; i++) bytes.push_back((uint8_t)(v >> (8 * i)));
+    }
+    void u64v(u64 v) {
+        u32v((u32)v);
+        u32v((u32)(v >> 32));
+    }
+    void qm(QM31 v) {
+        u32v(v.a);
+        u32v(v.b);
+        u32v(v.c);
+        u32v(v.d);
+    }
+    void hash(const Hash32& h) { bytes.insert(bytes.end(), h.b, h.b + 32); }
+    void decommitment(const MerkleDecommitment& d) {
+        u64v(d.hash_witness.size());
+        for (auto& h : d.hash_witness) hash(h);
+        u64v(d.column_witness.size());
+        for (u32 v : d.column_witness) u32v(v);
+    }
+    void fri_layer(const FriLayerProof& l) {
+        u64v(l.fri_witness.size());
+        for (auto& v : l.fri_witness) qm(v);
+        decommitment(l.decommitment);
+        hash(l.commitment);
+    }
+    void proof(const CommitmentSchemeProof& p) {
+        u32v(p.config.pow_bits);
+        u32v(p.config.fri_config.log_blowup_factor);
+        u32v(p.config.fri_config.log_last_layer_degree_bound);
+        u64v(p.config.fri_config.n_queries);
+        u64v(p.commitments.size());
+        for (auto& h : p.commitments) hash(h);
+        u64v(p.sampled_values.size());
+        for (auto& tree : p.sampled_values) {
+            u64v(tree.size());
+            for (auto& col : tree) {
+                u64v(col.size());
+                for (auto& v : col) qm(v);
+            }
+        }
+        u64v(p.decommitments.size());
+        for (auto& d : p.decommitments) decommitment(d);
+        u64v(p.queried_values.size());
+        for (auto& q : p.queried_values) {
+            u64v(q.size());
+            for (u32 v : q) u32v(v);
+        }
+        u64v(p.proof_of_work);
+        fri_layer(p.fri_proof.first_layer);
+        u64v(p.fri_proof.inner_layers.size());
+        for (auto& l : p.fri_proof.inner_layers) fri_layer(l);
+        u64v(p.fri_proof.last_layer_poly.size());
+        for (auto& v : p.fri_proof.last_layer_poly) qm(v);
+    }
+};
+
+class ProofReader {
+   public:
+    const uint8_t* p;
+    size_t n, pos = 0;
+    ProofReader(const uint8_t* data, size_t len) : p(data), n(len) {}
+    void need(size_t k) {
+        if (pos + k > n) throw std::runtime_error("proof blob truncated");
+    }
+    u32 u32v() {
+        need(4);
+        u32 v = (u32)p[pos] | ((u32)p[pos + 1] << 8) | ((u32)p[pos + 2] << 16) | ((u32)p[pos + 3] << 24);
+        pos += 4;
+        return v;
+    }
+    u64 u64v() {
+        u64 lo = u32v();
+        u64 hi = u32v();
+        return lo | (hi << 32);
+    }
+    QM31 qm() {
+        u32 a = u32v(), b = u32v(), c = u32v(), d = u32v();
+        return qm_make(a, b, c, d);
+    }
+    Hash32 hash() {
+        need(32);
+        Hash32 h;
+        memcpy(h.b, p + pos, 32);
+        pos += 32;
+        return h;
+    }
+    MerkleDecommitment decommitment() {
+        MerkleDecommitment d;
+        u64 nh = u64v();
+        for (u64 i = 0; i < nh; i++) d.hash_witness.push_back(hash());
+        u64 nc = u64v();
+        for (u64 i = 0; i < nc; i++) d.column_witness.push_back(u32v());
+        return d;
+    }
+    FriLayerProof fri_layer() {
+        FriLayerProof l;
+        u64 nw = u64v();
+        for (u64 i = 0; i < nw; i++) l.fri_witness.push_back(qm());
+        l.decommitment = decommitment();
+        l.commitment = hash();
+        return l;
+    }
+    CommitmentSchemeProof proof() {
+        CommitmentSchemeProof pr;
+        pr.config.pow_bits = u32v();
+        pr.config.fri_config.log_blowup_factor = u32v();
+        pr.config.fri_config.log_last_layer_degree_bound = u32v();
+        pr.config.fri_config.n_queries = (size_t)u64v();
+        u64 nc = u64v();
+        for (u64 i = 0; i < nc; i++) pr.commitments.push_back(hash());
+        u64 nt = u64v();
+        for (u64 t = 0; t < nt; t++) {
+            pr.sampled_values.emplace_back();
+            u64 ncol = u64v();
+            for (u64 c = 0; c < ncol; c++) {
+                pr.sampled_values.back().emplace_back();
+                u64 ns = u64v();
+                for (u64 k = 0; k < ns; k++) pr.sampled_values.back().back().push_back(qm());
+            }
+        }
+        u64 nd = u64v();
+        for (u64 i = 0; i < nd; i++) pr.decommitments.push_back(decommitment());
+        u64 nq = u64v();
+        for (u64 i = 0; i < nq; i++) {
+            pr.queried_values.emplace_back();
+            u64 k = u64v();
+            for (u64 j = 0; j < k; j++) pr.queried_values.back().push_back(u32v());
+        }
+        pr.proof_of_work = u64v();
+        pr.fri_proof.first_layer = fri_layer();
+        u64 ni = u64v();
+        for (u64 i = 0; i < ni; i++) pr.fri_proof.inner_layers.push_back(fri_layer());
+        u64 nl = u64v();
+        for (u64 i = 0; i < nl; i++) pr.fri_proof.last_layer_poly.push_back(qm());
+        return pr;
+    }
+};
+
+inline u32 ilog2(size_t n) {
+    u32 l = 0;
+    while (((size_t)1 << (l + 1)) <= n) l++;
+    return l;
+}
+
+// ------------------------------------------------------------------ MerkleProver (vcs/prover.rs)
+template <class B>
+struct MerkleProver {
+    typedef typename B::Col Col;
+    typedef typename B::HashCol HashCol;
+    std::vector<HashCol> layers;  // layers[0] = root layer
+
+    static MerkleProver commit(const std::vector<const Col*>& columns) {
+        MerkleProver mp;
+        if (columns.empty()) {
+            mp.layers.push_back(B::commit_on_layer(0, nullptr, {}));
+            return mp;
+        }
+        std::vector<const Col*> sorted = columns;
+        std::stable_sort(sorted.begin(), sorted.end(), [](const Col* a, const Col* b) { return B::len(*a) > B::len(*b); });
+        u32 max_log = ilog2(B::len(*sorted[0]));
+        size_t pos = 0;
+        std::vector<HashCol> layers;
+        for (int log_size = (int)max_log; log_size >= 0; log_size--) {
+            std::vector<const Col*> layer_cols;
+            while (pos < sorted.size() && ilog2(B::len(*sorted[pos])) == (u32)log_size) layer_cols.push_back(sorted[pos++]);
+            const HashCol* prev = layers.empty() ? nullptr : &layers.back();
+            layers.push_back(B::commit_on_layer((u32)log_size, prev, layer_cols));
+        }
+        std::reverse(layers.begin(), layers.end());
+        mp.layers = std::move(layers);
+        return mp;
+    }
+
+    Hash32 root() const {
+        std::vector<Hash32> out;
+        B::gather_hashes(layers[0], {0}, out);
+        return out[0];
+    }
+
+    // vcs/prover.rs:82-156.  The control flow only depends on indices, so the node lists are
+    // computed first and the values fetched with one batched gather per layer.
+    std::pair<std::vector<u32>, MerkleDecommitment> decommit(const std::map<u32, std::vector<size_t>>& queries_per_log_size,
+                                                             const std::vector<const Col*>& columns) const {
+        std::vector<u32> queried_values;
+        MerkleDecommitment decommitment;
+        std::vector<const Col*> sorted = columns;
+        std::stable_sort(sorted.begin(), sorted.end(), [](const Col* a, const Col* b) { return B::len(*a) > B::len(*b); });
+        size_t pos = 0;
+        std::vector<size_t> last_layer_queries;
+        for (int layer_log_size = (int)layers.size() - 1; layer_log_size >= 0; layer_log_size--) {
+            std::vector<const Col*> layer_columns;
+            while (pos < sorted.size() && ilog2(B::len(*sorted[pos])) == (u32)layer_log_size) layer_columns.push_back(sorted[pos++]);
+            const HashCol* previous_layer_hashes = (size_t)layer_log_size + 1 < layers.size() ? &layers[layer_log_size + 1] : nullptr;
+            static const std::vector<size_t> empty;
+            auto qit = queries_per_log_size.find((u32)layer_log_size);
+            const std::vector<size_t>& layer_column_queries = qit == queries_per_log_size.end() ? empty : qit->second;
+            size_t pi = 0, ci = 0;
+            std::vector<size_t> layer_total_queries;
+            std::vector<u32> hash_witness_idx;
+            std::vector<char> node_is_queried;
+            while (pi < last_layer_queries.size() || ci < layer_column_queries.size()) {
+                size_t node_index;
+                bool has_p = pi < last_layer_queries.size(), has_c = ci < layer_column_queries.size();
+                if (has_p && has_c) node_index = std::min(last_layer_queries[pi] / 2, layer_column_queries[ci]);
+                else if (has_p) node_index = last_layer_queries[pi] / 2;
+                else node_index = layer_column_queries[ci];
+                if (previous_layer_hashes) {
+                    if (pi < last_layer_queries.size() && last_layer_queries[pi] == 2 * node_index) pi++;
+                    else hash_witness_idx.push_back((u32)(2 * node_index));
+                    if (pi < last_layer_queries.size() && last_layer_queries[pi] == 2 * node_index + 1) pi++;
+                    else hash_witness_idx.push_back((u32)(2 * node_index + 1));
+                }
+                bool queried = ci < layer_column_queries.size() && layer_column_queries[ci] == node_index;
+                if (queried) ci++;
+                node_is_queried.push_back(queried ? 1 : 0);
+                layer_total_queries.push_back(node_index);
+            }
+            if (previous_layer_hashes && !hash_witness_idx.empty()) {
+                std::vector<Hash32> hs;
+                B::gather_hashes(*previous_layer_hashes, hash_witness_idx, hs);
+                decommitment.hash_witness.insert(decommitment.hash_witness.end(), hs.begin(), hs.end());
+            }
+            if (!layer_columns.empty() && !layer_total_queries.empty()) {
+                std::vector<u32> idx(layer_total_queries.begin(), layer_total_queries.end());
+                std::vector<std::vector<u32>> vals;
+                B::gather(layer_columns, idx, vals);
+                for (size_t q = 0; q < idx.size(); q++) {
+                    std::vector<u32>& dst = node_is_queried[q] ? queried_values : decommitment.column_witness;
+                    for (size_t c = 0; c < layer_columns.size(); c++) dst.push_back(vals[c][q]);
+                }
+            }
+            last_layer_queries = layer_total_queries;
+        }
+        return {queried_values, decommitment};
+    }
+};
+
+// ------------------------------------------------------------------ polynomials / evaluations
+template <class B>
+struct CirclePoly {
+    typename B::Col coeffs;
+    u32 log_size;
+};
+template <class B>
+struct CircleEvaluation {  // values on CanonicCoset(log_size).circle_domain(), bit-reversed order
+    typename B::Col values;
+    u32 log_size;
+};
+template <class B>
+struct SecureEvaluation {
+    std::array<typename B::Col, 4> columns;
+    u32 log_size;
+};
+
+struct PointSample {
+    SecurePoint point;
+    QM31 value;
+};
+struct ColumnSampleBatch {  // pcs/quotients.rs:39-70
+    SecurePoint point;
+    std::vector<std::pair<size_t, QM31>> columns_and_values;
+    static std::vector<ColumnSampleBatch> new_vec(const std::vector<const std::vector<PointSample>*>& samples) {
+        std::vector<ColumnSampleBatch> out;  // insertion order = first appearance of the point (IndexMap)
+        for (size_t column_index = 0; column_index < samples.size(); column_index++) {
+            for (const PointSample& s : *samples[column_index]) {
+                size_t k = 0;
+                for (; k < out.size(); k++)
+                    if (cpq_eq(out[k].point, s.point)) break;
+                if (k == out.size()) out.push_back(ColumnSampleBatch{s.point, {}});
+                out[k].columns_and_values.push_back({column_index, s.value});
+            }
+        }
+        return out;
+    }
+};
+
+// ------------------------------------------------------------------ CommitmentTreeProver / CommitmentSchemeProver
+template <class B>
+struct CommitmentTreeProver {
+    std::vector<CirclePoly<B>> polynomials;
+    std::vector<CircleEvaluation<B>> evaluations;
+    MerkleProver<B> commitment;
+
+    static CommitmentTreeProver create(std::vector<CirclePoly<B>> polynomials, u32 log_blowup_factor, Blake2sChannel& channel,
+                                       const typename B::Twiddles& twiddles) {
+        CommitmentTreeProver t;
+        t.polynomials = std::move(polynomials);
+        t.evaluations.resize(t.polynomials.size());
+        // B::evaluate_polynomials, batched per log size (ops.rs:51-65)
+        std::map<u32, std::vector<size_t>> by_size;
+        for (size_t i = 0; i < t.polynomials.size(); i++) by_size[t.polynomials[i].log_size].push_back(i);
+        for (auto& kv : by_size) {
+            u32 log_size = kv.first, log_eval = log_size + log_blowup_factor;
+            std::vector<const typename B::Col*> src;
+            std::vector<typename B::Col*> dst;
+            for (size_t i : kv.second) {
+                t.evaluations[i].values = B::uninit((size_t)1 << log_eval);
+                t.evaluations[i].log_size = log_eval;
+                src.push_back(&t.polynomials[i].coeffs);
+                dst.push_back(&t.evaluations[i].values);
+            }
+            B::evaluate_polynomials(src, dst, log_size, log_eval, twiddles);
+        }
+        std::vector<const typename B::Col*> cols;
+        for (auto& e : t.evaluations) cols.push_back(&e.values);
+        t.commitment = MerkleProver<B>::commit(cols);
+        channel.mix_root(t.commitment.root());
+        return t;
+    }
+    std::pair<std::vector<u32>, MerkleDecommitment> decommit(const std::map<u32, std::vector<size_t>>& queries) const {
+        std::vector<const typename B::Col*> cols;
+        for (auto& e : evaluations) cols.push_back(&e.values);
+        return commitment.decommit(queries, cols);
+    }
+};
+
+template <class B>
+struct FriProver;
+
+template <class B>
+struct CommitmentSchemeProver {
+    std::vector<CommitmentTreeProver<B>> trees;
+    PcsConfig config;
+    const typename B::Twiddles* twiddles;
+
+    CommitmentSchemeProver(PcsConfig cfg, const typename B::Twiddles* tw) : config(cfg), twiddles(tw) {}
+
+    // TreeBuilder::extend_evals + commit (pcs/prover.rs:173-203): columns are consumed.
+    void commit_evals(std::vector<CircleEvaluation<B>> columns, Blake2sChannel& channel) {
+        std::map<u32, std::vector<typename B::Col*>> by_size;
+        for (auto& c : columns) by_size[c.log_size].push_back(&c.values);
+        for (auto& kv : by_size) B::interpolate_columns(kv.second, kv.first, *twiddles);
+        std::vector<CirclePoly<B>> polys;
+        for (auto& c : columns) polys.push_back(CirclePoly<B>{std::move(c.values), c.log_size});
+        commit_polys(std::move(polys), channel);
+    }
+    void commit_polys(std::vector<CirclePoly<B>> polys, Blake2sChannel& channel) {
+        trees.push_back(CommitmentTreeProver<B>::create(std::move(polys), config.fri_config.log_blowup_factor, channel, *twiddles));
+    }
+    std::vector<Hash32> roots() const {
+        std::vector<Hash32> r;
+        for (auto& t : trees) r.push_back(t.commitment.root());
+        return r;
+    }
+
+    // prove_values (pcs/prover.rs:83-153)
+    CommitmentSchemeProof prove_values(const std::vector<std::vector<std::vector<SecurePoint>>>& sampled_points, Blake2sChannel& channel);
+};
+
+// ------------------------------------------------------------------ FRI (core/fri.rs)
+template <class B>
+struct FriProver {
+    typedef typename B::Col Col;
+    struct InnerLayer {
+        std::array<Col, 4> evaluation;
+        u32 log_size;
+        MerkleProver<B> merkle_tree;
+    };
+    FriConfig config;
+    const std::vector<SecureEvaluation<B>>* columns = nullptr;
+    MerkleProver<B> first_layer_tree;
+    std::vector<InnerLayer> inner_layers;
+    std::vector<QM31> last_layer_poly;
+
+    static std::vector<const Col*> coordinate_columns(const std::vector<SecureEvaluation<B>>& columns) {
+        std::vector<const Col*> out;
+        for (auto& sc : columns)
+            for (auto& c : sc.columns) out.push_back(&c);
+        return out;
+    }
+
+    static FriProver commit(Blake2sChannel& channel, FriConfig config, const std::vector<SecureEvaluation<B>>& columns,
+                            const typename B::Twiddles& twiddles) {
+        if (columns.empty()) throw std::logic_error("no columns");
+        for (size_t i = 0; i + 1 < columns.size(); i++)
+            if (!(columns[i].log_size > columns[i + 1].log_size)) throw std::logic_error("column sizes not decreasing");
+        FriProver fp;
+        fp.config = config;
+        fp.columns = &columns;
+        // commit_first_layer
+        fp.first_layer_tree = MerkleProver<B>::commit(coordinate_columns(columns));
+        channel.mix_root(fp.first_layer_tree.root());
+        // commit_inner_layers
+        u32 first_inner_log = columns[0].log_size - 1;
+        std::array<Col, 4> layer_eval;
+        for (auto& c : layer_eval) c = B::zeros((size_t)1 << first_inner_log);
+        u32 layer_log = first_inner_log;
+        size_t next_col = 0;
+        QM31 folding_alpha = channel.draw_secure_felt();
+        B::fold_circle_into_line(layer_eval, columns[next_col].columns, columns[next_col].log_size, folding_alpha, twiddles);
+        next_col++;
+        while (((size_t)1 << layer_log) > config.last_layer_domain_size()) {
+            InnerLayer layer;
+            std::vector<const Col*> cc;
+            for (auto& c : layer_eval) cc.push_back(&c);
+            layer.merkle_tree = MerkleProver<B>::commit(cc);
+            channel.mix_root(layer.merkle_tree.root());
+            QM31 alpha = channel.draw_secure_felt();
+            std::array<Col, 4> folded = B::fold_line(layer_eval, layer_log, alpha, twiddles);
+            layer.evaluation = std::move(layer_eval);
+            layer.log_size = layer_log;
+            layer_eval = std::move(folded);
+            layer_log -= 1;
+            if (next_col < columns.size() && columns[next_col].log_size - 1 == layer_log) {
+                B::fold_circle_into_line(layer_eval, columns[next_col].columns, columns[next_col].log_size, alpha, twiddles);
+                next_col++;
+            }
+            fp.inner_layers.push_back(std::move(layer));
+        }
+        if (next_col != columns.size()) throw std::logic_error("not all columns were folded");
+        // commit_last_layer (fri.rs:268-290): interpolate the line evaluation on the host
+        size_t n_last = (size_t)1 << layer_log;
+        if (n_last != config.last_layer_domain_size()) throw std::logic_error("bad last layer size");
+        std::vector<QM31> values(n_last);
+        {
+            std::vector<u32> h[4];
+            for (int k = 0; k < 4; k++) {
+                h[k].resize(n_last);
+                B::to_host(layer_eval[k], h[k].data());
+            }
+            for (size_t i = 0; i < n_last; i++) values[i] = qm_make(h[0][i], h[1][i], h[2][i], h[3][i]);
+        }
+        fp.last_layer_poly = interpolate_last_layer(values, layer_log, config);
+        channel.mix_felts(fp.last_layer_poly);
+        return fp;
+    }
+
+    // LineEvaluation::interpolate + into_ordered_coefficients/from_ordered_coefficients (poly/line.rs)
+    static std::vector<QM31> interpolate_last_layer(std::vector<QM31> values, u32 log_size, const FriConfig& config) {
+        size_t n = values.size();
+        // bit_reverse_column
+        for (size_t i = 0; i < n; i++) {
+            size_t j = bit_reverse((u32)i, log_size);
+            if (i < j) std::swap(values[i], values[j]);
+        }
+        // line_ifft on LineDomain(half_odds(log_size))
+        Coset dom = Coset::half_odds(log_size);
+        size_t dsize = n;
+        while (dsize > 1) {
+            for (size_t chunk = 0; chunk < n; chunk += dsize) {
+                for (size_t i = 0; i < dsize / 2; i++) {
+                    u32 x = dom.at(i).x;
+                    u32 xi = m31_inv(x);
+                    QM31& l = values[chunk + i];
+                    QM31& r = values[chunk + dsize / 2 + i];
+                    QM31 tmp = l;
+                    l = tmp + r;
+                    r = qm_mul_m31(tmp - r, xi);
+                }
+            }
+            dom = dom.doubled();
+            dsize /= 2;
+        }
+        u32 len_inv = m31_inv((u32)n);
+        for (auto& v : values) v = qm_mul_m31(v, len_inv);
+        // into_ordered_coefficients: bit reverse
+        for (size_t i = 0; i < n; i++) {
+            size_t j = bit_reverse((u32)i, log_size);
+            if (i < j) std::swap(values[i], values[j]);
+        }
+        size_t bound = (size_t)1 << config.log_last_layer_degree_bound;
+        for (size_t i = bound; i < n; i++)
+            if (!qm_is_zero(values[i])) throw std::logic_error("invalid degree");
+        values.resize(bound);
+        // from_ordered_coefficients: bit reverse again (over `bound` elements)
+        u32 lb = config.log_last_layer_degree_bound;
+        for (size_t i = 0; i < bound; i++) {
+            size_t j = bit_reverse((u32)i, lb);
+            if (i < j) std::swap(values[i], values[j]);
+        }
+        return values;
+    }
+
+    // compute_decommitment_positions_and_witness_evals (fri.rs:1002-1036), batched gather
+    static void positions_and_witness(const std::array<Col, 4>& column, const std::vector<size_t>& query_positions, u32 fold_step,
+                                      std::vector<size_t>& decommitment_positions, std::vector<QM31>& witness_evals) {
+        std::vector<u32> need;
+        size_t i = 0;
+        while (i < query_positions.size()) {
+            size_t j = i;
+            while (j < query_positions.size() && (query_positions[j] >> fold_step) == (query_positions[i] >> fold_step)) j++;
+            size_t subset_start = (query_positions[i] >> fold_step) << fold_step;
+            size_t qi = i;
+            for (size_t position = subset_start; position < subset_start + ((size_t)1 << fold_step); position++) {
+                decommitment_positions.push_back(position);
+                if (qi < j && query_positions[qi] == position) {
+                    qi++;
+                    continue;
+                }
+                need.push_back((u32)position);
+            }
+            i = j;
+        }
+        if (!need.empty()) {
+            std::vector<const Col*> cols;
+            for (auto& c : column) cols.push_back(&c);
+            std::vector<std::vector<u32>> vals;
+            B::gather(cols, need, vals);
+            for (size_t k = 0; k < need.size(); k++) witness_evals.push_back(qm_make(vals[0][k], vals[1][k], vals[2][k], vals[3][k]));
+        }
+    }
+
+    std::pair<FriProof, std::map<u32, std::vector<size_t>>> decommit(Blake2sChannel& channel) {
+        std::set<u32> column_log_sizes;
+        for (auto& c : *columns) column_log_sizes.insert(c.log_size);
+        u32 max_column_log_size = *column_log_sizes.rbegin();
+        Queries queries = Queries::generate(channel, max_column_log_size, config.n_queries);
+        std::map<u32, std::vector<size_t>> query_positions_by_log_size;
+        for (u32 ls : column_log_sizes) query_positions_by_log_size[ls] = queries.fold(queries.log_domain_size - ls).positions;
+        FriProof proof;
+        // first layer (fri.rs:906-945)
+        {
+            std::map<u32, std::vector<size_t>> decommitment_positions_by_log_size;
+            for (auto& column : *columns) {
+                Queries cq = queries.fold(queries.log_domain_size - column.log_size);
+                std::vector<size_t> positions;
+                positions_and_witness(column.columns, cq.positions, 1, positions, proof.first_layer.fri_witness);
+                decommitment_positions_by_log_size[column.log_size] = positions;
+            }
+            auto res = first_layer_tree.decommit(decommitment_positions_by_log_size, coordinate_columns(*columns));
+            proof.first_layer.decommitment = res.second;
+            proof.first_layer.commitment = first_layer_tree.root();
+        }
+        Queries layer_queries = queries.fold(1);
+        for (auto& layer : inner_layers) {
+            FriLayerProof lp;
+            std::vector<size_t> positions;
+            positions_and_witness(layer.evaluation, layer_queries.positions, 1, positions, lp.fri_witness);
+            std::map<u32, std::vector<size_t>> m;
+            m[layer.log_size] = positions;
+            std::vector<const Col*> cc;
+            for (auto& c : layer.evaluation) cc.push_back(&c);
+            auto res = layer.merkle_tree.decommit(m, cc);
+            lp.decommitment = res.second;
+            lp.commitment = layer.merkle_tree.root();
+            proof.inner_layers.push_back(std::move(lp));
+            layer_queries = layer_queries.fold(1);
+        }
+        proof.last_layer_poly = last_layer_poly;
+        return {proof, query_positions_by_log_size};
+    }
+};
+
+// compute_fri_quotients (pcs/quotients.rs:77-102)
+template <class B>
+std::vector<SecureEvaluation<B>> compute_fri_quotients(const std::vector<const CircleEvaluation<B>*>& columns,
+                                                       const std::vector<std::vector<PointSample>>& samples, QM31 random_coeff,
+                                                       u32 log_blowup_factor) {
+    std::vector<size_t> order(columns.size());
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return columns[a]->log_size > columns[b]->log_size; });
+    std::vector<SecureEvaluation<B>> out;
+    size_t i = 0;
+    while (i < order.size()) {
+        u32 log_size = columns[order[i]]->log_size;
+        std::vector<const typename B::Col*> cols;
+        std::vector<const std::vector<PointSample>*> smp;
+        while (i < order.size() && columns[order[i]]->log_size == log_size) {
+            cols.push_back(&columns[order[i]]->values);
+            smp.push_back(&samples[order[i]]);
+            i++;
+        }
+        std::vector<ColumnSampleBatch> batches = ColumnSampleBatch::new_vec(smp);
+        SecureEvaluation<B> ev;
+        ev.log_size = log_size;
+        ev.columns = B::accumulate_quotients(log_size, cols, random_coeff, batches, log_blowup_factor);
+        out.push_back(std::move(ev));
+    }
+    return out;
+}
+
+template <class B>
+CommitmentSchemeProof CommitmentSchemeProver<B>::prove_values(const std::vector<std::vector<std::vector<SecurePoint>>>& sampled_points,
+                                                              Blake2sChannel& channel) {
+    // Evaluate polynomials on open points: one batched eval_at_point over every (column, point).
+    std::vector<const typename B::Col*> polys;
+    std::vector<u32> log_sizes, point_idx;
+    std::vector<SecurePoint> points;
+    for (size_t t = 0; t < trees.size(); t++) {
+        if (sampled_points[t].size() != trees[t].polynomials.size()) throw std::logic_error("sampled_points shape mismatch");
+        for (size_t c = 0; c < trees[t].polynomials.size(); c++) {
+            for (const SecurePoint& p : sampled_points[t][c]) {
+                size_t k = 0;
+                for (; k < points.size(); k++)
+                    if (cpq_eq(points[k], p)) break;
+                if (k == points.size()) points.push_back(p);
+                polys.push_back(&trees[t].polynomials[c].coeffs);
+                log_sizes.push_back(trees[t].polynomials[c].log_size);
+                point_idx.push_back((u32)k);
+            }
+        }
+    }
+    std::vector<QM31> values;
+    B::eval_at_points(polys, log_sizes, points, point_idx, values);
+    CommitmentSchemeProof proof;
+    proof.config = config;
+    std::vector<std::vector<PointSample>> samples_flat;
+    std::vector<QM31> sampled_flat;
+    size_t vi = 0;
+    for (size_t t = 0; t < trees.size(); t++) {
+        proof.sampled_values.emplace_back();
+        for (size_t c = 0; c < trees[t].polynomials.size(); c++) {
+            std::vector<QM31> col_vals;
+            std::vector<PointSample> col_samples;
+            for (const SecurePoint& p : sampled_points[t][c]) {
+                col_vals.push_back(values[vi]);
+                col_samples.push_back(PointSample{p, values[vi]});
+                sampled_flat.push_back(values[vi]);
+                vi++;
+            }
+            proof.sampled_values.back().push_back(col_vals);
+            samples_flat.push_back(col_samples);
+        }
+    }
+    channel.mix_felts(sampled_flat);
+
+    std::vector<const CircleEvaluation<B>*> columns;
+    for (auto& t : trees)
+        for (auto& e : t.evaluations) columns.push_back(&e);
+    QM31 random_coeff = channel.draw_secure_felt();
+    std::vector<SecureEvaluation<B>> quotients = compute_fri_quotients<B>(columns, samples_flat, random_coeff, config.fri_config.log_blowup_factor);
+
+    FriProver<B> fri_prover = FriProver<B>::commit(channel, config.fri_config, quotients, *twiddles);
+
+    proof.proof_of_work = B::grind(channel.digest(), config.pow_bits);
+    channel.mix_u64(proof.proof_of_work);
+
+    auto fri_res = fri_prover.decommit(channel);
+    proof.fri_proof = std::move(fri_res.first);
+    const std::map<u32, std::vector<size_t>>& query_positions_per_log_size = fri_res.second;
+
+    for (auto& t : trees) {
+        auto res = t.decommit(query_positions_per_log_size);
+        proof.queried_values.push_back(std::move(res.first));
+        proof.decommitments.push_back(std::move(res.second));
+    }
+    proof.commitments = roots();
+    return proof;
+}
+
+// ------------------------------------------------------------------ components & prove()
+// DomainEvaluationAccumulator (air/accumulation.rs:49-154)
+template <class B>
+struct DomainEvaluationAccumulator {
+    std::vector<QM31> random_coeff_powers;
+    std::vector<std::unique_ptr<std::array<typename B::Col, 4>>> sub_accumulations;  // index = log size
+
+    DomainEvaluationAccumulator(QM31 random_coeff, u32 max_log_size, size_t total_columns) {
+        random_coeff_powers = B::generate_secure_powers(random_coeff, total_columns);
+        sub_accumulations.resize(max_log_size + 1);
+    }
+    u32 log_size() const { return (u32)sub_accumulations.size() - 1; }
+    // columns([(log_size, n_cols)]): hands out the LAST n_cols powers (accumulation.rs:75-96)
+    std::pair<std::vector<QM31>, std::array<typename B::Col, 4>*> columns(u32 log_size, size_t n_cols) {
+        if (n_cols > random_coeff_powers.size()) throw std::logic_error("not enough random coefficient powers");
+        std::vector<QM31> coeffs(random_coeff_powers.end() - n_cols, random_coeff_powers.end());
+        random_coeff_powers.resize(random_coeff_powers.size() - n_cols);
+        auto& slot = sub_accumulations.at(log_size);
+        if (!slot) {
+            slot.reset(new std::array<typename B::Col, 4>());
+            for (auto& c : *slot) c = B::zeros((size_t)1 << log_size);
+        }
+        return {coeffs, slot.get()};
+    }
+    // finalize (accumulation.rs:104-153): per size ascending, interpolate and lift the previous poly
+    std::array<CirclePoly<B>, 4> finalize(const typename B::Twiddles& twiddles) {
+        if (!random_coeff_powers.empty()) throw std::logic_error("not all random coefficients were used");
+        u32 max_log = log_size();
+        bool have = false;
+        std::array<CirclePoly<B>, 4> cur;
+        for (u32 ls = 1; ls <= max_log; ls++) {
+            if (!sub_accumulations[ls]) continue;
+            std::array<typename B::Col, 4>& values = *sub_accumulations[ls];
+            if (have) {
+                std::array<typename B::Col, 4> lifted;
+                std::vector<const typename B::Col*> src;
+                std::vector<typename B::Col*> dst;
+                for (int k = 0; k < 4; k++) {
+                    lifted[k] = B::uninit((size_t)1 << ls);
+                    src.push_back(&cur[k].coeffs);
+                    dst.push_back(&lifted[k]);
+                }
+                B::evaluate_polynomials(src, dst, cur[0].log_size, ls, twiddles);
+                B::accumulate(values, lifted);
+            }
+            std::vector<typename B::Col*> cols;
+            for (int k = 0; k < 4; k++) cols.push_back(&values[k]);
+            B::interpolate_columns(cols, ls, twiddles);
+            for (int k = 0; k < 4; k++) cur[k] = CirclePoly<B>{std::move(values[k]), ls};
+            have = true;
+        }
+        if (!have)
+            for (int k = 0; k < 4; k++) cur[k] = CirclePoly<B>{B::zeros((size_t)1 << max_log), max_log};
+        return cur;
+    }
+};
+
+struct PointEvaluationAccumulator {  // accumulation.rs:18-44
+    QM31 random_coeff, accumulation;
+    explicit PointEvaluationAccumulator(QM31 rc) : random_coeff(rc), accumulation(qm_zero()) {}
+    void accumulate(QM31 evaluation) { accumulation = accumulation * random_coeff + evaluation; }
+};
+
+template <class B>
+struct Trace {
+    const std::vector<CommitmentTreeProver<B>>* trees;
+};
+
+typedef std::vector<std::vector<std::vector<SecurePoint>>> MaskPoints;   // [tree][column][point]
+typedef std::vector<std::vector<std::vector<QM31>>> MaskValues;
+
+// Component + ComponentProver (air/mod.rs:26-67)
+template <class B>
+struct ComponentProver {
+    virtual ~ComponentProver() {}
+    virtual size_t n_constraints() const = 0;
+    virtual u32 max_constraint_log_degree_bound() const = 0;
+    virtual std::vector<std::vector<u32>> trace_log_degree_bounds() const = 0;
+    virtual MaskPoints mask_points(SecurePoint point) const = 0;
+    virtual std::vector<size_t> preprocessed_column_indices() const = 0;
+    virtual void evaluate_constraint_quotients_at_point(SecurePoint point, const MaskValues& mask, PointEvaluationAccumulator& acc) const = 0;
+    virtual void evaluate_constraint_quotients_on_domain(const Trace<B>& trace, DomainEvaluationAccumulator<B>& acc) const = 0;
+};
+
+template <class B>
+struct ComponentProvers {  // air/components.rs
+    std::vector<const ComponentProver<B>*> components;
+    size_t n_preprocessed_columns;
+
+    u32 composition_log_degree_bound() const {
+        u32 m = 0;
+        for (auto* c : components) m = std::max(m, c->max_constraint_log_degree_bound());
+        return m;
+    }
+    MaskPoints mask_points(SecurePoint point) const {
+        MaskPoints out;
+        for (auto* c : components) {
+            MaskPoints mp = c->mask_points(point);
+            if (out.size() < mp.size()) out.resize(mp.size());
+            for (size_t t = 0; t < mp.size(); t++) out[t].insert(out[t].end(), mp[t].begin(), mp[t].end());
+        }
+        out[PREPROCESSED_TRACE_IDX_()].assign(n_preprocessed_columns, {});
+        for (auto* c : components)
+            for (size_t idx : c->preprocessed_column_indices()) out[PREPROCESSED_TRACE_IDX_()][idx] = {point};
+        return out;
+    }
+    QM31 eval_composition_polynomial_at_point(SecurePoint point, const MaskValues& mask_values, QM31 random_coeff) const {
+        PointEvaluationAccumulator acc(random_coeff);
+        for (auto* c : components) c->evaluate_constraint_quotients_at_point(point, mask_values, acc);
+        return acc.accumulation;
+    }
+    std::array<CirclePoly<B>, 4> compute_composition_polynomial(QM31 random_coeff, const Trace<B>& trace, const typename B::Twiddles& tw) const {
+        size_t total = 0;
+        for (auto* c : components) total += c->n_constraints();
+        DomainEvaluationAccumulator<B> acc(random_coeff, composition_log_degree_bound(), total);
+        for (auto* c : components) c->evaluate_constraint_quotients_on_domain(trace, acc);
+        return acc.finalize(tw);
+    }
+    static size_t PREPROCESSED_TRACE_IDX_() { return 0; }
+};
+
+// prove (core/prover/mod.rs:28-85)
+template <class B>
+StarkProof prove(const std::vector<const ComponentProver<B>*>& components, Blake2sChannel& channel, CommitmentSchemeProver<B>& commitment_scheme) {
+    ComponentProvers<B> provers{components, commitment_scheme.trees[0].polynomials.size()};
+    Trace<B> trace{&commitment_scheme.trees};
+    QM31 random_coeff = channel.draw_secure_felt();
+    std::array<CirclePoly<B>, 4> composition = provers.compute_composition_polynomial(random_coeff, trace, *commitment_scheme.twiddles);
+    std::vector<CirclePoly<B>> comp_polys;
+    for (auto& p : composition) comp_polys.push_back(std::move(p));
+    commitment_scheme.commit_polys(std::move(comp_polys), channel);
+
+    SecurePoint oods_point = get_random_point(channel);
+    MaskPoints sample_points = provers.mask_points(oods_point);
+    // a component set without interaction columns commits fewer trees (TreeVec is sized by use)
+    size_t n_trace_trees = commitment_scheme.trees.size() - 1;
+    while (sample_points.size() > n_trace_trees && sample_points.back().empty()) sample_points.pop_back();
+    sample_points.push_back(std::vector<std::vector<SecurePoint>>(4, std::vector<SecurePoint>{oods_point}));
+
+    StarkProof proof = commitment_scheme.prove_values(sample_points, channel);
+
+    // sanity check (prover/mod.rs:76-82)
+    const auto& comp_mask = proof.sampled_values.back();
+    QM31 composition_oods_eval = qm_from_partial_evals(comp_mask[0][0], comp_mask[1][0], comp_mask[2][0], comp_mask[3][0]);
+    if (composition_oods_eval != provers.eval_composition_polynomial_at_point(oods_point, proof.sampled_values, random_coeff))
+        throw ConstraintsNotSatisfied();
+    return proof;
+}
+
+}  // namespace cm31

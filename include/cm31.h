@@ -135,12 +135,16 @@ int cm31_constraint_eval(const uint32_t* const* cols, size_t n_cols, uint32_t tr
                          uint32_t* const acc4[4]);
 
 /* ------------------------------------------------------------------ witness generation helpers
- * LogupTraceGenerator (S/constraint_framework/src/logup.rs:123-320) driven by the same bytecode:
- * the program writes, for every logup batch k, numerator/denominator QM31 pairs; the kernel
- * forms col_k = col_{k-1} + num_k/den_k on the 2^log_size trace rows. out columns: 4 per batch. */
-int cm31_logup_columns(const uint32_t* const* cols, size_t n_cols, uint32_t log_size, const uint64_t* code,
-                       size_t n_instr, uint32_t n_regs, const uint32_t* consts, size_t n_consts,
-                       uint32_t n_batches, uint32_t* const* out_cols /* 4*n_batches */);
+ * Generic AIR program over the 2^log_size TRACE rows (same bytecode as cm31_constraint_eval):
+ *  - LogupTraceGenerator (S/constraint_framework/src/logup.rs:123-320): the logup program stores,
+ *    for every logup batch k, the cumulative column col_k = col_{k-1} + num_k/den_k
+ *    (OP_STORE_E into out_cols[4k..4k+4]);
+ *  - lookup multiplicities (P/src/preprocessed/range_check/range_check_macro.rs:72-84,
+ *    P/src/components/opcodes/mod.rs:83-105): OP_HIST atomically counts looked-up values into
+ *    out_cols[k] used as a bin array. */
+int cm31_air_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* const* out_cols, size_t n_out,
+                     uint32_t log_size, const uint64_t* code, size_t n_instr, uint32_t n_regs,
+                     const uint32_t* consts, size_t n_consts);
 /* finalize_last (logup.rs:211-251): claimed_sum = sum(last col); last col -= claimed_sum/n;
  * inclusive prefix sum in coset order (simd/prefix_sum.rs:19, index map core/utils.rs:121-143). */
 int cm31_logup_finalize_last(uint32_t* const last4[4], uint32_t log_size, uint32_t claimed_sum_out[4]);

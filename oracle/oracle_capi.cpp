@@ -179,3 +179,60 @@ void orc_channel_draw_random_bytes(uint8_t* st, uint8_t* out) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ whole-proof checkers
+#include "host/test_provers.hpp"
+#include "oracle_air.hpp"
+#include "verifier.hpp"
+
+static int copy_out(const std::vector<uint8_t>& bytes, uint8_t* out, size_t cap, size_t* out_len) {
+    if (out_len) *out_len = bytes.size();
+    if (out && bytes.size() > cap) return -1;
+    if (out) memcpy(out, bytes.data(), bytes.size());
+    return 0;
+}
+static thread_local std::string g_orc_err;
+
+extern "C" {
+
+const char* orc_last_error() { return g_orc_err.c_str(); }
+
+int orc_prove_wide_fibonacci(u32 log_n_rows, u32 n_cols, u32 pow_bits, u32 n_queries, uint8_t* out, size_t cap, size_t* out_len) {
+    try {
+        cm31::PcsConfig cfg;
+        cfg.pow_bits = pow_bits;
+        cfg.fri_config.n_queries = n_queries;
+        cm31::StarkProof proof = cm31::prove_wide_fibonacci<OracleBackend, OracleComponent<cm31::WideFibonacciEval>>(log_n_rows, n_cols, cfg);
+        cm31::ProofWriter w;
+        w.proof(proof);
+        return copy_out(w.bytes, out, cap, out_len);
+    } catch (const std::exception& e) {
+        g_orc_err = e.what();
+        return -2;
+    }
+}
+
+// verify (wide_fibonacci/mod.rs:214-228): 0 = accepted
+int orc_verify_wide_fibonacci(u32 log_n_rows, u32 n_cols, const uint8_t* proof_bytes, size_t len) {
+    try {
+        cm31::ProofReader r(proof_bytes, len);
+        cm31::StarkProof proof = r.proof();
+        cm31::RelationSet relations;
+        OracleComponent<cm31::WideFibonacciEval> component(cm31::WideFibonacciEval{log_n_rows, n_cols}, &relations);
+        cm31::TraceLocationAllocator alloc;
+        component.allocate(alloc);
+        OChannel channel;
+        CommitmentSchemeVerifier cs(proof.config);
+        auto sizes = component.trace_log_degree_bounds();
+        cs.commit(proof.commitments.at(0), sizes[0], channel);
+        cs.commit(proof.commitments.at(1), sizes[1], channel);
+        std::vector<const OComponent*> comps = {&component};
+        verify(comps, channel, cs, proof);
+        return 0;
+    } catch (const std::exception& e) {
+        g_orc_err = e.what();
+        return 1;
+    }
+}
+
+}  // extern "C"

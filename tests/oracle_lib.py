@@ -197,3 +197,8 @@ class Channel:
         out = (C.c_uint8 * 32)()
         lib().orc_channel_draw_random_bytes(self.state, out)
         return bytes(out)
+
+
+def last_error() -> str:
+    lib().orc_last_error.restype = C.c_char_p
+    return (lib().orc_last_error() or b"").decode()
