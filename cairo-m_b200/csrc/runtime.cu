@@ -30,11 +30,10 @@ static int ensure_pool() {
 
 int DeviceTable::upload(const void* host, size_t bytes) {
     release();
-    if (bytes == 0) bytes = 4;
     if (int e = ensure_pool()) return e;
-    CM_CUDA(cudaMallocAsync(&d, bytes, stream()));
+    CM_CUDA(cudaMallocAsync(&d, bytes == 0 ? 4 : bytes, stream()));
     // pageable source: the runtime stages the bytes before returning, so `host` may be reused.
-    CM_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, stream()));
+    if (bytes != 0) CM_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, stream()));
     return 0;
 }
 void DeviceTable::release() {
