@@ -49,7 +49,7 @@ def cuda_sources():
 
 def headers():
     hs = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.hpp")) + list((ROOT / "include").glob("*.h"))
-    hs += list((CSRC / "host").glob("*.hpp")) + list((CSRC / "air").glob("*.hpp"))
+    hs += list((CSRC / "host").glob("*.hpp")) + list((CSRC / "air").glob("*.hpp")) + list((CSRC / "cairo").glob("*.hpp"))
     return hs
 
 

@@ -1,0 +1,501 @@
+// cairo-m AIR components needed by `fibonacci_loop` (Cpu opcodes + Memory + ClockUpdate + RangeCheck),
+// restated from the CODE of the reference, each as
+//   evaluate<E>(E&)     — the FrameworkEval::evaluate body (constraints + relation entries)
+//   write_trace<T>(T&)  — the witness row as expressions over the unpacked ExecutionBundle columns
+// Column order = order of next_trace_mask() calls; constraint order = order of add_constraint
+// calls followed by the logup constraints emitted by finalize_logup_in_pairs.
+//
+//   store_imm      crates/prover/src/components/opcodes/store_imm.rs:114-210 (write_trace), :325-419 (evaluate)
+//   store_fp_imm   .../opcodes/store_fp_imm.rs:147-300, :457-619
+//   store_fp_fp    .../opcodes/store_fp_fp.rs:153-309, :496-681
+//   jnz_fp_imm     .../opcodes/jnz_fp_imm.rs:121-232, :351-446
+//   jmp_imm        .../opcodes/jmp_imm.rs:110-190, :285-345
+//   ret            .../opcodes/ret.rs:117-225, :386-486
+//   memory         crates/prover/src/components/memory.rs:93-195, :294-366
+//   clock_update   crates/prover/src/components/clock_update.rs:70-160, :217-262
+//   range_check_N  crates/prover/src/preprocessed/range_check/range_check_macro.rs:62-112, :171-183
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../field.cuh"
+
+namespace cm31 {
+
+// relation ids, in Relations::draw order (crates/prover/src/components/mod.rs:311-323)
+enum CairoRelation : int { REL_REGISTERS = 0, REL_MEMORY, REL_MERKLE, REL_POSEIDON2, REL_RC8, REL_RC16, REL_RC20, REL_BITWISE, N_CAIRO_RELATIONS };
+// relation sizes (crates/prover/src/relations.rs:7-44)
+inline size_t cairo_relation_size(int r) {
+    static const size_t sizes[N_CAIRO_RELATIONS] = {3, 6, 4, 16, 1, 1, 1, 4};
+    return sizes[r];
+}
+
+// opcode ids (crates/common/src/instruction.rs:317-432)
+constexpr u32 OP_STORE_ADD_FP_FP = 0, OP_STORE_SUB_FP_FP = 1, OP_STORE_MUL_FP_FP = 2, OP_STORE_DIV_FP_FP = 3;
+constexpr u32 OP_STORE_ADD_FP_IMM = 4, OP_STORE_MUL_FP_IMM = 6, OP_STORE_IMM = 9, OP_CALL_ABS_IMM = 10, OP_RET = 11;
+constexpr u32 OP_JMP_ABS_IMM = 12, OP_JMP_REL_IMM = 13, OP_JNZ_FP_IMM = 14;
+
+constexpr u32 TREE_HEIGHT = 30;  // crates/prover/src/adapter/merkle.rs (memory address space 2^30)
+constexpr u32 LOG_SIZE_RC_20 = 20;
+constexpr u32 RC20_LIMIT = (1u << LOG_SIZE_RC_20) - 1;  // crates/prover/src/adapter/memory.rs:16
+
+// unpacked ExecutionBundle columns (crates/prover/src/utils/execution_bundle.rs:12-75,
+// crates/prover/src/utils/data_accesses.rs:10-28)
+constexpr int IN_PC = 0, IN_FP = 1, IN_CLOCK = 2, IN_INST_PREV_CLOCK = 3, IN_INST0 = 4;
+constexpr int IN_ACC_BASE = 10, ACC_ADDRESS = 0, ACC_PREV_CLOCK = 1, ACC_PREV_VALUE = 2, ACC_VALUE = 3;
+constexpr int MAX_ACCESSES = 3;
+constexpr int N_BUNDLE_INPUTS = IN_ACC_BASE + 4 * MAX_ACCESSES;
+inline int in_acc(int k, int field) { return IN_ACC_BASE + 4 * k + field; }
+
+struct OpcodeEvalBase {
+    u32 log_size_;
+    u32 log_size() const { return log_size_; }
+    u32 max_constraint_log_degree_bound() const { return log_size_ + 1; }
+};
+
+// ------------------------------------------------------------------ store_imm
+struct StoreImmEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 9;
+    static constexpr int N_ACCESSES = 1;
+    static const char* name() { return "store_imm"; }
+    static std::vector<u32> opcodes() { return {OP_STORE_IMM}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto zero = eval.f_const(0);
+        auto opcode_constant = eval.f_const(OP_STORE_IMM);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto off0 = eval.next_trace_mask();
+        auto off2 = eval.next_trace_mask();
+        auto dst_prev_clock = eval.next_trace_mask();
+        auto dst_prev_val = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, off0, off2});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, off0, off2});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + off2, dst_prev_clock, dst_prev_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + off2, clock, off0, zero, zero, zero});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        t.out(0, t.enabler());
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, t.in(IN_INST0 + 2));
+        t.out(7, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(8, t.in(in_acc(0, ACC_PREV_VALUE)));
+    }
+};
+
+// ------------------------------------------------------------------ store_fp_imm (StoreAddFpImm / StoreMulFpImm)
+struct StoreFpImmEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 18;
+    static constexpr int N_ACCESSES = 2;
+    static const char* name() { return "store_fp_imm"; }
+    static std::vector<u32> opcodes() { return {OP_STORE_ADD_FP_IMM, OP_STORE_MUL_FP_IMM}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto src_off = eval.next_trace_mask();
+        auto imm = eval.next_trace_mask();
+        auto dst_off = eval.next_trace_mask();
+        auto src_prev_clock = eval.next_trace_mask();
+        auto src_val = eval.next_trace_mask();
+        auto imm_inv = eval.next_trace_mask();
+        auto dst_prev_clock = eval.next_trace_mask();
+        auto dst_prev_val = eval.next_trace_mask();
+        auto dst_val = eval.next_trace_mask();
+        auto opcode_flag_0 = eval.next_trace_mask();
+        auto opcode_flag_1 = eval.next_trace_mask();
+        auto prod = eval.next_trace_mask();
+        auto div = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(opcode_flag_0 * (one - opcode_flag_0));
+        eval.add_constraint(opcode_flag_1 * (one - opcode_flag_1));
+        eval.add_constraint(prod - src_val * imm);
+        eval.add_constraint(imm * (imm_inv * imm - one));
+        eval.add_constraint(imm_inv * (imm_inv * imm - one));
+        eval.add_constraint(div - src_val * imm_inv);
+        auto is_add = eval.add_intermediate((one - opcode_flag_0) * (one - opcode_flag_1));
+        auto is_sub = eval.add_intermediate((one - opcode_flag_0) * opcode_flag_1);
+        auto is_mul = eval.add_intermediate(opcode_flag_0 * (one - opcode_flag_1));
+        auto is_div = eval.add_intermediate(opcode_flag_0 * opcode_flag_1);
+        auto opcode_id = eval.add_intermediate(eval.f_const(OP_STORE_ADD_FP_IMM) + eval.f_const(2) * opcode_flag_0 + opcode_flag_1);
+        auto res = eval.add_intermediate(is_add * (src_val + imm) + is_sub * (src_val - imm) + is_mul * prod + is_div * div);
+        eval.add_constraint(dst_val - res);
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_id, src_off, imm, dst_off});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_id, src_off, imm, dst_off});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src_off, src_prev_clock, src_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src_off, clock, src_val});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_clock, dst_prev_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, dst_val});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - src_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto enabler = t.enabler();
+        // padding rows carry the default bundle (a Ret with zero fields): imm = 0, flags * enabler = 0
+        auto imm = t.in(IN_INST0 + 2);
+        auto imm_inv = t.f_inv(imm);
+        auto src_val = t.in(in_acc(0, ACC_VALUE));
+        // flag = opcode.saturating_sub(STORE_ADD_FP_IMM); flag/2, flag%2, then * enabler
+        auto flag = enabler * (t.in(IN_INST0) - t.f_const(OP_STORE_ADD_FP_IMM));
+        t.out(0, enabler);
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, imm);
+        t.out(7, t.in(IN_INST0 + 3));
+        t.out(8, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(9, src_val);
+        t.out(10, imm_inv);
+        t.out(11, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(12, t.in(in_acc(1, ACC_PREV_VALUE)));
+        t.out(13, t.in(in_acc(1, ACC_VALUE)));
+        t.out(14, t.f_shr(flag, 1));
+        t.out(15, t.f_and(flag, 1));
+        t.out(16, src_val * imm);
+        t.out(17, src_val * imm_inv);
+    }
+};
+
+// ------------------------------------------------------------------ store_fp_fp (Add/Sub/Mul/Div)
+struct StoreFpFpEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 20;
+    static constexpr int N_ACCESSES = 3;
+    static const char* name() { return "store_fp_fp"; }
+    static std::vector<u32> opcodes() { return {OP_STORE_ADD_FP_FP, OP_STORE_SUB_FP_FP, OP_STORE_MUL_FP_FP, OP_STORE_DIV_FP_FP}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto off0 = eval.next_trace_mask();
+        auto off1 = eval.next_trace_mask();
+        auto off2 = eval.next_trace_mask();
+        auto op0_prev_clock = eval.next_trace_mask();
+        auto op0_val = eval.next_trace_mask();
+        auto op1_prev_clock = eval.next_trace_mask();
+        auto op1_val = eval.next_trace_mask();
+        auto op1_inv = eval.next_trace_mask();
+        auto dst_prev_clock = eval.next_trace_mask();
+        auto dst_prev_val = eval.next_trace_mask();
+        auto dst_val = eval.next_trace_mask();
+        auto opcode_flag_0 = eval.next_trace_mask();
+        auto opcode_flag_1 = eval.next_trace_mask();
+        auto prod = eval.next_trace_mask();
+        auto div = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(opcode_flag_0 * (one - opcode_flag_0));
+        eval.add_constraint(opcode_flag_1 * (one - opcode_flag_1));
+        eval.add_constraint(prod - op0_val * op1_val);
+        eval.add_constraint(op1_val * (op1_inv * op1_val - one));
+        eval.add_constraint(op1_inv * (op1_inv * op1_val - one));
+        eval.add_constraint(div - op0_val * op1_inv);
+        auto is_add = eval.add_intermediate((one - opcode_flag_0) * (one - opcode_flag_1));
+        auto is_sub = eval.add_intermediate((one - opcode_flag_0) * opcode_flag_1);
+        auto is_mul = eval.add_intermediate(opcode_flag_0 * (one - opcode_flag_1));
+        auto is_div = eval.add_intermediate(opcode_flag_0 * opcode_flag_1);
+        auto opcode_id = eval.add_intermediate(eval.f_const(OP_STORE_ADD_FP_FP) + eval.f_const(2) * opcode_flag_0 + opcode_flag_1);
+        auto res = eval.add_intermediate(is_add * (op0_val + op1_val) + is_sub * (op0_val - op1_val) + is_mul * prod + is_div * div);
+        eval.add_constraint(dst_val - res);
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_id, off0, off1, off2});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_id, off0, off1, off2});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + off0, op0_prev_clock, op0_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + off0, clock, op0_val});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + off1, op1_prev_clock, op1_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + off1, clock, op1_val});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + off2, dst_prev_clock, dst_prev_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + off2, clock, dst_val});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op1_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto enabler = t.enabler();
+        auto op0_val = t.in(in_acc(0, ACC_VALUE));
+        auto op1_val = t.in(in_acc(1, ACC_VALUE));
+        auto op1_inv = t.f_inv(op1_val);
+        // flag = (opcode == RET) ? 0 : opcode - STORE_ADD_FP_FP; only padding rows hold RET
+        auto flag = enabler * (t.in(IN_INST0) - t.f_const(OP_STORE_ADD_FP_FP));
+        t.out(0, enabler);
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, t.in(IN_INST0 + 2));
+        t.out(7, t.in(IN_INST0 + 3));
+        t.out(8, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(9, op0_val);
+        t.out(10, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(11, op1_val);
+        t.out(12, op1_inv);
+        t.out(13, t.in(in_acc(2, ACC_PREV_CLOCK)));
+        t.out(14, t.in(in_acc(2, ACC_PREV_VALUE)));
+        t.out(15, t.in(in_acc(2, ACC_VALUE)));
+        t.out(16, t.f_shr(flag, 1));
+        t.out(17, t.f_and(flag, 1));
+        t.out(18, op0_val * op1_val);
+        t.out(19, op0_val * op1_inv);
+    }
+};
+
+// ------------------------------------------------------------------ jnz_fp_imm
+struct JnzFpImmEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 12;
+    static constexpr int N_ACCESSES = 1;
+    static const char* name() { return "jnz_fp_imm"; }
+    static std::vector<u32> opcodes() { return {OP_JNZ_FP_IMM}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto opcode_constant = eval.f_const(OP_JNZ_FP_IMM);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto off0 = eval.next_trace_mask();
+        auto imm = eval.next_trace_mask();
+        auto op0_prev_clock = eval.next_trace_mask();
+        auto op0_val = eval.next_trace_mask();
+        auto op0_val_inv = eval.next_trace_mask();
+        auto taken = eval.next_trace_mask();
+        auto pc_new = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(enabler * op0_val * (taken - one));
+        eval.add_constraint(enabler * (taken - op0_val * op0_val_inv));
+        eval.add_constraint(enabler * (pc_new - pc - one - taken * (imm - one)));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc_new, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, off0, imm});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, off0, imm});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + off0, op0_prev_clock, op0_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + off0, clock, op0_val});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto one = t.f_const(1);
+        auto pc = t.in(IN_PC);
+        auto imm = t.in(IN_INST0 + 2);
+        auto op0_val = t.in(in_acc(0, ACC_VALUE));
+        auto op0_val_inv = t.f_inv(op0_val);
+        auto taken = op0_val * op0_val_inv;  // 1 if op0 != 0 else 0
+        t.out(0, t.enabler());
+        t.out(1, pc);
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, imm);
+        t.out(7, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(8, op0_val);
+        t.out(9, op0_val_inv);
+        t.out(10, taken);
+        t.out(11, pc + one + taken * (imm - one));
+    }
+};
+
+// ------------------------------------------------------------------ jmp_imm (JmpAbsImm / JmpRelImm)
+struct JmpImmEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 7;
+    static constexpr int N_ACCESSES = 0;
+    static const char* name() { return "jmp_imm"; }
+    static std::vector<u32> opcodes() { return {OP_JMP_ABS_IMM, OP_JMP_REL_IMM}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto opcode_constant = eval.f_const(OP_JMP_ABS_IMM);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto off0 = eval.next_trace_mask();
+        auto is_rel = eval.next_trace_mask();
+        auto opcode_id = opcode_constant + is_rel;
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(is_rel * (one - is_rel));
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_id, off0});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_id, off0});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {off0 + pc * is_rel, fp, clock + one});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto enabler = t.enabler();
+        t.out(0, enabler);
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, enabler * (t.in(IN_INST0) - t.f_const(OP_JMP_ABS_IMM)));
+    }
+};
+
+// ------------------------------------------------------------------ ret
+struct RetEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 9;
+    static constexpr int N_ACCESSES = 2;
+    static const char* name() { return "ret"; }
+    static std::vector<u32> opcodes() { return {OP_RET}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto two = eval.f_const(2);
+        auto opcode_constant = eval.f_const(OP_RET);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto fp_min_2_prev_clock = eval.next_trace_mask();
+        auto fp_min_2_val = eval.next_trace_mask();
+        auto fp_min_1_prev_clock = eval.next_trace_mask();
+        auto fp_min_1_val = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {fp_min_1_val, fp_min_2_val, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp - two, fp_min_2_prev_clock, fp_min_2_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp - two, clock, fp_min_2_val});
+        // the reference subtracts `enabler` (not the constant 1) here: ret.rs:452-462
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp - enabler, fp_min_1_prev_clock, fp_min_1_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp - enabler, clock, fp_min_1_val});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - fp_min_2_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - fp_min_1_prev_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        // the VM reads [fp-1] first, then [fp-2] (crates/runner/src/vm/instructions/call.rs:69-78)
+        t.out(0, t.enabler());
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(6, t.in(in_acc(1, ACC_VALUE)));
+        t.out(7, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(8, t.in(in_acc(0, ACC_VALUE)));
+    }
+};
+
+// ------------------------------------------------------------------ memory (boundary values)
+// inputs: address, clock, value0..3, multiplicity, root
+struct MemoryEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 9;
+    static const char* name() { return "memory"; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto m31_2 = eval.f_const(2);
+        auto m31_3 = eval.f_const(3);
+        auto m31_4 = eval.f_const(4);
+        auto tree_height = eval.f_const(TREE_HEIGHT);
+        auto enabler = eval.next_trace_mask();
+        auto address = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto value0 = eval.next_trace_mask();
+        auto value1 = eval.next_trace_mask();
+        auto value2 = eval.next_trace_mask();
+        auto value3 = eval.next_trace_mask();
+        auto multiplicity = eval.next_trace_mask();
+        auto root = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_to_relation(REL_MEMORY, eval.ef(multiplicity), {address, clock, value0, value1, value2, value3});
+        eval.add_to_relation(REL_MERKLE, -eval.ef(enabler), {address * m31_4, tree_height, value0, root});
+        eval.add_to_relation(REL_MERKLE, -eval.ef(enabler), {address * m31_4 + one, tree_height, value1, root});
+        eval.add_to_relation(REL_MERKLE, -eval.ef(enabler), {address * m31_4 + m31_2, tree_height, value2, root});
+        eval.add_to_relation(REL_MERKLE, -eval.ef(enabler), {address * m31_4 + m31_3, tree_height, value3, root});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        t.out(0, t.enabler());
+        for (int k = 0; k < 8; k++) t.out(1 + k, t.in(k));
+    }
+};
+
+// ------------------------------------------------------------------ clock_update
+// inputs: addr, prev_clk, value0..3
+struct ClockUpdateEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 7;
+    static const char* name() { return "clock_update"; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto enabler = eval.next_trace_mask();
+        auto address = eval.next_trace_mask();
+        auto prev_clk = eval.next_trace_mask();
+        auto value0 = eval.next_trace_mask();
+        auto value1 = eval.next_trace_mask();
+        auto value2 = eval.next_trace_mask();
+        auto value3 = eval.next_trace_mask();
+        auto one = eval.f_const(1);
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {address, prev_clk, value0, value1, value2, value3});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {address, prev_clk + eval.f_const(RC20_LIMIT), value0, value1, value2, value3});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        t.out(0, t.enabler());
+        for (int k = 0; k < 6; k++) t.out(1 + k, t.in(k));
+    }
+};
+
+// ------------------------------------------------------------------ range_check_N
+struct RangeCheckEval : OpcodeEvalBase {
+    int relation;
+    static constexpr int N_TRACE_COLUMNS = 1;
+    std::string column_id() const { return "range_check_" + std::to_string(log_size_); }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto value = eval.get_preprocessed_column(column_id());
+        auto multiplicity = eval.next_trace_mask();
+        eval.add_to_relation(relation, eval.ef(multiplicity), {value});
+        eval.finalize_logup();
+    }
+};
+
+}  // namespace cm31

@@ -1,0 +1,409 @@
+// prove_cairo_m: the cairo-m protocol driver, generic over the backend implementation `Impl`
+// (CudaAirImpl = product; the test oracle supplies a scalar CPU Impl).
+//
+// Mirrors crates/prover/src/prover.rs:23-147 (prove_cairo_m), components/mod.rs:94-308
+// (Claim::write_trace / InteractionClaim::write_interaction_trace / Relations::draw / Components::new),
+// components/opcodes/mod.rs:41-78,223-268 (opcode dispatch + order), public_data.rs:236-412,
+// preprocessed/mod.rs:43-82, relations.rs:47.  Transcript order = SURVEY.md Appendix A.
+//
+// Scope of this round: the Cpu opcode components exercised by
+// fibonacci_loop, Memory, ClockUpdate and RangeCheck8/16/20.  The Merkle/Poseidon2 memory
+// commitment components (blocked on the un-vendored zkhash constants) and the
+// u32/bitwise opcode families are not part of the statement yet.
+#pragma once
+#include <functional>
+#include <memory>
+
+#include "../air/cairo_components.hpp"
+#include "../host/framework.hpp"
+#include "../host/stark.hpp"
+#include "vm.hpp"
+
+namespace cm31 {
+
+constexpr u32 PREPROCESSED_TRACE_LOG_SIZE = 20;  // prover.rs:21
+constexpr u32 INTERACTION_POW_BITS = 2;          // relations.rs:47
+constexpr u32 LOG_N_LANES = 4;                   // minimum component size (store_fp_fp.rs:161)
+
+struct CairoClaim {
+    std::vector<std::pair<std::string, u32>> log_sizes;  // component name -> log_size, in mix order
+};
+struct CairoInteractionClaim {
+    std::vector<QM31> claimed_sums;  // same order
+};
+struct PublicEntry {
+    u32 addr;
+    u32 value[4];
+    u32 clock;
+};
+struct PublicData {  // public_data.rs:226-266
+    Registers initial_registers, final_registers;
+    u32 clock;
+    u32 initial_root, final_root;
+    std::vector<PublicEntry> program, input, output;
+
+    static PublicData from_input(const ProverInput& in) {
+        PublicData pd;
+        pd.initial_registers = in.initial_registers;
+        pd.final_registers = in.final_registers;
+        pd.clock = (u32)(in.n_steps % P);
+        pd.initial_root = in.initial_root;
+        pd.final_root = in.final_root;
+        auto extract = [](const std::vector<MemoryRow>& mem, u32 lo, u32 hi, std::vector<PublicEntry>& out) {
+            for (const MemoryRow& r : mem)
+                if (r.address >= lo && r.address < hi) {
+                    PublicEntry e;
+                    e.addr = r.address;
+                    for (int k = 0; k < 4; k++) e.value[k] = r.value[k];
+                    e.clock = r.clock;
+                    out.push_back(e);
+                }
+        };
+        extract(in.initial_memory, in.public_ranges.program_start, in.public_ranges.program_end, pd.program);
+        extract(in.initial_memory, in.public_ranges.input_start, in.public_ranges.input_end, pd.input);
+        extract(in.final_memory, in.public_ranges.output_start, in.public_ranges.output_end, pd.output);
+        return pd;
+    }
+    void mix_into(Blake2sChannel& ch, const PublicRanges& r) const {  // public_data.rs:401-412, :83-139
+        u32 head[7] = {initial_registers.pc, initial_registers.fp, final_registers.pc, final_registers.fp, clock, initial_root, final_root};
+        ch.mix_u32s(head, 7);
+        u32 lens[3] = {r.program_end - r.program_start, r.input_end - r.input_start, r.output_end - r.output_start};
+        ch.mix_u32s(lens, 3);
+        for (const std::vector<PublicEntry>* v : {&program, &input, &output}) {
+            std::vector<u32> w;
+            for (const PublicEntry& e : *v) {
+                w.push_back(e.addr);
+                for (int k = 0; k < 4; k++) w.push_back(e.value[k]);
+                w.push_back(e.clock);
+            }
+            ch.mix_u32s(w.data(), w.size());
+        }
+    }
+};
+
+struct CairoProof {  // crates/prover/src/lib.rs:61-73
+    CairoClaim claim;
+    CairoInteractionClaim interaction_claim;
+    PublicData public_data;
+    PublicRanges public_ranges;
+    StarkProof stark_proof;
+    u64 interaction_pow = 0;
+
+    std::vector<uint8_t> to_bytes() const {
+        ProofWriter w;
+        w.u64v(claim.log_sizes.size());
+        for (auto& kv : claim.log_sizes) w.u32v(kv.second);
+        w.u64v(interaction_claim.claimed_sums.size());
+        for (auto& s : interaction_claim.claimed_sums) w.qm(s);
+        const PublicData& pd = public_data;
+        for (u32 v : {pd.initial_registers.pc, pd.initial_registers.fp, pd.final_registers.pc, pd.final_registers.fp, pd.clock, pd.initial_root, pd.final_root}) w.u32v(v);
+        for (u32 v : {public_ranges.program_start, public_ranges.program_end, public_ranges.input_start, public_ranges.input_end,
+                      public_ranges.output_start, public_ranges.output_end})
+            w.u32v(v);
+        for (const std::vector<PublicEntry>* v : {&pd.program, &pd.input, &pd.output}) {
+            w.u64v(v->size());
+            for (const PublicEntry& e : *v) {
+                w.u32v(e.addr);
+                for (int k = 0; k < 4; k++) w.u32v(e.value[k]);
+                w.u32v(e.clock);
+            }
+        }
+        w.u64v(interaction_pow);
+        w.proof(stark_proof);
+        return w.bytes;
+    }
+    static CairoProof from_bytes(const uint8_t* data, size_t len, const std::vector<std::string>& component_names) {
+        ProofReader r(data, len);
+        CairoProof p;
+        u64 n = r.u64v();
+        if (n != component_names.size()) throw std::runtime_error("proof: component count mismatch");
+        for (u64 i = 0; i < n; i++) p.claim.log_sizes.push_back({component_names[i], r.u32v()});
+        u64 m = r.u64v();
+        for (u64 i = 0; i < m; i++) p.interaction_claim.claimed_sums.push_back(r.qm());
+        PublicData& pd = p.public_data;
+        pd.initial_registers.pc = r.u32v();
+        pd.initial_registers.fp = r.u32v();
+        pd.final_registers.pc = r.u32v();
+        pd.final_registers.fp = r.u32v();
+        pd.clock = r.u32v();
+        pd.initial_root = r.u32v();
+        pd.final_root = r.u32v();
+        p.public_ranges.program_start = r.u32v();
+        p.public_ranges.program_end = r.u32v();
+        p.public_ranges.input_start = r.u32v();
+        p.public_ranges.input_end = r.u32v();
+        p.public_ranges.output_start = r.u32v();
+        p.public_ranges.output_end = r.u32v();
+        for (std::vector<PublicEntry>* v : {&pd.program, &pd.input, &pd.output}) {
+            u64 k = r.u64v();
+            for (u64 i = 0; i < k; i++) {
+                PublicEntry e;
+                e.addr = r.u32v();
+                for (int j = 0; j < 4; j++) e.value[j] = r.u32v();
+                e.clock = r.u32v();
+                v->push_back(e);
+            }
+        }
+        p.interaction_pow = r.u64v();
+        ProofReader rest(data + r.pos, len - r.pos);
+        p.stark_proof = rest.proof();
+        return p;
+    }
+};
+
+inline RelationSet draw_cairo_relations(Blake2sChannel& ch) {  // components/mod.rs:311-323
+    RelationSet rs;
+    for (int r = 0; r < N_CAIRO_RELATIONS; r++) rs.relations.push_back(RelationElements::draw(ch, cairo_relation_size(r)));
+    return rs;
+}
+
+inline std::vector<std::string> cairo_preprocessed_ids() { return {"range_check_8", "range_check_16", "range_check_20"}; }
+inline std::vector<std::string> cairo_component_names() {
+    return {"jmp_imm", "jnz_fp_imm", "ret", "store_imm", "store_fp_fp", "store_fp_imm", "memory", "clock_update", "range_check_8", "range_check_16", "range_check_20"};
+}
+
+inline u32 padded_log_size(size_t n_real) {
+    u32 l = LOG_N_LANES;
+    while (((size_t)1 << l) < n_real) l++;
+    return l;
+}
+
+// The full component set; shared by prover and verifier.
+template <class Impl>
+struct CairoComponents {
+    typedef typename Impl::B B;
+    template <class Eval>
+    using Comp = typename Impl::template Component<Eval>;
+    std::unique_ptr<Comp<JmpImmEval>> jmp_imm;
+    std::unique_ptr<Comp<JnzFpImmEval>> jnz_fp_imm;
+    std::unique_ptr<Comp<RetEval>> ret;
+    std::unique_ptr<Comp<StoreImmEval>> store_imm;
+    std::unique_ptr<Comp<StoreFpFpEval>> store_fp_fp;
+    std::unique_ptr<Comp<StoreFpImmEval>> store_fp_imm;
+    std::unique_ptr<Comp<MemoryEval>> memory;
+    std::unique_ptr<Comp<ClockUpdateEval>> clock_update;
+    std::unique_ptr<Comp<RangeCheckEval>> rc8, rc16, rc20;
+
+    // `log_sizes` in cairo_component_names() order
+    CairoComponents(const std::vector<u32>& ls, const RelationSet* rel) {
+        auto base = [](u32 l) {
+            OpcodeEvalBase b;
+            b.log_size_ = l;
+            return b;
+        };
+        jmp_imm.reset(new Comp<JmpImmEval>(JmpImmEval{base(ls[0])}, rel));
+        jnz_fp_imm.reset(new Comp<JnzFpImmEval>(JnzFpImmEval{base(ls[1])}, rel));
+        ret.reset(new Comp<RetEval>(RetEval{base(ls[2])}, rel));
+        store_imm.reset(new Comp<StoreImmEval>(StoreImmEval{base(ls[3])}, rel));
+        store_fp_fp.reset(new Comp<StoreFpFpEval>(StoreFpFpEval{base(ls[4])}, rel));
+        store_fp_imm.reset(new Comp<StoreFpImmEval>(StoreFpImmEval{base(ls[5])}, rel));
+        memory.reset(new Comp<MemoryEval>(MemoryEval{base(ls[6])}, rel));
+        clock_update.reset(new Comp<ClockUpdateEval>(ClockUpdateEval{base(ls[7])}, rel));
+        rc8.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls[8]), REL_RC8}, rel));
+        rc16.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls[9]), REL_RC16}, rel));
+        rc20.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls[10]), REL_RC20}, rel));
+    }
+    template <class Fn>
+    void for_each(Fn fn) {
+        fn(*jmp_imm);
+        fn(*jnz_fp_imm);
+        fn(*ret);
+        fn(*store_imm);
+        fn(*store_fp_fp);
+        fn(*store_fp_imm);
+        fn(*memory);
+        fn(*clock_update);
+        fn(*rc8);
+        fn(*rc16);
+        fn(*rc20);
+    }
+    void allocate(TraceLocationAllocator& alloc) {
+        for_each([&](auto& c) { c.allocate(alloc); });
+    }
+    std::vector<const ComponentProver<B>*> provers() {
+        std::vector<const ComponentProver<B>*> v;
+        for_each([&](auto& c) { v.push_back(&c); });
+        return v;
+    }
+    void set_claimed_sums(const std::vector<QM31>& sums) {
+        size_t i = 0;
+        for_each([&](auto& c) { c.claimed_sum = sums.at(i++); });
+    }
+};
+
+// Per-phase wall-clock (host) milliseconds, filled when non-null (bench.py reports them).
+struct ProveTimings {
+    double preprocessed_ms = 0, trace_ms = 0, interaction_ms = 0, stark_ms = 0, total_ms = 0;
+};
+
+template <class Impl>
+CairoProof prove_cairo_m(const ProverInput& input, PcsConfig pcs_config, ProveTimings* timings = nullptr) {
+    typedef typename Impl::B B;
+    typedef typename B::Col Col;
+    auto t0 = Impl::now_ms();
+    Blake2sChannel channel;
+    pcs_config.mix_into(channel);
+
+    // trace_log_size (prover.rs:38-53; the merkle-tree term is absent with the merkle component)
+    size_t max_rows = 1;
+    for (auto& kv : input.states_by_opcodes) max_rows = std::max(max_rows, kv.second.size());
+    u32 trace_log_size = std::max(PREPROCESSED_TRACE_LOG_SIZE, padded_log_size(max_rows));
+    trace_log_size = std::max(trace_log_size, padded_log_size(input.initial_memory.size() + input.final_memory.size()));
+    typename B::Twiddles twiddles;
+    B::precompute_twiddles(trace_log_size + pcs_config.fri_config.log_blowup_factor + 2, twiddles);
+    CommitmentSchemeProver<B> commitment_scheme(pcs_config, &twiddles);
+
+    CairoProof proof;
+    proof.public_data = PublicData::from_input(input);
+    proof.public_ranges = input.public_ranges;
+    proof.public_data.mix_into(channel, input.public_ranges);
+
+    // ---- tree 0: preprocessed (range_check_8/16/20 value columns)
+    std::vector<u32> rc_bits = {8, 16, 20};
+    {
+        std::vector<CircleEvaluation<B>> pre;
+        for (u32 bits : rc_bits) pre.push_back(CircleEvaluation<B>{Impl::iota((size_t)1 << bits), bits});
+        commitment_scheme.commit_evals(std::move(pre), channel);
+    }
+    auto t1 = Impl::now_ms();
+
+    // ---- tree 1: execution traces
+    typename Impl::AccessLog access_log = Impl::upload_accesses(input.data_accesses);
+    std::vector<u32> log_sizes;
+    std::vector<std::vector<CircleEvaluation<B>>> traces;  // per component (kept until tree 2 is built)
+    auto opcode_trace = [&](auto eval_tag) {
+        typedef decltype(eval_tag) Eval;
+        std::vector<Bundle> rows;
+        for (u32 op : Eval::opcodes()) {
+            auto it = input.states_by_opcodes.find(op);
+            if (it != input.states_by_opcodes.end()) rows.insert(rows.end(), it->second.begin(), it->second.end());
+        }
+        u32 ls = padded_log_size(rows.size());
+        std::vector<Col> inputs = Impl::unpack_bundles(rows, access_log, ls);
+        Eval eval;
+        eval.log_size_ = ls;
+        log_sizes.push_back(ls);
+        traces.push_back(Impl::template write_trace<Eval>(eval, inputs, (u32)rows.size()));
+    };
+    opcode_trace(JmpImmEval{});
+    opcode_trace(JnzFpImmEval{});
+    opcode_trace(RetEval{});
+    opcode_trace(StoreImmEval{});
+    opcode_trace(StoreFpFpEval{});
+    opcode_trace(StoreFpImmEval{});
+    {  // memory (components/memory.rs:93-195): initial rows then final rows
+        std::vector<u32> rows;
+        size_t n_real = input.initial_memory.size() + input.final_memory.size();
+        for (const std::vector<MemoryRow>* v : {&input.initial_memory, &input.final_memory})
+            for (const MemoryRow& r : *v)
+                for (u32 w : {r.address, r.clock, r.value[0], r.value[1], r.value[2], r.value[3], r.multiplicity, r.root}) rows.push_back(w);
+        u32 ls = padded_log_size(n_real);
+        std::vector<Col> inputs = Impl::upload_rows(rows, n_real, 8, ls);
+        MemoryEval eval;
+        eval.log_size_ = ls;
+        log_sizes.push_back(ls);
+        traces.push_back(Impl::template write_trace<MemoryEval>(eval, inputs, (u32)n_real));
+    }
+    {  // clock_update (components/clock_update.rs:70-160)
+        std::vector<u32> rows;
+        for (const ClockUpdateRow& r : input.clock_update_data)
+            for (u32 w : {r.address, r.prev_clk, r.value[0], r.value[1], r.value[2], r.value[3]}) rows.push_back(w);
+        u32 ls = padded_log_size(input.clock_update_data.size());
+        std::vector<Col> inputs = Impl::upload_rows(rows, input.clock_update_data.size(), 6, ls);
+        ClockUpdateEval eval;
+        eval.log_size_ = ls;
+        log_sizes.push_back(ls);
+        traces.push_back(Impl::template write_trace<ClockUpdateEval>(eval, inputs, (u32)input.clock_update_data.size()));
+    }
+    // range-check multiplicities: histogram of every value the opcode components look up
+    // (opcodes/mod.rs:83-105 providers; range_check_macro.rs:72-84).  The AIR graphs drive it.
+    RelationSet dummy_relations;
+    for (int r = 0; r < N_CAIRO_RELATIONS; r++) dummy_relations.relations.push_back(RelationElements::dummy(cairo_relation_size(r)));
+    {
+        std::vector<u32> ls_all = log_sizes;
+        for (u32 bits : rc_bits) ls_all.push_back(bits);
+        CairoComponents<Impl> shape(ls_all, &dummy_relations);
+        int rc_rel[3] = {REL_RC8, REL_RC16, REL_RC20};
+        for (int k = 0; k < 3; k++) {
+            Col bins = B::zeros((size_t)1 << rc_bits[k]);
+            size_t ci = 0;
+            auto emit = [&](auto& comp) {
+                if (ci < 6) {  // opcode components only
+                    std::vector<const Col*> tc;
+                    for (auto& e : traces[ci]) tc.push_back(&e.values);
+                    Impl::emit_lookups(comp, rc_rel[k], tc, bins);
+                }
+                ci++;
+            };
+            shape.for_each(emit);
+            log_sizes.push_back(rc_bits[k]);
+            std::vector<CircleEvaluation<B>> t;
+            t.push_back(CircleEvaluation<B>{std::move(bins), rc_bits[k]});
+            traces.push_back(std::move(t));
+        }
+    }
+    std::vector<std::string> names = cairo_component_names();
+    for (size_t i = 0; i < names.size(); i++) {
+        proof.claim.log_sizes.push_back({names[i], log_sizes[i]});
+        channel.mix_u64(log_sizes[i]);  // Claim::mix_into
+    }
+    // Tree 1 consumes the trace columns (interpolated in place); the interaction trace needs the
+    // trace-domain values, so keep a copy of them for the logup programs.
+    std::vector<std::vector<Col>> trace_copies(traces.size());
+    {
+        std::vector<CircleEvaluation<B>> all;
+        for (size_t c = 0; c < traces.size(); c++)
+            for (auto& e : traces[c]) {
+                trace_copies[c].push_back(Impl::clone(e.values));
+                all.push_back(std::move(e));
+            }
+        commitment_scheme.commit_evals(std::move(all), channel);
+    }
+    auto t2 = Impl::now_ms();
+
+    // ---- interaction: PoW, relations, logup columns (prover.rs:84-102)
+    proof.interaction_pow = B::grind(channel.digest(), INTERACTION_POW_BITS);
+    channel.mix_u64(proof.interaction_pow);
+    RelationSet relations = draw_cairo_relations(channel);
+    CairoComponents<Impl> components(log_sizes, &relations);
+    {
+        std::vector<CircleEvaluation<B>> interaction;
+        std::vector<Col> pre_cols;
+        for (u32 bits : rc_bits) pre_cols.push_back(Impl::iota((size_t)1 << bits));
+        auto pre_lookup = [&](const std::string& id) -> const Col* {
+            std::vector<std::string> ids = cairo_preprocessed_ids();
+            for (size_t i = 0; i < ids.size(); i++)
+                if (ids[i] == id) return &pre_cols[i];
+            throw std::logic_error("unknown preprocessed column " + id);
+        };
+        size_t ci = 0;
+        components.for_each([&](auto& comp) {
+            std::vector<const Col*> tc;
+            for (auto& c : trace_copies[ci]) tc.push_back(&c);
+            auto cols = comp.gen_interaction_trace(tc, pre_lookup);
+            proof.interaction_claim.claimed_sums.push_back(comp.claimed_sum);
+            for (auto& e : cols) interaction.push_back(std::move(e));
+            ci++;
+        });
+        for (auto& s : proof.interaction_claim.claimed_sums) channel.mix_felts({s});  // InteractionClaim::mix_into
+        trace_copies.clear();
+        commitment_scheme.commit_evals(std::move(interaction), channel);
+    }
+    auto t3 = Impl::now_ms();
+
+    // ---- STARK (prover.rs:104-131)
+    TraceLocationAllocator alloc(cairo_preprocessed_ids());
+    components.allocate(alloc);
+    proof.stark_proof = prove<B>(components.provers(), channel, commitment_scheme);
+    auto t4 = Impl::now_ms();
+    if (timings) {
+        timings->preprocessed_ms = t1 - t0;
+        timings->trace_ms = t2 - t1;
+        timings->interaction_ms = t3 - t2;
+        timings->stark_ms = t4 - t3;
+        timings->total_ms = t4 - t0;
+    }
+    return proof;
+}
+
+}  // namespace cm31

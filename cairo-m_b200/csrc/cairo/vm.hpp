@@ -1,0 +1,342 @@
+// Host-side input producer for the proving hot path: a minimal Cairo-M VM for the felt opcode
+// subset used by `fibonacci_loop`, and the adapter that turns its trace + memory log into the
+// prover input (per-opcode ExecutionBundles + the global data-access log + boundary memory).
+//
+// These are the sequential steps immediately BEFORE the hot path; they are
+// restated here only to feed the prover with the reference's input format:
+//   VM step semantics      crates/runner/src/vm/instructions/{store,jnz,jump,call}.rs
+//   memory trace order     crates/runner/src/memory/mod.rs:94-170 (instruction word(s) first, then operands)
+//   ExecutionBundleIterator crates/prover/src/adapter/memory.rs:264-403
+//   Memory::push            crates/prover/src/adapter/memory.rs:470-537 (prev clock/value, clock-update splitting)
+//   update_multiplicities   crates/prover/src/adapter/memory.rs:411-457
+//   import_internal         crates/prover/src/adapter/mod.rs:97-193
+// Differences, by design: boundary-memory rows are emitted in ascending address order (the
+// reference iterates two std HashMaps, i.e. in a per-run random order, components/memory.rs:105-109),
+// and the Poseidon2 memory Merkle roots are placeholders (0) until the merkle/poseidon2 components
+// land.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <stdexcept>
+#include <vector>
+
+#include "../air/cairo_components.hpp"
+
+namespace cm31 {
+
+struct Bundle {  // ExecutionBundle, flattened (12 words)
+    u32 pc, fp, clock, inst_prev_clock;
+    u32 inst[6];
+    u32 span_start, span_len;
+};
+struct DataAccess {  // crates/prover/src/adapter/memory.rs:57-68
+    u32 address, prev_clock, prev_value, value;
+};
+struct MemoryRow {  // one boundary-memory entry: (address, (value, clock, multiplicity))
+    u32 address, clock;
+    u32 value[4];
+    u32 multiplicity, root;
+};
+struct ClockUpdateRow {
+    u32 address, prev_clk;
+    u32 value[4];
+};
+struct PublicRanges {
+    u32 program_start = 0, program_end = 0, input_start = 0, input_end = 0, output_start = 0, output_end = 0;
+};
+struct Registers {
+    u32 pc, fp;
+};
+
+struct ProverInput {
+    Registers initial_registers, final_registers;
+    std::map<u32, std::vector<Bundle>> states_by_opcodes;
+    std::vector<DataAccess> data_accesses;
+    std::vector<MemoryRow> initial_memory, final_memory;  // ascending address
+    std::vector<ClockUpdateRow> clock_update_data;
+    PublicRanges public_ranges;
+    u32 initial_root = 0, final_root = 0;
+    size_t n_steps = 0;
+};
+
+struct Word4 {
+    u32 v[4];
+};
+
+// ------------------------------------------------------------------ program: fibonacci_loop
+// Hand-assembled CASM for test_data/functions/fibonacci_loop.cm (same opcode families as the
+// compiler's while-loop lowering, crates/compiler/codegen/tests/snapshots/
+// mdtest_codegen_snapshots@loops_in_cairo_m___while_loop.snap): 8 VM steps per loop iteration.
+// Like the compiler's output, no instruction reads and writes the same cell (i = i + 1 goes
+// through a temporary): two accesses of one cell in one step would need clock - prev_clock - 1 = -1
+// in the RangeCheck20 relation.
+inline std::vector<Word4> fibonacci_loop_program() {
+    const u32 M3 = P - 3, M4 = P - 4, M8 = P - 8;
+    return {
+        {{OP_STORE_IMM, 0, 0, 0}},             //  0: a = [fp+0] = 0
+        {{OP_STORE_IMM, 1, 1, 0}},             //  1: b = [fp+1] = 1
+        {{OP_STORE_IMM, 0, 2, 0}},             //  2: i = [fp+2] = 0
+        {{OP_STORE_SUB_FP_FP, 2, M4, 3}},      //  3: [fp+3] = i - n        (n = [fp-4])
+        {{OP_JNZ_FP_IMM, 3, 2, 0}},            //  4: if [fp+3] != 0 jmp rel +2
+        {{OP_JMP_REL_IMM, 7, 0, 0}},           //  5: jmp rel +7 (exit)
+        {{OP_STORE_ADD_FP_FP, 0, 1, 4}},       //  6: temp = a + b
+        {{OP_STORE_ADD_FP_IMM, 1, 0, 0}},      //  7: a = b + 0
+        {{OP_STORE_ADD_FP_IMM, 4, 0, 1}},      //  8: b = temp + 0
+        {{OP_STORE_ADD_FP_IMM, 2, 1, 5}},      //  9: [fp+5] = i + 1
+        {{OP_STORE_ADD_FP_IMM, 5, 0, 2}},      // 10: i = [fp+5] + 0
+        {{OP_JMP_REL_IMM, M8, 0, 0}},          // 11: jmp rel -8 (loop head)
+        {{OP_STORE_ADD_FP_IMM, 0, 0, M3}},     // 12: [fp-3] = a + 0   (return value)
+        {{OP_RET, 0, 0, 0}},                   // 13: ret
+    };
+}
+inline size_t fibonacci_loop_steps(u32 n) { return 8 * (size_t)n + 8; }
+
+// ------------------------------------------------------------------ VM
+struct VmTrace {
+    std::vector<Registers> trace;                        // one entry per step + the final state
+    std::vector<std::pair<u32, Word4>> memory_trace;     // (addr, value) in access order
+    std::vector<Word4> initial_memory;                   // dense, address = index
+    PublicRanges public_ranges;
+    u32 return_value = 0;
+};
+
+// Runs `program` with one felt argument: frame = [arg, ret slot, old fp, return pc], fp after it.
+inline VmTrace run_program(const std::vector<Word4>& program, u32 arg, size_t max_steps = (size_t)1 << 30) {
+    VmTrace out;
+    u32 prog_len = (u32)program.size();
+    std::vector<Word4> mem(program);
+    auto cell = [&](u32 addr) -> Word4& {
+        if (addr >= (1u << 30)) throw std::runtime_error("vm: address out of bounds");
+        if (addr >= mem.size()) mem.resize(addr + 1, Word4{{0, 0, 0, 0}});
+        return mem[addr];
+    };
+    u32 fp0 = prog_len + 4;
+    cell(prog_len + 0) = Word4{{arg % P, 0, 0, 0}};
+    cell(prog_len + 1) = Word4{{0, 0, 0, 0}};
+    cell(prog_len + 2) = Word4{{fp0, 0, 0, 0}};       // old fp
+    cell(prog_len + 3) = Word4{{prog_len, 0, 0, 0}};  // return pc = end of program
+    out.initial_memory = mem;
+    out.public_ranges.program_start = 0;
+    out.public_ranges.program_end = prog_len;
+    out.public_ranges.input_start = prog_len;
+    out.public_ranges.input_end = prog_len + 1;
+    out.public_ranges.output_start = prog_len + 1;
+    out.public_ranges.output_end = prog_len + 2;
+    u32 pc = 0, fp = fp0;
+    auto rd = [&](u32 addr) -> u32 {
+        Word4 w = cell(addr);
+        out.memory_trace.push_back({addr, w});
+        return w.v[0];
+    };
+    auto wr = [&](u32 addr, u32 val) {
+        Word4 w{{val, 0, 0, 0}};
+        cell(addr) = w;
+        out.memory_trace.push_back({addr, w});
+    };
+    size_t steps = 0;
+    while (pc != prog_len) {
+        if (steps++ >= max_steps) throw std::runtime_error("vm: step limit reached");
+        out.trace.push_back(Registers{pc, fp});
+        if (pc >= prog_len) throw std::runtime_error("vm: pc outside the program");
+        Word4 ins = mem[pc];
+        out.memory_trace.push_back({pc, ins});
+        u32 op = ins.v[0], a = ins.v[1], b = ins.v[2], c = ins.v[3];
+        switch (op) {
+            case OP_STORE_ADD_FP_FP: case OP_STORE_SUB_FP_FP: case OP_STORE_MUL_FP_FP: case OP_STORE_DIV_FP_FP: {
+                u32 x = rd(m31_add(fp, a)), y = rd(m31_add(fp, b));
+                u32 r = op == OP_STORE_ADD_FP_FP ? m31_add(x, y) : op == OP_STORE_SUB_FP_FP ? m31_sub(x, y)
+                        : op == OP_STORE_MUL_FP_FP ? m31_mul(x, y) : m31_mul(x, m31_inv(y));
+                wr(m31_add(fp, c), r);
+                pc += 1;
+                break;
+            }
+            case OP_STORE_ADD_FP_IMM: case OP_STORE_MUL_FP_IMM: {
+                u32 x = rd(m31_add(fp, a));
+                wr(m31_add(fp, c), op == OP_STORE_ADD_FP_IMM ? m31_add(x, b) : m31_mul(x, b));
+                pc += 1;
+                break;
+            }
+            case OP_STORE_IMM:
+                wr(m31_add(fp, b), a);
+                pc += 1;
+                break;
+            case OP_JNZ_FP_IMM: {
+                u32 cond = rd(m31_add(fp, a));
+                pc = cond != 0 ? m31_add(pc, b) : pc + 1;
+                break;
+            }
+            case OP_JMP_ABS_IMM: pc = a; break;
+            case OP_JMP_REL_IMM: pc = m31_add(pc, a); break;
+            case OP_RET: {
+                u32 new_pc = rd(m31_sub(fp, 1));
+                u32 new_fp = rd(m31_sub(fp, 2));
+                pc = new_pc;
+                fp = new_fp;
+                break;
+            }
+            default: throw std::runtime_error("vm: unsupported opcode");
+        }
+    }
+    out.trace.push_back(Registers{pc, fp});
+    out.return_value = mem[prog_len + 1].v[0];
+    return out;
+}
+
+inline int opcode_memory_accesses(u32 op) {
+    switch (op) {
+        case OP_STORE_ADD_FP_FP: case OP_STORE_SUB_FP_FP: case OP_STORE_MUL_FP_FP: case OP_STORE_DIV_FP_FP: return 3;
+        case OP_STORE_ADD_FP_IMM: case OP_STORE_MUL_FP_IMM: return 2;
+        case OP_STORE_IMM: return 1;
+        case OP_JNZ_FP_IMM: return 1;
+        case OP_JMP_ABS_IMM: case OP_JMP_REL_IMM: return 0;
+        case OP_RET: return 2;
+        default: return -1;
+    }
+}
+inline int opcode_size_in_m31s(u32 op) {
+    switch (op) {
+        case OP_RET: return 1;
+        case OP_JMP_ABS_IMM: case OP_JMP_REL_IMM: return 2;
+        case OP_STORE_IMM: case OP_JNZ_FP_IMM: return 3;
+        default: return 4;
+    }
+}
+
+// ------------------------------------------------------------------ adapter
+class MemoryModel {  // adapter::memory::Memory with dense address-indexed storage
+   public:
+    struct Cell {
+        Word4 value;
+        u32 clock, multiplicity;
+        bool present = false;
+    };
+    std::vector<Cell> initial, final_;
+    std::vector<ClockUpdateRow> clock_update_data;
+
+    explicit MemoryModel(const std::vector<Word4>& initial_memory) {
+        initial.resize(initial_memory.size());
+        for (size_t a = 0; a < initial_memory.size(); a++) {
+            initial[a].value = initial_memory[a];
+            initial[a].clock = 0;
+            initial[a].multiplicity = 0;
+            initial[a].present = true;
+        }
+        final_ = initial;
+    }
+    struct Arg {
+        u32 address, prev_clock, clock;
+        Word4 prev_val, value;
+    };
+    Arg push(u32 address, Word4 value, u32 clock) {
+        if (address >= final_.size()) {
+            final_.resize(address + 1);
+            initial.resize(address + 1);
+        }
+        Cell prev;
+        if (final_[address].present) prev = final_[address];
+        else {
+            prev.value = value;
+            prev.clock = 0;
+            prev.multiplicity = P - 1;
+        }
+        final_[address].value = value;
+        final_[address].clock = clock;
+        final_[address].multiplicity = P - 1;
+        final_[address].present = true;
+        u32 prev_clk = prev.clock;
+        if (prev_clk == 0) {
+            if (initial[address].present) initial[address].multiplicity = 1;
+            else {
+                initial[address].value = value;
+                initial[address].clock = 0;
+                initial[address].multiplicity = 1;
+                initial[address].present = true;
+            }
+        }
+        if (clock > prev_clk) {
+            u32 delta = clock - prev_clk;
+            if (delta > RC20_LIMIT) {
+                u32 num_steps = delta / RC20_LIMIT;
+                for (u32 s = 0; s < num_steps; s++) {
+                    ClockUpdateRow r;
+                    r.address = address;
+                    r.prev_clk = prev_clk;
+                    for (int k = 0; k < 4; k++) r.value[k] = initial[address].value.v[k];
+                    clock_update_data.push_back(r);
+                    prev_clk = m31_add(prev_clk, RC20_LIMIT);
+                }
+            }
+        }
+        return Arg{address, prev_clk, clock, prev.value, value};
+    }
+    void update_multiplicities(const PublicRanges& r) {
+        auto fix_in = [&](u32 a) {
+            if (a < initial.size() && initial[a].present) initial[a].multiplicity = 0;
+            if (a < final_.size() && final_[a].present && final_[a].multiplicity == 0) final_[a].multiplicity = P - 1;
+        };
+        for (u32 a = r.program_start; a < r.program_end; a++) fix_in(a);
+        for (u32 a = r.input_start; a < r.input_end; a++) fix_in(a);
+        for (u32 a = r.output_start; a < r.output_end; a++) {
+            if (a < final_.size() && final_[a].present) final_[a].multiplicity = 0;
+            if (a < initial.size() && initial[a].present) initial[a].multiplicity = 1;
+        }
+    }
+};
+
+inline ProverInput import_from_vm(const VmTrace& vm) {
+    ProverInput in;
+    if (vm.trace.size() < 2) throw std::runtime_error("adapter: empty trace");
+    MemoryModel memory(vm.initial_memory);
+    in.initial_registers = vm.trace.front();
+    in.final_registers = vm.trace.back();
+    size_t mi = 0;
+    u32 clock = 1;  // clock 0 is reserved for preloaded values
+    auto next_mem = [&]() -> const std::pair<u32, Word4>& {
+        if (mi >= vm.memory_trace.size()) throw std::runtime_error("adapter: unexpected end of the memory trace");
+        return vm.memory_trace[mi++];
+    };
+    for (size_t s = 0; s + 1 < vm.trace.size(); s++) {
+        const auto& ie = next_mem();
+        MemoryModel::Arg iarg = memory.push(ie.first, ie.second, clock);
+        u32 opcode = ie.second.v[0];
+        int n_acc = opcode_memory_accesses(opcode);
+        if (n_acc < 0) throw std::runtime_error("adapter: invalid opcode");
+        int size_m31 = opcode_size_in_m31s(opcode);
+        Bundle b;
+        b.pc = vm.trace[s].pc;
+        b.fp = vm.trace[s].fp;
+        b.clock = clock;
+        b.inst_prev_clock = iarg.prev_clock;
+        for (int k = 0; k < 6; k++) b.inst[k] = (k < 4 && k < size_m31) ? ie.second.v[k] : 0;
+        b.span_start = (u32)in.data_accesses.size();
+        for (int k = 0; k < n_acc; k++) {
+            const auto& me = next_mem();
+            MemoryModel::Arg a = memory.push(me.first, me.second, clock);
+            in.data_accesses.push_back(DataAccess{a.address, a.prev_clock, a.prev_val.v[0], a.value.v[0]});
+        }
+        b.span_len = (u32)in.data_accesses.size() - b.span_start;
+        in.states_by_opcodes[opcode].push_back(b);
+        clock += 1;
+    }
+    in.n_steps = vm.trace.size() - 1;
+    memory.update_multiplicities(vm.public_ranges);
+    in.public_ranges = vm.public_ranges;
+    in.clock_update_data = memory.clock_update_data;
+    auto dump = [&](const std::vector<MemoryModel::Cell>& cells, u32 root, std::vector<MemoryRow>& out) {
+        for (size_t a = 0; a < cells.size(); a++) {
+            if (!cells[a].present) continue;
+            MemoryRow r;
+            r.address = (u32)a;
+            r.clock = cells[a].clock;
+            for (int k = 0; k < 4; k++) r.value[k] = cells[a].value.v[k];
+            r.multiplicity = cells[a].multiplicity;
+            r.root = root;
+            out.push_back(r);
+        }
+    };
+    dump(memory.initial, in.initial_root, in.initial_memory);
+    dump(memory.final_, in.final_root, in.final_memory);
+    return in;
+}
+
+}  // namespace cm31

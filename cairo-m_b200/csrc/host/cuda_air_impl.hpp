@@ -1,0 +1,121 @@
+// CudaAirImpl: the product's implementation choices for the cairo-m protocol driver
+// (cairo/prover.hpp): CudaBackend ops + bytecode-driven components + device-side trace fill.
+// Replaces the SimdBackend-concrete pieces listed in SURVEY.md §7 H2: `write_trace`
+// (crates/prover/src/components/opcodes/*.rs), `LogupTraceGenerator`, the multiplicity histograms.
+#pragma once
+#include <chrono>
+
+#include "../../../include/cm31.h"
+#include "../cairo/vm.hpp"
+#include "cuda_backend.hpp"
+#include "framework.hpp"
+
+extern "C" {
+int cm31_unpack_bundles(const uint32_t* bundles_dev, size_t n_real, uint32_t log_size, const uint32_t* accesses_dev,
+                        size_t n_accesses, uint32_t* const* out_cols);
+int cm31_unpack_rows(const uint32_t* rows_dev, size_t n_real, uint32_t n_fields, uint32_t log_size, uint32_t* const* out_cols);
+int cm31_iota(uint32_t* col, size_t n);
+}
+
+namespace cm31 {
+
+// Trace-fill program builder: `write_trace<T>` of a component captured into the AIR bytecode.
+struct TraceProgramBuilder {
+    typedef FExpr F;
+    ExprEvaluator ev;
+    u32 n_real;
+    std::vector<ProgramOutput> outs;
+    explicit TraceProgramBuilder(u32 n) : n_real(n) {}
+    F in(int i) { return ev.input(i); }
+    F enabler() { return ev.row_lt(n_real); }
+    F f_const(u32 v) { return ev.f_const(v); }
+    F f_inv(F a) { return ev.f_inv(a); }
+    F f_shr(F a, u32 k) { return ev.f_shr(a, k); }
+    F f_and(F a, u32 m) { return ev.f_and(a, m); }
+    void out(int col, F v) { outs.push_back(ProgramOutput{ProgramOutput::StoreF, v.id, col}); }
+    AirProgram compile() {
+        return ProgramBuilder::compile(ev.g, outs, 0, [](int interaction, int col) -> size_t {
+            if (interaction != 3) throw std::logic_error("trace program reads a non-input column");
+            return (size_t)col;
+        });
+    }
+};
+
+struct CudaAirImpl {
+    typedef CudaBackend B;
+    typedef DeviceCol Col;
+    template <class Eval>
+    using Component = FrameworkComponent<CudaBackend, Eval>;
+    struct AccessLog {
+        DeviceCol data;  // 4 words per access
+        size_t n = 0;
+    };
+    static double now_ms() {
+        cm_check(cm31_sync());
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
+    static Col iota(size_t n) {
+        Col c(n);
+        cm_check(cm31_iota(c.ptr(), n));
+        return c;
+    }
+    static Col clone(const Col& c) {
+        Col o(c.size());
+        cm_check(cm31_d2d(o.ptr(), c.ptr(), c.size() * 4));
+        return o;
+    }
+    static AccessLog upload_accesses(const std::vector<DataAccess>& acc) {
+        AccessLog l;
+        l.n = acc.size();
+        l.data = DeviceCol(std::max<size_t>(4, acc.size() * 4));
+        if (!acc.empty()) cm_check(cm31_h2d(l.data.ptr(), acc.data(), acc.size() * sizeof(DataAccess)));
+        return l;
+    }
+    static std::vector<Col> unpack_bundles(const std::vector<Bundle>& rows, const AccessLog& log, u32 log_size) {
+        DeviceCol dev(std::max<size_t>(12, rows.size() * 12));
+        if (!rows.empty()) cm_check(cm31_h2d(dev.ptr(), rows.data(), rows.size() * sizeof(Bundle)));
+        std::vector<Col> cols;
+        std::vector<u32*> p;
+        for (int k = 0; k < N_BUNDLE_INPUTS; k++) {
+            cols.emplace_back((size_t)1 << log_size);
+            p.push_back(cols.back().ptr());
+        }
+        cm_check(cm31_unpack_bundles(dev.ptr(), rows.size(), log_size, log.data.ptr(), log.n, p.data()));
+        return cols;
+    }
+    static std::vector<Col> upload_rows(const std::vector<u32>& rows, size_t n_real, u32 n_fields, u32 log_size) {
+        DeviceCol dev(std::max<size_t>(4, rows.size()));
+        if (!rows.empty()) cm_check(cm31_h2d(dev.ptr(), rows.data(), rows.size() * 4));
+        std::vector<Col> cols;
+        std::vector<u32*> p;
+        for (u32 k = 0; k < n_fields; k++) {
+            cols.emplace_back((size_t)1 << log_size);
+            p.push_back(cols.back().ptr());
+        }
+        cm_check(cm31_unpack_rows(dev.ptr(), n_real, n_fields, log_size, p.data()));
+        return cols;
+    }
+    template <class Eval>
+    static std::vector<CircleEvaluation<B>> write_trace(const Eval& eval, const std::vector<Col>& inputs, u32 n_real) {
+        TraceProgramBuilder tb(n_real);
+        eval.write_trace(tb);
+        AirProgram prog = tb.compile();
+        std::vector<CircleEvaluation<B>> out(Eval::N_TRACE_COLUMNS);
+        std::vector<Col*> outp;
+        for (auto& c : out) {
+            c.values = Col((size_t)1 << eval.log_size());
+            c.log_size = eval.log_size();
+            outp.push_back(&c.values);
+        }
+        std::vector<const Col*> in;
+        for (auto& c : inputs) in.push_back(&c);
+        B::air_program(in, outp, eval.log_size(), prog);
+        return out;
+    }
+    template <class Comp>
+    static void emit_lookups(Comp& comp, int relation, const std::vector<const Col*>& trace_cols, Col& bins) {
+        comp.emit_lookups(relation, trace_cols, bins);
+    }
+};
+
+}  // namespace cm31

@@ -34,3 +34,73 @@ int cm31_prove_wide_fibonacci(uint32_t log_n_rows, uint32_t n_cols, uint32_t pow
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ cairo-m
+#include "cairo/prover.hpp"
+#include "host/cuda_air_impl.hpp"
+
+struct cm31_prover_input {
+    cm31::ProverInput input;
+    uint32_t return_value = 0;
+};
+
+extern "C" {
+
+// Runs the (host) VM + adapter for fibonacci_loop(n): the prover input of crates/prover/src/adapter.
+int cm31_fib_input_create(uint32_t n, cm31_prover_input** out) {
+    try {
+        CM_REQUIRE(out != nullptr, "fib_input_create: null out");
+        VmTrace vm = run_program(fibonacci_loop_program(), n);
+        cm31_prover_input* h = new cm31_prover_input();
+        h->input = import_from_vm(vm);
+        h->return_value = vm.return_value;
+        *out = h;
+        return 0;
+    } catch (const std::exception& e) {
+        set_error(e.what());
+        return -2;
+    }
+}
+int cm31_input_destroy(cm31_prover_input* h) {
+    delete h;
+    return 0;
+}
+// info[0] = VM steps, info[1] = data accesses, info[2] = boundary memory rows, info[3] = return value,
+// info[4] = bytes of prover input copied host->device per proof
+int cm31_input_info(const cm31_prover_input* h, uint64_t info[5]) {
+    CM_REQUIRE(h != nullptr, "input_info: null handle");
+    info[0] = h->input.n_steps;
+    info[1] = h->input.data_accesses.size();
+    info[2] = h->input.initial_memory.size() + h->input.final_memory.size();
+    info[3] = h->return_value;
+    info[4] = h->input.n_steps * sizeof(Bundle) + h->input.data_accesses.size() * sizeof(DataAccess) + info[2] * 32 +
+              h->input.clock_update_data.size() * 24;
+    return 0;
+}
+
+// prove_cairo_m::<Blake2sMerkleChannel> (crates/prover/src/prover.rs:23) on the CUDA backend.
+// timings_ms (optional, 5 doubles): preprocessed, trace, interaction, stark, total.
+int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out,
+                       size_t proof_cap, size_t* proof_len, double* timings_ms) {
+    try {
+        CM_REQUIRE(h != nullptr, "prove_cairo_m: null input");
+        PcsConfig cfg = PcsConfig::regular_96_bits();
+        cfg.pow_bits = pow_bits;
+        cfg.fri_config.n_queries = n_queries;
+        ProveTimings t;
+        CairoProof proof = prove_cairo_m<CudaAirImpl>(h->input, cfg, &t);
+        if (timings_ms) {
+            timings_ms[0] = t.preprocessed_ms;
+            timings_ms[1] = t.trace_ms;
+            timings_ms[2] = t.interaction_ms;
+            timings_ms[3] = t.stark_ms;
+            timings_ms[4] = t.total_ms;
+        }
+        return write_out(proof.to_bytes(), proof_out, proof_cap, proof_len);
+    } catch (const std::exception& e) {
+        set_error(e.what());
+        return -2;
+    }
+}
+
+}  // extern "C"

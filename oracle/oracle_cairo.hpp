@@ -1,0 +1,263 @@
+// ORACLE (test infrastructure, not product): scalar CPU implementation choices for the cairo-m
+// protocol driver (cairo-m_b200/csrc/cairo/prover.hpp) + the cairo-m verifier.
+//   Pack::pack / get_access_field   crates/prover/src/utils/execution_bundle.rs:31-75, utils/data_accesses.rs:10-28
+//   write_trace row loops           crates/prover/src/components/opcodes/*.rs (direct evaluation, F = M31)
+//   multiplicity histograms         crates/prover/src/preprocessed/range_check/range_check_macro.rs:72-84
+//   verify_cairo_m                  crates/prover/src/verifier.rs:17-95
+//   initial_logup_sum               crates/prover/src/public_data.rs:287-399
+#pragma once
+#include <chrono>
+
+#include "cairo/prover.hpp"
+#include "oracle_air.hpp"
+#include "verifier.hpp"
+
+namespace orc {
+
+// direct evaluation of a component's write_trace<T> for one row
+struct TraceRowEvaluator {
+    typedef M31 F;
+    const std::vector<OCol>* inputs;
+    std::vector<OCol>* outputs;
+    size_t row;
+    u32 n_real;
+    F in(int i) { return (*inputs)[i][row]; }
+    F enabler() { return M31((u64)(row < n_real ? 1 : 0)); }
+    F f_const(u32 v) { return M31((u64)v); }
+    F f_inv(F a) { return a.v == 0 ? M31() : a.inverse(); }
+    F f_shr(F a, u32 k) { return M31((u64)(a.v >> k)); }
+    F f_and(F a, u32 m) { return M31((u64)(a.v & m)); }
+    void out(int col, F v) { (*outputs)[col][row] = v; }
+};
+
+struct OracleAirImpl {
+    typedef OracleBackend B;
+    typedef OCol Col;
+    template <class Eval>
+    using Component = OracleComponent<Eval>;
+    typedef std::vector<cm31::DataAccess> AccessLog;
+    static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    static Col iota(size_t n) {
+        Col c(n);
+        for (size_t i = 0; i < n; i++) c[i] = M31((u64)i);
+        return c;
+    }
+    static Col clone(const Col& c) { return c; }
+    static AccessLog upload_accesses(const std::vector<cm31::DataAccess>& acc) { return acc; }
+    static std::vector<Col> unpack_bundles(const std::vector<cm31::Bundle>& rows, const AccessLog& log, u32 log_size) {
+        size_t n = (size_t)1 << log_size;
+        std::vector<Col> cols(cm31::N_BUNDLE_INPUTS, Col(n));
+        for (size_t r = 0; r < n; r++) {
+            cm31::Bundle b;
+            if (r < rows.size()) b = rows[r];
+            else {
+                memset(&b, 0, sizeof(b));
+                b.inst[0] = cm31::OP_RET;  // ExecutionBundle::default()
+            }
+            u32 head[10] = {b.pc, b.fp, b.clock, b.inst_prev_clock, b.inst[0], b.inst[1], b.inst[2], b.inst[3], b.inst[4], b.inst[5]};
+            for (int k = 0; k < 10; k++) cols[k][r] = M31((u64)head[k]);
+            for (int k = 0; k < cm31::MAX_ACCESSES; k++) {
+                cm31::DataAccess a{0, 0, 0, 0};
+                if ((u32)k < b.span_len && (size_t)b.span_start + k < log.size()) a = log[b.span_start + k];
+                cols[cm31::in_acc(k, cm31::ACC_ADDRESS)][r] = M31((u64)a.address);
+                cols[cm31::in_acc(k, cm31::ACC_PREV_CLOCK)][r] = M31((u64)a.prev_clock);
+                cols[cm31::in_acc(k, cm31::ACC_PREV_VALUE)][r] = M31((u64)a.prev_value);
+                cols[cm31::in_acc(k, cm31::ACC_VALUE)][r] = M31((u64)a.value);
+            }
+        }
+        return cols;
+    }
+    static std::vector<Col> upload_rows(const std::vector<u32>& rows, size_t n_real, u32 n_fields, u32 log_size) {
+        size_t n = (size_t)1 << log_size;
+        std::vector<Col> cols(n_fields, Col(n));
+        for (size_t r = 0; r < n_real; r++)
+            for (u32 f = 0; f < n_fields; f++) cols[f][r] = M31((u64)rows[r * n_fields + f]);
+        return cols;
+    }
+    template <class Eval>
+    static std::vector<cm31::CircleEvaluation<B>> write_trace(const Eval& eval, const std::vector<Col>& inputs, u32 n_real) {
+        size_t n = (size_t)1 << eval.log_size();
+        std::vector<OCol> outs(Eval::N_TRACE_COLUMNS, OCol(n));
+#pragma omp parallel for schedule(static)
+        for (size_t row = 0; row < n; row++) {
+            TraceRowEvaluator t{&inputs, &outs, row, n_real};
+            eval.write_trace(t);
+        }
+        std::vector<cm31::CircleEvaluation<B>> out;
+        for (auto& c : outs) out.push_back(cm31::CircleEvaluation<B>{std::move(c), eval.log_size()});
+        return out;
+    }
+    template <class Comp>
+    static void emit_lookups(Comp& comp, int relation, const std::vector<const Col*>& trace_cols, Col& bins) {
+        size_t n = (size_t)1 << comp.log_size();
+        std::vector<const OCol*> pre;
+        for (size_t row = 0; row < n; row++) {
+            RowLogupEvaluator re;
+            re.relations = comp.relations;
+            re.cumsum_shift_value = QM31::zero();
+            re.trace_cols = &trace_cols;
+            re.preprocessed_cols = &pre;
+            re.row = row;
+            re.on_use = [&](int rel, M31 v) {
+                if (rel == relation) bins[v.v] = bins[v.v] + M31(1);
+            };
+            comp.eval.evaluate(re);
+        }
+    }
+};
+
+// verify_cairo_m (verifier.rs:17-95) without the closing logup-sum check, which needs the
+// merkle/poseidon2 components (see logup_residual below).
+inline void verify_cairo_m(const cm31::CairoProof& proof, cm31::PcsConfig pcs_config) {
+    OChannel channel;
+    channel.mix_u64(pcs_config.pow_bits);
+    channel.mix_u64(pcs_config.fri_config.log_blowup_factor);
+    channel.mix_u64(pcs_config.fri_config.n_queries);
+    channel.mix_u64(pcs_config.fri_config.log_last_layer_degree_bound);
+    {  // public_data.mix_into
+        const cm31::PublicData& pd = proof.public_data;
+        u32 head[7] = {pd.initial_registers.pc, pd.initial_registers.fp, pd.final_registers.pc, pd.final_registers.fp, pd.clock, pd.initial_root, pd.final_root};
+        channel.mix_u32s(head, 7);
+        const cm31::PublicRanges& r = proof.public_ranges;
+        u32 lens[3] = {r.program_end - r.program_start, r.input_end - r.input_start, r.output_end - r.output_start};
+        channel.mix_u32s(lens, 3);
+        for (const std::vector<cm31::PublicEntry>* v : {&pd.program, &pd.input, &pd.output}) {
+            std::vector<u32> w;
+            for (const cm31::PublicEntry& e : *v) {
+                w.push_back(e.addr);
+                for (int k = 0; k < 4; k++) w.push_back(e.value[k]);
+                w.push_back(e.clock);
+            }
+            channel.mix_u32s(w.data(), w.size());
+        }
+    }
+    if (proof.stark_proof.commitments.size() != 4) throw VerificationError("expected 4 commitments");
+    CommitmentSchemeVerifier cs(pcs_config);
+    cs.commit(proof.stark_proof.commitments[0], {8, 16, 20}, channel);
+    std::vector<u32> log_sizes;
+    for (auto& kv : proof.claim.log_sizes) {
+        log_sizes.push_back(kv.second);
+        channel.mix_u64(kv.second);
+    }
+    // components with dummy relations first: only their shapes are needed to size tree 1
+    cm31::RelationSet dummy;
+    for (int r = 0; r < cm31::N_CAIRO_RELATIONS; r++) dummy.relations.push_back(cm31::RelationElements::dummy(cm31::cairo_relation_size(r)));
+    {
+        cm31::CairoComponents<OracleAirImpl> shape(log_sizes, &dummy);
+        std::vector<u32> sizes;
+        shape.for_each([&](auto& c) {
+            for (size_t k = 0; k < c.n_trace_columns(); k++) sizes.push_back(c.log_size());
+        });
+        cs.commit(proof.stark_proof.commitments[1], sizes, channel);
+    }
+    channel.mix_u64(proof.interaction_pow);
+    if (channel.trailing_zeros() < cm31::INTERACTION_POW_BITS) throw VerificationError("Proof of work verification failed.");
+    cm31::RelationSet relations;  // Relations::draw with the oracle channel
+    for (int r = 0; r < cm31::N_CAIRO_RELATIONS; r++) {
+        cm31::RelationElements re;
+        std::vector<QM31> za = channel.draw_secure_felts(2);
+        re.z = from_orc(za[0]);
+        re.alpha = from_orc(za[1]);
+        QM31 cur = QM31::one();
+        for (size_t i = 0; i < cm31::cairo_relation_size(r); i++) {
+            re.alpha_powers.push_back(from_orc(cur));
+            cur = cur * za[1];
+        }
+        relations.relations.push_back(re);
+    }
+    if (proof.interaction_claim.claimed_sums.size() != log_sizes.size()) throw VerificationError("claimed sum count mismatch");
+    for (auto& s : proof.interaction_claim.claimed_sums) channel.mix_felts({to_orc(s)});
+    cm31::CairoComponents<OracleAirImpl> components(log_sizes, &relations);
+    components.set_claimed_sums(proof.interaction_claim.claimed_sums);
+    {
+        std::vector<u32> sizes;
+        components.for_each([&](auto& c) {
+            for (size_t k = 0; k < c.n_interaction_columns(); k++) sizes.push_back(c.log_size());
+        });
+        cs.commit(proof.stark_proof.commitments[2], sizes, channel);
+    }
+    cm31::TraceLocationAllocator alloc(cm31::cairo_preprocessed_ids());
+    components.allocate(alloc);
+    verify(components.provers(), channel, cs, proof.stark_proof);
+}
+
+// Logup balance (InteractionClaim::claimed_sum, components/mod.rs:288-302 + public_data.rs:287-399):
+//   Σ claimed sums + public-data sum == 0.
+// The Merkle relation is only emitted (memory.rs:332-360) in this round's component set, so the
+// leaf emissions of the private boundary memory are added back explicitly; every other relation
+// (Registers, Memory, RangeCheck20) must balance exactly.
+inline QM31 logup_residual(const cm31::CairoProof& proof, const cm31::ProverInput& input) {
+    // replay the transcript up to Relations::draw
+    OChannel channel;
+    cm31::PcsConfig cfg = proof.stark_proof.config;
+    channel.mix_u64(cfg.pow_bits);
+    channel.mix_u64(cfg.fri_config.log_blowup_factor);
+    channel.mix_u64(cfg.fri_config.n_queries);
+    channel.mix_u64(cfg.fri_config.log_last_layer_degree_bound);
+    const cm31::PublicData& pd = proof.public_data;
+    {
+        u32 head[7] = {pd.initial_registers.pc, pd.initial_registers.fp, pd.final_registers.pc, pd.final_registers.fp, pd.clock, pd.initial_root, pd.final_root};
+        channel.mix_u32s(head, 7);
+        const cm31::PublicRanges& r = proof.public_ranges;
+        u32 lens[3] = {r.program_end - r.program_start, r.input_end - r.input_start, r.output_end - r.output_start};
+        channel.mix_u32s(lens, 3);
+        for (const std::vector<cm31::PublicEntry>* v : {&pd.program, &pd.input, &pd.output}) {
+            std::vector<u32> w;
+            for (const cm31::PublicEntry& e : *v) {
+                w.push_back(e.addr);
+                for (int k = 0; k < 4; k++) w.push_back(e.value[k]);
+                w.push_back(e.clock);
+            }
+            channel.mix_u32s(w.data(), w.size());
+        }
+    }
+    channel.mix_root(to_hash(proof.stark_proof.commitments[0]));
+    for (auto& kv : proof.claim.log_sizes) channel.mix_u64(kv.second);
+    channel.mix_root(to_hash(proof.stark_proof.commitments[1]));
+    channel.mix_u64(proof.interaction_pow);
+    struct Rel {
+        QM31 z;
+        std::vector<QM31> pw;
+        QM31 combine(const std::vector<M31>& v) const {
+            QM31 acc = QM31::zero();
+            for (size_t i = 0; i < v.size(); i++) acc = acc + pw[i] * v[i];
+            return acc - z;
+        }
+    };
+    std::vector<Rel> rel;
+    for (int r = 0; r < cm31::N_CAIRO_RELATIONS; r++) {
+        std::vector<QM31> za = channel.draw_secure_felts(2);
+        Rel x;
+        x.z = za[0];
+        QM31 cur = QM31::one();
+        for (size_t i = 0; i < cm31::cairo_relation_size(r); i++) {
+            x.pw.push_back(cur);
+            cur = cur * za[1];
+        }
+        rel.push_back(x);
+    }
+    auto m = [](u32 v) { return M31((u64)v); };
+    QM31 sum = QM31::zero();
+    for (auto& s : proof.interaction_claim.claimed_sums) sum = sum + to_orc(s);
+    // public data: registers
+    sum = sum + rel[cm31::REL_REGISTERS].combine({m(pd.initial_registers.pc), m(pd.initial_registers.fp), M31(1)}).inverse();
+    sum = sum - rel[cm31::REL_REGISTERS].combine({m(pd.final_registers.pc), m(pd.final_registers.fp), m(pd.clock) + M31(1)}).inverse();
+    // public memory entries (program / input emitted, output consumed)
+    auto add_public = [&](const std::vector<cm31::PublicEntry>& es, bool emit) {
+        for (const cm31::PublicEntry& e : es) {
+            QM31 inv = rel[cm31::REL_MEMORY].combine({m(e.addr), m(e.clock), m(e.value[0]), m(e.value[1]), m(e.value[2]), m(e.value[3])}).inverse();
+            sum = emit ? sum + inv : sum - inv;
+        }
+    };
+    add_public(pd.program, true);
+    add_public(pd.input, true);
+    add_public(pd.output, false);
+    // add back the (unconsumed) Merkle leaf emissions of the memory component
+    for (const std::vector<cm31::MemoryRow>* v : {&input.initial_memory, &input.final_memory})
+        for (const cm31::MemoryRow& r : *v)
+            for (u32 k = 0; k < 4; k++)
+                sum = sum + rel[cm31::REL_MERKLE].combine({m(r.address) * M31(4) + M31((u64)k), M31((u64)cm31::TREE_HEIGHT), m(r.value[k]), m(r.root)}).inverse();
+    return sum;
+}
+
+}  // namespace orc

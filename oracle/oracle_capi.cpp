@@ -236,3 +236,66 @@ int orc_verify_wide_fibonacci(u32 log_n_rows, u32 n_cols, const uint8_t* proof_b
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ cairo-m (fibonacci_loop)
+#include "oracle_cairo.hpp"
+
+extern "C" {
+
+// prove_cairo_m on the scalar CPU oracle. timings_ms: preprocessed, trace, interaction, stark, total.
+int orc_fib_prove(u32 n, u32 pow_bits, u32 n_queries, uint8_t* out, size_t cap, size_t* out_len, double* timings_ms) {
+    try {
+        cm31::ProverInput input = cm31::import_from_vm(cm31::run_program(cm31::fibonacci_loop_program(), n));
+        cm31::PcsConfig cfg = cm31::PcsConfig::regular_96_bits();
+        cfg.pow_bits = pow_bits;
+        cfg.fri_config.n_queries = n_queries;
+        cm31::ProveTimings t;
+        cm31::CairoProof proof = cm31::prove_cairo_m<OracleAirImpl>(input, cfg, &t);
+        if (timings_ms) {
+            timings_ms[0] = t.preprocessed_ms;
+            timings_ms[1] = t.trace_ms;
+            timings_ms[2] = t.interaction_ms;
+            timings_ms[3] = t.stark_ms;
+            timings_ms[4] = t.total_ms;
+        }
+        return copy_out(proof.to_bytes(), out, cap, out_len);
+    } catch (const std::exception& e) {
+        g_orc_err = e.what();
+        return -2;
+    }
+}
+
+int orc_cairo_verify(const uint8_t* proof_bytes, size_t len, u32 pow_bits, u32 n_queries) {
+    try {
+        cm31::CairoProof proof = cm31::CairoProof::from_bytes(proof_bytes, len, cm31::cairo_component_names());
+        cm31::PcsConfig cfg = cm31::PcsConfig::regular_96_bits();
+        cfg.pow_bits = pow_bits;
+        cfg.fri_config.n_queries = n_queries;
+        verify_cairo_m(proof, cfg);
+        return 0;
+    } catch (const std::exception& e) {
+        g_orc_err = e.what();
+        return 1;
+    }
+}
+
+// residual of the logup balance (0,0,0,0 expected); also returns fib(n) and the VM step count
+int orc_fib_logup_residual(u32 n, const uint8_t* proof_bytes, size_t len, u32* residual_out, u64* info_out) {
+    try {
+        cm31::VmTrace vm = cm31::run_program(cm31::fibonacci_loop_program(), n);
+        cm31::ProverInput input = cm31::import_from_vm(vm);
+        cm31::CairoProof proof = cm31::CairoProof::from_bytes(proof_bytes, len, cm31::cairo_component_names());
+        logup_residual(proof, input).to_u32(residual_out);
+        if (info_out) {
+            info_out[0] = vm.return_value;
+            info_out[1] = input.n_steps;
+            info_out[2] = input.clock_update_data.size();
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_orc_err = e.what();
+        return 1;
+    }
+}
+
+}  // extern "C"

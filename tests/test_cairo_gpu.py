@@ -1,0 +1,50 @@
+"""GPU: cairo-m fibonacci_loop proofs from the CUDA path — byte-identical to the oracle prover,
+accepted by the oracle verifier, logup relations balanced.  (BASELINE config[0] and up.)"""
+import pytest
+
+from tests import cairo_helpers as ch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [0, 1, 10, 1000])
+def test_fib_proof_bit_exact(cm, n):
+    inp = ch.GpuFibInput(cm, n)
+    try:
+        assert inp.steps == 8 * n + 8
+        assert inp.return_value == ch.fib_mod_p(n)
+        got, _ = inp.prove()
+    finally:
+        inp.close()
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+    residual, info = ch.oracle_logup_residual(n, got)
+    assert residual == (0, 0, 0, 0)
+    want, _ = ch.oracle_fib_prove(n)
+    assert got == want
+
+
+def test_fib_2_17_steps_verifies(cm):
+    n = (1 << 17) // 8
+    inp = ch.GpuFibInput(cm, n)
+    try:
+        got, tm = inp.prove()
+    finally:
+        inp.close()
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+    residual, info = ch.oracle_logup_residual(n, got)
+    assert residual == (0, 0, 0, 0)
+
+
+def test_fib_2_20_steps_verifies_with_clock_updates(cm):
+    # BASELINE config[1]: 2^20 VM steps; the program words are re-read after > 2^20 clocks only at
+    # the very end (ret path), the loop cells every 8 steps
+    n = (1 << 20) // 8
+    inp = ch.GpuFibInput(cm, n)
+    try:
+        assert inp.steps == (1 << 20) + 8
+        got, tm = inp.prove()
+    finally:
+        inp.close()
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+    residual, info = ch.oracle_logup_residual(n, got)
+    assert residual == (0, 0, 0, 0)
