@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — VM-steps proven/sec for fibonacci_loop on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA prover
+  python bench.py --impl reference --gpus N --steps K ...   # CPU arm (oracle port, all host cores)
+
+A "step" is ONE whole proof (prove_cairo_m: trace fill -> 4 commitments -> constraint/quotient
+evaluation -> OODS -> DEEP quotients -> FRI -> PoW -> decommit) of a fibonacci_loop segment of
+2^log_steps VM steps.  `value` = VM steps proven per second with the prover input already resident
+in HBM; `e2e` = the same through cm31_prove_cairo_m with HOST input buffers (pinned), i.e. the
+per-proof host->device copy of the execution bundles / access log and the proof bytes read back
+are inside the timed region.  N > 1: one process per GPU, each proves its own continuation
+segment (independent proofs, no data-path collective; SURVEY.md §8e "replicas"), weak scaling.
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "VM-steps proven/sec (fibonacci_loop)"
+UNIT = "steps/s"
+
+
+def fib_iterations(log_steps: int) -> int:
+    return (1 << log_steps) // 8  # 8 VM steps per loop iteration + 8 for prologue/epilogue
+
+
+def workload_name(log_steps: int) -> str:
+    return f"fibonacci_loop 2^{log_steps} VM steps, full Cpu+Memory+ClockUpdate+RangeCheck AIR, REGULAR_96_BITS pcs config"
+
+
+# ------------------------------------------------------------------ clocks sampler (nvidia-smi recipe via NVML)
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                if util > 0:
+                    self.samples.append(mhz)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------ CPU arm (oracle port)
+def oracle_prove_timed(log_steps: int):
+    """One proof on the CPU oracle (C++ restatement of stwo's CpuBackend driving the same protocol,
+    OpenMP over the host cores).  Returns (steps, seconds)."""
+    from tests import cairo_helpers as ch
+    n = fib_iterations(log_steps)
+    t = time.perf_counter()
+    ch.oracle_fib_prove(n)
+    return 8 * n + 8, time.perf_counter() - t
+
+
+def cpu_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    sample_log = args.cpu_sample_log
+    for _ in range(min(args.warmup, 1)):  # the CPU path has no warm-up effects beyond page faults: one is enough
+        oracle_prove_timed(sample_log)
+    total_steps, total_s = 0, 0.0
+    for _ in range(args.steps):
+        s, dt = oracle_prove_timed(sample_log)
+        total_steps += s
+        total_s += dt
+    value = total_steps / total_s
+    cores = cpu_cores()
+    sample = (f"fibonacci_loop 2^{sample_log} VM steps per proof (bounded sample of the 2^{args.log_steps} workload; the "
+              f"2^20-row range-check tables are a fixed floor, so CPU steps/s grows with segment length)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 (M31/QM31 modular integer)", "data": "synthetic",
+        "config": {"workload": workload_name(args.log_steps), "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the Rust reference cannot be built in this image (no cargo/rustc, crates not vendored): this arm times "
+                "oracle/ (C++ restatement of stwo CpuBackend + the same protocol driver), OpenMP on all host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ CUDA arm
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cm = importlib.import_module("cairo-m_b200")
+    lib = cm.lib()
+    cm.check(lib.cm31_set_device(local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = fib_iterations(args.log_steps)
+    h = C.c_void_p()
+    cm.check(lib.cm31_fib_input_create(C.c_uint32(n), C.byref(h)))
+    info = (C.c_uint64 * 5)()
+    cm.check(lib.cm31_input_info(h, info))
+    vm_steps, h2d_bytes = int(info[0]), int(info[4])
+    cap = 1 << 26
+    proof_buf = (C.c_uint8 * cap)()
+    proof_len = C.c_size_t()
+    tm = (C.c_double * 5)()
+
+    def prove():
+        cm.check(lib.cm31_prove_cairo_m(h, 16, 80, proof_buf, C.c_size_t(cap), C.byref(proof_len), tm))
+
+    def timed_region(k_steps, with_profile):
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        cm.check(lib.cm31_profile_reset())
+        cm.check(lib.cm31_profile_enable(1 if with_profile else 0))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        phases = [0.0] * 5
+        e0.record()
+        for _ in range(k_steps):
+            prove()
+            for i in range(5):
+                phases[i] += tm[i]
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        launches = C.c_uint64()
+        cm.check(lib.cm31_profile_launches(C.byref(launches)))
+        report = None
+        if with_profile:
+            ln = C.c_size_t()
+            rb = C.create_string_buffer(1 << 16)
+            cm.check(lib.cm31_profile_report(rb, C.c_size_t(1 << 16), C.byref(ln)))
+            report = json.loads(rb.value.decode())
+        cm.check(lib.cm31_profile_enable(0))
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks, int(launches.value), report, [p / k_steps for p in phases]
+
+    # ---- device-resident: input staged in HBM once
+    cm.check(lib.cm31_input_upload(h))
+    for _ in range(args.warmup):
+        prove()
+    ms, clocks, launches, report, phases = timed_region(args.steps, True)
+    value = world * vm_steps * args.steps / (ms / 1e3)
+
+    # ---- end to end: host (pinned) input copied in, proof bytes copied out, every step
+    cm.check(lib.cm31_input_release_device(h))
+    prove()
+    e2e_ms, _, _, _, _ = timed_region(args.steps, False)
+    e2e_value = world * vm_steps * args.steps / (e2e_ms / 1e3)
+    proof_bytes = int(proof_len.value)
+    cm.check(lib.cm31_input_destroy(h))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    report.sort(key=lambda r: -r["ms"])
+    kern_total = sum(r["ms"] for r in report)
+    top = report[0]
+    avg_ms = top["ms"] / top["launches"]
+    achieved = (top["alg_bytes"] / top["launches"]) / (avg_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = ROOT / "profiles" / "traffic.json"
+    if tpath.exists():
+        traffic = json.loads(tpath.read_text()).get(top["kernel"])
+    roofline = {
+        "bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches_per_step": top["launches"] / args.steps,
+        "share_of_kernel_time": top["ms"] / kern_total if kern_total else None,
+        "kernel_time_share_of_step": kern_total / ms,
+        "kernels": [{"kernel": r["kernel"], "ms_per_step": r["ms"] / args.steps, "launches_per_step": r["launches"] / args.steps,
+                     "alg_GBps": (r["alg_bytes"] / (r["ms"] * 1e-3) / 1e9) if r["ms"] > 0 else None} for r in report],
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        s, dt = oracle_prove_timed(args.cpu_sample_log)
+        cpu_baseline = {
+            "value": s / dt, "unit": UNIT, "cores": cpu_cores(), "kind": "port",
+            "sample": f"one proof of fibonacci_loop 2^{args.cpu_sample_log} VM steps on oracle/ (C++ port of stwo CpuBackend + same "
+                      f"protocol, OpenMP); {dt:.1f} s",
+        }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 (M31/QM31 modular integer)", "data": "synthetic",
+        "config": {"workload": workload_name(args.log_steps), "vm_steps_per_proof": vm_steps,
+                   "parallelism": "one independent segment proof per GPU" if world > 1 else "single GPU",
+                   "l2": "working set per proof (GBs of trace/LDE columns) >> 126 MB L2; no flush between steps",
+                   "pcs": {"pow_bits": 16, "log_blowup": 1, "n_queries": 80}},
+        "phases_ms": dict(zip(["preprocessed", "trace", "interaction", "stark", "total"], phases)),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": proof_bytes,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-steps", type=int, default=22, help="log2 of VM steps per proof (BASELINE metric: 2^22)")
+    ap.add_argument("--cpu-sample-log", type=int, default=17, help="log2 VM steps of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if world == 1 and args.gpus > 1:
+            print(f"bench.py: --gpus {args.gpus} needs torchrun (one process per GPU); running 1 GPU", file=sys.stderr)
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

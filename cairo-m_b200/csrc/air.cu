@@ -131,6 +131,7 @@ static int run_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* co
     unsigned threads = 128, blocks = (unsigned)((n + threads - 1) / threads);
     u32 *a0 = acc4 ? acc4[0] : nullptr, *a1 = acc4 ? acc4[1] : nullptr, *a2 = acc4 ? acc4[2] : nullptr,
         *a3 = acc4 ? acc4[3] : nullptr;
+    ProfScope prof(acc4 ? "constraint_eval" : "air_program", acc4 ? 4ull * n * n_in + 32ull * n : 4ull * n * (n_in + n_out));
 #define CM_AIR_LAUNCH(NR)                                                                                              \
     air_program_kernel<NR><<<blocks, threads, 0, stream()>>>((const u32* const*)din.d, (u32* const*)dout.d, row_log,   \
                                                              trace_log, (const uint64_t*)dcode.d, (u32)n_instr,        \
@@ -286,7 +287,10 @@ int cm31_logup_finalize_last(uint32_t* const last4[4], uint32_t log_size, uint32
     CM_CUDA(cudaMallocAsync(&dsums, 32, stream()));
     CM_CUDA(cudaMemsetAsync(dsums, 0, 32, stream()));
     unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 1024);
-    sum4_kernel<<<blocks, 256, 0, stream()>>>(last4[0], last4[1], last4[2], last4[3], n, dsums);
+    {
+        ProfScope prof("logup_sum4", 16ull * n);
+        sum4_kernel<<<blocks, 256, 0, stream()>>>(last4[0], last4[1], last4[2], last4[3], n, dsums);
+    }
     CM_LAUNCH_CHECK();
     unsigned long long h[4];
     CM_CUDA(cudaMemcpyAsync(h, dsums, 32, cudaMemcpyDeviceToHost, stream()));
@@ -303,6 +307,7 @@ int cm31_logup_finalize_last(uint32_t* const last4[4], uint32_t log_size, uint32
     u32* dchunks = nullptr;
     CM_CUDA(cudaMallocAsync(&dchunks, (size_t)n_chunks * 4, stream()));
     for (int k = 0; k < 4; k++) {
+        ProfScope prof("logup_prefix_sum", 8ull * n, 3);
         scan_chunk_sums_kernel<<<n_chunks, 256, 0, stream()>>>(last4[k], log_size, sh[k], dchunks);
         scan_chunk_offsets_kernel<<<1, 1024, 0, stream()>>>(dchunks, n_chunks);
         scan_apply_kernel<<<n_chunks, 256, 0, stream()>>>(last4[k], log_size, sh[k], dchunks);
@@ -314,6 +319,7 @@ int cm31_logup_finalize_last(uint32_t* const last4[4], uint32_t log_size, uint32
 
 int cm31_histogram(const uint32_t* values, size_t n, uint32_t* bins, uint32_t log_bins) {
     if (n == 0) return 0;
+    ProfScope prof("histogram", 4ull * n);
     histogram_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(values, n, bins, 1u << log_bins);
     CM_LAUNCH_CHECK();
     return 0;

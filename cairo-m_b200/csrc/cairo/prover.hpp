@@ -236,8 +236,75 @@ struct ProveTimings {
     double preprocessed_ms = 0, trace_ms = 0, interaction_ms = 0, stark_ms = 0, total_ms = 0;
 };
 
+// Prover input resident in backend memory (device buffers for the CUDA path): the AoS records of
+// ProverInput flattened to u32 words, per component, in component order.  stage_input is the
+// host->device copy of a proof's inputs; prove_cairo_m itself never touches the host vectors.
 template <class Impl>
-CairoProof prove_cairo_m(const ProverInput& input, PcsConfig pcs_config, ProveTimings* timings = nullptr) {
+struct StagedInput {
+    struct Rows {
+        typename Impl::Words words;
+        size_t n_real = 0;
+    };
+    typename Impl::Words accesses;
+    size_t n_accesses = 0;
+    std::vector<Rows> opcode;  // jmp_imm, jnz_fp_imm, ret, store_imm, store_fp_fp, store_fp_imm
+    Rows memory, clock_update;
+    size_t bytes = 0;  // total bytes staged
+};
+
+template <class Impl>
+StagedInput<Impl> stage_input(const ProverInput& input) {
+    StagedInput<Impl> st;
+    st.n_accesses = input.data_accesses.size();
+    st.accesses = Impl::upload_words((const u32*)input.data_accesses.data(), st.n_accesses * 4);
+    st.bytes += st.n_accesses * 16;
+    auto opcode_rows = [&](const std::vector<u32>& opcodes) {
+        typename StagedInput<Impl>::Rows r;
+        std::vector<const std::vector<Bundle>*> parts;
+        for (u32 op : opcodes) {
+            auto it = input.states_by_opcodes.find(op);
+            if (it != input.states_by_opcodes.end() && !it->second.empty()) parts.push_back(&it->second);
+        }
+        if (parts.size() == 1) {  // common case: upload straight from the adapter's vector
+            r.n_real = parts[0]->size();
+            r.words = Impl::upload_words((const u32*)parts[0]->data(), r.n_real * 12);
+        } else {
+            std::vector<Bundle> rows;
+            for (auto* v : parts) rows.insert(rows.end(), v->begin(), v->end());
+            r.n_real = rows.size();
+            r.words = Impl::upload_words((const u32*)rows.data(), r.n_real * 12);
+        }
+        st.bytes += r.n_real * sizeof(Bundle);
+        st.opcode.push_back(std::move(r));
+    };
+    opcode_rows(JmpImmEval::opcodes());
+    opcode_rows(JnzFpImmEval::opcodes());
+    opcode_rows(RetEval::opcodes());
+    opcode_rows(StoreImmEval::opcodes());
+    opcode_rows(StoreFpFpEval::opcodes());
+    opcode_rows(StoreFpImmEval::opcodes());
+    {  // memory (components/memory.rs:93-195): initial rows then final rows
+        std::vector<u32> rows;
+        for (const std::vector<MemoryRow>* v : {&input.initial_memory, &input.final_memory})
+            for (const MemoryRow& r : *v)
+                for (u32 w : {r.address, r.clock, r.value[0], r.value[1], r.value[2], r.value[3], r.multiplicity, r.root}) rows.push_back(w);
+        st.memory.n_real = input.initial_memory.size() + input.final_memory.size();
+        st.memory.words = Impl::upload_words(rows.data(), rows.size());
+        st.bytes += rows.size() * 4;
+    }
+    {  // clock_update (components/clock_update.rs:70-160)
+        std::vector<u32> rows;
+        for (const ClockUpdateRow& r : input.clock_update_data)
+            for (u32 w : {r.address, r.prev_clk, r.value[0], r.value[1], r.value[2], r.value[3]}) rows.push_back(w);
+        st.clock_update.n_real = input.clock_update_data.size();
+        st.clock_update.words = Impl::upload_words(rows.data(), rows.size());
+        st.bytes += rows.size() * 4;
+    }
+    return st;
+}
+
+template <class Impl>
+CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& staged, PcsConfig pcs_config, ProveTimings* timings = nullptr) {
     typedef typename Impl::B B;
     typedef typename B::Col Col;
     auto t0 = Impl::now_ms();
@@ -246,9 +313,9 @@ CairoProof prove_cairo_m(const ProverInput& input, PcsConfig pcs_config, ProveTi
 
     // trace_log_size (prover.rs:38-53; the merkle-tree term is absent with the merkle component)
     size_t max_rows = 1;
-    for (auto& kv : input.states_by_opcodes) max_rows = std::max(max_rows, kv.second.size());
+    for (auto& r : staged.opcode) max_rows = std::max(max_rows, r.n_real);
     u32 trace_log_size = std::max(PREPROCESSED_TRACE_LOG_SIZE, padded_log_size(max_rows));
-    trace_log_size = std::max(trace_log_size, padded_log_size(input.initial_memory.size() + input.final_memory.size()));
+    trace_log_size = std::max(trace_log_size, padded_log_size(staged.memory.n_real));
     typename B::Twiddles twiddles;
     B::precompute_twiddles(trace_log_size + pcs_config.fri_config.log_blowup_factor + 2, twiddles);
     CommitmentSchemeProver<B> commitment_scheme(pcs_config, &twiddles);
@@ -268,22 +335,18 @@ CairoProof prove_cairo_m(const ProverInput& input, PcsConfig pcs_config, ProveTi
     auto t1 = Impl::now_ms();
 
     // ---- tree 1: execution traces
-    typename Impl::AccessLog access_log = Impl::upload_accesses(input.data_accesses);
     std::vector<u32> log_sizes;
     std::vector<std::vector<CircleEvaluation<B>>> traces;  // per component (kept until tree 2 is built)
+    size_t opcode_index = 0;
     auto opcode_trace = [&](auto eval_tag) {
         typedef decltype(eval_tag) Eval;
-        std::vector<Bundle> rows;
-        for (u32 op : Eval::opcodes()) {
-            auto it = input.states_by_opcodes.find(op);
-            if (it != input.states_by_opcodes.end()) rows.insert(rows.end(), it->second.begin(), it->second.end());
-        }
-        u32 ls = padded_log_size(rows.size());
-        std::vector<Col> inputs = Impl::unpack_bundles(rows, access_log, ls);
+        const auto& rows = staged.opcode.at(opcode_index++);
+        u32 ls = padded_log_size(rows.n_real);
+        std::vector<Col> inputs = Impl::unpack_bundles(rows.words, rows.n_real, staged.accesses, staged.n_accesses, ls);
         Eval eval;
         eval.log_size_ = ls;
         log_sizes.push_back(ls);
-        traces.push_back(Impl::template write_trace<Eval>(eval, inputs, (u32)rows.size()));
+        traces.push_back(Impl::template write_trace<Eval>(eval, inputs, (u32)rows.n_real));
     };
     opcode_trace(JmpImmEval{});
     opcode_trace(JnzFpImmEval{});
@@ -291,29 +354,21 @@ CairoProof prove_cairo_m(const ProverInput& input, PcsConfig pcs_config, ProveTi
     opcode_trace(StoreImmEval{});
     opcode_trace(StoreFpFpEval{});
     opcode_trace(StoreFpImmEval{});
-    {  // memory (components/memory.rs:93-195): initial rows then final rows
-        std::vector<u32> rows;
-        size_t n_real = input.initial_memory.size() + input.final_memory.size();
-        for (const std::vector<MemoryRow>* v : {&input.initial_memory, &input.final_memory})
-            for (const MemoryRow& r : *v)
-                for (u32 w : {r.address, r.clock, r.value[0], r.value[1], r.value[2], r.value[3], r.multiplicity, r.root}) rows.push_back(w);
-        u32 ls = padded_log_size(n_real);
-        std::vector<Col> inputs = Impl::upload_rows(rows, n_real, 8, ls);
+    {
+        u32 ls = padded_log_size(staged.memory.n_real);
+        std::vector<Col> inputs = Impl::unpack_rows(staged.memory.words, staged.memory.n_real, 8, ls);
         MemoryEval eval;
         eval.log_size_ = ls;
         log_sizes.push_back(ls);
-        traces.push_back(Impl::template write_trace<MemoryEval>(eval, inputs, (u32)n_real));
+        traces.push_back(Impl::template write_trace<MemoryEval>(eval, inputs, (u32)staged.memory.n_real));
     }
-    {  // clock_update (components/clock_update.rs:70-160)
-        std::vector<u32> rows;
-        for (const ClockUpdateRow& r : input.clock_update_data)
-            for (u32 w : {r.address, r.prev_clk, r.value[0], r.value[1], r.value[2], r.value[3]}) rows.push_back(w);
-        u32 ls = padded_log_size(input.clock_update_data.size());
-        std::vector<Col> inputs = Impl::upload_rows(rows, input.clock_update_data.size(), 6, ls);
+    {
+        u32 ls = padded_log_size(staged.clock_update.n_real);
+        std::vector<Col> inputs = Impl::unpack_rows(staged.clock_update.words, staged.clock_update.n_real, 6, ls);
         ClockUpdateEval eval;
         eval.log_size_ = ls;
         log_sizes.push_back(ls);
-        traces.push_back(Impl::template write_trace<ClockUpdateEval>(eval, inputs, (u32)input.clock_update_data.size()));
+        traces.push_back(Impl::template write_trace<ClockUpdateEval>(eval, inputs, (u32)staged.clock_update.n_real));
     }
     // range-check multiplicities: histogram of every value the opcode components look up
     // (opcodes/mod.rs:83-105 providers; range_check_macro.rs:72-84).  The AIR graphs drive it.
@@ -404,6 +459,13 @@ CairoProof prove_cairo_m(const ProverInput& input, PcsConfig pcs_config, ProveTi
         timings->total_ms = t4 - t0;
     }
     return proof;
+}
+
+// Host-input form (the reference's `prove_cairo_m(&mut ProverInput, ..)`): stages, then proves.
+template <class Impl>
+CairoProof prove_cairo_m(const ProverInput& input, PcsConfig pcs_config, ProveTimings* timings = nullptr) {
+    StagedInput<Impl> staged = stage_input<Impl>(input);
+    return prove_cairo_m<Impl>(input, staged, pcs_config, timings);
 }
 
 }  // namespace cm31

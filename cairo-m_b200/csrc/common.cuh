@@ -33,6 +33,16 @@ cudaStream_t stream();
 
 #define CM_LAUNCH_CHECK() CM_CUDA(cudaGetLastError())
 
+// Per-kernel device timing (cm31_profile_*): when enabled, a ProfScope brackets one launch with
+// two CUDA events on the launch stream and books `alg_bytes` ALGORITHMIC bytes
+// to the kernel's name.  Disabled (default) it costs one branch.
+void prof_begin(const char* name, uint64_t alg_bytes, unsigned n_kernels);
+void prof_end();
+struct ProfScope {
+    ProfScope(const char* name, uint64_t alg_bytes, unsigned n_kernels = 1) { prof_begin(name, alg_bytes, n_kernels); }
+    ~ProfScope() { prof_end(); }
+};
+
 // Uploads a small host table (pointer arrays, programs, constants) into a per-call device
 // allocation from a stream-ordered pool. Freed with release() (stream ordered).
 struct DeviceTable {

@@ -175,6 +175,7 @@ int cm31_fold_line(const uint32_t* const src4[4], uint32_t log_size, const uint3
     }
     size_t n_out = (size_t)1 << (log_size - 1);
     const u32* itw = tree_level_for_line_coset(tw, true, log_size);
+    ProfScope prof("fold_line", 24ull * (n_out * 2));
     fold_line_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, stream()>>>(s, d, n_out, qm_from_arr(alpha), itw);
     CM_LAUNCH_CHECK();
     return 0;
@@ -192,6 +193,7 @@ int cm31_fold_circle_into_line(uint32_t* const dst4[4], const uint32_t* const sr
     size_t n_out = (size_t)1 << (log_size - 1);
     QM31 a = qm_from_arr(alpha);
     QM31 a2 = qm_sqr(a);
+    ProfScope prof("fold_circle_into_line", 32ull * (n_out * 2));
     if (log_size <= 2) {
         CircleDomain dom = CanonicCoset(log_size).circle_domain();
         u32 iy0 = m31_inv(dom.at(bit_reverse(0, log_size)).y);
@@ -214,6 +216,7 @@ int cm31_accumulate(uint32_t* const dst4[4], const uint32_t* const src4[4], size
         d.p[k] = dst4[k];
     }
     if (n == 0) return 0;
+    ProfScope prof("accumulate", 48ull * n);
     accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(d, s, n);
     CM_LAUNCH_CHECK();
     return 0;
@@ -244,7 +247,10 @@ int cm31_decompose(const uint32_t* const src4[4], uint32_t log_size, uint32_t* c
     unsigned long long* dsums = nullptr;
     CM_CUDA(cudaMallocAsync(&dsums, 64, stream()));
     CM_CUDA(cudaMemsetAsync(dsums, 0, 64, stream()));
-    decompose_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(s, n, dsums);
+    {
+        ProfScope prof("decompose_sum", 16ull * n);
+        decompose_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(s, n, dsums);
+    }
     CM_LAUNCH_CHECK();
     unsigned long long h[8];
     CM_CUDA(cudaMemcpyAsync(h, dsums, 64, cudaMemcpyDeviceToHost, stream()));
@@ -261,6 +267,7 @@ int cm31_decompose(const uint32_t* const src4[4], uint32_t log_size, uint32_t* c
     lambda_out[1] = lam.b;
     lambda_out[2] = lam.c;
     lambda_out[3] = lam.d;
+    ProfScope prof("decompose_apply", 32ull * n);
     decompose_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(s, d, n, lam);
     CM_LAUNCH_CHECK();
     return 0;
@@ -319,6 +326,7 @@ int cm31_accumulate_quotients(uint32_t log_size, const uint32_t* const* cols, si
     for (int k = 0; k < 4; k++) o.p[k] = out4[k];
     Coset half = CanonicCoset(log_size).half_coset();
     size_t n = (size_t)1 << log_size;
+    ProfScope prof("accumulate_quotients", (4ull * n_cols + 16ull) * n);
     quotients_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(
         log_size, (const u32* const*)dcols.d, (const QuotBatch*)dqb.d, (u32)n_batches, (const u32*)didx.d,
         (const u32*)dc.d, half.initial_index, half.step_size, (const CirclePointM31*)dgen.d, o);

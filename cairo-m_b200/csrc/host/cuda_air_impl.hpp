@@ -46,10 +46,7 @@ struct CudaAirImpl {
     typedef DeviceCol Col;
     template <class Eval>
     using Component = FrameworkComponent<CudaBackend, Eval>;
-    struct AccessLog {
-        DeviceCol data;  // 4 words per access
-        size_t n = 0;
-    };
+    typedef DeviceCol Words;  // staged prover-input records (u32 words) in HBM
     static double now_ms() {
         cm_check(cm31_sync());
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -64,35 +61,29 @@ struct CudaAirImpl {
         cm_check(cm31_d2d(o.ptr(), c.ptr(), c.size() * 4));
         return o;
     }
-    static AccessLog upload_accesses(const std::vector<DataAccess>& acc) {
-        AccessLog l;
-        l.n = acc.size();
-        l.data = DeviceCol(std::max<size_t>(4, acc.size() * 4));
-        if (!acc.empty()) cm_check(cm31_h2d(l.data.ptr(), acc.data(), acc.size() * sizeof(DataAccess)));
-        return l;
+    static Words upload_words(const u32* src, size_t n_words) {
+        DeviceCol dev(std::max<size_t>(4, n_words));
+        if (n_words) cm_check(cm31_h2d(dev.ptr(), src, n_words * 4));
+        return dev;
     }
-    static std::vector<Col> unpack_bundles(const std::vector<Bundle>& rows, const AccessLog& log, u32 log_size) {
-        DeviceCol dev(std::max<size_t>(12, rows.size() * 12));
-        if (!rows.empty()) cm_check(cm31_h2d(dev.ptr(), rows.data(), rows.size() * sizeof(Bundle)));
+    static std::vector<Col> unpack_bundles(const Words& rows, size_t n_real, const Words& accesses, size_t n_accesses, u32 log_size) {
         std::vector<Col> cols;
         std::vector<u32*> p;
         for (int k = 0; k < N_BUNDLE_INPUTS; k++) {
             cols.emplace_back((size_t)1 << log_size);
             p.push_back(cols.back().ptr());
         }
-        cm_check(cm31_unpack_bundles(dev.ptr(), rows.size(), log_size, log.data.ptr(), log.n, p.data()));
+        cm_check(cm31_unpack_bundles(rows.ptr(), n_real, log_size, accesses.ptr(), n_accesses, p.data()));
         return cols;
     }
-    static std::vector<Col> upload_rows(const std::vector<u32>& rows, size_t n_real, u32 n_fields, u32 log_size) {
-        DeviceCol dev(std::max<size_t>(4, rows.size()));
-        if (!rows.empty()) cm_check(cm31_h2d(dev.ptr(), rows.data(), rows.size() * 4));
+    static std::vector<Col> unpack_rows(const Words& rows, size_t n_real, u32 n_fields, u32 log_size) {
         std::vector<Col> cols;
         std::vector<u32*> p;
         for (u32 k = 0; k < n_fields; k++) {
             cols.emplace_back((size_t)1 << log_size);
             p.push_back(cols.back().ptr());
         }
-        cm_check(cm31_unpack_rows(dev.ptr(), n_real, n_fields, log_size, p.data()));
+        cm_check(cm31_unpack_rows(rows.ptr(), n_real, n_fields, log_size, p.data()));
         return cols;
     }
     template <class Eval>

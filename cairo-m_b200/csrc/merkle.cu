@@ -82,6 +82,7 @@ int cm31_blake2s_commit_layer(uint32_t log_size, const uint32_t* prev_layer, con
     if (int e = dcols.upload(cols, n_cols * sizeof(void*))) return e;
     size_t n = (size_t)1 << log_size;
     unsigned threads = n < 256 ? (unsigned)((n + 31) / 32 * 32) : 256;
+    ProfScope prof(n_cols ? "merkle_leaf_layer" : "merkle_inner_layer", (4ull * n_cols + 32ull + (prev_layer ? 64ull : 0ull)) * n);
     merkle_layer_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream()>>>(
         log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, out_layer);
     CM_LAUNCH_CHECK();
@@ -100,7 +101,10 @@ int cm31_grind_blake2s(const uint8_t digest[32], uint32_t pow_bits, uint64_t* no
     u64 batch = 1ull << (pow_bits + 2 < 16 ? 16 : (pow_bits + 2 > 26 ? 26 : pow_bits + 2));
     for (u64 base = 0;; base += batch) {
         CM_CUDA(cudaMemcpyAsync(dbest, &none, 8, cudaMemcpyHostToDevice, stream()));
-        grind_kernel<<<(unsigned)(batch / 256), 256, 0, stream()>>>((const u32*)dd.d, pow_bits, base, dbest);
+        {
+            ProfScope prof("grind", 0);
+            grind_kernel<<<(unsigned)(batch / 256), 256, 0, stream()>>>((const u32*)dd.d, pow_bits, base, dbest);
+        }
         CM_LAUNCH_CHECK();
         unsigned long long got = none;
         CM_CUDA(cudaMemcpyAsync(&got, dbest, 8, cudaMemcpyDeviceToHost, stream()));

@@ -461,6 +461,7 @@ static int run_fft(const u32* const* src_host, u32* const* dst_host, size_t n_co
     u32* const* dst = (u32* const*)ddst.d;
     if (L <= 2) {
         CirclePointM31 p = CanonicCoset(L).half_coset().initial();
+        ProfScope prof(INV ? "ifft_small" : "rfft_small", 4ull * n_cols * ((1ull << L) + (1ull << log_in)));
         fft_small_kernel<INV><<<(unsigned)((n_cols + 127) / 128), 128, 0, stream()>>>(src, dst, (u32)n_cols, L, log_in,
                                                                                      p.x, p.y);
         CM_LAUNCH_CHECK();
@@ -485,6 +486,8 @@ static int run_fft(const u32* const* src_host, u32* const* dst_host, size_t n_co
         if (smem > 48 * 1024) CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         size_t n_blocks = n_cols * (((size_t)1 << L) >> tile_log);
         CM_REQUIRE(n_blocks < (1ull << 31), "fft: batch too large for one launch");
+        // algorithmic bytes of the whole transform (read 2^log_in, write 2^L words per column) split evenly over its passes
+        ProfScope prof(INV ? "ifft_pass" : "rfft_pass", 4ull * n_cols * ((1ull << L) + (1ull << log_in)) / np);
         kern<<<(unsigned)n_blocks, threads, smem, stream()>>>(first ? src : (const u32* const*)dst, dst, L,
                                                               first ? log_in : L, ps.lo, ps.nl, ps.b, tree,
                                                               tw->log_size, (INV && last) ? scale_last : 1u,
@@ -510,6 +513,7 @@ int cm31_twiddles_create(uint32_t log_size, cm31_twiddles** out) {
     if (int e = cm31_malloc((void**)&tw->tw, n * 4)) return e;
     if (int e = cm31_malloc((void**)&tw->itw, n * 4)) return e;
     Coset root = CanonicCoset(log_size).half_coset();
+    ProfScope prof("twiddles", 8ull * n);
     twiddle_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(tw->tw, tw->itw, k, root.initial_index,
                                                                      root.step_size);
     CM_LAUNCH_CHECK();
@@ -546,6 +550,7 @@ int cm31_evaluate_batch(const uint32_t* const* coeffs, uint32_t* const* out, siz
 
 int cm31_bit_reverse(uint32_t* col, uint32_t log_size) {
     size_t n = (size_t)1 << log_size;
+    ProfScope prof("bit_reverse", 8ull * n);
     bit_reverse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(col, log_size);
     CM_LAUNCH_CHECK();
     return 0;
@@ -592,10 +597,14 @@ int cm31_eval_at_point_batch(const uint32_t* const* coeffs, const uint32_t* log_
     u32 *dpart = nullptr, *dout = nullptr;
     CM_CUDA(cudaMallocAsync(&dpart, (size_t)part_off * 16, stream()));
     CM_CUDA(cudaMallocAsync(&dout, n_polys * 16, stream()));
-    eap_stage1_kernel<<<(unsigned)chunk_job.size(), 256, 0, stream()>>>((const EapJob*)djobs.d, (const u32*)dchunk.d,
-                                                                       (const u32*)dfac.d, dpart);
-    CM_LAUNCH_CHECK();
-    eap_stage2_kernel<<<(unsigned)n_polys, 256, 0, stream()>>>((const EapJob*)djobs.d, (const u32*)dfac.d, dpart, dout);
+    {
+        uint64_t coeff_bytes = 0;
+        for (size_t i = 0; i < n_polys; i++) coeff_bytes += 4ull << log_sizes_host[i];
+        ProfScope prof("eval_at_point", coeff_bytes, 2);
+        eap_stage1_kernel<<<(unsigned)chunk_job.size(), 256, 0, stream()>>>((const EapJob*)djobs.d, (const u32*)dchunk.d,
+                                                                           (const u32*)dfac.d, dpart);
+        eap_stage2_kernel<<<(unsigned)n_polys, 256, 0, stream()>>>((const EapJob*)djobs.d, (const u32*)dfac.d, dpart, dout);
+    }
     CM_LAUNCH_CHECK();
     CM_CUDA(cudaMemcpyAsync(out_host, dout, n_polys * 16, cudaMemcpyDeviceToHost, stream()));
     CM_CUDA(cudaFreeAsync(dpart, stream()));

@@ -28,6 +28,39 @@ static int ensure_pool() {
     return 0;
 }
 
+// ------------------------------------------------------------------ per-kernel timing
+struct ProfRec {
+    const char* name;
+    uint64_t bytes;
+    cudaEvent_t a, b;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_free;
+static uint64_t g_launches = 0;  // every bracketed launch, counted even when timing is off
+
+static cudaEvent_t prof_event() {
+    if (!g_prof_free.empty()) {
+        cudaEvent_t e = g_prof_free.back();
+        g_prof_free.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(const char* name, uint64_t alg_bytes, unsigned n_kernels) {
+    g_launches += n_kernels;
+    if (!g_prof_on) return;
+    ProfRec r{name, alg_bytes, prof_event(), prof_event()};
+    cudaEventRecord(r.a, stream());
+    g_prof.push_back(r);
+}
+void prof_end() {
+    if (!g_prof_on) return;
+    cudaEventRecord(g_prof.back().b, stream());
+}
+
 int DeviceTable::upload(const void* host, size_t bytes) {
     release();
     if (int e = ensure_pool()) return e;
@@ -79,6 +112,60 @@ int cm31_sync(void) {
     CM_CUDA(cudaStreamSynchronize(stream()));
     return 0;
 }
+int cm31_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return 0;
+}
+int cm31_profile_reset(void) {
+    for (ProfRec& r : g_prof) {
+        g_prof_free.push_back(r.a);
+        g_prof_free.push_back(r.b);
+    }
+    g_prof.clear();
+    g_launches = 0;
+    return 0;
+}
+int cm31_profile_launches(uint64_t* out) {
+    *out = g_launches;
+    return 0;
+}
+int cm31_profile_report(char* buf, size_t cap, size_t* len) {
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    struct Agg {
+        const char* name;
+        double ms = 0;
+        uint64_t launches = 0, bytes = 0;
+    };
+    std::vector<Agg> aggs;
+    for (ProfRec& r : g_prof) {
+        float ms = 0;
+        CM_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        Agg* a = nullptr;
+        for (Agg& x : aggs)
+            if (strcmp(x.name, r.name) == 0) a = &x;
+        if (!a) {
+            aggs.push_back(Agg());
+            a = &aggs.back();
+            a->name = r.name;
+        }
+        a->ms += ms;
+        a->launches++;
+        a->bytes += r.bytes;
+    }
+    std::string s = "[";
+    for (size_t i = 0; i < aggs.size(); i++) {
+        char line[256];
+        snprintf(line, sizeof line, "%s{\"kernel\": \"%s\", \"ms\": %.6f, \"launches\": %llu, \"alg_bytes\": %llu}", i ? ", " : "",
+                 aggs[i].name, aggs[i].ms, (unsigned long long)aggs[i].launches, (unsigned long long)aggs[i].bytes);
+        s += line;
+    }
+    s += "]";
+    if (len) *len = s.size();
+    CM_REQUIRE(buf == nullptr || s.size() + 1 <= cap, "profile_report: buffer too small");
+    if (buf) memcpy(buf, s.c_str(), s.size() + 1);
+    return 0;
+}
+
 int cm31_malloc(void** out, size_t bytes) {
     CM_REQUIRE(out != nullptr, "malloc: null out");
     if (int e = ensure_pool()) return e;
@@ -117,6 +204,7 @@ int cm31_gather_u32(const uint32_t* const* cols, size_t n_cols, const uint32_t* 
     u32* dout = nullptr;
     size_t total = n_cols * n_idx;
     CM_CUDA(cudaMallocAsync(&dout, total * 4, stream()));
+    ProfScope prof("gather_u32", 8ull * total);
     gather_u32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream()>>>((const u32* const*)dcols.d, n_cols,
                                                                             (const u32*)didx.d, n_idx, dout);
     CM_LAUNCH_CHECK();
@@ -132,6 +220,7 @@ int cm31_gather_hash(const uint32_t* layer, const uint32_t* idx_host, size_t n_i
     if (int e = didx.upload(idx_host, n_idx * 4)) return e;
     u32* dout = nullptr;
     CM_CUDA(cudaMallocAsync(&dout, n_idx * 32, stream()));
+    ProfScope prof("gather_hash", 64ull * n_idx);
     gather_hash_kernel<<<(unsigned)((n_idx * 8 + 255) / 256), 256, 0, stream()>>>(layer, (const u32*)didx.d, n_idx,
                                                                                  dout);
     CM_LAUNCH_CHECK();

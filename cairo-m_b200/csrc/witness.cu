@@ -68,6 +68,7 @@ int cm31_unpack_bundles(const uint32_t* bundles_dev, size_t n_real, uint32_t log
     DeviceTable dout;
     if (int e = dout.upload(out_cols, N_BUNDLE_INPUTS * sizeof(void*))) return e;
     size_t n = (size_t)1 << log_size;
+    ProfScope prof("unpack_bundles", 48ull * n_real + 4ull * N_BUNDLE_INPUTS * n);
     unpack_bundles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>((const uint4*)bundles_dev, (u32)n_real, log_size,
                                                                             (const uint4*)accesses_dev, (u32)n_accesses,
                                                                             (u32* const*)dout.d);
@@ -80,6 +81,7 @@ int cm31_unpack_rows(const uint32_t* rows_dev, size_t n_real, uint32_t n_fields,
     DeviceTable dout;
     if (int e = dout.upload(out_cols, n_fields * sizeof(void*))) return e;
     size_t total = ((size_t)1 << log_size) * n_fields;
+    ProfScope prof("unpack_rows", 8ull * total);
     unpack_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream()>>>(rows_dev, (u32)n_real, n_fields, log_size, (u32* const*)dout.d);
     CM_LAUNCH_CHECK();
     return 0;
@@ -87,6 +89,7 @@ int cm31_unpack_rows(const uint32_t* rows_dev, size_t n_real, uint32_t n_fields,
 
 int cm31_iota(uint32_t* col, size_t n) {
     if (n == 0) return 0;
+    ProfScope prof("iota", 4ull * n);
     iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(col, n);
     CM_LAUNCH_CHECK();
     return 0;

@@ -151,6 +151,37 @@ int cm31_logup_finalize_last(uint32_t* const last4[4], uint32_t log_size, uint32
 /* multiplicity histograms (P/src/preprocessed/range_check/range_check_macro.rs:72-84) */
 int cm31_histogram(const uint32_t* values, size_t n, uint32_t* bins, uint32_t log_bins);
 
+/* ------------------------------------------------------------------ whole proofs
+ * prove_cairo_m::<Blake2sMerkleChannel> (P/src/prover.rs:23-147) over the ops above.  The input
+ * handle owns the reference's ProverInput (P/src/adapter/mod.rs:97-193): per-opcode ExecutionBundles,
+ * the data-access log, boundary memory, clock-update rows.  Only the fibonacci_loop input producer
+ * (host VM + adapter, the serial step BEFORE the hot path) is built in this round. */
+typedef struct cm31_prover_input cm31_prover_input;
+int cm31_fib_input_create(uint32_t n, cm31_prover_input** out);
+int cm31_input_destroy(cm31_prover_input* h);
+/* info[0] VM steps, [1] data accesses, [2] boundary-memory rows, [3] return value, [4] input bytes staged per proof */
+int cm31_input_info(const cm31_prover_input* h, uint64_t info[5]);
+/* stage the input in HBM once (later proofs on this handle skip the host->device copy) / drop that copy */
+int cm31_input_upload(cm31_prover_input* h);
+int cm31_input_release_device(cm31_prover_input* h);
+/* proof bytes (ProofWriter layout, cairo/prover.hpp) into proof_out; timings_ms (optional, 5 doubles):
+ * preprocessed, trace, interaction, stark, total.  Returns non-zero with
+ * "ConstraintsNotSatisfied" (S/prover/src/core/prover/mod.rs:76-82) if the OODS check fails. */
+int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out,
+                       size_t proof_cap, size_t* proof_len, double* timings_ms);
+/* S/examples/src/wide_fibonacci/mod.rs:22-43 — the bring-up AIR (parity tests only) */
+int cm31_prove_wide_fibonacci(uint32_t log_n_rows, uint32_t n_cols, uint32_t pow_bits, uint32_t n_queries,
+                              uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+
+/* ------------------------------------------------------------------ per-kernel device timing
+ * (the reference's tracing spans, S/prover/src/tracing/mod.rs:22-50).  When enabled every kernel
+ * launch is bracketed by CUDA events on the launch stream; the report is a JSON array of
+ * {"kernel", "ms", "launches", "alg_bytes"} (algorithmic bytes per SURVEY.md §8d). */
+int cm31_profile_enable(int on);
+int cm31_profile_reset(void);
+int cm31_profile_launches(uint64_t* out); /* kernels launched since the last reset (always counted) */
+int cm31_profile_report(char* buf, size_t cap, size_t* len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,7 +35,7 @@ struct OracleAirImpl {
     typedef OCol Col;
     template <class Eval>
     using Component = OracleComponent<Eval>;
-    typedef std::vector<cm31::DataAccess> AccessLog;
+    typedef std::vector<u32> Words;
     static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
     static Col iota(size_t n) {
         Col c(n);
@@ -43,13 +43,15 @@ struct OracleAirImpl {
         return c;
     }
     static Col clone(const Col& c) { return c; }
-    static AccessLog upload_accesses(const std::vector<cm31::DataAccess>& acc) { return acc; }
-    static std::vector<Col> unpack_bundles(const std::vector<cm31::Bundle>& rows, const AccessLog& log, u32 log_size) {
+    static Words upload_words(const u32* src, size_t n_words) { return Words(src, src + n_words); }
+    static std::vector<Col> unpack_bundles(const Words& row_words, size_t n_real, const Words& access_words, size_t n_accesses, u32 log_size) {
+        const cm31::Bundle* rows = (const cm31::Bundle*)row_words.data();
+        const cm31::DataAccess* log = (const cm31::DataAccess*)access_words.data();
         size_t n = (size_t)1 << log_size;
         std::vector<Col> cols(cm31::N_BUNDLE_INPUTS, Col(n));
         for (size_t r = 0; r < n; r++) {
             cm31::Bundle b;
-            if (r < rows.size()) b = rows[r];
+            if (r < n_real) b = rows[r];
             else {
                 memset(&b, 0, sizeof(b));
                 b.inst[0] = cm31::OP_RET;  // ExecutionBundle::default()
@@ -58,7 +60,7 @@ struct OracleAirImpl {
             for (int k = 0; k < 10; k++) cols[k][r] = M31((u64)head[k]);
             for (int k = 0; k < cm31::MAX_ACCESSES; k++) {
                 cm31::DataAccess a{0, 0, 0, 0};
-                if ((u32)k < b.span_len && (size_t)b.span_start + k < log.size()) a = log[b.span_start + k];
+                if ((u32)k < b.span_len && (size_t)b.span_start + k < n_accesses) a = log[b.span_start + k];
                 cols[cm31::in_acc(k, cm31::ACC_ADDRESS)][r] = M31((u64)a.address);
                 cols[cm31::in_acc(k, cm31::ACC_PREV_CLOCK)][r] = M31((u64)a.prev_clock);
                 cols[cm31::in_acc(k, cm31::ACC_PREV_VALUE)][r] = M31((u64)a.prev_value);
@@ -67,7 +69,7 @@ struct OracleAirImpl {
         }
         return cols;
     }
-    static std::vector<Col> upload_rows(const std::vector<u32>& rows, size_t n_real, u32 n_fields, u32 log_size) {
+    static std::vector<Col> unpack_rows(const Words& rows, size_t n_real, u32 n_fields, u32 log_size) {
         size_t n = (size_t)1 << log_size;
         std::vector<Col> cols(n_fields, Col(n));
         for (size_t r = 0; r < n_real; r++)
