@@ -175,3 +175,23 @@ def gather_u32(cols, idx):
     out = (C.c_uint32 * (len(cols) * len(idx)))()
     check(lib().cm31_gather_u32(_ptr_array(cols), C.c_size_t(len(cols)), _u32_array(idx), C.c_size_t(len(idx)), out))
     return [list(out[c * len(idx):(c + 1) * len(idx)]) for c in range(len(cols))]
+
+
+def gather_words(srcs, src_id, word_idx):
+    """out[k] = srcs[src_id[k]][word_idx[k]] — the batched decommitment read (one launch per proof)."""
+    n = len(src_id)
+    out = (C.c_uint32 * n)()
+    check(lib().cm31_gather_words(_ptr_array(srcs), C.c_size_t(len(srcs)), _u32_array(src_id), _u32_array(word_idx),
+                                  C.c_size_t(n), out))
+    return list(out)
+
+
+def blake2s_commit_top(top_log: int, prev_layer, cols_by_layer, out_layers) -> None:
+    """Layers top_log..0 in one launch; cols_by_layer[l] = list of columns with 2^l rows."""
+    flat, start = [], []
+    for l in range(top_log + 1):
+        start.append(len(flat))
+        flat.extend(cols_by_layer[l])
+    start.append(len(flat))
+    prev = C.c_void_p(prev_layer.data_ptr()) if prev_layer is not None else C.c_void_p()
+    check(lib().cm31_blake2s_commit_top(C.c_uint32(top_log), prev, _ptr_array(flat), _u32_array(start), _ptr_array(out_layers)))

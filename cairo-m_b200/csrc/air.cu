@@ -93,7 +93,14 @@ __global__ void __launch_bounds__(128) air_program_kernel(const u32* const* __re
                 out_cols[b + 3][row] = regs[a + 3];
                 break;
             case OP_STORE_F: out_cols[b][row] = regs[a]; break;
-            case OP_HIST: atomicAdd(out_cols[b] + regs[a], 1u); break;
+            case OP_HIST: {
+                // lookups of a fibonacci-like trace hit a handful of bins (clock deltas, small offsets):
+                // aggregate equal values across the warp so each distinct value costs one atomic
+                const u32 v = regs[a];
+                const unsigned peers = __match_any_sync(__activemask(), v);
+                if ((threadIdx.x & 31u) == (u32)(__ffs(peers) - 1)) atomicAdd(out_cols[b] + v, (u32)__popc(peers));
+                break;
+            }
             case OP_INV: regs[dst] = m31_inv(regs[a]); break;
             case OP_SHR: regs[dst] = regs[a] >> b; break;
             case OP_AND: regs[dst] = regs[a] & b; break;

@@ -265,14 +265,12 @@ StagedInput<Impl> stage_input(const ProverInput& input) {
             auto it = input.states_by_opcodes.find(op);
             if (it != input.states_by_opcodes.end() && !it->second.empty()) parts.push_back(&it->second);
         }
-        if (parts.size() == 1) {  // common case: upload straight from the adapter's vector
-            r.n_real = parts[0]->size();
-            r.words = Impl::upload_words((const u32*)parts[0]->data(), r.n_real * 12);
-        } else {
-            std::vector<Bundle> rows;
-            for (auto* v : parts) rows.insert(rows.end(), v->begin(), v->end());
-            r.n_real = rows.size();
-            r.words = Impl::upload_words((const u32*)rows.data(), r.n_real * 12);
+        for (auto* v : parts) r.n_real += v->size();
+        r.words = Impl::alloc_words(r.n_real * 12);
+        size_t at = 0;
+        for (auto* v : parts) {  // straight from the adapter's (page-locked) vectors, no host-side concatenation
+            Impl::copy_words(r.words, at * 12, (const u32*)v->data(), v->size() * 12);
+            at += v->size();
         }
         st.bytes += r.n_real * sizeof(Bundle);
         st.opcode.push_back(std::move(r));

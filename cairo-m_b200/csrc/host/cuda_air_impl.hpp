@@ -61,6 +61,10 @@ struct CudaAirImpl {
         cm_check(cm31_d2d(o.ptr(), c.ptr(), c.size() * 4));
         return o;
     }
+    static Words alloc_words(size_t n_words) { return DeviceCol(std::max<size_t>(4, n_words)); }
+    static void copy_words(Words& dst, size_t at, const u32* src, size_t n_words) {
+        if (n_words) cm_check(cm31_h2d(dst.ptr() + at, src, n_words * 4));
+    }
     static Words upload_words(const u32* src, size_t n_words) {
         DeviceCol dev(std::max<size_t>(4, n_words));
         if (n_words) cm_check(cm31_h2d(dev.ptr(), src, n_words * 4));

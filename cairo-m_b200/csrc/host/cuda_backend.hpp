@@ -129,6 +129,28 @@ struct CudaBackend {
         out.assign(cols.size(), std::vector<u32>());
         for (size_t c = 0; c < cols.size(); c++) out[c].assign(flat.begin() + c * idx.size(), flat.begin() + (c + 1) * idx.size());
     }
+    // layers top_log..0 in one launch; cols_by_layer[l] = columns of 2^l rows. Returns layers[0..top_log].
+    static std::vector<HashCol> commit_top_layers(u32 top_log, const HashCol* prev, const std::vector<std::vector<const Col*>>& cols_by_layer) {
+        std::vector<HashCol> out;
+        std::vector<u32*> outp;
+        std::vector<const u32*> cols;
+        std::vector<u32> start;
+        for (u32 l = 0; l <= top_log; l++) {
+            out.emplace_back(((size_t)1 << l) * 8);
+            outp.push_back(out.back().ptr());
+            start.push_back((u32)cols.size());
+            for (auto* c : cols_by_layer[l]) cols.push_back(c->ptr());
+        }
+        start.push_back((u32)cols.size());
+        cm_check(cm31_blake2s_commit_top(top_log, prev ? prev->ptr() : nullptr, cols.data(), start.data(), outp.data()));
+        return out;
+    }
+    static const u32* col_words(const Col& c) { return c.ptr(); }
+    static const u32* hash_words(const HashCol& c) { return c.ptr(); }
+    static void gather_words(const std::vector<const u32*>& srcs, const std::vector<u32>& src_id, const std::vector<u32>& word,
+                             std::vector<u32>& out) {
+        cm_check(cm31_gather_words(srcs.data(), srcs.size(), src_id.data(), word.data(), src_id.size(), out.data()));
+    }
     static void gather_hashes(const HashCol& layer, const std::vector<u32>& idx, std::vector<Hash32>& out) {
         out.resize(idx.size());
         cm_check(cm31_gather_hash(layer.ptr(), idx.data(), idx.size(), (u32*)out.data()));

@@ -233,6 +233,44 @@ inline u32 ilog2(size_t n) {
     return l;
 }
 
+// ------------------------------------------------------------------ deferred gathers
+// The reference reads queried rows with Column::at(i) one element at a time (vcs/prover.rs:125-140,
+// fri.rs:1002-1036).  Which elements are read depends only on the query positions, never on the
+// values, so every decommitment of a proof (4 trees + all FRI layers) first records its reads here
+// and receives slot numbers; ONE batched device gather then serves them all.
+template <class B>
+struct GatherQueue {
+    std::vector<const u32*> srcs;
+    std::map<const u32*, u32> src_index;
+    std::vector<u32> src_id, word, results;
+    size_t request(const u32* base, size_t word_idx) {
+        auto it = src_index.find(base);
+        u32 id;
+        if (it == src_index.end()) {
+            id = (u32)srcs.size();
+            srcs.push_back(base);
+            src_index[base] = id;
+        } else id = it->second;
+        src_id.push_back(id);
+        word.push_back((u32)word_idx);
+        return src_id.size() - 1;
+    }
+    size_t request_hash(const u32* layer, size_t node) {  // 8 consecutive slots
+        size_t first = src_id.size();
+        for (size_t k = 0; k < 8; k++) request(layer, node * 8 + k);
+        return first;
+    }
+    void flush() {
+        results.resize(src_id.size());
+        if (!src_id.empty()) B::gather_words(srcs, src_id, word, results);
+    }
+    Hash32 hash_at(size_t slot) const {
+        Hash32 h;
+        memcpy(h.b, &results[slot], 32);
+        return h;
+    }
+};
+
 // ------------------------------------------------------------------ MerkleProver (vcs/prover.rs)
 template <class B>
 struct MerkleProver {
@@ -251,11 +289,23 @@ struct MerkleProver {
         u32 max_log = ilog2(B::len(*sorted[0]));
         size_t pos = 0;
         std::vector<HashCol> layers;
-        for (int log_size = (int)max_log; log_size >= 0; log_size--) {
+        constexpr int TOP_LOG = 10;  // layers of <= 2^10 nodes are hashed by one fused launch
+        int log_size = (int)max_log;
+        for (; log_size > TOP_LOG; log_size--) {
             std::vector<const Col*> layer_cols;
             while (pos < sorted.size() && ilog2(B::len(*sorted[pos])) == (u32)log_size) layer_cols.push_back(sorted[pos++]);
             const HashCol* prev = layers.empty() ? nullptr : &layers.back();
             layers.push_back(B::commit_on_layer((u32)log_size, prev, layer_cols));
+        }
+        {
+            std::vector<std::vector<const Col*>> by_layer(log_size + 1);
+            while (pos < sorted.size()) {
+                by_layer[ilog2(B::len(*sorted[pos]))].push_back(sorted[pos]);
+                pos++;
+            }
+            const HashCol* prev = layers.empty() ? nullptr : &layers.back();
+            std::vector<HashCol> top = B::commit_top_layers((u32)log_size, prev, by_layer);
+            for (int l = log_size; l >= 0; l--) layers.push_back(std::move(top[l]));
         }
         std::reverse(layers.begin(), layers.end());
         mp.layers = std::move(layers);
@@ -268,12 +318,22 @@ struct MerkleProver {
         return out[0];
     }
 
-    // vcs/prover.rs:82-156.  The control flow only depends on indices, so the node lists are
-    // computed first and the values fetched with one batched gather per layer.
-    std::pair<std::vector<u32>, MerkleDecommitment> decommit(const std::map<u32, std::vector<size_t>>& queries_per_log_size,
-                                                             const std::vector<const Col*>& columns) const {
-        std::vector<u32> queried_values;
-        MerkleDecommitment decommitment;
+    // vcs/prover.rs:82-156 in two phases: `plan` walks the layers exactly like the reference and
+    // records every read in the gather queue; `finish` (after queue.flush()) assembles the values.
+    struct PendingDecommit {
+        std::vector<size_t> queried_slots, column_witness_slots, hash_witness_slots;
+        std::pair<std::vector<u32>, MerkleDecommitment> finish(const GatherQueue<B>& q) const {
+            std::vector<u32> queried_values;
+            MerkleDecommitment d;
+            for (size_t s : queried_slots) queried_values.push_back(q.results[s]);
+            for (size_t s : column_witness_slots) d.column_witness.push_back(q.results[s]);
+            for (size_t s : hash_witness_slots) d.hash_witness.push_back(q.hash_at(s));
+            return {queried_values, d};
+        }
+    };
+    PendingDecommit plan_decommit(GatherQueue<B>& queue, const std::map<u32, std::vector<size_t>>& queries_per_log_size,
+                                  const std::vector<const Col*>& columns) const {
+        PendingDecommit pd;
         std::vector<const Col*> sorted = columns;
         std::stable_sort(sorted.begin(), sorted.end(), [](const Col* a, const Col* b) { return B::len(*a) > B::len(*b); });
         size_t pos = 0;
@@ -287,8 +347,6 @@ struct MerkleProver {
             const std::vector<size_t>& layer_column_queries = qit == queries_per_log_size.end() ? empty : qit->second;
             size_t pi = 0, ci = 0;
             std::vector<size_t> layer_total_queries;
-            std::vector<u32> hash_witness_idx;
-            std::vector<char> node_is_queried;
             while (pi < last_layer_queries.size() || ci < layer_column_queries.size()) {
                 size_t node_index;
                 bool has_p = pi < last_layer_queries.size(), has_c = ci < layer_column_queries.size();
@@ -296,33 +354,28 @@ struct MerkleProver {
                 else if (has_p) node_index = last_layer_queries[pi] / 2;
                 else node_index = layer_column_queries[ci];
                 if (previous_layer_hashes) {
+                    const u32* prev = B::hash_words(*previous_layer_hashes);
                     if (pi < last_layer_queries.size() && last_layer_queries[pi] == 2 * node_index) pi++;
-                    else hash_witness_idx.push_back((u32)(2 * node_index));
+                    else pd.hash_witness_slots.push_back(queue.request_hash(prev, 2 * node_index));
                     if (pi < last_layer_queries.size() && last_layer_queries[pi] == 2 * node_index + 1) pi++;
-                    else hash_witness_idx.push_back((u32)(2 * node_index + 1));
+                    else pd.hash_witness_slots.push_back(queue.request_hash(prev, 2 * node_index + 1));
                 }
                 bool queried = ci < layer_column_queries.size() && layer_column_queries[ci] == node_index;
                 if (queried) ci++;
-                node_is_queried.push_back(queried ? 1 : 0);
+                std::vector<size_t>& dst = queried ? pd.queried_slots : pd.column_witness_slots;
+                for (const Col* c : layer_columns) dst.push_back(queue.request(B::col_words(*c), node_index));
                 layer_total_queries.push_back(node_index);
-            }
-            if (previous_layer_hashes && !hash_witness_idx.empty()) {
-                std::vector<Hash32> hs;
-                B::gather_hashes(*previous_layer_hashes, hash_witness_idx, hs);
-                decommitment.hash_witness.insert(decommitment.hash_witness.end(), hs.begin(), hs.end());
-            }
-            if (!layer_columns.empty() && !layer_total_queries.empty()) {
-                std::vector<u32> idx(layer_total_queries.begin(), layer_total_queries.end());
-                std::vector<std::vector<u32>> vals;
-                B::gather(layer_columns, idx, vals);
-                for (size_t q = 0; q < idx.size(); q++) {
-                    std::vector<u32>& dst = node_is_queried[q] ? queried_values : decommitment.column_witness;
-                    for (size_t c = 0; c < layer_columns.size(); c++) dst.push_back(vals[c][q]);
-                }
             }
             last_layer_queries = layer_total_queries;
         }
-        return {queried_values, decommitment};
+        return pd;
+    }
+    std::pair<std::vector<u32>, MerkleDecommitment> decommit(const std::map<u32, std::vector<size_t>>& queries_per_log_size,
+                                                             const std::vector<const Col*>& columns) const {
+        GatherQueue<B> q;
+        PendingDecommit pd = plan_decommit(q, queries_per_log_size, columns);
+        q.flush();
+        return pd.finish(q);
     }
 };
 
@@ -403,6 +456,11 @@ struct CommitmentTreeProver {
         for (auto& e : evaluations) cols.push_back(&e.values);
         return commitment.decommit(queries, cols);
     }
+    typename MerkleProver<B>::PendingDecommit plan_decommit(GatherQueue<B>& queue, const std::map<u32, std::vector<size_t>>& queries) const {
+        std::vector<const typename B::Col*> cols;
+        for (auto& e : evaluations) cols.push_back(&e.values);
+        return commitment.plan_decommit(queue, queries, cols);
+    }
 };
 
 template <class B>
@@ -446,10 +504,12 @@ struct FriProver {
         std::array<Col, 4> evaluation;
         u32 log_size;
         MerkleProver<B> merkle_tree;
+        Hash32 root;
     };
     FriConfig config;
     const std::vector<SecureEvaluation<B>>* columns = nullptr;
     MerkleProver<B> first_layer_tree;
+    Hash32 first_layer_root;
     std::vector<InnerLayer> inner_layers;
     std::vector<QM31> last_layer_poly;
 
@@ -470,7 +530,8 @@ struct FriProver {
         fp.columns = &columns;
         // commit_first_layer
         fp.first_layer_tree = MerkleProver<B>::commit(coordinate_columns(columns));
-        channel.mix_root(fp.first_layer_tree.root());
+        fp.first_layer_root = fp.first_layer_tree.root();
+        channel.mix_root(fp.first_layer_root);
         // commit_inner_layers
         u32 first_inner_log = columns[0].log_size - 1;
         std::array<Col, 4> layer_eval;
@@ -485,7 +546,8 @@ struct FriProver {
             std::vector<const Col*> cc;
             for (auto& c : layer_eval) cc.push_back(&c);
             layer.merkle_tree = MerkleProver<B>::commit(cc);
-            channel.mix_root(layer.merkle_tree.root());
+            layer.root = layer.merkle_tree.root();
+            channel.mix_root(layer.root);
             QM31 alpha = channel.draw_secure_felt();
             std::array<Col, 4> folded = B::fold_line(layer_eval, layer_log, alpha, twiddles);
             layer.evaluation = std::move(layer_eval);
@@ -562,10 +624,9 @@ struct FriProver {
         return values;
     }
 
-    // compute_decommitment_positions_and_witness_evals (fri.rs:1002-1036), batched gather
-    static void positions_and_witness(const std::array<Col, 4>& column, const std::vector<size_t>& query_positions, u32 fold_step,
-                                      std::vector<size_t>& decommitment_positions, std::vector<QM31>& witness_evals) {
-        std::vector<u32> need;
+    // compute_decommitment_positions_and_witness_evals (fri.rs:1002-1036); reads are queued
+    static void positions_and_witness(GatherQueue<B>& queue, const std::array<Col, 4>& column, const std::vector<size_t>& query_positions,
+                                      u32 fold_step, std::vector<size_t>& decommitment_positions, std::vector<size_t>& witness_slots) {
         size_t i = 0;
         while (i < query_positions.size()) {
             size_t j = i;
@@ -578,52 +639,71 @@ struct FriProver {
                     qi++;
                     continue;
                 }
-                need.push_back((u32)position);
+                size_t first = queue.request(B::col_words(column[0]), position);
+                for (int k = 1; k < 4; k++) queue.request(B::col_words(column[k]), position);
+                witness_slots.push_back(first);  // 4 consecutive slots = one QM31
             }
             i = j;
         }
-        if (!need.empty()) {
-            std::vector<const Col*> cols;
-            for (auto& c : column) cols.push_back(&c);
-            std::vector<std::vector<u32>> vals;
-            B::gather(cols, need, vals);
-            for (size_t k = 0; k < need.size(); k++) witness_evals.push_back(qm_make(vals[0][k], vals[1][k], vals[2][k], vals[3][k]));
-        }
     }
 
-    std::pair<FriProof, std::map<u32, std::vector<size_t>>> decommit(Blake2sChannel& channel) {
+    struct PendingLayer {
+        std::vector<size_t> witness_slots;
+        typename MerkleProver<B>::PendingDecommit decommit;
+        Hash32 commitment;
+        FriLayerProof finish(const GatherQueue<B>& q) const {
+            FriLayerProof lp;
+            for (size_t s : witness_slots) lp.fri_witness.push_back(qm_make(q.results[s], q.results[s + 1], q.results[s + 2], q.results[s + 3]));
+            lp.decommitment = decommit.finish(q).second;
+            lp.commitment = commitment;
+            return lp;
+        }
+    };
+    struct PendingFriProof {
+        PendingLayer first_layer;
+        std::vector<PendingLayer> inner_layers;
+        std::vector<QM31> last_layer_poly;
+        FriProof finish(const GatherQueue<B>& q) const {
+            FriProof proof;
+            proof.first_layer = first_layer.finish(q);
+            for (auto& l : inner_layers) proof.inner_layers.push_back(l.finish(q));
+            proof.last_layer_poly = last_layer_poly;
+            return proof;
+        }
+    };
+
+    // FriProver::decommit (fri.rs:295-330) with every read deferred to `queue`
+    std::pair<PendingFriProof, std::map<u32, std::vector<size_t>>> plan_decommit(Blake2sChannel& channel, GatherQueue<B>& queue) {
         std::set<u32> column_log_sizes;
         for (auto& c : *columns) column_log_sizes.insert(c.log_size);
         u32 max_column_log_size = *column_log_sizes.rbegin();
         Queries queries = Queries::generate(channel, max_column_log_size, config.n_queries);
         std::map<u32, std::vector<size_t>> query_positions_by_log_size;
         for (u32 ls : column_log_sizes) query_positions_by_log_size[ls] = queries.fold(queries.log_domain_size - ls).positions;
-        FriProof proof;
+        PendingFriProof proof;
         // first layer (fri.rs:906-945)
         {
             std::map<u32, std::vector<size_t>> decommitment_positions_by_log_size;
             for (auto& column : *columns) {
                 Queries cq = queries.fold(queries.log_domain_size - column.log_size);
                 std::vector<size_t> positions;
-                positions_and_witness(column.columns, cq.positions, 1, positions, proof.first_layer.fri_witness);
+                positions_and_witness(queue, column.columns, cq.positions, 1, positions, proof.first_layer.witness_slots);
                 decommitment_positions_by_log_size[column.log_size] = positions;
             }
-            auto res = first_layer_tree.decommit(decommitment_positions_by_log_size, coordinate_columns(*columns));
-            proof.first_layer.decommitment = res.second;
-            proof.first_layer.commitment = first_layer_tree.root();
+            proof.first_layer.decommit = first_layer_tree.plan_decommit(queue, decommitment_positions_by_log_size, coordinate_columns(*columns));
+            proof.first_layer.commitment = first_layer_root;
         }
         Queries layer_queries = queries.fold(1);
         for (auto& layer : inner_layers) {
-            FriLayerProof lp;
+            PendingLayer lp;
             std::vector<size_t> positions;
-            positions_and_witness(layer.evaluation, layer_queries.positions, 1, positions, lp.fri_witness);
+            positions_and_witness(queue, layer.evaluation, layer_queries.positions, 1, positions, lp.witness_slots);
             std::map<u32, std::vector<size_t>> m;
             m[layer.log_size] = positions;
             std::vector<const Col*> cc;
             for (auto& c : layer.evaluation) cc.push_back(&c);
-            auto res = layer.merkle_tree.decommit(m, cc);
-            lp.decommitment = res.second;
-            lp.commitment = layer.merkle_tree.root();
+            lp.decommit = layer.merkle_tree.plan_decommit(queue, m, cc);
+            lp.commitment = layer.root;
             proof.inner_layers.push_back(std::move(lp));
             layer_queries = layer_queries.fold(1);
         }
@@ -716,12 +796,16 @@ CommitmentSchemeProof CommitmentSchemeProver<B>::prove_values(const std::vector<
     proof.proof_of_work = B::grind(channel.digest(), config.pow_bits);
     channel.mix_u64(proof.proof_of_work);
 
-    auto fri_res = fri_prover.decommit(channel);
-    proof.fri_proof = std::move(fri_res.first);
+    // FRI + the 4 trees decommit through one batched device gather
+    GatherQueue<B> queue;
+    auto fri_res = fri_prover.plan_decommit(channel, queue);
     const std::map<u32, std::vector<size_t>>& query_positions_per_log_size = fri_res.second;
-
-    for (auto& t : trees) {
-        auto res = t.decommit(query_positions_per_log_size);
+    std::vector<typename MerkleProver<B>::PendingDecommit> pending;
+    for (auto& t : trees) pending.push_back(t.plan_decommit(queue, query_positions_per_log_size));
+    queue.flush();
+    proof.fri_proof = fri_res.first.finish(queue);
+    for (auto& pd : pending) {
+        auto res = pd.finish(queue);
         proof.queried_values.push_back(std::move(res.first));
         proof.decommitments.push_back(std::move(res.second));
     }

@@ -12,11 +12,8 @@
 
 namespace cm31 {
 
-__global__ void __launch_bounds__(256) merkle_layer_kernel(u32 log_size, const u32* __restrict__ prev,
-                                                           const u32* const* __restrict__ cols, u32 n_cols,
-                                                           u32* __restrict__ out) {
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= ((size_t)1 << log_size)) return;
+__device__ __forceinline__ void hash_node(size_t i, const u32* __restrict__ prev, const u32* const* __restrict__ cols, u32 n_cols,
+                                          u32* __restrict__ out) {
     Blake2sState st;
     blake2s_init(st);
     u32 m[16];
@@ -24,7 +21,7 @@ __global__ void __launch_bounds__(256) merkle_layer_kernel(u32 log_size, const u
     u64 done = 0;
     if (prev) {
         const uint4* p4 = reinterpret_cast<const uint4*>(prev + i * 16);
-        uint4 a = __ldg(p4), b = __ldg(p4 + 1), c = __ldg(p4 + 2), d = __ldg(p4 + 3);
+        uint4 a = p4[0], b = p4[1], c = p4[2], d = p4[3];
         m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
         m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
         m[8] = c.x; m[9] = c.y; m[10] = c.z; m[11] = c.w;
@@ -43,6 +40,29 @@ __global__ void __launch_bounds__(256) merkle_layer_kernel(u32 log_size, const u
     uint4* o4 = reinterpret_cast<uint4*>(out + i * 8);
     o4[0] = make_uint4(st.h[0], st.h[1], st.h[2], st.h[3]);
     o4[1] = make_uint4(st.h[4], st.h[5], st.h[6], st.h[7]);
+}
+
+__global__ void __launch_bounds__(256) merkle_layer_kernel(u32 log_size, const u32* __restrict__ prev,
+                                                           const u32* const* __restrict__ cols, u32 n_cols,
+                                                           u32* __restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= ((size_t)1 << log_size)) return;
+    hash_node(i, prev, cols, n_cols, out);
+}
+
+// The top of a tree (layers top_log .. 0, at most 2^10 nodes wide) in ONE single-CTA launch:
+// these layers are pure latency (<= 1024 hashes each), a launch per layer costs more than the work.
+// layer_out[l] = output of layer l; cols of layer l = cols[col_start[l] .. col_start[l+1]).
+struct MerkleTopArgs {
+    u32* layer_out[11];
+    u32 col_start[12];
+};
+__global__ void __launch_bounds__(1024) merkle_top_kernel(u32 top_log, const u32* prev, const u32* const* cols, MerkleTopArgs args) {
+    for (int l = (int)top_log; l >= 0; l--) {
+        if (threadIdx.x < (1u << l)) hash_node(threadIdx.x, prev, cols + args.col_start[l], args.col_start[l + 1] - args.col_start[l], args.layer_out[l]);
+        prev = args.layer_out[l];
+        __syncthreads();  // block-scope visibility of the layer just written
+    }
 }
 
 // grind: thread t tests nonce = base + t; result = atomicMin over matching nonces.
@@ -85,6 +105,24 @@ int cm31_blake2s_commit_layer(uint32_t log_size, const uint32_t* prev_layer, con
     ProfScope prof(n_cols ? "merkle_leaf_layer" : "merkle_inner_layer", (4ull * n_cols + 32ull + (prev_layer ? 64ull : 0ull)) * n);
     merkle_layer_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream()>>>(
         log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, out_layer);
+    CM_LAUNCH_CHECK();
+    return 0;
+}
+
+int cm31_blake2s_commit_top(uint32_t top_log_size, const uint32_t* prev_layer, const uint32_t* const* cols,
+                            const uint32_t* col_start_host, uint32_t* const* out_layers) {
+    CM_REQUIRE(top_log_size <= 10, "commit_top: at most 2^10 nodes in the widest layer");
+    CM_REQUIRE(out_layers != nullptr && col_start_host != nullptr, "commit_top: null argument");
+    MerkleTopArgs args;
+    for (u32 l = 0; l <= top_log_size; l++) args.layer_out[l] = out_layers[l];
+    for (u32 l = 0; l <= top_log_size + 1; l++) args.col_start[l] = col_start_host[l];
+    size_t n_cols = col_start_host[top_log_size + 1];
+    DeviceTable dcols;
+    if (int e = dcols.upload(cols, n_cols * sizeof(void*))) return e;
+    uint64_t bytes = 0;
+    for (u32 l = 0; l <= top_log_size; l++) bytes += (4ull * (args.col_start[l + 1] - args.col_start[l]) + 96ull) << l;
+    ProfScope prof("merkle_top_layers", bytes);
+    merkle_top_kernel<<<1, 1u << top_log_size < 32 ? 32 : 1u << top_log_size, 0, stream()>>>(top_log_size, prev_layer, (const u32* const*)dcols.d, args);
     CM_LAUNCH_CHECK();
     return 0;
 }

@@ -82,6 +82,10 @@ __global__ void gather_u32_kernel(const u32* const* cols, size_t n_cols, const u
     size_t c = t / n_idx, q = t % n_idx;
     out[t] = cols[c][idx[q]];
 }
+__global__ void gather_words_kernel(const u32* const* srcs, const u32* src_id, const u32* word, size_t n, u32* out) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t < n) out[t] = srcs[src_id[t]][word[t]];
+}
 __global__ void gather_hash_kernel(const u32* layer, const u32* idx, size_t n_idx, u32* out) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t >= n_idx * 8) return;
@@ -209,6 +213,28 @@ int cm31_gather_u32(const uint32_t* const* cols, size_t n_cols, const uint32_t* 
                                                                             (const u32*)didx.d, n_idx, dout);
     CM_LAUNCH_CHECK();
     CM_CUDA(cudaMemcpyAsync(out_host, dout, total * 4, cudaMemcpyDeviceToHost, stream()));
+    CM_CUDA(cudaFreeAsync(dout, stream()));
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    return 0;
+}
+
+int cm31_gather_words(const uint32_t* const* srcs, size_t n_srcs, const uint32_t* src_id_host, const uint32_t* word_idx_host,
+                      size_t n, uint32_t* out_host) {
+    if (n == 0) return 0;
+    for (size_t k = 0; k < n; k++) CM_REQUIRE(src_id_host[k] < n_srcs, "gather_words: source id out of range");
+    DeviceTable dsrcs, dsid, dword;
+    if (int e = dsrcs.upload(srcs, n_srcs * sizeof(void*))) return e;
+    if (int e = dsid.upload(src_id_host, n * 4)) return e;
+    if (int e = dword.upload(word_idx_host, n * 4)) return e;
+    u32* dout = nullptr;
+    CM_CUDA(cudaMallocAsync(&dout, n * 4, stream()));
+    {
+        ProfScope prof("gather_words", 8ull * n);
+        gather_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>((const u32* const*)dsrcs.d, (const u32*)dsid.d,
+                                                                              (const u32*)dword.d, n, dout);
+    }
+    CM_LAUNCH_CHECK();
+    CM_CUDA(cudaMemcpyAsync(out_host, dout, n * 4, cudaMemcpyDeviceToHost, stream()));
     CM_CUDA(cudaFreeAsync(dout, stream()));
     CM_CUDA(cudaStreamSynchronize(stream()));
     return 0;

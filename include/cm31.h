@@ -47,6 +47,10 @@ int cm31_d2d(void* dst, const void* src, size_t bytes);
  * out_host[c * n_idx + q] = cols[c][idx_host[q]]   (S/prover/src/core/vcs/prover.rs:125-140) */
 int cm31_gather_u32(const uint32_t* const* cols, size_t n_cols, const uint32_t* idx_host, size_t n_idx,
                     uint32_t* out_host);
+/* every read of a whole proof's decommitment in one launch (4 trees + all FRI layers):
+ * out_host[k] = srcs[src_id_host[k]][word_idx_host[k]]; a hash node is 8 consecutive words */
+int cm31_gather_words(const uint32_t* const* srcs, size_t n_srcs, const uint32_t* src_id_host, const uint32_t* word_idx_host,
+                      size_t n, uint32_t* out_host);
 /* same for hash columns: out_host[q*8..] = layer[idx[q]] */
 int cm31_gather_hash(const uint32_t* layer, const uint32_t* idx_host, size_t n_idx, uint32_t* out_host);
 
@@ -83,6 +87,12 @@ int cm31_bit_reverse(uint32_t* col, uint32_t log_size);
  * prev_layer may be NULL (leaf layer). */
 int cm31_blake2s_commit_layer(uint32_t log_size, const uint32_t* prev_layer, const uint32_t* const* cols,
                               size_t n_cols, uint32_t* out_layer);
+
+/* Layers top_log_size .. 0 of MerkleProver::commit (vcs/prover.rs:52-64) in one launch (top_log_size <= 10):
+ * layer l hashes prev = layer l+1 (prev_layer for l = top_log_size, may be NULL) and the columns
+ * cols[col_start_host[l] .. col_start_host[l+1]) of 2^l words; out_layers[l] receives 2^l nodes. */
+int cm31_blake2s_commit_top(uint32_t top_log_size, const uint32_t* prev_layer, const uint32_t* const* cols,
+                            const uint32_t* col_start_host, uint32_t* const* out_layers);
 
 /* ------------------------------------------------------------------ AccumulationOps
  * S/prover/src/core/air/accumulation.rs:156-162 */

@@ -56,6 +56,20 @@ struct OracleBackend {
         for (size_t c = 0; c < cols.size(); c++)
             for (size_t q = 0; q < idx.size(); q++) out[c][q] = (*cols[c])[idx[q]].v;
     }
+    static std::vector<HashCol> commit_top_layers(u32 top_log, const HashCol* prev, const std::vector<std::vector<const Col*>>& cols_by_layer) {
+        std::vector<HashCol> out(top_log + 1);
+        for (int l = (int)top_log; l >= 0; l--) {
+            out[l] = orc::commit_on_layer((u32)l, prev, cols_by_layer[l]);
+            prev = &out[l];
+        }
+        return out;
+    }
+    static const u32* col_words(const Col& c) { return (const u32*)c.data(); }
+    static const u32* hash_words(const HashCol& c) { return (const u32*)c.data(); }
+    static void gather_words(const std::vector<const u32*>& srcs, const std::vector<u32>& src_id, const std::vector<u32>& word,
+                             std::vector<u32>& out) {
+        for (size_t k = 0; k < src_id.size(); k++) out[k] = srcs[src_id[k]][word[k]];
+    }
     static void gather_hashes(const HashCol& layer, const std::vector<u32>& idx, std::vector<cm31::Hash32>& out) {
         out.resize(idx.size());
         for (size_t q = 0; q < idx.size(); q++) memcpy(out[q].b, layer[idx[q]].b, 32);

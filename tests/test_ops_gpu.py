@@ -274,3 +274,32 @@ def test_gather(cm):
     got = cm.gather_u32(cols, idx)
     for c in range(3):
         assert got[c] == mat[c, idx].tolist()
+
+
+def test_gather_words(cm):
+    mat = orc.splitmix64(6, 4 * 256).reshape(4, 256)
+    cols = to_dev_cols(mat)
+    rng = np.random.default_rng(3)
+    sid = rng.integers(0, 4, 1000).tolist()
+    widx = rng.integers(0, 256, 1000).tolist()
+    got = cm.gather_words(cols, sid, widx)
+    assert got == [int(mat[s, w]) for s, w in zip(sid, widx)]
+
+
+@pytest.mark.parametrize("top,with_prev,col_layers", [(0, False, {0: 2}), (3, True, {}), (5, False, {5: 3, 4: 1, 2: 20}),
+                                                      (10, True, {10: 4, 7: 17, 0: 1}), (10, False, {10: 33})])
+def test_commit_top_layers_matches_layer_by_layer_oracle(cm, top, with_prev, col_layers):
+    # the fused top-of-tree launch == MerkleProver::commit's per-layer loop (vcs/prover.rs:52-64)
+    mats = {l: orc.splitmix64(0x70 + l, k << l).reshape(k, 1 << l) for l, k in col_layers.items()}
+    prev = None
+    if with_prev:
+        prev = (orc.splitmix64(0x99, (2 << top) * 8).astype(np.uint64) * 5 + 0x80000003).astype(np.uint32).reshape(2 << top, 8)
+    dprev = torch.from_numpy(prev.view(np.int32)).cuda() if prev is not None else None
+    dcols = {l: to_dev_cols(m) for l, m in mats.items()}
+    outs = [torch.empty((1 << l, 8), dtype=torch.int32, device="cuda") for l in range(top + 1)]
+    cm.blake2s_commit_top(top, dprev, [dcols.get(l, []) for l in range(top + 1)], outs)
+    cm.sync()
+    expect_prev = prev
+    for l in range(top, -1, -1):
+        expect_prev = orc.commit_on_layer(l, expect_prev, mats.get(l))
+        assert np.array_equal(host(outs[l]), expect_prev), f"layer {l}"
