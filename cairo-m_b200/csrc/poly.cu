@@ -447,6 +447,10 @@ static void plan_passes(u32 L, std::vector<Pass>& out) {
     }
 }
 
+// fft4.cu: four-columns-per-CTA passes for 2^12..2^24 points (returns 1 when it does not apply)
+template <bool INV>
+int run_fft4(const u32* const* src, u32* const* dst, size_t n_cols, u32 L, u32 log_in, const u32* tree, u32 M, u32 scale_last);
+
 template <bool INV>
 static int run_fft(const u32* const* src_host, u32* const* dst_host, size_t n_cols, u32 L, u32 log_in,
                    const cm31_twiddles* tw) {
@@ -467,11 +471,15 @@ static int run_fft(const u32* const* src_host, u32* const* dst_host, size_t n_co
         CM_LAUNCH_CHECK();
         return 0;
     }
-    std::vector<Pass> passes;
-    plan_passes(L, passes);
     const u32* tree = INV ? tw->itw : tw->tw;
     u32 scale_last = 1;
     if (INV) scale_last = m31_inv((u32)(((u64)1 << L) % P));
+    {
+        int e = run_fft4<INV>(src, dst, n_cols, L, log_in, tree, tw->log_size, scale_last);
+        if (e != 1) return e;
+    }
+    std::vector<Pass> passes;
+    plan_passes(L, passes);
     size_t np = passes.size();
     for (size_t i = 0; i < np; i++) {
         const Pass& ps = INV ? passes[i] : passes[np - 1 - i];
