@@ -43,8 +43,24 @@ def _run(cmd, log: Path | None = None):
     return res
 
 
+GEN_DIR = CSRC / "generated"
+GEN_TOOL_SRC = ROOT / "tools" / "gen_air_kernels.cpp"
+
+
+def generate_air_kernels(force: bool = False):
+    """AOT-specialised AIR kernels: build + run tools/gen_air_kernels.cpp -> csrc/generated/*.cu
+    (the generator only rewrites files whose content changed)."""
+    GEN_DIR.mkdir(exist_ok=True)
+    BUILD.mkdir(exist_ok=True)
+    tool = BUILD / "gen_air_kernels"
+    deps = [GEN_TOOL_SRC] + list((CSRC / "host").glob("*.hpp")) + list((CSRC / "air").glob("*.hpp")) + [CSRC / "field.cuh", CSRC / "circle.hpp"]
+    if force or not _newer(tool, deps):
+        _run(["g++", "-O1", "-std=c++17", "-I", str(CSRC), "-I", str(ROOT / "include"), str(GEN_TOOL_SRC), "-o", str(tool)])
+    _run([str(tool), str(GEN_DIR)])
+
+
 def cuda_sources():
-    return sorted(CSRC.glob("*.cu")) + sorted((CSRC / "host").glob("*.cu"))
+    return sorted(CSRC.glob("*.cu")) + sorted((CSRC / "host").glob("*.cu")) + sorted(GEN_DIR.glob("*.cu"))
 
 
 def headers():
@@ -55,6 +71,7 @@ def headers():
 
 def build_lib(force: bool = False) -> Path:
     BUILD.mkdir(exist_ok=True)
+    generate_air_kernels(force)
     srcs = cuda_sources()
     hdrs = headers()
     objs = []

@@ -8,6 +8,7 @@
 // One thread per row; every column access is a coalesced 4-byte-per-lane load; the program and
 // its constants are warp-uniform reads.  The register file lives in per-thread local memory
 // (hardware-interleaved, L1 resident), sized by the program's register allocation.
+#include "air_gen.cuh"
 #include "common.cuh"
 #include "host/air_expr.hpp"
 
@@ -119,12 +120,28 @@ __global__ void __launch_bounds__(128) air_program_kernel(const u32* const* __re
     }
 }
 
+static int g_air_mode = 0;  // 0 = AOT-specialised kernel when one exists, 1 = always the bytecode interpreter
+
 static int run_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* const* out_cols, size_t n_out, u32 row_log,
                        u32 trace_log, const uint64_t* code, size_t n_instr, u32 n_regs, const u32* consts, size_t n_consts,
                        const u32* denom_inv_host, size_t n_denom, uint32_t* const* acc4) {
     CM_REQUIRE(row_log <= 30, "air: too many rows");
     CM_REQUIRE(n_regs <= 2048, "air: program needs more than 2048 registers");
     CM_REQUIRE(trace_log <= row_log, "air: trace domain larger than the evaluation domain");
+    const GenEntry* gen = g_air_mode == 0 ? air_gen_lookup(air_code_hash(code, n_instr)) : nullptr;
+    if (gen) {
+        DeviceTable ddenom_gen;
+        if (acc4) {
+            CM_REQUIRE(n_denom == ((size_t)1 << (row_log - trace_log)), "air: wrong number of denominator inverses");
+            if (int e = ddenom_gen.upload(denom_inv_host, n_denom * 4)) return e;
+        }
+        GenLaunch gl{in_cols, n_in, out_cols, n_out, row_log, trace_log, consts, n_consts, (const u32*)ddenom_gen.d, acc4};
+        size_t rows = (size_t)1 << row_log;
+        ProfScope prof(acc4 ? "constraint_eval" : "air_program", acc4 ? 4ull * rows * n_in + 32ull * rows : 4ull * rows * (n_in + n_out));
+        if (int e = gen->launch(gl)) return e;
+        CM_LAUNCH_CHECK();
+        return 0;
+    }
     DeviceTable din, dout, dcode, dconsts, ddenom;
     if (int e = din.upload(in_cols, n_in * sizeof(void*))) return e;
     if (int e = dout.upload(out_cols, n_out * sizeof(void*))) return e;
@@ -271,6 +288,12 @@ __global__ void histogram_kernel(const u32* values, size_t n, u32* bins, u32 n_b
 using namespace cm31;
 
 extern "C" {
+
+int cm31_set_air_mode(int mode) {
+    CM_REQUIRE(mode == 0 || mode == 1, "set_air_mode: 0 (specialised kernels) or 1 (interpreter)");
+    g_air_mode = mode;
+    return 0;
+}
 
 int cm31_constraint_eval(const uint32_t* const* cols, size_t n_cols, uint32_t trace_log_size, uint32_t eval_log_size,
                          const uint64_t* code, size_t n_instr, uint32_t n_regs, const uint32_t* consts, size_t n_consts,

@@ -488,6 +488,7 @@ struct ClockUpdateEval : OpcodeEvalBase {
 struct RangeCheckEval : OpcodeEvalBase {
     int relation;
     static constexpr int N_TRACE_COLUMNS = 1;
+    static const char* name() { return "range_check"; }
     std::string column_id() const { return "range_check_" + std::to_string(log_size_); }
     template <class E>
     void evaluate(E& eval) const {

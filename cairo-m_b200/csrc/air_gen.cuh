@@ -1,0 +1,70 @@
+// Runtime side of the AOT-specialised AIR kernels (csrc/generated/*.cu, written by
+// tools/gen_air_kernels.cpp from the same captured AIR graphs that produce the bytecode).
+//
+// A generated kernel is the straight-line CUDA form of ONE bytecode program: one thread per row,
+// every SSA value in a register (nvcc allocates and schedules), column pointers and the constant /
+// parameter table passed BY VALUE as a __grid_constant__ kernel argument so they are constant-bank
+// operands.  It is selected at run time by the hash of the program's instruction words
+// (air_code_hash); programs without a generated kernel run on the bytecode interpreter (air.cu).
+#pragma once
+#include "common.cuh"
+
+namespace cm31 {
+
+struct GenLaunch {
+    const uint32_t* const* in_cols;  // host array of device pointers
+    size_t n_in;
+    uint32_t* const* out_cols;
+    size_t n_out;
+    u32 row_log, trace_log;
+    const u32* consts;  // host
+    size_t n_consts;
+    const u32* denom_inv_dev;  // device, or null
+    uint32_t* const* acc4;     // host array of 4 device pointers, or null
+};
+
+struct GenEntry {
+    uint64_t hash;
+    const char* name;
+    int (*launch)(const GenLaunch&);
+};
+
+// generated/air_registry.cu
+const GenEntry* air_gen_lookup(uint64_t hash);
+
+__device__ __forceinline__ u32 gen_offset_row(u32 row, u32 trace_log, u32 eval_log, int off) {
+    // core/utils.rs:74-90 offset_bit_reversed_circle_domain_index
+    u32 idx = bit_reverse(row, eval_log);
+    u32 half = 1u << (eval_log - 1);
+    int step = off * (int)(1u << (eval_log - trace_log - 1));
+    u32 mask = half - 1;
+    if (idx < half) idx = (u32)((int)idx + step) & mask;
+    else idx = ((u32)((int)(idx - half) - step) & mask) + half;
+    return bit_reverse(idx, eval_log);
+}
+
+__device__ __forceinline__ void gen_hist(u32* bins, u32 v) {
+    // equal values across the warp cost one atomic (lookups of a loop-shaped trace hit few bins)
+    const unsigned peers = __match_any_sync(__activemask(), v);
+    if ((threadIdx.x & 31u) == (u32)(__ffs(peers) - 1)) atomicAdd(bins + v, (u32)__popc(peers));
+}
+
+// QM31 product for the generated kernels.
+__device__ __forceinline__ QM31 g_qm_mul(QM31 x, QM31 y) { return qm_mul(x, y); }
+
+}  // namespace cm31
+
+// ---- vocabulary of the generated kernel bodies (a = the kernel's argument struct)
+#define ldcol(i) __ldg(a.in[i] + row)
+#define ldcol_off(i, off) __ldg(a.in[i] + cm31::gen_offset_row(row, a.trace_log, a.row_log, (off)))
+#define cw(s) (a.c[s])
+#define cq(s) cm31::qm_make(a.c[s], a.c[(s) + 1], a.c[(s) + 2], a.c[(s) + 3])
+#define st1(slot, f) a.out[slot][row] = (f)
+#define st4(slot, e)                 \
+    do {                             \
+        a.out[slot][row] = (e).a;    \
+        a.out[(slot) + 1][row] = (e).b; \
+        a.out[(slot) + 2][row] = (e).c; \
+        a.out[(slot) + 3][row] = (e).d; \
+    } while (0)
+#define hist(slot, f) cm31::gen_hist(a.out[slot], (f))

@@ -61,7 +61,22 @@ struct AirProgram {
     // host-filled parameter slots inside `consts` (each 4 words)
     std::vector<u32> param_slots;  // param id -> word offset in consts
     size_t n_mul_m31 = 0;          // algorithmic M31 multiplications per row (for ops/s reports)
+    // Same program as straight-line CUDA (filled when requested): the body of an AOT-specialised
+    // kernel (tools/gen_air_kernels.cpp -> csrc/generated/), keyed by `air_code_hash(code)`.
+    std::string cuda_body;
 };
+
+// FNV-1a over the instruction words: identifies a program independently of its parameter values
+// (all constants are read from the `consts` table at run time).
+inline uint64_t air_code_hash(const uint64_t* code, size_t n_instr) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n_instr; i++)
+        for (int b = 0; b < 8; b++) {
+            h ^= (code[i] >> (8 * b)) & 0xff;
+            h *= 1099511628211ull;
+        }
+    return h ^ (uint64_t)n_instr;
+}
 
 // ------------------------------------------------------------------ graph
 enum class NodeOp : uint8_t { Col, ConstF, ConstE, ParamE, AddF, SubF, MulF, NegF, AddE, SubE, MulE, NegE, MulEF, AddEF, SubEF, F2E, Combine4, InvE, InvF, ShrF, AndF, RowLt };
@@ -368,10 +383,38 @@ class ExprEvaluator : public LogupMixin<ExprEvaluator, FExpr, EFExpr> {
     EF ef_const(QM31 v) { return EF{this, g.conste(v)}; }
     EF ef_one() { return ef_const(qm_one()); }
     EF ef_zero() { return ef_const(qm_zero()); }
-    EF ef_add(EF a, EF b) { return EF{this, g.bin(NodeOp::AddE, true, a.id, b.id)}; }
-    EF ef_sub(EF a, EF b) { return EF{this, g.bin(NodeOp::SubE, true, a.id, b.id)}; }
-    EF ef_mul(EF a, EF b) { return EF{this, g.bin(NodeOp::MulE, true, a.id, b.id)}; }
-    EF ef_neg(EF a) { return EF{this, g.un(NodeOp::NegE, true, a.id)}; }
+    // Base-field operands embedded with ef() keep their cheap form: E*ef(f) is 4 multiplications,
+    // not 16 (exact field identities, so every evaluator computes the same values).
+    bool is_f2e(EF a, int* f = nullptr) const {
+        if (g.nodes[a.id].op != NodeOp::F2E) return false;
+        if (f) *f = g.nodes[a.id].a;
+        return true;
+    }
+    bool is_zero_e(EF a) const { return g.nodes[a.id].op == NodeOp::ConstE && qm_is_zero(g.nodes[a.id].econst); }
+    EF ef_add(EF a, EF b) {
+        int f;
+        if (is_zero_e(a)) return b;
+        if (is_zero_e(b)) return a;
+        if (is_f2e(b, &f)) return EF{this, g.bin(NodeOp::AddEF, true, a.id, f)};
+        if (is_f2e(a, &f)) return EF{this, g.bin(NodeOp::AddEF, true, b.id, f)};
+        return EF{this, g.bin(NodeOp::AddE, true, a.id, b.id)};
+    }
+    EF ef_sub(EF a, EF b) {
+        int f;
+        if (is_f2e(b, &f)) return EF{this, g.bin(NodeOp::SubEF, true, a.id, f)};
+        return EF{this, g.bin(NodeOp::SubE, true, a.id, b.id)};
+    }
+    EF ef_mul(EF a, EF b) {
+        int f;
+        if (is_f2e(b, &f)) return EF{this, g.bin(NodeOp::MulEF, true, a.id, f)};
+        if (is_f2e(a, &f)) return EF{this, g.bin(NodeOp::MulEF, true, b.id, f)};
+        return EF{this, g.bin(NodeOp::MulE, true, a.id, b.id)};
+    }
+    EF ef_neg(EF a) {
+        int f;
+        if (is_f2e(a, &f)) return EF{this, g.un(NodeOp::F2E, true, g.negf(f))};
+        return EF{this, g.un(NodeOp::NegE, true, a.id)};
+    }
     EF ef_mul_f(EF a, F b) { return EF{this, g.bin(NodeOp::MulEF, true, a.id, b.id)}; }
     EF ef_add_f(EF a, F b) { return EF{this, g.bin(NodeOp::AddEF, true, a.id, b.id)}; }
     EF cumsum_shift() { return EF{this, g.parame(PARAM_CUMSUM_SHIFT)}; }
@@ -503,8 +546,13 @@ class ProgramBuilder {
     // Extra QM31 parameters (beyond the evaluator's) can be appended by the caller: constraint
     // programs use params [n_eval_params + k] for the k-th random-coefficient power.
     template <class ColIndexFn>
-    static AirProgram compile(const Graph& g, const std::vector<ProgramOutput>& outputs, size_t n_params, ColIndexFn col_index) {
+    static AirProgram compile(const Graph& g, const std::vector<ProgramOutput>& outputs, size_t n_params, ColIndexFn col_index,
+                              bool emit_cuda = false) {
         AirProgram prog;
+        std::string& src = prog.cuda_body;
+        auto F = [](int id) { return "f" + std::to_string(id); };
+        auto E = [](int id) { return "e" + std::to_string(id); };
+        auto U = [](u32 v) { return std::to_string(v) + "u"; };
         size_t n = g.nodes.size();
         // liveness
         std::vector<char> live(n, 0);
@@ -578,8 +626,16 @@ class ProgramBuilder {
             const Node& nd = g.nodes[id];
             u32 r = alloc(nd.ext);
             reg[id] = r;
+            const int nid = (int)id;
+            auto fdef = [&](const std::string& rhs) { if (emit_cuda) src += "    const u32 " + F(nid) + " = " + rhs + ";\n"; };
+            auto edef = [&](const std::string& rhs) { if (emit_cuda) src += "    const QM31 " + E(nid) + " = " + rhs + ";\n"; };
             switch (nd.op) {
-                case NodeOp::Col: emit(OP_LOAD, r, (u32)col_index(nd.interaction, nd.col), (u32)(nd.offset & 0xfffff)); break;
+                case NodeOp::Col: {
+                    u32 ci = (u32)col_index(nd.interaction, nd.col);
+                    emit(OP_LOAD, r, ci, (u32)(nd.offset & 0xfffff));
+                    fdef(nd.offset == 0 ? "ldcol(" + U(ci) + ")" : "ldcol_off(" + U(ci) + ", " + std::to_string(nd.offset) + ")");
+                    break;
+                }
                 case NodeOp::ConstF: {
                     auto it = fconst_slot.find(nd.fconst);
                     u32 s;
@@ -589,6 +645,7 @@ class ProgramBuilder {
                         fconst_slot[nd.fconst] = s;
                     } else s = it->second;
                     emit(OP_CONSTF, r, s, 0);
+                    fdef("cw(" + U(s) + ")");
                     break;
                 }
                 case NodeOp::ConstE: {
@@ -601,29 +658,34 @@ class ProgramBuilder {
                         econst_slot[key] = s;
                     } else s = it->second;
                     emit(OP_CONSTE, r, s, 0);
+                    edef("cq(" + U(s) + ")");
                     break;
                 }
-                case NodeOp::ParamE: emit(OP_CONSTE, r, prog.param_slots.at(nd.param), 0); break;
-                case NodeOp::AddF: emit(OP_ADD, r, reg[nd.a], reg[nd.b]); break;
-                case NodeOp::SubF: emit(OP_SUB, r, reg[nd.a], reg[nd.b]); break;
-                case NodeOp::MulF: emit(OP_MUL, r, reg[nd.a], reg[nd.b]); prog.n_mul_m31 += 1; break;
-                case NodeOp::NegF: emit(OP_NEG, r, reg[nd.a], 0); break;
-                case NodeOp::AddE: emit(OP_EADD, r, reg[nd.a], reg[nd.b]); break;
-                case NodeOp::SubE: emit(OP_ESUB, r, reg[nd.a], reg[nd.b]); break;
-                case NodeOp::MulE: emit(OP_EMUL, r, reg[nd.a], reg[nd.b]); prog.n_mul_m31 += 16; break;
-                case NodeOp::NegE: emit(OP_ENEG, r, reg[nd.a], 0); break;
-                case NodeOp::MulEF: emit(OP_EMULF, r, reg[nd.a], reg[nd.b]); prog.n_mul_m31 += 4; break;
-                case NodeOp::AddEF: emit(OP_EADDF, r, reg[nd.a], reg[nd.b]); break;
-                case NodeOp::SubEF: emit(OP_ESUBF, r, reg[nd.a], reg[nd.b]); break;
-                case NodeOp::F2E: emit(OP_F2E, r, reg[nd.a], 0); break;
-                case NodeOp::InvE: emit(OP_EINV, r, reg[nd.a], 0); prog.n_mul_m31 += 100; break;
-                case NodeOp::InvF: emit(OP_INV, r, reg[nd.a], 0); prog.n_mul_m31 += 37; break;
-                case NodeOp::ShrF: emit(OP_SHR, r, reg[nd.a], nd.fconst); break;
-                case NodeOp::AndF: emit(OP_AND, r, reg[nd.a], nd.fconst); break;
+                case NodeOp::ParamE:
+                    emit(OP_CONSTE, r, prog.param_slots.at(nd.param), 0);
+                    edef("cq(" + U(prog.param_slots.at(nd.param)) + ")");
+                    break;
+                case NodeOp::AddF: emit(OP_ADD, r, reg[nd.a], reg[nd.b]); fdef("m31_add(" + F(nd.a) + ", " + F(nd.b) + ")"); break;
+                case NodeOp::SubF: emit(OP_SUB, r, reg[nd.a], reg[nd.b]); fdef("m31_sub(" + F(nd.a) + ", " + F(nd.b) + ")"); break;
+                case NodeOp::MulF: emit(OP_MUL, r, reg[nd.a], reg[nd.b]); prog.n_mul_m31 += 1; fdef("m31_mul(" + F(nd.a) + ", " + F(nd.b) + ")"); break;
+                case NodeOp::NegF: emit(OP_NEG, r, reg[nd.a], 0); fdef("m31_neg(" + F(nd.a) + ")"); break;
+                case NodeOp::AddE: emit(OP_EADD, r, reg[nd.a], reg[nd.b]); edef("qm_add(" + E(nd.a) + ", " + E(nd.b) + ")"); break;
+                case NodeOp::SubE: emit(OP_ESUB, r, reg[nd.a], reg[nd.b]); edef("qm_sub(" + E(nd.a) + ", " + E(nd.b) + ")"); break;
+                case NodeOp::MulE: emit(OP_EMUL, r, reg[nd.a], reg[nd.b]); prog.n_mul_m31 += 16; edef("g_qm_mul(" + E(nd.a) + ", " + E(nd.b) + ")"); break;
+                case NodeOp::NegE: emit(OP_ENEG, r, reg[nd.a], 0); edef("qm_neg(" + E(nd.a) + ")"); break;
+                case NodeOp::MulEF: emit(OP_EMULF, r, reg[nd.a], reg[nd.b]); prog.n_mul_m31 += 4; edef("qm_mul_m31(" + E(nd.a) + ", " + F(nd.b) + ")"); break;
+                case NodeOp::AddEF: emit(OP_EADDF, r, reg[nd.a], reg[nd.b]); edef("qm_add_m31(" + E(nd.a) + ", " + F(nd.b) + ")"); break;
+                case NodeOp::SubEF: emit(OP_ESUBF, r, reg[nd.a], reg[nd.b]); edef("qm_sub_m31(" + E(nd.a) + ", " + F(nd.b) + ")"); break;
+                case NodeOp::F2E: emit(OP_F2E, r, reg[nd.a], 0); edef("qm_from_m31(" + F(nd.a) + ")"); break;
+                case NodeOp::InvE: emit(OP_EINV, r, reg[nd.a], 0); prog.n_mul_m31 += 100; edef("qm_inv(" + E(nd.a) + ")"); break;
+                case NodeOp::InvF: emit(OP_INV, r, reg[nd.a], 0); prog.n_mul_m31 += 37; fdef("m31_inv(" + F(nd.a) + ")"); break;
+                case NodeOp::ShrF: emit(OP_SHR, r, reg[nd.a], nd.fconst); fdef("(" + F(nd.a) + " >> " + U(nd.fconst) + ")"); break;
+                case NodeOp::AndF: emit(OP_AND, r, reg[nd.a], nd.fconst); fdef("(" + F(nd.a) + " & " + U(nd.fconst) + ")"); break;
                 case NodeOp::RowLt: {
                     u32 sl = (u32)prog.consts.size();
                     prog.consts.push_back(nd.fconst);
                     emit(OP_ROWLT, r, sl, 0);
+                    fdef("(row < cw(" + U(sl) + ") ? 1u : 0u)");
                     break;
                 }
                 case NodeOp::Combine4:
@@ -631,6 +693,7 @@ class ProgramBuilder {
                     emit(OP_MOV, r + 1, reg[nd.b], 0);
                     emit(OP_MOV, r + 2, reg[nd.c], 0);
                     emit(OP_MOV, r + 3, reg[nd.d], 0);
+                    edef("qm_make(" + F(nd.a) + ", " + F(nd.b) + ", " + F(nd.c) + ", " + F(nd.d) + ")");
                     break;
             }
             for (size_t oi : outs_at[id]) {
@@ -639,10 +702,22 @@ class ProgramBuilder {
                     case ProgramOutput::ConstraintSum:
                         emit(nd.ext ? OP_CONSTRAINT_E : OP_CONSTRAINT_F, 0, r, prog.param_slots.at(o.slot));
                         prog.n_mul_m31 += nd.ext ? 16 : 4;
+                        if (emit_cuda)
+                            src += nd.ext ? "    acc = qm_add(acc, g_qm_mul(cq(" + U(prog.param_slots.at(o.slot)) + "), " + E(nid) + "));\n"
+                                          : "    acc = qm_add(acc, qm_mul_m31(cq(" + U(prog.param_slots.at(o.slot)) + "), " + F(nid) + "));\n";
                         break;
-                    case ProgramOutput::StoreE: emit(OP_STORE_E, 0, r, (u32)o.slot); break;
-                    case ProgramOutput::StoreF: emit(OP_STORE_F, 0, r, (u32)o.slot); break;
-                    case ProgramOutput::Hist: emit(OP_HIST, 0, r, (u32)o.slot); break;
+                    case ProgramOutput::StoreE:
+                        emit(OP_STORE_E, 0, r, (u32)o.slot);
+                        if (emit_cuda) src += "    st4(" + U((u32)o.slot) + ", " + E(nid) + ");\n";
+                        break;
+                    case ProgramOutput::StoreF:
+                        emit(OP_STORE_F, 0, r, (u32)o.slot);
+                        if (emit_cuda) src += "    st1(" + U((u32)o.slot) + ", " + F(nid) + ");\n";
+                        break;
+                    case ProgramOutput::Hist:
+                        emit(OP_HIST, 0, r, (u32)o.slot);
+                        if (emit_cuda) src += "    hist(" + U((u32)o.slot) + ", " + F(nid) + ");\n";
+                        break;
                 }
             }
             for (int d : dying[id]) {

@@ -19,28 +19,6 @@ int cm31_iota(uint32_t* col, size_t n);
 
 namespace cm31 {
 
-// Trace-fill program builder: `write_trace<T>` of a component captured into the AIR bytecode.
-struct TraceProgramBuilder {
-    typedef FExpr F;
-    ExprEvaluator ev;
-    u32 n_real;
-    std::vector<ProgramOutput> outs;
-    explicit TraceProgramBuilder(u32 n) : n_real(n) {}
-    F in(int i) { return ev.input(i); }
-    F enabler() { return ev.row_lt(n_real); }
-    F f_const(u32 v) { return ev.f_const(v); }
-    F f_inv(F a) { return ev.f_inv(a); }
-    F f_shr(F a, u32 k) { return ev.f_shr(a, k); }
-    F f_and(F a, u32 m) { return ev.f_and(a, m); }
-    void out(int col, F v) { outs.push_back(ProgramOutput{ProgramOutput::StoreF, v.id, col}); }
-    AirProgram compile() {
-        return ProgramBuilder::compile(ev.g, outs, 0, [](int interaction, int col) -> size_t {
-            if (interaction != 3) throw std::logic_error("trace program reads a non-input column");
-            return (size_t)col;
-        });
-    }
-};
-
 struct CudaAirImpl {
     typedef CudaBackend B;
     typedef DeviceCol Col;

@@ -44,6 +44,73 @@ struct TraceLocationAllocator {
     }
 };
 
+// ------------------------------------------------------------------ the programs of one captured AIR
+// (shared by the prover and by tools/gen_air_kernels.cpp, which emits each of them as an
+// AOT-specialised CUDA kernel).  Column index convention of every program: preprocessed columns
+// first (first-use order), then the trace columns, then the interaction columns.
+inline AirProgram build_constraint_program(const ExprEvaluator& ev, bool emit_cuda = false) {
+    std::vector<ProgramOutput> outs;
+    size_t n_eval_params = ev.params.size();
+    for (size_t k = 0; k < ev.constraints.size(); k++)
+        outs.push_back(ProgramOutput{ProgramOutput::ConstraintSum, ev.constraints[k], (int)(n_eval_params + k)});
+    size_t n_pre = ev.mask_offsets[0].size(), n_tr = ev.mask_offsets[1].size();
+    return ProgramBuilder::compile(ev.g, outs, n_eval_params + ev.constraints.size(), [&](int interaction, int col) -> size_t {
+        if (interaction == 0) return (size_t)col;
+        if (interaction == 1) return n_pre + (size_t)col;
+        return n_pre + n_tr + (size_t)col;
+    }, emit_cuda);
+}
+// cumulative logup columns col_b = col_{b-1} + num_b/den_b  (logup.rs:123-320); extends the graph
+inline AirProgram build_logup_program(ExprEvaluator& e, bool emit_cuda = false) {
+    std::vector<ProgramOutput> outs;
+    EFExpr cum = e.ef_zero();
+    for (size_t b = 0; b < e.batch_fracs.size(); b++) {
+        EFExpr term = e.ef_mul(e.batch_fracs[b].num, e.ef_inv(e.batch_fracs[b].den));
+        cum = b == 0 ? term : e.ef_add(cum, term);
+        outs.push_back(ProgramOutput{ProgramOutput::StoreE, cum.id, (int)(4 * b)});
+    }
+    size_t n_pre = e.mask_offsets[0].size();
+    return ProgramBuilder::compile(e.g, outs, e.params.size(), [&](int interaction, int col) -> size_t {
+        if (interaction == 0) return (size_t)col;
+        if (interaction == 1) return n_pre + (size_t)col;
+        throw std::logic_error("logup program reads an interaction column");
+    }, emit_cuda);
+}
+// multiplicity histogram of the values looked up in `relation` (empty program if none)
+inline AirProgram build_lookup_program(const ExprEvaluator& ev, int relation, bool emit_cuda = false) {
+    std::vector<ProgramOutput> outs;
+    for (auto& u : ev.logup_uses)
+        if (u.relation == relation) outs.push_back(ProgramOutput{ProgramOutput::Hist, u.values.at(0), 0});
+    if (outs.empty()) return AirProgram();
+    return ProgramBuilder::compile(ev.g, outs, ev.params.size(), [&](int interaction, int col) -> size_t {
+        if (interaction == 1) return (size_t)col;
+        throw std::logic_error("lookup emission reads a non-trace column");
+    }, emit_cuda);
+}
+
+// Trace-fill program builder: `write_trace<T>` of a component captured into the AIR bytecode
+// (replaces the per-opcode row loops, crates/prover/src/components/opcodes/*.rs write_trace).
+struct TraceProgramBuilder {
+    typedef FExpr F;
+    ExprEvaluator ev;
+    u32 n_real;
+    std::vector<ProgramOutput> outs;
+    explicit TraceProgramBuilder(u32 n) : n_real(n) {}
+    F in(int i) { return ev.input(i); }
+    F enabler() { return ev.row_lt(n_real); }
+    F f_const(u32 v) { return ev.f_const(v); }
+    F f_inv(F a) { return ev.f_inv(a); }
+    F f_shr(F a, u32 k) { return ev.f_shr(a, k); }
+    F f_and(F a, u32 m) { return ev.f_and(a, m); }
+    void out(int col, F v) { outs.push_back(ProgramOutput{ProgramOutput::StoreF, v.id, col}); }
+    AirProgram compile(bool emit_cuda = false) {
+        return ProgramBuilder::compile(ev.g, outs, 0, [](int interaction, int col) -> size_t {
+            if (interaction != 3) throw std::logic_error("trace program reads a non-input column");
+            return (size_t)col;
+        }, emit_cuda);
+    }
+};
+
 template <class B, class Eval>
 class FrameworkComponent : public ComponentProver<B> {
    public:
@@ -176,21 +243,7 @@ class FrameworkComponent : public ComponentProver<B> {
         if (n_batches == 0) return out;
         if (trace_cols.size() != n_trace_columns()) throw std::logic_error("gen_interaction_trace: wrong number of trace columns");
         ExprEvaluator& e = const_cast<ExprEvaluator&>(ev);
-        if (logup_program_.code.empty()) {
-            std::vector<ProgramOutput> outs;
-            EFExpr cum = e.ef_zero();
-            for (size_t b = 0; b < n_batches; b++) {
-                EFExpr term = e.ef_mul(e.batch_fracs[b].num, e.ef_inv(e.batch_fracs[b].den));
-                cum = b == 0 ? term : e.ef_add(cum, term);
-                outs.push_back(ProgramOutput{ProgramOutput::StoreE, cum.id, (int)(4 * b)});
-            }
-            size_t n_pre = ev.mask_offsets[0].size();
-            logup_program_ = ProgramBuilder::compile(e.g, outs, e.params.size(), [&](int interaction, int col) -> size_t {
-                if (interaction == 0) return (size_t)col;
-                if (interaction == 1) return n_pre + (size_t)col;
-                throw std::logic_error("logup program reads an interaction column");
-            });
-        }
+        if (logup_program_.code.empty()) logup_program_ = build_logup_program(e);
         std::vector<const Col*> in;
         for (auto& id : ev.preprocessed_ids) in.push_back(preprocessed(id));
         in.insert(in.end(), trace_cols.begin(), trace_cols.end());
@@ -213,14 +266,8 @@ class FrameworkComponent : public ComponentProver<B> {
     // Emits every value looked up in `relation` (first tuple element) into a multiplicity histogram
     // (crates/prover/src/components/opcodes/mod.rs:83-105 providers + range_check_macro.rs:72-84).
     void emit_lookups(int relation, const std::vector<const Col*>& trace_cols, Col& bins) const {
-        std::vector<ProgramOutput> outs;
-        for (auto& u : ev.logup_uses)
-            if (u.relation == relation) outs.push_back(ProgramOutput{ProgramOutput::Hist, u.values.at(0), 0});
-        if (outs.empty()) return;
-        AirProgram prog = ProgramBuilder::compile(ev.g, outs, ev.params.size(), [&](int interaction, int col) -> size_t {
-            if (interaction == 1) return (size_t)col;
-            throw std::logic_error("lookup emission reads a non-trace column");
-        });
+        AirProgram prog = build_lookup_program(ev, relation);
+        if (prog.code.empty()) return;
         std::vector<Col*> outp = {&bins};
         B::air_program(trace_cols, outp, log_size(), prog);
     }
@@ -238,18 +285,7 @@ class FrameworkComponent : public ComponentProver<B> {
             prog.consts[s + 3] = params[i].d;
         }
     }
-    void build_constraint_program() {
-        std::vector<ProgramOutput> outs;
-        size_t n_eval_params = ev.params.size();
-        for (size_t k = 0; k < ev.constraints.size(); k++)
-            outs.push_back(ProgramOutput{ProgramOutput::ConstraintSum, ev.constraints[k], (int)(n_eval_params + k)});
-        size_t n_pre = ev.mask_offsets[0].size(), n_tr = ev.mask_offsets[1].size();
-        constraint_program_ = ProgramBuilder::compile(ev.g, outs, n_eval_params + ev.constraints.size(), [&](int interaction, int col) -> size_t {
-            if (interaction == 0) return (size_t)col;
-            if (interaction == 1) return n_pre + (size_t)col;
-            return n_pre + n_tr + (size_t)col;
-        });
-    }
+    void build_constraint_program() { constraint_program_ = cm31::build_constraint_program(ev); }
     AirProgram constraint_program_;
     AirProgram logup_program_;
 };

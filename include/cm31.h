@@ -144,6 +144,11 @@ int cm31_constraint_eval(const uint32_t* const* cols, size_t n_cols, uint32_t tr
                          const uint32_t* consts, size_t n_consts, const uint32_t* denom_inv_host,
                          uint32_t* const acc4[4]);
 
+/* Programs of cairo-m's fixed component set have AOT-specialised kernels (csrc/generated/, selected
+ * by a hash of `code`); any other program runs on the bytecode interpreter.  mode 1 forces the
+ * interpreter (parity tests run both). */
+int cm31_set_air_mode(int mode);
+
 /* ------------------------------------------------------------------ witness generation helpers
  * Generic AIR program over the 2^log_size TRACE rows (same bytecode as cm31_constraint_eval):
  *  - LogupTraceGenerator (S/constraint_framework/src/logup.rs:123-320): the logup program stores,

@@ -48,3 +48,20 @@ def test_fib_2_20_steps_verifies_with_clock_updates(cm):
     assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
     residual, info = ch.oracle_logup_residual(n, got)
     assert residual == (0, 0, 0, 0)
+
+
+def test_generated_air_kernels_match_the_bytecode_interpreter(cm):
+    # every AIR program of the proof runs once on the AOT-specialised kernels (csrc/generated/)
+    # and once on the interpreter (csrc/air.cu): same proof bytes
+    n = 300
+    inp = ch.GpuFibInput(cm, n)
+    try:
+        cm.check(cm.lib().cm31_set_air_mode(1))
+        interp, _ = inp.prove()
+        cm.check(cm.lib().cm31_set_air_mode(0))
+        gen, _ = inp.prove()
+    finally:
+        cm.lib().cm31_set_air_mode(0)
+        inp.close()
+    assert gen == interp
+    assert ch.oracle_cairo_verify(gen) == 0, ch.orc.last_error()
