@@ -143,13 +143,54 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------ multi-rank plumbing
+def init_dist(world: int, local_rank: int, use_cuda: bool):
+    """One process per GPU (torchrun env).  NCCL on GPUs; gloo when there is no device (CPU tests)."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    if use_cuda:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist.init_process_group("gloo")
+
+
+def max_over_ranks(ms: float, world: int, use_cuda: bool) -> float:
+    """Every multi-GPU time is the MAX over ranks of the device-measured time."""
+    if world <= 1:
+        return ms
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], device="cuda" if use_cuda else "cpu", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def aggregate_value(world: int, vm_steps_per_proof: int, proofs_per_rank: int, ms: float) -> float:
+    """Whole-job VM steps per second: every rank proved `proofs_per_rank` segments in `ms`."""
+    return world * vm_steps_per_proof * proofs_per_rank / (ms / 1e3)
+
+
+def dist_selftest(rank: int, world: int):
+    """CPU/gloo check of the N>1 plumbing (tests/test_bench_dist.py): rank r reports (r+1)*10 ms."""
+    import torch.distributed as dist
+    init_dist(world, 0, use_cuda=False)
+    ms = max_over_ranks(10.0 * (rank + 1), world, use_cuda=False)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        print(json.dumps({"selftest": True, "n_gpus": world, "ms": ms, "value": aggregate_value(world, 1000, 2, ms)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------ CUDA arm
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    init_dist(world, local_rank, use_cuda=True)
     cm = importlib.import_module("cairo-m_b200")
     lib = cm.lib()
     cm.check(lib.cm31_set_device(local_rank))
@@ -199,10 +240,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             cm.check(lib.cm31_profile_report(rb, C.c_size_t(1 << 16), C.byref(ln)))
             report = json.loads(rb.value.decode())
         cm.check(lib.cm31_profile_enable(0))
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = max_over_ranks(ms, world, use_cuda=True)
         return ms, clocks, int(launches.value), report, [p / k_steps for p in phases]
 
     # ---- device-resident: input staged in HBM once
@@ -210,13 +248,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     for _ in range(args.warmup):
         prove()
     ms, clocks, launches, report, phases = timed_region(args.steps, True)
-    value = world * vm_steps * args.steps / (ms / 1e3)
+    value = aggregate_value(world, vm_steps, args.steps, ms)
 
     # ---- end to end: host (pinned) input copied in, proof bytes copied out, every step
     cm.check(lib.cm31_input_release_device(h))
     prove()
     e2e_ms, _, _, _, _ = timed_region(args.steps, False)
-    e2e_value = world * vm_steps * args.steps / (e2e_ms / 1e3)
+    e2e_value = aggregate_value(world, vm_steps, args.steps, e2e_ms)
     proof_bytes = int(proof_len.value)
     cm.check(lib.cm31_input_destroy(h))
 
@@ -287,10 +325,14 @@ def main():
     ap.add_argument("--log-steps", type=int, default=22, help="log2 of VM steps per proof (BASELINE metric: 2^22)")
     ap.add_argument("--cpu-sample-log", type=int, default=17, help="log2 VM steps of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dist-selftest", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.dist_selftest:
+        dist_selftest(rank, world)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

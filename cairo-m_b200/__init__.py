@@ -195,3 +195,14 @@ def blake2s_commit_top(top_log: int, prev_layer, cols_by_layer, out_layers) -> N
     start.append(len(flat))
     prev = C.c_void_p(prev_layer.data_ptr()) if prev_layer is not None else C.c_void_p()
     check(lib().cm31_blake2s_commit_top(C.c_uint32(top_log), prev, _ptr_array(flat), _u32_array(start), _ptr_array(out_layers)))
+
+
+def gather_runs(srcs, src_id, word_idx, counts):
+    """Request k copies counts[k] consecutive words from srcs[src_id[k]][word_idx[k]:]; returns the flat result."""
+    off = [0]
+    for c in counts:
+        off.append(off[-1] + c)
+    out = (C.c_uint32 * max(1, off[-1]))()
+    check(lib().cm31_gather_runs(_ptr_array(srcs), C.c_size_t(len(srcs)), _u32_array(src_id), _u32_array(word_idx), _u32_array(off),
+                                 C.c_size_t(len(src_id)), out))
+    return list(out)[: off[-1]]

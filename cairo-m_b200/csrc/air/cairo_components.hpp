@@ -489,6 +489,7 @@ struct RangeCheckEval : OpcodeEvalBase {
     int relation;
     static constexpr int N_TRACE_COLUMNS = 1;
     static const char* name() { return "range_check"; }
+    long cache_tag() const { return relation; }  // the captured graph names the relation's parameters
     std::string column_id() const { return "range_check_" + std::to_string(log_size_); }
     template <class E>
     void evaluate(E& eval) const {

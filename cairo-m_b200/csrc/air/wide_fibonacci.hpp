@@ -13,6 +13,7 @@ struct WideFibonacciEval {
     u32 n_cols;
     u32 log_size() const { return log_n_rows; }
     u32 max_constraint_log_degree_bound() const { return log_n_rows + 1; }
+    long cache_tag() const { return n_cols; }
     template <class E>
     void evaluate(E& eval) const {
         auto a = eval.next_trace_mask();

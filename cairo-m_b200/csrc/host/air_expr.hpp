@@ -60,6 +60,7 @@ struct AirProgram {
     u32 n_regs = 0;
     // host-filled parameter slots inside `consts` (each 4 words)
     std::vector<u32> param_slots;  // param id -> word offset in consts
+    std::vector<u32> rowlt_slots;  // consts words holding a row bound (Enabler): patched per trace
     size_t n_mul_m31 = 0;          // algorithmic M31 multiplications per row (for ops/s reports)
     // Same program as straight-line CUDA (filled when requested): the body of an AOT-specialised
     // kernel (tools/gen_air_kernels.cpp -> csrc/generated/), keyed by `air_code_hash(code)`.
@@ -684,6 +685,7 @@ class ProgramBuilder {
                 case NodeOp::RowLt: {
                     u32 sl = (u32)prog.consts.size();
                     prog.consts.push_back(nd.fconst);
+                    prog.rowlt_slots.push_back(sl);
                     emit(OP_ROWLT, r, sl, 0);
                     fdef("(row < cw(" + U(sl) + ") ? 1u : 0u)");
                     break;

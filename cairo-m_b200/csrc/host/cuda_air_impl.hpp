@@ -4,6 +4,7 @@
 // (crates/prover/src/components/opcodes/*.rs), `LogupTraceGenerator`, the multiplicity histograms.
 #pragma once
 #include <chrono>
+#include <map>
 
 #include "../../../include/cm31.h"
 #include "../cairo/vm.hpp"
@@ -70,9 +71,17 @@ struct CudaAirImpl {
     }
     template <class Eval>
     static std::vector<CircleEvaluation<B>> write_trace(const Eval& eval, const std::vector<Col>& inputs, u32 n_real) {
-        TraceProgramBuilder tb(n_real);
-        eval.write_trace(tb);
-        AirProgram prog = tb.compile();
+        // the trace-fill program of an AIR is captured once; only the enabler's row bound changes
+        static std::map<long, AirProgram> cache;
+        long tag = (long)air_cache_tag(eval, 0);
+        auto it = cache.find(tag);
+        if (it == cache.end()) {
+            TraceProgramBuilder tb(n_real);
+            eval.write_trace(tb);
+            it = cache.emplace(tag, tb.compile()).first;
+        }
+        AirProgram prog = it->second;
+        for (u32 slot : prog.rowlt_slots) prog.consts[slot] = n_real;
         std::vector<CircleEvaluation<B>> out(Eval::N_TRACE_COLUMNS);
         std::vector<Col*> outp;
         for (auto& c : out) {

@@ -147,9 +147,9 @@ struct CudaBackend {
     }
     static const u32* col_words(const Col& c) { return c.ptr(); }
     static const u32* hash_words(const HashCol& c) { return c.ptr(); }
-    static void gather_words(const std::vector<const u32*>& srcs, const std::vector<u32>& src_id, const std::vector<u32>& word,
-                             std::vector<u32>& out) {
-        cm_check(cm31_gather_words(srcs.data(), srcs.size(), src_id.data(), word.data(), src_id.size(), out.data()));
+    static void gather_runs(const std::vector<const u32*>& srcs, const std::vector<u32>& src_id, const std::vector<u32>& word,
+                            const std::vector<u32>& out_off, std::vector<u32>& out) {
+        cm_check(cm31_gather_runs(srcs.data(), srcs.size(), src_id.data(), word.data(), out_off.data(), src_id.size(), out.data()));
     }
     static void gather_hashes(const HashCol& layer, const std::vector<u32>& idx, std::vector<Hash32>& out) {
         out.resize(idx.size());

@@ -8,6 +8,8 @@
 // generation and lookup emission all run as bytecode programs on the backend.
 #pragma once
 #include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
 
 #include "air_expr.hpp"
@@ -111,22 +113,49 @@ struct TraceProgramBuilder {
     }
 };
 
+// One symbolic capture per AIR shape, shared by every component instance of every proof: the graph
+// and its programs depend on the Eval type (and its `cache_tag()`, e.g. the relation of a range
+// check or the width of wide_fibonacci), never on log_size or on drawn values.
+struct CapturedAir {
+    ExprEvaluator ev;
+    AirProgram constraint_program, logup_program;
+    std::map<int, AirProgram> lookup_programs;  // relation -> histogram program (built on demand)
+};
+template <class Eval>
+auto air_cache_tag(const Eval& e, int) -> decltype(e.cache_tag()) { return e.cache_tag(); }
+template <class Eval>
+long air_cache_tag(const Eval&, long) { return 0; }
+
+template <class Eval>
+std::shared_ptr<CapturedAir> capture_air(const Eval& eval) {
+    static std::map<long, std::shared_ptr<CapturedAir>> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    long tag = (long)air_cache_tag(eval, 0);
+    auto it = cache.find(tag);
+    if (it != cache.end()) return it->second;
+    auto cap = std::make_shared<CapturedAir>();
+    eval.evaluate(cap->ev);
+    if (!cap->ev.logup_finalized) throw std::logic_error("LogupAtRow was not finalized");
+    cap->constraint_program = build_constraint_program(cap->ev);
+    if (!cap->ev.batch_fracs.empty()) cap->logup_program = build_logup_program(cap->ev);
+    cache[tag] = cap;
+    return cap;
+}
+
 template <class B, class Eval>
 class FrameworkComponent : public ComponentProver<B> {
    public:
     typedef typename B::Col Col;
     Eval eval;
-    ExprEvaluator ev;  // captured AIR
+    std::shared_ptr<CapturedAir> captured;
+    const ExprEvaluator& ev;  // captured AIR (shared, immutable after capture)
     const RelationSet* relations = nullptr;
     std::vector<TreeSubspan> trace_locations;
     std::vector<size_t> preprocessed_indices;
     QM31 claimed_sum = {0, 0, 0, 0};
 
-    FrameworkComponent(Eval e, const RelationSet* rel) : eval(std::move(e)), relations(rel) {
-        eval.evaluate(ev);
-        if (!ev.logup_finalized) throw std::logic_error("LogupAtRow was not finalized");
-        build_constraint_program();
-    }
+    FrameworkComponent(Eval e, const RelationSet* rel) : eval(std::move(e)), captured(capture_air(eval)), ev(captured->ev), relations(rel) {}
     // FrameworkComponent::new (component.rs:139-180): trace locations in component creation order.
     void allocate(TraceLocationAllocator& alloc) {
         std::vector<size_t> n_cols(3, 0);
@@ -226,7 +255,7 @@ class FrameworkComponent : public ComponentProver<B> {
         auto accum = accumulator.columns(eval_log, n_constraints());
         std::vector<QM31>& coeffs = accum.first;
         std::reverse(coeffs.begin(), coeffs.end());
-        AirProgram prog = constraint_program_;
+        AirProgram prog = captured->constraint_program;
         std::vector<QM31> params = eval_params();
         params.insert(params.end(), coeffs.begin(), coeffs.end());
         fill_params(prog, params);
@@ -242,8 +271,6 @@ class FrameworkComponent : public ComponentProver<B> {
         std::vector<CircleEvaluation<B>> out;
         if (n_batches == 0) return out;
         if (trace_cols.size() != n_trace_columns()) throw std::logic_error("gen_interaction_trace: wrong number of trace columns");
-        ExprEvaluator& e = const_cast<ExprEvaluator&>(ev);
-        if (logup_program_.code.empty()) logup_program_ = build_logup_program(e);
         std::vector<const Col*> in;
         for (auto& id : ev.preprocessed_ids) in.push_back(preprocessed(id));
         in.insert(in.end(), trace_cols.begin(), trace_cols.end());
@@ -255,7 +282,7 @@ class FrameworkComponent : public ComponentProver<B> {
             c.log_size = log_size();
             outp.push_back(&c.values);
         }
-        AirProgram prog = logup_program_;
+        AirProgram prog = captured->logup_program;
         fill_params(prog, eval_params());  // cumsum shift is unused by this program
         B::air_program(in, outp, log_size(), prog);
         std::array<Col*, 4> last = {outp[4 * n_batches - 4], outp[4 * n_batches - 3], outp[4 * n_batches - 2], outp[4 * n_batches - 1]};
@@ -266,13 +293,15 @@ class FrameworkComponent : public ComponentProver<B> {
     // Emits every value looked up in `relation` (first tuple element) into a multiplicity histogram
     // (crates/prover/src/components/opcodes/mod.rs:83-105 providers + range_check_macro.rs:72-84).
     void emit_lookups(int relation, const std::vector<const Col*>& trace_cols, Col& bins) const {
-        AirProgram prog = build_lookup_program(ev, relation);
+        auto it = captured->lookup_programs.find(relation);
+        if (it == captured->lookup_programs.end()) it = captured->lookup_programs.emplace(relation, build_lookup_program(ev, relation)).first;
+        const AirProgram& prog = it->second;
         if (prog.code.empty()) return;
         std::vector<Col*> outp = {&bins};
         B::air_program(trace_cols, outp, log_size(), prog);
     }
 
-    const AirProgram& constraint_program() const { return constraint_program_; }
+    const AirProgram& constraint_program() const { return captured->constraint_program; }
 
    private:
     static void fill_params(AirProgram& prog, const std::vector<QM31>& params) {
@@ -285,9 +314,6 @@ class FrameworkComponent : public ComponentProver<B> {
             prog.consts[s + 3] = params[i].d;
         }
     }
-    void build_constraint_program() { constraint_program_ = cm31::build_constraint_program(ev); }
-    AirProgram constraint_program_;
-    AirProgram logup_program_;
 };
 
 }  // namespace cm31

@@ -240,29 +240,34 @@ inline u32 ilog2(size_t n) {
 // and receives slot numbers; ONE batched device gather then serves them all.
 template <class B>
 struct GatherQueue {
+    // a request = `count` consecutive words (1 for a column element, 8 for a hash node) of one source
     std::vector<const u32*> srcs;
     std::map<const u32*, u32> src_index;
-    std::vector<u32> src_id, word, results;
-    size_t request(const u32* base, size_t word_idx) {
+    std::vector<u32> src_id, word, out_off;  // per request; results of request k start at out_off[k]
+    std::vector<u32> results;
+    size_t n_words = 0;
+    u32 source(const u32* base) {
         auto it = src_index.find(base);
-        u32 id;
-        if (it == src_index.end()) {
-            id = (u32)srcs.size();
-            srcs.push_back(base);
-            src_index[base] = id;
-        } else id = it->second;
-        src_id.push_back(id);
-        word.push_back((u32)word_idx);
-        return src_id.size() - 1;
+        if (it != src_index.end()) return it->second;
+        u32 id = (u32)srcs.size();
+        srcs.push_back(base);
+        src_index[base] = id;
+        return id;
     }
-    size_t request_hash(const u32* layer, size_t node) {  // 8 consecutive slots
-        size_t first = src_id.size();
-        for (size_t k = 0; k < 8; k++) request(layer, node * 8 + k);
-        return first;
+    size_t request_run(u32 source_id, size_t first_word, u32 count) {  // returns the slot of the first word
+        src_id.push_back(source_id);
+        word.push_back((u32)first_word);
+        out_off.push_back((u32)n_words);
+        size_t slot = n_words;
+        n_words += count;
+        return slot;
     }
+    size_t request(u32 source_id, size_t word_idx) { return request_run(source_id, word_idx, 1); }
+    size_t request_hash(u32 source_id, size_t node) { return request_run(source_id, node * 8, 8); }
     void flush() {
-        results.resize(src_id.size());
-        if (!src_id.empty()) B::gather_words(srcs, src_id, word, results);
+        results.resize(n_words);
+        out_off.push_back((u32)n_words);
+        if (n_words) B::gather_runs(srcs, src_id, word, out_off, results);
     }
     Hash32 hash_at(size_t slot) const {
         Hash32 h;
@@ -347,6 +352,9 @@ struct MerkleProver {
             const std::vector<size_t>& layer_column_queries = qit == queries_per_log_size.end() ? empty : qit->second;
             size_t pi = 0, ci = 0;
             std::vector<size_t> layer_total_queries;
+            std::vector<u32> col_ids;
+            for (const Col* c : layer_columns) col_ids.push_back(queue.source(B::col_words(*c)));
+            const u32 prev_id = previous_layer_hashes ? queue.source(B::hash_words(*previous_layer_hashes)) : 0;
             while (pi < last_layer_queries.size() || ci < layer_column_queries.size()) {
                 size_t node_index;
                 bool has_p = pi < last_layer_queries.size(), has_c = ci < layer_column_queries.size();
@@ -354,16 +362,15 @@ struct MerkleProver {
                 else if (has_p) node_index = last_layer_queries[pi] / 2;
                 else node_index = layer_column_queries[ci];
                 if (previous_layer_hashes) {
-                    const u32* prev = B::hash_words(*previous_layer_hashes);
                     if (pi < last_layer_queries.size() && last_layer_queries[pi] == 2 * node_index) pi++;
-                    else pd.hash_witness_slots.push_back(queue.request_hash(prev, 2 * node_index));
+                    else pd.hash_witness_slots.push_back(queue.request_hash(prev_id, 2 * node_index));
                     if (pi < last_layer_queries.size() && last_layer_queries[pi] == 2 * node_index + 1) pi++;
-                    else pd.hash_witness_slots.push_back(queue.request_hash(prev, 2 * node_index + 1));
+                    else pd.hash_witness_slots.push_back(queue.request_hash(prev_id, 2 * node_index + 1));
                 }
                 bool queried = ci < layer_column_queries.size() && layer_column_queries[ci] == node_index;
                 if (queried) ci++;
                 std::vector<size_t>& dst = queried ? pd.queried_slots : pd.column_witness_slots;
-                for (const Col* c : layer_columns) dst.push_back(queue.request(B::col_words(*c), node_index));
+                for (u32 id : col_ids) dst.push_back(queue.request(id, node_index));
                 layer_total_queries.push_back(node_index);
             }
             last_layer_queries = layer_total_queries;
@@ -627,6 +634,8 @@ struct FriProver {
     // compute_decommitment_positions_and_witness_evals (fri.rs:1002-1036); reads are queued
     static void positions_and_witness(GatherQueue<B>& queue, const std::array<Col, 4>& column, const std::vector<size_t>& query_positions,
                                       u32 fold_step, std::vector<size_t>& decommitment_positions, std::vector<size_t>& witness_slots) {
+        u32 ids[4];
+        for (int k = 0; k < 4; k++) ids[k] = queue.source(B::col_words(column[k]));
         size_t i = 0;
         while (i < query_positions.size()) {
             size_t j = i;
@@ -639,8 +648,8 @@ struct FriProver {
                     qi++;
                     continue;
                 }
-                size_t first = queue.request(B::col_words(column[0]), position);
-                for (int k = 1; k < 4; k++) queue.request(B::col_words(column[k]), position);
+                size_t first = queue.request(ids[0], position);
+                for (int k = 1; k < 4; k++) queue.request(ids[k], position);
                 witness_slots.push_back(first);  // 4 consecutive slots = one QM31
             }
             i = j;

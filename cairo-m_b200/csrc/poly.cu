@@ -300,121 +300,101 @@ __global__ void bit_reverse_kernel(u32* col, u32 log_size) {
 }
 
 // --------------------------------------------------------------------------- eval_at_point
-// f(P) = fold(coeffs, [pi^{L-2}(x), ..., pi(x), x, y])  (cpu/circle.rs:73-87, poly/utils.rs:44-55):
-// coefficient j weighs prod over set bits i of j of factor_i, factor_0 = y, factor_1 = x,
-// factor_i = pi^{i-1}(x).  Stage 1: each CTA folds a chunk of 2^CH coefficients to one QM31;
-// stage 2: one CTA per polynomial folds the partials with the remaining factors.
-constexpr u32 EAP_CHUNK_LOG = 11;  // 256 threads x 8 coefficients
+// f(P) = fold(coeffs, [pi^{L-2}(x), ..., pi(x), x, y])  (cpu/circle.rs:73-87, poly/utils.rs:44-55)
+//      = sum_j c_j * prod_{bits i of j} factor_i,   factor_0 = y, factor_1 = x, factor_i = pi^{i-1}(x).
+// Split j = (chunk | r | t): t = bits 0-7 (thread), r = bits 8-14 (per-thread loop), chunk = bits 15+.
+//   stage 1 (one CTA per 2^15-coefficient chunk):  S_t = sum_r c[chunk, r, t] * mid[r]  is a dot product
+//     of BASE-field coefficients with QM31 constants: 4 u64 multiply-accumulates per coefficient
+//     (folded every 4 terms), coalesced 1 KB row reads;  partial = sum_t lo[t] * S_t  (one QM31
+//     product per thread + a block reduction).
+//   stage 2 (one CTA per polynomial): f(P) = sum_chunk hi[chunk] * partial[chunk].
+// The monomial tables lo[256], mid[128], hi[<=512] per sample point are built on the host.
+constexpr u32 EAP_LO_BITS = 8, EAP_MID_BITS = 7, EAP_CHUNK_LOG = EAP_LO_BITS + EAP_MID_BITS;
 constexpr u32 EAP_MAX_LEVELS = 32;
+constexpr u32 EAP_HI_MAX = 1024;                                            // polynomials up to 2^25 coefficients
+constexpr u32 EAP_TABLE_STRIDE = (256 + 128 + EAP_HI_MAX) * 4;              // words per point
 
 struct EapJob {
     const u32* coeffs;
     u32 log_size;
-    u32 point;        // index into the factor table
+    u32 point;        // index into the monomial tables
     u32 partial_off;  // offset (in QM31s) of this poly's partials
     u32 first_chunk;  // index of this poly's first chunk in the flattened chunk list
 };
 
-__device__ __forceinline__ QM31 ld_qm(const u32* p) { return qm_make(p[0], p[1], p[2], p[3]); }
+__device__ __forceinline__ QM31 ld_qm(const u32* p) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    return qm_make(v.x, v.y, v.z, v.w);
+}
+__device__ __forceinline__ u64 eap_fold64(u64 x) { return (x & P) + (x >> 31); }
+
+__device__ __forceinline__ QM31 block_sum_qm(QM31 v, QM31* sh) {
+    const u32 t = threadIdx.x;
+    sh[t] = v;
+    __syncthreads();
+    for (u32 stride = 128; stride > 0; stride >>= 1) {
+        if (t < stride) sh[t] = qm_add(sh[t], sh[t + stride]);
+        __syncthreads();
+    }
+    return sh[0];
+}
 
 __global__ void __launch_bounds__(256) eap_stage1_kernel(const EapJob* __restrict__ jobs, const u32* __restrict__ chunk_job,
-                                                          const u32* __restrict__ factors, u32* __restrict__ partials) {
+                                                          const u32* __restrict__ tables, u32* __restrict__ partials) {
     __shared__ QM31 sh[256];
     const u32 chunk = blockIdx.x;
     const EapJob job = jobs[chunk_job[chunk]];
     const u32 local_chunk = chunk - job.first_chunk;
-    const u32 ch_log = min(job.log_size, EAP_CHUNK_LOG);
-    const u32 n = 1u << ch_log;
-    const u32* c = job.coeffs + ((size_t)local_chunk << ch_log);
-    const u32* f = factors + (size_t)job.point * EAP_MAX_LEVELS * 4;
-    // each thread folds 8 consecutive coefficients (levels 0..2)
-    const u32 per = 8;
-    u32 t = threadIdx.x;
-    QM31 acc = qm_zero();
-    bool active = t * per < n;
-    if (active) {
-        u32 m = min(per, n);  // n may be < 8 for tiny polys
-        u32 v[8];
-        for (u32 i = 0; i < 8; i++) v[i] = i < m ? __ldg(c + t * per + i) : 0u;
-        QM31 f0 = ld_qm(f), f1 = ld_qm(f + 4), f2 = ld_qm(f + 8);
-        // level 0: c0 + c1*y
-        QM31 a0 = qm_add_m31(qm_mul_m31(f0, v[1]), v[0]);
-        QM31 a1 = qm_add_m31(qm_mul_m31(f0, v[3]), v[2]);
-        QM31 a2 = qm_add_m31(qm_mul_m31(f0, v[5]), v[4]);
-        QM31 a3 = qm_add_m31(qm_mul_m31(f0, v[7]), v[6]);
-        if (m == 1) a0 = qm_from_m31(v[0]);
-        QM31 b0 = a0, b1 = a2;
-        if (m > 2) {
-            b0 = qm_add(a0, qm_mul(a1, f1));
-            b1 = qm_add(a2, qm_mul(a3, f1));
+    const u32 L = job.log_size;
+    const u32 lo_bits = min(L, EAP_LO_BITS);
+    const u32 mid_bits = L > EAP_LO_BITS ? min(L - EAP_LO_BITS, EAP_MID_BITS) : 0;
+    const u32* c = job.coeffs + ((size_t)local_chunk << EAP_CHUNK_LOG);
+    const u32* tab = tables + (size_t)job.point * EAP_TABLE_STRIDE;
+    const u32* mid = tab + 256 * 4;
+    const u32 t = threadIdx.x;
+    QM31 v = qm_zero();
+    if (t < (1u << lo_bits)) {
+        u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        const u32 n_r = 1u << mid_bits;
+        for (u32 r0 = 0; r0 < n_r; r0 += 4) {
+#pragma unroll
+            for (u32 j = 0; j < 4; j++) {
+                const u32 r = r0 + j;
+                if (r < n_r) {
+                    const u64 f = __ldg(c + ((size_t)r << EAP_LO_BITS) + t);
+                    const uint4 m = __ldg(reinterpret_cast<const uint4*>(mid) + r);
+                    a0 += f * m.x;
+                    a1 += f * m.y;
+                    a2 += f * m.z;
+                    a3 += f * m.w;
+                }
+            }
+            a0 = eap_fold64(a0);
+            a1 = eap_fold64(a1);
+            a2 = eap_fold64(a2);
+            a3 = eap_fold64(a3);
         }
-        acc = b0;
-        if (m > 4) acc = qm_add(b0, qm_mul(b1, f2));
+        QM31 s = qm_make(m31_reduce64(a0), m31_reduce64(a1), m31_reduce64(a2), m31_reduce64(a3));
+        v = qm_mul(ld_qm(tab + t * 4), s);
     }
-    sh[t] = acc;
-    __syncthreads();
-    // tree over threads: level 3.. ch_log-1
-    u32 nthr = n > per ? n / per : 1;
-    u32 level = 3;
-    for (u32 stride = 1; stride < nthr; stride <<= 1, level++) {
-        if ((t & (2 * stride - 1)) == 0 && t + stride < nthr) {
-            QM31 fl = ld_qm(f + level * 4);
-            sh[t] = qm_add(sh[t], qm_mul(sh[t + stride], fl));
-        }
-        __syncthreads();
-    }
+    QM31 r = block_sum_qm(v, sh);
     if (t == 0) {
         u32* o = partials + ((size_t)job.partial_off + local_chunk) * 4;
-        QM31 r = sh[0];
         o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d;
     }
 }
 
-__global__ void __launch_bounds__(256) eap_stage2_kernel(const EapJob* __restrict__ jobs, const u32* __restrict__ factors,
+__global__ void __launch_bounds__(256) eap_stage2_kernel(const EapJob* __restrict__ jobs, const u32* __restrict__ tables,
                                                           const u32* __restrict__ partials, u32* __restrict__ out) {
     __shared__ QM31 sh[256];
     const EapJob job = jobs[blockIdx.x];
-    const u32 ch_log = min(job.log_size, EAP_CHUNK_LOG);
-    const u32 n_part = 1u << (job.log_size - ch_log);
-    const u32* f = factors + (size_t)job.point * EAP_MAX_LEVELS * 4;
+    const u32 n_part = job.log_size > EAP_CHUNK_LOG ? 1u << (job.log_size - EAP_CHUNK_LOG) : 1u;
+    const u32* hi = tables + (size_t)job.point * EAP_TABLE_STRIDE + (256 + 128) * 4;
     const u32* p = partials + (size_t)job.partial_off * 4;
-    u32 t = threadIdx.x;
-    // n_part can exceed 256: each thread first folds a contiguous run of 2^e partials serially.
-    u32 e = 0;
-    while ((n_part >> e) > 256) e++;
-    u32 run = 1u << e;
-    QM31 acc = qm_zero();
-    u32 nthr = n_part >> e;
-    if (t < nthr) {
-        // serial fold of `run` consecutive partials with levels ch_log .. ch_log+e-1 (Horner-free,
-        // done as an in-register binary tree by recursion depth via explicit stack of size e+1)
-        QM31 stack[24];
-        u32 sp = 0;
-        for (u32 i = 0; i < run; i++) {
-            QM31 v = ld_qm(p + ((size_t)t * run + i) * 4);
-            u32 lvl = 0, idx = i;
-            while (idx & 1) {  // merge with the left sibling waiting on the stack
-                QM31 fl = ld_qm(f + (ch_log + lvl) * 4);
-                v = qm_add(stack[--sp], qm_mul(v, fl));
-                idx >>= 1;
-                lvl++;
-            }
-            stack[sp++] = v;
-        }
-        acc = stack[0];
-    }
-    sh[t] = acc;
-    __syncthreads();
-    u32 level = ch_log + e;
-    for (u32 stride = 1; stride < nthr; stride <<= 1, level++) {
-        if ((t & (2 * stride - 1)) == 0 && t + stride < nthr) {
-            QM31 fl = ld_qm(f + level * 4);
-            sh[t] = qm_add(sh[t], qm_mul(sh[t + stride], fl));
-        }
-        __syncthreads();
-    }
-    if (t == 0) {
-        QM31 r = sh[0];
+    QM31 v = qm_zero();
+    for (u32 i = threadIdx.x; i < n_part; i += 256) v = qm_add(v, qm_mul(ld_qm(hi + i * 4), ld_qm(p + (size_t)i * 4)));
+    QM31 r = block_sum_qm(v, sh);
+    if (threadIdx.x == 0) {
         u32* o = out + (size_t)blockIdx.x * 4;
         o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d;
     }
@@ -568,25 +548,44 @@ int cm31_eval_at_point_batch(const uint32_t* const* coeffs, const uint32_t* log_
                              const uint32_t* points_host, size_t n_points, const uint32_t* point_idx_host,
                              uint32_t* out_host) {
     if (n_polys == 0) return 0;
-    // factor table: per point, factor_0 = y, factor_1 = x, factor_i = pi^{i-1}(x)
-    std::vector<u32> factors(n_points * EAP_MAX_LEVELS * 4, 0);
+    // monomial tables per point: lo[t] over factors 0..7, mid[r] over 8..14, hi[k] over 15..
+    u32 max_log = 0;
+    for (size_t i = 0; i < n_polys; i++) max_log = std::max(max_log, log_sizes_host[i]);
+    CM_REQUIRE(max_log <= EAP_CHUNK_LOG + 10, "eval_at_point: polynomial too large");
+    const u32 n_hi = max_log > EAP_CHUNK_LOG ? 1u << (max_log - EAP_CHUNK_LOG) : 1u;
+    std::vector<u32> factors(n_points * EAP_TABLE_STRIDE, 0);
     for (size_t k = 0; k < n_points; k++) {
         const u32* pt = points_host + k * 8;
         QM31 x = qm_make(pt[0], pt[1], pt[2], pt[3]);
         QM31 y = qm_make(pt[4], pt[5], pt[6], pt[7]);
-        u32* f = &factors[k * EAP_MAX_LEVELS * 4];
-        f[0] = y.a; f[1] = y.b; f[2] = y.c; f[3] = y.d;
+        QM31 fac[EAP_MAX_LEVELS];
+        fac[0] = y;
         for (u32 i = 1; i < EAP_MAX_LEVELS; i++) {
-            f[i * 4 + 0] = x.a; f[i * 4 + 1] = x.b; f[i * 4 + 2] = x.c; f[i * 4 + 3] = x.d;
+            fac[i] = x;
             x = qm_double_x(x);
         }
+        u32* tab = &factors[k * EAP_TABLE_STRIDE];
+        auto fill = [&](u32* dst, u32 count, u32 first_factor) {
+            // dst[j] = prod over set bits b of j of fac[first_factor + b]; dst[j] from dst[j without top bit]
+            std::vector<QM31> m(count);
+            m[0] = qm_one();
+            for (u32 j = 1; j < count; j++) {
+                u32 top = 31 - __builtin_clz(j);
+                m[j] = qm_mul(m[j & ~(1u << top)], fac[first_factor + top]);
+            }
+            for (u32 j = 0; j < count; j++) {
+                dst[4 * j] = m[j].a; dst[4 * j + 1] = m[j].b; dst[4 * j + 2] = m[j].c; dst[4 * j + 3] = m[j].d;
+            }
+        };
+        fill(tab, 256, 0);
+        fill(tab + 256 * 4, 128, EAP_LO_BITS);
+        fill(tab + (256 + 128) * 4, n_hi, EAP_CHUNK_LOG);
     }
     std::vector<EapJob> jobs(n_polys);
     std::vector<u32> chunk_job;
     u32 part_off = 0;
     for (size_t i = 0; i < n_polys; i++) {
         u32 L = log_sizes_host[i];
-        CM_REQUIRE(L < EAP_MAX_LEVELS, "eval_at_point: polynomial too large");
         CM_REQUIRE(point_idx_host[i] < n_points, "eval_at_point: point index out of range");
         u32 ch_log = L < EAP_CHUNK_LOG ? L : EAP_CHUNK_LOG;
         u32 n_chunks = 1u << (L - ch_log);

@@ -61,12 +61,35 @@ void prof_end() {
     cudaEventRecord(g_prof.back().b, stream());
 }
 
+// Small host tables (pointer arrays, bytecode, constants) go through a page-locked staging ring so
+// the H2D copy is a true async DMA (a pageable source costs a driver-side staging copy + ~10 us per
+// call, which dominated the gaps between short kernels).  A slot is reused only after the ring
+// wraps, at which point the stream is synchronised.
+static uint8_t* g_stage = nullptr;
+static size_t g_stage_cap = 0, g_stage_pos = 0;
+constexpr size_t STAGE_BYTES = 16u << 20;
+
 int DeviceTable::upload(const void* host, size_t bytes) {
     release();
     if (int e = ensure_pool()) return e;
     CM_CUDA(cudaMallocAsync(&d, bytes == 0 ? 4 : bytes, stream()));
-    // pageable source: the runtime stages the bytes before returning, so `host` may be reused.
-    if (bytes != 0) CM_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, stream()));
+    if (bytes == 0) return 0;
+    if (bytes > STAGE_BYTES / 4) {  // large: plain copy (the runtime stages pageable sources itself)
+        CM_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, stream()));
+        return 0;
+    }
+    if (!g_stage) {
+        CM_CUDA(cudaHostAlloc((void**)&g_stage, STAGE_BYTES, cudaHostAllocDefault));
+        g_stage_cap = STAGE_BYTES;
+    }
+    size_t need = (bytes + 63) & ~(size_t)63;
+    if (g_stage_pos + need > g_stage_cap) {
+        CM_CUDA(cudaStreamSynchronize(stream()));
+        g_stage_pos = 0;
+    }
+    memcpy(g_stage + g_stage_pos, host, bytes);
+    CM_CUDA(cudaMemcpyAsync(d, g_stage + g_stage_pos, bytes, cudaMemcpyHostToDevice, stream()));
+    g_stage_pos += need;
     return 0;
 }
 void DeviceTable::release() {
@@ -85,6 +108,13 @@ __global__ void gather_u32_kernel(const u32* const* cols, size_t n_cols, const u
 __global__ void gather_words_kernel(const u32* const* srcs, const u32* src_id, const u32* word, size_t n, u32* out) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t < n) out[t] = srcs[src_id[t]][word[t]];
+}
+__global__ void gather_runs_kernel(const u32* const* srcs, const u32* src_id, const u32* word, const u32* out_off, size_t n, u32* out) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const u32* s = srcs[src_id[t]] + word[t];
+    u32 o = out_off[t], cnt = out_off[t + 1] - o;
+    for (u32 j = 0; j < cnt; j++) out[o + j] = s[j];
 }
 __global__ void gather_hash_kernel(const u32* layer, const u32* idx, size_t n_idx, u32* out) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -170,6 +200,25 @@ int cm31_profile_report(char* buf, size_t cap, size_t* len) {
     return 0;
 }
 
+// CSV "kernel,start_ms,dur_ms" of every bracketed launch since the last reset (start relative to the first one):
+// the gaps between rows are host/driver time (uploads, allocations, synchronisations, transcript).
+int cm31_profile_trace(char* buf, size_t cap, size_t* len) {
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    std::string s;
+    for (ProfRec& r : g_prof) {
+        float t0 = 0, d = 0;
+        CM_CUDA(cudaEventElapsedTime(&t0, g_prof[0].a, r.a));
+        CM_CUDA(cudaEventElapsedTime(&d, r.a, r.b));
+        char line[160];
+        snprintf(line, sizeof line, "%s,%.4f,%.4f\n", r.name, t0, d);
+        s += line;
+    }
+    if (len) *len = s.size();
+    CM_REQUIRE(buf == nullptr || s.size() + 1 <= cap, "profile_trace: buffer too small");
+    if (buf) memcpy(buf, s.c_str(), s.size() + 1);
+    return 0;
+}
+
 int cm31_malloc(void** out, size_t bytes) {
     CM_REQUIRE(out != nullptr, "malloc: null out");
     if (int e = ensure_pool()) return e;
@@ -235,6 +284,30 @@ int cm31_gather_words(const uint32_t* const* srcs, size_t n_srcs, const uint32_t
     }
     CM_LAUNCH_CHECK();
     CM_CUDA(cudaMemcpyAsync(out_host, dout, n * 4, cudaMemcpyDeviceToHost, stream()));
+    CM_CUDA(cudaFreeAsync(dout, stream()));
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    return 0;
+}
+
+int cm31_gather_runs(const uint32_t* const* srcs, size_t n_srcs, const uint32_t* src_id_host, const uint32_t* word_idx_host,
+                     const uint32_t* out_off_host, size_t n, uint32_t* out_host) {
+    if (n == 0) return 0;
+    for (size_t k = 0; k < n; k++) CM_REQUIRE(src_id_host[k] < n_srcs && out_off_host[k] <= out_off_host[k + 1], "gather_runs: bad request");
+    size_t total = out_off_host[n];
+    DeviceTable dsrcs, dsid, dword, doff;
+    if (int e = dsrcs.upload(srcs, n_srcs * sizeof(void*))) return e;
+    if (int e = dsid.upload(src_id_host, n * 4)) return e;
+    if (int e = dword.upload(word_idx_host, n * 4)) return e;
+    if (int e = doff.upload(out_off_host, (n + 1) * 4)) return e;
+    u32* dout = nullptr;
+    CM_CUDA(cudaMallocAsync(&dout, std::max<size_t>(4, total * 4), stream()));
+    {
+        ProfScope prof("gather_runs", 8ull * total);
+        gather_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>((const u32* const*)dsrcs.d, (const u32*)dsid.d,
+                                                                             (const u32*)dword.d, (const u32*)doff.d, n, dout);
+    }
+    CM_LAUNCH_CHECK();
+    CM_CUDA(cudaMemcpyAsync(out_host, dout, total * 4, cudaMemcpyDeviceToHost, stream()));
     CM_CUDA(cudaFreeAsync(dout, stream()));
     CM_CUDA(cudaStreamSynchronize(stream()));
     return 0;

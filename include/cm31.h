@@ -51,6 +51,11 @@ int cm31_gather_u32(const uint32_t* const* cols, size_t n_cols, const uint32_t* 
  * out_host[k] = srcs[src_id_host[k]][word_idx_host[k]]; a hash node is 8 consecutive words */
 int cm31_gather_words(const uint32_t* const* srcs, size_t n_srcs, const uint32_t* src_id_host, const uint32_t* word_idx_host,
                       size_t n, uint32_t* out_host);
+/* run form: request k copies out_off_host[k+1]-out_off_host[k] consecutive words starting at
+ * srcs[src_id_host[k]][word_idx_host[k]] to out_host[out_off_host[k]..] (1 word = a column element,
+ * 8 words = a hash node); out_off_host has n+1 entries */
+int cm31_gather_runs(const uint32_t* const* srcs, size_t n_srcs, const uint32_t* src_id_host, const uint32_t* word_idx_host,
+                     const uint32_t* out_off_host, size_t n, uint32_t* out_host);
 /* same for hash columns: out_host[q*8..] = layer[idx[q]] */
 int cm31_gather_hash(const uint32_t* layer, const uint32_t* idx_host, size_t n_idx, uint32_t* out_host);
 
@@ -196,6 +201,7 @@ int cm31_profile_enable(int on);
 int cm31_profile_reset(void);
 int cm31_profile_launches(uint64_t* out); /* kernels launched since the last reset (always counted) */
 int cm31_profile_report(char* buf, size_t cap, size_t* len);
+int cm31_profile_trace(char* buf, size_t cap, size_t* len); /* CSV: kernel,start_ms,dur_ms per launch */
 
 #ifdef __cplusplus
 }

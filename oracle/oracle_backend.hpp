@@ -66,9 +66,10 @@ struct OracleBackend {
     }
     static const u32* col_words(const Col& c) { return (const u32*)c.data(); }
     static const u32* hash_words(const HashCol& c) { return (const u32*)c.data(); }
-    static void gather_words(const std::vector<const u32*>& srcs, const std::vector<u32>& src_id, const std::vector<u32>& word,
-                             std::vector<u32>& out) {
-        for (size_t k = 0; k < src_id.size(); k++) out[k] = srcs[src_id[k]][word[k]];
+    static void gather_runs(const std::vector<const u32*>& srcs, const std::vector<u32>& src_id, const std::vector<u32>& word,
+                            const std::vector<u32>& out_off, std::vector<u32>& out) {
+        for (size_t k = 0; k < src_id.size(); k++)
+            for (u32 j = 0; j < out_off[k + 1] - out_off[k]; j++) out[out_off[k] + j] = srcs[src_id[k]][word[k] + j];
     }
     static void gather_hashes(const HashCol& layer, const std::vector<u32>& idx, std::vector<cm31::Hash32>& out) {
         out.resize(idx.size());

@@ -304,3 +304,15 @@ def test_commit_top_layers_matches_layer_by_layer_oracle(cm, top, with_prev, col
     for l in range(top, -1, -1):
         expect_prev = orc.commit_on_layer(l, expect_prev, mats.get(l))
         assert np.array_equal(host(outs[l]), expect_prev), f"layer {l}"
+
+
+def test_gather_runs(cm):
+    mat = orc.splitmix64(8, 3 * 512).reshape(3, 512)
+    cols = to_dev_cols(mat)
+    rng = np.random.default_rng(4)
+    sid = rng.integers(0, 3, 300).tolist()
+    counts = rng.choice([1, 8], 300).tolist()
+    widx = [int(rng.integers(0, 512 - c + 1)) for c in counts]
+    got = cm.gather_runs(cols, sid, widx, counts)
+    want = [int(v) for s, w, c in zip(sid, widx, counts) for v in mat[s, w:w + c]]
+    assert got == want
