@@ -49,12 +49,45 @@ __device__ __forceinline__ void gen_hist(u32* bins, u32 v) {
     if ((threadIdx.x & 31u) == (u32)(__ffs(peers) - 1)) atomicAdd(bins + v, (u32)__popc(peers));
 }
 
-// QM31 product for the generated kernels.
-__device__ __forceinline__ QM31 g_qm_mul(QM31 x, QM31 y) { return qm_mul(x, y); }
+// ---- lazily reduced arithmetic of the generated kernels.  Canonical inputs (< P < 2^31) give
+// products < 2^62, so four of them fit a u64 accumulator (4*P*(P-1) < 2^64); dot_fold brings an
+// accumulator back below 2^34 so the next four fit again.  P - f (in [1, P]) stands for -f.
+__device__ __forceinline__ u64 g_fold64(u64 x) { return (x & P) + (x >> 31); }
+__device__ __forceinline__ void dot_term(u64& d0, u64& d1, u64& d2, u64& d3, QM31 e, u32 f) {
+    d0 += (u64)e.a * f;
+    d1 += (u64)e.b * f;
+    d2 += (u64)e.c * f;
+    d3 += (u64)e.d * f;
+}
+__device__ __forceinline__ void dot_fold(u64& d0, u64& d1, u64& d2, u64& d3) {
+    d0 = g_fold64(d0);
+    d1 = g_fold64(d1);
+    d2 = g_fold64(d2);
+    d3 = g_fold64(d3);
+}
+__device__ __forceinline__ QM31 dot_done(u64 d0, u64 d1, u64 d2, u64 d3) {
+    return qm_make(m31_reduce64(d0), m31_reduce64(d1), m31_reduce64(d2), m31_reduce64(d3));
+}
+// QM31 product as six u64 dot products (16 multiply-adds, 6 reductions) instead of four CM31
+// products with a reduction per partial product.  (A + Bu)(C + Du) = (AC + (2+i)BD) + (AD + BC)u.
+__device__ __forceinline__ QM31 g_qm_mul(QM31 x, QM31 y) {
+    const u32 nyb = P - y.b, nyd = P - y.d;
+    const u32 p = m31_reduce64((u64)x.c * y.c + (u64)x.d * nyd);  // Re(BD)
+    const u32 q = m31_reduce64((u64)x.c * y.d + (u64)x.d * y.c);  // Im(BD)
+    const u64 lre = (u64)x.a * y.a + (u64)x.b * nyb + 2ull * p + (P - q);
+    const u64 lim = (u64)x.a * y.b + (u64)x.b * y.a + p + 2ull * q;
+    const u64 hre = (u64)x.a * y.c + (u64)x.b * nyd + (u64)x.c * y.a + (u64)x.d * nyb;
+    const u64 him = (u64)x.a * y.d + (u64)x.b * y.c + (u64)x.c * y.b + (u64)x.d * y.a;
+    return qm_make(m31_reduce64(lre), m31_reduce64(lim), m31_reduce64(hre), m31_reduce64(him));
+}
 
 }  // namespace cm31
 
 // ---- vocabulary of the generated kernel bodies (a = the kernel's argument struct)
+using cm31::dot_term;
+using cm31::dot_fold;
+using cm31::dot_done;
+using cm31::g_qm_mul;
 #define ldcol(i) __ldg(a.in[i] + row)
 #define ldcol_off(i, off) __ldg(a.in[i] + cm31::gen_offset_row(row, a.trace_log, a.row_log, (off)))
 #define cw(s) (a.c[s])

@@ -166,37 +166,65 @@ struct QuotPointTable {
 };
 __device__ __forceinline__ u64 fold64(u64 x) { return (x & P) + (x >> 31); }
 
+// one thread per CTA of the main kernel: Q_blk = point(half_initial + half_step * bit_reverse(blk))
+__global__ void quotients_block_points_kernel(u32 log_size, u32 half_initial, u32 half_step, const CirclePointM31* __restrict__ gen_pow,
+                                              CirclePointM31* __restrict__ q_out) {
+    u32 blk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= (1u << (log_size - 8))) return;
+    u32 bk = bit_reverse(blk, log_size - 8);
+    u32 idx = (u32)((half_initial + (u64)half_step * bk) & 0x7fffffffu);
+    CirclePointM31 res = {1, 0};
+#pragma unroll 1
+    for (u32 bit = 0; bit < 31; bit++)
+        if (idx & (1u << bit)) res = cp_add(res, gen_pow[bit]);
+    q_out[blk] = res;
+}
+
+constexpr u32 QUOT_TILE = 256;  // (batch, column) terms staged in shared memory at a time
+
 __global__ void __launch_bounds__(256) quotients_fast_kernel(u32 log_size, const QuotEntry* __restrict__ entries,
-                                                             const QuotBatch* __restrict__ batches, u32 n_batches, u32 half_initial,
-                                                             u32 half_step, const CirclePointM31* __restrict__ gen_pow,
+                                                             const QuotBatch* __restrict__ batches, u32 n_batches,
+                                                             const CirclePointM31* __restrict__ q_blk,
                                                              const __grid_constant__ QuotPointTable table, Ptr4 out) {
-    __shared__ CirclePointM31 q_blk;
+    __shared__ uint4 sh_entries[QUOT_TILE * 2];
     const u32 t = threadIdx.x;
     const size_t row = blockIdx.x * (size_t)256 + t;
-    if (t == 0) {
-        u32 bk = bit_reverse(blockIdx.x, log_size - 8);
-        u32 idx = (u32)((half_initial + (u64)half_step * bk) & 0x7fffffffu);
-        CirclePointM31 res = {1, 0};
-#pragma unroll 1
-        for (u32 bit = 0; bit < 31; bit++)
-            if (idx & (1u << bit)) res = cp_add(res, gen_pow[bit]);
-        q_blk = res;
-    }
-    __syncthreads();
-    CirclePointM31 p = cp_add(q_blk, table.r[t >> 1]);
+    CirclePointM31 p = cp_add(q_blk[blockIdx.x], table.r[t >> 1]);
     if (t & 1) p.y = m31_neg(p.y);
     QM31 acc = qm_zero();
     for (u32 b = 0; b < n_batches; b++) {
         const QuotBatch qb = batches[b];
         u64 n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-        u32 k = qb.start;
-        for (; k + 4 <= qb.end; k += 4) {
+        for (u32 k0 = qb.start; k0 < qb.end; k0 += QUOT_TILE) {
+            const u32 cnt = min(QUOT_TILE, qb.end - k0);
+            __syncthreads();  // previous tile fully consumed
+            for (u32 i = t; i < cnt * 2; i += 256) sh_entries[i] = __ldg(reinterpret_cast<const uint4*>(entries + k0) + i);
+            __syncthreads();
+            u32 k = 0;
+            for (; k + 4 <= cnt; k += 4) {
+                u32 f[4];
 #pragma unroll
-            for (u32 j = 0; j < 4; j++) {
-                const uint4 e0 = __ldg(reinterpret_cast<const uint4*>(entries + k + j));
-                const uint4 c = __ldg(reinterpret_cast<const uint4*>(entries + k + j) + 1);
-                const u32* col = reinterpret_cast<const u32*>(((u64)e0.y << 32) | e0.x);
-                const u64 f = __ldg(col + row);
+                for (u32 j = 0; j < 4; j++) {  // the 4 column reads are independent: all in flight together
+                    const uint4 e0 = sh_entries[2 * (k + j)];
+                    f[j] = __ldg(reinterpret_cast<const u32*>(((u64)e0.y << 32) | e0.x) + row);
+                }
+#pragma unroll
+                for (u32 j = 0; j < 4; j++) {
+                    const uint4 c = sh_entries[2 * (k + j) + 1];
+                    n0 += (u64)f[j] * c.x;
+                    n1 += (u64)f[j] * c.y;
+                    n2 += (u64)f[j] * c.z;
+                    n3 += (u64)f[j] * c.w;
+                }
+                n0 = fold64(n0);
+                n1 = fold64(n1);
+                n2 = fold64(n2);
+                n3 = fold64(n3);
+            }
+            for (; k < cnt; k++) {  // <= 3 leftover terms: below 2^64 on top of a folded carry
+                const uint4 e0 = sh_entries[2 * k];
+                const uint4 c = sh_entries[2 * k + 1];
+                const u64 f = __ldg(reinterpret_cast<const u32*>(((u64)e0.y << 32) | e0.x) + row);
                 n0 += f * c.x;
                 n1 += f * c.y;
                 n2 += f * c.z;
@@ -206,16 +234,6 @@ __global__ void __launch_bounds__(256) quotients_fast_kernel(u32 log_size, const
             n1 = fold64(n1);
             n2 = fold64(n2);
             n3 = fold64(n3);
-        }
-        for (; k < qb.end; k++) {  // <= 3 leftover terms: still below 2^64 on top of a folded carry
-            const uint4 e0 = __ldg(reinterpret_cast<const uint4*>(entries + k));
-            const uint4 c = __ldg(reinterpret_cast<const uint4*>(entries + k) + 1);
-            const u32* col = reinterpret_cast<const u32*>(((u64)e0.y << 32) | e0.x);
-            const u64 f = __ldg(col + row);
-            n0 += f * c.x;
-            n1 += f * c.y;
-            n2 += f * c.z;
-            n3 += f * c.w;
         }
         QM31 num = qm_make(m31_reduce64(n0), m31_reduce64(n1), m31_reduce64(n2), m31_reduce64(n3));
         QM31 A = qm_make(qb.sum_a[0], qb.sum_a[1], qb.sum_a[2], qb.sum_a[3]);
@@ -423,11 +441,15 @@ int cm31_accumulate_quotients(uint32_t log_size, const uint32_t* const* cols, si
         }
         DeviceTable dent;
         if (int e = dent.upload(entries.data(), entries.size() * sizeof(QuotEntry))) return e;
-        ProfScope prof("accumulate_quotients", (4ull * n_cols + 16ull) * n);
+        CirclePointM31* dq = nullptr;
+        CM_CUDA(cudaMallocAsync(&dq, (n / 256) * sizeof(CirclePointM31), stream()));
+        ProfScope prof("accumulate_quotients", (4ull * n_cols + 16ull) * n, 2);
+        quotients_block_points_kernel<<<(unsigned)((n / 256 + 127) / 128), 128, 0, stream()>>>(log_size, half.initial_index, half.step_size,
+                                                                                             (const CirclePointM31*)dgen.d, dq);
         quotients_fast_kernel<<<(unsigned)(n / 256), 256, 0, stream()>>>(log_size, (const QuotEntry*)dent.d, (const QuotBatch*)dqb.d,
-                                                                       (u32)n_batches, half.initial_index, half.step_size,
-                                                                       (const CirclePointM31*)dgen.d, table, o);
+                                                                       (u32)n_batches, dq, table, o);
         CM_LAUNCH_CHECK();
+        CM_CUDA(cudaFreeAsync(dq, stream()));
         return 0;
     }
     ProfScope prof("accumulate_quotients", (4ull * n_cols + 16ull) * n);

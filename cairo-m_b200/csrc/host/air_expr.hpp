@@ -13,6 +13,7 @@
 #pragma once
 #include <cassert>
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -580,6 +581,55 @@ class ProgramBuilder {
                 if (ch >= 0) last_use[ch] = (int)id;
             if (last_use[id] < (int)id) last_use[id] = (int)id;
         }
+        // ---- CUDA emission only: fuse sums of E*f products (LookupElements::combine, logup
+        // numerators) into lazily reduced u64 dot products.  A chain  (((E0*f0 + E1*f1) + E2*f2) - z)
+        // costs 4 multiply-adds per term + one reduction per coordinate instead of a reduced
+        // multiplication and a reduced addition per term and coordinate.  Exact field arithmetic, so
+        // the value equals the bytecode's; interior nodes must have no other user.
+        struct FusedSum {
+            std::vector<std::tuple<int, int, int>> terms;  // (sign, E node, F node)
+            std::vector<std::pair<int, int>> addends;      // (sign, E node)
+            std::vector<int> interior;
+        };
+        std::map<int, FusedSum> fused;
+        std::vector<char> absorbed(n, 0);
+        if (emit_cuda) {
+            std::vector<int> uses(n, 0);
+            for (size_t id = 0; id < n; id++) {
+                if (!live[id]) continue;
+                const Node& nd = g.nodes[id];
+                for (int ch : {nd.a, nd.b, nd.c, nd.d})
+                    if (ch >= 0) uses[ch]++;
+            }
+            for (auto& o : outputs) uses[o.node] += 2;  // outputs are never interior
+            // Shared sub-sums (CSE across relation entries with a common prefix) are expanded into every
+            // user: re-accumulating a term is 4 multiply-adds, cheaper than one reduced QM31 addition.
+            // A shared node is still emitted on its own; nvcc drops it when every user was fused.
+            std::function<void(int, int, FusedSum&, bool)> collect = [&](int id, int sign, FusedSum& f, bool root) {
+                const Node& nd = g.nodes[id];
+                bool single = root || uses[id] == 1;
+                if (nd.op == NodeOp::MulEF && f.terms.size() < 48) {
+                    f.terms.push_back(std::make_tuple(sign, nd.a, nd.b));
+                    if (!root && single) f.interior.push_back(id);
+                } else if ((nd.op == NodeOp::AddE || nd.op == NodeOp::SubE) && f.terms.size() < 48) {
+                    if (!root && single) f.interior.push_back(id);
+                    collect(nd.a, sign, f, false);
+                    collect(nd.b, nd.op == NodeOp::AddE ? sign : -sign, f, false);
+                } else {
+                    f.addends.push_back({sign, id});
+                }
+            };
+            for (int id = (int)n - 1; id >= 0; id--) {
+                if (!live[id] || absorbed[id]) continue;
+                const Node& nd = g.nodes[id];
+                if (nd.op != NodeOp::AddE && nd.op != NodeOp::SubE) continue;
+                FusedSum f;
+                collect(id, 1, f, true);
+                if (f.terms.size() < 2) continue;
+                for (int i : f.interior) absorbed[i] = 1;
+                fused[id] = f;
+            }
+        }
         // params table first (4 words each), then constants
         prog.param_slots.resize(n_params);
         for (size_t p = 0; p < n_params; p++) {
@@ -629,7 +679,26 @@ class ProgramBuilder {
             reg[id] = r;
             const int nid = (int)id;
             auto fdef = [&](const std::string& rhs) { if (emit_cuda) src += "    const u32 " + F(nid) + " = " + rhs + ";\n"; };
-            auto edef = [&](const std::string& rhs) { if (emit_cuda) src += "    const QM31 " + E(nid) + " = " + rhs + ";\n"; };
+            auto edef = [&](const std::string& rhs) {
+                if (!emit_cuda || absorbed[nid]) return;
+                auto fit = fused.find(nid);
+                if (fit == fused.end()) {
+                    src += "    const QM31 " + E(nid) + " = " + rhs + ";\n";
+                    return;
+                }
+                const FusedSum& f = fit->second;
+                std::string d = "d" + std::to_string(nid);
+                src += "    u64 " + d + "_0 = 0, " + d + "_1 = 0, " + d + "_2 = 0, " + d + "_3 = 0;\n";
+                size_t k = 0;
+                for (auto& t : f.terms) {
+                    std::string fv = std::get<0>(t) > 0 ? F(std::get<2>(t)) : "(P - " + F(std::get<2>(t)) + ")";
+                    src += "    dot_term(" + d + "_0, " + d + "_1, " + d + "_2, " + d + "_3, " + E(std::get<1>(t)) + ", " + fv + ");\n";
+                    if (++k % 4 == 0 && k != f.terms.size()) src += "    dot_fold(" + d + "_0, " + d + "_1, " + d + "_2, " + d + "_3);\n";
+                }
+                std::string expr = "dot_done(" + d + "_0, " + d + "_1, " + d + "_2, " + d + "_3)";
+                for (auto& a : f.addends) expr = std::string(a.first > 0 ? "qm_add(" : "qm_sub(") + expr + ", " + E(a.second) + ")";
+                src += "    const QM31 " + E(nid) + " = " + expr + ";\n";
+            };
             switch (nd.op) {
                 case NodeOp::Col: {
                     u32 ci = (u32)col_index(nd.interaction, nd.col);

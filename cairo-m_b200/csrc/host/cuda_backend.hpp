@@ -151,6 +151,11 @@ struct CudaBackend {
                             const std::vector<u32>& out_off, std::vector<u32>& out) {
         cm_check(cm31_gather_runs(srcs.data(), srcs.size(), src_id.data(), word.data(), out_off.data(), src_id.size(), out.data()));
     }
+    static Hash32 read_root(const HashCol& root_layer) {
+        Hash32 h;
+        cm_check(cm31_d2h(h.b, root_layer.ptr(), 32));
+        return h;
+    }
     static void gather_hashes(const HashCol& layer, const std::vector<u32>& idx, std::vector<Hash32>& out) {
         out.resize(idx.size());
         cm_check(cm31_gather_hash(layer.ptr(), idx.data(), idx.size(), (u32*)out.data()));

@@ -65,9 +65,20 @@ inline AirProgram build_constraint_program(const ExprEvaluator& ev, bool emit_cu
 // cumulative logup columns col_b = col_{b-1} + num_b/den_b  (logup.rs:123-320); extends the graph
 inline AirProgram build_logup_program(ExprEvaluator& e, bool emit_cuda = false) {
     std::vector<ProgramOutput> outs;
+    // 1/den_b for every batch of the row with ONE inversion (Montgomery's trick, the per-row
+    // analogue of the reference's batch_inverse over a column, fields/mod.rs:69-99)
+    size_t k = e.batch_fracs.size();
+    std::vector<EFExpr> prefix(k), inv(k);
+    for (size_t b = 0; b < k; b++) prefix[b] = b == 0 ? e.batch_fracs[0].den : e.ef_mul(prefix[b - 1], e.batch_fracs[b].den);
+    EFExpr run = e.ef_inv(prefix[k - 1]);
+    for (size_t b = k - 1; b >= 1; b--) {
+        inv[b] = e.ef_mul(run, prefix[b - 1]);
+        run = e.ef_mul(run, e.batch_fracs[b].den);
+    }
+    inv[0] = run;
     EFExpr cum = e.ef_zero();
-    for (size_t b = 0; b < e.batch_fracs.size(); b++) {
-        EFExpr term = e.ef_mul(e.batch_fracs[b].num, e.ef_inv(e.batch_fracs[b].den));
+    for (size_t b = 0; b < k; b++) {
+        EFExpr term = e.ef_mul(e.batch_fracs[b].num, inv[b]);
         cum = b == 0 ? term : e.ef_add(cum, term);
         outs.push_back(ProgramOutput{ProgramOutput::StoreE, cum.id, (int)(4 * b)});
     }

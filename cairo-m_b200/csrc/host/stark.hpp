@@ -317,11 +317,7 @@ struct MerkleProver {
         return mp;
     }
 
-    Hash32 root() const {
-        std::vector<Hash32> out;
-        B::gather_hashes(layers[0], {0}, out);
-        return out[0];
-    }
+    Hash32 root() const { return B::read_root(layers[0]); }  // one 32-byte device->host copy
 
     // vcs/prover.rs:82-156 in two phases: `plan` walks the layers exactly like the reference and
     // records every read in the gather queue; `finish` (after queue.flush()) assembles the values.

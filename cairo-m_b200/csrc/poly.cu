@@ -30,27 +30,41 @@ __device__ __forceinline__ CirclePointM31 dev_point_from_index(u32 index) {
     return res;
 }
 
-__global__ void twiddle_kernel(u32* tw, u32* itw, u32 k, u32 root_initial, u32 root_step) {
-    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    size_t total = (size_t)1 << k;
-    if (t >= total) return;
-    if (t == total - 1) {  // pad element (cpu/circle.rs:185-187)
-        tw[t] = 1;
-        itw[t] = 1;
-        return;
-    }
-    // find level j: offset_j = 2^k - 2^(k-j) <= t
-    u32 rem = (u32)(total - t);           // in (1, 2^k]
-    u32 j = k - (32 - __clz(rem - 1));    // 2^(k-j-1) < rem <= 2^(k-j)
-    u32 level_off = (u32)(total - ((size_t)1 << (k - j)));
-    u32 i = (u32)t - level_off;           // < 2^(k-1-j)
-    u32 nat = bit_reverse(i, k - 1 - j);
-    u32 initial = (u32)(((u64)root_initial << j) & 0x7fffffffu);
-    u32 step = (u32)(((u64)root_step << j) & 0x7fffffffu);
-    u32 idx = (u32)((initial + (u64)step * nat) & 0x7fffffffu);
-    u32 x = dev_point_from_index(idx).x;
-    tw[t] = x;
-    itw[t] = m31_inv(x);
+// Point of index initial_j + step_j * nat as I_j + sum over set bits b of nat of T[j + b]
+// (T[b] = point(step * 2^b), I_j = point(initial * 2^j)): <= k-1 group additions instead of a
+// 31-step double-and-add; the 1/x tree uses one Montgomery batch inversion per 4 entries.
+struct TwiddleTables {
+    CirclePointM31 t[32];  // T[b]
+    CirclePointM31 i[32];  // I[j]
+};
+__device__ __forceinline__ u32 twiddle_x(const TwiddleTables& tab, u32 k, u32 t, u32 total) {
+    u32 rem = total - t;                  // in (1, 2^k]
+    u32 j = k - (32 - __clz(rem - 1));    // level: 2^(k-j-1) < rem <= 2^(k-j)
+    u32 level_off = total - (1u << (k - j));
+    u32 nat = bit_reverse(t - level_off, k - 1 - j);
+    CirclePointM31 p = tab.i[j];
+    for (u32 b = 0; nat != 0; b++, nat >>= 1)
+        if (nat & 1) p = cp_add(p, tab.t[j + b]);
+    return p.x;
+}
+__global__ void __launch_bounds__(256) twiddle_kernel(u32* tw, u32* itw, u32 k, const __grid_constant__ TwiddleTables tab) {
+    const u32 total = 1u << k;
+    const u32 t0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (t0 >= total) return;
+    u32 x[4];
+#pragma unroll
+    for (u32 q = 0; q < 4; q++) x[q] = (t0 + q == total - 1) ? 1u : twiddle_x(tab, k, t0 + q, total);  // pad element (cpu/circle.rs:185-187)
+    // batch inverse of 4 (fields/mod.rs:69-99)
+    u32 p01 = m31_mul(x[0], x[1]), p012 = m31_mul(p01, x[2]), p0123 = m31_mul(p012, x[3]);
+    u32 inv = m31_inv(p0123);
+    u32 i3 = m31_mul(inv, p012);
+    inv = m31_mul(inv, x[3]);
+    u32 i2 = m31_mul(inv, p01);
+    inv = m31_mul(inv, x[2]);
+    u32 i1 = m31_mul(inv, x[0]);
+    u32 i0 = m31_mul(inv, x[1]);
+    *reinterpret_cast<uint4*>(tw + t0) = make_uint4(x[0], x[1], x[2], x[3]);
+    *reinterpret_cast<uint4*>(itw + t0) = make_uint4(i0, i1, i2, i3);
 }
 
 // --------------------------------------------------------------------------- FFT passes
@@ -501,9 +515,13 @@ int cm31_twiddles_create(uint32_t log_size, cm31_twiddles** out) {
     if (int e = cm31_malloc((void**)&tw->tw, n * 4)) return e;
     if (int e = cm31_malloc((void**)&tw->itw, n * 4)) return e;
     Coset root = CanonicCoset(log_size).half_coset();
+    TwiddleTables tab;
+    for (u32 b = 0; b < 32; b++) {
+        tab.t[b] = cp_from_index((u32)(((u64)root.step_size << b) & 0x7fffffffu));
+        tab.i[b] = cp_from_index((u32)(((u64)root.initial_index << b) & 0x7fffffffu));
+    }
     ProfScope prof("twiddles", 8ull * n);
-    twiddle_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(tw->tw, tw->itw, k, root.initial_index,
-                                                                     root.step_size);
+    twiddle_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, stream()>>>(tw->tw, tw->itw, k, tab);
     CM_LAUNCH_CHECK();
     *out = tw;
     return 0;

@@ -71,6 +71,11 @@ struct OracleBackend {
         for (size_t k = 0; k < src_id.size(); k++)
             for (u32 j = 0; j < out_off[k + 1] - out_off[k]; j++) out[out_off[k] + j] = srcs[src_id[k]][word[k] + j];
     }
+    static cm31::Hash32 read_root(const HashCol& root_layer) {
+        cm31::Hash32 h;
+        memcpy(h.b, root_layer[0].b, 32);
+        return h;
+    }
     static void gather_hashes(const HashCol& layer, const std::vector<u32>& idx, std::vector<cm31::Hash32>& out) {
         out.resize(idx.size());
         for (size_t q = 0; q < idx.size(); q++) memcpy(out[q].b, layer[idx[q]].b, 32);

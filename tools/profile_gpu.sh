@@ -1,15 +1,23 @@
 #!/bin/bash
 # Run on the GPU box (under gpurun): launch list + full captures of the top kernels.
-# Usage: tools/profile_gpu.sh <round-tag> [log_steps]
+# The .ncu-rep files are summarised ON the box (tools/ncu_summary.py) and deleted: gpurun only
+# copies back 64 MiB.   Usage: tools/profile_gpu.sh <round-tag> [log_steps] [kernel regexes...]
 TAG=${1:-r01}
 LOG=${2:-22}
+shift 2
+KERNELS=${@:-fft4_pass_kernel merkle_layer_kernel quotients_fast_kernel k_.*_constraints k_.*_logup}
 mkdir -p gpurun_out
 BENCH="python bench.py --log-steps $LOG --steps 1 --warmup 0 --no-cpu-baseline"
-# every launch of the 2nd proof of the run (the first one is the cold start)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2300 -c 2300 --csv \
+# every launch of the 3rd proof of the run (value proof, staging proof, then the e2e proof)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1090 -c 560 --csv \
     --log-file gpurun_out/launches_${TAG}.csv $BENCH > gpurun_out/ncu_launches_${TAG}.log 2>&1
-for K in air_program_kernel fft_pass_kernel merkle_layer_kernel quotients_kernel eap_stage1_kernel; do
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 40 -c 12 \
-        -f -o gpurun_out/full_${K}_${TAG} $BENCH > gpurun_out/ncu_full_${K}_${TAG}.log 2>&1
+python tools/ncu_summary.py launches gpurun_out/launches_${TAG}.csv gpurun_out/launches_${TAG}.md > /dev/null
+for K in $KERNELS; do
+    N=$(echo $K | tr -cd 'a-z0-9_')
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 12 -c 8 \
+        -f -o /tmp/full_${N} $BENCH > gpurun_out/ncu_full_${N}_${TAG}.log 2>&1
+    python tools/ncu_summary.py full /tmp/full_${N}.ncu-rep gpurun_out/full_${N}_${TAG}.md > /dev/null
+    ncu -i /tmp/full_${N}.ncu-rep --page source --csv 2>/dev/null | gzip -9 > gpurun_out/source_${N}_${TAG}.csv.gz
+    rm -f /tmp/full_${N}.ncu-rep
 done
-ls -la gpurun_out
+ls -la gpurun_out | tail -20
