@@ -276,7 +276,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     traffic = None
     tpath = ROOT / "profiles" / "traffic.json"
     if tpath.exists():
-        traffic = json.loads(tpath.read_text()).get(top["kernel"])
+        t = json.loads(tpath.read_text()).get(top["kernel"])
+        if t:  # measured DRAM bytes per algorithmic byte (ncu --set full) x this launch's algorithmic bytes
+            traffic = t["dram_per_alg_byte"] * top["alg_bytes"] / top["launches"]
     roofline = {
         "bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches_per_step": top["launches"] / args.steps,
