@@ -117,6 +117,8 @@ def cpu_cores() -> int:
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core
+    os.environ["OMP_NUM_THREADS"] = str(cpu_cores())
     sample_log = args.cpu_sample_log
     for _ in range(min(args.warmup, 1)):  # the CPU path has no warm-up effects beyond page faults: one is enough
         oracle_prove_timed(sample_log)
