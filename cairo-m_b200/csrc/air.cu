@@ -182,16 +182,16 @@ __device__ __forceinline__ u32 coset_pos_to_row(u32 j, u32 L) {
 }
 
 constexpr u32 SCAN_CHUNK = 1024;  // elements per CTA in the chunked scan
+struct Col4 {
+    u32* p[4];
+};
 
-__global__ void __launch_bounds__(256) sum4_kernel(const u32* c0, const u32* c1, const u32* c2, const u32* c3, size_t n,
-                                                   unsigned long long* sums) {
+__global__ void __launch_bounds__(256) sum4_kernel(Col4 c, size_t n, unsigned long long* sums) {
     __shared__ unsigned long long sh[4][256];
     unsigned long long s[4] = {0, 0, 0, 0};
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        s[0] += c0[i];
-        s[1] += c1[i];
-        s[2] += c2[i];
-        s[3] += c3[i];
+#pragma unroll
+        for (int k = 0; k < 4; k++) s[k] += c.p[k][i];
     }
     for (int k = 0; k < 4; k++) sh[k][threadIdx.x] = s[k];
     __syncthreads();
@@ -203,10 +203,21 @@ __global__ void __launch_bounds__(256) sum4_kernel(const u32* c0, const u32* c1,
     if (threadIdx.x == 0)
         for (int k = 0; k < 4; k++) atomicAdd(&sums[k], sh[k][0] % P);
 }
+// claimed_sum = sums mod P (-> claimed_out, 4 words); shift = claimed_sum / n (-> shift_out, 4 words)
+__global__ void sums_to_shift_kernel(const unsigned long long* sums, u32 n_inv, u32* claimed_out, u32* shift_out) {
+    u32 k = threadIdx.x;
+    if (k >= 4) return;
+    u32 c = m31_reduce64(sums[k]);
+    claimed_out[k] = c;
+    shift_out[k] = m31_mul(c, n_inv);
+}
 
+// The three scan passes handle the 4 coordinate columns in one launch (blockIdx.y = coordinate).
 // pass 1: per-chunk totals of (value - shift) in coset order
-__global__ void __launch_bounds__(256) scan_chunk_sums_kernel(const u32* col, u32 L, u32 shift, u32* chunk_sums) {
+__global__ void __launch_bounds__(256) scan_chunk_sums_kernel(Col4 c, u32 L, const u32* __restrict__ shift4, u32* chunk_sums, u32 n_chunks) {
     __shared__ u32 sh[256];
+    const u32* col = c.p[blockIdx.y];
+    const u32 shift = shift4[blockIdx.y];
     u32 chunk = blockIdx.x;
     size_t n = (size_t)1 << L;
     u32 acc = 0;
@@ -220,12 +231,13 @@ __global__ void __launch_bounds__(256) scan_chunk_sums_kernel(const u32* col, u3
         if (threadIdx.x < st) sh[threadIdx.x] = m31_add(sh[threadIdx.x], sh[threadIdx.x + st]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) chunk_sums[chunk] = sh[0];
+    if (threadIdx.x == 0) chunk_sums[(size_t)blockIdx.y * n_chunks + chunk] = sh[0];
 }
-// pass 2: exclusive scan of the chunk totals (single CTA, sequential over <= 2^20 chunks in tiles)
-__global__ void __launch_bounds__(1024) scan_chunk_offsets_kernel(u32* chunk_sums, u32 n_chunks) {
+// pass 2: exclusive scan of the chunk totals (one CTA per coordinate, tiles of 1024)
+__global__ void __launch_bounds__(1024) scan_chunk_offsets_kernel(u32* chunk_sums_all, u32 n_chunks) {
     __shared__ u32 sh[1024];
     __shared__ u32 carry;
+    u32* chunk_sums = chunk_sums_all + (size_t)blockIdx.x * n_chunks;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (u32 base = 0; base < n_chunks; base += 1024) {
@@ -247,8 +259,11 @@ __global__ void __launch_bounds__(1024) scan_chunk_offsets_kernel(u32* chunk_sum
     }
 }
 // pass 3: in-chunk inclusive scan + chunk offset, written back in place
-__global__ void __launch_bounds__(256) scan_apply_kernel(u32* col, u32 L, u32 shift, const u32* chunk_offsets) {
+__global__ void __launch_bounds__(256) scan_apply_kernel(Col4 c, u32 L, const u32* __restrict__ shift4, const u32* chunk_offsets_all, u32 n_chunks) {
     __shared__ u32 sh[256];
+    u32* col = c.p[blockIdx.y];
+    const u32 shift = shift4[blockIdx.y];
+    const u32* chunk_offsets = chunk_offsets_all + (size_t)blockIdx.y * n_chunks;
     u32 chunk = blockIdx.x;
     size_t n = (size_t)1 << L;
     const u32 per = SCAN_CHUNK / 256;  // 4 consecutive coset positions per thread
@@ -274,6 +289,49 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(u32* col, u32 L, u32 sh
     u32 base = m31_add(chunk_offsets[chunk], excl);
     for (u32 k = 0; k < per; k++)
         if (rows[k] != 0xffffffffu) col[rows[k]] = m31_add(base, v[k]);
+}
+
+// Small components (n <= 2^11 rows; most of cairo-m's 34 components for a given program): the
+// whole finalize_last — sums, claimed sum, shift, coset-order scan of the 4 coordinates — in ONE
+// single-CTA launch.  64 threads per coordinate, each scanning a contiguous run.
+constexpr u32 FINALIZE_SMALL_LOG = 11;
+__global__ void __launch_bounds__(256) logup_finalize_small_kernel(Col4 c, u32 L, u32 n_inv, u32* claimed_out) {
+    __shared__ u32 vals[4][1u << FINALIZE_SMALL_LOG];
+    __shared__ u32 tot[4][64];
+    __shared__ u32 shift[4];
+    const u32 n = 1u << L;
+    const u32 k = threadIdx.x >> 6, t = threadIdx.x & 63;
+    u32* col = c.p[k];
+    const u32 run = n >= 64 ? n / 64 : 1;  // elements per thread (threads >= n idle when n < 64)
+    const bool active = t * run < n;
+    u32 acc = 0;
+    if (active)
+        for (u32 i = 0; i < run; i++) {
+            u32 j = t * run + i;
+            u32 x = col[coset_pos_to_row(j, L)];
+            vals[k][j] = x;
+            acc = m31_add(acc, x);
+        }
+    tot[k][t] = acc;
+    __syncthreads();
+    if (t == 0) {
+        u32 s = 0;
+        for (u32 i = 0; i < 64; i++) s = m31_add(s, tot[k][i]);
+        claimed_out[k] = s;
+        shift[k] = m31_mul(s, n_inv);
+    }
+    __syncthreads();
+    if (!active) return;
+    // prefix of the shifted values: offset of this run = sum of previous runs - shift * (elements before)
+    u32 before = 0;
+    for (u32 i = 0; i < t; i++) before = m31_add(before, tot[k][i]);
+    const u32 sh = shift[k];
+    u32 running = m31_sub(before, m31_mul(sh, (t * run) % P));
+    for (u32 i = 0; i < run; i++) {
+        u32 j = t * run + i;
+        running = m31_add(running, m31_sub(vals[k][j], sh));
+        col[coset_pos_to_row(j, L)] = running;
+    }
 }
 
 __global__ void histogram_kernel(const u32* values, size_t n, u32* bins, u32 n_bins) {
@@ -310,40 +368,55 @@ int cm31_air_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* cons
                        nullptr, 0, nullptr);
 }
 
-int cm31_logup_finalize_last(uint32_t* const last4[4], uint32_t log_size, uint32_t claimed_sum_out[4]) {
+// claimed_sum_dev: 4 device words receiving the claimed sum; nothing is synchronised.
+int cm31_logup_finalize_last_async(uint32_t* const last4[4], uint32_t log_size, uint32_t* claimed_sum_dev) {
     CM_REQUIRE(log_size >= 1 && log_size <= 30, "logup_finalize_last: bad log_size");
+    CM_REQUIRE(claimed_sum_dev != nullptr, "logup_finalize_last: null output");
     size_t n = (size_t)1 << log_size;
+    Col4 c;
+    for (int k = 0; k < 4; k++) c.p[k] = last4[k];
+    const u32 n_inv = m31_inv((u32)(n % P));
+    if (log_size <= FINALIZE_SMALL_LOG) {
+        ProfScope prof("logup_finalize_small", 32ull * n);
+        logup_finalize_small_kernel<<<1, 256, 0, stream()>>>(c, log_size, n_inv, claimed_sum_dev);
+        CM_LAUNCH_CHECK();
+        return 0;
+    }
     unsigned long long* dsums = nullptr;
+    u32* dshift = nullptr;
     CM_CUDA(cudaMallocAsync(&dsums, 32, stream()));
+    CM_CUDA(cudaMallocAsync(&dshift, 16, stream()));
     CM_CUDA(cudaMemsetAsync(dsums, 0, 32, stream()));
     unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 1024);
     {
-        ProfScope prof("logup_sum4", 16ull * n);
-        sum4_kernel<<<blocks, 256, 0, stream()>>>(last4[0], last4[1], last4[2], last4[3], n, dsums);
+        ProfScope prof("logup_sum4", 16ull * n, 2);
+        sum4_kernel<<<blocks, 256, 0, stream()>>>(c, n, dsums);
+        sums_to_shift_kernel<<<1, 32, 0, stream()>>>(dsums, n_inv, claimed_sum_dev, dshift);
     }
     CM_LAUNCH_CHECK();
-    unsigned long long h[4];
-    CM_CUDA(cudaMemcpyAsync(h, dsums, 32, cudaMemcpyDeviceToHost, stream()));
-    CM_CUDA(cudaStreamSynchronize(stream()));
-    CM_CUDA(cudaFreeAsync(dsums, stream()));
-    QM31 claimed = qm_make(m31_reduce64(h[0]), m31_reduce64(h[1]), m31_reduce64(h[2]), m31_reduce64(h[3]));
-    claimed_sum_out[0] = claimed.a;
-    claimed_sum_out[1] = claimed.b;
-    claimed_sum_out[2] = claimed.c;
-    claimed_sum_out[3] = claimed.d;
-    QM31 shift = qm_mul_m31(claimed, m31_inv((u32)(n % P)));
-    u32 sh[4] = {shift.a, shift.b, shift.c, shift.d};
     u32 n_chunks = (u32)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
     u32* dchunks = nullptr;
-    CM_CUDA(cudaMallocAsync(&dchunks, (size_t)n_chunks * 4, stream()));
-    for (int k = 0; k < 4; k++) {
-        ProfScope prof("logup_prefix_sum", 8ull * n, 3);
-        scan_chunk_sums_kernel<<<n_chunks, 256, 0, stream()>>>(last4[k], log_size, sh[k], dchunks);
-        scan_chunk_offsets_kernel<<<1, 1024, 0, stream()>>>(dchunks, n_chunks);
-        scan_apply_kernel<<<n_chunks, 256, 0, stream()>>>(last4[k], log_size, sh[k], dchunks);
+    CM_CUDA(cudaMallocAsync(&dchunks, (size_t)n_chunks * 16, stream()));
+    {
+        ProfScope prof("logup_prefix_sum", 32ull * n, 3);
+        scan_chunk_sums_kernel<<<dim3(n_chunks, 4), 256, 0, stream()>>>(c, log_size, dshift, dchunks, n_chunks);
+        scan_chunk_offsets_kernel<<<4, 1024, 0, stream()>>>(dchunks, n_chunks);
+        scan_apply_kernel<<<dim3(n_chunks, 4), 256, 0, stream()>>>(c, log_size, dshift, dchunks, n_chunks);
     }
     CM_LAUNCH_CHECK();
     CM_CUDA(cudaFreeAsync(dchunks, stream()));
+    CM_CUDA(cudaFreeAsync(dshift, stream()));
+    CM_CUDA(cudaFreeAsync(dsums, stream()));
+    return 0;
+}
+
+int cm31_logup_finalize_last(uint32_t* const last4[4], uint32_t log_size, uint32_t claimed_sum_out[4]) {
+    u32* dsum = nullptr;
+    CM_CUDA(cudaMallocAsync(&dsum, 16, stream()));
+    if (int e = cm31_logup_finalize_last_async(last4, log_size, dsum)) return e;
+    CM_CUDA(cudaMemcpyAsync(claimed_sum_out, dsum, 16, cudaMemcpyDeviceToHost, stream()));
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    CM_CUDA(cudaFreeAsync(dsum, stream()));
     return 0;
 }
 

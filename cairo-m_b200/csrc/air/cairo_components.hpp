@@ -11,6 +11,11 @@
 //   jnz_fp_imm     .../opcodes/jnz_fp_imm.rs:121-232, :351-446
 //   jmp_imm        .../opcodes/jmp_imm.rs:110-190, :285-345
 //   ret            .../opcodes/ret.rs:117-225, :386-486
+//   assert_eq_fp_imm     .../opcodes/assert_eq_fp_imm.rs:150-200, :323-417
+//   call_abs_imm         .../opcodes/call_abs_imm.rs:119-232, :381-494
+//   store_frame_pointer  .../opcodes/store_frame_pointer.rs:147-198, :321-417
+//   double_deref_fp_imm  .../opcodes/double_deref_fp_imm.rs:150-260, :395-509
+//   double_deref_fp_fp   .../opcodes/double_deref_fp_fp.rs:175-275, :430-562
 //   memory         crates/prover/src/components/memory.rs:93-195, :294-366
 //   clock_update   crates/prover/src/components/clock_update.rs:70-160, :217-262
 //   range_check_N  crates/prover/src/preprocessed/range_check/range_check_macro.rs:62-112, :171-183
@@ -34,6 +39,8 @@ inline size_t cairo_relation_size(int r) {
 constexpr u32 OP_STORE_ADD_FP_FP = 0, OP_STORE_SUB_FP_FP = 1, OP_STORE_MUL_FP_FP = 2, OP_STORE_DIV_FP_FP = 3;
 constexpr u32 OP_STORE_ADD_FP_IMM = 4, OP_STORE_MUL_FP_IMM = 6, OP_STORE_IMM = 9, OP_CALL_ABS_IMM = 10, OP_RET = 11;
 constexpr u32 OP_JMP_ABS_IMM = 12, OP_JMP_REL_IMM = 13, OP_JNZ_FP_IMM = 14;
+constexpr u32 OP_STORE_DOUBLE_DEREF_FP = 8, OP_STORE_DOUBLE_DEREF_FP_FP = 42, OP_STORE_FRAME_POINTER = 43;
+constexpr u32 OP_STORE_TO_DOUBLE_DEREF_FP_IMM = 44, OP_STORE_TO_DOUBLE_DEREF_FP_FP = 45, OP_ASSERT_EQ_FP_IMM = 50;
 
 constexpr u32 TREE_HEIGHT = 30;  // crates/prover/src/adapter/merkle.rs (memory address space 2^30)
 constexpr u32 LOG_SIZE_RC_20 = 20;
@@ -43,7 +50,7 @@ constexpr u32 RC20_LIMIT = (1u << LOG_SIZE_RC_20) - 1;  // crates/prover/src/ada
 // crates/prover/src/utils/data_accesses.rs:10-28)
 constexpr int IN_PC = 0, IN_FP = 1, IN_CLOCK = 2, IN_INST_PREV_CLOCK = 3, IN_INST0 = 4;
 constexpr int IN_ACC_BASE = 10, ACC_ADDRESS = 0, ACC_PREV_CLOCK = 1, ACC_PREV_VALUE = 2, ACC_VALUE = 3;
-constexpr int MAX_ACCESSES = 3;
+constexpr int MAX_ACCESSES = 4;  // double_deref_fp_fp touches 4 cells (the u32 families will need more)
 constexpr int N_BUNDLE_INPUTS = IN_ACC_BASE + 4 * MAX_ACCESSES;
 inline int in_acc(int k, int field) { return IN_ACC_BASE + 4 * k + field; }
 
@@ -420,6 +427,322 @@ struct RetEval : OpcodeEvalBase {
         t.out(8, t.in(in_acc(0, ACC_VALUE)));
     }
 };
+
+// ------------------------------------------------------------------ assert_eq_fp_imm
+struct AssertEqFpImmEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 9;
+    static const char* name() { return "assert_eq_fp_imm"; }
+    static std::vector<u32> opcodes() { return {OP_ASSERT_EQ_FP_IMM}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto opcode_constant = eval.f_const(OP_ASSERT_EQ_FP_IMM);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto src0_off = eval.next_trace_mask();
+        auto imm = eval.next_trace_mask();
+        auto op0_prev_clock = eval.next_trace_mask();
+        auto op0_val = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(op0_val - imm);
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, src0_off, imm});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src0_off, imm});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off, op0_prev_clock, op0_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off, clock, op0_val});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        t.out(0, t.enabler());
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, t.in(IN_INST0 + 2));
+        t.out(7, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(8, t.in(in_acc(0, ACC_VALUE)));
+    }
+};
+
+// ------------------------------------------------------------------ call_abs_imm
+struct CallAbsImmEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 11;
+    static const char* name() { return "call_abs_imm"; }
+    static std::vector<u32> opcodes() { return {OP_CALL_ABS_IMM}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto opcode_constant = eval.f_const(OP_CALL_ABS_IMM);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto off0 = eval.next_trace_mask();
+        auto off1 = eval.next_trace_mask();
+        auto op0_prev_clock = eval.next_trace_mask();
+        auto op0_prev_val = eval.next_trace_mask();
+        auto op0_plus_one_prev_clock = eval.next_trace_mask();
+        auto op0_plus_one_prev_val = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {off1, fp + off0 + one + one, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, off0, off1});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, off0, off1});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + off0, op0_prev_clock, op0_prev_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + off0, clock, fp});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + off0 + one, op0_plus_one_prev_clock, op0_plus_one_prev_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + off0 + one, clock, pc + one});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_plus_one_prev_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        t.out(0, t.enabler());
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, t.in(IN_INST0 + 2));
+        t.out(7, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(8, t.in(in_acc(0, ACC_PREV_VALUE)));
+        t.out(9, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(10, t.in(in_acc(1, ACC_PREV_VALUE)));
+    }
+};
+
+// ------------------------------------------------------------------ store_frame_pointer
+struct StoreFramePointerEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 9;
+    static const char* name() { return "store_frame_pointer"; }
+    static std::vector<u32> opcodes() { return {OP_STORE_FRAME_POINTER}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto opcode_constant = eval.f_const(OP_STORE_FRAME_POINTER);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto imm = eval.next_trace_mask();
+        auto dst_off = eval.next_trace_mask();
+        auto dst_prev_val = eval.next_trace_mask();
+        auto dst_prev_clock = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, imm, dst_off});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, imm, dst_off});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_clock, dst_prev_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, fp + imm});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        t.out(0, t.enabler());
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, t.in(IN_INST0 + 2));
+        t.out(7, t.in(in_acc(0, ACC_PREV_VALUE)));
+        t.out(8, t.in(in_acc(0, ACC_PREV_CLOCK)));
+    }
+};
+
+// ------------------------------------------------------------------ double_deref_fp_imm
+// StoreDoubleDerefFp: [fp+off2] = [[fp+off0]+off1];  StoreToDoubleDerefFpImm: [[fp+off0]+off1] = [fp+off2]
+struct DoubleDerefFpImmEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 17;
+    static const char* name() { return "double_deref_fp_imm"; }
+    static std::vector<u32> opcodes() { return {OP_STORE_DOUBLE_DEREF_FP, OP_STORE_TO_DOUBLE_DEREF_FP_IMM}; }
+    static u32 delta_inv() { return m31_inv(OP_STORE_TO_DOUBLE_DEREF_FP_IMM - OP_STORE_DOUBLE_DEREF_FP); }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto dinv = eval.f_const(delta_inv());
+        auto base_opcode = eval.f_const(OP_STORE_DOUBLE_DEREF_FP);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto opcode_constant = eval.next_trace_mask();
+        auto off0 = eval.next_trace_mask();
+        auto off1 = eval.next_trace_mask();
+        auto off2 = eval.next_trace_mask();
+        auto val0 = eval.next_trace_mask();
+        auto prev_clock0 = eval.next_trace_mask();
+        auto addr1 = eval.next_trace_mask();
+        auto val1 = eval.next_trace_mask();
+        auto prev_clock1 = eval.next_trace_mask();
+        auto addr2 = eval.next_trace_mask();
+        auto prev_val2 = eval.next_trace_mask();
+        auto prev_clock2 = eval.next_trace_mask();
+        auto write_lhs = (opcode_constant - base_opcode) * dinv;
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(write_lhs * (one - write_lhs));
+        eval.add_constraint(enabler * (addr1 - write_lhs * (fp + off2) - (one - write_lhs) * (val0 + off1)));
+        eval.add_constraint(enabler * (addr2 - write_lhs * (val0 + off1) - (one - write_lhs) * (fp + off2)));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, off0, off1, off2});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, off0, off1, off2});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + off0, prev_clock0, val0});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + off0, clock, val0});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {addr1, prev_clock1, val1});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {addr1, clock, val1});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {addr2, prev_clock2, prev_val2});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {addr2, clock, val1});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - prev_clock0 - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - prev_clock1 - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - prev_clock2 - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto enabler = t.enabler();
+        auto one = t.f_const(1);
+        auto base_opcode = t.f_const(OP_STORE_DOUBLE_DEREF_FP);
+        // padding rows hold the default bundle (a Ret): the reference rewrites their opcode to
+        // STORE_DOUBLE_DEREF_FP (double_deref_fp_imm.rs:183-189)
+        auto opcode_constant = enabler * (t.in(IN_INST0) - base_opcode) + base_opcode;
+        auto fp = t.in(IN_FP);
+        auto off1 = t.in(IN_INST0 + 2), off2 = t.in(IN_INST0 + 3);
+        auto val0 = t.in(in_acc(0, ACC_VALUE));
+        auto write_lhs = (opcode_constant - base_opcode) * t.f_const(delta_inv());
+        auto addr1 = write_lhs * (fp + off2) + (one - write_lhs) * (val0 + off1);
+        auto addr2 = write_lhs * (val0 + off1) + (one - write_lhs) * (fp + off2);
+        t.out(0, enabler);
+        t.out(1, t.in(IN_PC));
+        t.out(2, fp);
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, opcode_constant);
+        t.out(6, t.in(IN_INST0 + 1));
+        t.out(7, off1);
+        t.out(8, off2);
+        t.out(9, val0);
+        t.out(10, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(11, addr1);
+        t.out(12, t.in(in_acc(1, ACC_VALUE)));
+        t.out(13, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(14, addr2);
+        t.out(15, t.in(in_acc(2, ACC_PREV_VALUE)));
+        t.out(16, t.in(in_acc(2, ACC_PREV_CLOCK)));
+    }
+};
+
+// ------------------------------------------------------------------ double_deref_fp_fp
+// StoreDoubleDerefFpFp: [fp+off2] = [[fp+off0]+[fp+off1]];  StoreToDoubleDerefFpFp: the reverse
+struct DoubleDerefFpFpEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 19;
+    static const char* name() { return "double_deref_fp_fp"; }
+    static std::vector<u32> opcodes() { return {OP_STORE_DOUBLE_DEREF_FP_FP, OP_STORE_TO_DOUBLE_DEREF_FP_FP}; }
+    static u32 delta_inv() { return m31_inv(OP_STORE_TO_DOUBLE_DEREF_FP_FP - OP_STORE_DOUBLE_DEREF_FP_FP); }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto base_opcode = eval.f_const(OP_STORE_DOUBLE_DEREF_FP_FP);
+        auto dinv = eval.f_const(delta_inv());
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto opcode_constant = eval.next_trace_mask();
+        auto off0 = eval.next_trace_mask();
+        auto off1 = eval.next_trace_mask();
+        auto off2 = eval.next_trace_mask();
+        auto val0 = eval.next_trace_mask();
+        auto prev_clock0 = eval.next_trace_mask();
+        auto val1 = eval.next_trace_mask();
+        auto prev_clock1 = eval.next_trace_mask();
+        auto addr2 = eval.next_trace_mask();
+        auto val2 = eval.next_trace_mask();
+        auto prev_clock2 = eval.next_trace_mask();
+        auto addr3 = eval.next_trace_mask();
+        auto prev_val3 = eval.next_trace_mask();
+        auto prev_clock3 = eval.next_trace_mask();
+        auto write_lhs = (opcode_constant - base_opcode) * dinv;
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(write_lhs * (one - write_lhs));
+        eval.add_constraint(enabler * (addr2 - write_lhs * (fp + off2) - (one - write_lhs) * (val0 + val1)));
+        eval.add_constraint(enabler * (addr3 - write_lhs * (val0 + val1) - (one - write_lhs) * (fp + off2)));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, off0, off1, off2});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, off0, off1, off2});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + off0, prev_clock0, val0});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + off0, clock, val0});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + off1, prev_clock1, val1});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + off1, clock, val1});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {addr2, prev_clock2, val2});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {addr2, clock, val2});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {addr3, prev_clock3, prev_val3});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {addr3, clock, val2});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - prev_clock0 - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - prev_clock1 - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - prev_clock2 - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - prev_clock3 - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto enabler = t.enabler();
+        auto one = t.f_const(1);
+        auto base_opcode = t.f_const(OP_STORE_DOUBLE_DEREF_FP_FP);
+        auto opcode_constant = enabler * (t.in(IN_INST0) - base_opcode) + base_opcode;  // double_deref_fp_fp.rs:189-196
+        auto fp = t.in(IN_FP);
+        auto off2 = t.in(IN_INST0 + 3);
+        auto val0 = t.in(in_acc(0, ACC_VALUE)), val1 = t.in(in_acc(1, ACC_VALUE));
+        auto write_lhs = (opcode_constant - base_opcode) * t.f_const(delta_inv());
+        auto addr2 = write_lhs * (fp + off2) + (one - write_lhs) * (val0 + val1);
+        auto addr3 = write_lhs * (val0 + val1) + (one - write_lhs) * (fp + off2);
+        t.out(0, enabler);
+        t.out(1, t.in(IN_PC));
+        t.out(2, fp);
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, opcode_constant);
+        t.out(6, t.in(IN_INST0 + 1));
+        t.out(7, t.in(IN_INST0 + 2));
+        t.out(8, off2);
+        t.out(9, val0);
+        t.out(10, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(11, val1);
+        t.out(12, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(13, addr2);
+        t.out(14, t.in(in_acc(2, ACC_VALUE)));
+        t.out(15, t.in(in_acc(2, ACC_PREV_CLOCK)));
+        t.out(16, addr3);
+        t.out(17, t.in(in_acc(3, ACC_PREV_VALUE)));
+        t.out(18, t.in(in_acc(3, ACC_PREV_CLOCK)));
+    }
+};
+
+// Opcode components in claim order (crates/prover/src/components/opcodes/mod.rs:223-268); the u32 /
+// bitwise families and store_le_fp_imm are not restated yet.
+#define CM31_OPCODE_EVALS(X)                                                                                          \
+    X(AssertEqFpImmEval) X(CallAbsImmEval) X(JmpImmEval) X(JnzFpImmEval) X(RetEval) X(StoreImmEval) X(StoreFpFpEval) \
+    X(StoreFpImmEval) X(DoubleDerefFpImmEval) X(DoubleDerefFpFpEval) X(StoreFramePointerEval)
 
 // ------------------------------------------------------------------ memory (boundary values)
 // inputs: address, clock, value0..3, multiplicity, root

@@ -159,7 +159,19 @@ inline RelationSet draw_cairo_relations(Blake2sChannel& ch) {  // components/mod
 
 inline std::vector<std::string> cairo_preprocessed_ids() { return {"range_check_8", "range_check_16", "range_check_20"}; }
 inline std::vector<std::string> cairo_component_names() {
-    return {"jmp_imm", "jnz_fp_imm", "ret", "store_imm", "store_fp_fp", "store_fp_imm", "memory", "clock_update", "range_check_8", "range_check_16", "range_check_20"};
+    std::vector<std::string> names;
+#define CM31_X(E) names.push_back(E::name());
+    CM31_OPCODE_EVALS(CM31_X)
+#undef CM31_X
+    for (const char* n : {"memory", "clock_update", "range_check_8", "range_check_16", "range_check_20"}) names.push_back(n);
+    return names;
+}
+inline size_t n_opcode_components() {
+    size_t n = 0;
+#define CM31_X(E) n++;
+    CM31_OPCODE_EVALS(CM31_X)
+#undef CM31_X
+    return n;
 }
 
 inline u32 padded_log_size(size_t n_real) {
@@ -174,12 +186,9 @@ struct CairoComponents {
     typedef typename Impl::B B;
     template <class Eval>
     using Comp = typename Impl::template Component<Eval>;
-    std::unique_ptr<Comp<JmpImmEval>> jmp_imm;
-    std::unique_ptr<Comp<JnzFpImmEval>> jnz_fp_imm;
-    std::unique_ptr<Comp<RetEval>> ret;
-    std::unique_ptr<Comp<StoreImmEval>> store_imm;
-    std::unique_ptr<Comp<StoreFpFpEval>> store_fp_fp;
-    std::unique_ptr<Comp<StoreFpImmEval>> store_fp_imm;
+#define CM31_X(E) std::unique_ptr<Comp<E>> c_##E;
+    CM31_OPCODE_EVALS(CM31_X)
+#undef CM31_X
     std::unique_ptr<Comp<MemoryEval>> memory;
     std::unique_ptr<Comp<ClockUpdateEval>> clock_update;
     std::unique_ptr<Comp<RangeCheckEval>> rc8, rc16, rc20;
@@ -191,26 +200,21 @@ struct CairoComponents {
             b.log_size_ = l;
             return b;
         };
-        jmp_imm.reset(new Comp<JmpImmEval>(JmpImmEval{base(ls[0])}, rel));
-        jnz_fp_imm.reset(new Comp<JnzFpImmEval>(JnzFpImmEval{base(ls[1])}, rel));
-        ret.reset(new Comp<RetEval>(RetEval{base(ls[2])}, rel));
-        store_imm.reset(new Comp<StoreImmEval>(StoreImmEval{base(ls[3])}, rel));
-        store_fp_fp.reset(new Comp<StoreFpFpEval>(StoreFpFpEval{base(ls[4])}, rel));
-        store_fp_imm.reset(new Comp<StoreFpImmEval>(StoreFpImmEval{base(ls[5])}, rel));
-        memory.reset(new Comp<MemoryEval>(MemoryEval{base(ls[6])}, rel));
-        clock_update.reset(new Comp<ClockUpdateEval>(ClockUpdateEval{base(ls[7])}, rel));
-        rc8.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls[8]), REL_RC8}, rel));
-        rc16.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls[9]), REL_RC16}, rel));
-        rc20.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls[10]), REL_RC20}, rel));
+        size_t i = 0;
+#define CM31_X(E) c_##E.reset(new Comp<E>(E{base(ls.at(i++))}, rel));
+        CM31_OPCODE_EVALS(CM31_X)
+#undef CM31_X
+        memory.reset(new Comp<MemoryEval>(MemoryEval{base(ls.at(i++))}, rel));
+        clock_update.reset(new Comp<ClockUpdateEval>(ClockUpdateEval{base(ls.at(i++))}, rel));
+        rc8.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls.at(i)), REL_RC8}, rel));
+        rc16.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls.at(i + 1)), REL_RC16}, rel));
+        rc20.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls.at(i + 2)), REL_RC20}, rel));
     }
     template <class Fn>
     void for_each(Fn fn) {
-        fn(*jmp_imm);
-        fn(*jnz_fp_imm);
-        fn(*ret);
-        fn(*store_imm);
-        fn(*store_fp_fp);
-        fn(*store_fp_imm);
+#define CM31_X(E) fn(*c_##E);
+        CM31_OPCODE_EVALS(CM31_X)
+#undef CM31_X
         fn(*memory);
         fn(*clock_update);
         fn(*rc8);
@@ -247,7 +251,7 @@ struct StagedInput {
     };
     typename Impl::Words accesses;
     size_t n_accesses = 0;
-    std::vector<Rows> opcode;  // jmp_imm, jnz_fp_imm, ret, store_imm, store_fp_fp, store_fp_imm
+    std::vector<Rows> opcode;  // one per opcode component, CM31_OPCODE_EVALS order
     Rows memory, clock_update;
     size_t bytes = 0;  // total bytes staged
 };
@@ -275,12 +279,9 @@ StagedInput<Impl> stage_input(const ProverInput& input) {
         st.bytes += r.n_real * sizeof(Bundle);
         st.opcode.push_back(std::move(r));
     };
-    opcode_rows(JmpImmEval::opcodes());
-    opcode_rows(JnzFpImmEval::opcodes());
-    opcode_rows(RetEval::opcodes());
-    opcode_rows(StoreImmEval::opcodes());
-    opcode_rows(StoreFpFpEval::opcodes());
-    opcode_rows(StoreFpImmEval::opcodes());
+#define CM31_X(E) opcode_rows(E::opcodes());
+    CM31_OPCODE_EVALS(CM31_X)
+#undef CM31_X
     {  // memory (components/memory.rs:93-195): initial rows then final rows
         std::vector<u32> rows;
         for (const std::vector<MemoryRow>* v : {&input.initial_memory, &input.final_memory})
@@ -346,12 +347,9 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         log_sizes.push_back(ls);
         traces.push_back(Impl::template write_trace<Eval>(eval, inputs, (u32)rows.n_real));
     };
-    opcode_trace(JmpImmEval{});
-    opcode_trace(JnzFpImmEval{});
-    opcode_trace(RetEval{});
-    opcode_trace(StoreImmEval{});
-    opcode_trace(StoreFpFpEval{});
-    opcode_trace(StoreFpImmEval{});
+#define CM31_X(E) opcode_trace(E{});
+    CM31_OPCODE_EVALS(CM31_X)
+#undef CM31_X
     {
         u32 ls = padded_log_size(staged.memory.n_real);
         std::vector<Col> inputs = Impl::unpack_rows(staged.memory.words, staged.memory.n_real, 8, ls);
@@ -381,7 +379,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
             Col bins = B::zeros((size_t)1 << rc_bits[k]);
             size_t ci = 0;
             auto emit = [&](auto& comp) {
-                if (ci < 6) {  // opcode components only
+                if (ci < n_opcode_components()) {  // opcode components only
                     std::vector<const Col*> tc;
                     for (auto& e : traces[ci]) tc.push_back(&e.values);
                     Impl::emit_lookups(comp, rc_rel[k], tc, bins);
@@ -434,10 +432,11 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
             std::vector<const Col*> tc;
             for (auto& c : trace_copies[ci]) tc.push_back(&c);
             auto cols = comp.gen_interaction_trace(tc, pre_lookup);
-            proof.interaction_claim.claimed_sums.push_back(comp.claimed_sum);
             for (auto& e : cols) interaction.push_back(std::move(e));
             ci++;
         });
+        Impl::collect_claimed_sums(components);
+        components.for_each([&](auto& comp) { proof.interaction_claim.claimed_sums.push_back(comp.claimed_sum); });
         for (auto& s : proof.interaction_claim.claimed_sums) channel.mix_felts({s});  // InteractionClaim::mix_into
         trace_copies.clear();
         commitment_scheme.commit_evals(std::move(interaction), channel);

@@ -91,6 +91,61 @@ inline std::vector<Word4> fibonacci_loop_program() {
 }
 inline size_t fibonacci_loop_steps(u32 n) { return 8 * (size_t)n + 8; }
 
+// ------------------------------------------------------------------ program: array_sum
+// Exercises the call / pointer opcode families: main fills arr[i] = i*i through a frame pointer
+// (StoreFramePointer, StoreToDoubleDerefFpFp), patches arr[1] (StoreToDoubleDerefFpImm), calls
+// sum(ptr, n) (CallAbsImm / Ret, StoreDoubleDerefFpFp), reads arr[0] back (StoreDoubleDerefFp) and
+// asserts it is 0 (AssertEqFpImm).  Returns sum_{i<n} i^2 - 1 + n  (n >= 2).
+// main frame: [fp-4] = n, [fp-3] = return slot; locals fp+0..7; callee frame at fp+8 (its fp = fp+10,
+// args ptr = [fp'-4], n = [fp'-3], result [fp'-5]); the array starts at fp+20.
+inline std::vector<Word4> array_sum_program() {
+    const u32 M3 = P - 3, M4 = P - 4, M5 = P - 5, M8 = P - 8;
+    return {
+        {{OP_STORE_FRAME_POINTER, 20, 0, 0}},               //  0: ptr = fp + 20
+        {{OP_STORE_IMM, 0, 1, 0}},                          //  1: i = 0
+        {{OP_STORE_SUB_FP_FP, 1, M4, 2}},                   //  2: [fp+2] = i - n
+        {{OP_JNZ_FP_IMM, 2, 2, 0}},                         //  3: if != 0 -> 5
+        {{OP_JMP_REL_IMM, 7, 0, 0}},                        //  4: -> 11
+        {{OP_STORE_ADD_FP_IMM, 1, 0, 5}},                   //  5: [fp+5] = i   (one step never touches a cell twice)
+        {{OP_STORE_MUL_FP_FP, 1, 5, 3}},                    //  6: v = i * i
+        {{OP_STORE_TO_DOUBLE_DEREF_FP_FP, 0, 1, 3}},        //  7: ptr[i] = v
+        {{OP_STORE_ADD_FP_IMM, 1, 1, 4}},                   //  8: [fp+4] = i + 1
+        {{OP_STORE_ADD_FP_IMM, 4, 0, 1}},                   //  9: i = [fp+4]
+        {{OP_JMP_REL_IMM, M8, 0, 0}},                       // 10: -> 2
+        {{OP_STORE_TO_DOUBLE_DEREF_FP_IMM, 0, 1, 1}},       // 11: ptr[1] = i (= n)
+        {{OP_STORE_ADD_FP_IMM, 0, 0, 6}},                   // 12: arg ptr
+        {{OP_STORE_ADD_FP_IMM, M4, 0, 7}},                  // 13: arg n
+        {{OP_CALL_ABS_IMM, 8, 20, 0}},                      // 14: call sum (frame at fp+8)
+        {{OP_STORE_DOUBLE_DEREF_FP, 0, 0, 4}},              // 15: [fp+4] = ptr[0]
+        {{OP_ASSERT_EQ_FP_IMM, 4, 0, 0}},                   // 16: assert ptr[0] == 0
+        {{OP_STORE_ADD_FP_IMM, 5, 0, M3}},                  // 17: return value = sum (callee wrote [fp+5])
+        {{OP_RET, 0, 0, 0}},                                // 18
+        {{OP_JMP_REL_IMM, 0, 0, 0}},                        // 19: (unreachable filler)
+        {{OP_STORE_IMM, 0, 0, 0}},                          // 20: sum: acc = 0
+        {{OP_STORE_IMM, 0, 1, 0}},                          // 21: j = 0
+        {{OP_STORE_SUB_FP_FP, 1, M3, 2}},                   // 22: [fp+2] = j - n
+        {{OP_JNZ_FP_IMM, 2, 2, 0}},                         // 23: if != 0 -> 25
+        {{OP_JMP_REL_IMM, 7, 0, 0}},                        // 24: -> 31
+        {{OP_STORE_DOUBLE_DEREF_FP_FP, M4, 1, 3}},          // 25: x = ptr[j]
+        {{OP_STORE_ADD_FP_FP, 0, 3, 4}},                    // 26: t = acc + x
+        {{OP_STORE_ADD_FP_IMM, 4, 0, 0}},                   // 27: acc = t
+        {{OP_STORE_ADD_FP_IMM, 1, 1, 5}},                   // 28: [fp+5] = j + 1
+        {{OP_STORE_ADD_FP_IMM, 5, 0, 1}},                   // 29: j = [fp+5]
+        {{OP_JMP_REL_IMM, M8, 0, 0}},                       // 30: -> 22
+        {{OP_STORE_ADD_FP_IMM, 0, 0, M5}},                  // 31: result -> [fp-5]
+        {{OP_RET, 0, 0, 0}},                                // 32
+    };
+}
+
+enum CairoProgramId : u32 { PROGRAM_FIBONACCI_LOOP = 0, PROGRAM_ARRAY_SUM = 1 };
+inline std::vector<Word4> program_by_id(u32 id) {
+    switch (id) {
+        case PROGRAM_FIBONACCI_LOOP: return fibonacci_loop_program();
+        case PROGRAM_ARRAY_SUM: return array_sum_program();
+        default: throw std::runtime_error("unknown program id");
+    }
+}
+
 // ------------------------------------------------------------------ VM
 struct VmTrace {
     std::vector<Registers> trace;                        // one entry per step + the final state
@@ -165,6 +220,52 @@ inline VmTrace run_program(const std::vector<Word4>& program, u32 arg, size_t ma
                 pc = cond != 0 ? m31_add(pc, b) : pc + 1;
                 break;
             }
+            case OP_CALL_ABS_IMM: {  // call.rs:48-61: [fp+off0] = fp, [fp+off0+1] = pc+1, fp += off0+2, pc = target
+                wr(m31_add(fp, a), fp);
+                wr(m31_add(m31_add(fp, a), 1), pc + 1);
+                fp = m31_add(m31_add(fp, a), 2);
+                pc = b;
+                break;
+            }
+            case OP_ASSERT_EQ_FP_IMM: {  // assert.rs:13-26
+                if (rd(m31_add(fp, a)) != b) throw std::runtime_error("vm: assertion failed");
+                pc += 1;
+                break;
+            }
+            case OP_STORE_FRAME_POINTER:  // [fp+dst_off] = fp + imm
+                wr(m31_add(fp, b), m31_add(fp, a));
+                pc += 1;
+                break;
+            case OP_STORE_DOUBLE_DEREF_FP: {  // [fp+dst] = [[fp+base]+imm]   (store.rs:201-213)
+                u32 base = rd(m31_add(fp, a));
+                u32 v = rd(m31_add(base, b));
+                wr(m31_add(fp, c), v);
+                pc += 1;
+                break;
+            }
+            case OP_STORE_TO_DOUBLE_DEREF_FP_IMM: {  // [[fp+base]+imm] = [fp+src]   (store.rs:258-275)
+                u32 base = rd(m31_add(fp, a));
+                u32 v = rd(m31_add(fp, c));
+                wr(m31_add(base, b), v);
+                pc += 1;
+                break;
+            }
+            case OP_STORE_DOUBLE_DEREF_FP_FP: {  // [fp+dst] = [[fp+base]+[fp+offset]]   (store.rs:219-245)
+                u32 base = rd(m31_add(fp, a));
+                u32 off = rd(m31_add(fp, b));
+                u32 v = rd(m31_add(base, off));
+                wr(m31_add(fp, c), v);
+                pc += 1;
+                break;
+            }
+            case OP_STORE_TO_DOUBLE_DEREF_FP_FP: {  // [[fp+base]+[fp+offset]] = [fp+src]   (store.rs:284-303)
+                u32 base = rd(m31_add(fp, a));
+                u32 off = rd(m31_add(fp, b));
+                u32 v = rd(m31_add(fp, c));
+                wr(m31_add(base, off), v);
+                pc += 1;
+                break;
+            }
             case OP_JMP_ABS_IMM: pc = a; break;
             case OP_JMP_REL_IMM: pc = m31_add(pc, a); break;
             case OP_RET: {
@@ -190,6 +291,10 @@ inline int opcode_memory_accesses(u32 op) {
         case OP_JNZ_FP_IMM: return 1;
         case OP_JMP_ABS_IMM: case OP_JMP_REL_IMM: return 0;
         case OP_RET: return 2;
+        case OP_CALL_ABS_IMM: return 2;
+        case OP_ASSERT_EQ_FP_IMM: case OP_STORE_FRAME_POINTER: return 1;
+        case OP_STORE_DOUBLE_DEREF_FP: case OP_STORE_TO_DOUBLE_DEREF_FP_IMM: return 3;
+        case OP_STORE_DOUBLE_DEREF_FP_FP: case OP_STORE_TO_DOUBLE_DEREF_FP_FP: return 4;
         default: return -1;
     }
 }
@@ -197,7 +302,7 @@ inline int opcode_size_in_m31s(u32 op) {
     switch (op) {
         case OP_RET: return 1;
         case OP_JMP_ABS_IMM: case OP_JMP_REL_IMM: return 2;
-        case OP_STORE_IMM: case OP_JNZ_FP_IMM: return 3;
+        case OP_STORE_IMM: case OP_JNZ_FP_IMM: case OP_CALL_ABS_IMM: case OP_ASSERT_EQ_FP_IMM: case OP_STORE_FRAME_POINTER: return 3;
         default: return 4;
     }
 }

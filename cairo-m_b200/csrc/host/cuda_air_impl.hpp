@@ -94,6 +94,17 @@ struct CudaAirImpl {
         B::air_program(in, outp, eval.log_size(), prog);
         return out;
     }
+    // one device->host copy for the claimed sums of every component (InteractionClaim, components/mod.rs:288-302)
+    template <class Components>
+    static void collect_claimed_sums(Components& components) {
+        std::vector<QM31> sums = B::collect_sums();
+        components.for_each([&](auto& c) {
+            if (c.pending_sum_slot >= 0) {
+                c.claimed_sum = sums.at((size_t)c.pending_sum_slot);
+                c.pending_sum_slot = -1;
+            }
+        });
+    }
     template <class Comp>
     static void emit_lookups(Comp& comp, int relation, const std::vector<const Col*>& trace_cols, Col& bins) {
         comp.emit_lookups(relation, trace_cols, bins);

@@ -240,6 +240,33 @@ struct CudaBackend {
         cm_check(cm31_air_program(s.data(), s.size(), d.data(), d.size(), log_size, prog.code.data(), prog.code.size(), prog.n_regs,
                                   prog.consts.data(), prog.consts.size()));
     }
+    // Claimed sums of one interaction phase: finalize_last is stream-ordered and writes into a device
+    // arena; collect_sums() reads every pending sum with ONE copy.
+    struct SumArena {
+        DeviceCol buf;
+        size_t used = 0;
+    };
+    static SumArena& sums() {
+        static SumArena a;
+        return a;
+    }
+    static size_t logup_finalize_last_async(const std::array<Col*, 4>& last, u32 log_size) {
+        SumArena& a = sums();
+        if (a.buf.size() == 0) a.buf = DeviceCol(4 * 256);
+        if (a.used >= 256) throw CudaError("too many pending claimed sums");
+        u32* l4[4] = {last[0]->ptr(), last[1]->ptr(), last[2]->ptr(), last[3]->ptr()};
+        cm_check(cm31_logup_finalize_last_async(l4, log_size, a.buf.ptr() + 4 * a.used));
+        return a.used++;
+    }
+    static std::vector<QM31> collect_sums() {
+        SumArena& a = sums();
+        std::vector<u32> h(4 * a.used + 4);
+        if (a.used) cm_check(cm31_d2h(h.data(), a.buf.ptr(), a.used * 16));
+        std::vector<QM31> out;
+        for (size_t i = 0; i < a.used; i++) out.push_back(qm_make(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]));
+        a.used = 0;
+        return out;
+    }
     static QM31 logup_finalize_last(const std::array<Col*, 4>& last, u32 log_size) {
         u32* l4[4] = {last[0]->ptr(), last[1]->ptr(), last[2]->ptr(), last[3]->ptr()};
         u32 cs[4];

@@ -165,6 +165,7 @@ class FrameworkComponent : public ComponentProver<B> {
     std::vector<TreeSubspan> trace_locations;
     std::vector<size_t> preprocessed_indices;
     QM31 claimed_sum = {0, 0, 0, 0};
+    long pending_sum_slot = -1;  // index into the backend's pending claimed sums, -1 = none
 
     FrameworkComponent(Eval e, const RelationSet* rel) : eval(std::move(e)), captured(capture_air(eval)), ev(captured->ev), relations(rel) {}
     // FrameworkComponent::new (component.rs:139-180): trace locations in component creation order.
@@ -297,7 +298,8 @@ class FrameworkComponent : public ComponentProver<B> {
         fill_params(prog, eval_params());  // cumsum shift is unused by this program
         B::air_program(in, outp, log_size(), prog);
         std::array<Col*, 4> last = {outp[4 * n_batches - 4], outp[4 * n_batches - 3], outp[4 * n_batches - 2], outp[4 * n_batches - 1]};
-        claimed_sum = B::logup_finalize_last(last, log_size());
+        // stream-ordered: the sum is fetched later by the driver (Impl::collect_claimed_sums)
+        pending_sum_slot = (long)B::logup_finalize_last_async(last, log_size());
         return out;
     }
 

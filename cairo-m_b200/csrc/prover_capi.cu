@@ -60,10 +60,13 @@ static void pin_range(cm31_prover_input* h, const void* p, size_t bytes) {
 extern "C" {
 
 // Runs the (host) VM + adapter for fibonacci_loop(n): the prover input of crates/prover/src/adapter.
-int cm31_fib_input_create(uint32_t n, cm31_prover_input** out) {
+int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out);
+int cm31_fib_input_create(uint32_t n, cm31_prover_input** out) { return cm31_program_input_create(PROGRAM_FIBONACCI_LOOP, n, out); }
+// program_id: 0 = fibonacci_loop(n), 1 = array_sum(n) (call / frame-pointer / double-deref / assert opcodes)
+int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out) {
     try {
-        CM_REQUIRE(out != nullptr, "fib_input_create: null out");
-        VmTrace vm = run_program(fibonacci_loop_program(), n);
+        CM_REQUIRE(out != nullptr, "program_input_create: null out");
+        VmTrace vm = run_program(program_by_id(program_id), n);
         cm31_prover_input* h = new cm31_prover_input();
         h->input = import_from_vm(vm);
         h->return_value = vm.return_value;

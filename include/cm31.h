@@ -168,6 +168,9 @@ int cm31_air_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* cons
 /* finalize_last (logup.rs:211-251): claimed_sum = sum(last col); last col -= claimed_sum/n;
  * inclusive prefix sum in coset order (simd/prefix_sum.rs:19, index map core/utils.rs:121-143). */
 int cm31_logup_finalize_last(uint32_t* const last4[4], uint32_t log_size, uint32_t claimed_sum_out[4]);
+/* same, stream-ordered: the claimed sum lands in 4 DEVICE words; the prover reads the sums of all
+ * components with one copy after the interaction trace is generated */
+int cm31_logup_finalize_last_async(uint32_t* const last4[4], uint32_t log_size, uint32_t* claimed_sum_dev);
 /* multiplicity histograms (P/src/preprocessed/range_check/range_check_macro.rs:72-84) */
 int cm31_histogram(const uint32_t* values, size_t n, uint32_t* bins, uint32_t log_bins);
 
@@ -178,6 +181,8 @@ int cm31_histogram(const uint32_t* values, size_t n, uint32_t* bins, uint32_t lo
  * (host VM + adapter, the serial step BEFORE the hot path) is built in this round. */
 typedef struct cm31_prover_input cm31_prover_input;
 int cm31_fib_input_create(uint32_t n, cm31_prover_input** out);
+/* program_id 0 = fibonacci_loop(n); 1 = array_sum(n): call/ret, frame pointer, double-deref and assert opcodes */
+int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out);
 int cm31_input_destroy(cm31_prover_input* h);
 /* info[0] VM steps, [1] data accesses, [2] boundary-memory rows, [3] return value, [4] input bytes staged per proof */
 int cm31_input_info(const cm31_prover_input* h, uint64_t info[5]);

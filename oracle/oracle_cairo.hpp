@@ -91,6 +91,8 @@ struct OracleAirImpl {
         for (auto& c : outs) out.push_back(cm31::CircleEvaluation<B>{std::move(c), eval.log_size()});
         return out;
     }
+    template <class Components>
+    static void collect_claimed_sums(Components&) {}  // the oracle computes them eagerly
     template <class Comp>
     static void emit_lookups(Comp& comp, int relation, const std::vector<const Col*>& trace_cols, Col& bins) {
         size_t n = (size_t)1 << comp.log_size();

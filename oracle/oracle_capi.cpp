@@ -243,9 +243,13 @@ int orc_verify_wide_fibonacci(u32 log_n_rows, u32 n_cols, const uint8_t* proof_b
 extern "C" {
 
 // prove_cairo_m on the scalar CPU oracle. timings_ms: preprocessed, trace, interaction, stark, total.
+int orc_program_prove(u32 program_id, u32 n, u32 pow_bits, u32 n_queries, uint8_t* out, size_t cap, size_t* out_len, double* timings_ms);
 int orc_fib_prove(u32 n, u32 pow_bits, u32 n_queries, uint8_t* out, size_t cap, size_t* out_len, double* timings_ms) {
+    return orc_program_prove(cm31::PROGRAM_FIBONACCI_LOOP, n, pow_bits, n_queries, out, cap, out_len, timings_ms);
+}
+int orc_program_prove(u32 program_id, u32 n, u32 pow_bits, u32 n_queries, uint8_t* out, size_t cap, size_t* out_len, double* timings_ms) {
     try {
-        cm31::ProverInput input = cm31::import_from_vm(cm31::run_program(cm31::fibonacci_loop_program(), n));
+        cm31::ProverInput input = cm31::import_from_vm(cm31::run_program(cm31::program_by_id(program_id), n));
         cm31::PcsConfig cfg = cm31::PcsConfig::regular_96_bits();
         cfg.pow_bits = pow_bits;
         cfg.fri_config.n_queries = n_queries;
@@ -280,9 +284,13 @@ int orc_cairo_verify(const uint8_t* proof_bytes, size_t len, u32 pow_bits, u32 n
 }
 
 // residual of the logup balance (0,0,0,0 expected); also returns fib(n) and the VM step count
+int orc_program_logup_residual(u32 program_id, u32 n, const uint8_t* proof_bytes, size_t len, u32* residual_out, u64* info_out);
 int orc_fib_logup_residual(u32 n, const uint8_t* proof_bytes, size_t len, u32* residual_out, u64* info_out) {
+    return orc_program_logup_residual(cm31::PROGRAM_FIBONACCI_LOOP, n, proof_bytes, len, residual_out, info_out);
+}
+int orc_program_logup_residual(u32 program_id, u32 n, const uint8_t* proof_bytes, size_t len, u32* residual_out, u64* info_out) {
     try {
-        cm31::VmTrace vm = cm31::run_program(cm31::fibonacci_loop_program(), n);
+        cm31::VmTrace vm = cm31::run_program(cm31::program_by_id(program_id), n);
         cm31::ProverInput input = cm31::import_from_vm(vm);
         cm31::CairoProof proof = cm31::CairoProof::from_bytes(proof_bytes, len, cm31::cairo_component_names());
         logup_residual(proof, input).to_u32(residual_out);

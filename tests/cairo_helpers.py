@@ -6,12 +6,19 @@ from tests import oracle_lib as orc
 CAP = 1 << 27
 
 
+FIB, ARRAY_SUM = 0, 1
+
+
 def oracle_fib_prove(n, pow_bits=16, n_queries=80):
+    return oracle_program_prove(FIB, n, pow_bits, n_queries)
+
+
+def oracle_program_prove(program, n, pow_bits=16, n_queries=80):
     lib = orc.lib()
     buf = (C.c_uint8 * CAP)()
     ln = C.c_size_t()
     tm = (C.c_double * 5)()
-    rc = lib.orc_fib_prove(n, pow_bits, n_queries, buf, C.c_size_t(CAP), C.byref(ln), tm)
+    rc = lib.orc_program_prove(program, n, pow_bits, n_queries, buf, C.c_size_t(CAP), C.byref(ln), tm)
     assert rc == 0, orc.last_error()
     return bytes(buf[: ln.value]), list(tm)
 
@@ -21,20 +28,20 @@ def oracle_cairo_verify(proof: bytes, pow_bits=16, n_queries=80) -> int:
     return orc.lib().orc_cairo_verify(buf, C.c_size_t(len(proof)), pow_bits, n_queries)
 
 
-def oracle_logup_residual(n, proof: bytes):
+def oracle_logup_residual(n, proof: bytes, program=FIB):
     buf = (C.c_uint8 * len(proof)).from_buffer_copy(proof)
     res = (C.c_uint32 * 4)()
     info = (C.c_uint64 * 3)()
-    rc = orc.lib().orc_fib_logup_residual(n, buf, C.c_size_t(len(proof)), res, info)
+    rc = orc.lib().orc_program_logup_residual(program, n, buf, C.c_size_t(len(proof)), res, info)
     assert rc == 0, orc.last_error()
     return tuple(res), {"fib": info[0], "steps": info[1], "clock_updates": info[2]}
 
 
 class GpuFibInput:
-    def __init__(self, cm, n):
+    def __init__(self, cm, n, program=FIB):
         self.cm = cm
         self.h = C.c_void_p()
-        cm.check(cm.lib().cm31_fib_input_create(C.c_uint32(n), C.byref(self.h)))
+        cm.check(cm.lib().cm31_program_input_create(C.c_uint32(program), C.c_uint32(n), C.byref(self.h)))
         info = (C.c_uint64 * 5)()
         cm.check(cm.lib().cm31_input_info(self.h, info))
         self.steps, self.accesses, self.memory_rows, self.return_value, self.h2d_bytes = list(info)
@@ -57,3 +64,10 @@ def fib_mod_p(n):
     for _ in range(n):
         a, b = b, (a + b) % orc.P
     return a
+
+
+def array_sum_expected(n):
+    vals = [(i * i) % orc.P for i in range(n)]
+    if n >= 2:
+        vals[1] = n
+    return sum(vals) % orc.P

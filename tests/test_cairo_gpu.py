@@ -65,3 +65,31 @@ def test_generated_air_kernels_match_the_bytecode_interpreter(cm):
         inp.close()
     assert gen == interp
     assert ch.oracle_cairo_verify(gen) == 0, ch.orc.last_error()
+
+
+@pytest.mark.parametrize("n", [2, 9, 300])
+def test_array_sum_proof_bit_exact(cm, n):
+    # the call / frame-pointer / double-deref / assert opcode components
+    inp = ch.GpuFibInput(cm, n, program=ch.ARRAY_SUM)
+    try:
+        assert inp.return_value == ch.array_sum_expected(n)
+        got, _ = inp.prove()
+    finally:
+        inp.close()
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+    residual, _ = ch.oracle_logup_residual(n, got, program=ch.ARRAY_SUM)
+    assert residual == (0, 0, 0, 0)
+    want, _ = ch.oracle_program_prove(ch.ARRAY_SUM, n)
+    assert got == want
+
+
+def test_array_sum_2_16_iterations_verifies(cm):
+    n = 1 << 16
+    inp = ch.GpuFibInput(cm, n, program=ch.ARRAY_SUM)
+    try:
+        got, _ = inp.prove()
+    finally:
+        inp.close()
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+    residual, _ = ch.oracle_logup_residual(n, got, program=ch.ARRAY_SUM)
+    assert residual == (0, 0, 0, 0)

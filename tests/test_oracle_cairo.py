@@ -35,3 +35,21 @@ def test_fib_wrong_claim_breaks_logup(fib10):
     # a proof for n=10 does not balance against the public data of n=11
     residual, _ = ch.oracle_logup_residual(11, fib10)
     assert residual != (0, 0, 0, 0)
+
+
+# ---- array_sum: CallAbsImm / Ret, StoreFramePointer, StoreDoubleDerefFp(Fp), StoreToDoubleDerefFp(Imm|Fp), AssertEqFpImm
+@pytest.fixture(scope="module")
+def arr7():
+    return ch.oracle_program_prove(ch.ARRAY_SUM, 7)[0]
+
+
+def test_array_sum_proof_verifies_and_balances(arr7):
+    assert ch.oracle_cairo_verify(arr7) == 0, ch.orc.last_error()
+    residual, info = ch.oracle_logup_residual(7, arr7, program=ch.ARRAY_SUM)
+    assert residual == (0, 0, 0, 0)
+    assert info["fib"] == ch.array_sum_expected(7)  # info[0] is the program's return value
+
+
+def test_array_sum_wrong_claim_breaks_logup(arr7):
+    residual, _ = ch.oracle_logup_residual(8, arr7, program=ch.ARRAY_SUM)
+    assert residual != (0, 0, 0, 0)

@@ -140,12 +140,9 @@ static Eval make(u32 log_size = 4) {
 int main(int argc, char** argv) {
     std::string outdir = argc > 1 ? argv[1] : ".";
     std::vector<std::string> acc;
-    component(outdir, make<JmpImmEval>(), acc);
-    component(outdir, make<JnzFpImmEval>(), acc);
-    component(outdir, make<RetEval>(), acc);
-    component(outdir, make<StoreImmEval>(), acc);
-    component(outdir, make<StoreFpFpEval>(), acc);
-    component(outdir, make<StoreFpImmEval>(), acc);
+#define CM31_X(E) component(outdir, make<E>(), acc);
+    CM31_OPCODE_EVALS(CM31_X)
+#undef CM31_X
     component(outdir, make<MemoryEval>(), acc);
     component(outdir, make<ClockUpdateEval>(), acc);
     {
