@@ -316,3 +316,21 @@ def test_gather_runs(cm):
     got = cm.gather_runs(cols, sid, widx, counts)
     want = [int(v) for s, w, c in zip(sid, widx, counts) for v in mat[s, w:w + c]]
     assert got == want
+
+
+def test_sharded_commit_world1_equals_layer_by_layer_oracle(cm):
+    # cairo-m_b200/sharded_commit.py on one GPU == interpolate -> LDE -> Merkle layers of the oracle
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("sharded_commit", Path(__file__).resolve().parent.parent / "cairo-m_b200" / "sharded_commit.py")
+    sc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sc)
+    L, n_cols = 10, 7
+    trace = orc.splitmix64(0x5EED, n_cols << L).reshape(n_cols, 1 << L)
+    root, rows = sc.sharded_commit(sc.CudaOps(L + 2), to_dev_cols(trace), n_cols, L, 1)
+    lde = orc.evaluate(orc.interpolate(trace, L), L, L + 1)
+    layer = orc.commit_on_layer(L + 1, None, lde)
+    for log in range(L, -1, -1):
+        layer = orc.commit_on_layer(log, layer, None)
+    assert np.array_equal(host(root), layer.reshape(8))
+    assert all(np.array_equal(host(rows[c]), lde[c]) for c in range(n_cols))
