@@ -248,6 +248,32 @@ int cm31_d2d(void* dst, const void* src, size_t bytes) {
     return 0;
 }
 
+// ---- peer memory (NVLink): buffers other ranks' kernels read directly (sharded commitment)
+int cm31_ipc_alloc(size_t bytes, void** out, uint8_t handle_out[64]) {
+    CM_REQUIRE(out != nullptr && handle_out != nullptr, "ipc_alloc: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CM_CUDA(cudaMalloc(out, bytes == 0 ? 4 : bytes));  // IPC handles need a cudaMalloc allocation, not the async pool
+    cudaIpcMemHandle_t h;
+    CM_CUDA(cudaIpcGetMemHandle(&h, *out));
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+int cm31_ipc_free(void* p) {
+    if (p) CM_CUDA(cudaFree(p));
+    return 0;
+}
+int cm31_ipc_open(const uint8_t handle[64], void** out) {
+    CM_REQUIRE(out != nullptr && handle != nullptr, "ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CM_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int cm31_ipc_close(void* p) {
+    if (p) CM_CUDA(cudaIpcCloseMemHandle(p));
+    return 0;
+}
+
 int cm31_gather_u32(const uint32_t* const* cols, size_t n_cols, const uint32_t* idx_host, size_t n_idx,
                     uint32_t* out_host) {
     if (n_cols == 0 || n_idx == 0) return 0;

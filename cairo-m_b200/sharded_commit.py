@@ -132,6 +132,90 @@ def sharded_commit(ops, local_cols, n_cols_total: int, log_size: int, log_blowup
     return layer.reshape(8), rows
 
 
+class PeerLde:
+    """The LDE buffers of all ranks, each visible to every rank's kernels (CUDA IPC over
+    NVLink/NVSwitch).  Built once per (column count, size); reused by every commit."""
+
+    def __init__(self, n_cols_total: int, log_eval: int, dist, rank: int, world: int):
+        import ctypes as C
+        import torch
+        self.cm = importlib.import_module("cairo-m_b200")
+        self.C, self.torch = C, torch
+        self.rank, self.world, self.m = rank, world, 1 << log_eval
+        self.n_cols_total = n_cols_total
+        lo, hi = column_range(n_cols_total, world, rank)
+        self.n_local = hi - lo
+        lib = self.cm.lib()
+        self.local = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        self.cm.check(lib.cm31_ipc_alloc(C.c_size_t(4 * max(1, self.n_local) * self.m), C.byref(self.local), handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        handles = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        if world > 1:
+            dist.all_gather(handles, mine)
+        else:
+            handles = [mine]
+        self.base = []
+        for p in range(world):
+            if p == rank:
+                self.base.append(self.local.value)
+                continue
+            ptr = C.c_void_p()
+            h = (C.c_uint8 * 64)(*handles[p].cpu().tolist())
+            self.cm.check(lib.cm31_ipc_open(h, C.byref(ptr)))
+            self.base.append(ptr.value)
+
+    def local_column(self, i: int) -> int:
+        return self.local.value + 4 * i * self.m
+
+    def row_range_columns(self, first_row: int):
+        """Device addresses of every global column at `first_row` (remote ones are peer mappings)."""
+        out = []
+        for p in range(self.world):
+            plo, phi = column_range(self.n_cols_total, self.world, p)
+            for i in range(phi - plo):
+                out.append(self.base[p] + 4 * (i * self.m + first_row))
+        return out
+
+    def close(self):
+        lib = self.cm.lib()
+        for p, b in enumerate(self.base):
+            if p != self.rank:
+                lib.cm31_ipc_close(self.C.c_void_p(b))
+        lib.cm31_ipc_free(self.local)
+        self.base = []
+
+
+def sharded_commit_p2p(ops, peer: PeerLde, local_cols, log_size: int, log_blowup: int, dist=None):
+    """Same result as sharded_commit, with the exchange FUSED into the leaf hashing: every rank's
+    Merkle leaf kernel reads its row range of all columns straight from the owners' LDE buffers
+    (peer loads over NVLink, coalesced 128 B per warp per column) while it hashes — no all-to-all,
+    no staging copies; the only collective left is the 32-byte-per-rank root all-gather."""
+    torch = ops.torch
+    rank, world = peer.rank, peer.world
+    log_eval = log_size + log_blowup
+    assert peer.m == 1 << log_eval and len(local_cols) == peer.n_local
+    log_rows = log_eval - _ilog2(world)
+    ops.interpolate(local_cols, log_size)
+    if local_cols:
+        ops.evaluate(local_cols, [peer.local_column(i) for i in range(peer.n_local)], log_size, log_eval)
+    ops.sync()
+    if world > 1:
+        dist.barrier()  # every owner's LDE is complete before anyone reads it
+    layer = ops.commit_layer(log_rows, None, peer.row_range_columns(rank << log_rows))
+    for log in range(log_rows - 1, -1, -1):
+        layer = ops.commit_layer(log, layer, [])
+    ops.sync()
+    if world > 1:
+        roots = [ops.empty((1, 8)) for _ in range(world)]
+        dist.all_gather(roots, layer.contiguous())  # also orders the peers' reads before the buffers are reused
+        layer = torch.cat(roots, dim=0)
+        for log in range(_ilog2(world) - 1, -1, -1):
+            layer = ops.commit_layer(log, layer, [])
+        ops.sync()
+    return layer.reshape(8)
+
+
 def commit_bytes_per_column(log_size: int, log_blowup: int) -> int:
     """Algorithmic bytes of the column pipeline: interpolate 8n + LDE 4n+4m + leaf read 4m."""
     n, m = 1 << log_size, 1 << (log_size + log_blowup)

@@ -59,6 +59,15 @@ int cm31_gather_runs(const uint32_t* const* srcs, size_t n_srcs, const uint32_t*
 /* same for hash columns: out_host[q*8..] = layer[idx[q]] */
 int cm31_gather_hash(const uint32_t* layer, const uint32_t* idx_host, size_t n_idx, uint32_t* out_host);
 
+/* Peer memory for the multi-GPU commitment (one process per GPU): a buffer allocated with
+ * cm31_ipc_alloc can be opened by the other ranks (cm31_ipc_open on the 64-byte handle) and passed to
+ * any kernel as a column pointer — the Merkle leaf kernel then reads remote LDE columns over
+ * NVLink/NVSwitch while it hashes, instead of waiting for an all-to-all. */
+int cm31_ipc_alloc(size_t bytes, void** out, uint8_t handle_out[64]);
+int cm31_ipc_free(void* dptr);
+int cm31_ipc_open(const uint8_t handle[64], void** out);
+int cm31_ipc_close(void* dptr);
+
 /* ------------------------------------------------------------------ PolyOps
  * S/prover/src/core/poly/circle/ops.rs:13-69, CPU definition S/prover/src/core/backend/cpu/circle.rs */
 typedef struct cm31_twiddles cm31_twiddles;

@@ -334,3 +334,22 @@ def test_sharded_commit_world1_equals_layer_by_layer_oracle(cm):
         layer = orc.commit_on_layer(log, layer, None)
     assert np.array_equal(host(root), layer.reshape(8))
     assert all(np.array_equal(host(rows[c]), lde[c]) for c in range(n_cols))
+
+
+def test_sharded_commit_p2p_world1_matches_nccl_variant(cm):
+    # the peer-memory (cudaIpc) layout of the fused exchange: same root as the all-to-all variant
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("sharded_commit", Path(__file__).resolve().parent.parent / "cairo-m_b200" / "sharded_commit.py")
+    sc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sc)
+    L, n_cols = 12, 6
+    trace = orc.splitmix64(0xABCD, n_cols << L).reshape(n_cols, 1 << L)
+    ops = sc.CudaOps(L + 2)
+    root_a, _ = sc.sharded_commit(ops, to_dev_cols(trace), n_cols, L, 1)
+    peer = sc.PeerLde(n_cols, L + 1, None, 0, 1)
+    try:
+        root_b = sc.sharded_commit_p2p(ops, peer, to_dev_cols(trace), L, 1)
+        assert np.array_equal(host(root_a), host(root_b))
+    finally:
+        peer.close()

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--mode", default="p2p", choices=["p2p", "nccl"], help="p2p: leaf kernel reads peer LDE buffers; nccl: all-to-all")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -56,6 +57,7 @@ def main():
     lo, hi = sc.column_range(args.cols, world, rank)
     times = []
     root = None
+    peer = sc.PeerLde(args.cols, args.log_size + 1, dist if world > 1 else None, rank, world) if args.mode == "p2p" else None
     for it in range(args.warmup + args.iters):
         cols = make_columns(lo, hi, n, device)
         torch.cuda.synchronize()
@@ -63,7 +65,10 @@ def main():
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        root, _ = sc.sharded_commit(ops, cols, args.cols, args.log_size, 1, dist if world > 1 else None, rank, world)
+        if peer is not None:
+            root = sc.sharded_commit_p2p(ops, peer, cols, args.log_size, 1, dist if world > 1 else None)
+        else:
+            root, _ = sc.sharded_commit(ops, cols, args.cols, args.log_size, 1, dist if world > 1 else None, rank, world)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -85,11 +90,15 @@ def main():
         total_bytes = sc.commit_bytes_per_column(args.log_size, 1) * args.cols
         peaks = ROOT / "MEASURED_PEAKS.json"
         peak = json.loads(peaks.read_text())["hbm_gbs"] if peaks.exists() else 6650.0
-        print(json.dumps({"bench": "sharded_commit", "n_gpus": world, "log_size": args.log_size, "cols": args.cols, "ms": ms,
+        print(json.dumps({"bench": "sharded_commit", "mode": args.mode, "n_gpus": world, "log_size": args.log_size, "cols": args.cols, "ms": ms,
                           "alg_GBps_aggregate": total_bytes / ms / 1e6, "alg_GBps_per_gpu": total_bytes / ms / 1e6 / world,
                           "frac_of_hbm_peak_per_gpu": total_bytes / ms / 1e6 / world / peak,
                           "all_to_all_bytes_per_gpu": 4 * (hi - lo) * (2 * n) * (world - 1) // world, "root_matches_single_gpu": ok,
                           "root": root.cpu().numpy().view("uint32").tolist()}), flush=True)
+    if peer is not None:
+        if world > 1:
+            dist.barrier()
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
 
