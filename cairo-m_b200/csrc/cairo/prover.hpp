@@ -260,7 +260,8 @@ template <class Impl>
 StagedInput<Impl> stage_input(const ProverInput& input) {
     StagedInput<Impl> st;
     st.n_accesses = input.data_accesses.size();
-    st.accesses = Impl::upload_words((const u32*)input.data_accesses.data(), st.n_accesses * 4);
+    st.accesses = Impl::alloc_words(st.n_accesses * 4);
+    Impl::copy_words(st.accesses, 0, (const u32*)input.data_accesses.data(), st.n_accesses * 4);
     st.bytes += st.n_accesses * 16;
     auto opcode_rows = [&](const std::vector<u32>& opcodes) {
         typename StagedInput<Impl>::Rows r;
@@ -334,6 +335,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     auto t1 = Impl::now_ms();
 
     // ---- tree 1: execution traces
+    Impl::staging_fence();  // the staged input (background copies) is complete from here on
     std::vector<u32> log_sizes;
     std::vector<std::vector<CircleEvaluation<B>>> traces;  // per component (kept until tree 2 is built)
     size_t opcode_index = 0;

@@ -41,14 +41,17 @@ struct CudaAirImpl {
         return o;
     }
     static Words alloc_words(size_t n_words) { return DeviceCol(std::max<size_t>(4, n_words)); }
+    // staging runs on the background copy stream; prove_cairo_m fences before the first use
     static void copy_words(Words& dst, size_t at, const u32* src, size_t n_words) {
-        if (n_words) cm_check(cm31_h2d(dst.ptr() + at, src, n_words * 4));
+        if (n_words) cm_check(cm31_h2d_bg(dst.ptr() + at, src, n_words * 4));
     }
     static Words upload_words(const u32* src, size_t n_words) {
         DeviceCol dev(std::max<size_t>(4, n_words));
+        // small row tables come from temporaries: copy them synchronously-staged on the main stream
         if (n_words) cm_check(cm31_h2d(dev.ptr(), src, n_words * 4));
         return dev;
     }
+    static void staging_fence() { cm_check(cm31_bg_fence()); }
     static std::vector<Col> unpack_bundles(const Words& rows, size_t n_real, const Words& accesses, size_t n_accesses, u32 log_size) {
         std::vector<Col> cols;
         std::vector<u32*> p;

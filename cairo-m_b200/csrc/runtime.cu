@@ -238,6 +238,35 @@ int cm31_h2d(void* dst, const void* src, size_t bytes) {
     CM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream()));
     return 0;
 }
+// Background host->device copies (prover-input staging): issued on a second stream so the DMA of
+// the execution bundles / access log overlaps the input-independent start of the proof
+// (twiddles, preprocessed tree).  cm31_h2d_bg orders the copy after everything already enqueued on
+// the main stream (the destination was just allocated there); cm31_bg_fence makes the main stream
+// wait for all background copies issued so far.
+static cudaStream_t g_copy_stream = nullptr;
+static cudaEvent_t g_copy_event = nullptr, g_main_event = nullptr;
+static int ensure_copy_stream() {
+    if (!g_copy_stream) {
+        CM_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+        CM_CUDA(cudaEventCreateWithFlags(&g_copy_event, cudaEventDisableTiming));
+        CM_CUDA(cudaEventCreateWithFlags(&g_main_event, cudaEventDisableTiming));
+    }
+    return 0;
+}
+int cm31_h2d_bg(void* dst, const void* src_host, size_t bytes) {
+    if (int e = ensure_copy_stream()) return e;
+    CM_CUDA(cudaEventRecord(g_main_event, stream()));
+    CM_CUDA(cudaStreamWaitEvent(g_copy_stream, g_main_event, 0));
+    CM_CUDA(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, g_copy_stream));
+    return 0;
+}
+int cm31_bg_fence(void) {
+    if (!g_copy_stream) return 0;
+    CM_CUDA(cudaEventRecord(g_copy_event, g_copy_stream));
+    CM_CUDA(cudaStreamWaitEvent(stream(), g_copy_event, 0));
+    return 0;
+}
+
 int cm31_d2h(void* dst, const void* src, size_t bytes) {
     CM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream()));
     CM_CUDA(cudaStreamSynchronize(stream()));

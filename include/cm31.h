@@ -42,6 +42,10 @@ int cm31_free(void* dptr);
 int cm31_memset0(void* dptr, size_t bytes);
 int cm31_h2d(void* dst, const void* src_host, size_t bytes);
 int cm31_d2h(void* dst_host, const void* src, size_t bytes);
+/* staging copies on a background stream (overlap with the input-independent start of a proof);
+ * cm31_bg_fence() orders the main stream after every background copy issued so far */
+int cm31_h2d_bg(void* dst, const void* src_host, size_t bytes);
+int cm31_bg_fence(void);
 int cm31_d2d(void* dst, const void* src, size_t bytes);
 /* Column::at for many (column,row) pairs at once (decommit):
  * out_host[c * n_idx + q] = cols[c][idx_host[q]]   (S/prover/src/core/vcs/prover.rs:125-140) */

@@ -10,10 +10,17 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 
 
+def free_port() -> int:
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def torchrun(nproc, *bench_args, timeout=240):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
-           "--master-port", "29613", str(ROOT / "bench.py"), *bench_args]
+           "--master-port", str(free_port()), str(ROOT / "bench.py"), *bench_args]
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
 
 

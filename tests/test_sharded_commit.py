@@ -9,6 +9,13 @@ from pathlib import Path
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
+
+
+def free_port() -> int:
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
 WORKER = ROOT / "tests" / "dist" / "sharded_commit_worker.py"
 
 
@@ -18,7 +25,7 @@ def run(world, log_size, log_blowup, n_cols, port):
         cmd = [sys.executable, str(WORKER), str(log_size), str(log_blowup), str(n_cols)]
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-               "--master-port", str(port), str(WORKER), str(log_size), str(log_blowup), str(n_cols)]
+               "--master-port", str(free_port()), str(WORKER), str(log_size), str(log_blowup), str(n_cols)]
     return subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
 
 
