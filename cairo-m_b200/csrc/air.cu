@@ -106,6 +106,9 @@ __global__ void __launch_bounds__(128) air_program_kernel(const u32* const* __re
             case OP_SHR: regs[dst] = regs[a] >> b; break;
             case OP_AND: regs[dst] = regs[a] & b; break;
             case OP_ROWLT: regs[dst] = row < __ldg(consts + a) ? 1u : 0u; break;
+            case OP_LE: regs[dst] = regs[a] <= regs[b] ? 1u : 0u; break;
+            case OP_DIVC: regs[dst] = regs[a] / b; break;
+            case OP_MODC: regs[dst] = regs[a] % b; break;
             default: break;
         }
     }

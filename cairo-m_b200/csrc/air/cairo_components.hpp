@@ -16,6 +16,7 @@
 //   store_frame_pointer  .../opcodes/store_frame_pointer.rs:147-198, :321-417
 //   double_deref_fp_imm  .../opcodes/double_deref_fp_imm.rs:150-260, :395-509
 //   double_deref_fp_fp   .../opcodes/double_deref_fp_fp.rs:175-275, :430-562
+//   store_le_fp_imm      .../opcodes/store_le_fp_imm.rs:195-400, :560-747
 //   memory         crates/prover/src/components/memory.rs:93-195, :294-366
 //   clock_update   crates/prover/src/components/clock_update.rs:70-160, :217-262
 //   range_check_N  crates/prover/src/preprocessed/range_check/range_check_macro.rs:62-112, :171-183
@@ -40,6 +41,7 @@ constexpr u32 OP_STORE_ADD_FP_FP = 0, OP_STORE_SUB_FP_FP = 1, OP_STORE_MUL_FP_FP
 constexpr u32 OP_STORE_ADD_FP_IMM = 4, OP_STORE_MUL_FP_IMM = 6, OP_STORE_IMM = 9, OP_CALL_ABS_IMM = 10, OP_RET = 11;
 constexpr u32 OP_JMP_ABS_IMM = 12, OP_JMP_REL_IMM = 13, OP_JNZ_FP_IMM = 14;
 constexpr u32 OP_STORE_DOUBLE_DEREF_FP = 8, OP_STORE_DOUBLE_DEREF_FP_FP = 42, OP_STORE_FRAME_POINTER = 43;
+constexpr u32 OP_STORE_LE_FP_IMM = 48;
 constexpr u32 OP_STORE_TO_DOUBLE_DEREF_FP_IMM = 44, OP_STORE_TO_DOUBLE_DEREF_FP_FP = 45, OP_ASSERT_EQ_FP_IMM = 50;
 
 constexpr u32 TREE_HEIGHT = 30;  // crates/prover/src/adapter/merkle.rs (memory address space 2^30)
@@ -738,11 +740,131 @@ struct DoubleDerefFpFpEval : OpcodeEvalBase {
     }
 };
 
+// ------------------------------------------------------------------ store_le_fp_imm
+// [fp+dst_off] = ([fp+src_off] <= imm), proven with the arc argument of cairo-lang's assert_le_felt
+// (store_le_fp_imm.rs:1-95): of the three arcs a, b-a, P-1-b (a = min, b = max of the operands) the two
+// shortest are range-checked as 16-bit limb pairs.
+struct StoreLeFpImmEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 22;
+    static constexpr u32 PRIME_OVER_3_HIGH = ((P / 3) >> 16) + 1;  // store_le_fp_imm.rs:132-133
+    static constexpr u32 PRIME_OVER_2_HIGH = ((P / 2) >> 16) + 1;
+    static const char* name() { return "store_le_fp_imm"; }
+    static std::vector<u32> opcodes() { return {OP_STORE_LE_FP_IMM}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto opcode_constant = eval.f_const(OP_STORE_LE_FP_IMM);
+        auto prime_over_3_high = eval.f_const(PRIME_OVER_3_HIGH);
+        auto prime_over_2_high = eval.f_const(PRIME_OVER_2_HIGH);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto src_off = eval.next_trace_mask();
+        auto imm = eval.next_trace_mask();
+        auto dst_off = eval.next_trace_mask();
+        auto src_val = eval.next_trace_mask();
+        auto src_prev_clock = eval.next_trace_mask();
+        auto dst_prev_val = eval.next_trace_mask();
+        auto dst_prev_clock = eval.next_trace_mask();
+        auto a = eval.next_trace_mask();
+        auto b = eval.next_trace_mask();
+        auto keep_0_1 = eval.next_trace_mask();
+        auto keep_0_2 = eval.next_trace_mask();
+        auto keep_1_2 = eval.next_trace_mask();
+        auto arc_short_lo = eval.next_trace_mask();
+        auto arc_short_hi = eval.next_trace_mask();
+        auto arc_long_lo = eval.next_trace_mask();
+        auto arc_long_hi = eval.next_trace_mask();
+        auto is_le = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(keep_0_1 * (one - keep_0_1));
+        eval.add_constraint(keep_0_2 * (one - keep_0_2));
+        eval.add_constraint(keep_1_2 * (one - keep_1_2));
+        eval.add_constraint(enabler * (keep_0_1 + keep_0_2 + keep_1_2 - one));
+        eval.add_constraint(is_le * (one - is_le));
+        auto arc_short = arc_short_lo + arc_short_hi * prime_over_3_high;
+        auto arc_long = arc_long_lo + arc_long_hi * prime_over_2_high;
+        auto arc_sum = arc_short + arc_long;
+        auto arc_prod = arc_short * arc_long;
+        eval.add_constraint(keep_0_1 * (arc_sum - (a + b - a)));
+        eval.add_constraint(keep_0_1 * (arc_prod - a * (b - a)));
+        eval.add_constraint(keep_0_2 * (arc_sum - (a - one - b)));
+        eval.add_constraint(keep_0_2 * (arc_prod - a * (-one - b)));
+        eval.add_constraint(keep_1_2 * (arc_sum - (b - a - one - b)));
+        eval.add_constraint(keep_1_2 * (arc_prod - (b - a) * (-one - b)));
+        eval.add_constraint(enabler * (a - is_le * src_val - (one - is_le) * imm));
+        eval.add_constraint(enabler * (b - is_le * imm - (one - is_le) * src_val));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, src_off, imm, dst_off});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src_off, imm, dst_off});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src_off, src_prev_clock, src_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src_off, clock, src_val});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_clock, dst_prev_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, is_le});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {arc_short_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {arc_short_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {arc_long_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {arc_long_hi});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - src_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto enabler = t.enabler();
+        auto one = t.f_const(1), two = t.f_const(2);
+        auto half = t.f_const(m31_inv(2));
+        auto src_val = t.in(in_acc(0, ACC_VALUE));
+        auto imm = t.in(IN_INST0 + 2);
+        auto is_le = t.f_le(src_val, imm);  // also 1 on padding rows (0 <= 0), as in the reference
+        auto a = is_le * src_val + (one - is_le) * imm;  // min
+        auto b = is_le * imm + (one - is_le) * src_val;  // max
+        // the three arcs and their rank in the reference's STABLE ascending sort (sort_by_key on the
+        // length, ties keep index order): rank_i = #arcs placed before arc i
+        auto l0 = a, l1 = b - a, l2 = t.f_const(P - 1) - b;
+        auto lt = [&](decltype(a) x, decltype(a) y) { return one - t.f_le(y, x); };
+        auto r0 = lt(l1, l0) + lt(l2, l0);
+        auto r1 = t.f_le(l0, l1) + lt(l2, l1);
+        auto r2 = t.f_le(l0, l2) + t.f_le(l1, l2);
+        auto is0 = [&](decltype(a) r) { return (r - one) * (r - two) * half; };
+        auto is1 = [&](decltype(a) r) { return r * (two - r); };
+        auto is2 = [&](decltype(a) r) { return r * (r - one) * half; };
+        auto arc_short = is0(r0) * l0 + is0(r1) * l1 + is0(r2) * l2;
+        auto arc_long = is1(r0) * l0 + is1(r1) * l1 + is1(r2) * l2;
+        t.out(0, enabler);
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, imm);
+        t.out(7, t.in(IN_INST0 + 3));
+        t.out(8, src_val);
+        t.out(9, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(10, t.in(in_acc(1, ACC_PREV_VALUE)));
+        t.out(11, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(12, a);
+        t.out(13, b);
+        t.out(14, enabler * is2(r2));  // exclude == 2: keep arcs 0 and 1
+        t.out(15, enabler * is2(r1));  // exclude == 1
+        t.out(16, enabler * is2(r0));  // exclude == 0
+        t.out(17, t.f_modc(arc_short, PRIME_OVER_3_HIGH));
+        t.out(18, t.f_divc(arc_short, PRIME_OVER_3_HIGH));
+        t.out(19, t.f_modc(arc_long, PRIME_OVER_2_HIGH));
+        t.out(20, t.f_divc(arc_long, PRIME_OVER_2_HIGH));
+        t.out(21, is_le);
+    }
+};
+
 // Opcode components in claim order (crates/prover/src/components/opcodes/mod.rs:223-268); the u32 /
-// bitwise families and store_le_fp_imm are not restated yet.
+// bitwise families (between store_frame_pointer and store_le_fp_imm in the reference) are not restated yet.
 #define CM31_OPCODE_EVALS(X)                                                                                          \
     X(AssertEqFpImmEval) X(CallAbsImmEval) X(JmpImmEval) X(JnzFpImmEval) X(RetEval) X(StoreImmEval) X(StoreFpFpEval) \
-    X(StoreFpImmEval) X(DoubleDerefFpImmEval) X(DoubleDerefFpFpEval) X(StoreFramePointerEval)
+    X(StoreFpImmEval) X(DoubleDerefFpImmEval) X(DoubleDerefFpFpEval) X(StoreFramePointerEval) X(StoreLeFpImmEval)
 
 // ------------------------------------------------------------------ memory (boundary values)
 // inputs: address, clock, value0..3, multiplicity, root

@@ -118,9 +118,9 @@ inline std::vector<Word4> array_sum_program() {
         {{OP_CALL_ABS_IMM, 8, 20, 0}},                      // 14: call sum (frame at fp+8)
         {{OP_STORE_DOUBLE_DEREF_FP, 0, 0, 4}},              // 15: [fp+4] = ptr[0]
         {{OP_ASSERT_EQ_FP_IMM, 4, 0, 0}},                   // 16: assert ptr[0] == 0
-        {{OP_STORE_ADD_FP_IMM, 5, 0, M3}},                  // 17: return value = sum (callee wrote [fp+5])
-        {{OP_RET, 0, 0, 0}},                                // 18
-        {{OP_JMP_REL_IMM, 0, 0, 0}},                        // 19: (unreachable filler)
+        {{OP_STORE_LE_FP_IMM, 1, 5, 2}},                    // 17: [fp+2] = (i <= 5), i = n here
+        {{OP_STORE_ADD_FP_IMM, 5, 0, M3}},                  // 18: return value = sum (callee wrote [fp+5])
+        {{OP_RET, 0, 0, 0}},                                // 19
         {{OP_STORE_IMM, 0, 0, 0}},                          // 20: sum: acc = 0
         {{OP_STORE_IMM, 0, 1, 0}},                          // 21: j = 0
         {{OP_STORE_SUB_FP_FP, 1, M3, 2}},                   // 22: [fp+2] = j - n
@@ -232,6 +232,12 @@ inline VmTrace run_program(const std::vector<Word4>& program, u32 arg, size_t ma
                 pc += 1;
                 break;
             }
+            case OP_STORE_LE_FP_IMM: {  // [fp+dst] = ([fp+src] <= imm)   (store.rs:179-191)
+                u32 x = rd(m31_add(fp, a));
+                wr(m31_add(fp, c), x <= b ? 1u : 0u);
+                pc += 1;
+                break;
+            }
             case OP_STORE_FRAME_POINTER:  // [fp+dst_off] = fp + imm
                 wr(m31_add(fp, b), m31_add(fp, a));
                 pc += 1;
@@ -286,7 +292,7 @@ inline VmTrace run_program(const std::vector<Word4>& program, u32 arg, size_t ma
 inline int opcode_memory_accesses(u32 op) {
     switch (op) {
         case OP_STORE_ADD_FP_FP: case OP_STORE_SUB_FP_FP: case OP_STORE_MUL_FP_FP: case OP_STORE_DIV_FP_FP: return 3;
-        case OP_STORE_ADD_FP_IMM: case OP_STORE_MUL_FP_IMM: return 2;
+        case OP_STORE_ADD_FP_IMM: case OP_STORE_MUL_FP_IMM: case OP_STORE_LE_FP_IMM: return 2;
         case OP_STORE_IMM: return 1;
         case OP_JNZ_FP_IMM: return 1;
         case OP_JMP_ABS_IMM: case OP_JMP_REL_IMM: return 0;

@@ -50,6 +50,9 @@ enum AirOp : uint8_t {
     OP_SHR,        // dst <- F(a) >> b   (integer op on the canonical representative)
     OP_AND,        // dst <- F(a) & b
     OP_ROWLT,      // dst <- (row < consts[a]) ? 1 : 0     (Enabler, crates/prover/src/utils/enabler.rs:57-75)
+    OP_LE,         // dst <- (F(a) <= F(b)) ? 1 : 0   (integer comparison of canonical representatives; witness only)
+    OP_DIVC,       // dst <- F(a) / b   (integer division by the constant b; witness only)
+    OP_MODC,       // dst <- F(a) % b
 };
 inline uint64_t air_encode(AirOp op, u32 dst, u32 a, u32 b) {
     return (uint64_t)op | ((uint64_t)(dst & 0xffff) << 8) | ((uint64_t)(a & 0xfffff) << 24) | ((uint64_t)(b & 0xfffff) << 44);
@@ -81,7 +84,7 @@ inline uint64_t air_code_hash(const uint64_t* code, size_t n_instr) {
 }
 
 // ------------------------------------------------------------------ graph
-enum class NodeOp : uint8_t { Col, ConstF, ConstE, ParamE, AddF, SubF, MulF, NegF, AddE, SubE, MulE, NegE, MulEF, AddEF, SubEF, F2E, Combine4, InvE, InvF, ShrF, AndF, RowLt };
+enum class NodeOp : uint8_t { Col, ConstF, ConstE, ParamE, AddF, SubF, MulF, NegF, AddE, SubE, MulE, NegE, MulEF, AddEF, SubEF, F2E, Combine4, InvE, InvF, ShrF, AndF, RowLt, LeF, DivCF, ModCF };
 
 struct Node {
     NodeOp op;
@@ -183,7 +186,10 @@ class Graph {
    private:
     typedef std::tuple<int, int, int, int, int, u32, u32, u32, u32, int, int, int, int> Key;
     static Key key_of(const Node& n) {
-        u32 w0 = (n.op == NodeOp::ConstF || n.op == NodeOp::ShrF || n.op == NodeOp::AndF || n.op == NodeOp::RowLt) ? n.fconst : n.econst.a;
+        u32 w0 = (n.op == NodeOp::ConstF || n.op == NodeOp::ShrF || n.op == NodeOp::AndF || n.op == NodeOp::RowLt || n.op == NodeOp::DivCF ||
+                  n.op == NodeOp::ModCF)
+                     ? n.fconst
+                     : n.econst.a;
         return Key((int)n.op, n.a, n.b, n.c, n.d, w0, n.econst.b, n.econst.c, n.econst.d, n.interaction, n.col, n.offset, n.param);
     }
     std::map<Key, int> cse_;
@@ -435,6 +441,19 @@ class ExprEvaluator : public LogupMixin<ExprEvaluator, FExpr, EFExpr> {
         n.fconst = mask;
         return F{this, g.add(n)};
     }
+    F f_le(F a, F b) { return F{this, g.bin(NodeOp::LeF, false, a.id, b.id)}; }
+    F f_divc(F a, u32 c) {
+        Node n{NodeOp::DivCF, false};
+        n.a = a.id;
+        n.fconst = c;
+        return F{this, g.add(n)};
+    }
+    F f_modc(F a, u32 c) {
+        Node n{NodeOp::ModCF, false};
+        n.a = a.id;
+        n.fconst = c;
+        return F{this, g.add(n)};
+    }
     F row_lt(u32 bound) {
         Node n{NodeOp::RowLt, false};
         n.fconst = bound;
@@ -522,7 +541,8 @@ struct GraphPointEval {
             case NodeOp::NegF: case NodeOp::NegE: r = -eval(n.a); break;
             case NodeOp::F2E: r = eval(n.a); break;
             case NodeOp::InvE: r = qm_inv(eval(n.a)); break;
-            case NodeOp::InvF: case NodeOp::ShrF: case NodeOp::AndF: case NodeOp::RowLt:
+            case NodeOp::InvF: case NodeOp::ShrF: case NodeOp::AndF: case NodeOp::RowLt: case NodeOp::LeF: case NodeOp::DivCF:
+            case NodeOp::ModCF:
                 throw std::logic_error("GraphPointEval: witness-only op in a constraint graph");
             case NodeOp::Combine4:
                 // combine_ef of QM31 "base" values (point.rs: from_partial_evals)
@@ -751,6 +771,9 @@ class ProgramBuilder {
                 case NodeOp::InvF: emit(OP_INV, r, reg[nd.a], 0); prog.n_mul_m31 += 37; fdef("m31_inv(" + F(nd.a) + ")"); break;
                 case NodeOp::ShrF: emit(OP_SHR, r, reg[nd.a], nd.fconst); fdef("(" + F(nd.a) + " >> " + U(nd.fconst) + ")"); break;
                 case NodeOp::AndF: emit(OP_AND, r, reg[nd.a], nd.fconst); fdef("(" + F(nd.a) + " & " + U(nd.fconst) + ")"); break;
+                case NodeOp::LeF: emit(OP_LE, r, reg[nd.a], reg[nd.b]); fdef("(" + F(nd.a) + " <= " + F(nd.b) + " ? 1u : 0u)"); break;
+                case NodeOp::DivCF: emit(OP_DIVC, r, reg[nd.a], nd.fconst); fdef("(" + F(nd.a) + " / " + U(nd.fconst) + ")"); break;
+                case NodeOp::ModCF: emit(OP_MODC, r, reg[nd.a], nd.fconst); fdef("(" + F(nd.a) + " % " + U(nd.fconst) + ")"); break;
                 case NodeOp::RowLt: {
                     u32 sl = (u32)prog.consts.size();
                     prog.consts.push_back(nd.fconst);

@@ -115,6 +115,9 @@ struct TraceProgramBuilder {
     F f_inv(F a) { return ev.f_inv(a); }
     F f_shr(F a, u32 k) { return ev.f_shr(a, k); }
     F f_and(F a, u32 m) { return ev.f_and(a, m); }
+    F f_le(F a, F b) { return ev.f_le(a, b); }
+    F f_divc(F a, u32 c) { return ev.f_divc(a, c); }
+    F f_modc(F a, u32 c) { return ev.f_modc(a, c); }
     void out(int col, F v) { outs.push_back(ProgramOutput{ProgramOutput::StoreF, v.id, col}); }
     AirProgram compile(bool emit_cuda = false) {
         return ProgramBuilder::compile(ev.g, outs, 0, [](int interaction, int col) -> size_t {

@@ -27,6 +27,9 @@ struct TraceRowEvaluator {
     F f_inv(F a) { return a.v == 0 ? M31() : a.inverse(); }
     F f_shr(F a, u32 k) { return M31((u64)(a.v >> k)); }
     F f_and(F a, u32 m) { return M31((u64)(a.v & m)); }
+    F f_le(F a, F b) { return M31((u64)(a.v <= b.v ? 1 : 0)); }
+    F f_divc(F a, u32 c) { return M31((u64)(a.v / c)); }
+    F f_modc(F a, u32 c) { return M31((u64)(a.v % c)); }
     void out(int col, F v) { (*outputs)[col][row] = v; }
 };
 
