@@ -275,15 +275,25 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     top = report[0]
     avg_ms = top["ms"] / top["launches"]
     achieved = (top["alg_bytes"] / top["launches"]) / (avg_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, int_issue = None, None
     tpath = ROOT / "profiles" / "traffic.json"
     if tpath.exists():
         t = json.loads(tpath.read_text()).get(top["kernel"])
         if t:  # measured DRAM bytes per algorithmic byte (ncu --set full) x this launch's algorithmic bytes
             traffic = t["dram_per_alg_byte"] * top["alg_bytes"] / top["launches"]
+        if t and "thread_inst_per_alg_byte" in t:
+            # the roof that binds: integer issue.  Peak measured live (ALU-pipe, FMA-pipe, 1:1 mix microkernels);
+            # achieved = executed thread-instructions per algorithmic byte (ncu) x achieved algorithmic bytes/s
+            peak3 = (C.c_double * 3)()
+            cm.check(lib.cm31_int_peak(peak3))
+            ach = t["thread_inst_per_alg_byte"] * achieved * 1e9 / 1e12
+            int_issue = {"achieved_Tops": ach, "peak_Tops": peak3[2], "frac": ach / peak3[2], "unit": "tera thread-instructions/s",
+                         "peak_alu_pipe_Tops": peak3[0], "peak_fma_pipe_Tops": peak3[1], "peak_mixed_Tops": peak3[2],
+                         "thread_inst_per_alg_byte": t["thread_inst_per_alg_byte"],
+                         "note": "this kernel is integer-issue bound, not HBM bound (DESIGN.md §4); frac is against the measured 1:1 ALU/FMA mix"}
     roofline = {
         "bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches_per_step": top["launches"] / args.steps,
+        "traffic": traffic, "int_issue": int_issue, "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches_per_step": top["launches"] / args.steps,
         "share_of_kernel_time": top["ms"] / kern_total if kern_total else None,
         "kernel_time_share_of_step": kern_total / ms,
         "kernels": [{"kernel": r["kernel"], "ms_per_step": r["ms"] / args.steps, "launches_per_step": r["launches"] / args.steps,

@@ -221,6 +221,10 @@ int cm31_profile_launches(uint64_t* out); /* kernels launched since the last res
 int cm31_profile_report(char* buf, size_t cap, size_t* len);
 int cm31_profile_trace(char* buf, size_t cap, size_t* len); /* CSV: kernel,start_ms,dur_ms per launch */
 
+/* Integer issue-rate microbenchmark (the binding roof of this path; not in MEASURED_PEAKS.json):
+ * tera lane-operations per second for [0] ALU-pipe ops (LOP3/SHF), [1] FMA-pipe ops (IMAD), [2] the 1:1 mix. */
+int cm31_int_peak(double tera_lane_ops_per_s[3]);
+
 #ifdef __cplusplus
 }
 #endif
