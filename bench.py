@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.01)
 
     def stop(self):
         self._stop_evt.set()
@@ -333,7 +333,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-steps", type=int, default=22, help="log2 of VM steps per proof (BASELINE metric: 2^22)")
