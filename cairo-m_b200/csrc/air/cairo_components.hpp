@@ -17,6 +17,9 @@
 //   double_deref_fp_imm  .../opcodes/double_deref_fp_imm.rs:150-260, :395-509
 //   double_deref_fp_fp   .../opcodes/double_deref_fp_fp.rs:175-275, :430-562
 //   store_le_fp_imm      .../opcodes/store_le_fp_imm.rs:195-400, :560-747
+//   u32_store_imm        .../opcodes/u32_store_imm.rs:160-215, :435-566
+//   u32_store_add_fp_fp  .../opcodes/u32_store_add_fp_fp.rs:200-290, :590-809
+//   u32_store_sub_fp_fp  .../opcodes/u32_store_sub_fp_fp.rs:200-290, :540-814
 //   memory         crates/prover/src/components/memory.rs:93-195, :294-366
 //   clock_update   crates/prover/src/components/clock_update.rs:70-160, :217-262
 //   range_check_N  crates/prover/src/preprocessed/range_check/range_check_macro.rs:62-112, :171-183
@@ -42,6 +45,7 @@ constexpr u32 OP_STORE_ADD_FP_IMM = 4, OP_STORE_MUL_FP_IMM = 6, OP_STORE_IMM = 9
 constexpr u32 OP_JMP_ABS_IMM = 12, OP_JMP_REL_IMM = 13, OP_JNZ_FP_IMM = 14;
 constexpr u32 OP_STORE_DOUBLE_DEREF_FP = 8, OP_STORE_DOUBLE_DEREF_FP_FP = 42, OP_STORE_FRAME_POINTER = 43;
 constexpr u32 OP_STORE_LE_FP_IMM = 48;
+constexpr u32 OP_U32_STORE_ADD_FP_FP = 15, OP_U32_STORE_SUB_FP_FP = 16, OP_U32_STORE_IMM = 23;
 constexpr u32 OP_STORE_TO_DOUBLE_DEREF_FP_IMM = 44, OP_STORE_TO_DOUBLE_DEREF_FP_FP = 45, OP_ASSERT_EQ_FP_IMM = 50;
 
 constexpr u32 TREE_HEIGHT = 30;  // crates/prover/src/adapter/merkle.rs (memory address space 2^30)
@@ -52,7 +56,7 @@ constexpr u32 RC20_LIMIT = (1u << LOG_SIZE_RC_20) - 1;  // crates/prover/src/ada
 // crates/prover/src/utils/data_accesses.rs:10-28)
 constexpr int IN_PC = 0, IN_FP = 1, IN_CLOCK = 2, IN_INST_PREV_CLOCK = 3, IN_INST0 = 4;
 constexpr int IN_ACC_BASE = 10, ACC_ADDRESS = 0, ACC_PREV_CLOCK = 1, ACC_PREV_VALUE = 2, ACC_VALUE = 3;
-constexpr int MAX_ACCESSES = 4;  // double_deref_fp_fp touches 4 cells (the u32 families will need more)
+constexpr int MAX_ACCESSES = 6;  // u32 binary ops touch 3 operands x 2 limbs
 constexpr int N_BUNDLE_INPUTS = IN_ACC_BASE + 4 * MAX_ACCESSES;
 inline int in_acc(int k, int field) { return IN_ACC_BASE + 4 * k + field; }
 
@@ -740,6 +744,168 @@ struct DoubleDerefFpFpEval : OpcodeEvalBase {
     }
 };
 
+// ------------------------------------------------------------------ u32_store_imm
+// u32([fp+dst_off], [fp+dst_off+1]) = (imm_lo, imm_hi): a u32 lives in two consecutive cells as 16-bit limbs
+struct U32StoreImmEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 12;
+    static const char* name() { return "u32_store_imm"; }
+    static std::vector<u32> opcodes() { return {OP_U32_STORE_IMM}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto opcode_constant = eval.f_const(OP_U32_STORE_IMM);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto imm_lo = eval.next_trace_mask();
+        auto imm_hi = eval.next_trace_mask();
+        auto dst_off = eval.next_trace_mask();
+        auto dst_prev_val_lo = eval.next_trace_mask();
+        auto dst_prev_val_hi = eval.next_trace_mask();
+        auto dst_prev_clock_lo = eval.next_trace_mask();
+        auto dst_prev_clock_hi = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, imm_lo, imm_hi, dst_off});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, imm_lo, imm_hi, dst_off});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_clock_lo, dst_prev_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, imm_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off + one, dst_prev_clock_hi, dst_prev_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off + one, clock, imm_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {imm_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {imm_hi});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock_hi - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        t.out(0, t.enabler());
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, t.in(IN_INST0 + 2));
+        t.out(7, t.in(IN_INST0 + 3));
+        t.out(8, t.in(in_acc(0, ACC_PREV_VALUE)));
+        t.out(9, t.in(in_acc(1, ACC_PREV_VALUE)));
+        t.out(10, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(11, t.in(in_acc(1, ACC_PREV_CLOCK)));
+    }
+};
+
+// ------------------------------------------------------------------ u32_store_add_fp_fp / u32_store_sub_fp_fp
+// dst = op0 +/- op1 on 16-bit limbs with carry / borrow bits; limbs and results range-checked (RangeCheck16).
+// Shared body: SUB selects the borrow form (u32_store_sub_fp_fp.rs:572-575) instead of the carry form
+// (u32_store_add_fp_fp.rs res_lo/res_hi).
+template <bool SUB>
+struct U32StoreBinFpFpEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 22;
+    static const char* name() { return SUB ? "u32_store_sub_fp_fp" : "u32_store_add_fp_fp"; }
+    static std::vector<u32> opcodes() { return {SUB ? OP_U32_STORE_SUB_FP_FP : OP_U32_STORE_ADD_FP_FP}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto two_pow_16 = eval.f_const(1u << 16);
+        auto opcode_constant = eval.f_const(SUB ? OP_U32_STORE_SUB_FP_FP : OP_U32_STORE_ADD_FP_FP);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto src0_off = eval.next_trace_mask();
+        auto src1_off = eval.next_trace_mask();
+        auto dst_off = eval.next_trace_mask();
+        auto op0_val_lo = eval.next_trace_mask();
+        auto op0_val_hi = eval.next_trace_mask();
+        auto op0_prev_lo_clock = eval.next_trace_mask();
+        auto op0_prev_hi_clock = eval.next_trace_mask();
+        auto op1_val_lo = eval.next_trace_mask();
+        auto op1_val_hi = eval.next_trace_mask();
+        auto op1_prev_lo_clock = eval.next_trace_mask();
+        auto op1_prev_hi_clock = eval.next_trace_mask();
+        auto dst_prev_val_lo = eval.next_trace_mask();
+        auto dst_prev_val_hi = eval.next_trace_mask();
+        auto dst_prev_lo_clock = eval.next_trace_mask();
+        auto dst_prev_hi_clock = eval.next_trace_mask();
+        auto c_lo = eval.next_trace_mask();  // u16_carry | borrow_lo
+        auto c_hi = eval.next_trace_mask();  // u32_carry | borrow_hi
+        auto res_lo = SUB ? op0_val_lo + c_lo * two_pow_16 - op1_val_lo : op0_val_lo + op1_val_lo - c_lo * two_pow_16;
+        auto res_hi = SUB ? op0_val_hi - c_lo + c_hi * two_pow_16 - op1_val_hi : op0_val_hi + op1_val_hi + c_lo - c_hi * two_pow_16;
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(c_lo * (one - c_lo));
+        eval.add_constraint(c_hi * (one - c_hi));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, src0_off, src1_off, dst_off});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src0_off, src1_off, dst_off});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off, op0_prev_lo_clock, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off, clock, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off + one, op0_prev_hi_clock, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off + one, clock, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src1_off, op1_prev_lo_clock, op1_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src1_off, clock, op1_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src1_off + one, op1_prev_hi_clock, op1_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src1_off + one, clock, op1_val_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_lo_clock, dst_prev_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, res_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off + one, dst_prev_hi_clock, dst_prev_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off + one, clock, res_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op0_val_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op0_val_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op1_val_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op1_val_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {res_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {res_hi});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_lo_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_hi_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op1_prev_lo_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op1_prev_hi_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_lo_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_hi_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto one = t.f_const(1);
+        auto op0_lo = t.in(in_acc(0, ACC_VALUE)), op0_hi = t.in(in_acc(1, ACC_VALUE));
+        auto op1_lo = t.in(in_acc(2, ACC_VALUE)), op1_hi = t.in(in_acc(3, ACC_VALUE));
+        // carries: limb sum > 0xFFFF (u32_store_add_fp_fp.rs:226-243); borrows: x < y (u32_store_sub_fp_fp.rs:229-249)
+        auto c_lo = SUB ? one - t.f_le(op1_lo, op0_lo) : t.f_le(t.f_const(1u << 16), op0_lo + op1_lo);
+        auto c_hi = SUB ? one - t.f_le(op1_hi + c_lo, op0_hi) : t.f_le(t.f_const(1u << 16), op0_hi + op1_hi + c_lo);
+        t.out(0, t.enabler());
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, t.in(IN_INST0 + 2));
+        t.out(7, t.in(IN_INST0 + 3));
+        t.out(8, op0_lo);
+        t.out(9, op0_hi);
+        t.out(10, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(11, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(12, op1_lo);
+        t.out(13, op1_hi);
+        t.out(14, t.in(in_acc(2, ACC_PREV_CLOCK)));
+        t.out(15, t.in(in_acc(3, ACC_PREV_CLOCK)));
+        t.out(16, t.in(in_acc(4, ACC_PREV_VALUE)));
+        t.out(17, t.in(in_acc(5, ACC_PREV_VALUE)));
+        t.out(18, t.in(in_acc(4, ACC_PREV_CLOCK)));
+        t.out(19, t.in(in_acc(5, ACC_PREV_CLOCK)));
+        t.out(20, c_lo);
+        t.out(21, c_hi);
+    }
+};
+typedef U32StoreBinFpFpEval<false> U32StoreAddFpFpEval;
+typedef U32StoreBinFpFpEval<true> U32StoreSubFpFpEval;
+
 // ------------------------------------------------------------------ store_le_fp_imm
 // [fp+dst_off] = ([fp+src_off] <= imm), proven with the arc argument of cairo-lang's assert_le_felt
 // (store_le_fp_imm.rs:1-95): of the three arcs a, b-a, P-1-b (a = min, b = max of the operands) the two
@@ -861,10 +1027,11 @@ struct StoreLeFpImmEval : OpcodeEvalBase {
 };
 
 // Opcode components in claim order (crates/prover/src/components/opcodes/mod.rs:223-268); the u32 /
-// bitwise families (between store_frame_pointer and store_le_fp_imm in the reference) are not restated yet.
+// bitwise families are restated only for u32_store_imm / add_fp_fp / sub_fp_fp so far (11 more to go).
 #define CM31_OPCODE_EVALS(X)                                                                                          \
     X(AssertEqFpImmEval) X(CallAbsImmEval) X(JmpImmEval) X(JnzFpImmEval) X(RetEval) X(StoreImmEval) X(StoreFpFpEval) \
-    X(StoreFpImmEval) X(DoubleDerefFpImmEval) X(DoubleDerefFpFpEval) X(StoreFramePointerEval) X(StoreLeFpImmEval)
+    X(StoreFpImmEval) X(DoubleDerefFpImmEval) X(DoubleDerefFpFpEval) X(StoreFramePointerEval) X(U32StoreImmEval)   \
+    X(U32StoreAddFpFpEval) X(U32StoreSubFpFpEval) X(StoreLeFpImmEval)
 
 // ------------------------------------------------------------------ memory (boundary values)
 // inputs: address, clock, value0..3, multiplicity, root

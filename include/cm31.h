@@ -194,7 +194,7 @@ int cm31_histogram(const uint32_t* values, size_t n, uint32_t* bins, uint32_t lo
  * (host VM + adapter, the serial step BEFORE the hot path) is built in this round. */
 typedef struct cm31_prover_input cm31_prover_input;
 int cm31_fib_input_create(uint32_t n, cm31_prover_input** out);
-/* program_id 0 = fibonacci_loop(n); 1 = array_sum(n): call/ret, frame pointer, double-deref and assert opcodes */
+/* program_id 0 = fibonacci_loop(n); 1 = array_sum(n): call/ret, frame pointer, double-deref, assert, le; 2 = u32_counter(n): u32 limb ops */
 int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out);
 int cm31_input_destroy(cm31_prover_input* h);
 /* info[0] VM steps, [1] data accesses, [2] boundary-memory rows, [3] return value, [4] input bytes staged per proof */

@@ -6,7 +6,7 @@ from tests import oracle_lib as orc
 CAP = 1 << 27
 
 
-FIB, ARRAY_SUM = 0, 1
+FIB, ARRAY_SUM, U32_COUNTER = 0, 1, 2
 
 
 def oracle_fib_prove(n, pow_bits=16, n_queries=80):
@@ -71,3 +71,11 @@ def array_sum_expected(n):
     if n >= 2:
         vals[1] = n
     return sum(vals) % orc.P
+
+
+def u32_counter_expected(n):
+    x, y = 0x0001FFF0, 0x11
+    for _ in range(n):
+        x = (x + y) & 0xFFFFFFFF
+        y = (y - 1) & 0xFFFFFFFF
+    return x & 0xFFFF

@@ -93,3 +93,19 @@ def test_array_sum_2_16_iterations_verifies(cm):
     assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
     residual, _ = ch.oracle_logup_residual(n, got, program=ch.ARRAY_SUM)
     assert residual == (0, 0, 0, 0)
+
+
+@pytest.mark.parametrize("n", [3, 40, 1000])
+def test_u32_counter_proof_bit_exact(cm, n):
+    # the u32 limb components (u32_store_imm, u32_store_add_fp_fp, u32_store_sub_fp_fp)
+    inp = ch.GpuFibInput(cm, n, program=ch.U32_COUNTER)
+    try:
+        assert inp.return_value == ch.u32_counter_expected(n)
+        got, _ = inp.prove()
+    finally:
+        inp.close()
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+    residual, _ = ch.oracle_logup_residual(n, got, program=ch.U32_COUNTER)
+    assert residual == (0, 0, 0, 0)
+    want, _ = ch.oracle_program_prove(ch.U32_COUNTER, n)
+    assert got == want

@@ -53,3 +53,13 @@ def test_array_sum_proof_verifies_and_balances(arr7):
 def test_array_sum_wrong_claim_breaks_logup(arr7):
     residual, _ = ch.oracle_logup_residual(8, arr7, program=ch.ARRAY_SUM)
     assert residual != (0, 0, 0, 0)
+
+
+# ---- u32_counter: U32StoreImm, U32StoreAddFpFp, U32StoreSubFpFp (16-bit limbs, carries/borrows, RangeCheck16)
+def test_u32_counter_proof_verifies_and_balances():
+    n = 40  # y borrows through zero after 17 rounds, x carries across the limb boundary at once
+    proof = ch.oracle_program_prove(ch.U32_COUNTER, n)[0]
+    assert ch.oracle_cairo_verify(proof) == 0, ch.orc.last_error()
+    residual, info = ch.oracle_logup_residual(n, proof, program=ch.U32_COUNTER)
+    assert residual == (0, 0, 0, 0)
+    assert info["fib"] == ch.u32_counter_expected(n)
