@@ -400,17 +400,13 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         proof.claim.log_sizes.push_back({names[i], log_sizes[i]});
         channel.mix_u64(log_sizes[i]);  // Claim::mix_into
     }
-    // Tree 1 consumes the trace columns (interpolated in place); the interaction trace needs the
-    // trace-domain values, so keep a copy of them for the logup programs.
-    std::vector<std::vector<Col>> trace_copies(traces.size());
+    // Tree 1 borrows the trace columns (out-of-place interpolation): the interaction trace needs the
+    // trace-domain values again for the logup programs.
     {
-        std::vector<CircleEvaluation<B>> all;
-        for (size_t c = 0; c < traces.size(); c++)
-            for (auto& e : traces[c]) {
-                trace_copies[c].push_back(Impl::clone(e.values));
-                all.push_back(std::move(e));
-            }
-        commitment_scheme.commit_evals(std::move(all), channel);
+        std::vector<const CircleEvaluation<B>*> all;
+        for (auto& comp : traces)
+            for (auto& e : comp) all.push_back(&e);
+        commitment_scheme.commit_evals_keep(all, channel);
     }
     auto t2 = Impl::now_ms();
 
@@ -432,7 +428,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         size_t ci = 0;
         components.for_each([&](auto& comp) {
             std::vector<const Col*> tc;
-            for (auto& c : trace_copies[ci]) tc.push_back(&c);
+            for (auto& e : traces[ci]) tc.push_back(&e.values);
             auto cols = comp.gen_interaction_trace(tc, pre_lookup);
             for (auto& e : cols) interaction.push_back(std::move(e));
             ci++;
@@ -440,7 +436,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         Impl::collect_claimed_sums(components);
         components.for_each([&](auto& comp) { proof.interaction_claim.claimed_sums.push_back(comp.claimed_sum); });
         for (auto& s : proof.interaction_claim.claimed_sums) channel.mix_felts({s});  // InteractionClaim::mix_into
-        trace_copies.clear();
+        traces.clear();
         commitment_scheme.commit_evals(std::move(interaction), channel);
     }
     auto t3 = Impl::now_ms();

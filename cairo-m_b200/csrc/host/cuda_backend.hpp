@@ -99,6 +99,11 @@ struct CudaBackend {
         auto p = ptrs(cols);
         cm_check(cm31_interpolate_batch(p.data(), p.size(), log_size, tw.h));
     }
+    static void interpolate_columns_to(const std::vector<const Col*>& evals, const std::vector<Col*>& outs, u32 log_size, const Twiddles& tw) {
+        auto s = cptrs(evals);
+        auto d = ptrs(outs);
+        cm_check(cm31_interpolate_batch_to(s.data(), d.data(), s.size(), log_size, tw.h));
+    }
     static void evaluate_polynomials(const std::vector<const Col*>& polys, const std::vector<Col*>& outs, u32 log_size, u32 log_eval,
                                      const Twiddles& tw) {
         auto s = cptrs(polys);

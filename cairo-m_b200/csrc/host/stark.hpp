@@ -486,6 +486,19 @@ struct CommitmentSchemeProver {
         for (auto& c : columns) polys.push_back(CirclePoly<B>{std::move(c.values), c.log_size});
         commit_polys(std::move(polys), channel);
     }
+    // Same commitment, but the evaluations are only borrowed: coefficients go to fresh columns.
+    void commit_evals_keep(const std::vector<const CircleEvaluation<B>*>& columns, Blake2sChannel& channel) {
+        std::vector<CirclePoly<B>> polys(columns.size());
+        std::map<u32, std::pair<std::vector<const typename B::Col*>, std::vector<typename B::Col*>>> by_size;
+        for (size_t i = 0; i < columns.size(); i++) {
+            polys[i].coeffs = B::uninit((size_t)1 << columns[i]->log_size);
+            polys[i].log_size = columns[i]->log_size;
+            by_size[columns[i]->log_size].first.push_back(&columns[i]->values);
+            by_size[columns[i]->log_size].second.push_back(&polys[i].coeffs);
+        }
+        for (auto& kv : by_size) B::interpolate_columns_to(kv.second.first, kv.second.second, kv.first, *twiddles);
+        commit_polys(std::move(polys), channel);
+    }
     void commit_polys(std::vector<CirclePoly<B>> polys, Blake2sChannel& channel) {
         trees.push_back(CommitmentTreeProver<B>::create(std::move(polys), config.fri_config.log_blowup_factor, channel, *twiddles));
     }

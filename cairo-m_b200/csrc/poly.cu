@@ -548,6 +548,11 @@ int cm31_interpolate_batch(uint32_t* const* cols, size_t n_cols, uint32_t log_si
     return run_fft<true>((const u32* const*)cols, cols, n_cols, log_size, log_size, tw);
 }
 
+int cm31_interpolate_batch_to(const uint32_t* const* evals, uint32_t* const* coeffs_out, size_t n_cols, uint32_t log_size,
+                              const cm31_twiddles* tw) {
+    return run_fft<true>(evals, coeffs_out, n_cols, log_size, log_size, tw);
+}
+
 int cm31_evaluate_batch(const uint32_t* const* coeffs, uint32_t* const* out, size_t n_cols, uint32_t log_size,
                         uint32_t log_eval_size, const cm31_twiddles* tw) {
     CM_REQUIRE(log_eval_size >= log_size, "evaluate: domain smaller than the polynomial");

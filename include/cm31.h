@@ -85,6 +85,10 @@ int cm31_twiddles_buffers(const cm31_twiddles* tw, const uint32_t** twiddles, co
 /* PolyOps::interpolate / interpolate_columns (ops.rs:19-33, cpu/circle.rs:18-71): in place,
  * evaluations on CanonicCoset(log_size).circle_domain() in bit-reversed order -> FFT-basis coeffs. */
 int cm31_interpolate_batch(uint32_t* const* cols, size_t n_cols, uint32_t log_size, const cm31_twiddles* tw);
+/* out-of-place form: the evaluations stay valid (cairo-m needs the trace values again for the logup
+ * columns, so the prover keeps them instead of copying every column before interpolating) */
+int cm31_interpolate_batch_to(const uint32_t* const* evals, uint32_t* const* coeffs_out, size_t n_cols, uint32_t log_size,
+                              const cm31_twiddles* tw);
 /* PolyOps::evaluate / evaluate_polynomials (ops.rs:43-65, cpu/circle.rs:97-135): coefficient
  * vectors of 2^log_size words -> evaluations on CanonicCoset(log_eval_size).circle_domain(),
  * bit-reversed order, out columns of 2^log_eval_size words (log_eval_size >= log_size). */

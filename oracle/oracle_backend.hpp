@@ -38,6 +38,13 @@ struct OracleBackend {
 #pragma omp parallel for schedule(dynamic)
         for (size_t i = 0; i < cols.size(); i++) interpolate(*cols[i], tw);
     }
+    static void interpolate_columns_to(const std::vector<const Col*>& evals, const std::vector<Col*>& outs, u32, const Twiddles& tw) {
+#pragma omp parallel for schedule(dynamic)
+        for (size_t i = 0; i < evals.size(); i++) {
+            *outs[i] = *evals[i];
+            interpolate(*outs[i], tw);
+        }
+    }
     static void evaluate_polynomials(const std::vector<const Col*>& polys, const std::vector<Col*>& outs, u32, u32 log_eval, const Twiddles& tw) {
 #pragma omp parallel for schedule(dynamic)
         for (size_t i = 0; i < polys.size(); i++) *outs[i] = evaluate(*polys[i], log_eval, tw);
