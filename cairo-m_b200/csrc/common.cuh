@@ -43,10 +43,12 @@ struct ProfScope {
     ~ProfScope() { prof_end(); }
 };
 
-// Uploads a small host table (pointer arrays, programs, constants) into a per-call device
-// allocation from a stream-ordered pool. Freed with release() (stream ordered).
+// Uploads a small host table (pointer arrays, programs, constants): bump-allocated from a device
+// ring mirrored by a pinned host ring (one async DMA per table, no allocation calls); slots are
+// recycled when the ring wraps, after a stream synchronise.
 struct DeviceTable {
     void* d = nullptr;
+    bool owned = false;
     int upload(const void* host, size_t bytes);
     void release();
     ~DeviceTable() { release(); }

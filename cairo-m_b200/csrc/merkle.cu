@@ -99,7 +99,8 @@ int cm31_blake2s_commit_layer(uint32_t log_size, const uint32_t* prev_layer, con
     CM_REQUIRE(out_layer != nullptr, "commit_layer: null output");
     CM_REQUIRE(log_size <= 30, "commit_layer: layer too large");
     DeviceTable dcols;
-    if (int e = dcols.upload(cols, n_cols * sizeof(void*))) return e;
+    if (n_cols != 0)  // inner layers carry no columns: nothing to upload
+        if (int e = dcols.upload(cols, n_cols * sizeof(void*))) return e;
     size_t n = (size_t)1 << log_size;
     unsigned threads = n < 256 ? (unsigned)((n + 31) / 32 * 32) : 256;
     ProfScope prof(n_cols ? "merkle_leaf_layer" : "merkle_inner_layer", (4ull * n_cols + 32ull + (prev_layer ? 64ull : 0ull)) * n);

@@ -65,38 +65,42 @@ void prof_end() {
 // the H2D copy is a true async DMA (a pageable source costs a driver-side staging copy + ~10 us per
 // call, which dominated the gaps between short kernels).  A slot is reused only after the ring
 // wraps, at which point the stream is synchronised.
-static uint8_t* g_stage = nullptr;
-static size_t g_stage_cap = 0, g_stage_pos = 0;
+static uint8_t* g_stage = nullptr;      // pinned host ring
+static uint8_t* g_stage_dev = nullptr;  // device ring: a table lives at the SAME offset in both
+static size_t g_stage_pos = 0;
 constexpr size_t STAGE_BYTES = 16u << 20;
 
 int DeviceTable::upload(const void* host, size_t bytes) {
     release();
-    if (int e = ensure_pool()) return e;
-    CM_CUDA(cudaMallocAsync(&d, bytes == 0 ? 4 : bytes, stream()));
-    if (bytes == 0) return 0;
-    if (bytes > STAGE_BYTES / 4) {  // large: plain copy (the runtime stages pageable sources itself)
+    if (bytes == 0) bytes = 4;
+    if (bytes > STAGE_BYTES / 4) {  // large: own allocation, plain copy (the runtime stages pageable sources itself)
+        if (int e = ensure_pool()) return e;
+        CM_CUDA(cudaMallocAsync(&d, bytes, stream()));
+        owned = true;
         CM_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, stream()));
         return 0;
     }
     if (!g_stage) {
         CM_CUDA(cudaHostAlloc((void**)&g_stage, STAGE_BYTES, cudaHostAllocDefault));
-        g_stage_cap = STAGE_BYTES;
+        CM_CUDA(cudaMalloc((void**)&g_stage_dev, STAGE_BYTES));
     }
-    size_t need = (bytes + 63) & ~(size_t)63;
-    if (g_stage_pos + need > g_stage_cap) {
+    size_t need = (bytes + 255) & ~(size_t)255;
+    if (g_stage_pos + need > STAGE_BYTES) {
+        // wrap: every table issued so far must be consumed (kernels done) before its slot is reused
         CM_CUDA(cudaStreamSynchronize(stream()));
         g_stage_pos = 0;
     }
-    memcpy(g_stage + g_stage_pos, host, bytes);
+    if (host) memcpy(g_stage + g_stage_pos, host, bytes);
+    d = g_stage_dev + g_stage_pos;
+    owned = false;
     CM_CUDA(cudaMemcpyAsync(d, g_stage + g_stage_pos, bytes, cudaMemcpyHostToDevice, stream()));
     g_stage_pos += need;
     return 0;
 }
 void DeviceTable::release() {
-    if (d) {
-        cudaFreeAsync(d, stream());
-        d = nullptr;
-    }
+    if (d && owned) cudaFreeAsync(d, stream());
+    d = nullptr;
+    owned = false;
 }
 
 __global__ void gather_u32_kernel(const u32* const* cols, size_t n_cols, const u32* idx, size_t n_idx, u32* out) {
