@@ -53,22 +53,16 @@ struct CudaAirImpl {
     }
     static void staging_fence() { cm_check(cm31_bg_fence()); }
     static std::vector<Col> unpack_bundles(const Words& rows, size_t n_real, const Words& accesses, size_t n_accesses, u32 log_size) {
-        std::vector<Col> cols;
+        std::vector<Col> cols = Col::many(N_BUNDLE_INPUTS, (size_t)1 << log_size);
         std::vector<u32*> p;
-        for (int k = 0; k < N_BUNDLE_INPUTS; k++) {
-            cols.emplace_back((size_t)1 << log_size);
-            p.push_back(cols.back().ptr());
-        }
+        for (auto& c : cols) p.push_back(c.ptr());
         cm_check(cm31_unpack_bundles(rows.ptr(), n_real, log_size, accesses.ptr(), n_accesses, p.data()));
         return cols;
     }
     static std::vector<Col> unpack_rows(const Words& rows, size_t n_real, u32 n_fields, u32 log_size) {
-        std::vector<Col> cols;
+        std::vector<Col> cols = Col::many(n_fields, (size_t)1 << log_size);
         std::vector<u32*> p;
-        for (u32 k = 0; k < n_fields; k++) {
-            cols.emplace_back((size_t)1 << log_size);
-            p.push_back(cols.back().ptr());
-        }
+        for (auto& c : cols) p.push_back(c.ptr());
         cm_check(cm31_unpack_rows(rows.ptr(), n_real, n_fields, log_size, p.data()));
         return cols;
     }
@@ -86,11 +80,12 @@ struct CudaAirImpl {
         AirProgram prog = it->second;
         for (u32 slot : prog.rowlt_slots) prog.consts[slot] = n_real;
         std::vector<CircleEvaluation<B>> out(Eval::N_TRACE_COLUMNS);
+        std::vector<Col> slab = Col::many(Eval::N_TRACE_COLUMNS, (size_t)1 << eval.log_size());
         std::vector<Col*> outp;
-        for (auto& c : out) {
-            c.values = Col((size_t)1 << eval.log_size());
-            c.log_size = eval.log_size();
-            outp.push_back(&c.values);
+        for (size_t i = 0; i < out.size(); i++) {
+            out[i].values = std::move(slab[i]);
+            out[i].log_size = eval.log_size();
+            outp.push_back(&out[i].values);
         }
         std::vector<const Col*> in;
         for (auto& c : inputs) in.push_back(&c);

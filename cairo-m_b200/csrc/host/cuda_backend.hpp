@@ -3,6 +3,7 @@
 // `cm31_*` entry points, exactly what the shim's trait impls would bind
 // (Backend: external/stwo/crates/prover/src/core/backend/mod.rs:19-65).
 #pragma once
+#include <memory>
 #include <stdexcept>
 #include <string>
 
@@ -24,7 +25,7 @@ class DeviceCol {
    public:
     DeviceCol() {}
     explicit DeviceCol(size_t n) : n_(n) { cm_check(cm31_malloc((void**)&p_, n * 4)); }
-    DeviceCol(DeviceCol&& o) noexcept : p_(o.p_), n_(o.n_) {
+    DeviceCol(DeviceCol&& o) noexcept : p_(o.p_), n_(o.n_), slab_(std::move(o.slab_)) {
         o.p_ = nullptr;
         o.n_ = 0;
     }
@@ -33,6 +34,7 @@ class DeviceCol {
             release();
             p_ = o.p_;
             n_ = o.n_;
+            slab_ = std::move(o.slab_);
             o.p_ = nullptr;
             o.n_ = 0;
         }
@@ -44,13 +46,33 @@ class DeviceCol {
     u32* ptr() const { return p_; }
     size_t size() const { return n_; }
 
+    // `count` columns of n words carved out of ONE allocation (freed when the last of them dies):
+    // a component's columns are created and dropped together, so this replaces dozens of
+    // stream-ordered malloc/free calls per component by one pair.
+    static std::vector<DeviceCol> many(size_t count, size_t n) {
+        std::vector<DeviceCol> out(count);
+        if (count == 0) return out;
+        size_t stride = (n + 3) & ~(size_t)3;  // keep every column 16-byte aligned
+        u32* base = nullptr;
+        cm_check(cm31_malloc((void**)&base, count * stride * 4));
+        std::shared_ptr<void> slab(base, [](void* p) { cm31_free(p); });
+        for (size_t i = 0; i < count; i++) {
+            out[i].p_ = base + i * stride;
+            out[i].n_ = n;
+            out[i].slab_ = slab;
+        }
+        return out;
+    }
+
    private:
     void release() {
-        if (p_) cm31_free(p_);
+        if (slab_) slab_.reset();
+        else if (p_) cm31_free(p_);
         p_ = nullptr;
     }
     u32* p_ = nullptr;
     size_t n_ = 0;
+    std::shared_ptr<void> slab_;
 };
 
 struct CudaTwiddles {
@@ -75,6 +97,7 @@ struct CudaBackend {
         return c;
     }
     static Col uninit(size_t n) { return Col(n); }
+    static std::vector<Col> uninit_many(size_t count, size_t n) { return Col::many(count, n); }
     static Col from_host(const u32* src, size_t n) {
         Col c(n);
         cm_check(cm31_h2d(c.ptr(), src, n * 4));

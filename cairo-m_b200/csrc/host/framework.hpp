@@ -291,11 +291,12 @@ class FrameworkComponent : public ComponentProver<B> {
         in.insert(in.end(), trace_cols.begin(), trace_cols.end());
         size_t n = (size_t)1 << log_size();
         out.resize(4 * n_batches);
+        std::vector<Col> slab = B::uninit_many(4 * n_batches, n);
         std::vector<Col*> outp;
-        for (auto& c : out) {
-            c.values = B::uninit(n);
-            c.log_size = log_size();
-            outp.push_back(&c.values);
+        for (size_t i = 0; i < out.size(); i++) {
+            out[i].values = std::move(slab[i]);
+            out[i].log_size = log_size();
+            outp.push_back(&out[i].values);
         }
         AirProgram prog = captured->logup_program;
         fill_params(prog, eval_params());  // cumsum shift is unused by this program

@@ -440,8 +440,10 @@ struct CommitmentTreeProver {
             u32 log_size = kv.first, log_eval = log_size + log_blowup_factor;
             std::vector<const typename B::Col*> src;
             std::vector<typename B::Col*> dst;
+            std::vector<typename B::Col> slab = B::uninit_many(kv.second.size(), (size_t)1 << log_eval);
+            size_t si = 0;
             for (size_t i : kv.second) {
-                t.evaluations[i].values = B::uninit((size_t)1 << log_eval);
+                t.evaluations[i].values = std::move(slab[si++]);
                 t.evaluations[i].log_size = log_eval;
                 src.push_back(&t.polynomials[i].coeffs);
                 dst.push_back(&t.evaluations[i].values);
@@ -489,12 +491,18 @@ struct CommitmentSchemeProver {
     // Same commitment, but the evaluations are only borrowed: coefficients go to fresh columns.
     void commit_evals_keep(const std::vector<const CircleEvaluation<B>*>& columns, Blake2sChannel& channel) {
         std::vector<CirclePoly<B>> polys(columns.size());
+        std::map<u32, std::vector<size_t>> idx_by_size;
+        for (size_t i = 0; i < columns.size(); i++) idx_by_size[columns[i]->log_size].push_back(i);
         std::map<u32, std::pair<std::vector<const typename B::Col*>, std::vector<typename B::Col*>>> by_size;
-        for (size_t i = 0; i < columns.size(); i++) {
-            polys[i].coeffs = B::uninit((size_t)1 << columns[i]->log_size);
-            polys[i].log_size = columns[i]->log_size;
-            by_size[columns[i]->log_size].first.push_back(&columns[i]->values);
-            by_size[columns[i]->log_size].second.push_back(&polys[i].coeffs);
+        for (auto& kv : idx_by_size) {
+            std::vector<typename B::Col> slab = B::uninit_many(kv.second.size(), (size_t)1 << kv.first);
+            size_t si = 0;
+            for (size_t i : kv.second) {
+                polys[i].coeffs = std::move(slab[si++]);
+                polys[i].log_size = kv.first;
+                by_size[kv.first].first.push_back(&columns[i]->values);
+                by_size[kv.first].second.push_back(&polys[i].coeffs);
+            }
         }
         for (auto& kv : by_size) B::interpolate_columns_to(kv.second.first, kv.second.second, kv.first, *twiddles);
         commit_polys(std::move(polys), channel);

@@ -25,6 +25,7 @@ struct OracleBackend {
     static size_t len(const Col& c) { return c.size(); }
     static Col zeros(size_t n) { return Col(n); }
     static Col uninit(size_t n) { return Col(n); }
+    static std::vector<Col> uninit_many(size_t count, size_t n) { return std::vector<Col>(count, Col(n)); }
     static Col from_host(const u32* src, size_t n) {
         Col c(n);
         for (size_t i = 0; i < n; i++) c[i] = M31((u64)src[i]);
