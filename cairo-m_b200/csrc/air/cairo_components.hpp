@@ -20,6 +20,8 @@
 //   u32_store_imm        .../opcodes/u32_store_imm.rs:160-215, :435-566
 //   u32_store_add_fp_fp  .../opcodes/u32_store_add_fp_fp.rs:200-290, :590-809
 //   u32_store_sub_fp_fp  .../opcodes/u32_store_sub_fp_fp.rs:200-290, :540-814
+//   u32_store_bitwise_fp_fp .../opcodes/u32_store_bitwise_fp_fp.rs:190-360, :560-783
+//   bitwise (table)      crates/prover/src/preprocessed/bitwise.rs:72-140 (multiplicities), :196-215 (evaluate), :253-290 (columns)
 //   memory         crates/prover/src/components/memory.rs:93-195, :294-366
 //   clock_update   crates/prover/src/components/clock_update.rs:70-160, :217-262
 //   range_check_N  crates/prover/src/preprocessed/range_check/range_check_macro.rs:62-112, :171-183
@@ -46,6 +48,16 @@ constexpr u32 OP_JMP_ABS_IMM = 12, OP_JMP_REL_IMM = 13, OP_JNZ_FP_IMM = 14;
 constexpr u32 OP_STORE_DOUBLE_DEREF_FP = 8, OP_STORE_DOUBLE_DEREF_FP_FP = 42, OP_STORE_FRAME_POINTER = 43;
 constexpr u32 OP_STORE_LE_FP_IMM = 48;
 constexpr u32 OP_U32_STORE_ADD_FP_FP = 15, OP_U32_STORE_SUB_FP_FP = 16, OP_U32_STORE_IMM = 23;
+constexpr u32 OP_U32_STORE_AND_FP_FP = 36, OP_U32_STORE_OR_FP_FP = 37, OP_U32_STORE_XOR_FP_FP = 38;
+
+// Lookup tables (preprocessed columns with a multiplicity component): the table row a looked-up
+// tuple lands on.  RangeCheckN: the value itself (range_check_macro.rs:72-84); Bitwise: the stacked
+// index op * 2^16 + input1 * 2^8 + input2 (preprocessed/bitwise.rs:86-99).
+constexpr u32 BITWISE_STACKED_LOG_SIZE = 18;
+inline std::vector<u32> cairo_table_index_weights(int relation) {
+    if (relation == REL_BITWISE) return {1u << 16, 1u << 8, 1u, 0u};
+    return {1u};
+}
 constexpr u32 OP_STORE_TO_DOUBLE_DEREF_FP_IMM = 44, OP_STORE_TO_DOUBLE_DEREF_FP_FP = 45, OP_ASSERT_EQ_FP_IMM = 50;
 
 constexpr u32 TREE_HEIGHT = 30;  // crates/prover/src/adapter/merkle.rs (memory address space 2^30)
@@ -906,6 +918,125 @@ struct U32StoreBinFpFpEval : OpcodeEvalBase {
 typedef U32StoreBinFpFpEval<false> U32StoreAddFpFpEval;
 typedef U32StoreBinFpFpEval<true> U32StoreSubFpFpEval;
 
+// ------------------------------------------------------------------ u32_store_bitwise_fp_fp (And / Or / Xor)
+// operands and result are decomposed into bytes; each byte triple is looked up in the Bitwise table
+struct U32StoreBitwiseFpFpEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 29;
+    static const char* name() { return "u32_store_bitwise_fp_fp"; }
+    static std::vector<u32> opcodes() { return {OP_U32_STORE_AND_FP_FP, OP_U32_STORE_OR_FP_FP, OP_U32_STORE_XOR_FP_FP}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto two_pow_8 = eval.f_const(1u << 8);
+        auto one = eval.f_const(1);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto opcode_constant = eval.next_trace_mask();
+        auto src0_off = eval.next_trace_mask();
+        auto src1_off = eval.next_trace_mask();
+        auto dst_off = eval.next_trace_mask();
+        auto op0_val_0 = eval.next_trace_mask();
+        auto op0_val_1 = eval.next_trace_mask();
+        auto op0_val_2 = eval.next_trace_mask();
+        auto op0_val_3 = eval.next_trace_mask();
+        auto op0_prev_clock_lo = eval.next_trace_mask();
+        auto op0_prev_clock_hi = eval.next_trace_mask();
+        auto op1_val_0 = eval.next_trace_mask();
+        auto op1_val_1 = eval.next_trace_mask();
+        auto op1_val_2 = eval.next_trace_mask();
+        auto op1_val_3 = eval.next_trace_mask();
+        auto op1_prev_clock_lo = eval.next_trace_mask();
+        auto op1_prev_clock_hi = eval.next_trace_mask();
+        auto dst_prev_val_lo = eval.next_trace_mask();
+        auto dst_prev_val_hi = eval.next_trace_mask();
+        auto dst_val_0 = eval.next_trace_mask();
+        auto dst_val_1 = eval.next_trace_mask();
+        auto dst_val_2 = eval.next_trace_mask();
+        auto dst_val_3 = eval.next_trace_mask();
+        auto dst_prev_clock_lo = eval.next_trace_mask();
+        auto dst_prev_clock_hi = eval.next_trace_mask();
+        eval.add_constraint(enabler * (enabler - one));  // sign as in the reference (u32_store_bitwise_fp_fp.rs evaluate)
+        auto bitwise_op = opcode_constant - eval.f_const(OP_U32_STORE_AND_FP_FP);
+        auto op0_val_lo = op0_val_0 + op0_val_1 * two_pow_8;
+        auto op0_val_hi = op0_val_2 + op0_val_3 * two_pow_8;
+        auto op1_val_lo = op1_val_0 + op1_val_1 * two_pow_8;
+        auto op1_val_hi = op1_val_2 + op1_val_3 * two_pow_8;
+        auto dst_val_lo = dst_val_0 + dst_val_1 * two_pow_8;
+        auto dst_val_hi = dst_val_2 + dst_val_3 * two_pow_8;
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, src0_off, src1_off, dst_off});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src0_off, src1_off, dst_off});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off, op0_prev_clock_lo, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off, clock, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off + one, op0_prev_clock_hi, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off + one, clock, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src1_off, op1_prev_clock_lo, op1_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src1_off, clock, op1_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src1_off + one, op1_prev_clock_hi, op1_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src1_off + one, clock, op1_val_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_clock_lo, dst_prev_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, dst_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off + one, dst_prev_clock_hi, dst_prev_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off + one, clock, dst_val_hi});
+        eval.add_to_relation(REL_BITWISE, -eval.ef_one(), {bitwise_op, op0_val_0, op1_val_0, dst_val_0});
+        eval.add_to_relation(REL_BITWISE, -eval.ef_one(), {bitwise_op, op0_val_1, op1_val_1, dst_val_1});
+        eval.add_to_relation(REL_BITWISE, -eval.ef_one(), {bitwise_op, op0_val_2, op1_val_2, dst_val_2});
+        eval.add_to_relation(REL_BITWISE, -eval.ef_one(), {bitwise_op, op0_val_3, op1_val_3, dst_val_3});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_hi - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op1_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op1_prev_clock_hi - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock_hi - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto enabler = t.enabler();
+        auto base_opcode = t.f_const(OP_U32_STORE_AND_FP_FP);
+        // padding rows (default bundle = Ret) are rewritten to U32_STORE_AND_FP_FP (u32_store_bitwise_fp_fp.rs:197-203)
+        auto opcode_constant = enabler * (t.in(IN_INST0) - base_opcode) + base_opcode;
+        auto lo8 = [&](decltype(enabler) v) { return t.f_and(v, 0xff); };
+        auto hi8 = [&](decltype(enabler) v) { return t.f_and(t.f_shr(v, 8), 0xff); };
+        auto op0_lo = t.in(in_acc(0, ACC_VALUE)), op0_hi = t.in(in_acc(1, ACC_VALUE));
+        auto op1_lo = t.in(in_acc(2, ACC_VALUE)), op1_hi = t.in(in_acc(3, ACC_VALUE));
+        auto dst_lo = t.in(in_acc(4, ACC_VALUE)), dst_hi = t.in(in_acc(5, ACC_VALUE));
+        t.out(0, enabler);
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, opcode_constant);
+        t.out(6, t.in(IN_INST0 + 1));
+        t.out(7, t.in(IN_INST0 + 2));
+        t.out(8, t.in(IN_INST0 + 3));
+        t.out(9, lo8(op0_lo));
+        t.out(10, hi8(op0_lo));
+        t.out(11, lo8(op0_hi));
+        t.out(12, hi8(op0_hi));
+        t.out(13, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(14, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(15, lo8(op1_lo));
+        t.out(16, hi8(op1_lo));
+        t.out(17, lo8(op1_hi));
+        t.out(18, hi8(op1_hi));
+        t.out(19, t.in(in_acc(2, ACC_PREV_CLOCK)));
+        t.out(20, t.in(in_acc(3, ACC_PREV_CLOCK)));
+        t.out(21, t.in(in_acc(4, ACC_PREV_VALUE)));
+        t.out(22, t.in(in_acc(5, ACC_PREV_VALUE)));
+        t.out(23, lo8(dst_lo));
+        t.out(24, hi8(dst_lo));
+        t.out(25, lo8(dst_hi));
+        t.out(26, hi8(dst_hi));
+        t.out(27, t.in(in_acc(4, ACC_PREV_CLOCK)));
+        t.out(28, t.in(in_acc(5, ACC_PREV_CLOCK)));
+    }
+};
+
 // ------------------------------------------------------------------ store_le_fp_imm
 // [fp+dst_off] = ([fp+src_off] <= imm), proven with the arc argument of cairo-lang's assert_le_felt
 // (store_le_fp_imm.rs:1-95): of the three arcs a, b-a, P-1-b (a = min, b = max of the operands) the two
@@ -1031,7 +1162,7 @@ struct StoreLeFpImmEval : OpcodeEvalBase {
 #define CM31_OPCODE_EVALS(X)                                                                                          \
     X(AssertEqFpImmEval) X(CallAbsImmEval) X(JmpImmEval) X(JnzFpImmEval) X(RetEval) X(StoreImmEval) X(StoreFpFpEval) \
     X(StoreFpImmEval) X(DoubleDerefFpImmEval) X(DoubleDerefFpFpEval) X(StoreFramePointerEval) X(U32StoreImmEval)   \
-    X(U32StoreAddFpFpEval) X(U32StoreSubFpFpEval) X(StoreLeFpImmEval)
+    X(U32StoreAddFpFpEval) X(U32StoreSubFpFpEval) X(U32StoreBitwiseFpFpEval) X(StoreLeFpImmEval)
 
 // ------------------------------------------------------------------ memory (boundary values)
 // inputs: address, clock, value0..3, multiplicity, root
@@ -1111,5 +1242,32 @@ struct RangeCheckEval : OpcodeEvalBase {
         eval.finalize_logup();
     }
 };
+
+// ------------------------------------------------------------------ bitwise (table multiplicities)
+// preprocessed columns (operation_id, input1, input2, result) stacked for AND, OR, XOR: 2^18 rows
+struct BitwiseEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 1;
+    static const char* name() { return "bitwise"; }
+    static std::string column_id(int k) { return "bitwise_stacked_col_" + std::to_string(k); }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto operation_id = eval.get_preprocessed_column(column_id(0));
+        auto input1 = eval.get_preprocessed_column(column_id(1));
+        auto input2 = eval.get_preprocessed_column(column_id(2));
+        auto result = eval.get_preprocessed_column(column_id(3));
+        auto multiplicity = eval.next_trace_mask();
+        eval.add_to_relation(REL_BITWISE, eval.ef(multiplicity), {operation_id, input1, input2, result});
+        eval.finalize_logup();
+    }
+};
+// value of preprocessed bitwise column `k` at table row `i` (preprocessed/bitwise.rs:253-290)
+CM_HD u32 bitwise_table_value(int k, u32 i) {
+    u32 op = i >> 16, in1 = (i >> 8) & 0xff, in2 = i & 0xff;
+    if (op >= 3) return 0;  // rows beyond the three stacked operations are zero padding
+    if (k == 0) return op;
+    if (k == 1) return in1;
+    if (k == 2) return in2;
+    return op == 0 ? (in1 & in2) : op == 1 ? (in1 | in2) : (in1 ^ in2);
+}
 
 }  // namespace cm31

@@ -157,13 +157,20 @@ inline RelationSet draw_cairo_relations(Blake2sChannel& ch) {  // components/mod
     return rs;
 }
 
-inline std::vector<std::string> cairo_preprocessed_ids() { return {"range_check_8", "range_check_16", "range_check_20"}; }
+// PreProcessedTraceBuilder::default (preprocessed/mod.rs:75-82): bitwise x4, rc8, rc16, rc20
+inline std::vector<std::string> cairo_preprocessed_ids() {
+    return {BitwiseEval::column_id(0), BitwiseEval::column_id(1), BitwiseEval::column_id(2), BitwiseEval::column_id(3),
+            "range_check_8", "range_check_16", "range_check_20"};
+}
+inline std::vector<u32> cairo_preprocessed_log_sizes() {
+    return {BITWISE_STACKED_LOG_SIZE, BITWISE_STACKED_LOG_SIZE, BITWISE_STACKED_LOG_SIZE, BITWISE_STACKED_LOG_SIZE, 8, 16, 20};
+}
 inline std::vector<std::string> cairo_component_names() {
     std::vector<std::string> names;
 #define CM31_X(E) names.push_back(E::name());
     CM31_OPCODE_EVALS(CM31_X)
 #undef CM31_X
-    for (const char* n : {"memory", "clock_update", "range_check_8", "range_check_16", "range_check_20"}) names.push_back(n);
+    for (const char* n : {"memory", "clock_update", "range_check_8", "range_check_16", "range_check_20", "bitwise"}) names.push_back(n);
     return names;
 }
 inline size_t n_opcode_components() {
@@ -192,6 +199,7 @@ struct CairoComponents {
     std::unique_ptr<Comp<MemoryEval>> memory;
     std::unique_ptr<Comp<ClockUpdateEval>> clock_update;
     std::unique_ptr<Comp<RangeCheckEval>> rc8, rc16, rc20;
+    std::unique_ptr<Comp<BitwiseEval>> bitwise;
 
     // `log_sizes` in cairo_component_names() order
     CairoComponents(const std::vector<u32>& ls, const RelationSet* rel) {
@@ -209,6 +217,7 @@ struct CairoComponents {
         rc8.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls.at(i)), REL_RC8}, rel));
         rc16.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls.at(i + 1)), REL_RC16}, rel));
         rc20.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls.at(i + 2)), REL_RC20}, rel));
+        bitwise.reset(new Comp<BitwiseEval>(BitwiseEval{base(ls.at(i + 3))}, rel));
     }
     template <class Fn>
     void for_each(Fn fn) {
@@ -220,6 +229,7 @@ struct CairoComponents {
         fn(*rc8);
         fn(*rc16);
         fn(*rc20);
+        fn(*bitwise);
     }
     void allocate(TraceLocationAllocator& alloc) {
         for_each([&](auto& c) { c.allocate(alloc); });
@@ -325,11 +335,21 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     proof.public_ranges = input.public_ranges;
     proof.public_data.mix_into(channel, input.public_ranges);
 
-    // ---- tree 0: preprocessed (range_check_8/16/20 value columns)
+    // ---- tree 0: preprocessed (stacked bitwise table x4, range_check_8/16/20 value columns)
     std::vector<u32> rc_bits = {8, 16, 20};
+    // lookup tables with a multiplicity component, in component order: (relation, log2 rows)
+    const std::vector<std::pair<int, u32>> tables = {{REL_RC8, 8}, {REL_RC16, 16}, {REL_RC20, 20}, {REL_BITWISE, BITWISE_STACKED_LOG_SIZE}};
+    auto preprocessed_columns = [&]() {
+        std::vector<Col> cols;
+        for (int k = 0; k < 4; k++) cols.push_back(Impl::bitwise_table_col(k));
+        for (u32 bits : rc_bits) cols.push_back(Impl::iota((size_t)1 << bits));
+        return cols;
+    };
     {
         std::vector<CircleEvaluation<B>> pre;
-        for (u32 bits : rc_bits) pre.push_back(CircleEvaluation<B>{Impl::iota((size_t)1 << bits), bits});
+        std::vector<u32> sizes = cairo_preprocessed_log_sizes();
+        std::vector<Col> cols = preprocessed_columns();
+        for (size_t i = 0; i < cols.size(); i++) pre.push_back(CircleEvaluation<B>{std::move(cols[i]), sizes[i]});
         commitment_scheme.commit_evals(std::move(pre), channel);
     }
     auto t1 = Impl::now_ms();
@@ -374,24 +394,23 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     for (int r = 0; r < N_CAIRO_RELATIONS; r++) dummy_relations.relations.push_back(RelationElements::dummy(cairo_relation_size(r)));
     {
         std::vector<u32> ls_all = log_sizes;
-        for (u32 bits : rc_bits) ls_all.push_back(bits);
+        for (auto& tb : tables) ls_all.push_back(tb.second);
         CairoComponents<Impl> shape(ls_all, &dummy_relations);
-        int rc_rel[3] = {REL_RC8, REL_RC16, REL_RC20};
-        for (int k = 0; k < 3; k++) {
-            Col bins = B::zeros((size_t)1 << rc_bits[k]);
+        for (auto& tb : tables) {
+            Col bins = B::zeros((size_t)1 << tb.second);
             size_t ci = 0;
             auto emit = [&](auto& comp) {
                 if (ci < n_opcode_components()) {  // opcode components only
                     std::vector<const Col*> tc;
                     for (auto& e : traces[ci]) tc.push_back(&e.values);
-                    Impl::emit_lookups(comp, rc_rel[k], tc, bins);
+                    Impl::emit_lookups(comp, tb.first, tc, bins);
                 }
                 ci++;
             };
             shape.for_each(emit);
-            log_sizes.push_back(rc_bits[k]);
+            log_sizes.push_back(tb.second);
             std::vector<CircleEvaluation<B>> t;
-            t.push_back(CircleEvaluation<B>{std::move(bins), rc_bits[k]});
+            t.push_back(CircleEvaluation<B>{std::move(bins), tb.second});
             traces.push_back(std::move(t));
         }
     }
@@ -417,8 +436,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     CairoComponents<Impl> components(log_sizes, &relations);
     {
         std::vector<CircleEvaluation<B>> interaction;
-        std::vector<Col> pre_cols;
-        for (u32 bits : rc_bits) pre_cols.push_back(Impl::iota((size_t)1 << bits));
+        std::vector<Col> pre_cols = preprocessed_columns();
         auto pre_lookup = [&](const std::string& id) -> const Col* {
             std::vector<std::string> ids = cairo_preprocessed_ids();
             for (size_t i = 0; i < ids.size(); i++)

@@ -138,10 +138,11 @@ inline std::vector<Word4> array_sum_program() {
 }
 
 // ------------------------------------------------------------------ program: u32_counter
-// u32 arithmetic: x = 0x0001fff0, y = 0x11; n times { x += y; y -= 1 } with wrap-around (y borrows
-// through zero after 17 rounds, x carries across the limb boundary at once).  Returns x's low limb.
+// u32 arithmetic and bitwise ops: x = 0x0001fff0, y = 0x11; n times { t = x + y; x = (((t ^ y) & t) | y); y -= 1 }
+// with wrap-around (y borrows through zero after 17 rounds, the first add carries across the limb
+// boundary).  Returns x's low limb.
 inline std::vector<Word4> u32_counter_program() {
-    const u32 M3 = P - 3, M4 = P - 4, M9 = P - 9;
+    const u32 M3 = P - 3, M4 = P - 4;
     return {
         {{OP_U32_STORE_IMM, 0xfff0, 0x0001, 0}},        //  0: x
         {{OP_U32_STORE_IMM, 0x0011, 0x0000, 2}},        //  1: y
@@ -150,16 +151,19 @@ inline std::vector<Word4> u32_counter_program() {
         {{OP_STORE_IMM, 0, 6, 0}},                      //  4: i = 0
         {{OP_STORE_SUB_FP_FP, 6, M4, 7}},               //  5: [fp+7] = i - n
         {{OP_JNZ_FP_IMM, 7, 2, 0}},                     //  6: if != 0 -> 8
-        {{OP_JMP_REL_IMM, 8, 0, 0}},                    //  7: -> 15
+        {{OP_JMP_REL_IMM, 11, 0, 0}},                   //  7: -> 18
         {{OP_U32_STORE_ADD_FP_FP, 0, 2, 4}},            //  8: t = x + y
-        {{OP_U32_STORE_ADD_FP_FP, 4, 8, 0}},            //  9: x = t + 0
-        {{OP_U32_STORE_SUB_FP_FP, 2, 10, 12}},          // 10: t2 = y - 1
-        {{OP_U32_STORE_ADD_FP_FP, 12, 8, 2}},           // 11: y = t2 + 0
-        {{OP_STORE_ADD_FP_IMM, 6, 1, 13}},              // 12: [fp+13] = i + 1
-        {{OP_STORE_ADD_FP_IMM, 13, 0, 6}},              // 13: i = [fp+13]
-        {{OP_JMP_REL_IMM, M9, 0, 0}},                   // 14: -> 5
-        {{OP_STORE_ADD_FP_IMM, 0, 0, M3}},              // 15: return x.lo
-        {{OP_RET, 0, 0, 0}},                            // 16
+        {{OP_U32_STORE_XOR_FP_FP, 4, 2, 14}},           //  9: a = t ^ y
+        {{OP_U32_STORE_AND_FP_FP, 14, 4, 16}},          // 10: b = a & t
+        {{OP_U32_STORE_OR_FP_FP, 16, 2, 18}},           // 11: c = b | y
+        {{OP_U32_STORE_ADD_FP_FP, 18, 8, 0}},           // 12: x = c + 0
+        {{OP_U32_STORE_SUB_FP_FP, 2, 10, 12}},          // 13: t2 = y - 1
+        {{OP_U32_STORE_ADD_FP_FP, 12, 8, 2}},           // 14: y = t2 + 0
+        {{OP_STORE_ADD_FP_IMM, 6, 1, 13}},              // 15: [fp+13] = i + 1
+        {{OP_STORE_ADD_FP_IMM, 13, 0, 6}},              // 16: i = [fp+13]
+        {{OP_JMP_REL_IMM, P - 12, 0, 0}},               // 17: -> 5
+        {{OP_STORE_ADD_FP_IMM, 0, 0, M3}},              // 18: return x.lo
+        {{OP_RET, 0, 0, 0}},                            // 19
     };
 }
 
@@ -265,12 +269,14 @@ inline VmTrace run_program(const std::vector<Word4>& program, u32 arg, size_t ma
                 wr(m31_add(m31_add(fp, c), 1), b);
                 pc += 1;
                 break;
+            case OP_U32_STORE_AND_FP_FP: case OP_U32_STORE_OR_FP_FP: case OP_U32_STORE_XOR_FP_FP:
             case OP_U32_STORE_ADD_FP_FP: case OP_U32_STORE_SUB_FP_FP: {  // exec_u32_bin_op_fp_fp (store.rs:15-35)
                 u32 x_lo = rd(m31_add(fp, a)), x_hi = rd(m31_add(m31_add(fp, a), 1));
                 u32 y_lo = rd(m31_add(fp, b)), y_hi = rd(m31_add(m31_add(fp, b), 1));
                 if ((x_lo | x_hi | y_lo | y_hi) > 0xffff) throw std::runtime_error("vm: u32 limb out of range");
                 u32 x = (x_hi << 16) | x_lo, y = (y_hi << 16) | y_lo;
-                u32 r = op == OP_U32_STORE_ADD_FP_FP ? x + y : x - y;
+                u32 r = op == OP_U32_STORE_ADD_FP_FP ? x + y : op == OP_U32_STORE_SUB_FP_FP ? x - y : op == OP_U32_STORE_AND_FP_FP ? (x & y)
+                        : op == OP_U32_STORE_OR_FP_FP ? (x | y) : (x ^ y);
                 wr(m31_add(fp, c), r & 0xffff);
                 wr(m31_add(m31_add(fp, c), 1), r >> 16);
                 pc += 1;
@@ -342,7 +348,8 @@ inline int opcode_memory_accesses(u32 op) {
         case OP_JMP_ABS_IMM: case OP_JMP_REL_IMM: return 0;
         case OP_RET: return 2;
         case OP_CALL_ABS_IMM: case OP_U32_STORE_IMM: return 2;
-        case OP_U32_STORE_ADD_FP_FP: case OP_U32_STORE_SUB_FP_FP: return 6;
+        case OP_U32_STORE_ADD_FP_FP: case OP_U32_STORE_SUB_FP_FP: case OP_U32_STORE_AND_FP_FP: case OP_U32_STORE_OR_FP_FP:
+        case OP_U32_STORE_XOR_FP_FP: return 6;
         case OP_ASSERT_EQ_FP_IMM: case OP_STORE_FRAME_POINTER: return 1;
         case OP_STORE_DOUBLE_DEREF_FP: case OP_STORE_TO_DOUBLE_DEREF_FP_IMM: return 3;
         case OP_STORE_DOUBLE_DEREF_FP_FP: case OP_STORE_TO_DOUBLE_DEREF_FP_FP: return 4;

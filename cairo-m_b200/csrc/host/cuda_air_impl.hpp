@@ -12,6 +12,7 @@
 #include "framework.hpp"
 
 extern "C" {
+int cm31_bitwise_table_col(int k, uint32_t* col);
 int cm31_unpack_bundles(const uint32_t* bundles_dev, size_t n_real, uint32_t log_size, const uint32_t* accesses_dev,
                         size_t n_accesses, uint32_t* const* out_cols);
 int cm31_unpack_rows(const uint32_t* rows_dev, size_t n_real, uint32_t n_fields, uint32_t log_size, uint32_t* const* out_cols);
@@ -33,6 +34,11 @@ struct CudaAirImpl {
     static Col iota(size_t n) {
         Col c(n);
         cm_check(cm31_iota(c.ptr(), n));
+        return c;
+    }
+    static Col bitwise_table_col(int k) {
+        Col c((size_t)1 << BITWISE_STACKED_LOG_SIZE);
+        cm_check(cm31_bitwise_table_col(k, c.ptr()));
         return c;
     }
     static Col clone(const Col& c) {

@@ -12,6 +12,7 @@
 #include <mutex>
 #include <string>
 
+#include "../air/cairo_components.hpp"
 #include "air_expr.hpp"
 #include "stark.hpp"
 
@@ -89,13 +90,21 @@ inline AirProgram build_logup_program(ExprEvaluator& e, bool emit_cuda = false) 
         throw std::logic_error("logup program reads an interaction column");
     }, emit_cuda);
 }
-// multiplicity histogram of the values looked up in `relation` (empty program if none)
-inline AirProgram build_lookup_program(const ExprEvaluator& ev, int relation, bool emit_cuda = false) {
+// multiplicity histogram of the tuples looked up in `relation` (empty program if none): the table
+// row of a tuple is sum_i weights[i] * value_i (cairo_table_index_weights: the value itself for a
+// range check, op*2^16 + in1*2^8 + in2 for the stacked bitwise table)
+inline AirProgram build_lookup_program(const ExprEvaluator& ev, int relation, const std::vector<u32>& weights, bool emit_cuda = false) {
+    Graph g = ev.g;  // the index expressions are appended to a private copy
     std::vector<ProgramOutput> outs;
-    for (auto& u : ev.logup_uses)
-        if (u.relation == relation) outs.push_back(ProgramOutput{ProgramOutput::Hist, u.values.at(0), 0});
+    for (auto& u : ev.logup_uses) {
+        if (u.relation != relation) continue;
+        int idx = g.constf(0);
+        for (size_t i = 0; i < u.values.size() && i < weights.size(); i++)
+            if (weights[i] != 0) idx = g.addf(idx, g.mulf(g.constf(weights[i]), u.values[i]));
+        outs.push_back(ProgramOutput{ProgramOutput::Hist, idx, 0});
+    }
     if (outs.empty()) return AirProgram();
-    return ProgramBuilder::compile(ev.g, outs, ev.params.size(), [&](int interaction, int col) -> size_t {
+    return ProgramBuilder::compile(g, outs, ev.params.size(), [&](int interaction, int col) -> size_t {
         if (interaction == 1) return (size_t)col;
         throw std::logic_error("lookup emission reads a non-trace column");
     }, emit_cuda);
@@ -311,7 +320,8 @@ class FrameworkComponent : public ComponentProver<B> {
     // (crates/prover/src/components/opcodes/mod.rs:83-105 providers + range_check_macro.rs:72-84).
     void emit_lookups(int relation, const std::vector<const Col*>& trace_cols, Col& bins) const {
         auto it = captured->lookup_programs.find(relation);
-        if (it == captured->lookup_programs.end()) it = captured->lookup_programs.emplace(relation, build_lookup_program(ev, relation)).first;
+        if (it == captured->lookup_programs.end())
+            it = captured->lookup_programs.emplace(relation, build_lookup_program(ev, relation, cairo_table_index_weights(relation))).first;
         const AirProgram& prog = it->second;
         if (prog.code.empty()) return;
         std::vector<Col*> outp = {&bins};

@@ -51,6 +51,11 @@ __global__ void unpack_rows_kernel(const u32* __restrict__ rows, u32 n_real, u32
     out[f][row] = row < n_real ? __ldg(rows + (size_t)row * n_fields + f) : 0u;
 }
 
+__global__ void bitwise_table_kernel(int k, u32* col) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (1u << BITWISE_STACKED_LOG_SIZE)) col[i] = bitwise_table_value(k, i);
+}
+
 __global__ void iota_kernel(u32* col, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) col[i] = (u32)i;
@@ -83,6 +88,15 @@ int cm31_unpack_rows(const uint32_t* rows_dev, size_t n_real, uint32_t n_fields,
     size_t total = ((size_t)1 << log_size) * n_fields;
     ProfScope prof("unpack_rows", 8ull * total);
     unpack_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream()>>>(rows_dev, (u32)n_real, n_fields, log_size, (u32* const*)dout.d);
+    CM_LAUNCH_CHECK();
+    return 0;
+}
+
+// preprocessed column k of the stacked bitwise table (crates/prover/src/preprocessed/bitwise.rs:253-290)
+int cm31_bitwise_table_col(int k, uint32_t* col) {
+    CM_REQUIRE(k >= 0 && k < 4 && col != nullptr, "bitwise_table_col: bad argument");
+    ProfScope prof("bitwise_table", 4ull << BITWISE_STACKED_LOG_SIZE);
+    bitwise_table_kernel<<<(1u << BITWISE_STACKED_LOG_SIZE) / 256, 256, 0, stream()>>>(k, col);
     CM_LAUNCH_CHECK();
     return 0;
 }

@@ -146,7 +146,7 @@ struct RowLogupEvaluator : EvalCommon<RowLogupEvaluator, M31, QM31> {
     const std::vector<const OCol*>* preprocessed_cols;
     size_t n_trace = 0, n_pre = 0;
     size_t row;
-    std::function<void(int, M31)> on_use;  // (relation, first value) for histograms
+    std::function<void(int, u32)> on_use;  // (relation, table row of the looked-up tuple) for histograms
 
     F next_trace_mask() { return (*(*trace_cols)[n_trace++])[row]; }
     F get_preprocessed_column(const std::string&) { return (*(*preprocessed_cols)[n_pre++])[row]; }
@@ -167,7 +167,11 @@ struct RowLogupEvaluator : EvalCommon<RowLogupEvaluator, M31, QM31> {
     EF ef(F v) { return QM31::from_m31(v); }
     EF mul_ef_f(EF a, F b) { return a * b; }
     void on_relation_use(int relation, const std::vector<F>& values) {
-        if (on_use) on_use(relation, values.at(0));
+        if (!on_use) return;
+        std::vector<u32> w = cm31::cairo_table_index_weights(relation);
+        u64 idx = 0;
+        for (size_t i = 0; i < values.size() && i < w.size(); i++) idx += (u64)w[i] * values[i].v;
+        on_use(relation, (u32)idx);
     }
 };
 
@@ -290,7 +294,7 @@ class OracleComponent : public cm31::ComponentProver<OracleBackend> {
     // LogupTraceGenerator restated per row + finalize_last (logup.rs:211-251)
     std::vector<cm31::CircleEvaluation<OracleBackend>> gen_interaction_trace(const std::vector<const OCol*>& trace_cols,
                                                                             const std::function<const OCol*(const std::string&)>& preprocessed,
-                                                                            const std::function<void(int, M31)>& on_use = nullptr) {
+                                                                            const std::function<void(int, u32)>& on_use = nullptr) {
         size_t n = (size_t)1 << log_size();
         size_t n_batches = n_interaction_columns() / 4;
         std::vector<const OCol*> pre;

@@ -46,6 +46,11 @@ struct OracleAirImpl {
         return c;
     }
     static Col clone(const Col& c) { return c; }
+    static Col bitwise_table_col(int k) {
+        Col c((size_t)1 << cm31::BITWISE_STACKED_LOG_SIZE);
+        for (size_t i = 0; i < c.size(); i++) c[i] = M31((u64)cm31::bitwise_table_value(k, (u32)i));
+        return c;
+    }
     static Words upload_words(const u32* src, size_t n_words) { return Words(src, src + n_words); }
     static Words alloc_words(size_t n_words) { return Words(n_words); }
     static void staging_fence() {}
@@ -108,8 +113,8 @@ struct OracleAirImpl {
             re.trace_cols = &trace_cols;
             re.preprocessed_cols = &pre;
             re.row = row;
-            re.on_use = [&](int rel, M31 v) {
-                if (rel == relation) bins[v.v] = bins[v.v] + M31(1);
+            re.on_use = [&](int rel, u32 idx) {
+                if (rel == relation) bins.at(idx) = bins.at(idx) + M31(1);  // an out-of-table tuple is a witness bug
             };
             comp.eval.evaluate(re);
         }
@@ -143,7 +148,7 @@ inline void verify_cairo_m(const cm31::CairoProof& proof, cm31::PcsConfig pcs_co
     }
     if (proof.stark_proof.commitments.size() != 4) throw VerificationError("expected 4 commitments");
     CommitmentSchemeVerifier cs(pcs_config);
-    cs.commit(proof.stark_proof.commitments[0], {8, 16, 20}, channel);
+    cs.commit(proof.stark_proof.commitments[0], cm31::cairo_preprocessed_log_sizes(), channel);
     std::vector<u32> log_sizes;
     for (auto& kv : proof.claim.log_sizes) {
         log_sizes.push_back(kv.second);

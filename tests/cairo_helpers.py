@@ -76,6 +76,7 @@ def array_sum_expected(n):
 def u32_counter_expected(n):
     x, y = 0x0001FFF0, 0x11
     for _ in range(n):
-        x = (x + y) & 0xFFFFFFFF
+        t = (x + y) & 0xFFFFFFFF
+        x = (((t ^ y) & t) | y) & 0xFFFFFFFF
         y = (y - 1) & 0xFFFFFFFF
     return x & 0xFFFF

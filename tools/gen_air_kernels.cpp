@@ -92,9 +92,9 @@ static void component(const std::string& outdir, Eval eval, std::vector<std::str
         emit_kernel(os, k, table);
     }
     // multiplicity histograms exist for the table relations only (opcodes/mod.rs:83-105)
-    for (int rel : {REL_RC8, REL_RC16, REL_RC20}) {
+    for (int rel : {REL_RC8, REL_RC16, REL_RC20, REL_BITWISE}) {
         if (!has_trace_program) break;  // the tables themselves look nothing up
-        Kernel k{cname + "_lookups_rel" + std::to_string(rel), build_lookup_program(ev, rel, true)};
+        Kernel k{cname + "_lookups_rel" + std::to_string(rel), build_lookup_program(ev, rel, cairo_table_index_weights(rel), true)};
         if (k.prog.code.empty()) continue;
         shape_of(k);
         emit_kernel(os, k, table);
@@ -107,7 +107,7 @@ static void component(const std::string& outdir, Eval eval, std::vector<std::str
             emit_kernel(os, k, table);
         }
     }
-    if constexpr (!std::is_same<Eval, RangeCheckEval>::value) {
+    if constexpr (!std::is_same<Eval, RangeCheckEval>::value && !std::is_same<Eval, BitwiseEval>::value) {
         if (has_trace_program) {
             TraceProgramBuilder tb(1);
             eval.write_trace(tb);
@@ -151,6 +151,7 @@ int main(int argc, char** argv) {
         e.relation = REL_RC20;
         component(outdir, e, acc, false);
     }
+    component(outdir, make<BitwiseEval>(BITWISE_STACKED_LOG_SIZE), acc, false);
     std::ostringstream os;
     os << "// GENERATED by tools/gen_air_kernels.cpp — do not edit.\n#include \"../air_gen.cuh\"\n\nnamespace cm31 {\n\n";
     for (auto& a : acc) os << "const GenEntry* " << a << "();\n";

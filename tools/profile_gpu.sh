@@ -9,7 +9,7 @@ KERNELS=${@:-fft4_pass_kernel merkle_layer_kernel quotients_fast_kernel k_.*_con
 mkdir -p gpurun_out
 BENCH="python bench.py --log-steps $LOG --steps 1 --warmup 0 --no-cpu-baseline"
 # every launch of the 3rd proof of the run (value proof, staging proof, then the e2e proof)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1090 -c 560 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 960 -c 480 --csv \
     --log-file gpurun_out/launches_${TAG}.csv $BENCH > gpurun_out/ncu_launches_${TAG}.log 2>&1
 python tools/ncu_summary.py launches gpurun_out/launches_${TAG}.csv gpurun_out/launches_${TAG}.md > /dev/null
 for K in $KERNELS; do
