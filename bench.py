@@ -202,9 +202,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n = fib_iterations(args.log_steps)
+    programs = {"fibonacci_loop": 0, "array_sum": 1, "u32_counter": 2}
+    n = args.iterations if args.iterations else fib_iterations(args.log_steps)
     h = C.c_void_p()
-    cm.check(lib.cm31_fib_input_create(C.c_uint32(n), C.byref(h)))
+    cm.check(lib.cm31_program_input_create(C.c_uint32(programs[args.program]), C.c_uint32(n), C.byref(h)))
     info = (C.c_uint64 * 5)()
     cm.check(lib.cm31_input_info(h, info))
     vm_steps, h2d_bytes = int(info[0]), int(info[4])
@@ -313,7 +314,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 (M31/QM31 modular integer)", "data": "synthetic",
-        "config": {"workload": workload_name(args.log_steps), "vm_steps_per_proof": vm_steps,
+        "config": {"workload": workload_name(args.log_steps) if args.program == "fibonacci_loop" and not args.iterations
+                   else f"{args.program}({n}) [side measurement, not the BASELINE workload]", "vm_steps_per_proof": vm_steps,
                    "parallelism": "one independent segment proof per GPU" if world > 1 else "single GPU",
                    "l2": "working set per proof (GBs of trace/LDE columns) >> 126 MB L2; no flush between steps",
                    "pcs": {"pow_bits": 16, "log_blowup": 1, "n_queries": 80}},
@@ -339,6 +341,9 @@ def main():
     ap.add_argument("--log-steps", type=int, default=22, help="log2 of VM steps per proof (BASELINE metric: 2^22)")
     ap.add_argument("--cpu-sample-log", type=int, default=17, help="log2 VM steps of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--program", default="fibonacci_loop", choices=["fibonacci_loop", "array_sum", "u32_counter"],
+                    help="side measurements on the other hand-assembled programs (the headline is fibonacci_loop)")
+    ap.add_argument("--iterations", type=int, default=0, help="program argument n (default: 2^log_steps / 8 for fibonacci_loop)")
     ap.add_argument("--dist-selftest", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

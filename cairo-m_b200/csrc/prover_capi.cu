@@ -79,6 +79,22 @@ int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input
         return -2;
     }
 }
+// Test hook: corrupt one value of the adapter output so that a POLYNOMIAL constraint of the store_fp_fp
+// AIR (dst_val - res, store_fp_fp.rs evaluate) no longer holds; the prover must then refuse
+// (ConstraintsNotSatisfied, stwo prover/mod.rs:76-82).  A corruption that only unbalances a lookup would
+// still prove — as in the reference — and be caught by the verifier's logup-sum check instead.
+//   kind 0: the value written by the middle StoreAddFpFp step;  kind 1: the second operand read by the middle StoreSubFpFp step
+int cm31_input_tamper(cm31_prover_input* h, uint32_t kind) {
+    CM_REQUIRE(h != nullptr, "input_tamper: null handle");
+    h->staged.reset();
+    auto it = h->input.states_by_opcodes.find(kind == 0 ? OP_STORE_ADD_FP_FP : OP_STORE_SUB_FP_FP);
+    CM_REQUIRE(it != h->input.states_by_opcodes.end() && !it->second.empty(), "input_tamper: the program has no such step");
+    const Bundle& b = it->second[it->second.size() / 2];
+    CM_REQUIRE(b.span_len == 3, "input_tamper: unexpected access span");
+    DataAccess& a = h->input.data_accesses[b.span_start + (kind == 0 ? 2 : 1)];
+    a.value = m31_add(a.value, 1);
+    return 0;
+}
 int cm31_input_destroy(cm31_prover_input* h) {
     delete h;
     return 0;

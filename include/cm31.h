@@ -201,6 +201,8 @@ int cm31_fib_input_create(uint32_t n, cm31_prover_input** out);
 /* program_id 0 = fibonacci_loop(n); 1 = array_sum(n): call/ret, frame pointer, double-deref, assert, le; 2 = u32_counter(n): u32 limb ops */
 int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out);
 int cm31_input_destroy(cm31_prover_input* h);
+/* test hook: corrupt the adapter output so a store_fp_fp constraint fails (kind 0: a written value, 1: an operand read) */
+int cm31_input_tamper(cm31_prover_input* h, uint32_t kind);
 /* info[0] VM steps, [1] data accesses, [2] boundary-memory rows, [3] return value, [4] input bytes staged per proof */
 int cm31_input_info(const cm31_prover_input* h, uint64_t info[5]);
 /* stage the input in HBM once (later proofs on this handle skip the host->device copy) / drop that copy */

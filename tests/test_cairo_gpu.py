@@ -109,3 +109,18 @@ def test_u32_counter_proof_bit_exact(cm, n):
     assert residual == (0, 0, 0, 0)
     want, _ = ch.oracle_program_prove(ch.U32_COUNTER, n)
     assert got == want
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_invalid_trace_is_refused(cm, kind):
+    # an execution trace that does not satisfy the AIR must not yield a proof: the composition OODS
+    # check fails and the C ABI returns ConstraintsNotSatisfied (stwo prover/mod.rs:76-82)
+    import ctypes as C
+    inp = ch.GpuFibInput(cm, 50)
+    try:
+        cm.check(cm.lib().cm31_input_tamper(inp.h, C.c_uint32(kind)))
+        with pytest.raises(Exception) as err:
+            inp.prove()
+        assert "ConstraintsNotSatisfied" in str(err.value) or "onstraint" in str(err.value)
+    finally:
+        inp.close()
