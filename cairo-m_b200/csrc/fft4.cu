@@ -240,7 +240,27 @@ static int launch_second(u32 nl2, const u32* const* src, u32* const* dst, u32 L,
 // Returns 1 if this path does not cover (L, n_cols); 0 on success; <0 / cuda error otherwise.
 template <bool INV>
 int run_fft4(const u32* const* src, u32* const* dst, size_t n_cols, u32 L, u32 log_in, const u32* tree, u32 M, u32 scale_last) {
-    if (L < 12 || L > 24 || log_in < 2) return 1;
+    if (L < 12 || L > 26 || log_in < 2) return 1;
+    if (L >= 25) {
+        // three passes: 13 contiguous layers, then two strided passes of 6-7 layers on 2^13-point tiles
+        // with 256-512-byte runs (cfg5 sizes: 2^25, 2^26 points)
+        const u32 nl2 = L - 19;  // 6 or 7
+        auto p1 = [&](const u32* const* s_, u32 lin, u32 scale) { return launch_fft4<INV, 13, 0, 1024>(s_, dst, L, lin, 0, tree, M, scale, n_cols, 3); };
+        auto p2 = [&](const u32* const* s_, u32 lin, u32 scale) {
+            return nl2 == 6 ? launch_fft4<INV, 6, 7, 1024>(s_, dst, L, lin, 13, tree, M, scale, n_cols, 3)
+                            : launch_fft4<INV, 7, 6, 1024>(s_, dst, L, lin, 13, tree, M, scale, n_cols, 3);
+        };
+        auto p3 = [&](const u32* const* s_, u32 lin, u32 scale) { return launch_fft4<INV, 6, 7, 1024>(s_, dst, L, lin, 13 + nl2, tree, M, scale, n_cols, 3); };
+        const u32* const* d = (const u32* const*)dst;
+        if (INV) {
+            if (int e = p1(src, log_in, 1)) return e;
+            if (int e = p2(d, L, 1)) return e;
+            return p3(d, L, scale_last);
+        }
+        if (int e = p3(src, log_in, 1)) return e;
+        if (int e = p2(d, L, 1)) return e;
+        return p1(d, L, 1);
+    }
     if (L == 12) return launch_fft4<INV, 12, 0, 512>(src, dst, L, log_in, 0, tree, M, scale_last, n_cols, 1);
     // two passes: the contiguous one covers layers [0, NL1), the strided one [NL1, L)
     const bool big = L > 21;  // second pass would fall below 32-byte runs with 2^12-point tiles

@@ -124,3 +124,18 @@ def test_invalid_trace_is_refused(cm, kind):
         assert "ConstraintsNotSatisfied" in str(err.value) or "onstraint" in str(err.value)
     finally:
         inp.close()
+
+
+def test_fib_2_22_steps_headline_size_verifies(cm):
+    # the size bench.py reports (BASELINE metric: 2^22 trace): GPU proof accepted by the oracle
+    # verifier, logup sums balanced against the public data
+    n = (1 << 22) // 8
+    inp = ch.GpuFibInput(cm, n)
+    try:
+        assert inp.steps == (1 << 22) + 8
+        got, _ = inp.prove()
+    finally:
+        inp.close()
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+    residual, _ = ch.oracle_logup_residual(n, got)
+    assert residual == (0, 0, 0, 0)

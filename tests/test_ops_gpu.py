@@ -30,7 +30,7 @@ def host(t) -> np.ndarray:
 
 @pytest.fixture(scope="module")
 def tw(cm):
-    t = cm.Twiddles(25)
+    t = cm.Twiddles(27)
     yield t
     t.close()
 
@@ -45,9 +45,9 @@ def test_twiddle_tree_matches_oracle(cm):
         t.close()
 
 
-@pytest.mark.parametrize("L", [1, 2, 3, 4, 5, 7, 8, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23])
+@pytest.mark.parametrize("L", [1, 2, 3, 4, 5, 7, 8, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 25])
 def test_interpolate_matches_oracle(cm, tw, L):
-    n_cols = 3 if L <= 11 else (5 if L <= 20 else 2)  # 5: one full column quad + a ragged one (fft4.cu)
+    n_cols = 3 if L <= 11 else (5 if L <= 20 else (2 if L <= 23 else 1))  # 5: one full column quad + a ragged one (fft4.cu)
     vals = orc.splitmix64(0xCA1120 + L, n_cols << L).reshape(n_cols, 1 << L)
     cols = to_dev_cols(vals)
     cm.interpolate_batch(cols, L, tw)
@@ -59,9 +59,9 @@ def test_interpolate_matches_oracle(cm, tw, L):
 
 @pytest.mark.parametrize("L,LE", [(1, 1), (1, 2), (2, 2), (2, 3), (3, 3), (3, 4), (4, 5), (7, 8), (10, 11), (11, 12),
                                   (12, 13), (13, 14), (14, 15), (15, 16), (16, 17), (17, 18), (18, 19), (19, 20), (5, 9),
-                                  (20, 21), (21, 22), (22, 23), (12, 12), (10, 14), (3, 13), (1, 12), (20, 22)])
+                                  (20, 21), (21, 22), (22, 23), (12, 12), (10, 14), (3, 13), (1, 12), (20, 22), (24, 25), (25, 26)])
 def test_evaluate_matches_oracle(cm, tw, L, LE):
-    n_cols = 3 if LE <= 11 else (5 if LE <= 20 else 2)
+    n_cols = 3 if LE <= 11 else (5 if LE <= 20 else (2 if LE <= 23 else 1))
     coeffs = orc.splitmix64(0xBEEF + L, n_cols << L).reshape(n_cols, 1 << L)
     src = to_dev_cols(coeffs)
     out = [torch.empty(1 << LE, dtype=torch.int32, device="cuda") for _ in range(n_cols)]

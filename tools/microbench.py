@@ -1,4 +1,5 @@
 """Per-kernel microbenchmarks: CUDA-event timings + algorithmic GB/s."""
+import ctypes as C
 import importlib
 import json
 import sys
@@ -29,8 +30,10 @@ def timeit(fn, iters=5, warm=2):
 
 def main():
     res = {}
-    tw = cm.Twiddles(25)
-    for L, ncols in [(20, 64), (22, 16), (24, 8)]:
+    tw = cm.Twiddles(27)
+    peaks = ROOT / "MEASURED_PEAKS.json"
+    res["hbm_peak_GBps"] = json.loads(peaks.read_text())["hbm_gbs"] if peaks.exists() else 6650.0
+    for L, ncols in [(20, 64), (22, 16), (24, 8), (25, 4)]:
         n = 1 << L
         cols = [torch.randint(0, cm.P, (n,), dtype=torch.int32, device="cuda") for _ in range(ncols)]
         out = [torch.empty(2 * n, dtype=torch.int32, device="cuda") for _ in range(ncols)]
@@ -62,6 +65,9 @@ def main():
         torch.cuda.empty_cache()
     med, best = timeit(lambda: cm.grind_blake2s(bytes(range(32)), 16), iters=3, warm=1)
     res["grind16"] = {"ms": med}
+    peak3 = (C.c_double * 3)()
+    cm.check(cm.lib().cm31_int_peak(peak3))
+    res["int_peak_Tops"] = {"alu_pipe": peak3[0], "fma_pipe": peak3[1], "mixed": peak3[2]}
     for k, v in res.items():
         print(k, json.dumps(v))
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
