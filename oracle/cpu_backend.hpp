@@ -12,6 +12,8 @@
 // vcs/blake2_merkle.rs:59-130, prefix-sum simd/prefix_sum.rs:153-187, and whole proofs verified
 // by oracle/verifier.hpp.
 #pragma once
+#include <omp.h>
+
 #include <algorithm>
 #include <cassert>
 #include <cstring>
@@ -90,6 +92,7 @@ inline OTwiddles precompute_twiddles(u32 log_size) {
         size_t i0 = t.tw.size();
         size_t half = coset.size() / 2;
         std::vector<M31> xs(half);
+#pragma omp parallel for schedule(static)
         for (size_t i = 0; i < half; i++) xs[i] = coset.at(i).x;
         u32 lg = coset.log_size - 1;
         t.tw.resize(i0 + half);
@@ -98,6 +101,7 @@ inline OTwiddles precompute_twiddles(u32 log_size) {
     }
     t.tw.push_back(M31(1));
     t.itw.resize(t.tw.size());
+#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < t.tw.size(); i++) t.itw[i] = t.tw[i].inverse();
     return t;
 }
@@ -125,6 +129,19 @@ inline void fft_layer_loop(std::vector<M31>& values, u32 i, size_t h, M31 t, F b
         size_t idx0 = (h << (i + 1)) + l;
         size_t idx1 = idx0 + ((size_t)1 << i);
         bf(values[idx0], values[idx1], t);
+    }
+}
+// One whole FFT layer: all (h, l) butterflies are independent, so a lone large column (e.g. the 2^20-row
+// range-check table) still uses every host core when the caller is not already inside a parallel
+// region over columns (bench.py's CPU arm is entitled to all cores).
+template <class F>
+inline void fft_layer(std::vector<M31>& values, u32 i, const M31* tw, size_t n_tw, F bf) {
+    const size_t per = (size_t)1 << i, total = n_tw << i;
+#pragma omp parallel for schedule(static) if (total >= (1u << 14) && !omp_in_parallel())
+    for (size_t b = 0; b < total; b++) {
+        size_t h = b >> i, l = b & (per - 1);
+        size_t idx0 = (h << (i + 1)) + l;
+        bf(values[idx0], values[idx0 + per], tw[h]);
     }
 }
 inline std::vector<M31> circle_twiddles_from_line(const M31* line0, size_t len) {  // cpu/circle.rs:209-229
@@ -170,11 +187,11 @@ inline void interpolate(std::vector<M31>& values, const OTwiddles& tw) {
     size_t len0;
     const M31* l0 = line_twiddles(tw.itw, k, 0, &len0);
     std::vector<M31> ct = circle_twiddles_from_line(l0, len0);
-    for (size_t h = 0; h < ct.size(); h++) fft_layer_loop(values, 0, h, ct[h], ibutterfly);
+    fft_layer(values, 0, ct.data(), ct.size(), ibutterfly);
     for (u32 layer = 0; layer < k; layer++) {
         size_t len;
         const M31* lt = line_twiddles(tw.itw, k, layer, &len);
-        for (size_t h = 0; h < len; h++) fft_layer_loop(values, layer + 1, h, lt[h], ibutterfly);
+        fft_layer(values, layer + 1, lt, len, ibutterfly);
     }
     M31 inv = M31((u64)values.size()).inverse();
     for (auto& v : values) v = v * inv;
@@ -201,12 +218,12 @@ inline std::vector<M31> evaluate(const std::vector<M31>& coeffs, u32 log_eval, c
     for (int layer = (int)k - 1; layer >= 0; layer--) {
         size_t len;
         const M31* lt = line_twiddles(tw.tw, k, (u32)layer, &len);
-        for (size_t h = 0; h < len; h++) fft_layer_loop(values, (u32)layer + 1, h, lt[h], butterfly);
+        fft_layer(values, (u32)layer + 1, lt, len, butterfly);
     }
     size_t len0;
     const M31* l0 = line_twiddles(tw.tw, k, 0, &len0);
     std::vector<M31> ct = circle_twiddles_from_line(l0, len0);
-    for (size_t h = 0; h < ct.size(); h++) fft_layer_loop(values, 0, h, ct[h], butterfly);
+    fft_layer(values, 0, ct.data(), ct.size(), butterfly);
     return values;
 }
 

@@ -304,6 +304,8 @@ class OracleComponent : public cm31::ComponentProver<OracleBackend> {
             c.values.assign(n, M31());
             c.log_size = log_size();
         }
+        bool mismatch = false;
+#pragma omp parallel for schedule(static) if (!on_use)
         for (size_t row = 0; row < n; row++) {
             RowLogupEvaluator re;
             re.relations = relations;
@@ -313,7 +315,10 @@ class OracleComponent : public cm31::ComponentProver<OracleBackend> {
             re.row = row;
             re.on_use = on_use;
             eval.evaluate(re);
-            if (re.batch_fracs.size() != n_batches) throw std::logic_error("logup batch count mismatch");
+            if (re.batch_fracs.size() != n_batches) {
+                mismatch = true;
+                continue;
+            }
             QM31 cum = QM31::zero();
             for (size_t b = 0; b < n_batches; b++) {
                 cum = cum + re.batch_fracs[b].num * re.batch_fracs[b].den.inverse();
@@ -323,6 +328,7 @@ class OracleComponent : public cm31::ComponentProver<OracleBackend> {
                 out[4 * b + 3].values[row] = cum.y.b;
             }
         }
+        if (mismatch) throw std::logic_error("logup batch count mismatch");
         if (n_batches == 0) return out;
         // finalize_last
         QM31 claimed = QM31::zero();

@@ -35,19 +35,21 @@ struct OracleBackend {
         for (size_t i = 0; i < c.size(); i++) out[i] = c[i].v;
     }
     static void precompute_twiddles(u32 log_size, Twiddles& out) { out = orc::precompute_twiddles(log_size); }
+    // across columns when there are at least as many as threads, inside each FFT otherwise
+    static bool many(size_t n_cols) { return n_cols >= (size_t)omp_get_max_threads(); }
     static void interpolate_columns(const std::vector<Col*>& cols, u32, const Twiddles& tw) {
-#pragma omp parallel for schedule(dynamic)
+#pragma omp parallel for schedule(dynamic) if (many(cols.size()))
         for (size_t i = 0; i < cols.size(); i++) interpolate(*cols[i], tw);
     }
     static void interpolate_columns_to(const std::vector<const Col*>& evals, const std::vector<Col*>& outs, u32, const Twiddles& tw) {
-#pragma omp parallel for schedule(dynamic)
+#pragma omp parallel for schedule(dynamic) if (many(evals.size()))
         for (size_t i = 0; i < evals.size(); i++) {
             *outs[i] = *evals[i];
             interpolate(*outs[i], tw);
         }
     }
     static void evaluate_polynomials(const std::vector<const Col*>& polys, const std::vector<Col*>& outs, u32, u32 log_eval, const Twiddles& tw) {
-#pragma omp parallel for schedule(dynamic)
+#pragma omp parallel for schedule(dynamic) if (many(polys.size()))
         for (size_t i = 0; i < polys.size(); i++) *outs[i] = evaluate(*polys[i], log_eval, tw);
     }
     static void eval_at_points(const std::vector<const Col*>& polys, const std::vector<u32>&, const std::vector<cm31::SecurePoint>& points,

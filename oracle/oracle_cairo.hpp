@@ -106,6 +106,9 @@ struct OracleAirImpl {
     static void emit_lookups(Comp& comp, int relation, const std::vector<const Col*>& trace_cols, Col& bins) {
         size_t n = (size_t)1 << comp.log_size();
         std::vector<const OCol*> pre;
+        std::vector<u32> counts(bins.size(), 0);
+        bool bad = false;
+#pragma omp parallel for schedule(static)
         for (size_t row = 0; row < n; row++) {
             RowLogupEvaluator re;
             re.relations = comp.relations;
@@ -114,10 +117,18 @@ struct OracleAirImpl {
             re.preprocessed_cols = &pre;
             re.row = row;
             re.on_use = [&](int rel, u32 idx) {
-                if (rel == relation) bins.at(idx) = bins.at(idx) + M31(1);  // an out-of-table tuple is a witness bug
+                if (rel != relation) return;
+                if (idx >= counts.size()) {  // an out-of-table tuple is a witness bug
+                    bad = true;
+                    return;
+                }
+#pragma omp atomic
+                counts[idx]++;
             };
             comp.eval.evaluate(re);
         }
+        if (bad) throw std::runtime_error("lookup outside its table");
+        for (size_t i = 0; i < bins.size(); i++) bins[i] = bins[i] + M31((u64)counts[i]);
     }
 };
 
