@@ -20,6 +20,7 @@
 //   u32_store_imm        .../opcodes/u32_store_imm.rs:160-215, :435-566
 //   u32_store_add_fp_fp  .../opcodes/u32_store_add_fp_fp.rs:200-290, :590-809
 //   u32_store_sub_fp_fp  .../opcodes/u32_store_sub_fp_fp.rs:200-290, :540-814
+//   u32_store_lt_fp_fp   .../opcodes/u32_store_lt_fp_fp.rs:195-290, :560-794
 //   u32_store_bitwise_fp_fp .../opcodes/u32_store_bitwise_fp_fp.rs:190-360, :560-783
 //   bitwise (table)      crates/prover/src/preprocessed/bitwise.rs:72-140 (multiplicities), :196-215 (evaluate), :253-290 (columns)
 //   memory         crates/prover/src/components/memory.rs:93-195, :294-366
@@ -48,6 +49,7 @@ constexpr u32 OP_JMP_ABS_IMM = 12, OP_JMP_REL_IMM = 13, OP_JNZ_FP_IMM = 14;
 constexpr u32 OP_STORE_DOUBLE_DEREF_FP = 8, OP_STORE_DOUBLE_DEREF_FP_FP = 42, OP_STORE_FRAME_POINTER = 43;
 constexpr u32 OP_STORE_LE_FP_IMM = 48;
 constexpr u32 OP_U32_STORE_ADD_FP_FP = 15, OP_U32_STORE_SUB_FP_FP = 16, OP_U32_STORE_IMM = 23;
+constexpr u32 OP_U32_STORE_LT_FP_FP = 28;
 constexpr u32 OP_U32_STORE_AND_FP_FP = 36, OP_U32_STORE_OR_FP_FP = 37, OP_U32_STORE_XOR_FP_FP = 38;
 
 // Lookup tables (preprocessed columns with a multiplicity component): the table row a looked-up
@@ -811,6 +813,100 @@ struct U32StoreImmEval : OpcodeEvalBase {
     }
 };
 
+// ------------------------------------------------------------------ u32_store_lt_fp_fp
+// [fp+dst_off] = u32(op0) < u32(op1): no borrow out of op1 - op0 - 1, limb differences range-checked
+struct U32StoreLtFpFpEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 20;
+    static const char* name() { return "u32_store_lt_fp_fp"; }
+    static std::vector<u32> opcodes() { return {OP_U32_STORE_LT_FP_FP}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto two_pow_16 = eval.f_const(1u << 16);
+        auto opcode_constant = eval.f_const(OP_U32_STORE_LT_FP_FP);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto src0_off = eval.next_trace_mask();
+        auto src1_off = eval.next_trace_mask();
+        auto dst_off = eval.next_trace_mask();
+        auto op0_val_lo = eval.next_trace_mask();
+        auto op0_val_hi = eval.next_trace_mask();
+        auto op0_prev_clock_lo = eval.next_trace_mask();
+        auto op0_prev_clock_hi = eval.next_trace_mask();
+        auto op1_val_lo = eval.next_trace_mask();
+        auto op1_val_hi = eval.next_trace_mask();
+        auto op1_prev_clock_lo = eval.next_trace_mask();
+        auto op1_prev_clock_hi = eval.next_trace_mask();
+        auto dst_prev_val = eval.next_trace_mask();
+        auto dst_prev_clock = eval.next_trace_mask();
+        auto borrow_lo = eval.next_trace_mask();
+        auto borrow_hi = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(borrow_lo * (one - borrow_lo));
+        eval.add_constraint(borrow_hi * (one - borrow_hi));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, src0_off, src1_off, dst_off});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src0_off, src1_off, dst_off});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off, op0_prev_clock_lo, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off, clock, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off + one, op0_prev_clock_hi, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off + one, clock, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src1_off, op1_prev_clock_lo, op1_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src1_off, clock, op1_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src1_off + one, op1_prev_clock_hi, op1_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src1_off + one, clock, op1_val_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_clock, dst_prev_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, one - borrow_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op0_val_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op0_val_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op1_val_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op1_val_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op1_val_lo - enabler + borrow_lo * two_pow_16 - op0_val_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op1_val_hi - borrow_lo + borrow_hi * two_pow_16 - op0_val_hi});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_hi - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op1_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op1_prev_clock_hi - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto enabler = t.enabler();
+        auto one = t.f_const(1);
+        auto op0_lo = t.in(in_acc(0, ACC_VALUE)), op0_hi = t.in(in_acc(1, ACC_VALUE));
+        auto op1_lo = t.in(in_acc(2, ACC_VALUE)), op1_hi = t.in(in_acc(3, ACC_VALUE));
+        // borrows of op1 - op0 - enabler (u32_store_lt_fp_fp.rs:222-256): x < y + z
+        auto borrow_lo = one - t.f_le(op0_lo + enabler, op1_lo);
+        auto borrow_hi = one - t.f_le(op0_hi + borrow_lo, op1_hi);
+        t.out(0, enabler);
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, t.in(IN_INST0 + 2));
+        t.out(7, t.in(IN_INST0 + 3));
+        t.out(8, op0_lo);
+        t.out(9, op0_hi);
+        t.out(10, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(11, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(12, op1_lo);
+        t.out(13, op1_hi);
+        t.out(14, t.in(in_acc(2, ACC_PREV_CLOCK)));
+        t.out(15, t.in(in_acc(3, ACC_PREV_CLOCK)));
+        t.out(16, t.in(in_acc(4, ACC_PREV_VALUE)));
+        t.out(17, t.in(in_acc(4, ACC_PREV_CLOCK)));
+        t.out(18, borrow_lo);
+        t.out(19, borrow_hi);
+    }
+};
+
 // ------------------------------------------------------------------ u32_store_add_fp_fp / u32_store_sub_fp_fp
 // dst = op0 +/- op1 on 16-bit limbs with carry / borrow bits; limbs and results range-checked (RangeCheck16).
 // Shared body: SUB selects the borrow form (u32_store_sub_fp_fp.rs:572-575) instead of the carry form
@@ -1162,7 +1258,7 @@ struct StoreLeFpImmEval : OpcodeEvalBase {
 #define CM31_OPCODE_EVALS(X)                                                                                          \
     X(AssertEqFpImmEval) X(CallAbsImmEval) X(JmpImmEval) X(JnzFpImmEval) X(RetEval) X(StoreImmEval) X(StoreFpFpEval) \
     X(StoreFpImmEval) X(DoubleDerefFpImmEval) X(DoubleDerefFpFpEval) X(StoreFramePointerEval) X(U32StoreImmEval)   \
-    X(U32StoreAddFpFpEval) X(U32StoreSubFpFpEval) X(U32StoreBitwiseFpFpEval) X(StoreLeFpImmEval)
+    X(U32StoreLtFpFpEval) X(U32StoreAddFpFpEval) X(U32StoreSubFpFpEval) X(U32StoreBitwiseFpFpEval) X(StoreLeFpImmEval)
 
 // ------------------------------------------------------------------ memory (boundary values)
 // inputs: address, clock, value0..3, multiplicity, root

@@ -151,7 +151,7 @@ inline std::vector<Word4> u32_counter_program() {
         {{OP_STORE_IMM, 0, 6, 0}},                      //  4: i = 0
         {{OP_STORE_SUB_FP_FP, 6, M4, 7}},               //  5: [fp+7] = i - n
         {{OP_JNZ_FP_IMM, 7, 2, 0}},                     //  6: if != 0 -> 8
-        {{OP_JMP_REL_IMM, 11, 0, 0}},                   //  7: -> 18
+        {{OP_JMP_REL_IMM, 12, 0, 0}},                   //  7: -> 19
         {{OP_U32_STORE_ADD_FP_FP, 0, 2, 4}},            //  8: t = x + y
         {{OP_U32_STORE_XOR_FP_FP, 4, 2, 14}},           //  9: a = t ^ y
         {{OP_U32_STORE_AND_FP_FP, 14, 4, 16}},          // 10: b = a & t
@@ -159,11 +159,12 @@ inline std::vector<Word4> u32_counter_program() {
         {{OP_U32_STORE_ADD_FP_FP, 18, 8, 0}},           // 12: x = c + 0
         {{OP_U32_STORE_SUB_FP_FP, 2, 10, 12}},          // 13: t2 = y - 1
         {{OP_U32_STORE_ADD_FP_FP, 12, 8, 2}},           // 14: y = t2 + 0
-        {{OP_STORE_ADD_FP_IMM, 6, 1, 13}},              // 15: [fp+13] = i + 1
-        {{OP_STORE_ADD_FP_IMM, 13, 0, 6}},              // 16: i = [fp+13]
-        {{OP_JMP_REL_IMM, P - 12, 0, 0}},               // 17: -> 5
-        {{OP_STORE_ADD_FP_IMM, 0, 0, M3}},              // 18: return x.lo
-        {{OP_RET, 0, 0, 0}},                            // 19
+        {{OP_U32_STORE_LT_FP_FP, 2, 0, 20}},            // 15: [fp+20] = (y < x)
+        {{OP_STORE_ADD_FP_IMM, 6, 1, 13}},              // 16: [fp+13] = i + 1
+        {{OP_STORE_ADD_FP_IMM, 13, 0, 6}},              // 17: i = [fp+13]
+        {{OP_JMP_REL_IMM, P - 13, 0, 0}},               // 18: -> 5
+        {{OP_STORE_ADD_FP_IMM, 0, 0, M3}},              // 19: return x.lo
+        {{OP_RET, 0, 0, 0}},                            // 20
     };
 }
 
@@ -282,6 +283,14 @@ inline VmTrace run_program(const std::vector<Word4>& program, u32 arg, size_t ma
                 pc += 1;
                 break;
             }
+            case OP_U32_STORE_LT_FP_FP: {  // [fp+dst] = u32(src0) < u32(src1)
+                u32 x_lo = rd(m31_add(fp, a)), x_hi = rd(m31_add(m31_add(fp, a), 1));
+                u32 y_lo = rd(m31_add(fp, b)), y_hi = rd(m31_add(m31_add(fp, b), 1));
+                if ((x_lo | x_hi | y_lo | y_hi) > 0xffff) throw std::runtime_error("vm: u32 limb out of range");
+                wr(m31_add(fp, c), ((x_hi << 16) | x_lo) < ((y_hi << 16) | y_lo) ? 1u : 0u);
+                pc += 1;
+                break;
+            }
             case OP_STORE_LE_FP_IMM: {  // [fp+dst] = ([fp+src] <= imm)   (store.rs:179-191)
                 u32 x = rd(m31_add(fp, a));
                 wr(m31_add(fp, c), x <= b ? 1u : 0u);
@@ -348,6 +357,7 @@ inline int opcode_memory_accesses(u32 op) {
         case OP_JMP_ABS_IMM: case OP_JMP_REL_IMM: return 0;
         case OP_RET: return 2;
         case OP_CALL_ABS_IMM: case OP_U32_STORE_IMM: return 2;
+        case OP_U32_STORE_LT_FP_FP: return 5;
         case OP_U32_STORE_ADD_FP_FP: case OP_U32_STORE_SUB_FP_FP: case OP_U32_STORE_AND_FP_FP: case OP_U32_STORE_OR_FP_FP:
         case OP_U32_STORE_XOR_FP_FP: return 6;
         case OP_ASSERT_EQ_FP_IMM: case OP_STORE_FRAME_POINTER: return 1;
