@@ -202,7 +202,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    programs = {"fibonacci_loop": 0, "array_sum": 1, "u32_counter": 2}
+    programs = {"fibonacci_loop": 0, "array_sum": 1, "u32_counter": 2, "u32_mix": 3}
     n = args.iterations if args.iterations else fib_iterations(args.log_steps)
     h = C.c_void_p()
     cm.check(lib.cm31_program_input_create(C.c_uint32(programs[args.program]), C.c_uint32(n), C.byref(h)))
@@ -341,7 +341,7 @@ def main():
     ap.add_argument("--log-steps", type=int, default=22, help="log2 of VM steps per proof (BASELINE metric: 2^22)")
     ap.add_argument("--cpu-sample-log", type=int, default=17, help="log2 VM steps of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--program", default="fibonacci_loop", choices=["fibonacci_loop", "array_sum", "u32_counter"],
+    ap.add_argument("--program", default="fibonacci_loop", choices=["fibonacci_loop", "array_sum", "u32_counter", "u32_mix"],
                     help="side measurements on the other hand-assembled programs (the headline is fibonacci_loop)")
     ap.add_argument("--iterations", type=int, default=0, help="program argument n (default: 2^log_steps / 8 for fibonacci_loop)")
     ap.add_argument("--dist-selftest", action="store_true", help=argparse.SUPPRESS)

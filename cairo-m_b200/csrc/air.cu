@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(128) air_program_kernel(const u32* const* __re
             case OP_LE: regs[dst] = regs[a] <= regs[b] ? 1u : 0u; break;
             case OP_DIVC: regs[dst] = regs[a] / b; break;
             case OP_MODC: regs[dst] = regs[a] % b; break;
+            case OP_U32DIVREM: regs[dst] = u32_divrem_part(qm_make(regs[a], regs[a + 1], regs[a + 2], regs[a + 3]), b); break;
             default: break;
         }
     }

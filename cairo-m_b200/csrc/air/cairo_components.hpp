@@ -22,6 +22,8 @@
 //   u32_store_sub_fp_fp  .../opcodes/u32_store_sub_fp_fp.rs:200-290, :540-814
 //   u32_store_lt_fp_fp   .../opcodes/u32_store_lt_fp_fp.rs:195-290, :560-794
 //   u32_store_bitwise_fp_fp .../opcodes/u32_store_bitwise_fp_fp.rs:190-360, :560-783
+//   u32_store_add_fp_imm, u32_store_lt_fp_imm, u32_store_eq_fp_fp, u32_store_eq_fp_imm, u32_store_mul_fp_fp,
+//   u32_store_mul_fp_imm, u32_store_div_fp_fp, u32_store_div_fp_imm, u32_store_bitwise_fp_imm: cited at each struct
 //   bitwise (table)      crates/prover/src/preprocessed/bitwise.rs:72-140 (multiplicities), :196-215 (evaluate), :253-290 (columns)
 //   memory         crates/prover/src/components/memory.rs:93-195, :294-366
 //   clock_update   crates/prover/src/components/clock_update.rs:70-160, :217-262
@@ -50,6 +52,10 @@ constexpr u32 OP_STORE_DOUBLE_DEREF_FP = 8, OP_STORE_DOUBLE_DEREF_FP_FP = 42, OP
 constexpr u32 OP_STORE_LE_FP_IMM = 48;
 constexpr u32 OP_U32_STORE_ADD_FP_FP = 15, OP_U32_STORE_SUB_FP_FP = 16, OP_U32_STORE_IMM = 23;
 constexpr u32 OP_U32_STORE_LT_FP_FP = 28;
+constexpr u32 OP_U32_STORE_MUL_FP_FP = 17, OP_U32_STORE_DIV_REM_FP_FP = 18, OP_U32_STORE_ADD_FP_IMM = 19;
+constexpr u32 OP_U32_STORE_MUL_FP_IMM = 21, OP_U32_STORE_DIV_REM_FP_IMM = 22, OP_U32_STORE_EQ_FP_FP = 24;
+constexpr u32 OP_U32_STORE_EQ_FP_IMM = 30, OP_U32_STORE_LT_FP_IMM = 34;
+constexpr u32 OP_U32_STORE_AND_FP_IMM = 39, OP_U32_STORE_OR_FP_IMM = 40, OP_U32_STORE_XOR_FP_IMM = 41;
 constexpr u32 OP_U32_STORE_AND_FP_FP = 36, OP_U32_STORE_OR_FP_FP = 37, OP_U32_STORE_XOR_FP_FP = 38;
 
 // Lookup tables (preprocessed columns with a multiplicity component): the table row a looked-up
@@ -70,7 +76,7 @@ constexpr u32 RC20_LIMIT = (1u << LOG_SIZE_RC_20) - 1;  // crates/prover/src/ada
 // crates/prover/src/utils/data_accesses.rs:10-28)
 constexpr int IN_PC = 0, IN_FP = 1, IN_CLOCK = 2, IN_INST_PREV_CLOCK = 3, IN_INST0 = 4;
 constexpr int IN_ACC_BASE = 10, ACC_ADDRESS = 0, ACC_PREV_CLOCK = 1, ACC_PREV_VALUE = 2, ACC_VALUE = 3;
-constexpr int MAX_ACCESSES = 6;  // u32 binary ops touch 3 operands x 2 limbs
+constexpr int MAX_ACCESSES = 8;  // u32 DivRem touches 4 operands x 2 limbs
 constexpr int N_BUNDLE_INPUTS = IN_ACC_BASE + 4 * MAX_ACCESSES;
 inline int in_acc(int k, int field) { return IN_ACC_BASE + 4 * k + field; }
 
@@ -1253,12 +1259,854 @@ struct StoreLeFpImmEval : OpcodeEvalBase {
     }
 };
 
-// Opcode components in claim order (crates/prover/src/components/opcodes/mod.rs:223-268); the u32 /
-// bitwise families are restated only for u32_store_imm / add_fp_fp / sub_fp_fp so far (11 more to go).
+// ------------------------------------------------------------------ two-word u32 instructions
+// The *_fp_imm u32 opcodes (and DivRem) carry 5-6 M31s: they span two QM31 words at pc, pc+1 (registers advance by
+// 2), the second word is read with the same inst_prev_clock (e.g. u32_store_add_fp_imm.rs:568-586).
+
+// ------------------------------------------------------------------ u32_store_add_fp_imm
+//   .../opcodes/u32_store_add_fp_imm.rs:186-335 (write_trace), :520-742 (evaluate)
+struct U32StoreAddFpImmEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 19;
+    static const char* name() { return "u32_store_add_fp_imm"; }
+    static std::vector<u32> opcodes() { return {OP_U32_STORE_ADD_FP_IMM}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto two_pow_16 = eval.f_const(1u << 16);
+        auto opcode_constant = eval.f_const(OP_U32_STORE_ADD_FP_IMM);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto src_off = eval.next_trace_mask();
+        auto imm_lo = eval.next_trace_mask();
+        auto imm_hi = eval.next_trace_mask();
+        auto dst_off = eval.next_trace_mask();
+        auto op0_val_lo = eval.next_trace_mask();
+        auto op0_val_hi = eval.next_trace_mask();
+        auto op0_prev_clock_lo = eval.next_trace_mask();
+        auto op0_prev_clock_hi = eval.next_trace_mask();
+        auto dst_prev_val_lo = eval.next_trace_mask();
+        auto dst_prev_val_hi = eval.next_trace_mask();
+        auto dst_prev_clock_lo = eval.next_trace_mask();
+        auto dst_prev_clock_hi = eval.next_trace_mask();
+        auto u16_carry = eval.next_trace_mask();
+        auto u32_carry = eval.next_trace_mask();
+        auto res_lo = op0_val_lo + imm_lo - u16_carry * two_pow_16;
+        auto res_hi = op0_val_hi + imm_hi + u16_carry - u32_carry * two_pow_16;
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(u16_carry * (one - u16_carry));
+        eval.add_constraint(u32_carry * (one - u32_carry));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, src_off, imm_lo, imm_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src_off, imm_lo, imm_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc + one, inst_prev_clock, dst_off});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc + one, clock, dst_off});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src_off, op0_prev_clock_lo, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src_off, clock, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src_off + one, op0_prev_clock_hi, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src_off + one, clock, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_clock_lo, dst_prev_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, res_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off + one, dst_prev_clock_hi, dst_prev_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off + one, clock, res_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op0_val_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op0_val_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {imm_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {imm_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {res_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {res_hi});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_hi - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock_hi - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto one = t.f_const(1);
+        auto limb_max = t.f_const(0xffff);
+        auto imm_lo = t.in(IN_INST0 + 2), imm_hi = t.in(IN_INST0 + 3);
+        auto op0_lo = t.in(in_acc(0, ACC_VALUE)), op0_hi = t.in(in_acc(1, ACC_VALUE));
+        auto u16_carry = one - t.f_le(op0_lo + imm_lo, limb_max);
+        auto u32_carry = one - t.f_le(op0_hi + imm_hi + u16_carry, limb_max);
+        t.out(0, t.enabler());
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, imm_lo);
+        t.out(7, imm_hi);
+        t.out(8, t.in(IN_INST0 + 4));
+        t.out(9, op0_lo);
+        t.out(10, op0_hi);
+        t.out(11, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(12, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(13, t.in(in_acc(2, ACC_PREV_VALUE)));
+        t.out(14, t.in(in_acc(3, ACC_PREV_VALUE)));
+        t.out(15, t.in(in_acc(2, ACC_PREV_CLOCK)));
+        t.out(16, t.in(in_acc(3, ACC_PREV_CLOCK)));
+        t.out(17, u16_carry);
+        t.out(18, u32_carry);
+    }
+};
+
+// ------------------------------------------------------------------ u32_store_lt_fp_imm
+//   .../opcodes/u32_store_lt_fp_imm.rs:188-331, :492-694
+struct U32StoreLtFpImmEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 17;
+    static const char* name() { return "u32_store_lt_fp_imm"; }
+    static std::vector<u32> opcodes() { return {OP_U32_STORE_LT_FP_IMM}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto two_pow_16 = eval.f_const(1u << 16);
+        auto opcode_constant = eval.f_const(OP_U32_STORE_LT_FP_IMM);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto src_off = eval.next_trace_mask();
+        auto imm_lo = eval.next_trace_mask();
+        auto imm_hi = eval.next_trace_mask();
+        auto dst_off = eval.next_trace_mask();
+        auto op0_val_lo = eval.next_trace_mask();
+        auto op0_val_hi = eval.next_trace_mask();
+        auto op0_prev_clock_lo = eval.next_trace_mask();
+        auto op0_prev_clock_hi = eval.next_trace_mask();
+        auto dst_prev_val = eval.next_trace_mask();
+        auto dst_prev_clock = eval.next_trace_mask();
+        auto borrow_lo = eval.next_trace_mask();
+        auto borrow_hi = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(borrow_lo * (one - borrow_lo));
+        eval.add_constraint(borrow_hi * (one - borrow_hi));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, src_off, imm_lo, imm_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src_off, imm_lo, imm_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc + one, inst_prev_clock, dst_off});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc + one, clock, dst_off});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src_off, op0_prev_clock_lo, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src_off, clock, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src_off + one, op0_prev_clock_hi, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src_off + one, clock, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_clock, dst_prev_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, one - borrow_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op0_val_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op0_val_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {imm_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {imm_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {imm_lo - enabler + borrow_lo * two_pow_16 - op0_val_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {imm_hi - borrow_lo + borrow_hi * two_pow_16 - op0_val_hi});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_hi - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto enabler = t.enabler();
+        auto one = t.f_const(1);
+        auto imm_lo = t.in(IN_INST0 + 2), imm_hi = t.in(IN_INST0 + 3);
+        auto op0_lo = t.in(in_acc(0, ACC_VALUE)), op0_hi = t.in(in_acc(1, ACC_VALUE));
+        // borrows of imm - op0 - enabler (u32_store_lt_fp_imm.rs:215-252): x < y + z
+        auto borrow_lo = one - t.f_le(op0_lo + enabler, imm_lo);
+        auto borrow_hi = one - t.f_le(op0_hi + borrow_lo, imm_hi);
+        t.out(0, enabler);
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, imm_lo);
+        t.out(7, imm_hi);
+        t.out(8, t.in(IN_INST0 + 4));
+        t.out(9, op0_lo);
+        t.out(10, op0_hi);
+        t.out(11, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(12, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(13, t.in(in_acc(2, ACC_PREV_VALUE)));
+        t.out(14, t.in(in_acc(2, ACC_PREV_CLOCK)));
+        t.out(15, borrow_lo);
+        t.out(16, borrow_hi);
+    }
+};
+
+// ------------------------------------------------------------------ u32_store_eq_fp_fp
+//   .../opcodes/u32_store_eq_fp_fp.rs:200-353, :498-742
+// As in the reference, dst_off is taken from instruction word 4 (u32_store_eq_fp_fp.rs:210), which a one-word
+// instruction leaves at 0: only `U32StoreEqFpFp` instructions with dst_off = 0 are provable there and here.
+struct U32StoreEqFpFpEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 22;
+    static const char* name() { return "u32_store_eq_fp_fp"; }
+    static std::vector<u32> opcodes() { return {OP_U32_STORE_EQ_FP_FP}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto opcode_constant = eval.f_const(OP_U32_STORE_EQ_FP_FP);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto src0_off = eval.next_trace_mask();
+        auto src1_off = eval.next_trace_mask();
+        auto dst_off = eval.next_trace_mask();
+        auto op0_val_lo = eval.next_trace_mask();
+        auto op0_val_hi = eval.next_trace_mask();
+        auto op0_prev_clock_lo = eval.next_trace_mask();
+        auto op0_prev_clock_hi = eval.next_trace_mask();
+        auto op1_val_lo = eval.next_trace_mask();
+        auto op1_val_hi = eval.next_trace_mask();
+        auto op1_prev_clock_lo = eval.next_trace_mask();
+        auto op1_prev_clock_hi = eval.next_trace_mask();
+        auto dst_prev_val = eval.next_trace_mask();
+        auto dst_prev_clock = eval.next_trace_mask();
+        auto diff_inv_lo = eval.next_trace_mask();
+        auto diff_inv_hi = eval.next_trace_mask();
+        auto is_eq_lo = eval.next_trace_mask();
+        auto is_eq_prod = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        auto diff_lo = op1_val_lo - op0_val_lo;
+        auto diff_hi = op1_val_hi - op0_val_hi;
+        eval.add_constraint(diff_lo * (diff_inv_lo * diff_lo - one));
+        eval.add_constraint(diff_hi * (diff_inv_hi * diff_hi - one));
+        eval.add_constraint(is_eq_lo - (one - diff_lo * diff_inv_lo));
+        eval.add_constraint(is_eq_prod - is_eq_lo * (one - diff_hi * diff_inv_hi));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, src0_off, src1_off, dst_off});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src0_off, src1_off, dst_off});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off, op0_prev_clock_lo, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off, clock, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off + one, op0_prev_clock_hi, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off + one, clock, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src1_off, op1_prev_clock_lo, op1_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src1_off, clock, op1_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src1_off + one, op1_prev_clock_hi, op1_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src1_off + one, clock, op1_val_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_clock, dst_prev_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, is_eq_prod});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op0_val_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op0_val_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op1_val_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op1_val_hi});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_hi - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op1_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op1_prev_clock_hi - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto one = t.f_const(1);
+        auto op0_lo = t.in(in_acc(0, ACC_VALUE)), op0_hi = t.in(in_acc(1, ACC_VALUE));
+        auto op1_lo = t.in(in_acc(2, ACC_VALUE)), op1_hi = t.in(in_acc(3, ACC_VALUE));
+        auto diff_lo = op1_lo - op0_lo, diff_hi = op1_hi - op0_hi;
+        auto diff_inv_lo = t.f_inv(diff_lo), diff_inv_hi = t.f_inv(diff_hi);  // 0 -> 0
+        auto is_eq_lo = one - diff_lo * diff_inv_lo;
+        auto is_eq_prod = is_eq_lo * (one - diff_hi * diff_inv_hi);
+        t.out(0, t.enabler());
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, t.in(IN_INST0 + 2));
+        t.out(7, t.in(IN_INST0 + 4));  // sic: instruction word 4 (see the note above the struct)
+        t.out(8, op0_lo);
+        t.out(9, op0_hi);
+        t.out(10, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(11, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(12, op1_lo);
+        t.out(13, op1_hi);
+        t.out(14, t.in(in_acc(2, ACC_PREV_CLOCK)));
+        t.out(15, t.in(in_acc(3, ACC_PREV_CLOCK)));
+        t.out(16, t.in(in_acc(4, ACC_PREV_VALUE)));
+        t.out(17, t.in(in_acc(4, ACC_PREV_CLOCK)));
+        t.out(18, diff_inv_lo);
+        t.out(19, diff_inv_hi);
+        t.out(20, is_eq_lo);
+        t.out(21, is_eq_prod);
+    }
+};
+
+// ------------------------------------------------------------------ u32_store_eq_fp_imm
+//   .../opcodes/u32_store_eq_fp_imm.rs:191-294, :438-628
+// Restated as written: the second instruction word is looked up at `pc` (not pc + 1) with the value dst_off
+// (u32_store_eq_fp_imm.rs:500-512), so the Memory relation cannot balance for an enabled row; in the reference as
+// here the component only ever proves its padding (it is part of every proof with 16 empty rows).  The host VM does
+// not execute this opcode.
+struct U32StoreEqFpImmEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 16;
+    static const char* name() { return "u32_store_eq_fp_imm"; }
+    static std::vector<u32> opcodes() { return {OP_U32_STORE_EQ_FP_IMM}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto two_pow_16 = eval.f_const(1u << 16);
+        auto opcode_constant = eval.f_const(OP_U32_STORE_EQ_FP_IMM);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto src0_off = eval.next_trace_mask();
+        auto imm_lo = eval.next_trace_mask();
+        auto imm_hi = eval.next_trace_mask();
+        auto dst_off = eval.next_trace_mask();
+        auto op0_val_lo = eval.next_trace_mask();
+        auto op0_val_hi = eval.next_trace_mask();
+        auto op0_prev_clock_lo = eval.next_trace_mask();
+        auto op0_prev_clock_hi = eval.next_trace_mask();
+        auto dst_prev_val = eval.next_trace_mask();
+        auto dst_prev_clock = eval.next_trace_mask();
+        auto diff_inv = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        auto diff = op0_val_lo + op0_val_hi * two_pow_16 - imm_lo - imm_hi * two_pow_16;
+        eval.add_constraint(diff * (diff_inv * diff - one));
+        eval.add_constraint(diff_inv * (diff_inv * diff - one));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, src0_off, imm_lo, imm_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src0_off, imm_lo, imm_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, dst_off});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, dst_off});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off, op0_prev_clock_lo, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off, clock, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off + one, op0_prev_clock_hi, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off + one, clock, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_clock, dst_prev_val});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, one - diff * diff_inv});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op0_val_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {op0_val_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {imm_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {imm_hi});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_hi - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto two_pow_16 = t.f_const(1u << 16);
+        auto imm_lo = t.in(IN_INST0 + 2), imm_hi = t.in(IN_INST0 + 3);
+        auto op0_lo = t.in(in_acc(0, ACC_VALUE)), op0_hi = t.in(in_acc(1, ACC_VALUE));
+        auto diff = op0_lo + op0_hi * two_pow_16 - imm_lo - imm_hi * two_pow_16;
+        t.out(0, t.enabler());
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, t.in(IN_INST0 + 1));
+        t.out(6, imm_lo);
+        t.out(7, imm_hi);
+        t.out(8, t.in(IN_INST0 + 4));
+        t.out(9, op0_lo);
+        t.out(10, op0_hi);
+        t.out(11, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(12, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(13, t.in(in_acc(2, ACC_PREV_VALUE)));
+        t.out(14, t.in(in_acc(2, ACC_PREV_CLOCK)));
+        t.out(15, t.f_inv(diff));
+    }
+};
+
+// ------------------------------------------------------------------ u32_store_mul_fp_fp / u32_store_mul_fp_imm
+//   .../opcodes/u32_store_mul_fp_fp.rs:235-495, :672-1058;  .../opcodes/u32_store_mul_fp_imm.rs:229-451, :651-985
+// Schoolbook product of 8-bit limbs, low 32 bits kept; carries bounded through RangeCheck16(MAX_CARRY_k - carry_k).
+// As in the reference, op1's previous clocks are not range-checked in the fp_fp form (5 RangeCheck20 lookups).
+constexpr u32 U32_MUL_MAX_CARRY[4] = {254, 509, 764, 1019};
+template <bool IMM>
+struct U32StoreMulEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = IMM ? 29 : 32;
+    static const char* name() { return IMM ? "u32_store_mul_fp_imm" : "u32_store_mul_fp_fp"; }
+    static std::vector<u32> opcodes() { return {IMM ? OP_U32_STORE_MUL_FP_IMM : OP_U32_STORE_MUL_FP_FP}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        typedef decltype(eval.f_const(0)) F;
+        auto one = eval.f_const(1);
+        auto two_pow_8 = eval.f_const(1u << 8);
+        auto opcode_constant = eval.f_const(IMM ? OP_U32_STORE_MUL_FP_IMM : OP_U32_STORE_MUL_FP_FP);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto src0_off = eval.next_trace_mask();
+        F x[4] = {one, one, one, one}, y[4] = {one, one, one, one}, res[4] = {one, one, one, one}, carry[4] = {one, one, one, one};
+        F src1_off = one, dst_off = one, op1_prev_clock_lo = one, op1_prev_clock_hi = one;
+        if (IMM) {
+            for (int k = 0; k < 4; k++) y[k] = eval.next_trace_mask();  // imm_0..3
+            dst_off = eval.next_trace_mask();
+        } else {
+            src1_off = eval.next_trace_mask();
+            dst_off = eval.next_trace_mask();
+        }
+        for (int k = 0; k < 4; k++) x[k] = eval.next_trace_mask();  // op0_0..3
+        auto op0_prev_clock_lo = eval.next_trace_mask();
+        auto op0_prev_clock_hi = eval.next_trace_mask();
+        if (!IMM) {
+            for (int k = 0; k < 4; k++) y[k] = eval.next_trace_mask();  // op1_0..3
+            op1_prev_clock_lo = eval.next_trace_mask();
+            op1_prev_clock_hi = eval.next_trace_mask();
+        }
+        auto dst_prev_val_lo = eval.next_trace_mask();
+        auto dst_prev_val_hi = eval.next_trace_mask();
+        auto dst_prev_clock_lo = eval.next_trace_mask();
+        auto dst_prev_clock_hi = eval.next_trace_mask();
+        for (int k = 0; k < 4; k++) res[k] = eval.next_trace_mask();
+        for (int k = 0; k < 4; k++) carry[k] = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(enabler * (res[0] - (x[0] * y[0] - carry[0] * two_pow_8)));
+        eval.add_constraint(enabler * (res[1] - (x[0] * y[1] + x[1] * y[0] + carry[0] - carry[1] * two_pow_8)));
+        eval.add_constraint(enabler * (res[2] - (x[0] * y[2] + x[1] * y[1] + x[2] * y[0] + carry[1] - carry[2] * two_pow_8)));
+        eval.add_constraint(enabler * (res[3] - (x[0] * y[3] + x[1] * y[2] + x[2] * y[1] + x[3] * y[0] + carry[2] - carry[3] * two_pow_8)));
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        if (IMM) {
+            eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one + one, fp, clock + one});
+            eval.add_to_relation(REL_MEMORY, -eval.ef(enabler),
+                                 {pc, inst_prev_clock, opcode_constant, src0_off, y[0] + y[1] * two_pow_8, y[2] + y[3] * two_pow_8});
+            eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src0_off, y[0] + y[1] * two_pow_8, y[2] + y[3] * two_pow_8});
+            eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc + one, inst_prev_clock, dst_off});
+            eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc + one, clock, dst_off});
+        } else {
+            eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one, fp, clock + one});
+            eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, src0_off, src1_off, dst_off});
+            eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src0_off, src1_off, dst_off});
+        }
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off, op0_prev_clock_lo, x[0] + x[1] * two_pow_8});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off, clock, x[0] + x[1] * two_pow_8});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off + one, op0_prev_clock_hi, x[2] + x[3] * two_pow_8});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off + one, clock, x[2] + x[3] * two_pow_8});
+        if (!IMM) {
+            eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src1_off, op1_prev_clock_lo, y[0] + y[1] * two_pow_8});
+            eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src1_off, clock, y[0] + y[1] * two_pow_8});
+            eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src1_off + one, op1_prev_clock_hi, y[2] + y[3] * two_pow_8});
+            eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src1_off + one, clock, y[2] + y[3] * two_pow_8});
+        }
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_clock_lo, dst_prev_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, res[0] + res[1] * two_pow_8});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off + one, dst_prev_clock_hi, dst_prev_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off + one, clock, res[2] + res[3] * two_pow_8});
+        for (int k = 0; k < 4; k++) eval.add_to_relation(REL_RC8, -eval.ef_one(), {x[k]});
+        for (int k = 0; k < 4; k++) eval.add_to_relation(REL_RC8, -eval.ef_one(), {y[k]});
+        for (int k = 0; k < 4; k++) eval.add_to_relation(REL_RC8, -eval.ef_one(), {res[k]});
+        for (int k = 0; k < 4; k++) eval.add_to_relation(REL_RC16, -eval.ef_one(), {eval.f_const(U32_MUL_MAX_CARRY[k]) - carry[k]});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_hi - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock_hi - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        typedef decltype(t.f_const(0)) F;
+        auto two_pow_8 = t.f_const(1u << 8);
+        auto lo8 = [&](F v) { return t.f_and(v, 0xff); };
+        auto hi8 = [&](F v) { return t.f_shr(v, 8); };  // no mask, as in decompose_8 of the mul components
+        const int dst_acc = IMM ? 2 : 4;
+        F op0_lo = t.in(in_acc(0, ACC_VALUE)), op0_hi = t.in(in_acc(1, ACC_VALUE));
+        F op1_lo = IMM ? t.in(IN_INST0 + 2) : t.in(in_acc(2, ACC_VALUE));
+        F op1_hi = IMM ? t.in(IN_INST0 + 3) : t.in(in_acc(3, ACC_VALUE));
+        F x[4] = {lo8(op0_lo), hi8(op0_lo), lo8(op0_hi), hi8(op0_hi)};
+        F y[4] = {lo8(op1_lo), hi8(op1_lo), lo8(op1_hi), hi8(op1_hi)};
+        F sum0 = x[0] * y[0];
+        F carry0 = t.f_shr(sum0, 8);
+        F sum1 = x[0] * y[1] + x[1] * y[0] + carry0;
+        F carry1 = t.f_shr(sum1, 8);
+        F sum2 = x[0] * y[2] + x[1] * y[1] + x[2] * y[0] + carry1;
+        F carry2 = t.f_shr(sum2, 8);
+        F sum3 = x[0] * y[3] + x[1] * y[2] + x[2] * y[1] + x[3] * y[0] + carry2;
+        F carry3 = t.f_shr(sum3, 8);
+        F res[4] = {sum0 - carry0 * two_pow_8, sum1 - carry1 * two_pow_8, sum2 - carry2 * two_pow_8, sum3 - carry3 * two_pow_8};
+        F carry[4] = {carry0, carry1, carry2, carry3};
+        int c = 0;
+        t.out(c++, t.enabler());
+        t.out(c++, t.in(IN_PC));
+        t.out(c++, t.in(IN_FP));
+        t.out(c++, t.in(IN_CLOCK));
+        t.out(c++, t.in(IN_INST_PREV_CLOCK));
+        t.out(c++, t.in(IN_INST0 + 1));
+        if (IMM) {
+            for (int k = 0; k < 4; k++) t.out(c++, y[k]);
+            t.out(c++, t.in(IN_INST0 + 4));
+        } else {
+            t.out(c++, t.in(IN_INST0 + 2));
+            t.out(c++, t.in(IN_INST0 + 3));
+        }
+        for (int k = 0; k < 4; k++) t.out(c++, x[k]);
+        t.out(c++, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(c++, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        if (!IMM) {
+            for (int k = 0; k < 4; k++) t.out(c++, y[k]);
+            t.out(c++, t.in(in_acc(2, ACC_PREV_CLOCK)));
+            t.out(c++, t.in(in_acc(3, ACC_PREV_CLOCK)));
+        }
+        t.out(c++, t.in(in_acc(dst_acc, ACC_PREV_VALUE)));
+        t.out(c++, t.in(in_acc(dst_acc + 1, ACC_PREV_VALUE)));
+        t.out(c++, t.in(in_acc(dst_acc, ACC_PREV_CLOCK)));
+        t.out(c++, t.in(in_acc(dst_acc + 1, ACC_PREV_CLOCK)));
+        for (int k = 0; k < 4; k++) t.out(c++, res[k]);
+        for (int k = 0; k < 4; k++) t.out(c++, carry[k]);
+    }
+};
+typedef U32StoreMulEval<false> U32StoreMulFpFpEval;
+typedef U32StoreMulEval<true> U32StoreMulFpImmEval;
+
+// ------------------------------------------------------------------ u32_store_div_fp_fp / u32_store_div_fp_imm (DivRem)
+//   .../opcodes/u32_store_div_fp_fp.rs:298-752, :977-1509;  .../opcodes/u32_store_div_fp_imm.rs:288-710, :937-1436
+// n = q * d + r with r < d: q * d as a 64-bit schoolbook product of 8-bit limbs (prod_0..7), prod + r = n on 16-bit
+// limbs with the upper half forced to zero, and d - r - 1 without a final borrow.
+constexpr u32 U32_DIV_MAX_CARRY[7] = {254, 509, 764, 1019, 765, 510, 255};
+template <bool IMM>
+struct U32StoreDivEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = IMM ? 51 : 54;
+    static const char* name() { return IMM ? "u32_store_div_fp_imm" : "u32_store_div_fp_fp"; }
+    static std::vector<u32> opcodes() { return {IMM ? OP_U32_STORE_DIV_REM_FP_IMM : OP_U32_STORE_DIV_REM_FP_FP}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        typedef decltype(eval.f_const(0)) F;
+        auto one = eval.f_const(1);
+        auto two_pow_8 = eval.f_const(1u << 8);
+        auto two_pow_16 = eval.f_const(1u << 16);
+        auto opcode_constant = eval.f_const(IMM ? OP_U32_STORE_DIV_REM_FP_IMM : OP_U32_STORE_DIV_REM_FP_FP);
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto src0_off = eval.next_trace_mask();
+        F d[4] = {one, one, one, one}, q[4] = {one, one, one, one};
+        F src1_off = one, dst_off = one, dst_rem_off = one, op1_prev_clock_lo = one, op1_prev_clock_hi = one;
+        if (IMM) {
+            for (int k = 0; k < 4; k++) d[k] = eval.next_trace_mask();  // imm_0..3
+            dst_off = eval.next_trace_mask();
+            dst_rem_off = eval.next_trace_mask();
+        } else {
+            src1_off = eval.next_trace_mask();
+            dst_off = eval.next_trace_mask();
+            dst_rem_off = eval.next_trace_mask();
+        }
+        auto n_lo = eval.next_trace_mask();
+        auto n_hi = eval.next_trace_mask();
+        auto op0_prev_clock_lo = eval.next_trace_mask();
+        auto op0_prev_clock_hi = eval.next_trace_mask();
+        if (!IMM) {
+            for (int k = 0; k < 4; k++) d[k] = eval.next_trace_mask();  // op1_val_0..3
+            op1_prev_clock_lo = eval.next_trace_mask();
+            op1_prev_clock_hi = eval.next_trace_mask();
+        }
+        auto dst_prev_val_lo = eval.next_trace_mask();
+        auto dst_prev_val_hi = eval.next_trace_mask();
+        auto dst_prev_clock_lo = eval.next_trace_mask();
+        auto dst_prev_clock_hi = eval.next_trace_mask();
+        auto dst_rem_prev_val_lo = eval.next_trace_mask();
+        auto dst_rem_prev_val_hi = eval.next_trace_mask();
+        auto dst_rem_prev_clock_lo = eval.next_trace_mask();
+        auto dst_rem_prev_clock_hi = eval.next_trace_mask();
+        for (int k = 0; k < 4; k++) q[k] = eval.next_trace_mask();
+        std::vector<F> mc, prod;
+        for (int k = 0; k < 7; k++) mc.push_back(eval.next_trace_mask());    // mul_carry_0..6
+        for (int k = 0; k < 8; k++) prod.push_back(eval.next_trace_mask());  // prod_0..7
+        auto add_carry_0 = eval.next_trace_mask();
+        auto add_carry_1 = eval.next_trace_mask();
+        auto add_carry_2 = eval.next_trace_mask();
+        auto add_carry_3 = eval.next_trace_mask();
+        auto sub_borrow_0 = eval.next_trace_mask();
+        auto sub_borrow_1 = eval.next_trace_mask();
+        auto r_lo = eval.next_trace_mask();
+        auto r_hi = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(enabler * add_carry_0 * (one - add_carry_0));
+        eval.add_constraint(enabler * add_carry_1 * (one - add_carry_1));
+        eval.add_constraint(enabler * add_carry_2 * (one - add_carry_2));
+        eval.add_constraint(enabler * sub_borrow_0 * (one - sub_borrow_0));
+        auto d_lo = d[0] + d[1] * two_pow_8;
+        auto d_hi = d[2] + d[3] * two_pow_8;
+        eval.add_constraint(enabler * (q[0] * d[0] - mc[0] * two_pow_8 - prod[0]));
+        eval.add_constraint(enabler * (q[0] * d[1] + q[1] * d[0] + mc[0] - mc[1] * two_pow_8 - prod[1]));
+        eval.add_constraint(enabler * (q[0] * d[2] + q[2] * d[0] + q[1] * d[1] + mc[1] - mc[2] * two_pow_8 - prod[2]));
+        eval.add_constraint(enabler * (q[0] * d[3] + q[3] * d[0] + q[1] * d[2] + q[2] * d[1] + mc[2] - mc[3] * two_pow_8 - prod[3]));
+        eval.add_constraint(enabler * (q[1] * d[3] + q[3] * d[1] + q[2] * d[2] + mc[3] - mc[4] * two_pow_8 - prod[4]));
+        eval.add_constraint(enabler * (q[2] * d[3] + q[3] * d[2] + mc[4] - mc[5] * two_pow_8 - prod[5]));
+        eval.add_constraint(enabler * (q[3] * d[3] + mc[5] - mc[6] * two_pow_8 - prod[6]));
+        eval.add_constraint(enabler * (mc[6] - prod[7]));
+        eval.add_constraint(enabler * (n_lo - (prod[0] + prod[1] * two_pow_8 + r_lo - add_carry_0 * two_pow_16)));
+        eval.add_constraint(enabler * (n_hi - (prod[2] + prod[3] * two_pow_8 + r_hi + add_carry_0 - add_carry_1 * two_pow_16)));
+        eval.add_constraint(enabler * (prod[4] + prod[5] * two_pow_8 + add_carry_1 - add_carry_2 * two_pow_16));
+        eval.add_constraint(enabler * (prod[6] + prod[7] * two_pow_8 + add_carry_2 - add_carry_3 * two_pow_16));
+        eval.add_constraint(enabler * add_carry_3);
+        auto sub_check_lo = d[0] + d[1] * two_pow_8 + sub_borrow_0 * two_pow_16 - r_lo - one;
+        auto sub_check_hi = d[2] + d[3] * two_pow_8 + sub_borrow_1 * two_pow_16 - r_hi - sub_borrow_0;
+        eval.add_constraint(enabler * sub_borrow_1);
+        auto res_lo = q[0] + q[1] * two_pow_8;
+        auto res_hi = q[2] + q[3] * two_pow_8;
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one + one, fp, clock + one});
+        if (IMM) {
+            eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, src0_off, d_lo, d_hi});
+            eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src0_off, d_lo, d_hi});
+            eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc + one, inst_prev_clock, dst_off, dst_rem_off});
+            eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc + one, clock, dst_off, dst_rem_off});
+        } else {
+            eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, src0_off, src1_off, dst_off});
+            eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src0_off, src1_off, dst_off});
+            eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc + one, inst_prev_clock, dst_rem_off});
+            eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc + one, clock, dst_rem_off});
+        }
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off, op0_prev_clock_lo, n_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off, clock, n_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src0_off + one, op0_prev_clock_hi, n_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src0_off + one, clock, n_hi});
+        if (!IMM) {
+            eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src1_off, op1_prev_clock_lo, d_lo});
+            eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src1_off, clock, d_lo});
+            eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src1_off + one, op1_prev_clock_hi, d_hi});
+            eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src1_off + one, clock, d_hi});
+        }
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_clock_lo, dst_prev_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, res_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off + one, dst_prev_clock_hi, dst_prev_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off + one, clock, res_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_rem_off, dst_rem_prev_clock_lo, dst_rem_prev_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_rem_off, clock, r_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_rem_off + one, dst_rem_prev_clock_hi, dst_rem_prev_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_rem_off + one, clock, r_hi});
+        for (int k = 0; k < 4; k++) eval.add_to_relation(REL_RC8, -eval.ef_one(), {d[k]});
+        for (int k = 0; k < 4; k++) eval.add_to_relation(REL_RC8, -eval.ef_one(), {q[k]});
+        for (int k = 0; k < 8; k++) eval.add_to_relation(REL_RC8, -eval.ef_one(), {prod[k]});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {n_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {n_hi});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {r_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {r_hi});
+        for (int k = 0; k < 7; k++) eval.add_to_relation(REL_RC16, -eval.ef_one(), {eval.f_const(U32_DIV_MAX_CARRY[k]) - mc[k]});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {sub_check_lo});
+        eval.add_to_relation(REL_RC16, -eval.ef_one(), {sub_check_hi});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_hi - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock_hi - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_rem_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_rem_prev_clock_hi - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        typedef decltype(t.f_const(0)) F;
+        auto one = t.f_const(1);
+        auto two_pow_8 = t.f_const(1u << 8);
+        auto limb_max = t.f_const(0xffff);
+        auto lo8 = [&](F v) { return t.f_and(v, 0xff); };
+        auto hi8 = [&](F v) { return t.f_and(t.f_shr(v, 8), 0xff); };
+        const int dst_acc = IMM ? 2 : 4;
+        F n_lo = t.in(in_acc(0, ACC_VALUE)), n_hi = t.in(in_acc(1, ACC_VALUE));
+        F d_lo = IMM ? t.in(IN_INST0 + 2) : t.in(in_acc(2, ACC_VALUE));
+        F d_hi = IMM ? t.in(IN_INST0 + 3) : t.in(in_acc(3, ACC_VALUE));
+        F d[4] = {lo8(d_lo), hi8(d_lo), lo8(d_hi), hi8(d_hi)};
+        F q_lo = t.f_u32_divrem(n_lo, n_hi, d_lo, d_hi, 0), q_hi = t.f_u32_divrem(n_lo, n_hi, d_lo, d_hi, 1);
+        F r_lo = t.f_u32_divrem(n_lo, n_hi, d_lo, d_hi, 2), r_hi = t.f_u32_divrem(n_lo, n_hi, d_lo, d_hi, 3);
+        F q[4] = {lo8(q_lo), hi8(q_lo), lo8(q_hi), hi8(q_hi)};
+        F raw[7] = {q[0] * d[0],
+                    q[0] * d[1] + q[1] * d[0],
+                    q[0] * d[2] + q[2] * d[0] + q[1] * d[1],
+                    q[0] * d[3] + q[3] * d[0] + q[1] * d[2] + q[2] * d[1],
+                    q[1] * d[3] + q[3] * d[1] + q[2] * d[2],
+                    q[2] * d[3] + q[3] * d[2],
+                    q[3] * d[3]};
+        std::vector<F> mc, prod;
+        for (int k = 0; k < 7; k++) {
+            F with_carry = k == 0 ? raw[0] : raw[k] + mc[k - 1];
+            mc.push_back(t.f_shr(with_carry, 8));
+            prod.push_back(with_carry - mc[k] * two_pow_8);
+        }
+        prod.push_back(mc[6]);
+        F add_carry_0 = one - t.f_le(prod[0] + prod[1] * two_pow_8 + r_lo, limb_max);
+        F add_carry_1 = one - t.f_le(prod[2] + prod[3] * two_pow_8 + r_hi + add_carry_0, limb_max);
+        F add_carry_2 = one - t.f_le(prod[4] + prod[5] * two_pow_8 + add_carry_1, limb_max);
+        F add_carry_3 = one - t.f_le(prod[6] + prod[7] * two_pow_8 + add_carry_2, limb_max);
+        // borrows of d - r - 1: d_val < r + 1, then d_val < r + borrow
+        F sub_borrow_0 = one - t.f_le(r_lo + one, d[0] + d[1] * two_pow_8);
+        F sub_borrow_1 = one - t.f_le(r_hi + sub_borrow_0, d[2] + d[3] * two_pow_8);
+        int c = 0;
+        t.out(c++, t.enabler());
+        t.out(c++, t.in(IN_PC));
+        t.out(c++, t.in(IN_FP));
+        t.out(c++, t.in(IN_CLOCK));
+        t.out(c++, t.in(IN_INST_PREV_CLOCK));
+        t.out(c++, t.in(IN_INST0 + 1));
+        if (IMM) {
+            for (int k = 0; k < 4; k++) t.out(c++, d[k]);
+            t.out(c++, t.in(IN_INST0 + 4));
+            // dst_rem_off is rebuilt from the remainder's write address (u32_store_div_fp_imm.rs:311-313)
+            t.out(c++, t.in(in_acc(4, ACC_ADDRESS)) - t.in(IN_FP));
+        } else {
+            t.out(c++, t.in(IN_INST0 + 2));
+            t.out(c++, t.in(IN_INST0 + 3));
+            t.out(c++, t.in(IN_INST0 + 4));
+        }
+        t.out(c++, n_lo);
+        t.out(c++, n_hi);
+        t.out(c++, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(c++, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        if (!IMM) {
+            for (int k = 0; k < 4; k++) t.out(c++, d[k]);
+            t.out(c++, t.in(in_acc(2, ACC_PREV_CLOCK)));
+            t.out(c++, t.in(in_acc(3, ACC_PREV_CLOCK)));
+        }
+        t.out(c++, t.in(in_acc(dst_acc, ACC_PREV_VALUE)));
+        t.out(c++, t.in(in_acc(dst_acc + 1, ACC_PREV_VALUE)));
+        t.out(c++, t.in(in_acc(dst_acc, ACC_PREV_CLOCK)));
+        t.out(c++, t.in(in_acc(dst_acc + 1, ACC_PREV_CLOCK)));
+        t.out(c++, t.in(in_acc(dst_acc + 2, ACC_PREV_VALUE)));
+        t.out(c++, t.in(in_acc(dst_acc + 3, ACC_PREV_VALUE)));
+        t.out(c++, t.in(in_acc(dst_acc + 2, ACC_PREV_CLOCK)));
+        t.out(c++, t.in(in_acc(dst_acc + 3, ACC_PREV_CLOCK)));
+        for (int k = 0; k < 4; k++) t.out(c++, q[k]);
+        for (int k = 0; k < 7; k++) t.out(c++, mc[k]);
+        for (int k = 0; k < 8; k++) t.out(c++, prod[k]);
+        t.out(c++, add_carry_0);
+        t.out(c++, add_carry_1);
+        t.out(c++, add_carry_2);
+        t.out(c++, add_carry_3);
+        t.out(c++, sub_borrow_0);
+        t.out(c++, sub_borrow_1);
+        t.out(c++, r_lo);
+        t.out(c++, r_hi);
+    }
+};
+typedef U32StoreDivEval<false> U32StoreDivFpFpEval;
+typedef U32StoreDivEval<true> U32StoreDivFpImmEval;
+
+// ------------------------------------------------------------------ u32_store_bitwise_fp_imm (And / Or / Xor with an immediate)
+//   .../opcodes/u32_store_bitwise_fp_imm.rs:185-341, :500-716
+struct U32StoreBitwiseFpImmEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 26;
+    static const char* name() { return "u32_store_bitwise_fp_imm"; }
+    static std::vector<u32> opcodes() { return {OP_U32_STORE_AND_FP_IMM, OP_U32_STORE_OR_FP_IMM, OP_U32_STORE_XOR_FP_IMM}; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto enabler = eval.next_trace_mask();
+        auto pc = eval.next_trace_mask();
+        auto fp = eval.next_trace_mask();
+        auto clock = eval.next_trace_mask();
+        auto inst_prev_clock = eval.next_trace_mask();
+        auto opcode_constant = eval.next_trace_mask();
+        auto src_off = eval.next_trace_mask();
+        auto imm_0 = eval.next_trace_mask();
+        auto imm_1 = eval.next_trace_mask();
+        auto imm_2 = eval.next_trace_mask();
+        auto imm_3 = eval.next_trace_mask();
+        auto dst_off = eval.next_trace_mask();
+        auto op0_val_0 = eval.next_trace_mask();
+        auto op0_val_1 = eval.next_trace_mask();
+        auto op0_val_2 = eval.next_trace_mask();
+        auto op0_val_3 = eval.next_trace_mask();
+        auto op0_prev_clock_lo = eval.next_trace_mask();
+        auto op0_prev_clock_hi = eval.next_trace_mask();
+        auto dst_prev_val_lo = eval.next_trace_mask();
+        auto dst_prev_val_hi = eval.next_trace_mask();
+        auto dst_val_0 = eval.next_trace_mask();
+        auto dst_val_1 = eval.next_trace_mask();
+        auto dst_val_2 = eval.next_trace_mask();
+        auto dst_val_3 = eval.next_trace_mask();
+        auto dst_prev_clock_lo = eval.next_trace_mask();
+        auto dst_prev_clock_hi = eval.next_trace_mask();
+        auto two_pow_8 = eval.f_const(1u << 8);
+        auto one = eval.f_const(1);
+        eval.add_constraint(enabler * (enabler - one));
+        auto bitwise_op = opcode_constant - eval.f_const(OP_U32_STORE_AND_FP_IMM);
+        auto op0_val_lo = op0_val_0 + op0_val_1 * two_pow_8;
+        auto op0_val_hi = op0_val_2 + op0_val_3 * two_pow_8;
+        auto imm_lo = imm_0 + imm_1 * two_pow_8;
+        auto imm_hi = imm_2 + imm_3 * two_pow_8;
+        auto dst_val_lo = dst_val_0 + dst_val_1 * two_pow_8;
+        auto dst_val_hi = dst_val_2 + dst_val_3 * two_pow_8;
+        eval.add_to_relation(REL_REGISTERS, -eval.ef(enabler), {pc, fp, clock});
+        eval.add_to_relation(REL_REGISTERS, eval.ef(enabler), {pc + one + one, fp, clock + one});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc, inst_prev_clock, opcode_constant, src_off, imm_lo, imm_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc, clock, opcode_constant, src_off, imm_lo, imm_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {pc + one, inst_prev_clock, dst_off});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {pc + one, clock, dst_off});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src_off, op0_prev_clock_lo, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src_off, clock, op0_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + src_off + one, op0_prev_clock_hi, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + src_off + one, clock, op0_val_hi});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off, dst_prev_clock_lo, dst_prev_val_lo});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off, clock, dst_val_lo});
+        eval.add_to_relation(REL_MEMORY, -eval.ef(enabler), {fp + dst_off + one, dst_prev_clock_hi, dst_prev_val_hi});
+        eval.add_to_relation(REL_MEMORY, eval.ef(enabler), {fp + dst_off + one, clock, dst_val_hi});
+        eval.add_to_relation(REL_BITWISE, -eval.ef_one(), {bitwise_op, op0_val_0, imm_0, dst_val_0});
+        eval.add_to_relation(REL_BITWISE, -eval.ef_one(), {bitwise_op, op0_val_1, imm_1, dst_val_1});
+        eval.add_to_relation(REL_BITWISE, -eval.ef_one(), {bitwise_op, op0_val_2, imm_2, dst_val_2});
+        eval.add_to_relation(REL_BITWISE, -eval.ef_one(), {bitwise_op, op0_val_3, imm_3, dst_val_3});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - inst_prev_clock - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - op0_prev_clock_hi - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock_lo - enabler});
+        eval.add_to_relation(REL_RC20, -eval.ef_one(), {clock - dst_prev_clock_hi - enabler});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        auto enabler = t.enabler();
+        auto base_opcode = t.f_const(OP_U32_STORE_AND_FP_IMM);
+        // padding rows (default bundle = Ret) are rewritten to U32_STORE_AND_FP_IMM (u32_store_bitwise_fp_imm.rs:192-198)
+        auto opcode_constant = enabler * (t.in(IN_INST0) - base_opcode) + base_opcode;
+        auto lo8 = [&](decltype(enabler) v) { return t.f_and(v, 0xff); };
+        auto hi8 = [&](decltype(enabler) v) { return t.f_and(t.f_shr(v, 8), 0xff); };
+        auto imm_lo = t.in(IN_INST0 + 2), imm_hi = t.in(IN_INST0 + 3);
+        auto op0_lo = t.in(in_acc(0, ACC_VALUE)), op0_hi = t.in(in_acc(1, ACC_VALUE));
+        auto dst_lo = t.in(in_acc(2, ACC_VALUE)), dst_hi = t.in(in_acc(3, ACC_VALUE));
+        t.out(0, enabler);
+        t.out(1, t.in(IN_PC));
+        t.out(2, t.in(IN_FP));
+        t.out(3, t.in(IN_CLOCK));
+        t.out(4, t.in(IN_INST_PREV_CLOCK));
+        t.out(5, opcode_constant);
+        t.out(6, t.in(IN_INST0 + 1));
+        t.out(7, lo8(imm_lo));
+        t.out(8, hi8(imm_lo));
+        t.out(9, lo8(imm_hi));
+        t.out(10, hi8(imm_hi));
+        t.out(11, t.in(IN_INST0 + 4));
+        t.out(12, lo8(op0_lo));
+        t.out(13, hi8(op0_lo));
+        t.out(14, lo8(op0_hi));
+        t.out(15, hi8(op0_hi));
+        t.out(16, t.in(in_acc(0, ACC_PREV_CLOCK)));
+        t.out(17, t.in(in_acc(1, ACC_PREV_CLOCK)));
+        t.out(18, t.in(in_acc(2, ACC_PREV_VALUE)));
+        t.out(19, t.in(in_acc(3, ACC_PREV_VALUE)));
+        t.out(20, lo8(dst_lo));
+        t.out(21, hi8(dst_lo));
+        t.out(22, lo8(dst_hi));
+        t.out(23, hi8(dst_hi));
+        t.out(24, t.in(in_acc(2, ACC_PREV_CLOCK)));
+        t.out(25, t.in(in_acc(3, ACC_PREV_CLOCK)));
+    }
+};
+
+// Opcode components in claim order (crates/prover/src/components/opcodes/mod.rs:223-268): all 26.
 #define CM31_OPCODE_EVALS(X)                                                                                          \
     X(AssertEqFpImmEval) X(CallAbsImmEval) X(JmpImmEval) X(JnzFpImmEval) X(RetEval) X(StoreImmEval) X(StoreFpFpEval) \
     X(StoreFpImmEval) X(DoubleDerefFpImmEval) X(DoubleDerefFpFpEval) X(StoreFramePointerEval) X(U32StoreImmEval)   \
-    X(U32StoreLtFpFpEval) X(U32StoreAddFpFpEval) X(U32StoreSubFpFpEval) X(U32StoreBitwiseFpFpEval) X(StoreLeFpImmEval)
+    X(U32StoreAddFpImmEval) X(U32StoreMulFpImmEval) X(U32StoreDivFpImmEval) X(U32StoreEqFpFpEval)                  \
+    X(U32StoreEqFpImmEval) X(U32StoreLtFpImmEval) X(U32StoreLtFpFpEval) X(U32StoreAddFpFpEval)                     \
+    X(U32StoreSubFpFpEval) X(U32StoreMulFpFpEval) X(U32StoreDivFpFpEval) X(U32StoreBitwiseFpFpEval)                \
+    X(U32StoreBitwiseFpImmEval) X(StoreLeFpImmEval)
 
 // ------------------------------------------------------------------ memory (boundary values)
 // inputs: address, clock, value0..3, multiplicity, root

@@ -168,17 +168,64 @@ inline std::vector<Word4> u32_counter_program() {
     };
 }
 
-enum CairoProgramId : u32 { PROGRAM_FIBONACCI_LOOP = 0, PROGRAM_ARRAY_SUM = 1, PROGRAM_U32_COUNTER = 2 };
+// ------------------------------------------------------------------ program: u32_mix
+// The u32 multiplication / division / comparison family and every two-word (*_fp_imm) u32 instruction: per round
+//   t = x * y; u = t + K; (q, r) = u divrem y; v = q * M; w = v ^ A; a = w & B; b = a | 1; (c, d) = b divrem 7;
+//   [fp+28] = (d < 3); [fp+0] = (c == q); x = b + r; y += 2
+// 18 VM steps per round (18 n + 8 in total).  U32StoreEqFpFp writes [fp+0]: the reference's component only proves dst_off = 0
+// (see U32StoreEqFpFpEval).  Two-word instructions occupy two consecutive cells; jump offsets count cells.
+inline std::vector<Word4> u32_mix_program() {
+    const u32 M3 = P - 3, M4 = P - 4;
+    std::vector<Word4> p;
+    auto one_word = [&](u32 op, u32 a, u32 b, u32 c) { p.push_back(Word4{{op, a, b, c}}); };
+    auto two_words = [&](u32 op, u32 a, u32 b, u32 c, u32 d, u32 e = 0) {
+        p.push_back(Word4{{op, a, b, c}});
+        p.push_back(Word4{{d, e, 0, 0}});
+    };
+    one_word(OP_U32_STORE_IMM, 0x1234, 0x5678, 30);                      // x = 0x56781234
+    one_word(OP_U32_STORE_IMM, 0x00f1, 0x0000, 2);                       // y = 0xf1
+    one_word(OP_STORE_IMM, 0, 6, 0);                                     // i = 0
+    const u32 loop = (u32)p.size();
+    one_word(OP_STORE_SUB_FP_FP, 6, M4, 7);                              // [fp+7] = i - n
+    one_word(OP_JNZ_FP_IMM, 7, 2, 0);                                    // if != 0 skip the exit jump
+    const u32 exit_jmp = (u32)p.size();
+    one_word(OP_JMP_REL_IMM, 0, 0, 0);                                   // -> exit (patched below)
+    one_word(OP_U32_STORE_MUL_FP_FP, 30, 2, 8);                          // t = x * y
+    two_words(OP_U32_STORE_ADD_FP_IMM, 8, 0x79b9, 0x9e37, 10);           // u = t + 0x9e3779b9
+    two_words(OP_U32_STORE_DIV_REM_FP_FP, 10, 2, 12, 14);                // q = u / y, r = u % y
+    two_words(OP_U32_STORE_MUL_FP_IMM, 12, 0x0065, 0x0001, 16);          // v = q * 0x10065
+    two_words(OP_U32_STORE_XOR_FP_IMM, 16, 0xa5a5, 0x5a5a, 18);          // w = v ^ 0x5a5aa5a5
+    two_words(OP_U32_STORE_AND_FP_IMM, 18, 0xffff, 0x0fff, 20);          // a = w & 0x0fffffff
+    two_words(OP_U32_STORE_OR_FP_IMM, 20, 0x0001, 0x0000, 22);           // b = a | 1
+    two_words(OP_U32_STORE_DIV_REM_FP_IMM, 22, 7, 0, 24, 26);            // c = b / 7, d = b % 7
+    two_words(OP_U32_STORE_LT_FP_IMM, 26, 3, 0, 28);                     // [fp+28] = (d < 3)
+    one_word(OP_U32_STORE_EQ_FP_FP, 24, 12, 0);                          // [fp+0] = (c == q)
+    one_word(OP_U32_STORE_ADD_FP_FP, 22, 14, 30);                        // x = b + r
+    two_words(OP_U32_STORE_ADD_FP_IMM, 2, 2, 0, 32);                     // y2 = y + 2
+    two_words(OP_U32_STORE_ADD_FP_IMM, 32, 0, 0, 2);                     // y = y2
+    one_word(OP_STORE_ADD_FP_IMM, 6, 1, 5);                              // [fp+5] = i + 1
+    one_word(OP_STORE_ADD_FP_IMM, 5, 0, 6);                              // i = [fp+5]
+    const u32 back = (u32)p.size();
+    one_word(OP_JMP_REL_IMM, m31_sub(loop, back), 0, 0);                 // -> loop
+    p[exit_jmp].v[1] = (u32)p.size() - exit_jmp;
+    one_word(OP_STORE_ADD_FP_IMM, 30, 0, M3);                            // return x.lo
+    one_word(OP_RET, 0, 0, 0);
+    return p;
+}
+
+enum CairoProgramId : u32 { PROGRAM_FIBONACCI_LOOP = 0, PROGRAM_ARRAY_SUM = 1, PROGRAM_U32_COUNTER = 2, PROGRAM_U32_MIX = 3 };
 inline std::vector<Word4> program_by_id(u32 id) {
     switch (id) {
         case PROGRAM_FIBONACCI_LOOP: return fibonacci_loop_program();
         case PROGRAM_ARRAY_SUM: return array_sum_program();
         case PROGRAM_U32_COUNTER: return u32_counter_program();
+        case PROGRAM_U32_MIX: return u32_mix_program();
         default: throw std::runtime_error("unknown program id");
     }
 }
 
 // ------------------------------------------------------------------ VM
+inline int opcode_size_in_m31s(u32 op);
 struct VmTrace {
     std::vector<Registers> trace;                        // one entry per step + the final state
     std::vector<std::pair<u32, Word4>> memory_trace;     // (addr, value) in access order
@@ -228,6 +275,16 @@ inline VmTrace run_program(const std::vector<Word4>& program, u32 arg, size_t ma
         Word4 ins = mem[pc];
         out.memory_trace.push_back({pc, ins});
         u32 op = ins.v[0], a = ins.v[1], b = ins.v[2], c = ins.v[3];
+        int size_m31 = opcode_size_in_m31s(op);
+        u32 d = 0, e = 0;  // operands 4 and 5 live in the second QM31 word of a two-word instruction
+        if (size_m31 > 4) {
+            if (pc + 1 >= prog_len) throw std::runtime_error("vm: truncated two-word instruction");
+            Word4 ins2 = mem[pc + 1];
+            out.memory_trace.push_back({pc + 1, ins2});
+            d = ins2.v[0];
+            e = ins2.v[1];
+        }
+        const u32 pc_step = size_m31 > 4 ? 2 : 1;  // State::advance_by(size_in_qm31s)
         switch (op) {
             case OP_STORE_ADD_FP_FP: case OP_STORE_SUB_FP_FP: case OP_STORE_MUL_FP_FP: case OP_STORE_DIV_FP_FP: {
                 u32 x = rd(m31_add(fp, a)), y = rd(m31_add(fp, b));
@@ -289,6 +346,72 @@ inline VmTrace run_program(const std::vector<Word4>& program, u32 arg, size_t ma
                 if ((x_lo | x_hi | y_lo | y_hi) > 0xffff) throw std::runtime_error("vm: u32 limb out of range");
                 wr(m31_add(fp, c), ((x_hi << 16) | x_lo) < ((y_hi << 16) | y_lo) ? 1u : 0u);
                 pc += 1;
+                break;
+            }
+            case OP_U32_STORE_MUL_FP_FP: {  // wrapping_mul (store.rs:343-344)
+                u32 x_lo = rd(m31_add(fp, a)), x_hi = rd(m31_add(m31_add(fp, a), 1));
+                u32 y_lo = rd(m31_add(fp, b)), y_hi = rd(m31_add(m31_add(fp, b), 1));
+                if ((x_lo | x_hi | y_lo | y_hi) > 0xffff) throw std::runtime_error("vm: u32 limb out of range");
+                u32 r = ((x_hi << 16) | x_lo) * ((y_hi << 16) | y_lo);
+                wr(m31_add(fp, c), r & 0xffff);
+                wr(m31_add(m31_add(fp, c), 1), r >> 16);
+                pc += 1;
+                break;
+            }
+            case OP_U32_STORE_EQ_FP_FP: {  // [fp+dst] = u32(src0) == u32(src1)
+                u32 x_lo = rd(m31_add(fp, a)), x_hi = rd(m31_add(m31_add(fp, a), 1));
+                u32 y_lo = rd(m31_add(fp, b)), y_hi = rd(m31_add(m31_add(fp, b), 1));
+                if ((x_lo | x_hi | y_lo | y_hi) > 0xffff) throw std::runtime_error("vm: u32 limb out of range");
+                wr(m31_add(fp, c), (x_lo == y_lo && x_hi == y_hi) ? 1u : 0u);
+                pc += 1;
+                break;
+            }
+            case OP_U32_STORE_DIV_REM_FP_FP: {  // u32_store_div_rem_fp_fp (store.rs:346-373): dst = n / d, dst_rem = n % d
+                u32 x_lo = rd(m31_add(fp, a)), x_hi = rd(m31_add(m31_add(fp, a), 1));
+                u32 y_lo = rd(m31_add(fp, b)), y_hi = rd(m31_add(m31_add(fp, b), 1));
+                if ((x_lo | x_hi | y_lo | y_hi) > 0xffff) throw std::runtime_error("vm: u32 limb out of range");
+                u32 x = (x_hi << 16) | x_lo, y = (y_hi << 16) | y_lo;
+                if (y == 0) throw std::runtime_error("vm: division by zero");
+                wr(m31_add(fp, c), (x / y) & 0xffff);
+                wr(m31_add(m31_add(fp, c), 1), (x / y) >> 16);
+                wr(m31_add(fp, d), (x % y) & 0xffff);
+                wr(m31_add(m31_add(fp, d), 1), (x % y) >> 16);
+                pc += pc_step;
+                break;
+            }
+            case OP_U32_STORE_ADD_FP_IMM: case OP_U32_STORE_MUL_FP_IMM: case OP_U32_STORE_AND_FP_IMM: case OP_U32_STORE_OR_FP_IMM:
+            case OP_U32_STORE_XOR_FP_IMM: {  // exec_u32_bin_op_fp_imm (store.rs:37-66): operands src_off, imm_lo, imm_hi, dst_off
+                if (b > 0xffff || c > 0xffff) throw std::runtime_error("vm: u32 limb out of range");
+                u32 x_lo = rd(m31_add(fp, a)), x_hi = rd(m31_add(m31_add(fp, a), 1));
+                if ((x_lo | x_hi) > 0xffff) throw std::runtime_error("vm: u32 limb out of range");
+                u32 x = (x_hi << 16) | x_lo, y = (c << 16) | b;
+                u32 r = op == OP_U32_STORE_ADD_FP_IMM ? x + y : op == OP_U32_STORE_MUL_FP_IMM ? x * y : op == OP_U32_STORE_AND_FP_IMM ? (x & y)
+                        : op == OP_U32_STORE_OR_FP_IMM ? (x | y) : (x ^ y);
+                wr(m31_add(fp, d), r & 0xffff);
+                wr(m31_add(m31_add(fp, d), 1), r >> 16);
+                pc += pc_step;
+                break;
+            }
+            case OP_U32_STORE_LT_FP_IMM: {  // [fp+dst] = u32(src) < u32(imm)
+                if (b > 0xffff || c > 0xffff) throw std::runtime_error("vm: u32 limb out of range");
+                u32 x_lo = rd(m31_add(fp, a)), x_hi = rd(m31_add(m31_add(fp, a), 1));
+                if ((x_lo | x_hi) > 0xffff) throw std::runtime_error("vm: u32 limb out of range");
+                wr(m31_add(fp, d), ((x_hi << 16) | x_lo) < ((c << 16) | b) ? 1u : 0u);
+                pc += pc_step;
+                break;
+            }
+            case OP_U32_STORE_DIV_REM_FP_IMM: {  // u32_store_div_rem_fp_imm (store.rs:375-419): operands src, imm_lo, imm_hi, dst, dst_rem
+                if (b > 0xffff || c > 0xffff) throw std::runtime_error("vm: u32 limb out of range");
+                u32 y = (c << 16) | b;
+                if (y == 0) throw std::runtime_error("vm: division by zero");
+                u32 x_lo = rd(m31_add(fp, a)), x_hi = rd(m31_add(m31_add(fp, a), 1));
+                if ((x_lo | x_hi) > 0xffff) throw std::runtime_error("vm: u32 limb out of range");
+                u32 x = (x_hi << 16) | x_lo;
+                wr(m31_add(fp, d), (x / y) & 0xffff);
+                wr(m31_add(m31_add(fp, d), 1), (x / y) >> 16);
+                wr(m31_add(fp, e), (x % y) & 0xffff);
+                wr(m31_add(m31_add(fp, e), 1), (x % y) >> 16);
+                pc += pc_step;
                 break;
             }
             case OP_STORE_LE_FP_IMM: {  // [fp+dst] = ([fp+src] <= imm)   (store.rs:179-191)
@@ -357,7 +480,13 @@ inline int opcode_memory_accesses(u32 op) {
         case OP_JMP_ABS_IMM: case OP_JMP_REL_IMM: return 0;
         case OP_RET: return 2;
         case OP_CALL_ABS_IMM: case OP_U32_STORE_IMM: return 2;
-        case OP_U32_STORE_LT_FP_FP: return 5;
+        case OP_U32_STORE_LT_FP_FP: case OP_U32_STORE_EQ_FP_FP: return 5;
+        case OP_U32_STORE_MUL_FP_FP: return 6;
+        case OP_U32_STORE_DIV_REM_FP_FP: return 8;
+        case OP_U32_STORE_ADD_FP_IMM: case OP_U32_STORE_MUL_FP_IMM: case OP_U32_STORE_AND_FP_IMM: case OP_U32_STORE_OR_FP_IMM:
+        case OP_U32_STORE_XOR_FP_IMM: return 4;
+        case OP_U32_STORE_LT_FP_IMM: return 3;
+        case OP_U32_STORE_DIV_REM_FP_IMM: return 6;
         case OP_U32_STORE_ADD_FP_FP: case OP_U32_STORE_SUB_FP_FP: case OP_U32_STORE_AND_FP_FP: case OP_U32_STORE_OR_FP_FP:
         case OP_U32_STORE_XOR_FP_FP: return 6;
         case OP_ASSERT_EQ_FP_IMM: case OP_STORE_FRAME_POINTER: return 1;
@@ -371,6 +500,9 @@ inline int opcode_size_in_m31s(u32 op) {
         case OP_RET: return 1;
         case OP_JMP_ABS_IMM: case OP_JMP_REL_IMM: return 2;
         case OP_STORE_IMM: case OP_JNZ_FP_IMM: case OP_CALL_ABS_IMM: case OP_ASSERT_EQ_FP_IMM: case OP_STORE_FRAME_POINTER: return 3;
+        case OP_U32_STORE_DIV_REM_FP_FP: case OP_U32_STORE_ADD_FP_IMM: case OP_U32_STORE_MUL_FP_IMM: case OP_U32_STORE_LT_FP_IMM:
+        case OP_U32_STORE_AND_FP_IMM: case OP_U32_STORE_OR_FP_IMM: case OP_U32_STORE_XOR_FP_IMM: case OP_U32_STORE_EQ_FP_IMM: return 5;
+        case OP_U32_STORE_DIV_REM_FP_IMM: return 6;
         default: return 4;
     }
 }
@@ -481,6 +613,12 @@ inline ProverInput import_from_vm(const VmTrace& vm) {
         b.clock = clock;
         b.inst_prev_clock = iarg.prev_clock;
         for (int k = 0; k < 6; k++) b.inst[k] = (k < 4 && k < size_m31) ? ie.second.v[k] : 0;
+        if (size_m31 > 4) {  // second QM31 word of the instruction, pushed at the same clock (adapter/memory.rs:317-339)
+            const auto& ie2 = next_mem();
+            memory.push(ie2.first, ie2.second, clock);
+            b.inst[4] = ie2.second.v[0];
+            if (size_m31 > 5) b.inst[5] = ie2.second.v[1];
+        }
         b.span_start = (u32)in.data_accesses.size();
         for (int k = 0; k < n_acc; k++) {
             const auto& me = next_mem();

@@ -111,6 +111,14 @@ CM_HD QM31 qm_make(u32 a, u32 b, u32 c, u32 d) {
     r.d = d;
     return r;
 }
+// Witness helper of the u32 DivRem components (crates/prover/src/components/opcodes/u32_store_div_fp_fp.rs:360-400):
+// v = (n_lo, n_hi, d_lo, d_hi) as 16-bit limbs; part 0..3 = q_lo, q_hi, r_lo, r_hi of n / d, (0, 0) when d == 0.
+CM_HD u32 u32_divrem_part(QM31 v, u32 part) {
+    u32 n = v.a | (v.b << 16), d = v.c | (v.d << 16);
+    u32 q = d == 0 ? 0u : n / d, r = d == 0 ? 0u : n % d;
+    u32 x = part < 2 ? q : r;
+    return (part & 1u) ? x >> 16 : x & 0xffffu;
+}
 CM_HD QM31 qm_zero() { return qm_make(0, 0, 0, 0); }
 CM_HD QM31 qm_one() { return qm_make(1, 0, 0, 0); }
 CM_HD QM31 qm_from_m31(u32 v) { return qm_make(v, 0, 0, 0); }

@@ -53,6 +53,8 @@ enum AirOp : uint8_t {
     OP_LE,         // dst <- (F(a) <= F(b)) ? 1 : 0   (integer comparison of canonical representatives; witness only)
     OP_DIVC,       // dst <- F(a) / b   (integer division by the constant b; witness only)
     OP_MODC,       // dst <- F(a) % b
+    OP_U32DIVREM,  // dst <- 16-bit part b (0: q_lo, 1: q_hi, 2: r_lo, 3: r_hi) of the euclidean division of the u32
+                   //        (F(a) | F(a+1) << 16) by (F(a+2) | F(a+3) << 16); divisor 0 gives (0, 0)   (witness only)
 };
 inline uint64_t air_encode(AirOp op, u32 dst, u32 a, u32 b) {
     return (uint64_t)op | ((uint64_t)(dst & 0xffff) << 8) | ((uint64_t)(a & 0xfffff) << 24) | ((uint64_t)(b & 0xfffff) << 44);
@@ -84,7 +86,7 @@ inline uint64_t air_code_hash(const uint64_t* code, size_t n_instr) {
 }
 
 // ------------------------------------------------------------------ graph
-enum class NodeOp : uint8_t { Col, ConstF, ConstE, ParamE, AddF, SubF, MulF, NegF, AddE, SubE, MulE, NegE, MulEF, AddEF, SubEF, F2E, Combine4, InvE, InvF, ShrF, AndF, RowLt, LeF, DivCF, ModCF };
+enum class NodeOp : uint8_t { Col, ConstF, ConstE, ParamE, AddF, SubF, MulF, NegF, AddE, SubE, MulE, NegE, MulEF, AddEF, SubEF, F2E, Combine4, InvE, InvF, ShrF, AndF, RowLt, LeF, DivCF, ModCF, U32DivRemF };
 
 struct Node {
     NodeOp op;
@@ -187,7 +189,7 @@ class Graph {
     typedef std::tuple<int, int, int, int, int, u32, u32, u32, u32, int, int, int, int> Key;
     static Key key_of(const Node& n) {
         u32 w0 = (n.op == NodeOp::ConstF || n.op == NodeOp::ShrF || n.op == NodeOp::AndF || n.op == NodeOp::RowLt || n.op == NodeOp::DivCF ||
-                  n.op == NodeOp::ModCF)
+                  n.op == NodeOp::ModCF || n.op == NodeOp::U32DivRemF)
                      ? n.fconst
                      : n.econst.a;
         return Key((int)n.op, n.a, n.b, n.c, n.d, w0, n.econst.b, n.econst.c, n.econst.d, n.interaction, n.col, n.offset, n.param);
@@ -454,6 +456,19 @@ class ExprEvaluator : public LogupMixin<ExprEvaluator, FExpr, EFExpr> {
         n.fconst = c;
         return F{this, g.add(n)};
     }
+    // euclidean division of two u32s held as 16-bit limb pairs (u32_store_div_fp_fp.rs:360-400): part 0..3 =
+    // q_lo, q_hi, r_lo, r_hi
+    F f_u32_divrem(F n_lo, F n_hi, F d_lo, F d_hi, u32 part) {
+        Node pack{NodeOp::Combine4, true};
+        pack.a = n_lo.id;
+        pack.b = n_hi.id;
+        pack.c = d_lo.id;
+        pack.d = d_hi.id;
+        Node n{NodeOp::U32DivRemF, false};
+        n.a = g.add(pack);
+        n.fconst = part;
+        return F{this, g.add(n)};
+    }
     F row_lt(u32 bound) {
         Node n{NodeOp::RowLt, false};
         n.fconst = bound;
@@ -542,7 +557,7 @@ struct GraphPointEval {
             case NodeOp::F2E: r = eval(n.a); break;
             case NodeOp::InvE: r = qm_inv(eval(n.a)); break;
             case NodeOp::InvF: case NodeOp::ShrF: case NodeOp::AndF: case NodeOp::RowLt: case NodeOp::LeF: case NodeOp::DivCF:
-            case NodeOp::ModCF:
+            case NodeOp::ModCF: case NodeOp::U32DivRemF:
                 throw std::logic_error("GraphPointEval: witness-only op in a constraint graph");
             case NodeOp::Combine4:
                 // combine_ef of QM31 "base" values (point.rs: from_partial_evals)
@@ -774,6 +789,10 @@ class ProgramBuilder {
                 case NodeOp::LeF: emit(OP_LE, r, reg[nd.a], reg[nd.b]); fdef("(" + F(nd.a) + " <= " + F(nd.b) + " ? 1u : 0u)"); break;
                 case NodeOp::DivCF: emit(OP_DIVC, r, reg[nd.a], nd.fconst); fdef("(" + F(nd.a) + " / " + U(nd.fconst) + ")"); break;
                 case NodeOp::ModCF: emit(OP_MODC, r, reg[nd.a], nd.fconst); fdef("(" + F(nd.a) + " % " + U(nd.fconst) + ")"); break;
+                case NodeOp::U32DivRemF:
+                    emit(OP_U32DIVREM, r, reg[nd.a], nd.fconst);
+                    fdef("u32_divrem_part(" + E(nd.a) + ", " + U(nd.fconst) + ")");
+                    break;
                 case NodeOp::RowLt: {
                     u32 sl = (u32)prog.consts.size();
                     prog.consts.push_back(nd.fconst);

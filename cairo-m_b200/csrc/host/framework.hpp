@@ -127,6 +127,7 @@ struct TraceProgramBuilder {
     F f_le(F a, F b) { return ev.f_le(a, b); }
     F f_divc(F a, u32 c) { return ev.f_divc(a, c); }
     F f_modc(F a, u32 c) { return ev.f_modc(a, c); }
+    F f_u32_divrem(F n_lo, F n_hi, F d_lo, F d_hi, u32 part) { return ev.f_u32_divrem(n_lo, n_hi, d_lo, d_hi, part); }
     void out(int col, F v) { outs.push_back(ProgramOutput{ProgramOutput::StoreF, v.id, col}); }
     AirProgram compile(bool emit_cuda = false) {
         return ProgramBuilder::compile(ev.g, outs, 0, [](int interaction, int col) -> size_t {

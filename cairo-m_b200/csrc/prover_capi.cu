@@ -62,7 +62,7 @@ extern "C" {
 // Runs the (host) VM + adapter for fibonacci_loop(n): the prover input of crates/prover/src/adapter.
 int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out);
 int cm31_fib_input_create(uint32_t n, cm31_prover_input** out) { return cm31_program_input_create(PROGRAM_FIBONACCI_LOOP, n, out); }
-// program_id: 0 = fibonacci_loop(n), 1 = array_sum(n) (call / frame-pointer / double-deref / assert / le opcodes), 2 = u32_counter(n)
+// program_id: 0 = fibonacci_loop(n), 1 = array_sum(n) (call / frame-pointer / double-deref / assert / le opcodes), 2 = u32_counter(n), 3 = u32_mix(n) (u32 mul / divrem / eq / lt and the two-word *_fp_imm u32 instructions)
 int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out) {
     try {
         CM_REQUIRE(out != nullptr, "program_input_create: null out");

@@ -198,7 +198,7 @@ int cm31_histogram(const uint32_t* values, size_t n, uint32_t* bins, uint32_t lo
  * (host VM + adapter, the serial step BEFORE the hot path) is built in this round. */
 typedef struct cm31_prover_input cm31_prover_input;
 int cm31_fib_input_create(uint32_t n, cm31_prover_input** out);
-/* program_id 0 = fibonacci_loop(n); 1 = array_sum(n): call/ret, frame pointer, double-deref, assert, le; 2 = u32_counter(n): u32 limb ops */
+/* program_id 0 = fibonacci_loop(n); 1 = array_sum(n): call/ret, frame pointer, double-deref, assert, le; 2 = u32_counter(n): u32 limb ops; 3 = u32_mix(n): u32 mul/divrem/eq/lt + two-word *_fp_imm u32 instructions */
 int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out);
 int cm31_input_destroy(cm31_prover_input* h);
 /* test hook: corrupt the adapter output so a store_fp_fp constraint fails (kind 0: a written value, 1: an operand read) */

@@ -30,6 +30,13 @@ struct TraceRowEvaluator {
     F f_le(F a, F b) { return M31((u64)(a.v <= b.v ? 1 : 0)); }
     F f_divc(F a, u32 c) { return M31((u64)(a.v / c)); }
     F f_modc(F a, u32 c) { return M31((u64)(a.v % c)); }
+    // u32_store_div_fp_fp.rs:360-400: euclidean division on the limb pairs, (0, 0) for a zero divisor
+    F f_u32_divrem(F n_lo, F n_hi, F d_lo, F d_hi, u32 part) {
+        u32 n = n_lo.v | (n_hi.v << 16), d = d_lo.v | (d_hi.v << 16);
+        u32 q = d == 0 ? 0 : n / d, r = d == 0 ? 0 : n % d;
+        u32 x = part < 2 ? q : r;
+        return M31((u64)((part & 1) ? x >> 16 : x & 0xffff));
+    }
     void out(int col, F v) { (*outputs)[col][row] = v; }
 };
 

@@ -6,7 +6,7 @@ from tests import oracle_lib as orc
 CAP = 1 << 27
 
 
-FIB, ARRAY_SUM, U32_COUNTER = 0, 1, 2
+FIB, ARRAY_SUM, U32_COUNTER, U32_MIX = 0, 1, 2, 3
 
 
 def oracle_fib_prove(n, pow_bits=16, n_queries=80):
@@ -79,4 +79,21 @@ def u32_counter_expected(n):
         t = (x + y) & 0xFFFFFFFF
         x = (((t ^ y) & t) | y) & 0xFFFFFFFF
         y = (y - 1) & 0xFFFFFFFF
+    return x & 0xFFFF
+
+
+def u32_mix_expected(n):
+    """x.lo after n rounds of the u32_mix program (csrc/cairo/vm.hpp)."""
+    M = 0xFFFFFFFF
+    x, y = 0x56781234, 0xF1
+    for _ in range(n):
+        t = (x * y) & M
+        u = (t + 0x9E3779B9) & M
+        q, r = divmod(u, y)
+        v = (q * 0x10065) & M
+        w = v ^ 0x5A5AA5A5
+        a = w & 0x0FFFFFFF
+        b = a | 1
+        x = (b + r) & M
+        y = (y + 2) & M
     return x & 0xFFFF

@@ -111,6 +111,37 @@ def test_u32_counter_proof_bit_exact(cm, n):
     assert got == want
 
 
+@pytest.mark.parametrize("n", [1, 23, 700])
+def test_u32_mix_proof_bit_exact(cm, n):
+    # u32 mul / divrem / eq / lt and every two-word *_fp_imm u32 instruction (all 26 opcode components are in the proof)
+    inp = ch.GpuFibInput(cm, n, program=ch.U32_MIX)
+    try:
+        assert inp.return_value == ch.u32_mix_expected(n)
+        assert inp.steps == 18 * n + 8
+        got, _ = inp.prove()
+    finally:
+        inp.close()
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+    residual, _ = ch.oracle_logup_residual(n, got, program=ch.U32_MIX)
+    assert residual == (0, 0, 0, 0)
+    want, _ = ch.oracle_program_prove(ch.U32_MIX, n)
+    assert got == want
+
+
+def test_u32_mix_2_14_rounds_verifies(cm):
+    # ~2^18 VM steps of the u32-heavy program (BASELINE configs[2] stand-in): accepted by the oracle verifier
+    n = 1 << 14
+    inp = ch.GpuFibInput(cm, n, program=ch.U32_MIX)
+    try:
+        assert inp.return_value == ch.u32_mix_expected(n)
+        got, _ = inp.prove()
+    finally:
+        inp.close()
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+    residual, _ = ch.oracle_logup_residual(n, got, program=ch.U32_MIX)
+    assert residual == (0, 0, 0, 0)
+
+
 @pytest.mark.parametrize("kind", [0, 1])
 def test_invalid_trace_is_refused(cm, kind):
     # an execution trace that does not satisfy the AIR must not yield a proof: the composition OODS

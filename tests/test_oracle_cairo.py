@@ -63,3 +63,21 @@ def test_u32_counter_proof_verifies_and_balances():
     residual, info = ch.oracle_logup_residual(n, proof, program=ch.U32_COUNTER)
     assert residual == (0, 0, 0, 0)
     assert info["fib"] == ch.u32_counter_expected(n)
+
+
+# ---- u32_mix: U32StoreMul*, U32StoreDivRem*, U32StoreEqFpFp, U32StoreLtFpImm, U32StoreAddFpImm, U32Store{And,Or,Xor}FpImm
+# (two-word instructions: the second QM31 word is read at pc + 1, registers advance by 2)
+def test_u32_mix_proof_verifies_and_balances():
+    n = 9
+    proof = ch.oracle_program_prove(ch.U32_MIX, n)[0]
+    assert ch.oracle_cairo_verify(proof) == 0, ch.orc.last_error()
+    residual, info = ch.oracle_logup_residual(n, proof, program=ch.U32_MIX)
+    assert residual == (0, 0, 0, 0)
+    assert info["fib"] == ch.u32_mix_expected(n)
+    assert info["steps"] == 18 * n + 8
+
+
+def test_u32_mix_wrong_claim_breaks_logup():
+    proof = ch.oracle_program_prove(ch.U32_MIX, 4)[0]
+    residual, _ = ch.oracle_logup_residual(5, proof, program=ch.U32_MIX)  # public data of another run
+    assert residual != (0, 0, 0, 0)
