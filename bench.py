@@ -34,7 +34,10 @@ UNIT = "steps/s"
 
 
 def fib_iterations(log_steps: int) -> int:
-    return (1 << log_steps) // 8  # 8 VM steps per loop iteration + 8 for prologue/epilogue
+    # 8 VM steps per loop iteration + 8 for prologue/epilogue: n = 2^log/8 - 1 gives EXACTLY 2^log_steps VM steps
+    # (segment.trace.len() of the reference's bench, P/benches/prover_speed_benchmark.rs:49).  One more iteration
+    # would push every live opcode component one row past a power of two and double its padded size.
+    return (1 << log_steps) // 8 - 1
 
 
 def workload_name(log_steps: int) -> str:

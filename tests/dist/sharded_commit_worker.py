@@ -63,9 +63,18 @@ def main():
     m = 1 << (log_size + log_blowup)
     r0 = rank * (m // world)
     ok_rows = all(np.array_equal(rows[c].numpy().view(np.uint32), lde[c, r0:r0 + m // world]) for c in range(n_cols))
-    print(f"RESULT rank={rank} root_ok={ok} rows_ok={ok_rows}", flush=True)
+    line = f"RESULT rank={rank} root_ok={ok} rows_ok={ok_rows}"
     if world > 1:
+        # one writer: concurrent prints of several ranks can interleave inside a line on a shared pipe
+        lines = [None] * world
+        dist.all_gather_object(lines, line)
+        if rank == 0:
+            sys.stdout.write("\n".join(lines) + "\n")
+            sys.stdout.flush()
         dist.barrier()
+    else:
+        print(line, flush=True)
+    if world > 1:
         dist.destroy_process_group()
     sys.exit(0 if ok and ok_rows else 1)
 
