@@ -125,6 +125,13 @@ def blake2s_commit_layer(log_size: int, prev_layer, cols, out_layer) -> None:
                                           C.c_void_p(out_layer.data_ptr())))
 
 
+def blake2s_commit_multi(log_size: int, prev_layer, cols, out_layers) -> None:
+    """Layers log_size, log_size-1, .. (len(out_layers) of them, only the first with columns) in one launch."""
+    prev = C.c_void_p(prev_layer.data_ptr()) if prev_layer is not None else C.c_void_p()
+    check(lib().cm31_blake2s_commit_multi(C.c_uint32(log_size), prev, _ptr_array(cols), C.c_size_t(len(cols)),
+                                          C.c_uint32(len(out_layers)), _ptr_array(out_layers)))
+
+
 def fold_line(src4, log_size: int, alpha, tw: Twiddles, dst4) -> None:
     check(lib().cm31_fold_line(_ptr_array(src4), C.c_uint32(log_size), _qm(alpha), tw.handle, _ptr_array(dst4)))
 
@@ -195,6 +202,21 @@ def blake2s_commit_top(top_log: int, prev_layer, cols_by_layer, out_layers) -> N
     start.append(len(flat))
     prev = C.c_void_p(prev_layer.data_ptr()) if prev_layer is not None else C.c_void_p()
     check(lib().cm31_blake2s_commit_top(C.c_uint32(top_log), prev, _ptr_array(flat), _u32_array(start), _ptr_array(out_layers)))
+
+
+def gather_batch(srcs, src_id, word_idx, out_off, counts, grids, total_words):
+    """cm31_gather_batch: run requests (counts[k] words of srcs[src_id[k]] from word_idx[k] to out[out_off[k]:]) plus row-grid
+    requests `grids` = [(col_ids, rows, out_base)] (out[out_base + k*len(col_ids) + c] = srcs[col_ids[c]][rows[k]])."""
+    desc, gcols, grows = [], [], []
+    for col_ids, rows, base in grids:
+        desc += [len(gcols), len(col_ids), len(grows), len(rows), base]
+        gcols += list(col_ids)
+        grows += list(rows)
+    out = (C.c_uint32 * max(1, total_words))()
+    check(lib().cm31_gather_batch(_ptr_array(srcs), C.c_size_t(len(srcs)), _u32_array(src_id), _u32_array(word_idx), _u32_array(out_off),
+                                  _u32_array(counts), C.c_size_t(len(src_id)), _u32_array(desc), C.c_size_t(len(grids)), _u32_array(gcols),
+                                  C.c_size_t(len(gcols)), _u32_array(grows), C.c_size_t(len(grows)), C.c_size_t(total_words), out))
+    return list(out)[:total_words]
 
 
 def gather_runs(srcs, src_id, word_idx, counts):

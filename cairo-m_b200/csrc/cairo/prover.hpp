@@ -363,17 +363,20 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         typedef decltype(eval_tag) Eval;
         const auto& rows = staged.opcode.at(opcode_index++);
         u32 ls = padded_log_size(rows.n_real);
+        B::lane(ls);  // small components go to the side lane; every temporary below dies on the lane that used it
         std::vector<Col> inputs = Impl::unpack_bundles(rows.words, rows.n_real, staged.accesses, staged.n_accesses, ls);
         Eval eval;
         eval.log_size_ = ls;
         log_sizes.push_back(ls);
         traces.push_back(Impl::template write_trace<Eval>(eval, inputs, (u32)rows.n_real));
     };
+    B::prepare();
 #define CM31_X(E) opcode_trace(E{});
     CM31_OPCODE_EVALS(CM31_X)
 #undef CM31_X
     {
         u32 ls = padded_log_size(staged.memory.n_real);
+        B::lane(ls);
         std::vector<Col> inputs = Impl::unpack_rows(staged.memory.words, staged.memory.n_real, 8, ls);
         MemoryEval eval;
         eval.log_size_ = ls;
@@ -382,12 +385,14 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     }
     {
         u32 ls = padded_log_size(staged.clock_update.n_real);
+        B::lane(ls);
         std::vector<Col> inputs = Impl::unpack_rows(staged.clock_update.words, staged.clock_update.n_real, 6, ls);
         ClockUpdateEval eval;
         eval.log_size_ = ls;
         log_sizes.push_back(ls);
         traces.push_back(Impl::template write_trace<ClockUpdateEval>(eval, inputs, (u32)staged.clock_update.n_real));
     }
+    B::lanes_join();
     // range-check multiplicities: histogram of every value the opcode components look up
     // (opcodes/mod.rs:83-105 providers; range_check_macro.rs:72-84).  The AIR graphs drive it.
     RelationSet dummy_relations;
@@ -396,21 +401,31 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         std::vector<u32> ls_all = log_sizes;
         for (auto& tb : tables) ls_all.push_back(tb.second);
         CairoComponents<Impl> shape(ls_all, &dummy_relations);
-        for (auto& tb : tables) {
-            Col bins = B::zeros((size_t)1 << tb.second);
+        // all bins are zeroed on lane 0 before the first histogram kernel forks to the side lane; the histograms of
+        // different components only meet in atomicAdds
+        std::vector<Col> all_bins;
+        for (auto& tb : tables) all_bins.push_back(B::zeros((size_t)1 << tb.second));
+        for (size_t ti = 0; ti < tables.size(); ti++) {
+            auto& tb = tables[ti];
+            Col& bins = all_bins[ti];
             size_t ci = 0;
             auto emit = [&](auto& comp) {
                 if (ci < n_opcode_components()) {  // opcode components only
                     std::vector<const Col*> tc;
                     for (auto& e : traces[ci]) tc.push_back(&e.values);
+                    B::lane(log_sizes[ci]);
                     Impl::emit_lookups(comp, tb.first, tc, bins);
                 }
                 ci++;
             };
             shape.for_each(emit);
+        }
+        B::lanes_join();
+        for (size_t ti = 0; ti < tables.size(); ti++) {
+            auto& tb = tables[ti];
             log_sizes.push_back(tb.second);
             std::vector<CircleEvaluation<B>> t;
-            t.push_back(CircleEvaluation<B>{std::move(bins), tb.second});
+            t.push_back(CircleEvaluation<B>{std::move(all_bins[ti]), tb.second});
             traces.push_back(std::move(t));
         }
     }
@@ -447,10 +462,12 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         components.for_each([&](auto& comp) {
             std::vector<const Col*> tc;
             for (auto& e : traces[ci]) tc.push_back(&e.values);
+            B::lane(comp.log_size());
             auto cols = comp.gen_interaction_trace(tc, pre_lookup);
             for (auto& e : cols) interaction.push_back(std::move(e));
             ci++;
         });
+        B::lanes_join();
         Impl::collect_claimed_sums(components);
         components.for_each([&](auto& comp) { proof.interaction_claim.claimed_sums.push_back(comp.claimed_sum); });
         for (auto& s : proof.interaction_claim.claimed_sums) channel.mix_felts({s});  // InteractionClaim::mix_into

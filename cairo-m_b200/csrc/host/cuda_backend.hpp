@@ -90,6 +90,10 @@ struct CudaBackend {
     typedef DeviceCol HashCol;  // 8 words per node
     typedef CudaTwiddles Twiddles;
 
+    // components / size groups of at most 2^LANE_SPLIT_LOG rows are issued on the side lane (cm31_lane)
+    static constexpr u32 LANE_SPLIT_LOG = 12;
+    static void lane(u32 log_size) { cm_check(cm31_lane(log_size <= LANE_SPLIT_LOG ? 1 : 0)); }
+    static void lanes_join() { cm_check(cm31_lanes_join()); }
     static size_t len(const Col& c) { return c.size(); }
     static Col zeros(size_t n) {
         Col c(n);
@@ -150,6 +154,18 @@ struct CudaBackend {
         cm_check(cm31_blake2s_commit_layer(log_size, prev ? prev->ptr() : nullptr, s.data(), s.size(), out.ptr()));
         return out;
     }
+    // layers log_size .. log_size-n_levels+1 (only the first with columns) in one launch; returns them in that order
+    static std::vector<HashCol> commit_layers_fused(u32 log_size, const HashCol* prev, const std::vector<const Col*>& cols, u32 n_levels) {
+        std::vector<HashCol> out;
+        std::vector<u32*> outp;
+        for (u32 l = 0; l < n_levels; l++) {
+            out.emplace_back(((size_t)1 << (log_size - l)) * 8);
+            outp.push_back(out.back().ptr());
+        }
+        auto s = cptrs(cols);
+        cm_check(cm31_blake2s_commit_multi(log_size, prev ? prev->ptr() : nullptr, s.data(), s.size(), n_levels, outp.data()));
+        return out;
+    }
     static void gather(const std::vector<const Col*>& cols, const std::vector<u32>& idx, std::vector<std::vector<u32>>& out) {
         auto s = cptrs(cols);
         std::vector<u32> flat(cols.size() * idx.size());
@@ -176,8 +192,11 @@ struct CudaBackend {
     static const u32* col_words(const Col& c) { return c.ptr(); }
     static const u32* hash_words(const HashCol& c) { return c.ptr(); }
     static void gather_runs(const std::vector<const u32*>& srcs, const std::vector<u32>& src_id, const std::vector<u32>& word,
-                            const std::vector<u32>& out_off, std::vector<u32>& out) {
-        cm_check(cm31_gather_runs(srcs.data(), srcs.size(), src_id.data(), word.data(), out_off.data(), src_id.size(), out.data()));
+                            const std::vector<u32>& out_off, const std::vector<u32>& cnt, const std::vector<u32>& grid_desc,
+                            const std::vector<u32>& grid_cols, const std::vector<u32>& grid_rows, std::vector<u32>& out) {
+        cm_check(cm31_gather_batch(srcs.data(), srcs.size(), src_id.data(), word.data(), out_off.data(), cnt.data(), src_id.size(), grid_desc.data(),
+                                   grid_desc.size() / 5, grid_cols.data(), grid_cols.size(), grid_rows.data(), grid_rows.size(), out.size(),
+                                   out.data()));
     }
     static Hash32 read_root(const HashCol& root_layer) {
         Hash32 h;
@@ -277,6 +296,10 @@ struct CudaBackend {
     static SumArena& sums() {
         static SumArena a;
         return a;
+    }
+    static void prepare() {  // persistent buffers are created on lane 0, before any fork
+        SumArena& a = sums();
+        if (a.buf.size() == 0) a.buf = DeviceCol(4 * 256);
     }
     static size_t logup_finalize_last_async(const std::array<Col*, 4>& last, u32 log_size) {
         SumArena& a = sums();

@@ -11,12 +11,18 @@
 // CpuBackend) — the order of channel mixes/draws below is part of the proof contract
 // (SURVEY.md Appendix A).
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <array>
+#include <functional>
 #include <map>
 #include <memory>
 #include <numeric>
 #include <set>
+#include <unordered_map>
+#include <cstring>
 #include <stdexcept>
 #include <vector>
 
@@ -24,6 +30,35 @@
 #include "qm_ops.hpp"
 
 namespace cm31 {
+
+// Host-side section timers (CM31_HOST_TIMING=1): where the host thread spends time between launches.
+struct HostTimer {
+    static bool enabled() {
+        static const bool on = getenv("CM31_HOST_TIMING") != nullptr;
+        return on;
+    }
+    static std::map<std::string, std::pair<double, size_t>>& table() {
+        static std::map<std::string, std::pair<double, size_t>> t;
+        return t;
+    }
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    explicit HostTimer(const char* n) : name(n) {
+        if (enabled()) t0 = std::chrono::steady_clock::now();
+    }
+    ~HostTimer() {
+        if (!enabled()) return;
+        auto& e = table()[name];
+        e.first += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        e.second++;
+    }
+    static void report() {
+        if (!enabled()) return;
+        for (auto& kv : table()) fprintf(stderr, "[host] %-28s %9.3f ms  x%zu\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        table().clear();
+    }
+};
+
 
 struct FriConfig {
     u32 log_blowup_factor = 1;
@@ -88,9 +123,14 @@ struct ConstraintsNotSatisfied : std::runtime_error {
 class ProofWriter {
    public:
     std::vector<uint8_t> bytes;
-    void u32v(u32 v) {
-        for (int i = 0; i < 4; i++) bytes.push_back((uint8_t)(v >> (8 * i)));
+    ProofWriter() { bytes.reserve((size_t)4 << 20); }
+    // little-endian words; the host is little-endian (x86-64 / aarch64), so a word run is one memcpy
+    void u32s(const u32* v, size_t n) {
+        size_t at = bytes.size();
+        bytes.resize(at + 4 * n);
+        if (n) memcpy(bytes.data() + at, v, 4 * n);
     }
+    void u32v(u32 v) { u32s(&v, 1); }
     void u64v(u64 v) {
         u32v((u32)v);
         u32v((u32)(v >> 32));
@@ -106,7 +146,7 @@ class ProofWriter {
         u64v(d.hash_witness.size());
         for (auto& h : d.hash_witness) hash(h);
         u64v(d.column_witness.size());
-        for (u32 v : d.column_witness) u32v(v);
+        u32s(d.column_witness.data(), d.column_witness.size());
     }
     void fri_layer(const FriLayerProof& l) {
         u64v(l.fri_witness.size());
@@ -134,7 +174,7 @@ class ProofWriter {
         u64v(p.queried_values.size());
         for (auto& q : p.queried_values) {
             u64v(q.size());
-            for (u32 v : q) u32v(v);
+            u32s(q.data(), q.size());
         }
         u64v(p.proof_of_work);
         fri_layer(p.fri_proof.first_layer);
@@ -242,8 +282,8 @@ template <class B>
 struct GatherQueue {
     // a request = `count` consecutive words (1 for a column element, 8 for a hash node) of one source
     std::vector<const u32*> srcs;
-    std::map<const u32*, u32> src_index;
-    std::vector<u32> src_id, word, out_off;  // per request; results of request k start at out_off[k]
+    std::unordered_map<const u32*, u32> src_index;
+    std::vector<u32> src_id, word, out_off, cnt;  // per run request: cnt[k] words land at results[out_off[k]..]
     std::vector<u32> results;
     size_t n_words = 0;
     u32 source(const u32* base) {
@@ -258,16 +298,29 @@ struct GatherQueue {
         src_id.push_back(source_id);
         word.push_back((u32)first_word);
         out_off.push_back((u32)n_words);
+        cnt.push_back(count);
         size_t slot = n_words;
         n_words += count;
         return slot;
     }
     size_t request(u32 source_id, size_t word_idx) { return request_run(source_id, word_idx, 1); }
     size_t request_hash(u32 source_id, size_t node) { return request_run(source_id, node * 8, 8); }
+    // A Merkle layer's decommitment reads the same rows of ALL its columns: one descriptor
+    // (col_off, n_cols, row_off, n_rows, out_base) instead of n_cols * n_rows single-word requests.
+    // Results are row-major: the word of column c at rows[k] lands in slot base + k * n_cols + c.
+    std::vector<u32> grid_desc, grid_cols, grid_rows;
+    size_t request_rows(const std::vector<u32>& col_ids, const std::vector<size_t>& rows) {
+        size_t base = n_words;
+        if (col_ids.empty() || rows.empty()) return base;
+        for (u32 v : {(u32)grid_cols.size(), (u32)col_ids.size(), (u32)grid_rows.size(), (u32)rows.size(), (u32)base}) grid_desc.push_back(v);
+        grid_cols.insert(grid_cols.end(), col_ids.begin(), col_ids.end());
+        for (size_t r : rows) grid_rows.push_back((u32)r);
+        n_words += col_ids.size() * rows.size();
+        return base;
+    }
     void flush() {
         results.resize(n_words);
-        out_off.push_back((u32)n_words);
-        if (n_words) B::gather_runs(srcs, src_id, word, out_off, results);
+        if (n_words) B::gather_runs(srcs, src_id, word, out_off, cnt, grid_desc, grid_cols, grid_rows, results);
     }
     Hash32 hash_at(size_t slot) const {
         Hash32 h;
@@ -296,11 +349,21 @@ struct MerkleProver {
         std::vector<HashCol> layers;
         constexpr int TOP_LOG = 10;  // layers of <= 2^10 nodes are hashed by one fused launch
         int log_size = (int)max_log;
-        for (; log_size > TOP_LOG; log_size--) {
+        while (log_size > TOP_LOG) {
             std::vector<const Col*> layer_cols;
             while (pos < sorted.size() && ilog2(B::len(*sorted[pos])) == (u32)log_size) layer_cols.push_back(sorted[pos++]);
+            // the layers below that receive no columns are hashed by the same launch (<= 9 levels: 256 nodes -> 1 per CTA)
+            int next_with_cols = pos < sorted.size() ? (int)ilog2(B::len(*sorted[pos])) : -1;
+            int n_levels = 1;
+            while (log_size - n_levels > TOP_LOG && log_size - n_levels > next_with_cols && n_levels < 9) n_levels++;
             const HashCol* prev = layers.empty() ? nullptr : &layers.back();
-            layers.push_back(B::commit_on_layer((u32)log_size, prev, layer_cols));
+            if (n_levels == 1) {
+                layers.push_back(B::commit_on_layer((u32)log_size, prev, layer_cols));
+            } else {
+                std::vector<HashCol> fused = B::commit_layers_fused((u32)log_size, prev, layer_cols, (u32)n_levels);
+                for (auto& l : fused) layers.push_back(std::move(l));
+            }
+            log_size -= n_levels;
         }
         {
             std::vector<std::vector<const Col*>> by_layer(log_size + 1);
@@ -322,12 +385,14 @@ struct MerkleProver {
     // vcs/prover.rs:82-156 in two phases: `plan` walks the layers exactly like the reference and
     // records every read in the gather queue; `finish` (after queue.flush()) assembles the values.
     struct PendingDecommit {
-        std::vector<size_t> queried_slots, column_witness_slots, hash_witness_slots;
+        std::vector<std::pair<size_t, size_t>> queried_runs, column_witness_runs;  // (first slot, count)
+        std::vector<size_t> hash_witness_slots;
         std::pair<std::vector<u32>, MerkleDecommitment> finish(const GatherQueue<B>& q) const {
             std::vector<u32> queried_values;
             MerkleDecommitment d;
-            for (size_t s : queried_slots) queried_values.push_back(q.results[s]);
-            for (size_t s : column_witness_slots) d.column_witness.push_back(q.results[s]);
+            for (auto& r : queried_runs) queried_values.insert(queried_values.end(), q.results.begin() + r.first, q.results.begin() + r.first + r.second);
+            for (auto& r : column_witness_runs)
+                d.column_witness.insert(d.column_witness.end(), q.results.begin() + r.first, q.results.begin() + r.first + r.second);
             for (size_t s : hash_witness_slots) d.hash_witness.push_back(q.hash_at(s));
             return {queried_values, d};
         }
@@ -348,6 +413,7 @@ struct MerkleProver {
             const std::vector<size_t>& layer_column_queries = qit == queries_per_log_size.end() ? empty : qit->second;
             size_t pi = 0, ci = 0;
             std::vector<size_t> layer_total_queries;
+            std::vector<char> node_is_queried;
             std::vector<u32> col_ids;
             for (const Col* c : layer_columns) col_ids.push_back(queue.source(B::col_words(*c)));
             const u32 prev_id = previous_layer_hashes ? queue.source(B::hash_words(*previous_layer_hashes)) : 0;
@@ -365,9 +431,13 @@ struct MerkleProver {
                 }
                 bool queried = ci < layer_column_queries.size() && layer_column_queries[ci] == node_index;
                 if (queried) ci++;
-                std::vector<size_t>& dst = queried ? pd.queried_slots : pd.column_witness_slots;
-                for (u32 id : col_ids) dst.push_back(queue.request(id, node_index));
+                node_is_queried.push_back(queried);
                 layer_total_queries.push_back(node_index);
+            }
+            if (!col_ids.empty()) {  // every column of the layer at every visited node: one row-grid request
+                size_t base = queue.request_rows(col_ids, layer_total_queries);
+                for (size_t k = 0; k < layer_total_queries.size(); k++)
+                    (node_is_queried[k] ? pd.queried_runs : pd.column_witness_runs).push_back({base + k * col_ids.size(), col_ids.size()});
             }
             last_layer_queries = layer_total_queries;
         }
@@ -438,6 +508,7 @@ struct CommitmentTreeProver {
         for (size_t i = 0; i < t.polynomials.size(); i++) by_size[t.polynomials[i].log_size].push_back(i);
         for (auto& kv : by_size) {
             u32 log_size = kv.first, log_eval = log_size + log_blowup_factor;
+            B::lane(log_size);  // size groups are independent until the Merkle tree reads them all
             std::vector<const typename B::Col*> src;
             std::vector<typename B::Col*> dst;
             std::vector<typename B::Col> slab = B::uninit_many(kv.second.size(), (size_t)1 << log_eval);
@@ -450,6 +521,7 @@ struct CommitmentTreeProver {
             }
             B::evaluate_polynomials(src, dst, log_size, log_eval, twiddles);
         }
+        B::lanes_join();
         std::vector<const typename B::Col*> cols;
         for (auto& e : t.evaluations) cols.push_back(&e.values);
         t.commitment = MerkleProver<B>::commit(cols);
@@ -483,7 +555,11 @@ struct CommitmentSchemeProver {
     void commit_evals(std::vector<CircleEvaluation<B>> columns, Blake2sChannel& channel) {
         std::map<u32, std::vector<typename B::Col*>> by_size;
         for (auto& c : columns) by_size[c.log_size].push_back(&c.values);
-        for (auto& kv : by_size) B::interpolate_columns(kv.second, kv.first, *twiddles);
+        for (auto& kv : by_size) {
+            B::lane(kv.first);
+            B::interpolate_columns(kv.second, kv.first, *twiddles);
+        }
+        B::lane(0xffffffffu);  // back to lane 0 (no join: each size stays on its lane through the LDE)
         std::vector<CirclePoly<B>> polys;
         for (auto& c : columns) polys.push_back(CirclePoly<B>{std::move(c.values), c.log_size});
         commit_polys(std::move(polys), channel);
@@ -504,7 +580,11 @@ struct CommitmentSchemeProver {
                 by_size[kv.first].second.push_back(&polys[i].coeffs);
             }
         }
-        for (auto& kv : by_size) B::interpolate_columns_to(kv.second.first, kv.second.second, kv.first, *twiddles);
+        for (auto& kv : by_size) {
+            B::lane(kv.first);
+            B::interpolate_columns_to(kv.second.first, kv.second.second, kv.first, *twiddles);
+        }
+        B::lane(0xffffffffu);
         commit_polys(std::move(polys), channel);
     }
     void commit_polys(std::vector<CirclePoly<B>> polys, Blake2sChannel& channel) {
@@ -517,7 +597,11 @@ struct CommitmentSchemeProver {
     }
 
     // prove_values (pcs/prover.rs:83-153)
-    CommitmentSchemeProof prove_values(const std::vector<std::vector<std::vector<SecurePoint>>>& sampled_points, Blake2sChannel& channel);
+    // `after_sampling` (optional) runs on the host once the sampled values are known and the DEEP quotient kernels are
+    // enqueued: prove() puts its OODS sanity check there so it overlaps device work instead of trailing the proof.
+    typedef std::function<void(const std::vector<std::vector<std::vector<QM31>>>&)> SampledHook;
+    CommitmentSchemeProof prove_values(const std::vector<std::vector<std::vector<SecurePoint>>>& sampled_points, Blake2sChannel& channel,
+                                       const SampledHook& after_sampling = SampledHook());
 };
 
 // ------------------------------------------------------------------ FRI (core/fri.rs)
@@ -750,6 +834,7 @@ std::vector<SecureEvaluation<B>> compute_fri_quotients(const std::vector<const C
     size_t i = 0;
     while (i < order.size()) {
         u32 log_size = columns[order[i]]->log_size;
+        B::lane(log_size > log_blowup_factor ? log_size - log_blowup_factor : 0);  // lane of the trace size this LDE belongs to
         std::vector<const typename B::Col*> cols;
         std::vector<const std::vector<PointSample>*> smp;
         while (i < order.size() && columns[order[i]]->log_size == log_size) {
@@ -763,13 +848,15 @@ std::vector<SecureEvaluation<B>> compute_fri_quotients(const std::vector<const C
         ev.columns = B::accumulate_quotients(log_size, cols, random_coeff, batches, log_blowup_factor);
         out.push_back(std::move(ev));
     }
+    B::lanes_join();
     return out;
 }
 
 template <class B>
 CommitmentSchemeProof CommitmentSchemeProver<B>::prove_values(const std::vector<std::vector<std::vector<SecurePoint>>>& sampled_points,
-                                                              Blake2sChannel& channel) {
+                                                              Blake2sChannel& channel, const SampledHook& after_sampling) {
     // Evaluate polynomials on open points: one batched eval_at_point over every (column, point).
+    std::unique_ptr<HostTimer> ht(new HostTimer("pv_prep"));
     std::vector<const typename B::Col*> polys;
     std::vector<u32> log_sizes, point_idx;
     std::vector<SecurePoint> points;
@@ -788,7 +875,9 @@ CommitmentSchemeProof CommitmentSchemeProver<B>::prove_values(const std::vector<
         }
     }
     std::vector<QM31> values;
+    ht.reset(new HostTimer("pv_eval_at_points"));
     B::eval_at_points(polys, log_sizes, points, point_idx, values);
+    ht.reset(new HostTimer("pv_assemble"));
     CommitmentSchemeProof proof;
     proof.config = config;
     std::vector<std::vector<PointSample>> samples_flat;
@@ -815,21 +904,33 @@ CommitmentSchemeProof CommitmentSchemeProver<B>::prove_values(const std::vector<
     for (auto& t : trees)
         for (auto& e : t.evaluations) columns.push_back(&e);
     QM31 random_coeff = channel.draw_secure_felt();
+    ht.reset(new HostTimer("pv_quotients"));
     std::vector<SecureEvaluation<B>> quotients = compute_fri_quotients<B>(columns, samples_flat, random_coeff, config.fri_config.log_blowup_factor);
 
+    if (after_sampling) {
+        ht.reset(new HostTimer("pv_after_sampling_hook"));
+        after_sampling(proof.sampled_values);
+    }
+    ht.reset(new HostTimer("pv_fri_commit"));
     FriProver<B> fri_prover = FriProver<B>::commit(channel, config.fri_config, quotients, *twiddles);
 
+    ht.reset(new HostTimer("pv_grind"));
     proof.proof_of_work = B::grind(channel.digest(), config.pow_bits);
     channel.mix_u64(proof.proof_of_work);
+    ht.reset(new HostTimer("pv_decommit_plan"));
 
     // FRI + the 4 trees decommit through one batched device gather
     GatherQueue<B> queue;
     auto fri_res = fri_prover.plan_decommit(channel, queue);
     const std::map<u32, std::vector<size_t>>& query_positions_per_log_size = fri_res.second;
     std::vector<typename MerkleProver<B>::PendingDecommit> pending;
+    ht.reset(new HostTimer("pv_decommit_plan_trees"));
     for (auto& t : trees) pending.push_back(t.plan_decommit(queue, query_positions_per_log_size));
+    ht.reset(new HostTimer("pv_decommit_flush"));
     queue.flush();
+    ht.reset(new HostTimer("pv_decommit_finish"));
     proof.fri_proof = fri_res.first.finish(queue);
+    ht.reset(new HostTimer("pv_decommit_finish_trees"));
     for (auto& pd : pending) {
         auto res = pd.finish(queue);
         proof.queried_values.push_back(std::move(res.first));
@@ -954,7 +1055,12 @@ struct ComponentProvers {  // air/components.rs
         size_t total = 0;
         for (auto* c : components) total += c->n_constraints();
         DomainEvaluationAccumulator<B> acc(random_coeff, composition_log_degree_bound(), total);
-        for (auto* c : components) c->evaluate_constraint_quotients_on_domain(trace, acc);
+        // accumulators are per evaluation size and a component's lane is a function of its size: no two lanes share one
+        for (auto* c : components) {
+            B::lane(c->max_constraint_log_degree_bound() - 1);
+            c->evaluate_constraint_quotients_on_domain(trace, acc);
+        }
+        B::lanes_join();
         return acc.finalize(tw);
     }
     static size_t PREPROCESSED_TRACE_IDX_() { return 0; }
@@ -966,26 +1072,32 @@ StarkProof prove(const std::vector<const ComponentProver<B>*>& components, Blake
     ComponentProvers<B> provers{components, commitment_scheme.trees[0].polynomials.size()};
     Trace<B> trace{&commitment_scheme.trees};
     QM31 random_coeff = channel.draw_secure_felt();
+    std::unique_ptr<HostTimer> ht0(new HostTimer("composition"));
     std::array<CirclePoly<B>, 4> composition = provers.compute_composition_polynomial(random_coeff, trace, *commitment_scheme.twiddles);
+    ht0.reset(new HostTimer("composition_commit"));
     std::vector<CirclePoly<B>> comp_polys;
     for (auto& p : composition) comp_polys.push_back(std::move(p));
     commitment_scheme.commit_polys(std::move(comp_polys), channel);
+    ht0.reset();
 
     SecurePoint oods_point = get_random_point(channel);
+    std::unique_ptr<HostTimer> ht(new HostTimer("mask_points"));
     MaskPoints sample_points = provers.mask_points(oods_point);
     // a component set without interaction columns commits fewer trees (TreeVec is sized by use)
     size_t n_trace_trees = commitment_scheme.trees.size() - 1;
     while (sample_points.size() > n_trace_trees && sample_points.back().empty()) sample_points.pop_back();
     sample_points.push_back(std::vector<std::vector<SecurePoint>>(4, std::vector<SecurePoint>{oods_point}));
 
-    StarkProof proof = commitment_scheme.prove_values(sample_points, channel);
-
-    // sanity check (prover/mod.rs:76-82)
-    const auto& comp_mask = proof.sampled_values.back();
-    QM31 composition_oods_eval = qm_from_partial_evals(comp_mask[0][0], comp_mask[1][0], comp_mask[2][0], comp_mask[3][0]);
-    if (composition_oods_eval != provers.eval_composition_polynomial_at_point(oods_point, proof.sampled_values, random_coeff))
-        throw ConstraintsNotSatisfied();
-    return proof;
+    ht.reset();
+    // sanity check (prover/mod.rs:76-82): evaluated as soon as the sampled values exist (same inputs, same outcome as
+    // after prove_values; the reference only returns Err(ConstraintsNotSatisfied) later)
+    auto sanity_check = [&](const std::vector<std::vector<std::vector<QM31>>>& sampled_values) {
+        const auto& comp_mask = sampled_values.back();
+        QM31 composition_oods_eval = qm_from_partial_evals(comp_mask[0][0], comp_mask[1][0], comp_mask[2][0], comp_mask[3][0]);
+        if (composition_oods_eval != provers.eval_composition_polynomial_at_point(oods_point, sampled_values, random_coeff))
+            throw ConstraintsNotSatisfied();
+    };
+    return commitment_scheme.prove_values(sample_points, channel, sanity_check);
 }
 
 }  // namespace cm31

@@ -12,8 +12,10 @@
 
 namespace cm31 {
 
-__device__ __forceinline__ void hash_node(size_t i, const u32* __restrict__ prev, const u32* const* __restrict__ cols, u32 n_cols,
-                                          u32* __restrict__ out) {
+// PREV_IN_FLIGHT: `prev` was written earlier in the SAME launch by other threads of this CTA (fused layers): its loads
+// must stay coherent (ld.global.cg), never the read-only path.
+template <bool PREV_IN_FLIGHT = false>
+__device__ __forceinline__ void hash_node(size_t i, const u32* prev, const u32* const* __restrict__ cols, u32 n_cols, u32* out) {
     Blake2sState st;
     blake2s_init(st);
     u32 m[16];
@@ -21,7 +23,18 @@ __device__ __forceinline__ void hash_node(size_t i, const u32* __restrict__ prev
     u64 done = 0;
     if (prev) {
         const uint4* p4 = reinterpret_cast<const uint4*>(prev + i * 16);
-        uint4 a = p4[0], b = p4[1], c = p4[2], d = p4[3];
+        uint4 a, b, c, d;
+        if (PREV_IN_FLIGHT) {
+            a = __ldcg(p4);
+            b = __ldcg(p4 + 1);
+            c = __ldcg(p4 + 2);
+            d = __ldcg(p4 + 3);
+        } else {
+            a = p4[0];
+            b = p4[1];
+            c = p4[2];
+            d = p4[3];
+        }
         m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
         m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
         m[8] = c.x; m[9] = c.y; m[10] = c.z; m[11] = c.w;
@@ -59,9 +72,29 @@ struct MerkleTopArgs {
 };
 __global__ void __launch_bounds__(1024) merkle_top_kernel(u32 top_log, const u32* prev, const u32* const* cols, MerkleTopArgs args) {
     for (int l = (int)top_log; l >= 0; l--) {
-        if (threadIdx.x < (1u << l)) hash_node(threadIdx.x, prev, cols + args.col_start[l], args.col_start[l + 1] - args.col_start[l], args.layer_out[l]);
+        if (threadIdx.x < (1u << l)) {
+            if (l == (int)top_log) hash_node<false>(threadIdx.x, prev, cols + args.col_start[l], args.col_start[l + 1] - args.col_start[l], args.layer_out[l]);
+            else hash_node<true>(threadIdx.x, prev, cols + args.col_start[l], args.col_start[l + 1] - args.col_start[l], args.layer_out[l]);
+        }
         prev = args.layer_out[l];
         __syncthreads();  // block-scope visibility of the layer just written
+    }
+}
+
+// Layers log_size, log_size-1, .., log_size-n_levels+1 in ONE launch, when only the first of them carries columns (FRI
+// layer trees, the composition tree, the gaps between column sizes of a trace tree): a CTA hashes 256 nodes of the
+// first layer and keeps halving inside the block, so a tree costs a few launches instead of one per layer.
+struct MerkleMultiArgs {
+    u32* layer_out[9];
+};
+__global__ void __launch_bounds__(256) merkle_multi_kernel(u32 log_size, const u32* prev, const u32* const* cols, u32 n_cols, u32 n_levels,
+                                                           MerkleMultiArgs args) {
+    const size_t i = blockIdx.x * (size_t)256 + threadIdx.x;
+    if (i < ((size_t)1 << log_size)) hash_node<false>(i, prev, cols, n_cols, args.layer_out[0]);
+    for (u32 lvl = 1; lvl < n_levels; lvl++) {
+        __syncthreads();  // the children written by this CTA are visible to it
+        const u32 cnt = 256u >> lvl;
+        if (threadIdx.x < cnt) hash_node<true>(blockIdx.x * (size_t)cnt + threadIdx.x, args.layer_out[lvl - 1], nullptr, 0, args.layer_out[lvl]);
     }
 }
 
@@ -106,6 +139,24 @@ int cm31_blake2s_commit_layer(uint32_t log_size, const uint32_t* prev_layer, con
     ProfScope prof(n_cols ? "merkle_leaf_layer" : "merkle_inner_layer", (4ull * n_cols + 32ull + (prev_layer ? 64ull : 0ull)) * n);
     merkle_layer_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream()>>>(
         log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, out_layer);
+    CM_LAUNCH_CHECK();
+    return 0;
+}
+
+int cm31_blake2s_commit_multi(uint32_t log_size, const uint32_t* prev_layer, const uint32_t* const* cols, size_t n_cols,
+                              uint32_t n_levels, uint32_t* const* out_layers) {
+    CM_REQUIRE(out_layers != nullptr && n_levels >= 1 && n_levels <= 9, "commit_multi: 1..9 levels");
+    CM_REQUIRE(log_size <= 30 && log_size >= 8 && log_size + 1 >= n_levels, "commit_multi: first layer needs at least 256 nodes");
+    MerkleMultiArgs args;
+    for (u32 l = 0; l < 9; l++) args.layer_out[l] = l < n_levels ? out_layers[l] : nullptr;
+    DeviceTable dcols;
+    if (n_cols != 0)
+        if (int e = dcols.upload(cols, n_cols * sizeof(void*))) return e;
+    size_t n = (size_t)1 << log_size;
+    uint64_t bytes = (4ull * n_cols + 32ull + (prev_layer ? 64ull : 0ull)) * n;
+    for (u32 l = 1; l < n_levels; l++) bytes += 96ull * (n >> l);
+    ProfScope prof(n_cols ? "merkle_leaf_layer" : "merkle_inner_layer", bytes);
+    merkle_multi_kernel<<<(unsigned)(n / 256), 256, 0, stream()>>>(log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, n_levels, args);
     CM_LAUNCH_CHECK();
     return 0;
 }

@@ -147,8 +147,15 @@ int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n
             timings_ms[3] = t.stark_ms;
             timings_ms[4] = t.total_ms;
         }
-        return write_out(proof.to_bytes(), proof_out, proof_cap, proof_len);
+        int rc;
+        {
+            HostTimer ht("proof_to_bytes");
+            rc = write_out(proof.to_bytes(), proof_out, proof_cap, proof_len);
+        }
+        HostTimer::report();
+        return rc;
     } catch (const std::exception& e) {
+        cm31_lanes_join();  // an error may have been raised while the side lane was current
         set_error(e.what());
         return -2;
     }

@@ -9,7 +9,15 @@
 namespace cm31 {
 
 static thread_local std::string g_err;
-static cudaStream_t g_stream = 0;
+static cudaStream_t g_stream = 0;  // the stream every cm31_* call issues on (= the current lane)
+// Lanes: the proof's own work lives on the caller's stream (lane 0); groups that are independent of
+// each other until the next join -- the per-component witness / logup / constraint programs and the
+// per-size FFT and quotient batches of SMALL components -- may be issued on a side stream (lane 1),
+// so their latency-bound launches overlap the large components' kernels.
+static cudaStream_t g_main = 0, g_side = nullptr;
+static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+static bool g_forked = false;
+static int g_lanes_on = -1;
 static bool g_pool_ready[64] = {false};
 
 void set_error(const std::string& msg) { g_err = msg; }
@@ -86,8 +94,9 @@ int DeviceTable::upload(const void* host, size_t bytes) {
     }
     size_t need = (bytes + 255) & ~(size_t)255;
     if (g_stage_pos + need > STAGE_BYTES) {
-        // wrap: every table issued so far must be consumed (kernels done) before its slot is reused
-        CM_CUDA(cudaStreamSynchronize(stream()));
+        // wrap: every table issued so far (on either lane) must be consumed before its slot is reused
+        CM_CUDA(cudaStreamSynchronize(g_main));
+        if (g_side) CM_CUDA(cudaStreamSynchronize(g_side));
         g_stage_pos = 0;
     }
     if (host) memcpy(g_stage + g_stage_pos, host, bytes);
@@ -120,6 +129,23 @@ __global__ void gather_runs_kernel(const u32* const* srcs, const u32* src_id, co
     u32 o = out_off[t], cnt = out_off[t + 1] - o;
     for (u32 j = 0; j < cnt; j++) out[o + j] = s[j];
 }
+__global__ void gather_runs2_kernel(const u32* const* srcs, const u32* src_id, const u32* word, const u32* out_off, const u32* cnt, size_t n,
+                                    u32* out) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const u32* s = srcs[src_id[t]] + word[t];
+    u32 o = out_off[t], c = cnt[t];
+    for (u32 j = 0; j < c; j++) out[o + j] = s[j];
+}
+// one CTA row (blockIdx.y) per grid request; thread t -> (row k = t / n_cols, column c = t % n_cols)
+__global__ void gather_grid_kernel(const u32* const* srcs, const u32* desc, const u32* cols, const u32* rows, u32* out) {
+    const u32* d = desc + 5 * blockIdx.y;
+    const u32 col_off = d[0], n_cols = d[1], row_off = d[2], n_rows = d[3], base = d[4];
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < (size_t)n_cols * n_rows; t += (size_t)gridDim.x * blockDim.x) {
+        u32 k = (u32)(t / n_cols), c = (u32)(t % n_cols);
+        out[base + t] = __ldg(srcs[cols[col_off + c]] + rows[row_off + k]);
+    }
+}
 __global__ void gather_hash_kernel(const u32* layer, const u32* idx, size_t n_idx, u32* out) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t >= n_idx * 8) return;
@@ -143,7 +169,45 @@ int cm31_set_device(int ordinal) {
     return 0;
 }
 int cm31_set_stream(void* s) {
-    g_stream = (cudaStream_t)s;
+    g_main = (cudaStream_t)s;
+    g_stream = g_main;
+    return 0;
+}
+// lane 1: the side stream, ordered after everything issued on lane 0 up to the FIRST switch since the
+// last join (fork); lane 0: the caller's stream.  Work issued on one lane between a fork and the next
+// cm31_lanes_join() must not depend on work issued on the other lane in that window, and buffers
+// must be freed on the lane that last used them (or after the join).  CM31_NO_LANES=1 keeps
+// everything on lane 0.
+int cm31_lane(int lane) {
+    if (g_lanes_on < 0) g_lanes_on = getenv("CM31_NO_LANES") ? 0 : 1;
+    if (!g_lanes_on || lane == 0) {
+        g_stream = g_main;
+        return 0;
+    }
+    if (!g_side) {
+        // highest priority: the side lane's few-CTA kernels are dispatched as soon as an SM slot frees up instead of
+        // queueing behind every CTA of a large lane-0 kernel
+        int prio_low = 0, prio_high = 0;
+        CM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+        CM_CUDA(cudaStreamCreateWithPriority(&g_side, cudaStreamNonBlocking, prio_high));
+        CM_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+        CM_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+    }
+    if (!g_forked) {
+        CM_CUDA(cudaEventRecord(g_ev_fork, g_main));
+        CM_CUDA(cudaStreamWaitEvent(g_side, g_ev_fork, 0));
+        g_forked = true;
+    }
+    g_stream = g_side;
+    return 0;
+}
+int cm31_lanes_join(void) {
+    g_stream = g_main;
+    if (g_forked) {
+        CM_CUDA(cudaEventRecord(g_ev_join, g_side));
+        CM_CUDA(cudaStreamWaitEvent(g_main, g_ev_join, 0));
+        g_forked = false;
+    }
     return 0;
 }
 int cm31_sync(void) {
@@ -369,6 +433,58 @@ int cm31_gather_runs(const uint32_t* const* srcs, size_t n_srcs, const uint32_t*
     CM_CUDA(cudaMemcpyAsync(out_host, dout, total * 4, cudaMemcpyDeviceToHost, stream()));
     CM_CUDA(cudaFreeAsync(dout, stream()));
     CM_CUDA(cudaStreamSynchronize(stream()));
+    return 0;
+}
+
+int cm31_gather_batch(const uint32_t* const* srcs, size_t n_srcs, const uint32_t* src_id_host, const uint32_t* word_idx_host,
+                      const uint32_t* out_off_host, const uint32_t* cnt_host, size_t n_runs, const uint32_t* grid_desc_host,
+                      size_t n_grids, const uint32_t* grid_cols_host, size_t n_grid_cols, const uint32_t* grid_rows_host,
+                      size_t n_grid_rows, size_t total_words, uint32_t* out_host) {
+    if (total_words == 0) return 0;
+    for (size_t k = 0; k < n_runs; k++)
+        CM_REQUIRE(src_id_host[k] < n_srcs && (size_t)out_off_host[k] + cnt_host[k] <= total_words, "gather_batch: bad run request");
+    size_t max_work = 0;
+    for (size_t g = 0; g < n_grids; g++) {
+        const uint32_t* d = grid_desc_host + 5 * g;
+        CM_REQUIRE((size_t)d[0] + d[1] <= n_grid_cols && (size_t)d[2] + d[3] <= n_grid_rows && (size_t)d[4] + (size_t)d[1] * d[3] <= total_words,
+                   "gather_batch: bad grid request");
+        max_work = std::max(max_work, (size_t)d[1] * d[3]);
+    }
+    for (size_t c = 0; c < n_grid_cols; c++) CM_REQUIRE(grid_cols_host[c] < n_srcs, "gather_batch: bad grid column");
+    // page-locked landing buffer (grow-only): the result copy is a true DMA instead of a driver-staged pageable copy
+    static u32* pinned = nullptr;
+    static size_t pinned_words = 0;
+    if (pinned_words < total_words) {
+        if (pinned) cudaFreeHost(pinned);
+        pinned_words = std::max<size_t>(total_words * 2, (size_t)1 << 18);
+        CM_CUDA(cudaHostAlloc((void**)&pinned, pinned_words * 4, cudaHostAllocDefault));
+    }
+    DeviceTable dsrcs, dsid, dword, doff, dcnt, ddesc, dcols, drows;
+    if (int e = dsrcs.upload(srcs, n_srcs * sizeof(void*))) return e;
+    u32* dout = nullptr;
+    CM_CUDA(cudaMallocAsync(&dout, total_words * 4, stream()));
+    ProfScope prof("gather_runs", 8ull * total_words, (n_runs ? 1 : 0) + (n_grids ? 1 : 0));
+    if (n_runs) {
+        if (int e = dsid.upload(src_id_host, n_runs * 4)) return e;
+        if (int e = dword.upload(word_idx_host, n_runs * 4)) return e;
+        if (int e = doff.upload(out_off_host, n_runs * 4)) return e;
+        if (int e = dcnt.upload(cnt_host, n_runs * 4)) return e;
+        gather_runs2_kernel<<<(unsigned)((n_runs + 255) / 256), 256, 0, stream()>>>((const u32* const*)dsrcs.d, (const u32*)dsid.d, (const u32*)dword.d,
+                                                                                   (const u32*)doff.d, (const u32*)dcnt.d, n_runs, dout);
+        CM_LAUNCH_CHECK();
+    }
+    if (n_grids) {
+        if (int e = ddesc.upload(grid_desc_host, n_grids * 20)) return e;
+        if (int e = dcols.upload(grid_cols_host, n_grid_cols * 4)) return e;
+        if (int e = drows.upload(grid_rows_host, n_grid_rows * 4)) return e;
+        dim3 grid((unsigned)std::min<size_t>((max_work + 255) / 256, 64), (unsigned)n_grids);
+        gather_grid_kernel<<<grid, 256, 0, stream()>>>((const u32* const*)dsrcs.d, (const u32*)ddesc.d, (const u32*)dcols.d, (const u32*)drows.d, dout);
+        CM_LAUNCH_CHECK();
+    }
+    CM_CUDA(cudaMemcpyAsync(pinned, dout, total_words * 4, cudaMemcpyDeviceToHost, stream()));
+    CM_CUDA(cudaFreeAsync(dout, stream()));
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    memcpy(out_host, pinned, total_words * 4);
     return 0;
 }
 

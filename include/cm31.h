@@ -36,6 +36,14 @@ int cm31_device_count(int* out);
 int cm31_set_device(int ordinal);
 int cm31_set_stream(void* cuda_stream); /* cudaStream_t; NULL = legacy default stream */
 int cm31_sync(void);
+/* Lanes (SimdBackend's rayon pool has no analogue of this: it is the CUDA backend's way of overlapping the many
+ * latency-bound launches of small components with the kernels of large ones).  cm31_lane(1) routes the following
+ * calls to a side stream ordered after everything issued so far on the caller's stream; cm31_lane(0) returns to the
+ * caller's stream; cm31_lanes_join() makes the caller's stream wait for the side stream.  Between a fork and the join,
+ * work on one lane must not consume results produced on the other, and a buffer must be freed on the lane that last
+ * used it.  Calls that return host-readable values must be made on lane 0 after a join. */
+int cm31_lane(int lane);
+int cm31_lanes_join(void);
 /* Column<T>::zeros / uninitialized / to_cpu / from_iter  (S/prover/src/core/backend/mod.rs:46-65) */
 int cm31_malloc(void** out, size_t bytes);
 int cm31_free(void* dptr);
@@ -60,6 +68,15 @@ int cm31_gather_words(const uint32_t* const* srcs, size_t n_srcs, const uint32_t
  * 8 words = a hash node); out_off_host has n+1 entries */
 int cm31_gather_runs(const uint32_t* const* srcs, size_t n_srcs, const uint32_t* src_id_host, const uint32_t* word_idx_host,
                      const uint32_t* out_off_host, size_t n, uint32_t* out_host);
+/* One decommitment gather per proof (vcs/prover.rs:125-140 and fri.rs:1002-1036 read element by element):
+ * n_runs run requests (cnt_host[k] words from srcs[src_id_host[k]][word_idx_host[k]] to out_host[out_off_host[k]..]) plus
+ * n_grids row-grid requests, 5 words each in grid_desc_host = (col_off, n_cols, row_off, n_rows, out_base):
+ * out_host[out_base + k*n_cols + c] = srcs[grid_cols_host[col_off + c]][grid_rows_host[row_off + k]] -- every column of a
+ * Merkle layer at every visited node.  total_words = size of out_host. */
+int cm31_gather_batch(const uint32_t* const* srcs, size_t n_srcs, const uint32_t* src_id_host, const uint32_t* word_idx_host,
+                      const uint32_t* out_off_host, const uint32_t* cnt_host, size_t n_runs, const uint32_t* grid_desc_host,
+                      size_t n_grids, const uint32_t* grid_cols_host, size_t n_grid_cols, const uint32_t* grid_rows_host,
+                      size_t n_grid_rows, size_t total_words, uint32_t* out_host);
 /* same for hash columns: out_host[q*8..] = layer[idx[q]] */
 int cm31_gather_hash(const uint32_t* layer, const uint32_t* idx_host, size_t n_idx, uint32_t* out_host);
 
@@ -113,6 +130,10 @@ int cm31_blake2s_commit_layer(uint32_t log_size, const uint32_t* prev_layer, con
 /* Layers top_log_size .. 0 of MerkleProver::commit (vcs/prover.rs:52-64) in one launch (top_log_size <= 10):
  * layer l hashes prev = layer l+1 (prev_layer for l = top_log_size, may be NULL) and the columns
  * cols[col_start_host[l] .. col_start_host[l+1]) of 2^l words; out_layers[l] receives 2^l nodes. */
+/* n_levels (1..9) consecutive layers log_size, log_size-1, .. in one launch; only the first may carry columns (and a
+ * previous layer); out_layers[l] receives layer log_size - l.  Same hashes as n_levels calls of commit_layer. */
+int cm31_blake2s_commit_multi(uint32_t log_size, const uint32_t* prev_layer, const uint32_t* const* cols, size_t n_cols,
+                              uint32_t n_levels, uint32_t* const* out_layers);
 int cm31_blake2s_commit_top(uint32_t top_log_size, const uint32_t* prev_layer, const uint32_t* const* cols,
                             const uint32_t* col_start_host, uint32_t* const* out_layers);
 

@@ -66,6 +66,13 @@ struct OracleBackend {
         for (size_t c = 0; c < cols.size(); c++)
             for (size_t q = 0; q < idx.size(); q++) out[c][q] = (*cols[c])[idx[q]].v;
     }
+    static std::vector<HashCol> commit_layers_fused(u32 log_size, const HashCol* prev, const std::vector<const Col*>& cols, u32 n_levels) {
+        std::vector<HashCol> out;
+        for (u32 l = 0; l < n_levels; l++) {
+            out.push_back(orc::commit_on_layer(log_size - l, l == 0 ? prev : &out[l - 1], l == 0 ? cols : std::vector<const Col*>()));
+        }
+        return out;
+    }
     static std::vector<HashCol> commit_top_layers(u32 top_log, const HashCol* prev, const std::vector<std::vector<const Col*>>& cols_by_layer) {
         std::vector<HashCol> out(top_log + 1);
         for (int l = (int)top_log; l >= 0; l--) {
@@ -74,12 +81,21 @@ struct OracleBackend {
         }
         return out;
     }
+    static void lane(u32) {}  // the CUDA backend's stream lanes have no CPU counterpart
+    static void lanes_join() {}
+    static void prepare() {}
     static const u32* col_words(const Col& c) { return (const u32*)c.data(); }
     static const u32* hash_words(const HashCol& c) { return (const u32*)c.data(); }
     static void gather_runs(const std::vector<const u32*>& srcs, const std::vector<u32>& src_id, const std::vector<u32>& word,
-                            const std::vector<u32>& out_off, std::vector<u32>& out) {
+                            const std::vector<u32>& out_off, const std::vector<u32>& cnt, const std::vector<u32>& grid_desc,
+                            const std::vector<u32>& grid_cols, const std::vector<u32>& grid_rows, std::vector<u32>& out) {
         for (size_t k = 0; k < src_id.size(); k++)
-            for (u32 j = 0; j < out_off[k + 1] - out_off[k]; j++) out[out_off[k] + j] = srcs[src_id[k]][word[k] + j];
+            for (u32 j = 0; j < cnt[k]; j++) out[out_off[k] + j] = srcs[src_id[k]][word[k] + j];
+        for (size_t g = 0; g + 5 <= grid_desc.size(); g += 5) {  // (col_off, n_cols, row_off, n_rows, out_base), row-major output
+            const u32 col_off = grid_desc[g], n_cols = grid_desc[g + 1], row_off = grid_desc[g + 2], n_rows = grid_desc[g + 3], base = grid_desc[g + 4];
+            for (u32 k = 0; k < n_rows; k++)
+                for (u32 c = 0; c < n_cols; c++) out[base + (size_t)k * n_cols + c] = srcs[grid_cols[col_off + c]][grid_rows[row_off + k]];
+        }
     }
     static cm31::Hash32 read_root(const HashCol& root_layer) {
         cm31::Hash32 h;

@@ -306,6 +306,25 @@ def test_commit_top_layers_matches_layer_by_layer_oracle(cm, top, with_prev, col
         assert np.array_equal(host(outs[l]), expect_prev), f"layer {l}"
 
 
+@pytest.mark.parametrize("log_size,n_cols,with_prev,n_levels", [(8, 4, False, 9), (11, 4, False, 1), (13, 0, True, 3), (12, 21, True, 2),
+                                                               (16, 4, False, 6), (17, 17, True, 9)])
+def test_commit_multi_matches_layer_by_layer_oracle(cm, log_size, n_cols, with_prev, n_levels):
+    # fused consecutive layers (first with columns / a previous layer, the rest column-free) == one commit_on_layer per layer
+    mat = orc.splitmix64(0x51 + log_size, n_cols << log_size).reshape(n_cols, 1 << log_size) if n_cols else None
+    prev = None
+    if with_prev:
+        prev = (orc.splitmix64(0x77, (2 << log_size) * 8).astype(np.uint64) * 7 + 0x80000005).astype(np.uint32).reshape(2 << log_size, 8)
+    dprev = torch.from_numpy(prev.view(np.int32)).cuda() if prev is not None else None
+    dcols = to_dev_cols(mat) if n_cols else []
+    outs = [torch.empty((1 << (log_size - l), 8), dtype=torch.int32, device="cuda") for l in range(n_levels)]
+    cm.blake2s_commit_multi(log_size, dprev, dcols, outs)
+    cm.sync()
+    expect = prev
+    for l in range(n_levels):
+        expect = orc.commit_on_layer(log_size - l, expect, mat if l == 0 else None)
+        assert np.array_equal(host(outs[l]), expect), f"level {l}"
+
+
 def test_gather_runs(cm):
     mat = orc.splitmix64(8, 3 * 512).reshape(3, 512)
     cols = to_dev_cols(mat)
@@ -316,6 +335,30 @@ def test_gather_runs(cm):
     got = cm.gather_runs(cols, sid, widx, counts)
     want = [int(v) for s, w, c in zip(sid, widx, counts) for v in mat[s, w:w + c]]
     assert got == want
+
+
+def test_gather_batch_runs_and_row_grids(cm):
+    # the per-proof decommitment gather: interleaved run requests (hash nodes, single words) and row grids (all columns of a
+    # Merkle layer at the visited nodes), including an empty-run-only and a grid-only call
+    mat = orc.splitmix64(9, 5 * 1024).reshape(5, 1024)
+    cols = to_dev_cols(mat)
+    rng = np.random.default_rng(5)
+    want, sid, widx, off, cnt, grids = [], [], [], [], [], []
+    for it in range(40):
+        if it % 3 == 2:
+            cids = rng.permutation(5)[: int(rng.integers(1, 6))].tolist()
+            rows = sorted(rng.choice(1024, int(rng.integers(1, 50)), replace=False).tolist())
+            grids.append((cids, rows, len(want)))
+            want += [int(mat[c, r]) for r in rows for c in cids]
+        else:
+            c = int(rng.choice([1, 8]))
+            s, w = int(rng.integers(0, 5)), int(rng.integers(0, 1024 - c + 1))
+            sid.append(s); widx.append(w); off.append(len(want)); cnt.append(c)
+            want += [int(v) for v in mat[s, w:w + c]]
+    assert cm.gather_batch(cols, sid, widx, off, cnt, grids, len(want)) == want
+    g_only = [([0, 4], [3, 1000], 0)]
+    assert cm.gather_batch(cols, [], [], [], [], g_only, 4) == [int(mat[0, 3]), int(mat[4, 3]), int(mat[0, 1000]), int(mat[4, 1000])]
+    assert cm.gather_batch(cols, [2], [7], [0], [8], [], 8) == [int(v) for v in mat[2, 7:15]]
 
 
 def test_sharded_commit_world1_equals_layer_by_layer_oracle(cm):
