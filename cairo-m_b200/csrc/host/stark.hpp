@@ -347,7 +347,14 @@ struct MerkleProver {
         u32 max_log = ilog2(B::len(*sorted[0]));
         size_t pos = 0;
         std::vector<HashCol> layers;
-        constexpr int TOP_LOG = 10;  // layers of <= 2^10 nodes are hashed by one fused launch
+        // Layers of <= 2^TOP_LOG nodes are hashed by ONE single-CTA launch (which can inject columns at every layer): 2^10 when
+        // columns of 2^8..2^10 rows exist; otherwise 2^7, so the 2^8..2^10 layers stay multi-CTA inside the fused launch
+        // above them (FRI layer trees, the composition tree).
+        int TOP_LOG = 7;
+        for (const Col* c : sorted) {
+            u32 l = ilog2(B::len(*c));
+            if (l > 7 && l <= 10) TOP_LOG = 10;
+        }
         int log_size = (int)max_log;
         while (log_size > TOP_LOG) {
             std::vector<const Col*> layer_cols;

@@ -5,11 +5,11 @@
 TAG=${1:-r01}
 LOG=${2:-22}
 shift 2
-KERNELS=${@:-fft4_pass_kernel merkle_layer_kernel quotients_fast_kernel k_.*_constraints k_.*_logup}
+KERNELS=${@:-fft4_pass_kernel merkle_layer_kernel merkle_multi_kernel quotients_fast_kernel k_store_fp_imm_constraints k_store_fp_imm_logup}
 mkdir -p gpurun_out
 BENCH="python bench.py --log-steps $LOG --steps 1 --warmup 0 --no-cpu-baseline"
-# every launch of the 3rd proof of the run (value proof, staging proof, then the e2e proof)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 960 -c 480 --csv \
+# every launch of the run's 3 proofs (value proof, staging proof, e2e proof): shares are per kernel over identical proofs
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
     --log-file gpurun_out/launches_${TAG}.csv $BENCH > gpurun_out/ncu_launches_${TAG}.log 2>&1
 python tools/ncu_summary.py launches gpurun_out/launches_${TAG}.csv gpurun_out/launches_${TAG}.md > /dev/null
 for K in $KERNELS; do
