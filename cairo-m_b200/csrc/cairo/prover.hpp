@@ -258,9 +258,11 @@ struct StagedInput {
     struct Rows {
         typename Impl::Words words;
         size_t n_real = 0;
+        u32 mark = 0;  // staging mark: the rows have landed once it is reached
     };
     typename Impl::Words accesses;
     size_t n_accesses = 0;
+    u32 accesses_mark = 0;
     std::vector<Rows> opcode;  // one per opcode component, CM31_OPCODE_EVALS order
     Rows memory, clock_update;
     size_t bytes = 0;  // total bytes staged
@@ -269,10 +271,12 @@ struct StagedInput {
 template <class Impl>
 StagedInput<Impl> stage_input(const ProverInput& input) {
     StagedInput<Impl> st;
+    // pass 1: every destination buffer (stream-ordered allocations on the proof's stream); pass 2, after ONE ordering
+    // point (Impl::staging_begin), the copies on the background stream, each followed by its mark
     st.n_accesses = input.data_accesses.size();
     st.accesses = Impl::alloc_words(st.n_accesses * 4);
-    Impl::copy_words(st.accesses, 0, (const u32*)input.data_accesses.data(), st.n_accesses * 4);
     st.bytes += st.n_accesses * 16;
+    std::vector<std::vector<const std::vector<Bundle>*>> parts_of;
     auto opcode_rows = [&](const std::vector<u32>& opcodes) {
         typename StagedInput<Impl>::Rows r;
         std::vector<const std::vector<Bundle>*> parts;
@@ -282,17 +286,24 @@ StagedInput<Impl> stage_input(const ProverInput& input) {
         }
         for (auto* v : parts) r.n_real += v->size();
         r.words = Impl::alloc_words(r.n_real * 12);
-        size_t at = 0;
-        for (auto* v : parts) {  // straight from the adapter's (page-locked) vectors, no host-side concatenation
-            Impl::copy_words(r.words, at * 12, (const u32*)v->data(), v->size() * 12);
-            at += v->size();
-        }
         st.bytes += r.n_real * sizeof(Bundle);
         st.opcode.push_back(std::move(r));
+        parts_of.push_back(std::move(parts));
     };
 #define CM31_X(E) opcode_rows(E::opcodes());
     CM31_OPCODE_EVALS(CM31_X)
 #undef CM31_X
+    Impl::staging_begin();
+    Impl::copy_words(st.accesses, 0, (const u32*)input.data_accesses.data(), st.n_accesses * 4);
+    st.accesses_mark = Impl::staging_mark();
+    for (size_t c = 0; c < st.opcode.size(); c++) {
+        size_t at = 0;
+        for (auto* v : parts_of[c]) {  // straight from the adapter's (page-locked) vectors, no host-side concatenation
+            Impl::copy_words(st.opcode[c].words, at * 12, (const u32*)v->data(), v->size() * 12);
+            at += v->size();
+        }
+        st.opcode[c].mark = Impl::staging_mark();
+    }
     {  // memory (components/memory.rs:93-195): initial rows then final rows
         std::vector<u32> rows;
         for (const std::vector<MemoryRow>* v : {&input.initial_memory, &input.final_memory})
@@ -355,7 +366,8 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     auto t1 = Impl::now_ms();
 
     // ---- tree 1: execution traces
-    Impl::staging_fence();  // the staged input (background copies) is complete from here on
+    // the access log (copied first) must be complete before any trace fill; each component then waits for its own rows only
+    Impl::staging_wait(staged.accesses_mark);
     std::vector<u32> log_sizes;
     std::vector<std::vector<CircleEvaluation<B>>> traces;  // per component (kept until tree 2 is built)
     size_t opcode_index = 0;
@@ -364,6 +376,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         const auto& rows = staged.opcode.at(opcode_index++);
         u32 ls = padded_log_size(rows.n_real);
         B::lane(ls);  // small components go to the side lane; every temporary below dies on the lane that used it
+        Impl::staging_wait(rows.mark);
         std::vector<Col> inputs = Impl::unpack_bundles(rows.words, rows.n_real, staged.accesses, staged.n_accesses, ls);
         Eval eval;
         eval.log_size_ = ls;

@@ -48,8 +48,9 @@ struct CudaAirImpl {
     }
     static Words alloc_words(size_t n_words) { return DeviceCol(std::max<size_t>(4, n_words)); }
     // staging runs on the background copy stream; prove_cairo_m fences before the first use
+    static void staging_begin() { cm_check(cm31_bg_begin()); }
     static void copy_words(Words& dst, size_t at, const u32* src, size_t n_words) {
-        if (n_words) cm_check(cm31_h2d_bg(dst.ptr() + at, src, n_words * 4));
+        if (n_words) cm_check(cm31_h2d_bg_ordered(dst.ptr() + at, src, n_words * 4));
     }
     static Words upload_words(const u32* src, size_t n_words) {
         DeviceCol dev(std::max<size_t>(4, n_words));
@@ -58,6 +59,12 @@ struct CudaAirImpl {
         return dev;
     }
     static void staging_fence() { cm_check(cm31_bg_fence()); }
+    static u32 staging_mark() {
+        u32 m = 0;
+        cm_check(cm31_bg_mark(&m));
+        return m;
+    }
+    static void staging_wait(u32 mark) { cm_check(cm31_bg_wait(mark)); }
     static std::vector<Col> unpack_bundles(const Words& rows, size_t n_real, const Words& accesses, size_t n_accesses, u32 log_size) {
         std::vector<Col> cols = Col::many(N_BUNDLE_INPUTS, (size_t)1 << log_size);
         std::vector<u32*> p;

@@ -36,6 +36,8 @@ int cm31_prove_wide_fibonacci(uint32_t log_n_rows, uint32_t n_cols, uint32_t pow
 }  // extern "C"
 
 // ------------------------------------------------------------------ cairo-m
+#include <deque>
+
 #include "cairo/prover.hpp"
 #include "host/cuda_air_impl.hpp"
 
@@ -43,6 +45,7 @@ struct cm31_prover_input {
     cm31::ProverInput input;
     uint32_t return_value = 0;
     std::unique_ptr<cm31::StagedInput<cm31::CudaAirImpl>> staged;  // set by cm31_input_upload
+    std::deque<std::unique_ptr<cm31::StagedInput<cm31::CudaAirImpl>>> prefetched;  // cm31_input_prefetch, consumed oldest first
     std::vector<void*> pinned;                                     // host ranges registered with CUDA
     ~cm31_prover_input() {
         for (void* p : pinned) cudaHostUnregister(p);
@@ -87,6 +90,7 @@ int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input
 int cm31_input_tamper(cm31_prover_input* h, uint32_t kind) {
     CM_REQUIRE(h != nullptr, "input_tamper: null handle");
     h->staged.reset();
+    h->prefetched.clear();
     auto it = h->input.states_by_opcodes.find(kind == 0 ? OP_STORE_ADD_FP_FP : OP_STORE_SUB_FP_FP);
     CM_REQUIRE(it != h->input.states_by_opcodes.end() && !it->second.empty(), "input_tamper: the program has no such step");
     const Bundle& b = it->second[it->second.size() / 2];
@@ -114,7 +118,19 @@ int cm31_input_upload(cm31_prover_input* h) {
 int cm31_input_release_device(cm31_prover_input* h) {
     CM_REQUIRE(h != nullptr, "input_release_device: null handle");
     h->staged.reset();
+    h->prefetched.clear();
     return 0;
+}
+int cm31_input_prefetch(cm31_prover_input* h) {
+    try {
+        CM_REQUIRE(h != nullptr, "input_prefetch: null handle");
+        CM_REQUIRE(h->prefetched.size() < 4, "input_prefetch: too many uploads in flight");
+        h->prefetched.emplace_back(new StagedInput<CudaAirImpl>(stage_input<CudaAirImpl>(h->input)));
+        return 0;
+    } catch (const std::exception& e) {
+        set_error(e.what());
+        return -2;
+    }
 }
 // info[0] = VM steps, info[1] = data accesses, info[2] = boundary memory rows, info[3] = return value,
 // info[4] = bytes of prover input copied host->device per proof
@@ -139,7 +155,14 @@ int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n
         cfg.pow_bits = pow_bits;
         cfg.fri_config.n_queries = n_queries;
         ProveTimings t;
-        CairoProof proof = h->staged ? prove_cairo_m<CudaAirImpl>(h->input, *h->staged, cfg, &t) : prove_cairo_m<CudaAirImpl>(h->input, cfg, &t);
+        std::unique_ptr<StagedInput<CudaAirImpl>> pre;
+        if (!h->staged && !h->prefetched.empty()) {
+            pre = std::move(const_cast<cm31_prover_input*>(h)->prefetched.front());
+            const_cast<cm31_prover_input*>(h)->prefetched.pop_front();
+        }
+        CairoProof proof = h->staged ? prove_cairo_m<CudaAirImpl>(h->input, *h->staged, cfg, &t)
+                           : pre     ? prove_cairo_m<CudaAirImpl>(h->input, *pre, cfg, &t)
+                                     : prove_cairo_m<CudaAirImpl>(h->input, cfg, &t);
         if (timings_ms) {
             timings_ms[0] = t.preprocessed_ms;
             timings_ms[1] = t.trace_ms;

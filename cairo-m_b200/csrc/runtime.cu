@@ -328,6 +328,39 @@ int cm31_h2d_bg(void* dst, const void* src_host, size_t bytes) {
     CM_CUDA(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, g_copy_stream));
     return 0;
 }
+// Bracketed form: cm31_bg_begin orders the copy stream after the main stream ONCE (all destinations allocated before it),
+// cm31_h2d_bg_ordered then only enqueues the copy (2 driver calls fewer per copy).
+int cm31_bg_begin(void) {
+    if (int e = ensure_copy_stream()) return e;
+    CM_CUDA(cudaEventRecord(g_main_event, stream()));
+    CM_CUDA(cudaStreamWaitEvent(g_copy_stream, g_main_event, 0));
+    return 0;
+}
+int cm31_h2d_bg_ordered(void* dst, const void* src_host, size_t bytes) {
+    if (int e = ensure_copy_stream()) return e;
+    CM_CUDA(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, g_copy_stream));
+    return 0;
+}
+// Marks: an event after the background copies issued so far; cm31_bg_wait(mark) makes the CURRENT lane wait for it, so a
+// component's trace fill starts as soon as ITS rows have landed instead of after the whole input (256 recyclable events:
+// a recycled mark only over-waits).
+static cudaEvent_t g_marks[256] = {nullptr};
+static uint32_t g_next_mark = 0;
+int cm31_bg_mark(uint32_t* mark_out) {
+    CM_REQUIRE(mark_out != nullptr, "bg_mark: null output");
+    if (int e = ensure_copy_stream()) return e;
+    uint32_t m = g_next_mark++ % 256;
+    if (!g_marks[m]) CM_CUDA(cudaEventCreateWithFlags(&g_marks[m], cudaEventDisableTiming));
+    CM_CUDA(cudaEventRecord(g_marks[m], g_copy_stream));
+    *mark_out = m;
+    return 0;
+}
+int cm31_bg_wait(uint32_t mark) {
+    CM_REQUIRE(mark < 256, "bg_wait: bad mark");
+    if (!g_marks[mark]) return 0;
+    CM_CUDA(cudaStreamWaitEvent(stream(), g_marks[mark], 0));
+    return 0;
+}
 int cm31_bg_fence(void) {
     if (!g_copy_stream) return 0;
     CM_CUDA(cudaEventRecord(g_copy_event, g_copy_stream));

@@ -54,6 +54,12 @@ int cm31_d2h(void* dst_host, const void* src, size_t bytes);
  * cm31_bg_fence() orders the main stream after every background copy issued so far */
 int cm31_h2d_bg(void* dst, const void* src_host, size_t bytes);
 int cm31_bg_fence(void);
+/* finer than the fence: *mark_out names the background copies issued so far; cm31_bg_wait(mark) orders the current
+ * stream (lane) after them */
+int cm31_bg_begin(void); /* order the background stream after the current one, once, then: */
+int cm31_h2d_bg_ordered(void* dst, const void* src_host, size_t bytes);
+int cm31_bg_mark(uint32_t* mark_out);
+int cm31_bg_wait(uint32_t mark);
 int cm31_d2d(void* dst, const void* src, size_t bytes);
 /* Column::at for many (column,row) pairs at once (decommit):
  * out_host[c * n_idx + q] = cols[c][idx_host[q]]   (S/prover/src/core/vcs/prover.rs:125-140) */
@@ -219,6 +225,10 @@ int cm31_histogram(const uint32_t* values, size_t n, uint32_t* bins, uint32_t lo
  * (host VM + adapter, the serial step BEFORE the hot path) is built in this round. */
 typedef struct cm31_prover_input cm31_prover_input;
 int cm31_fib_input_create(uint32_t n, cm31_prover_input** out);
+/* Starts the host->device copy of this handle's prover input on the background stream and returns at once; the next
+ * cm31_prove_cairo_m on the handle consumes it (oldest first) instead of copying itself: the upload of segment i+1 overlaps
+ * the proof of segment i. */
+int cm31_input_prefetch(cm31_prover_input* h);
 /* program_id 0 = fibonacci_loop(n); 1 = array_sum(n): call/ret, frame pointer, double-deref, assert, le; 2 = u32_counter(n): u32 limb ops; 3 = u32_mix(n): u32 mul/divrem/eq/lt + two-word *_fp_imm u32 instructions */
 int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out);
 int cm31_input_destroy(cm31_prover_input* h);

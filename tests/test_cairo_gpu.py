@@ -142,6 +142,27 @@ def test_u32_mix_2_14_rounds_verifies(cm):
     assert residual == (0, 0, 0, 0)
 
 
+def test_prefetched_input_gives_the_same_proof(cm):
+    # cm31_input_prefetch: uploads issued ahead (two in flight) are consumed oldest-first by the following proofs; the
+    # proof bytes do not depend on how the input reached the device (host-input, prefetched, device-resident)
+    n = 300
+    inp = ch.GpuFibInput(cm, n)
+    try:
+        plain, _ = inp.prove()
+        cm.check(cm.lib().cm31_input_prefetch(inp.h))
+        cm.check(cm.lib().cm31_input_prefetch(inp.h))
+        first, _ = inp.prove()
+        second, _ = inp.prove()
+        third, _ = inp.prove()  # nothing prefetched any more: stages its own input again
+        cm.check(cm.lib().cm31_input_upload(inp.h))
+        resident, _ = inp.prove()
+    finally:
+        inp.close()
+    assert plain == first == second == third == resident
+    want, _ = ch.oracle_fib_prove(n)
+    assert plain == want
+
+
 @pytest.mark.parametrize("kind", [0, 1])
 def test_invalid_trace_is_refused(cm, kind):
     # an execution trace that does not satisfy the AIR must not yield a proof: the composition OODS
