@@ -26,12 +26,15 @@
 //   u32_store_mul_fp_imm, u32_store_div_fp_fp, u32_store_div_fp_imm, u32_store_bitwise_fp_imm: cited at each struct
 //   bitwise (table)      crates/prover/src/preprocessed/bitwise.rs:72-140 (multiplicities), :196-215 (evaluate), :253-290 (columns)
 //   memory         crates/prover/src/components/memory.rs:93-195, :294-366
+//   merkle         crates/prover/src/components/merkle.rs:73-170, :285-377
+//   poseidon2      crates/prover/src/components/poseidon2.rs:143-290, :385-505 (constants: csrc/cairo/poseidon2.hpp, PLACEHOLDER)
 //   clock_update   crates/prover/src/components/clock_update.rs:70-160, :217-262
 //   range_check_N  crates/prover/src/preprocessed/range_check/range_check_macro.rs:62-112, :171-183
 #pragma once
 #include <string>
 #include <vector>
 
+#include "../cairo/poseidon2.hpp"
 #include "../field.cuh"
 
 namespace cm31 {
@@ -2141,6 +2144,146 @@ struct MemoryEval : OpcodeEvalBase {
     void write_trace(T& t) const {
         t.out(0, t.enabler());
         for (int k = 0; k < 8; k++) t.out(1 + k, t.in(k));
+    }
+};
+
+// ------------------------------------------------------------------ merkle (partial Merkle tree of the boundary memory)
+//   crates/prover/src/components/merkle.rs:73-170 (write_trace), :285-377 (evaluate)
+// inputs: index, depth, left_value, right_value, parent_value, left/right/parent multiplicity, root
+struct MerkleEval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 10;
+    static const char* name() { return "merkle"; }
+    template <class E>
+    void evaluate(E& eval) const {
+        auto one = eval.f_const(1);
+        auto two = eval.f_const(2);
+        auto m31_2_inv = eval.f_const(m31_inv(2));
+        auto enabler = eval.next_trace_mask();
+        auto index = eval.next_trace_mask();
+        auto depth = eval.next_trace_mask();
+        auto left_value = eval.next_trace_mask();
+        auto right_value = eval.next_trace_mask();
+        auto parent_value = eval.next_trace_mask();
+        auto left_multiplicity = eval.next_trace_mask();
+        auto right_multiplicity = eval.next_trace_mask();
+        auto parent_multiplicity = eval.next_trace_mask();
+        auto root = eval.next_trace_mask();
+        eval.add_constraint(enabler * (one - enabler));
+        eval.add_constraint(left_multiplicity * (left_multiplicity - one) * (left_multiplicity - one * two));
+        eval.add_constraint(right_multiplicity * (right_multiplicity - one) * (right_multiplicity - one * two));
+        eval.add_constraint(parent_multiplicity * (parent_multiplicity - one) * (parent_multiplicity - one * two));
+        eval.add_to_relation(REL_MERKLE, eval.ef(left_multiplicity), {index, depth, left_value, root});
+        eval.add_to_relation(REL_MERKLE, eval.ef(right_multiplicity), {index + one, depth, right_value, root});
+        eval.add_to_relation(REL_MERKLE, -eval.ef(parent_multiplicity), {index * m31_2_inv, depth - one, parent_value, root});
+        eval.add_to_relation(REL_POSEIDON2, eval.ef(enabler), {left_value, right_value});
+        eval.add_to_relation(REL_POSEIDON2, -eval.ef(enabler), {parent_value});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        t.out(0, t.enabler());
+        for (int k = 0; k < 9; k++) t.out(1 + k, t.in(k));
+    }
+};
+
+// ------------------------------------------------------------------ poseidon2 (one permutation per row)
+//   crates/prover/src/components/poseidon2.rs:143-290 (write_trace), :385-505 (evaluate); round structure and the
+//   (placeholder) constants in csrc/cairo/poseidon2.hpp.  inputs: the 16 words of the initial state.
+struct Poseidon2Eval : OpcodeEvalBase {
+    static constexpr int N_TRACE_COLUMNS = 1 + POSEIDON2_T * (1 + POSEIDON2_FULL_ROUNDS * 3) + 3 * POSEIDON2_PARTIAL_ROUNDS;  // 443
+    static const char* name() { return "poseidon2"; }
+    template <class E>
+    void evaluate(E& eval) const {
+        typedef decltype(eval.f_const(0)) F;
+        const Poseidon2Constants& k = poseidon2_constants();
+        auto enabler = eval.next_trace_mask();
+        std::array<F, 16> state = {enabler, enabler, enabler, enabler, enabler, enabler, enabler, enabler,
+                                   enabler, enabler, enabler, enabler, enabler, enabler, enabler, enabler};
+        for (int i = 0; i < 16; i++) state[i] = eval.next_trace_mask();
+        std::array<F, 16> initial_state = state;
+        auto mulc = [&](F x, u32 c) { return x * eval.f_const(c); };
+        auto constrain_to_mask = [&](F& s) {
+            auto m = eval.next_trace_mask();
+            eval.add_constraint(enabler * (s - m));
+            s = m;
+        };
+        auto full_round = [&](int r) {
+            for (int i = 0; i < 16; i++) state[i] = state[i] + eval.f_const(k.external[r][i]);
+            std::array<F, 16> round_input = state;
+            for (int i = 0; i < 16; i++) state[i] = state[i] * state[i];
+            for (int i = 0; i < 16; i++) constrain_to_mask(state[i]);
+            for (int i = 0; i < 16; i++) state[i] = state[i] * state[i];
+            for (int i = 0; i < 16; i++) constrain_to_mask(state[i]);
+            for (int i = 0; i < 16; i++) state[i] = state[i] * round_input[i];
+            poseidon2_external_matrix(state);
+            for (int i = 0; i < 16; i++) constrain_to_mask(state[i]);
+        };
+        poseidon2_external_matrix(state);
+        for (int r = 0; r < POSEIDON2_FULL_ROUNDS / 2; r++) full_round(r);
+        for (int r = 0; r < POSEIDON2_PARTIAL_ROUNDS; r++) {
+            state[0] = state[0] + eval.f_const(k.internal[r]);
+            F round_input = state[0];
+            {
+                auto m = eval.next_trace_mask();
+                eval.add_constraint(enabler * (state[0] * state[0] - m));
+                state[0] = m;
+            }
+            {
+                auto m = eval.next_trace_mask();
+                eval.add_constraint(enabler * (state[0] * state[0] - m));
+                state[0] = m;
+            }
+            {
+                auto m = eval.next_trace_mask();
+                eval.add_constraint(enabler * (round_input * state[0] - m));
+                state[0] = m;
+            }
+            poseidon2_internal_matrix(state, mulc);
+        }
+        for (int r = 0; r < POSEIDON2_FULL_ROUNDS / 2; r++) full_round(POSEIDON2_FULL_ROUNDS / 2 + r);
+        eval.add_to_relation(REL_POSEIDON2, -eval.ef(enabler), std::vector<F>(initial_state.begin(), initial_state.end()));
+        eval.add_to_relation(REL_POSEIDON2, eval.ef(enabler), {state[0]});
+        eval.finalize_logup_in_pairs();
+    }
+    template <class T>
+    void write_trace(T& t) const {
+        typedef decltype(t.f_const(0)) F;
+        const Poseidon2Constants& k = poseidon2_constants();
+        int c = 0;
+        F enabler = t.enabler();
+        t.out(c++, enabler);
+        std::array<F, 16> state = {enabler, enabler, enabler, enabler, enabler, enabler, enabler, enabler,
+                                   enabler, enabler, enabler, enabler, enabler, enabler, enabler, enabler};
+        for (int i = 0; i < 16; i++) {
+            state[i] = t.in(i);
+            t.out(c++, state[i]);
+        }
+        auto mulc = [&](F x, u32 cst) { return x * t.f_const(cst); };
+        auto full_round = [&](int r) {
+            for (int i = 0; i < 16; i++) state[i] = state[i] + t.f_const(k.external[r][i]);
+            std::array<F, 16> round_input = state;
+            for (int i = 0; i < 16; i++) state[i] = state[i] * state[i];
+            for (int i = 0; i < 16; i++) t.out(c++, state[i]);
+            for (int i = 0; i < 16; i++) state[i] = state[i] * state[i];
+            for (int i = 0; i < 16; i++) t.out(c++, state[i]);
+            for (int i = 0; i < 16; i++) state[i] = state[i] * round_input[i];
+            poseidon2_external_matrix(state);
+            for (int i = 0; i < 16; i++) t.out(c++, state[i]);
+        };
+        poseidon2_external_matrix(state);
+        for (int r = 0; r < POSEIDON2_FULL_ROUNDS / 2; r++) full_round(r);
+        for (int r = 0; r < POSEIDON2_PARTIAL_ROUNDS; r++) {
+            state[0] = state[0] + t.f_const(k.internal[r]);
+            F round_input = state[0];
+            state[0] = state[0] * state[0];
+            t.out(c++, state[0]);
+            state[0] = state[0] * state[0];
+            t.out(c++, state[0]);
+            state[0] = round_input * state[0];
+            t.out(c++, state[0]);
+            poseidon2_internal_matrix(state, mulc);
+        }
+        for (int r = 0; r < POSEIDON2_FULL_ROUNDS / 2; r++) full_round(POSEIDON2_FULL_ROUNDS / 2 + r);
     }
 };
 

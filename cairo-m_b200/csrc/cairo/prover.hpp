@@ -170,7 +170,8 @@ inline std::vector<std::string> cairo_component_names() {
 #define CM31_X(E) names.push_back(E::name());
     CM31_OPCODE_EVALS(CM31_X)
 #undef CM31_X
-    for (const char* n : {"memory", "clock_update", "range_check_8", "range_check_16", "range_check_20", "bitwise"}) names.push_back(n);
+    // components/mod.rs:77-104: opcodes, memory, merkle, clock_update, poseidon2, range checks, bitwise
+    for (const char* n : {"memory", "merkle", "clock_update", "poseidon2", "range_check_8", "range_check_16", "range_check_20", "bitwise"}) names.push_back(n);
     return names;
 }
 inline size_t n_opcode_components() {
@@ -197,7 +198,9 @@ struct CairoComponents {
     CM31_OPCODE_EVALS(CM31_X)
 #undef CM31_X
     std::unique_ptr<Comp<MemoryEval>> memory;
+    std::unique_ptr<Comp<MerkleEval>> merkle;
     std::unique_ptr<Comp<ClockUpdateEval>> clock_update;
+    std::unique_ptr<Comp<Poseidon2Eval>> poseidon2;
     std::unique_ptr<Comp<RangeCheckEval>> rc8, rc16, rc20;
     std::unique_ptr<Comp<BitwiseEval>> bitwise;
 
@@ -213,7 +216,9 @@ struct CairoComponents {
         CM31_OPCODE_EVALS(CM31_X)
 #undef CM31_X
         memory.reset(new Comp<MemoryEval>(MemoryEval{base(ls.at(i++))}, rel));
+        merkle.reset(new Comp<MerkleEval>(MerkleEval{base(ls.at(i++))}, rel));
         clock_update.reset(new Comp<ClockUpdateEval>(ClockUpdateEval{base(ls.at(i++))}, rel));
+        poseidon2.reset(new Comp<Poseidon2Eval>(Poseidon2Eval{base(ls.at(i++))}, rel));
         rc8.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls.at(i)), REL_RC8}, rel));
         rc16.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls.at(i + 1)), REL_RC16}, rel));
         rc20.reset(new Comp<RangeCheckEval>(RangeCheckEval{base(ls.at(i + 2)), REL_RC20}, rel));
@@ -225,7 +230,9 @@ struct CairoComponents {
         CM31_OPCODE_EVALS(CM31_X)
 #undef CM31_X
         fn(*memory);
+        fn(*merkle);
         fn(*clock_update);
+        fn(*poseidon2);
         fn(*rc8);
         fn(*rc16);
         fn(*rc20);
@@ -264,7 +271,7 @@ struct StagedInput {
     size_t n_accesses = 0;
     u32 accesses_mark = 0;
     std::vector<Rows> opcode;  // one per opcode component, CM31_OPCODE_EVALS order
-    Rows memory, clock_update;
+    Rows memory, merkle, clock_update, poseidon2;
     size_t bytes = 0;  // total bytes staged
 };
 
@@ -313,6 +320,22 @@ StagedInput<Impl> stage_input(const ProverInput& input) {
         st.memory.words = Impl::upload_words(rows.data(), rows.size());
         st.bytes += rows.size() * 4;
     }
+    {  // merkle (components/merkle.rs:82-104: initial tree then final tree, each node with its tree's root) and the
+       // poseidon2 inputs derived from the same nodes (adapter/mod.rs:165-174: state = [left, right, 0, ..])
+        std::vector<u32> rows, states;
+        for (const MerkleNode& nd : input.merkle_nodes) {
+            for (u32 w : {nd.index, nd.depth, nd.left_value, nd.right_value, nd.parent_value, nd.left_multiplicity, nd.right_multiplicity,
+                          nd.parent_multiplicity, nd.root})
+                rows.push_back(w);
+            states.push_back(nd.left_value);
+            states.push_back(nd.right_value);
+            for (int k = 2; k < POSEIDON2_T; k++) states.push_back(0);
+        }
+        st.merkle.n_real = st.poseidon2.n_real = input.merkle_nodes.size();
+        st.merkle.words = Impl::upload_words(rows.data(), rows.size());
+        st.poseidon2.words = Impl::upload_words(states.data(), states.size());
+        st.bytes += (rows.size() + states.size()) * 4;
+    }
     {  // clock_update (components/clock_update.rs:70-160)
         std::vector<u32> rows;
         for (const ClockUpdateRow& r : input.clock_update_data)
@@ -332,11 +355,12 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     Blake2sChannel channel;
     pcs_config.mix_into(channel);
 
-    // trace_log_size (prover.rs:38-53; the merkle-tree term is absent with the merkle component)
+    // trace_log_size (prover.rs:38-53)
     size_t max_rows = 1;
     for (auto& r : staged.opcode) max_rows = std::max(max_rows, r.n_real);
     u32 trace_log_size = std::max(PREPROCESSED_TRACE_LOG_SIZE, padded_log_size(max_rows));
     trace_log_size = std::max(trace_log_size, padded_log_size(staged.memory.n_real));
+    trace_log_size = std::max(trace_log_size, padded_log_size(staged.merkle.n_real));
     typename B::Twiddles twiddles;
     B::precompute_twiddles(trace_log_size + pcs_config.fri_config.log_blowup_factor + 2, twiddles);
     CommitmentSchemeProver<B> commitment_scheme(pcs_config, &twiddles);
@@ -397,6 +421,15 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         traces.push_back(Impl::template write_trace<MemoryEval>(eval, inputs, (u32)staged.memory.n_real));
     }
     {
+        u32 ls = padded_log_size(staged.merkle.n_real);
+        B::lane(ls);
+        std::vector<Col> inputs = Impl::unpack_rows(staged.merkle.words, staged.merkle.n_real, 9, ls);
+        MerkleEval eval;
+        eval.log_size_ = ls;
+        log_sizes.push_back(ls);
+        traces.push_back(Impl::template write_trace<MerkleEval>(eval, inputs, (u32)staged.merkle.n_real));
+    }
+    {
         u32 ls = padded_log_size(staged.clock_update.n_real);
         B::lane(ls);
         std::vector<Col> inputs = Impl::unpack_rows(staged.clock_update.words, staged.clock_update.n_real, 6, ls);
@@ -404,6 +437,15 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         eval.log_size_ = ls;
         log_sizes.push_back(ls);
         traces.push_back(Impl::template write_trace<ClockUpdateEval>(eval, inputs, (u32)staged.clock_update.n_real));
+    }
+    {
+        u32 ls = padded_log_size(staged.poseidon2.n_real);
+        B::lane(ls);
+        std::vector<Col> inputs = Impl::unpack_rows(staged.poseidon2.words, staged.poseidon2.n_real, POSEIDON2_T, ls);
+        Poseidon2Eval eval;
+        eval.log_size_ = ls;
+        log_sizes.push_back(ls);
+        traces.push_back(Impl::template write_trace<Poseidon2Eval>(eval, inputs, (u32)staged.poseidon2.n_real));
     }
     B::lanes_join();
     // range-check multiplicities: histogram of every value the opcode components look up

@@ -12,8 +12,8 @@
 //   import_internal         crates/prover/src/adapter/mod.rs:97-193
 // Differences, by design: boundary-memory rows are emitted in ascending address order (the
 // reference iterates two std HashMaps, i.e. in a per-run random order, components/memory.rs:105-109),
-// and the Poseidon2 memory Merkle roots are placeholders (0) until the merkle/poseidon2 components
-// land.
+// and the Poseidon2 ROUND CONSTANTS are placeholders (csrc/cairo/poseidon2.hpp): the memory roots are
+// real Merkle roots under that placeholder permutation.
 #pragma once
 #include <cstdint>
 #include <map>
@@ -41,6 +41,9 @@ struct ClockUpdateRow {
     u32 address, prev_clk;
     u32 value[4];
 };
+struct MerkleNode {  // adapter::merkle::NodeData::to_m31_array (crates/prover/src/adapter/merkle.rs:84-123) + the tree's root
+    u32 index, depth, left_value, right_value, parent_value, left_multiplicity, right_multiplicity, parent_multiplicity, root;
+};
 struct PublicRanges {
     u32 program_start = 0, program_end = 0, input_start = 0, input_end = 0, output_start = 0, output_end = 0;
 };
@@ -56,6 +59,7 @@ struct ProverInput {
     std::vector<ClockUpdateRow> clock_update_data;
     PublicRanges public_ranges;
     u32 initial_root = 0, final_root = 0;
+    std::vector<MerkleNode> merkle_nodes;  // initial tree then final tree (components/merkle.rs:82-104)
     size_t n_steps = 0;
 };
 
@@ -588,6 +592,57 @@ class MemoryModel {  // adapter::memory::Memory with dense address-indexed stora
     }
 };
 
+// build_partial_merkle_tree (crates/prover/src/adapter/merkle.rs:163-258): leaves = the 4 M31 words of every present
+// cell at depth 30 (multiplicity 2 inside the public ranges of the tree's side, else 1); per depth 30..1, pairs in ascending
+// index order, a missing sibling is the default hash of that depth with multiplicity 0; parents get multiplicity 1.
+inline const std::vector<u32>& poseidon2_default_hashes() {  // Poseidon2Hash::default_hashes (poseidon2.rs:35-56)
+    static const std::vector<u32> d = [] {
+        std::vector<u32> v(TREE_HEIGHT + 1, 0);
+        for (int depth = (int)TREE_HEIGHT - 1; depth >= 0; depth--) v[depth] = poseidon2_hash(v[depth + 1], v[depth + 1]);
+        return v;
+    }();
+    return d;
+}
+struct MerkleLeafCell {
+    u32 address;
+    u32 value[4];
+};
+inline u32 build_partial_merkle_tree(const std::vector<MerkleLeafCell>& cells, bool initial_tree, const PublicRanges& r,
+                                     std::vector<MerkleNode>& nodes_out) {
+    if (cells.empty()) throw std::runtime_error("adapter: empty memory has no Merkle root");
+    struct Val {
+        u32 value, multiplicity;
+    };
+    std::map<u32, Val> cur;  // ordered: the reference sorts the indices of every depth
+    for (const MerkleLeafCell& c : cells) {
+        if (c.address >= (1u << 28)) throw std::runtime_error("adapter: address outside the 2^28-cell memory");
+        bool is_public = initial_tree ? ((c.address >= r.program_start && c.address < r.program_end) || (c.address >= r.input_start && c.address < r.input_end))
+                                      : (c.address >= r.output_start && c.address < r.output_end);
+        for (u32 k = 0; k < 4; k++) cur[(c.address << 2) + k] = Val{c.value[k], is_public ? 2u : 1u};
+    }
+    const std::vector<u32>& defaults = poseidon2_default_hashes();
+    size_t first = nodes_out.size();
+    for (u32 depth = TREE_HEIGHT; depth >= 1; depth--) {
+        std::map<u32, Val> parents;
+        for (auto it = cur.begin(); it != cur.end(); ++it) {
+            u32 index = it->first, left_index = index & ~1u, right_index = left_index | 1u;
+            if (parents.count(index >> 1)) continue;  // the pair was processed with its left sibling
+            auto l = cur.find(left_index), rr = cur.find(right_index);
+            Val left = l != cur.end() ? l->second : Val{defaults[depth], 0u};
+            Val right = rr != cur.end() ? rr->second : Val{defaults[depth], 0u};
+            Val parent{poseidon2_hash(left.value, right.value), 1u};
+            nodes_out.push_back(MerkleNode{left_index, depth, left.value, right.value, parent.value, left.multiplicity, right.multiplicity,
+                                           parent.multiplicity, 0u});
+            parents[index >> 1] = parent;
+        }
+        cur.swap(parents);
+    }
+    if (cur.size() != 1) throw std::logic_error("adapter: Merkle tree did not reduce to one root");
+    u32 root = cur.begin()->second.value;
+    for (size_t i = first; i < nodes_out.size(); i++) nodes_out[i].root = root;
+    return root;
+}
+
 inline ProverInput import_from_vm(const VmTrace& vm) {
     ProverInput in;
     if (vm.trace.size() < 2) throw std::runtime_error("adapter: empty trace");
@@ -645,6 +700,15 @@ inline ProverInput import_from_vm(const VmTrace& vm) {
             out.push_back(r);
         }
     };
+    // memory commitments (adapter/mod.rs:152-174): partial Poseidon2 Merkle trees of the initial and the final memory
+    auto leaves = [&](const std::vector<MemoryModel::Cell>& cells) {
+        std::vector<MerkleLeafCell> v;
+        for (size_t a = 0; a < cells.size(); a++)
+            if (cells[a].present) v.push_back(MerkleLeafCell{(u32)a, {cells[a].value.v[0], cells[a].value.v[1], cells[a].value.v[2], cells[a].value.v[3]}});
+        return v;
+    };
+    in.initial_root = build_partial_merkle_tree(leaves(memory.initial), true, vm.public_ranges, in.merkle_nodes);
+    in.final_root = build_partial_merkle_tree(leaves(memory.final_), false, vm.public_ranges, in.merkle_nodes);
     dump(memory.initial, in.initial_root, in.initial_memory);
     dump(memory.final_, in.final_root, in.final_memory);
     return in;

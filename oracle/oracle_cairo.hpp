@@ -142,8 +142,9 @@ struct OracleAirImpl {
     }
 };
 
-// verify_cairo_m (verifier.rs:17-95) without the closing logup-sum check, which needs the
-// merkle/poseidon2 components (see logup_residual below).
+inline QM31 logup_residual(const cm31::CairoProof& proof, const cm31::ProverInput& input);
+
+// verify_cairo_m (verifier.rs:17-95), closing logup-sum check included (verifier.rs:84-92: InvalidLogupSum).
 inline void verify_cairo_m(const cm31::CairoProof& proof, cm31::PcsConfig pcs_config) {
     OChannel channel;
     channel.mix_u64(pcs_config.pow_bits);
@@ -215,13 +216,13 @@ inline void verify_cairo_m(const cm31::CairoProof& proof, cm31::PcsConfig pcs_co
     cm31::TraceLocationAllocator alloc(cm31::cairo_preprocessed_ids());
     components.allocate(alloc);
     verify(components.provers(), channel, cs, proof.stark_proof);
+    if (!(logup_residual(proof, cm31::ProverInput()) == QM31::zero())) throw VerificationError("InvalidLogupSum");
 }
 
 // Logup balance (InteractionClaim::claimed_sum, components/mod.rs:288-302 + public_data.rs:287-399):
 //   Σ claimed sums + public-data sum == 0.
-// The Merkle relation is only emitted (memory.rs:332-360) in this round's component set, so the
-// leaf emissions of the private boundary memory are added back explicitly; every other relation
-// (Registers, Memory, RangeCheck20) must balance exactly.
+// Every relation must balance exactly (the Merkle / Poseidon2 relations through the merkle and poseidon2 components,
+// under the placeholder Poseidon2 constants of csrc/cairo/poseidon2.hpp).
 inline QM31 logup_residual(const cm31::CairoProof& proof, const cm31::ProverInput& input) {
     // replay the transcript up to Relations::draw
     OChannel channel;
@@ -288,11 +289,19 @@ inline QM31 logup_residual(const cm31::CairoProof& proof, const cm31::ProverInpu
     add_public(pd.program, true);
     add_public(pd.input, true);
     add_public(pd.output, false);
-    // add back the (unconsumed) Merkle leaf emissions of the memory component
-    for (const std::vector<cm31::MemoryRow>* v : {&input.initial_memory, &input.final_memory})
-        for (const cm31::MemoryRow& r : *v)
+    // public_data.rs:307-321: the two roots are consumed (index 0, depth 0, value = root, tree = root)
+    sum = sum + rel[cm31::REL_MERKLE].combine({M31(0), M31(0), m(pd.initial_root), m(pd.initial_root)}).inverse();
+    sum = sum + rel[cm31::REL_MERKLE].combine({M31(0), M31(0), m(pd.final_root), m(pd.final_root)}).inverse();
+    // public_data.rs:323-382: every public cell also takes its four leaves out of the tree of its side
+    auto public_leaves = [&](const std::vector<cm31::PublicEntry>& es, u32 root) {
+        for (const cm31::PublicEntry& e : es)
             for (u32 k = 0; k < 4; k++)
-                sum = sum + rel[cm31::REL_MERKLE].combine({m(r.address) * M31(4) + M31((u64)k), M31((u64)cm31::TREE_HEIGHT), m(r.value[k]), m(r.root)}).inverse();
+                sum = sum - rel[cm31::REL_MERKLE].combine({m(e.addr) * M31(4) + M31((u64)k), M31((u64)cm31::TREE_HEIGHT), m(e.value[k]), m(root)}).inverse();
+    };
+    public_leaves(pd.program, pd.initial_root);
+    public_leaves(pd.input, pd.initial_root);
+    public_leaves(pd.output, pd.final_root);
+    (void)input;
     return sum;
 }
 

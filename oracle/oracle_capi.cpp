@@ -306,4 +306,81 @@ int orc_program_logup_residual(u32 program_id, u32 n, const uint8_t* proof_bytes
     }
 }
 
+// Poseidon2 permutation of csrc/cairo/poseidon2.hpp (PLACEHOLDER constants) -- the reference KAT cannot hold with them
+int orc_poseidon2_permutation(const u32* in16, u32* out16) {
+    std::array<u32, 16> in;
+    for (int i = 0; i < 16; i++) in[i] = in16[i];
+    std::array<u32, 16> out = cm31::poseidon2_permutation(in);
+    for (int i = 0; i < 16; i++) out16[i] = out[i];
+    return 0;
+}
+// The scenarios of the reference's adapter/merkle.rs tests (:262-424) on build_partial_merkle_tree; 0 = all hold.
+int orc_merkle_selftest(void) {
+    using namespace cm31;
+    try {
+        PublicRanges none;
+        auto find = [](const std::vector<MerkleNode>& t, u32 index, u32 depth) -> const MerkleNode* {
+            for (auto& n : t)
+                if (n.index == index && n.depth == depth) return &n;
+            return nullptr;
+        };
+        {  // empty memory: no tree (here: refused)
+            std::vector<MerkleNode> t;
+            bool threw = false;
+            try {
+                build_partial_merkle_tree({}, true, none, t);
+            } catch (const std::exception&) {
+                threw = true;
+            }
+            if (!threw || !t.empty()) return 1;
+        }
+        {  // single element: one node per depth 30..1, every parent = hash(left, right), the last parent is the root
+            std::vector<MerkleNode> t;
+            u32 root = build_partial_merkle_tree({MerkleLeafCell{5, {42, 0, 0, 0}}}, true, none, t);
+            if (t.size() != 2 + 29) return 2;  // two leaf pairs at depth 30, then one node per depth 29..1
+            for (auto& n : t)
+                if (n.parent_value != poseidon2_hash(n.left_value, n.right_value) || n.root != root) return 3;
+            if (t.back().depth != 1 || t.back().parent_value != root) return 4;
+        }
+        {  // two cells: leaves 0..3 and 4..7
+            std::vector<MerkleNode> t;
+            build_partial_merkle_tree({MerkleLeafCell{0, {10, 11, 12, 13}}, MerkleLeafCell{1, {20, 21, 22, 23}}}, true, none, t);
+            const MerkleNode* n = find(t, 0, 30);
+            if (!n || n->left_value != 10 || n->right_value != 11) return 5;
+            n = find(t, 2, 30);
+            if (!n || n->left_value != 12 || n->right_value != 13) return 6;
+            n = find(t, 4, 30);
+            if (!n || n->left_value != 20 || n->right_value != 21) return 7;
+            n = find(t, 0, 29);  // parents of (0,1) and (2,3) meet at depth 29, both real nodes (multiplicity 1)
+            if (!n || n->left_multiplicity != 1 || n->right_multiplicity != 1) return 8;
+        }
+        {  // addresses at both ends: depth range 1..30, missing siblings are default hashes with multiplicity 0
+            std::vector<MerkleNode> t;
+            build_partial_merkle_tree({MerkleLeafCell{0, {1, 0, 0, 0}}, MerkleLeafCell{(1u << 28) - 1, {2, 0, 0, 0}}}, true, none, t);
+            u32 min_depth = 99, max_depth = 0;
+            for (auto& n : t) {
+                min_depth = std::min(min_depth, n.depth);
+                max_depth = std::max(max_depth, n.depth);
+            }
+            if (min_depth != 1 || max_depth != TREE_HEIGHT) return 9;
+            const MerkleNode* n = find(t, 0, 28);
+            if (!n || n->right_multiplicity != 0 || n->right_value != poseidon2_default_hashes()[28]) return 10;
+        }
+        {  // public ranges: multiplicity 2 for program / input cells of the initial tree, output cells of the final tree
+            PublicRanges r;
+            r.program_start = 0, r.program_end = 1, r.output_start = 7, r.output_end = 8;
+            std::vector<MerkleNode> ti, tf;
+            std::vector<MerkleLeafCell> cells = {MerkleLeafCell{0, {1, 2, 3, 4}}, MerkleLeafCell{7, {5, 6, 7, 8}}};
+            build_partial_merkle_tree(cells, true, r, ti);
+            build_partial_merkle_tree(cells, false, r, tf);
+            if (find(ti, 0, 30)->left_multiplicity != 2 || find(ti, 28, 30)->left_multiplicity != 1) return 11;
+            if (find(tf, 0, 30)->left_multiplicity != 1 || find(tf, 28, 30)->left_multiplicity != 2) return 12;
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_orc_err = e.what();
+        return -1;
+    }
+}
+
 }  // extern "C"

@@ -97,3 +97,10 @@ def u32_mix_expected(n):
         x = (b + r) & M
         y = (y + 2) & M
     return x & 0xFFFF
+
+
+def corrupt_first_claimed_sum(proof: bytes) -> bytes:
+    """Flips one bit of the first component's claimed sum (proof blob: u64 n, n x u32 log sizes, u64 n, n x QM31 sums, ...)."""
+    n = int.from_bytes(proof[:8], "little")
+    off = 8 + 4 * n + 8
+    return proof[:off] + bytes([proof[off] ^ 1]) + proof[off + 1:]

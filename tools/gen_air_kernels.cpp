@@ -151,7 +151,9 @@ int main(int argc, char** argv) {
     CM31_OPCODE_EVALS(CM31_X)
 #undef CM31_X
     component(outdir, make<MemoryEval>(), acc);
+    component(outdir, make<MerkleEval>(), acc);
     component(outdir, make<ClockUpdateEval>(), acc);
+    component(outdir, make<Poseidon2Eval>(), acc);
     {
         RangeCheckEval e;
         e.log_size_ = 20;
