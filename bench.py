@@ -190,6 +190,67 @@ def dist_selftest(rank: int, world: int):
         dist.destroy_process_group()
 
 
+def measure_adapter(cm, lib, torch, program_id, n, k_steps, vm_steps, proof_buf, cap, proof_len, tm):
+    t0 = time.perf_counter()
+    vt = C.c_void_p()
+    cm.check(lib.cm31_vm_trace_create(C.c_uint32(program_id), C.c_uint32(n), C.byref(vt)))
+    vm_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    hh = C.c_void_p()
+    cm.check(lib.cm31_program_input_create(C.c_uint32(program_id), C.c_uint32(n), C.byref(hh)))  # VM + host adapter
+    host_adapter_ms = max(0.0, (time.perf_counter() - t0) - vm_s) * 1e3
+    cm.check(lib.cm31_input_destroy(hh))
+    info = (C.c_uint64 * 4)()
+    cm.check(lib.cm31_vm_trace_info(vt, info))
+    n_trace, n_mem, n_init = int(info[0]), int(info[1]), int(info[2])
+    pt, pm, pi = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
+    ranges = (C.c_uint32 * 6)()
+    cm.check(lib.cm31_vm_trace_data(vt, C.byref(pt), C.byref(pm), C.byref(pi), ranges))
+    import numpy as np
+
+    def pinned(ptr, words):  # the logs in page-locked host memory, as a runner would hand them over
+        a = np.ctypeslib.as_array(ptr, shape=(words,))
+        return torch.from_numpy(a.view(np.int32)).clone().pin_memory()
+
+    trace, mem, init = pinned(pt, 2 * n_trace), pinned(pm, 5 * n_mem), pinned(pi, 4 * n_init)
+    cm.check(lib.cm31_vm_trace_destroy(vt))
+    as_p = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_uint32))
+
+    def import_logs():
+        h = C.c_void_p()
+        cm.check(lib.cm31_adapter_import(as_p(trace), C.c_size_t(n_trace), as_p(mem), C.c_size_t(n_mem), as_p(init), C.c_size_t(n_init),
+                                         ranges, C.byref(h)))
+        return h
+
+    def timed(fn, reps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def import_only():
+        cm.check(lib.cm31_input_destroy(import_logs()))
+
+    def import_and_prove():
+        h = import_logs()
+        cm.check(lib.cm31_prove_cairo_m(h, 16, 80, proof_buf, C.c_size_t(cap), C.byref(proof_len), tm))
+        cm.check(lib.cm31_input_destroy(h))
+
+    import_and_prove()  # warm-up (allocator pools, CUB temp sizes)
+    device_ms = timed(import_only, max(3, k_steps // 2))
+    step_ms = timed(import_and_prove, k_steps)
+    log_bytes = 4 * (2 * n_trace + 5 * n_mem + 4 * n_init)
+    return {"device_adapter_ms": device_ms, "host_adapter_ms": host_adapter_ms, "host_vm_ms": vm_s * 1e3,
+            "h2d_bytes": log_bytes, "steps_per_s_device_adapter": vm_steps / (device_ms * 1e-3),
+            "from_logs_ms_per_step": step_ms, "from_logs_value": vm_steps / (step_ms * 1e-3),
+            "note": "device_adapter_ms = pinned runner logs -> resident prover input (H2D copy included); host_adapter_ms = the serial "
+                    "host restatement of import_from_runner_output on one core; from_logs = upload + device adapter + proof + proof bytes back"}
+
+
 # ------------------------------------------------------------------ CUDA arm
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
@@ -272,6 +333,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     proof_bytes = int(proof_len.value)
     cm.check(lib.cm31_input_destroy(h))
 
+    # ---- the step BEFORE the path: the runner's logs -> prover input.  Host restatement of the
+    # reference adapter (serial walk, csrc/cairo/vm.hpp) vs the device adapter (csrc/adapter.cu), and whole steps that
+    # START from the pinned logs: upload + device adapter + proof + proof bytes back.
+    adapter = None
+    if world == 1 and not args.no_adapter:
+        adapter = measure_adapter(cm, lib, torch, programs[args.program], n, args.steps, vm_steps, proof_buf, cap, proof_len, tm)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -336,6 +404,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "pipeline": "host->device copy of step i+1 overlaps the proof of step i (cm31_input_prefetch); K copies + K proofs timed",
                 "serial_ms_per_step": e2e_serial_ms / args.steps,
                 "serial_value": aggregate_value(world, vm_steps, args.steps, e2e_serial_ms)},
+        "adapter": adapter,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
@@ -355,6 +424,7 @@ def main():
     ap.add_argument("--log-steps", type=int, default=22, help="log2 of VM steps per proof (BASELINE metric: 2^22)")
     ap.add_argument("--cpu-sample-log", type=int, default=17, help="log2 VM steps of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-adapter", action="store_true", help="skip the adapter side measurement")
     ap.add_argument("--program", default="fibonacci_loop", choices=["fibonacci_loop", "array_sum", "u32_counter", "u32_mix"],
                     help="side measurements on the other hand-assembled programs (the headline is fibonacci_loop)")
     ap.add_argument("--iterations", type=int, default=0, help="program argument n (default: 2^log_steps / 8 for fibonacci_loop)")

@@ -275,6 +275,38 @@ struct StagedInput {
     size_t bytes = 0;  // total bytes staged
 };
 
+// The O(memory footprint) tables of a prover input: boundary-memory rows, Merkle nodes and the Poseidon2 states derived from
+// them.  Shared by stage_input (host adapter output) and the device adapter (cm31_adapter_import), whose per-step tables are
+// produced in HBM directly.
+template <class Impl>
+void stage_boundary_rows(const ProverInput& input, StagedInput<Impl>& st) {
+    {  // memory (components/memory.rs:93-195): initial rows then final rows
+        std::vector<u32> rows;
+        for (const std::vector<MemoryRow>* v : {&input.initial_memory, &input.final_memory})
+            for (const MemoryRow& r : *v)
+                for (u32 w : {r.address, r.clock, r.value[0], r.value[1], r.value[2], r.value[3], r.multiplicity, r.root}) rows.push_back(w);
+        st.memory.n_real = input.initial_memory.size() + input.final_memory.size();
+        st.memory.words = Impl::upload_words(rows.data(), rows.size());
+        st.bytes += rows.size() * 4;
+    }
+    {  // merkle (components/merkle.rs:82-104: initial tree then final tree, each node with its tree's root) and the
+       // poseidon2 inputs derived from the same nodes (adapter/mod.rs:165-174: state = [left, right, 0, ..])
+        std::vector<u32> rows, states;
+        for (const MerkleNode& nd : input.merkle_nodes) {
+            for (u32 w : {nd.index, nd.depth, nd.left_value, nd.right_value, nd.parent_value, nd.left_multiplicity, nd.right_multiplicity,
+                          nd.parent_multiplicity, nd.root})
+                rows.push_back(w);
+            states.push_back(nd.left_value);
+            states.push_back(nd.right_value);
+            for (int k = 2; k < POSEIDON2_T; k++) states.push_back(0);
+        }
+        st.merkle.n_real = st.poseidon2.n_real = input.merkle_nodes.size();
+        st.merkle.words = Impl::upload_words(rows.data(), rows.size());
+        st.poseidon2.words = Impl::upload_words(states.data(), states.size());
+        st.bytes += (rows.size() + states.size()) * 4;
+    }
+}
+
 template <class Impl>
 StagedInput<Impl> stage_input(const ProverInput& input) {
     StagedInput<Impl> st;
@@ -311,31 +343,7 @@ StagedInput<Impl> stage_input(const ProverInput& input) {
         }
         st.opcode[c].mark = Impl::staging_mark();
     }
-    {  // memory (components/memory.rs:93-195): initial rows then final rows
-        std::vector<u32> rows;
-        for (const std::vector<MemoryRow>* v : {&input.initial_memory, &input.final_memory})
-            for (const MemoryRow& r : *v)
-                for (u32 w : {r.address, r.clock, r.value[0], r.value[1], r.value[2], r.value[3], r.multiplicity, r.root}) rows.push_back(w);
-        st.memory.n_real = input.initial_memory.size() + input.final_memory.size();
-        st.memory.words = Impl::upload_words(rows.data(), rows.size());
-        st.bytes += rows.size() * 4;
-    }
-    {  // merkle (components/merkle.rs:82-104: initial tree then final tree, each node with its tree's root) and the
-       // poseidon2 inputs derived from the same nodes (adapter/mod.rs:165-174: state = [left, right, 0, ..])
-        std::vector<u32> rows, states;
-        for (const MerkleNode& nd : input.merkle_nodes) {
-            for (u32 w : {nd.index, nd.depth, nd.left_value, nd.right_value, nd.parent_value, nd.left_multiplicity, nd.right_multiplicity,
-                          nd.parent_multiplicity, nd.root})
-                rows.push_back(w);
-            states.push_back(nd.left_value);
-            states.push_back(nd.right_value);
-            for (int k = 2; k < POSEIDON2_T; k++) states.push_back(0);
-        }
-        st.merkle.n_real = st.poseidon2.n_real = input.merkle_nodes.size();
-        st.merkle.words = Impl::upload_words(rows.data(), rows.size());
-        st.poseidon2.words = Impl::upload_words(states.data(), states.size());
-        st.bytes += (rows.size() + states.size()) * 4;
-    }
+    stage_boundary_rows<Impl>(input, st);
     {  // clock_update (components/clock_update.rs:70-160)
         std::vector<u32> rows;
         for (const ClockUpdateRow& r : input.clock_update_data)

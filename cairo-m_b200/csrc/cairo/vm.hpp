@@ -643,6 +643,37 @@ inline u32 build_partial_merkle_tree(const std::vector<MerkleLeafCell>& cells, b
     return root;
 }
 
+// Tail of import_internal (adapter/mod.rs:134-174): boundary multiplicities, the partial Poseidon2 Merkle trees of the
+// initial and the final memory, the boundary rows in ascending address order.  Shared by the host adapter below and the
+// device adapter (csrc/adapter.cu), which fills `memory` from the distinct cells it resolved on the GPU.
+inline void finish_memory(MemoryModel& memory, const PublicRanges& ranges, ProverInput& in) {
+    memory.update_multiplicities(ranges);
+    in.public_ranges = ranges;
+    auto dump = [&](const std::vector<MemoryModel::Cell>& cells, u32 root, std::vector<MemoryRow>& out) {
+        for (size_t a = 0; a < cells.size(); a++) {
+            if (!cells[a].present) continue;
+            MemoryRow r;
+            r.address = (u32)a;
+            r.clock = cells[a].clock;
+            for (int k = 0; k < 4; k++) r.value[k] = cells[a].value.v[k];
+            r.multiplicity = cells[a].multiplicity;
+            r.root = root;
+            out.push_back(r);
+        }
+    };
+    // memory commitments (adapter/mod.rs:152-174): partial Poseidon2 Merkle trees of the initial and the final memory
+    auto leaves = [&](const std::vector<MemoryModel::Cell>& cells) {
+        std::vector<MerkleLeafCell> v;
+        for (size_t a = 0; a < cells.size(); a++)
+            if (cells[a].present) v.push_back(MerkleLeafCell{(u32)a, {cells[a].value.v[0], cells[a].value.v[1], cells[a].value.v[2], cells[a].value.v[3]}});
+        return v;
+    };
+    in.initial_root = build_partial_merkle_tree(leaves(memory.initial), true, ranges, in.merkle_nodes);
+    in.final_root = build_partial_merkle_tree(leaves(memory.final_), false, ranges, in.merkle_nodes);
+    dump(memory.initial, in.initial_root, in.initial_memory);
+    dump(memory.final_, in.final_root, in.final_memory);
+}
+
 inline ProverInput import_from_vm(const VmTrace& vm) {
     ProverInput in;
     if (vm.trace.size() < 2) throw std::runtime_error("adapter: empty trace");
@@ -685,32 +716,8 @@ inline ProverInput import_from_vm(const VmTrace& vm) {
         clock += 1;
     }
     in.n_steps = vm.trace.size() - 1;
-    memory.update_multiplicities(vm.public_ranges);
-    in.public_ranges = vm.public_ranges;
     in.clock_update_data = memory.clock_update_data;
-    auto dump = [&](const std::vector<MemoryModel::Cell>& cells, u32 root, std::vector<MemoryRow>& out) {
-        for (size_t a = 0; a < cells.size(); a++) {
-            if (!cells[a].present) continue;
-            MemoryRow r;
-            r.address = (u32)a;
-            r.clock = cells[a].clock;
-            for (int k = 0; k < 4; k++) r.value[k] = cells[a].value.v[k];
-            r.multiplicity = cells[a].multiplicity;
-            r.root = root;
-            out.push_back(r);
-        }
-    };
-    // memory commitments (adapter/mod.rs:152-174): partial Poseidon2 Merkle trees of the initial and the final memory
-    auto leaves = [&](const std::vector<MemoryModel::Cell>& cells) {
-        std::vector<MerkleLeafCell> v;
-        for (size_t a = 0; a < cells.size(); a++)
-            if (cells[a].present) v.push_back(MerkleLeafCell{(u32)a, {cells[a].value.v[0], cells[a].value.v[1], cells[a].value.v[2], cells[a].value.v[3]}});
-        return v;
-    };
-    in.initial_root = build_partial_merkle_tree(leaves(memory.initial), true, vm.public_ranges, in.merkle_nodes);
-    in.final_root = build_partial_merkle_tree(leaves(memory.final_), false, vm.public_ranges, in.merkle_nodes);
-    dump(memory.initial, in.initial_root, in.initial_memory);
-    dump(memory.final_, in.final_root, in.final_memory);
+    finish_memory(memory, vm.public_ranges, in);
     return in;
 }
 

@@ -47,6 +47,8 @@ struct cm31_prover_input {
     std::unique_ptr<cm31::StagedInput<cm31::CudaAirImpl>> staged;  // set by cm31_input_upload
     std::deque<std::unique_ptr<cm31::StagedInput<cm31::CudaAirImpl>>> prefetched;  // cm31_input_prefetch, consumed oldest first
     std::vector<void*> pinned;                                     // host ranges registered with CUDA
+    bool device_adapted = false;  // cm31_adapter_import: the per-step tables exist in HBM only (`staged`), not in `input`
+    uint64_t adapted_info[2] = {0, 0};  // data accesses, bytes of runner logs uploaded
     ~cm31_prover_input() {
         for (void* p : pinned) cudaHostUnregister(p);
     }
@@ -89,6 +91,7 @@ int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input
 //   kind 0: the value written by the middle StoreAddFpFp step;  kind 1: the second operand read by the middle StoreSubFpFp step
 int cm31_input_tamper(cm31_prover_input* h, uint32_t kind) {
     CM_REQUIRE(h != nullptr, "input_tamper: null handle");
+    CM_REQUIRE(!h->device_adapted, "input_tamper: not available on a device-adapted input");
     h->staged.reset();
     h->prefetched.clear();
     auto it = h->input.states_by_opcodes.find(kind == 0 ? OP_STORE_ADD_FP_FP : OP_STORE_SUB_FP_FP);
@@ -108,6 +111,7 @@ int cm31_input_destroy(cm31_prover_input* h) {
 int cm31_input_upload(cm31_prover_input* h) {
     try {
         CM_REQUIRE(h != nullptr, "input_upload: null handle");
+        if (h->device_adapted) return 0;  // already resident
         h->staged.reset(new StagedInput<CudaAirImpl>(stage_input<CudaAirImpl>(h->input)));
         return cm31_sync();
     } catch (const std::exception& e) {
@@ -117,6 +121,7 @@ int cm31_input_upload(cm31_prover_input* h) {
 }
 int cm31_input_release_device(cm31_prover_input* h) {
     CM_REQUIRE(h != nullptr, "input_release_device: null handle");
+    CM_REQUIRE(!h->device_adapted, "input_release_device: a device-adapted input has no host copy to fall back to");
     h->staged.reset();
     h->prefetched.clear();
     return 0;
@@ -124,6 +129,7 @@ int cm31_input_release_device(cm31_prover_input* h) {
 int cm31_input_prefetch(cm31_prover_input* h) {
     try {
         CM_REQUIRE(h != nullptr, "input_prefetch: null handle");
+        CM_REQUIRE(!h->device_adapted, "input_prefetch: a device-adapted input is already resident");
         CM_REQUIRE(h->prefetched.size() < 4, "input_prefetch: too many uploads in flight");
         h->prefetched.emplace_back(new StagedInput<CudaAirImpl>(stage_input<CudaAirImpl>(h->input)));
         return 0;
@@ -142,7 +148,181 @@ int cm31_input_info(const cm31_prover_input* h, uint64_t info[5]) {
     info[3] = h->return_value;
     info[4] = h->input.n_steps * sizeof(Bundle) + h->input.data_accesses.size() * sizeof(DataAccess) + info[2] * 32 +
               h->input.clock_update_data.size() * 24;
+    if (h->device_adapted) {
+        info[1] = h->adapted_info[0];
+        info[4] = h->adapted_info[1];
+    }
     return 0;
+}
+
+// ------------------------------------------------------------------ runner logs + device adapter
+}  // extern "C"
+struct cm31_vm_trace {
+    cm31::VmTrace vm;
+    std::vector<uint32_t> trace_words;  // IoTraceEntry {fp, pc} per entry (crates/prover/src/adapter/io.rs:38-43)
+};
+static_assert(sizeof(std::pair<cm31::u32, cm31::Word4>) == 20, "memory-trace entries must be IoMemoryEntry-shaped (5 words)");
+extern "C" {
+int cm31_adapter_scan(const uint32_t* trace_host, size_t n_trace, const uint32_t* mem_host, size_t n_mem, const uint32_t* init_host,
+                      size_t n_init, void** plan_out, uint64_t counts_out[67]);
+int cm31_adapter_emit(void* plan, uint32_t* const opcode_rows_dev[64], const uint64_t counts[67], uint32_t* accesses_dev,
+                      uint32_t* clock_update_dev, uint32_t* cells_host);
+int cm31_adapter_free(void* plan);
+
+// The runner's output for one of the built-in programs (what cairo-m-runner hands to import_from_runner_output):
+// execution trace, memory-access log, preloaded memory, public address ranges.
+int cm31_vm_trace_create(uint32_t program_id, uint32_t n, cm31_vm_trace** out) {
+    try {
+        CM_REQUIRE(out != nullptr, "vm_trace_create: null out");
+        std::unique_ptr<cm31_vm_trace> h(new cm31_vm_trace());
+        h->vm = run_program(program_by_id(program_id), n);
+        h->trace_words.reserve(h->vm.trace.size() * 2);
+        for (const Registers& r : h->vm.trace) {
+            h->trace_words.push_back(r.fp);
+            h->trace_words.push_back(r.pc);
+        }
+        *out = h.release();
+        return 0;
+    } catch (const std::exception& e) {
+        set_error(e.what());
+        return -2;
+    }
+}
+// info[0] = trace entries (steps + 1), [1] = memory-log entries, [2] = preloaded cells, [3] = return value
+int cm31_vm_trace_info(const cm31_vm_trace* h, uint64_t info[4]) {
+    CM_REQUIRE(h != nullptr && info != nullptr, "vm_trace_info: null argument");
+    info[0] = h->vm.trace.size();
+    info[1] = h->vm.memory_trace.size();
+    info[2] = h->vm.initial_memory.size();
+    info[3] = h->vm.return_value;
+    return 0;
+}
+int cm31_vm_trace_data(const cm31_vm_trace* h, const uint32_t** trace, const uint32_t** memory_trace, const uint32_t** initial_memory,
+                       uint32_t public_ranges[6]) {
+    CM_REQUIRE(h != nullptr, "vm_trace_data: null handle");
+    if (trace) *trace = h->trace_words.data();
+    if (memory_trace) *memory_trace = (const uint32_t*)h->vm.memory_trace.data();
+    if (initial_memory) *initial_memory = (const uint32_t*)h->vm.initial_memory.data();
+    if (public_ranges) {
+        const PublicRanges& r = h->vm.public_ranges;
+        uint32_t v[6] = {r.program_start, r.program_end, r.input_start, r.input_end, r.output_start, r.output_end};
+        memcpy(public_ranges, v, sizeof(v));
+    }
+    return 0;
+}
+int cm31_vm_trace_destroy(cm31_vm_trace* h) {
+    delete h;
+    return 0;
+}
+
+// Reads one table of the input resident in HBM back to the host (parity tests compare the host adapter's upload with the
+// device adapter's output word for word).  table 0 = data-access log, 1..26 = opcode components (CM31_OPCODE_EVALS order),
+// 100 = memory rows, 101 = merkle rows, 102 = clock-update rows, 103 = poseidon2 states.  n_words_out = words of REAL rows.
+int cm31_input_staged_words(const cm31_prover_input* h, uint32_t table, uint32_t* out, size_t cap_words, size_t* n_words_out) {
+    CM_REQUIRE(h != nullptr && n_words_out != nullptr, "input_staged_words: null argument");
+    CM_REQUIRE(h->staged != nullptr, "input_staged_words: the input is not resident (cm31_input_upload first)");
+    const StagedInput<CudaAirImpl>& st = *h->staged;
+    const DeviceCol* words = nullptr;
+    size_t n = 0;
+    if (table == 0) words = &st.accesses, n = st.n_accesses * 4;
+    else if (table >= 1 && table <= st.opcode.size()) words = &st.opcode[table - 1].words, n = st.opcode[table - 1].n_real * 12;
+    else if (table == 100) words = &st.memory.words, n = st.memory.n_real * 8;
+    else if (table == 101) words = &st.merkle.words, n = st.merkle.n_real * 9;
+    else if (table == 102) words = &st.clock_update.words, n = st.clock_update.n_real * 6;
+    else if (table == 103) words = &st.poseidon2.words, n = st.poseidon2.n_real * POSEIDON2_T;
+    CM_REQUIRE(words != nullptr, "input_staged_words: no such table");
+    *n_words_out = n;
+    if (out == nullptr || n == 0) return 0;
+    CM_REQUIRE(n <= cap_words, "input_staged_words: buffer too small");
+    if (int e = cm31_bg_fence()) return e;
+    if (int e = cm31_d2h(out, words->ptr(), n * 4)) return e;
+    return cm31_sync();
+}
+
+// import_from_runner_output (crates/prover/src/adapter/mod.rs:233-…) with the per-step work on the device (csrc/adapter.cu):
+// the returned handle is resident in HBM and proves with cm31_prove_cairo_m like an uploaded one.
+int cm31_adapter_import(const uint32_t* trace, size_t n_trace, const uint32_t* memory_trace, size_t n_mem, const uint32_t* initial_memory,
+                        size_t n_initial, const uint32_t public_ranges[6], cm31_prover_input** out) {
+    void* plan = nullptr;
+    try {
+        CM_REQUIRE(trace && memory_trace && initial_memory && public_ranges && out, "adapter_import: null argument");
+        uint64_t counts[67];
+        if (int e = cm31_adapter_scan(trace, n_trace, memory_trace, n_mem, initial_memory, n_initial, &plan, counts)) return e;
+        std::unique_ptr<cm31_prover_input> h(new cm31_prover_input());
+        h->device_adapted = true;
+        ProverInput& in = h->input;
+        in.initial_registers = Registers{trace[1], trace[0]};
+        in.final_registers = Registers{trace[2 * (n_trace - 1) + 1], trace[2 * (n_trace - 1)]};
+        in.n_steps = n_trace - 1;
+        typedef StagedInput<CudaAirImpl> Staged;
+        std::unique_ptr<Staged> st(new Staged());
+        st->n_accesses = counts[64];
+        st->accesses = CudaAirImpl::alloc_words(st->n_accesses * 4);
+        uint32_t* rows_by_opcode[64] = {nullptr};
+        auto opcode_rows = [&](const std::vector<u32>& opcodes) {  // one buffer per component, its opcodes' groups in list order
+            Staged::Rows r;
+            for (u32 op : opcodes) r.n_real += counts[op];
+            r.words = CudaAirImpl::alloc_words(r.n_real * 12);
+            size_t at = 0;
+            for (u32 op : opcodes) {
+                if (counts[op]) rows_by_opcode[op] = r.words.ptr() + 12 * at;
+                at += counts[op];
+            }
+            st->opcode.push_back(std::move(r));
+        };
+#define CM31_X(E) opcode_rows(E::opcodes());
+        CM31_OPCODE_EVALS(CM31_X)
+#undef CM31_X
+        st->clock_update.n_real = counts[65];
+        st->clock_update.words = CudaAirImpl::alloc_words(counts[65] * 6);
+        std::vector<uint32_t> cells(10 * counts[66] + 1);
+        int rc = cm31_adapter_emit(plan, rows_by_opcode, counts, st->accesses.ptr(), st->clock_update.words.ptr(), cells.data());
+        cm31_adapter_free(plan);
+        plan = nullptr;
+        if (rc) return rc;
+        // boundary memory from the distinct cells (Memory::push's bookkeeping of initial_memory / final_memory)
+        std::vector<Word4> preloaded(n_initial);
+        memcpy(preloaded.data(), initial_memory, n_initial * 16);
+        MemoryModel memory(preloaded);
+        for (size_t c = 0; c < counts[66]; c++) {
+            const uint32_t* w = &cells[10 * c];
+            uint32_t a = w[0];
+            if (a >= memory.final_.size()) {
+                memory.final_.resize((size_t)a + 1);
+                memory.initial.resize((size_t)a + 1);
+            }
+            if (memory.initial[a].present) memory.initial[a].multiplicity = 1;
+            else {
+                memory.initial[a].value = Word4{{w[1], w[2], w[3], w[4]}};
+                memory.initial[a].clock = 0;
+                memory.initial[a].multiplicity = 1;
+                memory.initial[a].present = true;
+            }
+            memory.final_[a].value = Word4{{w[5], w[6], w[7], w[8]}};
+            memory.final_[a].clock = w[9];
+            memory.final_[a].multiplicity = P - 1;
+            memory.final_[a].present = true;
+        }
+        PublicRanges ranges;
+        ranges.program_start = public_ranges[0];
+        ranges.program_end = public_ranges[1];
+        ranges.input_start = public_ranges[2];
+        ranges.input_end = public_ranges[3];
+        ranges.output_start = public_ranges[4];
+        ranges.output_end = public_ranges[5];
+        finish_memory(memory, ranges, in);
+        stage_boundary_rows<CudaAirImpl>(in, *st);
+        h->adapted_info[0] = counts[64];
+        h->adapted_info[1] = n_trace * 8 + n_mem * 20 + n_initial * 16;
+        h->staged = std::move(st);
+        if (int e = cm31_sync()) return e;
+        *out = h.release();
+        return 0;
+    } catch (const std::exception& e) {
+        if (plan) cm31_adapter_free(plan);
+        set_error(e.what());
+        return -2;
+    }
 }
 
 // prove_cairo_m::<Blake2sMerkleChannel> (crates/prover/src/prover.rs:23) on the CUDA backend.

@@ -244,6 +244,34 @@ int cm31_input_release_device(cm31_prover_input* h);
  * "ConstraintsNotSatisfied" (S/prover/src/core/prover/mod.rs:76-82) if the OODS check fails. */
 int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out,
                        size_t proof_cap, size_t* proof_len, double* timings_ms);
+/* ------------------------------------------------------------------ adapter on the device
+ * import_from_runner_output (P/src/adapter/mod.rs:233-…; import_internal :97-193; ExecutionBundleIterator and Memory::push,
+ * P/src/adapter/memory.rs:264-403, 470-…) with the per-step work done in HBM: the runner's logs go in, a prover input
+ * resident on the device comes out (prev clock / prev value of every access, clock-update rows, per-opcode bundles).
+ *   trace          : IoTraceEntry {fp, pc} x n_trace   (P/src/adapter/io.rs:38-43; one per step + the final state)
+ *   memory_trace   : IoMemoryEntry {address, value[4]} x n_mem, access order (io.rs:54-59)
+ *   initial_memory : preloaded cells, QM31 x n_initial, address = index (Segment::initial_memory)
+ *   public_ranges  : program [start, end), input [start, end), output [start, end) (PublicAddressRanges)
+ * Errors (non-zero + cm31_last_error): "empty trace", "invalid opcode", "unexpected end of the memory trace",
+ * "unexpected memory access" — VmImportError's cases (io.rs:12-36).  Stricter than the reference in one point: log entries
+ * left over after the last step are an error instead of being ignored. */
+int cm31_adapter_import(const uint32_t* trace, size_t n_trace, const uint32_t* memory_trace, size_t n_mem,
+                        const uint32_t* initial_memory, size_t n_initial, const uint32_t public_ranges[6],
+                        cm31_prover_input** out);
+/* One table of a resident input read back to the host (parity tests): table 0 = data-access log (4 words per access),
+ * 1..26 = opcode components in claim order (12 words per step), 100 = memory rows (8), 101 = merkle rows (9),
+ * 102 = clock-update rows (6), 103 = poseidon2 states (16).  out may be NULL to query the size. */
+int cm31_input_staged_words(const cm31_prover_input* h, uint32_t table, uint32_t* out, size_t cap_words, size_t* n_words_out);
+/* The runner's output for a built-in program (program_id as in cm31_program_input_create): the host VM only, no adapter. */
+typedef struct cm31_vm_trace cm31_vm_trace;
+int cm31_vm_trace_create(uint32_t program_id, uint32_t n, cm31_vm_trace** out);
+/* info[0] trace entries (steps + 1), [1] memory-log entries, [2] preloaded cells, [3] return value */
+int cm31_vm_trace_info(const cm31_vm_trace* h, uint64_t info[4]);
+/* pointers into the handle, laid out as cm31_adapter_import takes them */
+int cm31_vm_trace_data(const cm31_vm_trace* h, const uint32_t** trace, const uint32_t** memory_trace,
+                       const uint32_t** initial_memory, uint32_t public_ranges[6]);
+int cm31_vm_trace_destroy(cm31_vm_trace* h);
+
 /* S/examples/src/wide_fibonacci/mod.rs:22-43 — the bring-up AIR (parity tests only) */
 int cm31_prove_wide_fibonacci(uint32_t log_n_rows, uint32_t n_cols, uint32_t pow_bits, uint32_t n_queries,
                               uint8_t* proof_out, size_t proof_cap, size_t* proof_len);

@@ -59,6 +59,62 @@ class GpuFibInput:
             self.h = C.c_void_p()
 
 
+class VmTrace:
+    """The runner's output for a built-in program (host VM only): what import_from_runner_output consumes."""
+
+    def __init__(self, cm, program, n):
+        self.cm = cm
+        self.h = C.c_void_p()
+        cm.check(cm.lib().cm31_vm_trace_create(C.c_uint32(program), C.c_uint32(n), C.byref(self.h)))
+        info = (C.c_uint64 * 4)()
+        cm.check(cm.lib().cm31_vm_trace_info(self.h, info))
+        self.n_trace, self.n_mem, self.n_init, self.return_value = list(info)
+
+    def arrays(self):
+        """(trace {fp, pc} words, memory log {addr, value[4]} words, preloaded memory words, public ranges) as numpy copies."""
+        import numpy as np
+        pt, pm, pi = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
+        ranges = (C.c_uint32 * 6)()
+        self.cm.check(self.cm.lib().cm31_vm_trace_data(self.h, C.byref(pt), C.byref(pm), C.byref(pi), ranges))
+        trace = np.ctypeslib.as_array(pt, shape=(2 * self.n_trace,)).copy()
+        mem = np.ctypeslib.as_array(pm, shape=(5 * self.n_mem,)).copy()
+        init = np.ctypeslib.as_array(pi, shape=(4 * self.n_init,)).copy()
+        return trace, mem, init, np.array(list(ranges), dtype=np.uint32)
+
+    def close(self):
+        if self.h:
+            self.cm.lib().cm31_vm_trace_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def adapter_import(cm, trace, mem, init, ranges, handle_out):
+    """cm31_adapter_import on numpy u32 arrays; returns the status (the caller decides whether an error is expected)."""
+    import numpy as np
+    trace, mem, init, ranges = (np.ascontiguousarray(a, dtype=np.uint32) for a in (trace, mem, init, ranges))
+    as_p = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+    return cm.lib().cm31_adapter_import(as_p(trace), C.c_size_t(trace.size // 2), as_p(mem), C.c_size_t(mem.size // 5), as_p(init),
+                                        C.c_size_t(init.size // 4), as_p(ranges), C.byref(handle_out))
+
+
+class GpuAdaptedInput(GpuFibInput):
+    """Prover input produced by the DEVICE adapter from the runner's logs (resident in HBM)."""
+
+    def __init__(self, cm, n, program=FIB):
+        self.cm = cm
+        self.h = C.c_void_p()
+        vm = VmTrace(cm, program, n)
+        try:
+            self.logs = vm.arrays()
+            rv = vm.return_value
+        finally:
+            vm.close()
+        cm.check(adapter_import(cm, *self.logs, self.h))
+        info = (C.c_uint64 * 5)()
+        cm.check(cm.lib().cm31_input_info(self.h, info))
+        self.steps, self.accesses, self.memory_rows, _, self.h2d_bytes = list(info)
+        self.return_value = rv
+
+
 def fib_mod_p(n):
     a, b = 0, 1
     for _ in range(n):
