@@ -14,8 +14,9 @@
 //   1. one thread per STEP reads the opcode of the instruction at pc (preloaded program cell) -> number of log
 //      entries the step consumes (1-2 instruction words + its data accesses); an exclusive scan gives every
 //      step its offset into the memory log (the fetched word is then checked against the log itself);
-//   2. the log is sorted by address, stable in access order (LSD radix sort over the address bits in use):
-//      the predecessor of an access in the sorted order IS Memory::push's previous (clock, value) of that cell;
+//   2. the log is sorted by address, stable in access order (LSD radix sort over the address bits in use) with
+//      {access index, clock, value} as payload: the neighbouring element of the sorted order IS Memory::push's
+//      previous (clock, value) of that cell;
 //   3. one thread per sorted position resolves prev_clock / prev_value and the clock-update count
 //      (delta / RC20_LIMIT); a scan in ACCESS order places the clock-update rows where the reference pushes them;
 //   4. steps are stably partitioned by opcode (radix sort on the 6-bit opcode) = states_by_opcodes in execution
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) adapter_count_kernel(const uint2* __restr
 // ---- per step: check the fetched instruction against the log, emit sort keys (address) and the clock of every entry
 __global__ void __launch_bounds__(256) adapter_keys_kernel(const uint2* __restrict__ trace, u32 n_steps, const u32* __restrict__ mem, u32 n_mem,
                                                            const u32* __restrict__ opcode, const u32* __restrict__ off,
-                                                           const u32* __restrict__ cnt, u32* __restrict__ keys, u32* __restrict__ clk,
+                                                           const u32* __restrict__ cnt, u32* __restrict__ keys, uint4* __restrict__ pay,
                                                            u32* __restrict__ max_addr, u32* __restrict__ err) {
     u32 s = blockIdx.x * blockDim.x + threadIdx.x;
     u32 mx = 0;
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(256) adapter_keys_kernel(const uint2* __restri
             for (u32 k = 0; k < c; k++) {
                 u32 a = e[5 * k];
                 keys[o + k] = a;
-                clk[o + k] = s + 1;  // clock 0 is reserved for preloaded values
+                pay[o + k] = make_uint4(o + k, s + 1, e[5 * k + 1], 0u);  // access index, clock (0 is reserved for preloaded values), value limb 0
                 mx = max(mx, a);
             }
         }
@@ -106,52 +107,54 @@ __global__ void adapter_iota_kernel(u32* p, u32 n) {
 }
 
 // ---- 3. one thread per position of the address-sorted log: Memory::push's (prev_clock, prev_value) and the number of
-// clock-update rows; head[p] = 1 on the first access of a cell
-__device__ __forceinline__ void adapter_prev(u32 p, const u32* addr_sorted, const u32* perm, const u32* mem, const u32* clk,
-                                             const uint4* init, u32 n_init, bool& head, u32& pclk, u32& pv0) {
-    u32 a = addr_sorted[p], i = perm[p];
+// clock-update rows; head[p] = 1 on the first access of a cell.  The sort carries {access index, clock, value limb 0} as its
+// payload, so the predecessor is the neighbouring (coalesced) element: nothing is gathered through the permutation, and the
+// only scattered traffic is ONE 8-byte store per access (the first version gathered 4-byte words through the permutation
+// and scattered three: 4.0 GB of DRAM sectors for 0.6 GB of algorithmic bytes, profiles/full_adapter_resolve_kernel_r01e.md).
+__device__ __forceinline__ void adapter_prev(u32 p, const u32* addr_sorted, const uint4* pay, const uint4* init, u32 n_init, bool& head,
+                                             u32& pclk, u32& pv0) {
+    u32 a = addr_sorted[p];
     head = p == 0 || addr_sorted[p - 1] != a;
     if (!head) {
-        u32 j = perm[p - 1];
-        pclk = clk[j];
-        pv0 = mem[5 * (size_t)j + 1];
+        uint4 q = pay[p - 1];
+        pclk = q.y;
+        pv0 = q.z;
     } else if (a < n_init) {  // preloaded cell: (value, clock 0)
         pclk = 0;
         pv0 = __ldg(&init[a]).x;
     } else {  // first touch of a fresh cell: its own value at clock 0
         pclk = 0;
-        pv0 = mem[5 * (size_t)i + 1];
+        pv0 = pay[p].z;
     }
 }
-__global__ void __launch_bounds__(256) adapter_resolve_kernel(const u32* __restrict__ addr_sorted, const u32* __restrict__ perm, u32 n_mem,
-                                                              const u32* __restrict__ mem, const u32* __restrict__ clk,
-                                                              const uint4* __restrict__ init, u32 n_init, u32* __restrict__ prev_clock,
-                                                              u32* __restrict__ prev_val, u32* __restrict__ n_cu, u32* __restrict__ head_flag) {
+__global__ void __launch_bounds__(256) adapter_resolve_kernel(const u32* __restrict__ addr_sorted, const uint4* __restrict__ pay, u32 n_mem,
+                                                              const uint4* __restrict__ init, u32 n_init, uint2* __restrict__ prev,
+                                                              u32* __restrict__ n_cu, u32* __restrict__ head_flag) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_mem) return;
     bool head;
     u32 pclk, pv0;
-    adapter_prev(p, addr_sorted, perm, mem, clk, init, n_init, head, pclk, pv0);
-    u32 i = perm[p], clock = clk[i], steps = 0;
+    adapter_prev(p, addr_sorted, pay, init, n_init, head, pclk, pv0);
+    uint4 me = pay[p];
+    u32 i = me.x, clock = me.y, steps = 0;
     if (clock > pclk && clock - pclk > RC20_LIMIT) steps = (clock - pclk) / RC20_LIMIT;
-    prev_clock[i] = pclk + steps * RC20_LIMIT;  // < clock < P: no reduction needed
-    prev_val[i] = pv0;
-    n_cu[i] = steps;
+    prev[i] = make_uint2(pclk + steps * RC20_LIMIT, pv0);  // < clock < P: no reduction needed
+    if (steps) n_cu[i] = steps;                            // n_cu is zero-filled: rows are rare
     head_flag[p] = head ? 1u : 0u;
 }
 
 // ---- clock-update rows {address, prev_clk, initial value[4]} at the position the reference pushes them (access order)
-__global__ void __launch_bounds__(256) adapter_clock_update_kernel(const u32* __restrict__ addr_sorted, const u32* __restrict__ perm, u32 n_mem,
-                                                                   const u32* __restrict__ mem, const u32* __restrict__ clk,
-                                                                   const uint4* __restrict__ init, u32 n_init, const u32* __restrict__ n_cu,
-                                                                   const u32* __restrict__ cu_off, u32* __restrict__ rows) {
+__global__ void __launch_bounds__(256) adapter_clock_update_kernel(const u32* __restrict__ addr_sorted, const uint4* __restrict__ pay, u32 n_mem,
+                                                                   const u32* __restrict__ mem, const uint4* __restrict__ init, u32 n_init,
+                                                                   const u32* __restrict__ n_cu, const u32* __restrict__ cu_off,
+                                                                   u32* __restrict__ rows) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_mem) return;
-    u32 i = perm[p], steps = n_cu[i];
+    u32 i = pay[p].x, steps = n_cu[i];
     if (!steps) return;
     bool head;
     u32 pclk, pv0;
-    adapter_prev(p, addr_sorted, perm, mem, clk, init, n_init, head, pclk, pv0);
+    adapter_prev(p, addr_sorted, pay, init, n_init, head, pclk, pv0);
     u32 a = addr_sorted[p];
     uint4 v;
     if (a < n_init) v = __ldg(&init[a]);
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(256) adapter_clock_update_kernel(const u32* __
             if (addr_sorted[mid] < a) lo = mid + 1;
             else hi = mid;
         }
-        const u32* e = mem + 5 * (size_t)perm[lo];
+        const u32* e = mem + 5 * (size_t)pay[lo].x;
         v = make_uint4(e[1], e[2], e[3], e[4]);
     }
     u32* r = rows + 6 * (size_t)cu_off[i];
@@ -174,23 +177,24 @@ __global__ void __launch_bounds__(256) adapter_clock_update_kernel(const u32* __
 }
 
 // ---- distinct cells: {address, first value[4], last value[4], last clock}
-__global__ void __launch_bounds__(256) adapter_cells_kernel(const u32* __restrict__ addr_sorted, const u32* __restrict__ perm, u32 n_mem,
-                                                            const u32* __restrict__ mem, const u32* __restrict__ clk,
-                                                            const u32* __restrict__ head_incl, u32* __restrict__ cells) {
+__global__ void __launch_bounds__(256) adapter_cells_kernel(const u32* __restrict__ addr_sorted, const uint4* __restrict__ pay, u32 n_mem,
+                                                            const u32* __restrict__ mem, const u32* __restrict__ head_incl,
+                                                            u32* __restrict__ cells) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_mem) return;
     u32 a = addr_sorted[p];
     bool head = p == 0 || addr_sorted[p - 1] != a, tail = p + 1 == n_mem || addr_sorted[p + 1] != a;
     if (!head && !tail) return;
     u32* c = cells + 10 * (size_t)(head_incl[p] - 1);
-    const u32* e = mem + 5 * (size_t)perm[p];
+    uint4 me = pay[p];
+    const u32* e = mem + 5 * (size_t)me.x;
     if (head) {
         c[0] = a;
         c[1] = e[1]; c[2] = e[2]; c[3] = e[3]; c[4] = e[4];
     }
     if (tail) {
         c[5] = e[1]; c[6] = e[2]; c[7] = e[3]; c[8] = e[4];
-        c[9] = clk[perm[p]];
+        c[9] = me.y;
     }
 }
 
@@ -202,7 +206,7 @@ struct AdapterDest {
 __global__ void __launch_bounds__(256) adapter_bundles_kernel(const u32* __restrict__ steps_sorted, u32 n_steps, const uint2* __restrict__ trace,
                                                               const u32* __restrict__ opcode, const u32* __restrict__ off,
                                                               const u32* __restrict__ dstart, const u32* __restrict__ mem,
-                                                              const u32* __restrict__ prev_clock, const AdapterDest* __restrict__ dest) {
+                                                              const uint2* __restrict__ prev, const AdapterDest* __restrict__ dest) {
     u32 q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_steps) return;
     u32 s = steps_sorted[q], op = opcode[s], o = off[s];
@@ -215,21 +219,21 @@ __global__ void __launch_bounds__(256) adapter_bundles_kernel(const u32* __restr
     inst[4] = size > 4 ? e[6] : 0u;  // second QM31 word of the instruction, fetched at the same clock (memory.rs:317-339)
     inst[5] = size > 5 ? e[7] : 0u;
     uint4* out = (uint4*)(dest->base[op] + 12 * (size_t)(q - dest->start[op]));
-    out[0] = make_uint4(r.y, r.x, s + 1, prev_clock[o]);  // pc, fp, clock, inst_prev_clock
+    out[0] = make_uint4(r.y, r.x, s + 1, prev[o].x);  // pc, fp, clock, inst_prev_clock
     out[1] = make_uint4(inst[0], inst[1], inst[2], inst[3]);
     out[2] = make_uint4(inst[4], inst[5], dstart[s], (u32)c_ops.n_acc[op]);
 }
 // the global data-access log {address, prev_clock, prev_value, value}, in execution order (instruction fetches excluded)
 __global__ void __launch_bounds__(256) adapter_accesses_kernel(u32 n_steps, const u32* __restrict__ opcode, const u32* __restrict__ off,
                                                                const u32* __restrict__ dstart, const u32* __restrict__ mem,
-                                                               const u32* __restrict__ prev_clock, const u32* __restrict__ prev_val,
-                                                               uint4* __restrict__ accesses) {
+                                                               const uint2* __restrict__ prev, uint4* __restrict__ accesses) {
     u32 s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_steps) return;
     u32 op = opcode[s], n = c_ops.n_acc[op], i = off[s] + c_ops.n_inst[op], d = dstart[s];
     for (u32 k = 0; k < n; k++, i++) {
         const u32* e = mem + 5 * (size_t)i;
-        accesses[d + k] = make_uint4(e[0], prev_clock[i], prev_val[i], e[1]);
+        uint2 pr = prev[i];
+        accesses[d + k] = make_uint4(e[0], pr.x, pr.y, e[1]);
     }
 }
 
@@ -239,8 +243,10 @@ struct AdapterPlan {
     uint2* trace = nullptr;
     u32 *mem = nullptr, *opcode = nullptr, *cnt = nullptr, *off = nullptr, *ndata = nullptr, *dstart = nullptr;
     uint4* init = nullptr;
-    u32 *keys = nullptr, *clk = nullptr, *addr_sorted = nullptr, *iota = nullptr, *perm = nullptr, *steps_sorted = nullptr, *op_sorted = nullptr;
-    u32 *prev_clock = nullptr, *prev_val = nullptr, *n_cu = nullptr, *cu_off = nullptr, *head = nullptr, *head_incl = nullptr;
+    u32 *keys = nullptr, *addr_sorted = nullptr, *iota = nullptr, *steps_sorted = nullptr, *op_sorted = nullptr;
+    uint4 *pay = nullptr, *pay_sorted = nullptr;  // {access index, clock, value limb 0, -}: the sort's payload
+    uint2* prev = nullptr;                        // per access: {prev_clock, prev_value limb 0}
+    u32 *n_cu = nullptr, *cu_off = nullptr, *head = nullptr, *head_incl = nullptr;
     u32* small = nullptr;  // [0..63] hist, [64] err, [65] max address
     void* temp = nullptr;
     size_t temp_bytes = 0;
@@ -310,9 +316,9 @@ int cm31_adapter_scan(const uint32_t* trace_host, size_t n_trace, const uint32_t
     int e = 0;
     if ((e = P_.alloc(P_.trace, n_trace)) || (e = P_.alloc(P_.mem, 5 * n_mem)) || (e = P_.alloc(P_.init, n_init)) || (e = P_.alloc(P_.opcode, n)) ||
         (e = P_.alloc(P_.cnt, (size_t)n + 1)) || (e = P_.alloc(P_.off, (size_t)n + 1)) || (e = P_.alloc(P_.ndata, (size_t)n + 1)) ||
-        (e = P_.alloc(P_.dstart, (size_t)n + 1)) || (e = P_.alloc(P_.keys, M)) || (e = P_.alloc(P_.clk, M)) || (e = P_.alloc(P_.addr_sorted, M)) ||
-        (e = P_.alloc(P_.iota, std::max(M, n))) || (e = P_.alloc(P_.perm, M)) || (e = P_.alloc(P_.steps_sorted, n)) || (e = P_.alloc(P_.op_sorted, n)) ||
-        (e = P_.alloc(P_.prev_clock, M)) || (e = P_.alloc(P_.prev_val, M)) || (e = P_.alloc(P_.n_cu, (size_t)M + 1)) ||
+        (e = P_.alloc(P_.dstart, (size_t)n + 1)) || (e = P_.alloc(P_.keys, M)) || (e = P_.alloc(P_.pay, M)) || (e = P_.alloc(P_.addr_sorted, M)) ||
+        (e = P_.alloc(P_.iota, n)) || (e = P_.alloc(P_.pay_sorted, M)) || (e = P_.alloc(P_.steps_sorted, n)) || (e = P_.alloc(P_.op_sorted, n)) ||
+        (e = P_.alloc(P_.prev, M)) || (e = P_.alloc(P_.n_cu, (size_t)M + 1)) ||
         (e = P_.alloc(P_.cu_off, (size_t)M + 1)) || (e = P_.alloc(P_.head, M)) || (e = P_.alloc(P_.head_incl, M)) || (e = P_.alloc(P_.small, 68)))
         return e;
     // temp storage for the CUB calls below (the largest request)
@@ -321,7 +327,7 @@ int cm31_adapter_scan(const uint32_t* trace_host, size_t n_trace, const uint32_t
     need = std::max(need, t);
     cub::DeviceScan::InclusiveSum(nullptr, t, P_.head, P_.head_incl, (int)M, stream());
     need = std::max(need, t);
-    cub::DeviceRadixSort::SortPairs(nullptr, t, P_.keys, P_.addr_sorted, P_.iota, P_.perm, (int)M, 0, 32, stream());
+    cub::DeviceRadixSort::SortPairs(nullptr, t, P_.keys, P_.addr_sorted, P_.pay, P_.pay_sorted, (int)M, 0, 32, stream());
     need = std::max(need, t);
     cub::DeviceRadixSort::SortPairs(nullptr, t, P_.opcode, P_.op_sorted, P_.iota, P_.steps_sorted, (int)n, 0, 6, stream());
     need = std::max(need, t);
@@ -335,7 +341,7 @@ int cm31_adapter_scan(const uint32_t* trace_host, size_t n_trace, const uint32_t
     CM_CUDA(cudaMemsetAsync(P_.small, 0, 68 * 4, stream()));
     CM_CUDA(cudaMemsetAsync(P_.cnt + n, 0, 4, stream()));
     CM_CUDA(cudaMemsetAsync(P_.ndata + n, 0, 4, stream()));
-    CM_CUDA(cudaMemsetAsync(P_.n_cu + M, 0, 4, stream()));
+    CM_CUDA(cudaMemsetAsync(P_.n_cu, 0, ((size_t)M + 1) * 4, stream()));
     {
         ProfScope prof("adapter_count", 8ull * n + 12ull * n);
         adapter_count_kernel<<<grid_for(n), 256, 0, stream()>>>(P_.trace, n, P_.init, P_.n_init, P_.opcode, P_.cnt, P_.ndata, P_.small, P_.small + 64);
@@ -349,11 +355,11 @@ int cm31_adapter_scan(const uint32_t* trace_host, size_t n_trace, const uint32_t
         CM_CUDA(cub::DeviceScan::ExclusiveSum(P_.temp, tb, P_.ndata, P_.dstart, (int)(n + 1), stream()));
     }
     {
-        ProfScope prof("adapter_keys", 20ull * n + 4ull * M + 8ull * M);
-        adapter_keys_kernel<<<grid_for(n), 256, 0, stream()>>>(P_.trace, n, P_.mem, M, P_.opcode, P_.off, P_.cnt, P_.keys, P_.clk, P_.small + 65,
+        ProfScope prof("adapter_keys", 20ull * n + 8ull * M + 20ull * M, 2);
+        adapter_keys_kernel<<<grid_for(n), 256, 0, stream()>>>(P_.trace, n, P_.mem, M, P_.opcode, P_.off, P_.cnt, P_.keys, P_.pay, P_.small + 65,
                                                                P_.small + 64);
         CM_LAUNCH_CHECK();
-        adapter_iota_kernel<<<grid_for(std::max(M, n)), 256, 0, stream()>>>(P_.iota, std::max(M, n));
+        adapter_iota_kernel<<<grid_for(n), 256, 0, stream()>>>(P_.iota, n);
         CM_LAUNCH_CHECK();
     }
     u32 small[68], totals[2];
@@ -367,16 +373,15 @@ int cm31_adapter_scan(const uint32_t* trace_host, size_t n_trace, const uint32_t
     u32 addr_bits = 1;
     while (addr_bits < 32 && (small[65] >> addr_bits)) addr_bits++;
     {
-        ProfScope prof("adapter_sort", 16ull * M * ((addr_bits + 7) / 8) + 16ull * n, 0);
+        ProfScope prof("adapter_sort", 40ull * M * ((addr_bits + 7) / 8) + 16ull * n, 0);
         size_t tb = P_.temp_bytes;
-        CM_CUDA(cub::DeviceRadixSort::SortPairs(P_.temp, tb, P_.keys, P_.addr_sorted, P_.iota, P_.perm, (int)M, 0, (int)addr_bits, stream()));
+        CM_CUDA(cub::DeviceRadixSort::SortPairs(P_.temp, tb, P_.keys, P_.addr_sorted, P_.pay, P_.pay_sorted, (int)M, 0, (int)addr_bits, stream()));
         tb = P_.temp_bytes;
         CM_CUDA(cub::DeviceRadixSort::SortPairs(P_.temp, tb, P_.opcode, P_.op_sorted, P_.iota, P_.steps_sorted, (int)n, 0, 6, stream()));
     }
     {
-        ProfScope prof("adapter_resolve", 12ull * M + 20ull * M + 16ull * M);
-        adapter_resolve_kernel<<<grid_for(M), 256, 0, stream()>>>(P_.addr_sorted, P_.perm, M, P_.mem, P_.clk, P_.init, P_.n_init, P_.prev_clock,
-                                                                  P_.prev_val, P_.n_cu, P_.head);
+        ProfScope prof("adapter_resolve", 20ull * M + 12ull * M);
+        adapter_resolve_kernel<<<grid_for(M), 256, 0, stream()>>>(P_.addr_sorted, P_.pay_sorted, M, P_.init, P_.n_init, P_.prev, P_.n_cu, P_.head);
         CM_LAUNCH_CHECK();
     }
     {
@@ -421,20 +426,19 @@ int cm31_adapter_emit(void* plan, uint32_t* const opcode_rows_dev[64], const uin
     if (int e = dt.upload(&dest, sizeof(dest))) return e;
     {
         ProfScope prof("adapter_bundles", 8ull * n + 20ull * n + 48ull * n);
-        adapter_bundles_kernel<<<grid_for(n), 256, 0, stream()>>>(P_.steps_sorted, n, P_.trace, P_.opcode, P_.off, P_.dstart, P_.mem, P_.prev_clock,
+        adapter_bundles_kernel<<<grid_for(n), 256, 0, stream()>>>(P_.steps_sorted, n, P_.trace, P_.opcode, P_.off, P_.dstart, P_.mem, P_.prev,
                                                                   (const AdapterDest*)dt.d);
         CM_LAUNCH_CHECK();
     }
     {
         ProfScope prof("adapter_accesses", 12ull * n + 32ull * P_.n_data);
-        adapter_accesses_kernel<<<grid_for(n), 256, 0, stream()>>>(n, P_.opcode, P_.off, P_.dstart, P_.mem, P_.prev_clock, P_.prev_val,
-                                                                   (uint4*)accesses_dev);
+        adapter_accesses_kernel<<<grid_for(n), 256, 0, stream()>>>(n, P_.opcode, P_.off, P_.dstart, P_.mem, P_.prev, (uint4*)accesses_dev);
         CM_LAUNCH_CHECK();
     }
     if (P_.n_cu_rows) {
         CM_REQUIRE(clock_update_dev != nullptr, "adapter_emit: null clock-update buffer");
         ProfScope prof("adapter_clock_update", 8ull * M + 24ull * P_.n_cu_rows);
-        adapter_clock_update_kernel<<<grid_for(M), 256, 0, stream()>>>(P_.addr_sorted, P_.perm, M, P_.mem, P_.clk, P_.init, P_.n_init, P_.n_cu,
+        adapter_clock_update_kernel<<<grid_for(M), 256, 0, stream()>>>(P_.addr_sorted, P_.pay_sorted, M, P_.mem, P_.init, P_.n_init, P_.n_cu,
                                                                        P_.cu_off, clock_update_dev);
         CM_LAUNCH_CHECK();
     }
@@ -442,7 +446,7 @@ int cm31_adapter_emit(void* plan, uint32_t* const opcode_rows_dev[64], const uin
     if (int e = P_.alloc(cells, 10 * (size_t)P_.n_cells)) return e;
     {
         ProfScope prof("adapter_cells", 8ull * M + 40ull * P_.n_cells);
-        adapter_cells_kernel<<<grid_for(M), 256, 0, stream()>>>(P_.addr_sorted, P_.perm, M, P_.mem, P_.clk, P_.head_incl, cells);
+        adapter_cells_kernel<<<grid_for(M), 256, 0, stream()>>>(P_.addr_sorted, P_.pay_sorted, M, P_.mem, P_.head_incl, cells);
         CM_LAUNCH_CHECK();
     }
     CM_CUDA(cudaMemcpyAsync(cells_host, cells, 40 * (size_t)P_.n_cells, cudaMemcpyDeviceToHost, stream()));

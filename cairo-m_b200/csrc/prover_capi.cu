@@ -47,6 +47,8 @@ struct cm31_prover_input {
     std::unique_ptr<cm31::StagedInput<cm31::CudaAirImpl>> staged;  // set by cm31_input_upload
     std::deque<std::unique_ptr<cm31::StagedInput<cm31::CudaAirImpl>>> prefetched;  // cm31_input_prefetch, consumed oldest first
     std::vector<void*> pinned;                                     // host ranges registered with CUDA
+    std::vector<uint32_t> desc_ids, desc_bundles;  // cm31_input_describe: states_by_opcodes flattened
+    std::vector<uint64_t> desc_start;
     bool device_adapted = false;  // cm31_adapter_import: the per-step tables exist in HBM only (`staged`), not in `input`
     uint64_t adapted_info[2] = {0, 0};  // data accesses, bytes of runner logs uploaded
     ~cm31_prover_input() {
@@ -152,6 +154,99 @@ int cm31_input_info(const cm31_prover_input* h, uint64_t info[5]) {
         info[1] = h->adapted_info[0];
         info[4] = h->adapted_info[1];
     }
+    return 0;
+}
+
+// ProverInput from caller-owned flat tables / the flat view of a handle (include/cm31.h: cm31_prover_input_desc)
+static_assert(sizeof(Bundle) == 48 && sizeof(DataAccess) == 16 && sizeof(MemoryRow) == 32 && sizeof(ClockUpdateRow) == 24 && sizeof(MerkleNode) == 36,
+              "prover-input records must be packed u32 rows");
+int cm31_input_create(const cm31_prover_input_desc* d, cm31_prover_input** out) {
+    try {
+        CM_REQUIRE(d != nullptr && out != nullptr, "input_create: null argument");
+        CM_REQUIRE(d->n_steps >= 1, "adapter: empty trace");
+        CM_REQUIRE(d->n_opcodes == 0 || (d->opcode_ids && d->bundle_start && d->bundles), "input_create: null bundle tables");
+        CM_REQUIRE((d->n_data_accesses == 0 || d->data_accesses) && (d->n_initial_memory == 0 || d->initial_memory) &&
+                       (d->n_final_memory == 0 || d->final_memory) && (d->n_clock_updates == 0 || d->clock_updates) &&
+                       (d->n_merkle_nodes == 0 || d->merkle_nodes),
+                   "input_create: null table with a non-zero count");
+        std::unique_ptr<cm31_prover_input> h(new cm31_prover_input());
+        ProverInput& in = h->input;
+        in.initial_registers = Registers{d->initial_pc, d->initial_fp};
+        in.final_registers = Registers{d->final_pc, d->final_fp};
+        in.public_ranges.program_start = d->public_ranges[0];
+        in.public_ranges.program_end = d->public_ranges[1];
+        in.public_ranges.input_start = d->public_ranges[2];
+        in.public_ranges.input_end = d->public_ranges[3];
+        in.public_ranges.output_start = d->public_ranges[4];
+        in.public_ranges.output_end = d->public_ranges[5];
+        in.initial_root = d->initial_root;
+        in.final_root = d->final_root;
+        in.n_steps = d->n_steps;
+        uint64_t total = 0;
+        for (uint64_t g = 0; g < d->n_opcodes; g++) {
+            uint32_t op = d->opcode_ids[g];
+            CM_REQUIRE(opcode_memory_accesses(op) >= 0, "adapter: invalid opcode");
+            CM_REQUIRE(d->bundle_start[g] <= d->bundle_start[g + 1] && !in.states_by_opcodes.count(op), "input_create: bad opcode groups");
+            const Bundle* b = (const Bundle*)d->bundles;
+            std::vector<Bundle>& v = in.states_by_opcodes[op];
+            v.assign(b + d->bundle_start[g], b + d->bundle_start[g + 1]);
+            for (const Bundle& x : v)
+                CM_REQUIRE((uint64_t)x.span_start + x.span_len <= d->n_data_accesses && x.span_len <= MAX_ACCESSES, "input_create: access span outside the data-access log");
+            total += v.size();
+        }
+        CM_REQUIRE(total == d->n_steps, "input_create: the opcode groups do not add up to n_steps");
+        in.data_accesses.assign((const DataAccess*)d->data_accesses, (const DataAccess*)d->data_accesses + d->n_data_accesses);
+        in.initial_memory.assign((const MemoryRow*)d->initial_memory, (const MemoryRow*)d->initial_memory + d->n_initial_memory);
+        in.final_memory.assign((const MemoryRow*)d->final_memory, (const MemoryRow*)d->final_memory + d->n_final_memory);
+        in.clock_update_data.assign((const ClockUpdateRow*)d->clock_updates, (const ClockUpdateRow*)d->clock_updates + d->n_clock_updates);
+        in.merkle_nodes.assign((const MerkleNode*)d->merkle_nodes, (const MerkleNode*)d->merkle_nodes + d->n_merkle_nodes);
+        pin_range(h.get(), in.data_accesses.data(), in.data_accesses.size() * sizeof(DataAccess));
+        for (auto& kv : in.states_by_opcodes) pin_range(h.get(), kv.second.data(), kv.second.size() * sizeof(Bundle));
+        *out = h.release();
+        return 0;
+    } catch (const std::exception& e) {
+        set_error(e.what());
+        return -2;
+    }
+}
+int cm31_input_describe(cm31_prover_input* h, cm31_prover_input_desc* d) {
+    CM_REQUIRE(h != nullptr && d != nullptr, "input_describe: null argument");
+    CM_REQUIRE(!h->device_adapted, "input_describe: the per-step tables of a device-adapted input exist in HBM only (cm31_input_staged_words)");
+    const ProverInput& in = h->input;
+    h->desc_ids.clear();
+    h->desc_bundles.clear();
+    h->desc_start.assign(1, 0);
+    for (const auto& kv : in.states_by_opcodes) {
+        h->desc_ids.push_back(kv.first);
+        const uint32_t* w = (const uint32_t*)kv.second.data();
+        h->desc_bundles.insert(h->desc_bundles.end(), w, w + 12 * kv.second.size());
+        h->desc_start.push_back(h->desc_start.back() + kv.second.size());
+    }
+    memset(d, 0, sizeof(*d));
+    d->initial_pc = in.initial_registers.pc;
+    d->initial_fp = in.initial_registers.fp;
+    d->final_pc = in.final_registers.pc;
+    d->final_fp = in.final_registers.fp;
+    const PublicRanges& r = in.public_ranges;
+    uint32_t ranges[6] = {r.program_start, r.program_end, r.input_start, r.input_end, r.output_start, r.output_end};
+    memcpy(d->public_ranges, ranges, sizeof(ranges));
+    d->initial_root = in.initial_root;
+    d->final_root = in.final_root;
+    d->n_steps = in.n_steps;
+    d->n_opcodes = h->desc_ids.size();
+    d->opcode_ids = h->desc_ids.data();
+    d->bundle_start = h->desc_start.data();
+    d->bundles = h->desc_bundles.data();
+    d->data_accesses = (const uint32_t*)in.data_accesses.data();
+    d->n_data_accesses = in.data_accesses.size();
+    d->initial_memory = (const uint32_t*)in.initial_memory.data();
+    d->n_initial_memory = in.initial_memory.size();
+    d->final_memory = (const uint32_t*)in.final_memory.data();
+    d->n_final_memory = in.final_memory.size();
+    d->clock_updates = (const uint32_t*)in.clock_update_data.data();
+    d->n_clock_updates = in.clock_update_data.size();
+    d->merkle_nodes = (const uint32_t*)in.merkle_nodes.data();
+    d->n_merkle_nodes = in.merkle_nodes.size();
     return 0;
 }
 

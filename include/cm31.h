@@ -244,6 +244,41 @@ int cm31_input_release_device(cm31_prover_input* h);
  * "ConstraintsNotSatisfied" (S/prover/src/core/prover/mod.rs:76-82) if the OODS check fails. */
 int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out,
                        size_t proof_cap, size_t* proof_len, double* timings_ms);
+/* The reference's ProverInput (P/src/adapter/mod.rs:40-95: Instructions {initial/final registers, states_by_opcodes,
+ * data_accesses}, Memory {initial_memory, final_memory, clock_update_data}, MerkleTrees, public_address_ranges) as flat
+ * u32 tables — what a Rust caller that ran its own adapter hands over.  Record layouts (words):
+ *   bundle (12)       pc, fp, clock, inst_prev_clock, inst[6], access span start, access span len   (ExecutionBundle)
+ *   data access (4)   address, prev_clock, prev_value, value                                       (DataAccess, memory.rs:57-68)
+ *   memory row (8)    address, clock, value[4], multiplicity, root   (initial/final_memory entries, ascending address)
+ *   clock update (6)  address, prev_clock, value[4]
+ *   merkle node (9)   index, depth, left, right, parent, left/right/parent multiplicity, root   (initial tree, then final tree)
+ * states_by_opcodes: group g holds the bundles of opcode opcode_ids[g], rows bundle_start[g] .. bundle_start[g+1] of `bundles`,
+ * in execution order. */
+typedef struct cm31_prover_input_desc {
+    uint32_t initial_pc, initial_fp, final_pc, final_fp;
+    uint32_t public_ranges[6]; /* program, input, output: [start, end) each */
+    uint32_t initial_root, final_root;
+    uint64_t n_steps;
+    uint64_t n_opcodes;
+    const uint32_t* opcode_ids;   /* n_opcodes */
+    const uint64_t* bundle_start; /* n_opcodes + 1 */
+    const uint32_t* bundles;
+    const uint32_t* data_accesses;
+    uint64_t n_data_accesses;
+    const uint32_t* initial_memory;
+    uint64_t n_initial_memory;
+    const uint32_t* final_memory;
+    uint64_t n_final_memory;
+    const uint32_t* clock_updates;
+    uint64_t n_clock_updates;
+    const uint32_t* merkle_nodes;
+    uint64_t n_merkle_nodes;
+} cm31_prover_input_desc;
+/* copies the tables into a new handle (prove with cm31_prove_cairo_m, stage with cm31_input_upload / cm31_input_prefetch) */
+int cm31_input_create(const cm31_prover_input_desc* desc, cm31_prover_input** out);
+/* the same view of an existing host-adapted handle (pointers stay valid until the handle is destroyed or tampered with) */
+int cm31_input_describe(cm31_prover_input* h, cm31_prover_input_desc* out);
+
 /* ------------------------------------------------------------------ adapter on the device
  * import_from_runner_output (P/src/adapter/mod.rs:233-…; import_internal :97-193; ExecutionBundleIterator and Memory::push,
  * P/src/adapter/memory.rs:264-403, 470-…) with the per-step work done in HBM: the runner's logs go in, a prover input

@@ -59,6 +59,61 @@ class GpuFibInput:
             self.h = C.c_void_p()
 
 
+class ProverInputDesc(C.Structure):
+    """include/cm31.h: cm31_prover_input_desc — the reference's ProverInput as flat u32 tables."""
+    _fields_ = [("initial_pc", C.c_uint32), ("initial_fp", C.c_uint32), ("final_pc", C.c_uint32), ("final_fp", C.c_uint32),
+                ("public_ranges", C.c_uint32 * 6), ("initial_root", C.c_uint32), ("final_root", C.c_uint32),
+                ("n_steps", C.c_uint64), ("n_opcodes", C.c_uint64),
+                ("opcode_ids", C.POINTER(C.c_uint32)), ("bundle_start", C.POINTER(C.c_uint64)), ("bundles", C.POINTER(C.c_uint32)),
+                ("data_accesses", C.POINTER(C.c_uint32)), ("n_data_accesses", C.c_uint64),
+                ("initial_memory", C.POINTER(C.c_uint32)), ("n_initial_memory", C.c_uint64),
+                ("final_memory", C.POINTER(C.c_uint32)), ("n_final_memory", C.c_uint64),
+                ("clock_updates", C.POINTER(C.c_uint32)), ("n_clock_updates", C.c_uint64),
+                ("merkle_nodes", C.POINTER(C.c_uint32)), ("n_merkle_nodes", C.c_uint64)]
+
+
+DESC_TABLES = [("data_accesses", "n_data_accesses", 4), ("initial_memory", "n_initial_memory", 8), ("final_memory", "n_final_memory", 8),
+               ("clock_updates", "n_clock_updates", 6), ("merkle_nodes", "n_merkle_nodes", 9)]
+
+
+def describe_input(cm, handle):
+    """cm31_input_describe -> (scalars dict, tables dict of numpy COPIES)."""
+    import numpy as np
+    d = ProverInputDesc()
+    cm.check(cm.lib().cm31_input_describe(handle, C.byref(d)))
+
+    def arr(ptr, n, dtype=np.uint32):
+        return np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n else np.zeros(0, dtype=dtype)
+
+    g = int(d.n_opcodes)
+    tables = {"opcode_ids": arr(d.opcode_ids, g), "bundle_start": arr(d.bundle_start, g + 1, np.uint64)}
+    tables["bundles"] = arr(d.bundles, 12 * int(tables["bundle_start"][-1]))
+    for name, count, width in DESC_TABLES:
+        tables[name] = arr(getattr(d, name), width * int(getattr(d, count)))
+    scalars = {k: getattr(d, k) for k in ["initial_pc", "initial_fp", "final_pc", "final_fp", "initial_root", "final_root", "n_steps"]}
+    scalars["public_ranges"] = list(d.public_ranges)
+    return scalars, tables
+
+
+def create_input(cm, scalars, tables, handle_out):
+    """cm31_input_create from (scalars, tables) as describe_input returns them; returns the status."""
+    import numpy as np
+    d = ProverInputDesc()
+    for k in ["initial_pc", "initial_fp", "final_pc", "final_fp", "initial_root", "final_root", "n_steps"]:
+        setattr(d, k, int(scalars[k]))
+    for i, v in enumerate(scalars["public_ranges"]):
+        d.public_ranges[i] = int(v)
+    keep = {k: np.ascontiguousarray(v) for k, v in tables.items()}
+    d.n_opcodes = keep["opcode_ids"].size
+    d.opcode_ids = keep["opcode_ids"].ctypes.data_as(C.POINTER(C.c_uint32))
+    d.bundle_start = keep["bundle_start"].ctypes.data_as(C.POINTER(C.c_uint64))
+    d.bundles = keep["bundles"].ctypes.data_as(C.POINTER(C.c_uint32))
+    for name, count, width in DESC_TABLES:
+        setattr(d, name, keep[name].ctypes.data_as(C.POINTER(C.c_uint32)))
+        setattr(d, count, keep[name].size // width)
+    return cm.lib().cm31_input_create(C.byref(d), C.byref(handle_out))
+
+
 class VmTrace:
     """The runner's output for a built-in program (host VM only): what import_from_runner_output consumes."""
 

@@ -120,3 +120,25 @@ def test_device_adapter_rejects_malformed_logs(cm):
     bad = trace.copy()
     bad[2 * 5 + 1] = init.size                                                      # pc outside the preloaded memory
     expect_error(bad, mem, init, "pc outside")
+
+
+@pytest.mark.parametrize("program,n", [(ch.FIB, 64), (ch.U32_COUNTER, 40)])
+def test_proof_from_caller_supplied_prover_input(cm, program, n):
+    # cm31_input_create: the ProverInput tables of a caller-side adapter -> same proof bytes as the built-in path
+    src = ch.GpuFibInput(cm, n, program)
+    try:
+        want, _ = src.prove()
+        scalars, tables = ch.describe_input(cm, src.h)
+    finally:
+        src.close()
+    inp = ch.GpuFibInput.__new__(ch.GpuFibInput)
+    inp.cm, inp.h = cm, C.c_void_p()
+    cm.check(ch.create_input(cm, scalars, tables, inp.h))
+    try:
+        got, _ = inp.prove()
+        cm.check(cm.lib().cm31_input_upload(inp.h))
+        resident, _ = inp.prove()
+    finally:
+        inp.close()
+    assert got == want and resident == want
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()

@@ -44,3 +44,50 @@ def test_adapter_import_fails_loudly_without_a_device(cm):
     assert ch.adapter_import(cm, *logs, h) != 0
     assert not h.value
     assert cm.lib().cm31_last_error()
+
+
+@pytest.mark.parametrize("program,n", [(ch.FIB, 40), (ch.ARRAY_SUM, 30), (ch.U32_COUNTER, 25), (ch.U32_MIX, 8)])
+def test_input_create_round_trips_the_reference_prover_input(cm, program, n):
+    # a caller that ran its own adapter hands the ProverInput over as flat tables (cm31_input_create); the handle holds
+    # exactly those tables (cm31_input_describe)
+    src = ch.GpuFibInput(cm, n, program)
+    try:
+        scalars, tables = ch.describe_input(cm, src.h)
+    finally:
+        src.close()
+    assert scalars["n_steps"] == int(tables["bundle_start"][-1]) and scalars["n_steps"] >= 1
+    assert tables["bundles"].size == 12 * scalars["n_steps"]
+    h = C.c_void_p()
+    cm.check(ch.create_input(cm, scalars, tables, h))
+    try:
+        scalars2, tables2 = ch.describe_input(cm, h)
+        info = (C.c_uint64 * 5)()
+        cm.check(cm.lib().cm31_input_info(h, info))
+    finally:
+        cm.lib().cm31_input_destroy(h)
+    assert scalars2 == scalars
+    assert int(info[0]) == scalars["n_steps"] and int(info[1]) == tables["data_accesses"].size // 4
+    for k in tables:
+        assert np.array_equal(tables[k], tables2[k]), k
+
+
+def test_input_create_rejects_inconsistent_tables(cm):
+    src = ch.GpuFibInput(cm, 10)
+    try:
+        scalars, tables = ch.describe_input(cm, src.h)
+    finally:
+        src.close()
+
+    def expect_error(scalars, tables, needle):
+        h = C.c_void_p()
+        assert ch.create_input(cm, scalars, tables, h) != 0
+        assert needle in cm.lib().cm31_last_error().decode()
+
+    expect_error(dict(scalars, n_steps=scalars["n_steps"] + 1), tables, "do not add up")
+    bad = dict(tables, opcode_ids=tables["opcode_ids"].copy())
+    bad["opcode_ids"][0] = 63
+    expect_error(scalars, bad, "invalid opcode")
+    bad = dict(tables, bundles=tables["bundles"].copy())
+    bad["bundles"][10] = tables["data_accesses"].size  # span start past the end of the access log
+    expect_error(scalars, bad, "access span")
+    expect_error(dict(scalars, n_steps=0), tables, "empty trace")
