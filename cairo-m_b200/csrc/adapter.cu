@@ -251,6 +251,8 @@ struct AdapterPlan {
     void* temp = nullptr;
     size_t temp_bytes = 0;
     u32 n_cells = 0, n_cu_rows = 0, n_data = 0;
+    u32 upload_mark = 0;       // background upload: the logs have landed once this staging mark is reached
+    bool wait_upload = false;
     ~AdapterPlan() {
         for (void* p : owned) cudaFreeAsync(p, stream());
     }
@@ -303,9 +305,12 @@ extern "C" {
 //   mem_host   : IoMemoryEntry {address, value[4]} x n_mem, access order
 //   init_host  : preloaded memory, QM31 x n_init, address = index
 // counts_out[0..63] = steps per opcode, [64] = data accesses, [65] = clock-update rows, [66] = distinct cells touched
-int cm31_adapter_scan(const uint32_t* trace_host, size_t n_trace, const uint32_t* mem_host, size_t n_mem, const uint32_t* init_host,
-                      size_t n_init, void** plan_out, uint64_t counts_out[67]) {
-    CM_REQUIRE(plan_out && counts_out && trace_host && mem_host && init_host, "adapter_scan: null argument");
+// Phase 0: device buffers + the upload of the logs.  background != 0 issues the three copies on the background copy stream
+// (ordered after the work already queued on the main stream) and returns at once: with page-locked logs the upload of
+// segment i+1 overlaps the adapter kernels and the proof of segment i; cm31_adapter_scan_staged waits for it on the device.
+int cm31_adapter_stage_logs(const uint32_t* trace_host, size_t n_trace, const uint32_t* mem_host, size_t n_mem, const uint32_t* init_host,
+                            size_t n_init, int background, void** plan_out) {
+    CM_REQUIRE(plan_out && trace_host && mem_host && init_host, "adapter_scan: null argument");
     CM_REQUIRE(n_trace >= 2, "adapter: empty trace");
     CM_REQUIRE(n_trace - 1 < (1u << 31) - 1 && n_mem < 0xFFFFFFF0u && n_mem >= 1 && n_init >= 1 && n_init < (1u << 31), "adapter_scan: sizes out of range");
     if (int e = upload_opcode_tables()) return e;
@@ -335,9 +340,29 @@ int cm31_adapter_scan(const uint32_t* trace_host, size_t n_trace, const uint32_t
     if ((e = cm31_malloc(&P_.temp, need))) return e;
     P_.owned.push_back(P_.temp);
 
-    CM_CUDA(cudaMemcpyAsync(P_.trace, trace_host, n_trace * 8, cudaMemcpyHostToDevice, stream()));
-    CM_CUDA(cudaMemcpyAsync(P_.mem, mem_host, n_mem * 20, cudaMemcpyHostToDevice, stream()));
-    CM_CUDA(cudaMemcpyAsync(P_.init, init_host, n_init * 16, cudaMemcpyHostToDevice, stream()));
+    if (background) {
+        if ((e = cm31_bg_begin()) || (e = cm31_h2d_bg_ordered(P_.trace, trace_host, n_trace * 8)) || (e = cm31_h2d_bg_ordered(P_.init, init_host, n_init * 16)) ||
+            (e = cm31_h2d_bg_ordered(P_.mem, mem_host, n_mem * 20)) || (e = cm31_bg_mark(&P_.upload_mark)))
+            return e;
+        P_.wait_upload = true;
+    } else {
+        CM_CUDA(cudaMemcpyAsync(P_.trace, trace_host, n_trace * 8, cudaMemcpyHostToDevice, stream()));
+        CM_CUDA(cudaMemcpyAsync(P_.mem, mem_host, n_mem * 20, cudaMemcpyHostToDevice, stream()));
+        CM_CUDA(cudaMemcpyAsync(P_.init, init_host, n_init * 16, cudaMemcpyHostToDevice, stream()));
+    }
+    *plan_out = pl.release();
+    return 0;
+}
+
+// Phase 1: resolve everything whose size is data dependent (see cm31_adapter_scan).
+int cm31_adapter_scan_staged(void* plan, uint64_t counts_out[67]) {
+    CM_REQUIRE(plan && counts_out, "adapter_scan: null argument");
+    AdapterPlan& P_ = *(AdapterPlan*)plan;
+    u32 n = P_.n_steps, M = P_.n_mem;
+    if (P_.wait_upload) {
+        if (int e = cm31_bg_wait(P_.upload_mark)) return e;
+        P_.wait_upload = false;
+    }
     CM_CUDA(cudaMemsetAsync(P_.small, 0, 68 * 4, stream()));
     CM_CUDA(cudaMemsetAsync(P_.cnt + n, 0, 4, stream()));
     CM_CUDA(cudaMemsetAsync(P_.ndata + n, 0, 4, stream()));
@@ -400,7 +425,20 @@ int cm31_adapter_scan(const uint32_t* trace_host, size_t n_trace, const uint32_t
     counts_out[64] = P_.n_data;
     counts_out[65] = P_.n_cu_rows;
     counts_out[66] = P_.n_cells;
-    *plan_out = pl.release();
+    return 0;
+}
+
+int cm31_adapter_free(void* plan);
+int cm31_adapter_scan(const uint32_t* trace_host, size_t n_trace, const uint32_t* mem_host, size_t n_mem, const uint32_t* init_host,
+                      size_t n_init, void** plan_out, uint64_t counts_out[67]) {
+    CM_REQUIRE(plan_out && counts_out, "adapter_scan: null argument");
+    void* plan = nullptr;
+    if (int e = cm31_adapter_stage_logs(trace_host, n_trace, mem_host, n_mem, init_host, n_init, 0, &plan)) return e;
+    if (int e = cm31_adapter_scan_staged(plan, counts_out)) {
+        cm31_adapter_free(plan);
+        return e;
+    }
+    *plan_out = plan;
     return 0;
 }
 

@@ -46,6 +46,7 @@ struct cm31_prover_input {
     uint32_t return_value = 0;
     std::unique_ptr<cm31::StagedInput<cm31::CudaAirImpl>> staged;  // set by cm31_input_upload
     std::deque<std::unique_ptr<cm31::StagedInput<cm31::CudaAirImpl>>> prefetched;  // cm31_input_prefetch, consumed oldest first
+    std::unique_ptr<cm31::StagedInput<cm31::CudaAirImpl>> spare;   // the last consumed prefetch slot: its buffers take the next upload
     std::vector<void*> pinned;                                     // host ranges registered with CUDA
     std::vector<uint32_t> desc_ids, desc_bundles;  // cm31_input_describe: states_by_opcodes flattened
     std::vector<uint64_t> desc_start;
@@ -126,6 +127,7 @@ int cm31_input_release_device(cm31_prover_input* h) {
     CM_REQUIRE(!h->device_adapted, "input_release_device: a device-adapted input has no host copy to fall back to");
     h->staged.reset();
     h->prefetched.clear();
+    h->spare.reset();
     return 0;
 }
 int cm31_input_prefetch(cm31_prover_input* h) {
@@ -133,7 +135,9 @@ int cm31_input_prefetch(cm31_prover_input* h) {
         CM_REQUIRE(h != nullptr, "input_prefetch: null handle");
         CM_REQUIRE(!h->device_adapted, "input_prefetch: a device-adapted input is already resident");
         CM_REQUIRE(h->prefetched.size() < 4, "input_prefetch: too many uploads in flight");
-        h->prefetched.emplace_back(new StagedInput<CudaAirImpl>(stage_input<CudaAirImpl>(h->input)));
+        static const bool slots = getenv("CM31_NO_INPUT_SLOTS") == nullptr;
+        std::unique_ptr<StagedInput<CudaAirImpl>> spare = std::move(h->spare);
+        h->prefetched.emplace_back(new StagedInput<CudaAirImpl>(stage_input<CudaAirImpl>(h->input, slots ? spare.get() : nullptr)));
         return 0;
     } catch (const std::exception& e) {
         set_error(e.what());
@@ -258,8 +262,9 @@ struct cm31_vm_trace {
 };
 static_assert(sizeof(std::pair<cm31::u32, cm31::Word4>) == 20, "memory-trace entries must be IoMemoryEntry-shaped (5 words)");
 extern "C" {
-int cm31_adapter_scan(const uint32_t* trace_host, size_t n_trace, const uint32_t* mem_host, size_t n_mem, const uint32_t* init_host,
-                      size_t n_init, void** plan_out, uint64_t counts_out[67]);
+int cm31_adapter_stage_logs(const uint32_t* trace_host, size_t n_trace, const uint32_t* mem_host, size_t n_mem, const uint32_t* init_host,
+                            size_t n_init, int background, void** plan_out);
+int cm31_adapter_scan_staged(void* plan, uint64_t counts_out[67]);
 int cm31_adapter_emit(void* plan, uint32_t* const opcode_rows_dev[64], const uint64_t counts[67], uint32_t* accesses_dev,
                       uint32_t* clock_update_dev, uint32_t* cells_host);
 int cm31_adapter_free(void* plan);
@@ -336,13 +341,23 @@ int cm31_input_staged_words(const cm31_prover_input* h, uint32_t table, uint32_t
 
 // import_from_runner_output (crates/prover/src/adapter/mod.rs:233-…) with the per-step work on the device (csrc/adapter.cu):
 // the returned handle is resident in HBM and proves with cm31_prove_cairo_m like an uploaded one.
-int cm31_adapter_import(const uint32_t* trace, size_t n_trace, const uint32_t* memory_trace, size_t n_mem, const uint32_t* initial_memory,
-                        size_t n_initial, const uint32_t public_ranges[6], cm31_prover_input** out) {
+}  // extern "C"
+struct cm31_adapter_logs {  // cm31_adapter_prefetch: the logs on their way to HBM + what the host tail needs
     void* plan = nullptr;
+    const uint32_t *trace = nullptr, *initial_memory = nullptr;
+    size_t n_trace = 0, n_mem = 0, n_initial = 0;
+    uint32_t ranges[6] = {0, 0, 0, 0, 0, 0};
+    ~cm31_adapter_logs() {
+        if (plan) cm31_adapter_free(plan);
+    }
+};
+// phases 1-2 + the host tail, from logs already staged (consumes logs->plan)
+static int adapter_finish(cm31_adapter_logs& logs, cm31_prover_input** out) {
     try {
-        CM_REQUIRE(trace && memory_trace && initial_memory && public_ranges && out, "adapter_import: null argument");
         uint64_t counts[67];
-        if (int e = cm31_adapter_scan(trace, n_trace, memory_trace, n_mem, initial_memory, n_initial, &plan, counts)) return e;
+        if (int e = cm31_adapter_scan_staged(logs.plan, counts)) return e;
+        const uint32_t* trace = logs.trace;
+        const size_t n_trace = logs.n_trace, n_initial = logs.n_initial;
         std::unique_ptr<cm31_prover_input> h(new cm31_prover_input());
         h->device_adapted = true;
         ProverInput& in = h->input;
@@ -371,13 +386,13 @@ int cm31_adapter_import(const uint32_t* trace, size_t n_trace, const uint32_t* m
         st->clock_update.n_real = counts[65];
         st->clock_update.words = CudaAirImpl::alloc_words(counts[65] * 6);
         std::vector<uint32_t> cells(10 * counts[66] + 1);
-        int rc = cm31_adapter_emit(plan, rows_by_opcode, counts, st->accesses.ptr(), st->clock_update.words.ptr(), cells.data());
-        cm31_adapter_free(plan);
-        plan = nullptr;
+        int rc = cm31_adapter_emit(logs.plan, rows_by_opcode, counts, st->accesses.ptr(), st->clock_update.words.ptr(), cells.data());
+        cm31_adapter_free(logs.plan);
+        logs.plan = nullptr;
         if (rc) return rc;
         // boundary memory from the distinct cells (Memory::push's bookkeeping of initial_memory / final_memory)
         std::vector<Word4> preloaded(n_initial);
-        memcpy(preloaded.data(), initial_memory, n_initial * 16);
+        memcpy(preloaded.data(), logs.initial_memory, n_initial * 16);
         MemoryModel memory(preloaded);
         for (size_t c = 0; c < counts[66]; c++) {
             const uint32_t* w = &cells[10 * c];
@@ -399,25 +414,67 @@ int cm31_adapter_import(const uint32_t* trace, size_t n_trace, const uint32_t* m
             memory.final_[a].present = true;
         }
         PublicRanges ranges;
-        ranges.program_start = public_ranges[0];
-        ranges.program_end = public_ranges[1];
-        ranges.input_start = public_ranges[2];
-        ranges.input_end = public_ranges[3];
-        ranges.output_start = public_ranges[4];
-        ranges.output_end = public_ranges[5];
+        ranges.program_start = logs.ranges[0];
+        ranges.program_end = logs.ranges[1];
+        ranges.input_start = logs.ranges[2];
+        ranges.input_end = logs.ranges[3];
+        ranges.output_start = logs.ranges[4];
+        ranges.output_end = logs.ranges[5];
         finish_memory(memory, ranges, in);
         stage_boundary_rows<CudaAirImpl>(in, *st);
         h->adapted_info[0] = counts[64];
-        h->adapted_info[1] = n_trace * 8 + n_mem * 20 + n_initial * 16;
+        h->adapted_info[1] = n_trace * 8 + logs.n_mem * 20 + n_initial * 16;
         h->staged = std::move(st);
         if (int e = cm31_sync()) return e;
         *out = h.release();
         return 0;
     } catch (const std::exception& e) {
-        if (plan) cm31_adapter_free(plan);
         set_error(e.what());
         return -2;
     }
+}
+static int adapter_stage(const uint32_t* trace, size_t n_trace, const uint32_t* memory_trace, size_t n_mem, const uint32_t* initial_memory,
+                         size_t n_initial, const uint32_t public_ranges[6], int background, cm31_adapter_logs& logs) {
+    CM_REQUIRE(trace && memory_trace && initial_memory && public_ranges, "adapter_import: null argument");
+    if (int e = cm31_adapter_stage_logs(trace, n_trace, memory_trace, n_mem, initial_memory, n_initial, background, &logs.plan)) return e;
+    logs.trace = trace;
+    logs.initial_memory = initial_memory;
+    logs.n_trace = n_trace;
+    logs.n_mem = n_mem;
+    logs.n_initial = n_initial;
+    memcpy(logs.ranges, public_ranges, sizeof(logs.ranges));
+    return 0;
+}
+extern "C" {
+int cm31_adapter_import(const uint32_t* trace, size_t n_trace, const uint32_t* memory_trace, size_t n_mem, const uint32_t* initial_memory,
+                        size_t n_initial, const uint32_t public_ranges[6], cm31_prover_input** out) {
+    CM_REQUIRE(out != nullptr, "adapter_import: null argument");
+    cm31_adapter_logs logs;
+    if (int e = adapter_stage(trace, n_trace, memory_trace, n_mem, initial_memory, n_initial, public_ranges, 0, logs)) return e;
+    return adapter_finish(logs, out);
+}
+// Pipelined form for a prover fed with continuation segments: cm31_adapter_prefetch starts the upload of a segment's logs on
+// the background copy stream and returns at once (the logs must stay valid, and should be page-locked, until
+// cm31_adapter_import_prefetched returns); the adapter kernels and the proof of the PREVIOUS segment run meanwhile.
+int cm31_adapter_prefetch(const uint32_t* trace, size_t n_trace, const uint32_t* memory_trace, size_t n_mem, const uint32_t* initial_memory,
+                          size_t n_initial, const uint32_t public_ranges[6], cm31_adapter_logs** out) {
+    CM_REQUIRE(out != nullptr, "adapter_prefetch: null argument");
+    std::unique_ptr<cm31_adapter_logs> logs(new cm31_adapter_logs());
+    if (int e = adapter_stage(trace, n_trace, memory_trace, n_mem, initial_memory, n_initial, public_ranges, 1, *logs)) return e;
+    *out = logs.release();
+    return 0;
+}
+// consumes (and frees) `logs`, also on error
+int cm31_adapter_import_prefetched(cm31_adapter_logs* logs, cm31_prover_input** out) {
+    CM_REQUIRE(logs != nullptr && out != nullptr, "adapter_import_prefetched: null argument");
+    std::unique_ptr<cm31_adapter_logs> own(logs);
+    CM_REQUIRE(own->plan != nullptr, "adapter_import_prefetched: the logs were already consumed");
+    return adapter_finish(*own, out);
+}
+int cm31_adapter_logs_destroy(cm31_adapter_logs* logs) {
+    if (logs && logs->plan) cm31_bg_fence();  // the upload may still be in flight: order the (stream-ordered) frees after it
+    delete logs;
+    return 0;
 }
 
 // prove_cairo_m::<Blake2sMerkleChannel> (crates/prover/src/prover.rs:23) on the CUDA backend.
@@ -445,6 +502,7 @@ int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n
             timings_ms[3] = t.stark_ms;
             timings_ms[4] = t.total_ms;
         }
+        if (pre) const_cast<cm31_prover_input*>(h)->spare = std::move(pre);  // keep the slot for the next prefetch
         int rc;
         {
             HostTimer ht("proof_to_bytes");

@@ -293,6 +293,15 @@ int cm31_input_describe(cm31_prover_input* h, cm31_prover_input_desc* out);
 int cm31_adapter_import(const uint32_t* trace, size_t n_trace, const uint32_t* memory_trace, size_t n_mem,
                         const uint32_t* initial_memory, size_t n_initial, const uint32_t public_ranges[6],
                         cm31_prover_input** out);
+/* Pipelined form (continuation segments): cm31_adapter_prefetch starts the upload of a segment's logs on the background copy
+ * stream and returns at once — the logs must stay valid (and should be page-locked) until cm31_adapter_import_prefetched, which
+ * consumes the handle, returns; the adapter kernels and the proof of the previous segment run while the next logs arrive. */
+typedef struct cm31_adapter_logs cm31_adapter_logs;
+int cm31_adapter_prefetch(const uint32_t* trace, size_t n_trace, const uint32_t* memory_trace, size_t n_mem,
+                          const uint32_t* initial_memory, size_t n_initial, const uint32_t public_ranges[6],
+                          cm31_adapter_logs** out);
+int cm31_adapter_import_prefetched(cm31_adapter_logs* logs, cm31_prover_input** out);
+int cm31_adapter_logs_destroy(cm31_adapter_logs* logs); /* only for logs that were never imported */
 /* One table of a resident input read back to the host (parity tests): table 0 = data-access log (4 words per access),
  * 1..26 = opcode components in claim order (12 words per step), 100 = memory rows (8), 101 = merkle rows (9),
  * 102 = clock-update rows (6), 103 = poseidon2 states (16).  out may be NULL to query the size. */

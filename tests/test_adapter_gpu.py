@@ -142,3 +142,49 @@ def test_proof_from_caller_supplied_prover_input(cm, program, n):
         inp.close()
     assert got == want and resident == want
     assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+
+
+def test_prefetched_logs_give_the_same_input_and_proof(cm):
+    # cm31_adapter_prefetch / cm31_adapter_import_prefetched: two segments in flight, uploads on the background stream
+    import torch
+    lib = cm.lib()
+    n_a, n_b = 300, 77
+    logs = {}
+    for n in (n_a, n_b):
+        vm = ch.VmTrace(cm, ch.FIB, n)
+        try:
+            # page-locked copies, as a runner would hand them over
+            logs[n] = [torch.from_numpy(a.view(np.int32)).pin_memory() for a in vm.arrays()]
+        finally:
+            vm.close()
+
+    def prefetch(n):
+        t, m, i, r = logs[n]
+        as_p = lambda x: C.cast(x.data_ptr(), C.POINTER(C.c_uint32))
+        lg = C.c_void_p()
+        cm.check(lib.cm31_adapter_prefetch(as_p(t), C.c_size_t(t.numel() // 2), as_p(m), C.c_size_t(m.numel() // 5), as_p(i),
+                                           C.c_size_t(i.numel() // 4), as_p(r), C.byref(lg)))
+        return lg
+
+    lg_a, lg_b = prefetch(n_a), prefetch(n_b)  # both uploads queued before anything is adapted
+    proofs = {}
+    for n, lg in ((n_a, lg_a), (n_b, lg_b)):
+        inp = ch.GpuFibInput.__new__(ch.GpuFibInput)
+        inp.cm, inp.h = cm, C.c_void_p()
+        cm.check(lib.cm31_adapter_import_prefetched(lg, C.byref(inp.h)))
+        try:
+            host = ch.GpuFibInput(cm, n)
+            try:
+                cm.check(lib.cm31_input_upload(host.h))
+                assert_same_tables(cm, host.h, inp.h)
+            finally:
+                host.close()
+            proofs[n], _ = inp.prove()
+        finally:
+            inp.close()
+    for n in (n_a, n_b):
+        want, _ = ch.oracle_fib_prove(n)
+        assert proofs[n] == want
+    # logs that are never imported can be dropped
+    lg = prefetch(n_b)
+    cm.check(lib.cm31_adapter_logs_destroy(lg))
