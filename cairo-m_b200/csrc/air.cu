@@ -237,31 +237,80 @@ __global__ void __launch_bounds__(256) scan_chunk_sums_kernel(Col4 c, u32 L, con
     }
     if (threadIdx.x == 0) chunk_sums[(size_t)blockIdx.y * n_chunks + chunk] = sh[0];
 }
-// pass 2: exclusive scan of the chunk totals (one CTA per coordinate, tiles of 1024)
+// pass 2: exclusive scan of the chunk / segment totals (one CTA per coordinate, tiles of 1024; warp-shuffle scans)
+__device__ __forceinline__ u32 warp_inclusive_m31(u32 x, u32 lane) {
+#pragma unroll
+    for (u32 d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x = m31_add(x, t);
+    }
+    return x;
+}
 __global__ void __launch_bounds__(1024) scan_chunk_offsets_kernel(u32* chunk_sums_all, u32 n_chunks) {
-    __shared__ u32 sh[1024];
-    __shared__ u32 carry;
+    __shared__ u32 wsum[32];
+    __shared__ u32 tile_total;
     u32* chunk_sums = chunk_sums_all + (size_t)blockIdx.x * n_chunks;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 carry = 0;  // identical in every thread
     for (u32 base = 0; base < n_chunks; base += 1024) {
         u32 i = base + threadIdx.x;
         u32 v = i < n_chunks ? chunk_sums[i] : 0;
-        sh[threadIdx.x] = v;
+        u32 x = warp_inclusive_m31(v, lane);
+        if (lane == 31) wsum[warp] = x;
         __syncthreads();
-        for (u32 st = 1; st < 1024; st <<= 1) {
-            u32 t = threadIdx.x >= st ? sh[threadIdx.x - st] : 0;
-            __syncthreads();
-            sh[threadIdx.x] = m31_add(sh[threadIdx.x], t);
-            __syncthreads();
+        if (warp == 0) {
+            u32 w = wsum[lane];
+            u32 y = warp_inclusive_m31(w, lane);
+            wsum[lane] = m31_sub(y, w);  // exclusive over warps
+            if (lane == 31) tile_total = y;
         }
-        u32 incl = sh[threadIdx.x];
-        if (i < n_chunks) chunk_sums[i] = m31_add(carry, m31_sub(incl, v));  // exclusive
         __syncthreads();
-        if (threadIdx.x == 1023) carry = m31_add(carry, incl);
+        u32 incl = m31_add(x, wsum[warp]);
+        if (i < n_chunks) chunk_sums[i] = m31_add(carry, m31_sub(incl, v));  // exclusive
+        carry = m31_add(carry, tile_total);
         __syncthreads();
     }
 }
+
+// Segmented form of passes 1 and 3 for large columns.  The coset order is cut into S = 2^s contiguous segments of
+// 2^(SEG_Q+1) positions.  With L = 1 + s + SEG_Q, position j = 2y (+1), y = sigma * 2^SEG_Q + i:
+//   even j: cd = y        -> row = bitrev_q(i) << (s+1) | bitrev_s(sigma) << 1
+//   odd  j: cd = n-1-y    -> row = n - 1 - (row of the even partner)          (every bit complemented)
+// so thread tau = bitrev_s(sigma) walks rows (h << (s+1)) | 2 tau and their mirror images: at every step the threads
+// of a warp touch CONSECUTIVE even (resp. odd) words — whole sectors, shared with the warp of the mirrored segment —
+// instead of one word per sector (pass 1/3 of the chunked form: rows bitrev(cd) of consecutive cd, 8x sector
+// amplification, 210-270 GB/s).  Each thread scans its 2^(SEG_Q+1) values sequentially; loads are issued 8 steps ahead.
+constexpr u32 SEG_Q = 6;
+template <bool APPLY>
+__global__ void __launch_bounds__(256) seg_scan_kernel(Col4 c, u32 L, const u32* __restrict__ shift4, u32* seg_all, u32 s) {
+    u32* col = c.p[blockIdx.y];
+    const u32 shift = shift4[blockIdx.y];
+    const u32 S = 1u << s;
+    u32 tau = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tau >= S) return;
+    u32* slot = seg_all + (size_t)blockIdx.y * S + (__brev(tau) >> (32 - s));  // totals / offsets are kept in sigma order
+    const u32 n1 = (u32)(((u64)1 << L) - 1);
+    u32 acc = APPLY ? *slot : 0u;
+    for (u32 i0 = 0; i0 < (1u << SEG_Q); i0 += 8) {
+        u32 re[8], xe[8], xo[8];
+#pragma unroll
+        for (u32 k = 0; k < 8; k++) {
+            u32 h = __brev(i0 + k) >> (32 - SEG_Q);
+            re[k] = (h << (s + 1)) | (tau << 1);
+            xe[k] = col[re[k]];
+            xo[k] = col[n1 - re[k]];
+        }
+#pragma unroll
+        for (u32 k = 0; k < 8; k++) {
+            acc = m31_add(acc, m31_sub(xe[k], shift));
+            if (APPLY) col[re[k]] = acc;
+            acc = m31_add(acc, m31_sub(xo[k], shift));
+            if (APPLY) col[n1 - re[k]] = acc;
+        }
+    }
+    if (!APPLY) *slot = acc;
+}
+
 // pass 3: in-chunk inclusive scan + chunk offset, written back in place
 __global__ void __launch_bounds__(256) scan_apply_kernel(Col4 c, u32 L, const u32* __restrict__ shift4, const u32* chunk_offsets_all, u32 n_chunks) {
     __shared__ u32 sh[256];
@@ -398,14 +447,24 @@ int cm31_logup_finalize_last_async(uint32_t* const last4[4], uint32_t log_size, 
         sums_to_shift_kernel<<<1, 32, 0, stream()>>>(dsums, n_inv, claimed_sum_dev, dshift);
     }
     CM_LAUNCH_CHECK();
-    u32 n_chunks = (u32)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    static const bool chunked = getenv("CM31_CHUNKED_SCAN") != nullptr;  // the first (gathering) form, kept for A/B runs
+    const bool segmented = !chunked && log_size >= SEG_Q + 6;
+    u32 n_chunks = segmented ? 1u << (log_size - 1 - SEG_Q) : (u32)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
     u32* dchunks = nullptr;
     CM_CUDA(cudaMallocAsync(&dchunks, (size_t)n_chunks * 16, stream()));
     {
         ProfScope prof("logup_prefix_sum", 32ull * n, 3);
-        scan_chunk_sums_kernel<<<dim3(n_chunks, 4), 256, 0, stream()>>>(c, log_size, dshift, dchunks, n_chunks);
-        scan_chunk_offsets_kernel<<<4, 1024, 0, stream()>>>(dchunks, n_chunks);
-        scan_apply_kernel<<<dim3(n_chunks, 4), 256, 0, stream()>>>(c, log_size, dshift, dchunks, n_chunks);
+        if (segmented) {
+            const u32 s = log_size - 1 - SEG_Q;
+            dim3 grid((n_chunks + 255) / 256, 4);
+            seg_scan_kernel<false><<<grid, 256, 0, stream()>>>(c, log_size, dshift, dchunks, s);
+            scan_chunk_offsets_kernel<<<4, 1024, 0, stream()>>>(dchunks, n_chunks);
+            seg_scan_kernel<true><<<grid, 256, 0, stream()>>>(c, log_size, dshift, dchunks, s);
+        } else {
+            scan_chunk_sums_kernel<<<dim3(n_chunks, 4), 256, 0, stream()>>>(c, log_size, dshift, dchunks, n_chunks);
+            scan_chunk_offsets_kernel<<<4, 1024, 0, stream()>>>(dchunks, n_chunks);
+            scan_apply_kernel<<<dim3(n_chunks, 4), 256, 0, stream()>>>(c, log_size, dshift, dchunks, n_chunks);
+        }
     }
     CM_LAUNCH_CHECK();
     CM_CUDA(cudaFreeAsync(dchunks, stream()));

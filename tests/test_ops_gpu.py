@@ -396,3 +396,24 @@ def test_sharded_commit_p2p_world1_matches_nccl_variant(cm):
         assert np.array_equal(host(root_a), host(root_b))
     finally:
         peer.close()
+
+
+@pytest.mark.parametrize("L", [1, 4, 10, 11, 12, 13, 16, 19, 22])
+def test_logup_finalize_last_matches_oracle(cm, L):
+    # LogupTraceGenerator::finalize_last (constraint_framework/src/logup.rs:211-251): claimed sum of the last cumulative
+    # column, shift by claimed_sum / n, inclusive prefix sum in coset order (simd/prefix_sum.rs:19; the oracle follows
+    # inclusive_prefix_sum_slow).  L <= 11: single-CTA kernel; L >= 12: the segmented coset-order scan.
+    import ctypes as C
+    n = 1 << L
+    src = orc.splitmix64(0x10C0 + L, 4 * n).reshape(4, n)
+    cols = to_dev_cols(src)
+    ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in cols])
+    claimed = (C.c_uint32 * 4)()
+    cm.check(cm.lib().cm31_logup_finalize_last(ptrs, C.c_uint32(L), claimed))
+    n_inv = pow(n % P, P - 2, P)
+    for k in range(4):
+        total = int(src[k].astype(np.uint64).sum() % P)
+        assert claimed[k] == total
+        shift = total * n_inv % P
+        shifted = ((src[k].astype(np.int64) - shift) % P).astype(np.uint32)
+        assert np.array_equal(host(cols[k]), orc.prefix_sum(shifted, L)), f"coordinate {k}"
