@@ -288,7 +288,11 @@ def test_gather_words(cm):
 
 
 @pytest.mark.parametrize("top,with_prev,col_layers", [(0, False, {0: 2}), (3, True, {}), (5, False, {5: 3, 4: 1, 2: 20}),
-                                                      (10, True, {10: 4, 7: 17, 0: 1}), (10, False, {10: 33})])
+                                                      (10, True, {10: 4, 7: 17, 0: 1}), (10, False, {10: 33}),
+                                                      # layers with many injected columns (1100 x 16 like cairo-m's padding
+                                                      # components): long per-node hash chains
+                                                      (4, True, {4: 1100, 3: 40, 0: 33}), (6, False, {6: 64, 5: 32, 4: 31, 1: 257}),
+                                                      (7, True, {7: 500, 2: 1000})])
 def test_commit_top_layers_matches_layer_by_layer_oracle(cm, top, with_prev, col_layers):
     # the fused top-of-tree launch == MerkleProver::commit's per-layer loop (vcs/prover.rs:52-64)
     mats = {l: orc.splitmix64(0x70 + l, k << l).reshape(k, 1 << l) for l, k in col_layers.items()}
