@@ -52,8 +52,27 @@ __global__ void __launch_bounds__(256) twiddle_kernel(u32* tw, u32* itw, u32 k, 
     const u32 t0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (t0 >= total) return;
     u32 x[4];
+    const u32 rem = total - t0;
+    const u32 j = k - (32 - __clz(rem - 1));
+    const u32 bits = k - 1 - j;  // level j holds 2^bits entries
+    if (bits >= 2) {
+        // The thread's 4 entries sit in one level and their indices differ only in the low 2 bits, i.e. (bit-reversed) in the
+        // TOP 2 bits of `nat`: the group additions for the shared low bits are done once, then x(P + C_q) for
+        // C_q in {0, T[top], T[top-1], T[top] + T[top-1]} (2 products each) — ~2.4x fewer products than 4 independent sums.
+        const u32 level_off = total - (1u << (k - j));
+        u32 nat = bit_reverse(t0 - level_off, bits);  // low 2 bits of the index are 0 -> top 2 bits of nat are 0
+        CirclePointM31 p = tab.i[j];
+        for (u32 b = 0; nat != 0; b++, nat >>= 1)
+            if (nat & 1) p = cp_add(p, tab.t[j + b]);
+        const CirclePointM31 c1 = tab.t[j + bits - 1], c2 = tab.t[j + bits - 2], c3 = cp_add(c1, c2);
+        x[0] = p.x;
+        x[1] = m31_sub(m31_mul(p.x, c1.x), m31_mul(p.y, c1.y));  // index +1 -> top bit of nat
+        x[2] = m31_sub(m31_mul(p.x, c2.x), m31_mul(p.y, c2.y));  // index +2 -> second bit from the top
+        x[3] = m31_sub(m31_mul(p.x, c3.x), m31_mul(p.y, c3.y));
+    } else {
 #pragma unroll
-    for (u32 q = 0; q < 4; q++) x[q] = (t0 + q == total - 1) ? 1u : twiddle_x(tab, k, t0 + q, total);  // pad element (cpu/circle.rs:185-187)
+        for (u32 q = 0; q < 4; q++) x[q] = (t0 + q == total - 1) ? 1u : twiddle_x(tab, k, t0 + q, total);  // pad element (cpu/circle.rs:185-187)
+    }
     // batch inverse of 4 (fields/mod.rs:69-99)
     u32 p01 = m31_mul(x[0], x[1]), p012 = m31_mul(p01, x[2]), p0123 = m31_mul(p012, x[3]);
     u32 inv = m31_inv(p0123);
