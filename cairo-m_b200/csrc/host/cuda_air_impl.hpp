@@ -15,6 +15,8 @@ extern "C" {
 int cm31_bitwise_table_col(int k, uint32_t* col);
 int cm31_unpack_bundles(const uint32_t* bundles_dev, size_t n_real, uint32_t log_size, const uint32_t* accesses_dev,
                         size_t n_accesses, uint32_t* const* out_cols);
+int cm31_unpack_bundles_slots(const uint32_t* bundles_dev, size_t n_real, uint32_t log_size, const uint32_t* accesses_dev,
+                              size_t n_accesses, uint32_t* const* out_cols, uint32_t n_access_slots);
 int cm31_unpack_rows(const uint32_t* rows_dev, size_t n_real, uint32_t n_fields, uint32_t log_size, uint32_t* const* out_cols);
 int cm31_iota(uint32_t* col, size_t n);
 }
@@ -65,12 +67,41 @@ struct CudaAirImpl {
         return m;
     }
     static void staging_wait(u32 mark) { cm_check(cm31_bg_wait(mark)); }
+    // The AoS -> SoA unpack of a component's bundles is issued by write_trace, which knows the component's trace program and
+    // therefore how many of the 8 access slots it reads: the columns of the other slots are allocated (fixed column indices)
+    // but never written — for store_fp_imm (2 accesses) 18 columns instead of 42.
+    struct PendingUnpack {
+        const u32 *rows = nullptr, *accesses = nullptr;
+        size_t n_real = 0, n_accesses = 0;
+        u32 log_size = 0;
+        std::vector<u32*> out;
+        bool active = false;
+    };
+    static PendingUnpack& pending_unpack() {
+        static PendingUnpack p;
+        return p;
+    }
     static std::vector<Col> unpack_bundles(const Words& rows, size_t n_real, const Words& accesses, size_t n_accesses, u32 log_size) {
         std::vector<Col> cols = Col::many(N_BUNDLE_INPUTS, (size_t)1 << log_size);
-        std::vector<u32*> p;
-        for (auto& c : cols) p.push_back(c.ptr());
-        cm_check(cm31_unpack_bundles(rows.ptr(), n_real, log_size, accesses.ptr(), n_accesses, p.data()));
+        PendingUnpack& pu = pending_unpack();
+        // (a still-active entry belongs to a proof that was aborted by an exception: its columns are gone, drop it)
+        pu.out.clear();
+        for (auto& c : cols) pu.out.push_back(c.ptr());
+        pu.rows = rows.ptr();
+        pu.accesses = accesses.ptr();
+        pu.n_real = n_real;
+        pu.n_accesses = n_accesses;
+        pu.log_size = log_size;
+        pu.active = true;
         return cols;
+    }
+    // access slots read by a trace program: the highest input column it loads
+    static u32 access_slots_read(const AirProgram& prog) {
+        u32 max_col = 0;
+        for (uint64_t ins : prog.code)
+            if ((ins & 0xff) == OP_LOAD) max_col = std::max<u32>(max_col, (u32)((ins >> 24) & 0xfffff));
+        if (max_col < (u32)IN_ACC_BASE) return 0;
+        return std::min<u32>(MAX_ACCESSES, (max_col - IN_ACC_BASE) / 4 + 1);
     }
     static std::vector<Col> unpack_rows(const Words& rows, size_t n_real, u32 n_fields, u32 log_size) {
         std::vector<Col> cols = Col::many(n_fields, (size_t)1 << log_size);
@@ -92,6 +123,12 @@ struct CudaAirImpl {
         }
         AirProgram prog = it->second;
         for (u32 slot : prog.rowlt_slots) prog.consts[slot] = n_real;
+        PendingUnpack& pu = pending_unpack();
+        if (pu.active) {  // an opcode component: its inputs are unpacked here, only as wide as the program reads
+            if (inputs.empty() || pu.out.empty() || inputs[0].ptr() != pu.out[0]) throw std::logic_error("write_trace: pending unpack belongs to other inputs");
+            pu.active = false;
+            cm_check(cm31_unpack_bundles_slots(pu.rows, pu.n_real, pu.log_size, pu.accesses, pu.n_accesses, pu.out.data(), access_slots_read(prog)));
+        }
         std::vector<CircleEvaluation<B>> out(Eval::N_TRACE_COLUMNS);
         std::vector<Col> slab = Col::many(Eval::N_TRACE_COLUMNS, (size_t)1 << eval.log_size());
         std::vector<Col*> outp;

@@ -8,6 +8,8 @@
 //                                                    components/opcodes/store_fp_fp.rs:169
 // One thread per (row); bundle words are read with 128-bit loads, the access log is gathered
 // through the per-step span, every output column is written coalesced.
+#include <cstdlib>
+
 #include "air/cairo_components.hpp"
 #include "common.cuh"
 
@@ -15,7 +17,7 @@ namespace cm31 {
 
 __global__ void __launch_bounds__(256) unpack_bundles_kernel(const uint4* __restrict__ bundles, u32 n_real, u32 log_size,
                                                              const uint4* __restrict__ accesses, u32 n_accesses,
-                                                             u32* const* __restrict__ out) {
+                                                             u32* const* __restrict__ out, u32 n_slots) {
     u32 row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (1u << log_size)) return;
     u32 w[12];
@@ -34,6 +36,7 @@ __global__ void __launch_bounds__(256) unpack_bundles_kernel(const uint4* __rest
     u32 start = w[10], len = w[11];
 #pragma unroll
     for (int k = 0; k < MAX_ACCESSES; k++) {
+        if ((u32)k >= n_slots) break;  // access slots the component's trace program never reads are not written
         uint4 acc = make_uint4(0, 0, 0, 0);
         if ((u32)k < len && start + k < n_accesses) acc = __ldg(accesses + start + k);
         out[IN_ACC_BASE + 4 * k + ACC_ADDRESS][row] = acc.x;
@@ -67,16 +70,27 @@ using namespace cm31;
 
 extern "C" {
 
+int cm31_unpack_bundles_slots(const uint32_t* bundles_dev, size_t n_real, uint32_t log_size, const uint32_t* accesses_dev,
+                              size_t n_accesses, uint32_t* const* out_cols, uint32_t n_access_slots);
 int cm31_unpack_bundles(const uint32_t* bundles_dev, size_t n_real, uint32_t log_size, const uint32_t* accesses_dev,
                         size_t n_accesses, uint32_t* const* out_cols) {
+    return cm31_unpack_bundles_slots(bundles_dev, n_real, log_size, accesses_dev, n_accesses, out_cols, MAX_ACCESSES);
+}
+// n_access_slots: only the first n_access_slots x 4 access columns are written (a store_fp_imm step has 2 accesses, a jump
+// none: the other columns of the 8-slot layout are never read by that component's trace program)
+int cm31_unpack_bundles_slots(const uint32_t* bundles_dev, size_t n_real, uint32_t log_size, const uint32_t* accesses_dev,
+                              size_t n_accesses, uint32_t* const* out_cols, uint32_t n_access_slots) {
     CM_REQUIRE(log_size <= 30 && n_real <= ((size_t)1 << log_size), "unpack_bundles: more rows than the padded size");
+    CM_REQUIRE(n_access_slots <= (uint32_t)MAX_ACCESSES, "unpack_bundles: at most 8 access slots");
+    static const bool full = getenv("CM31_FULL_UNPACK") != nullptr;  // A/B runs: write all 8 slots as the first version did
+    if (full) n_access_slots = MAX_ACCESSES;
     DeviceTable dout;
     if (int e = dout.upload(out_cols, N_BUNDLE_INPUTS * sizeof(void*))) return e;
     size_t n = (size_t)1 << log_size;
-    ProfScope prof("unpack_bundles", 48ull * n_real + 4ull * N_BUNDLE_INPUTS * n);
+    ProfScope prof("unpack_bundles", 48ull * n_real + 4ull * (IN_ACC_BASE + 4ull * n_access_slots) * n);
     unpack_bundles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>((const uint4*)bundles_dev, (u32)n_real, log_size,
                                                                             (const uint4*)accesses_dev, (u32)n_accesses,
-                                                                            (u32* const*)dout.d);
+                                                                            (u32* const*)dout.d, n_access_slots);
     CM_LAUNCH_CHECK();
     return 0;
 }
