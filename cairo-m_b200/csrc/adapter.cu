@@ -312,7 +312,7 @@ int cm31_adapter_stage_logs(const uint32_t* trace_host, size_t n_trace, const ui
                             size_t n_init, int background, void** plan_out) {
     CM_REQUIRE(plan_out && trace_host && mem_host && init_host, "adapter_scan: null argument");
     CM_REQUIRE(n_trace >= 2, "adapter: empty trace");
-    CM_REQUIRE(n_trace - 1 < (1u << 31) - 1 && n_mem < 0xFFFFFFF0u && n_mem >= 1 && n_init >= 1 && n_init < (1u << 31), "adapter_scan: sizes out of range");
+    CM_REQUIRE(n_trace - 1 < (1u << 31) - 1 && n_mem < (1u << 31) - 1 && n_mem >= 1 && n_init >= 1 && n_init < (1u << 31), "adapter_scan: sizes out of range");
     if (int e = upload_opcode_tables()) return e;
     std::unique_ptr<AdapterPlan> pl(new AdapterPlan());
     AdapterPlan& P_ = *pl;
