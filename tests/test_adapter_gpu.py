@@ -188,3 +188,22 @@ def test_prefetched_logs_give_the_same_input_and_proof(cm):
     # logs that are never imported can be dropped
     lg = prefetch(n_b)
     cm.check(lib.cm31_adapter_logs_destroy(lg))
+
+
+def test_device_adapted_headline_size_proof_equals_host_adapted(cm):
+    # 2^22 VM steps (the BASELINE workload): the proof from the device-adapted input is byte-identical to the proof from the
+    # host-adapted one (which the headline-size test of test_cairo_gpu.py verifies with the oracle verifier)
+    n = (1 << 19) - 1
+    host = ch.GpuFibInput(cm, n)
+    try:
+        assert host.steps == 1 << 22
+        want, _ = host.prove()
+    finally:
+        host.close()
+    dev = ch.GpuAdaptedInput(cm, n)
+    try:
+        assert dev.steps == 1 << 22
+        got, _ = dev.prove()
+    finally:
+        dev.close()
+    assert got == want
