@@ -27,7 +27,7 @@
 //   bitwise (table)      crates/prover/src/preprocessed/bitwise.rs:72-140 (multiplicities), :196-215 (evaluate), :253-290 (columns)
 //   memory         crates/prover/src/components/memory.rs:93-195, :294-366
 //   merkle         crates/prover/src/components/merkle.rs:73-170, :285-377
-//   poseidon2      crates/prover/src/components/poseidon2.rs:143-290, :385-505 (constants: csrc/cairo/poseidon2.hpp, PLACEHOLDER)
+//   poseidon2      crates/prover/src/components/poseidon2.rs:143-290, :385-505 (constants: csrc/cairo/poseidon2_constants.hpp)
 //   clock_update   crates/prover/src/components/clock_update.rs:70-160, :217-262
 //   range_check_N  crates/prover/src/preprocessed/range_check/range_check_macro.rs:62-112, :171-183
 #pragma once
@@ -2187,8 +2187,8 @@ struct MerkleEval : OpcodeEvalBase {
 };
 
 // ------------------------------------------------------------------ poseidon2 (one permutation per row)
-//   crates/prover/src/components/poseidon2.rs:143-290 (write_trace), :385-505 (evaluate); round structure and the
-//   (placeholder) constants in csrc/cairo/poseidon2.hpp.  inputs: the 16 words of the initial state.
+//   crates/prover/src/components/poseidon2.rs:143-290 (write_trace), :385-505 (evaluate); round structure in
+//   csrc/cairo/poseidon2.hpp, constants in csrc/cairo/poseidon2_constants.hpp (KAT-pinned).  inputs: the 16 words of the initial state.
 struct Poseidon2Eval : OpcodeEvalBase {
     static constexpr int N_TRACE_COLUMNS = 1 + POSEIDON2_T * (1 + POSEIDON2_FULL_ROUNDS * 3) + 3 * POSEIDON2_PARTIAL_ROUNDS;  // 443
     static const char* name() { return "poseidon2"; }

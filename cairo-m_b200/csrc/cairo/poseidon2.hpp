@@ -1,19 +1,18 @@
 // Poseidon2 over M31, state size 16, 8 full + 14 partial rounds, S-box x^5: the hash of the memory commitment
 // (crates/prover/src/poseidon2.rs:10-57, crates/prover/src/components/poseidon2.rs:70-140).
 //
-// *** PLACEHOLDER CONSTANTS -- parity unpinned. ***  The reference takes its round constants and internal diagonal from
-// `zkhash 0.2.0` (git+https://github.com/AntoineFONDEUR/poseidon2?branch=poseidon2-M31#5f715d0c:
-// poseidon2_instance_m31::{RC16, MAT_DIAG16_M_1}, extracted by crates/prover/build.rs:26-106).  That dependency is not
-// vendored in the reference checkout and there is no network, so the tables below are generated from a fixed seed
-// instead.  Everything else -- the permutation structure, the Merkle tree built with it, the merkle / poseidon2 AIRs --
-// is restated from the reference code, and GPU prover, oracle prover and oracle verifier share these tables, so proofs
-// are self-consistent; they are NOT interoperable with the stock Rust verifier until the real tables are dropped in
-// (the reference KAT of crates/prover/tests/poseidon2.rs:15-35 is an expected failure in tests/test_oracle_cairo.py).
+// Constants: the reference takes its round constants and internal diagonal from `zkhash 0.2.0`
+// (git+https://github.com/AntoineFONDEUR/poseidon2?branch=poseidon2-M31#5f715d0c:
+// poseidon2_instance_m31::{RC16, MAT_DIAG16_M_1}, extracted by crates/prover/build.rs:26-106), a dependency that is not
+// vendored in the reference checkout.  `poseidon2_constants.hpp` holds those tables re-derived with the Poseidon2
+// parameter script's Grain LFSR (tools/gen_poseidon2_constants.py); they reproduce the reference known-answer test
+// (crates/prover/tests/poseidon2.rs:15-35), which is a hard test in tests/test_oracle_cairo.py.
 #pragma once
 #include <array>
 #include <cstdint>
 
 #include "../field.cuh"
+#include "poseidon2_constants.hpp"
 
 namespace cm31 {
 
@@ -24,22 +23,10 @@ struct Poseidon2Constants {
     u32 internal[POSEIDON2_PARTIAL_ROUNDS];            // INTERNAL_ROUND_CONSTS
     u32 diag[POSEIDON2_T];                             // INTERNAL_MATRIX (the diagonal of M_I - 1)
     Poseidon2Constants() {
-        uint64_t s = 0x706f736569646f6eull;  // "poseidon": placeholder seed
-        auto next = [&]() {
-            s += 0x9e3779b97f4a7c15ull;
-            uint64_t z = s;
-            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-            z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-            z ^= z >> 31;
-            return (u32)(z % P);
-        };
-        for (auto& r : external)
-            for (u32& v : r) v = next();
-        for (u32& v : internal) v = next();
-        for (u32& v : diag) {
-            do v = next();
-            while (v == 0);
-        }
+        for (int r = 0; r < POSEIDON2_FULL_ROUNDS; r++)
+            for (int i = 0; i < POSEIDON2_T; i++) external[r][i] = POSEIDON2_EXTERNAL_RC[r][i];
+        for (int r = 0; r < POSEIDON2_PARTIAL_ROUNDS; r++) internal[r] = POSEIDON2_INTERNAL_RC[r];
+        for (int i = 0; i < POSEIDON2_T; i++) diag[i] = POSEIDON2_INTERNAL_DIAG[i];
     }
 };
 inline const Poseidon2Constants& poseidon2_constants() {

@@ -6,10 +6,8 @@
 // components/opcodes/mod.rs:41-78,223-268 (opcode dispatch + order), public_data.rs:236-412,
 // preprocessed/mod.rs:43-82, relations.rs:47.  Transcript order = SURVEY.md Appendix A.
 //
-// Scope of this round: the Cpu opcode components exercised by
-// fibonacci_loop, Memory, ClockUpdate and RangeCheck8/16/20.  The Merkle/Poseidon2 memory
-// commitment components (blocked on the un-vendored zkhash constants) and the
-// u32/bitwise opcode families are not part of the statement yet.
+// Scope: all 34 components of the reference's statement -- the 26 opcode components,
+// memory, merkle, clock_update, poseidon2, range_check_8/16/20 and the bitwise table.
 #pragma once
 #include <functional>
 #include <memory>

@@ -11,9 +11,8 @@
 //   update_multiplicities   crates/prover/src/adapter/memory.rs:411-457
 //   import_internal         crates/prover/src/adapter/mod.rs:97-193
 // Differences, by design: boundary-memory rows are emitted in ascending address order (the
-// reference iterates two std HashMaps, i.e. in a per-run random order, components/memory.rs:105-109),
-// and the Poseidon2 ROUND CONSTANTS are placeholders (csrc/cairo/poseidon2.hpp): the memory roots are
-// real Merkle roots under that placeholder permutation.
+// reference iterates two std HashMaps, i.e. in a per-run random order, components/memory.rs:105-109).
+// The memory roots are Merkle roots under the reference's Poseidon2-M31 instance (csrc/cairo/poseidon2_constants.hpp).
 #pragma once
 #include <cstdint>
 #include <map>

@@ -222,7 +222,7 @@ inline void verify_cairo_m(const cm31::CairoProof& proof, cm31::PcsConfig pcs_co
 // Logup balance (InteractionClaim::claimed_sum, components/mod.rs:288-302 + public_data.rs:287-399):
 //   Σ claimed sums + public-data sum == 0.
 // Every relation must balance exactly (the Merkle / Poseidon2 relations through the merkle and poseidon2 components,
-// under the placeholder Poseidon2 constants of csrc/cairo/poseidon2.hpp).
+// under the Poseidon2 tables of csrc/cairo/poseidon2_constants.hpp, pinned by the reference KAT).
 inline QM31 logup_residual(const cm31::CairoProof& proof, const cm31::ProverInput& input) {
     // replay the transcript up to Relations::draw
     OChannel channel;

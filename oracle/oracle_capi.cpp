@@ -306,7 +306,7 @@ int orc_program_logup_residual(u32 program_id, u32 n, const uint8_t* proof_bytes
     }
 }
 
-// Poseidon2 permutation of csrc/cairo/poseidon2.hpp (PLACEHOLDER constants) -- the reference KAT cannot hold with them
+// Poseidon2 permutation of csrc/cairo/poseidon2.hpp; checked against the reference KAT (crates/prover/tests/poseidon2.rs:15-35)
 int orc_poseidon2_permutation(const u32* in16, u32* out16) {
     std::array<u32, 16> in;
     for (int i = 0; i < 16; i++) in[i] = in16[i];

@@ -98,8 +98,6 @@ def test_all_34_components_are_in_the_proof(fib10):
     assert n == 34  # 26 opcode components, memory, merkle, clock_update, poseidon2, range_check_8/16/20, bitwise
 
 
-@pytest.mark.xfail(strict=True, reason="PARITY UNPINNED: the zkhash round constants (RC16, MAT_DIAG16_M_1) are not in the reference "
-                                       "checkout (un-vendored git dependency); csrc/cairo/poseidon2.hpp uses placeholder tables")
 def test_poseidon2_reference_kat():
     # crates/prover/tests/poseidon2.rs:15-35: permutation of (0, 1, .., 15)
     import ctypes as C
