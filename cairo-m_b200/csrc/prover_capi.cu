@@ -479,6 +479,65 @@ int cm31_adapter_logs_destroy(cm31_adapter_logs* logs) {
 
 // prove_cairo_m::<Blake2sMerkleChannel> (crates/prover/src/prover.rs:23) on the CUDA backend.
 // timings_ms (optional, 5 doubles): preprocessed, trace, interaction, stark, total.
+// AIR shapes of the 34 components as captured from their `evaluate` bodies (the InfoEvaluator pass of
+// FrameworkComponent::new, S/constraint_framework/src/component.rs:139-180, info.rs): host-only, no device work.
+extern "C++" {
+template <class E>
+static auto eval_opcodes(const E&, int) -> decltype(E::opcodes()) { return E::opcodes(); }
+template <class E>
+static std::vector<cm31::u32> eval_opcodes(const E&, long) { return {}; }
+}
+int cm31_air_shapes(char* buf, size_t cap, size_t* len) {
+    try {
+        static const char* rel_names[N_CAIRO_RELATIONS] = {"registers", "memory", "merkle", "poseidon2", "range_check_8", "range_check_16",
+                                                           "range_check_20", "bitwise"};
+        RelationSet dummy;
+        for (int r = 0; r < N_CAIRO_RELATIONS; r++) dummy.relations.push_back(RelationElements::dummy(cairo_relation_size(r)));
+        std::vector<std::string> names = cairo_component_names();
+        std::vector<u32> ls(names.size(), LOG_N_LANES);
+        CairoComponents<CudaAirImpl> comps(ls, &dummy);
+        std::string out = "{\"relations\": {";
+        for (int r = 0; r < N_CAIRO_RELATIONS; r++)
+            out += std::string(r ? ", " : "") + "\"" + rel_names[r] + "\": " + std::to_string(cairo_relation_size(r));
+        out += "}, \"components\": [";
+        size_t ci = 0;
+        comps.for_each([&](auto& c) {
+            const ExprEvaluator& ev = c.ev;
+            if (ci) out += ", ";
+            out += "{\"name\": \"" + names[ci] + "\", \"opcodes\": [";
+            std::vector<u32> ops = eval_opcodes(c.eval, 0);
+            for (size_t i = 0; i < ops.size(); i++) out += (i ? ", " : "") + std::to_string(ops[i]);
+            out += "], \"n_trace_columns\": " + std::to_string(c.n_trace_columns());
+            out += ", \"n_interaction_columns\": " + std::to_string(c.n_interaction_columns());
+            out += ", \"n_preprocessed_columns\": " + std::to_string(ev.preprocessed_ids.size());
+            out += ", \"n_constraints\": " + std::to_string(ev.n_constraints());
+            size_t prev_masks = 0;  // interaction columns read at offsets [-1, 0]: the last logup batch (lib.rs:210-234)
+            for (auto& offs : ev.mask_offsets[INTERACTION_TRACE_IDX]) prev_masks += offs.size() == 2;
+            out += ", \"n_cumsum_columns\": " + std::to_string(prev_masks);
+            out += ", \"n_lookups\": " + std::to_string(ev.logup_uses.size()) + ", \"lookups\": {";
+            bool first = true;
+            for (int r = 0; r < N_CAIRO_RELATIONS; r++) {
+                size_t k = 0, widest = 0;
+                for (auto& u : ev.logup_uses)
+                    if (u.relation == r) k++, widest = std::max(widest, u.values.size());
+                if (!k) continue;
+                out += std::string(first ? "" : ", ") + "\"" + rel_names[r] + "\": [" + std::to_string(k) + ", " + std::to_string(widest) + "]";
+                first = false;
+            }
+            out += "}}";
+            ci++;
+        });
+        out += "]}";
+        if (len) *len = out.size();
+        CM_REQUIRE(buf == nullptr || out.size() < cap, "air_shapes: buffer too small");
+        if (buf) memcpy(buf, out.c_str(), out.size() + 1);
+        return 0;
+    } catch (const std::exception& e) {
+        set_error(e.what());
+        return -2;
+    }
+}
+
 int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out,
                        size_t proof_cap, size_t* proof_len, double* timings_ms) {
     try {

@@ -316,6 +316,14 @@ int cm31_vm_trace_data(const cm31_vm_trace* h, const uint32_t** trace, const uin
                        const uint32_t** initial_memory, uint32_t public_ranges[6]);
 int cm31_vm_trace_destroy(cm31_vm_trace* h);
 
+/* The AIR shapes of the 34 components as captured from their `evaluate` bodies — what FrameworkComponent::new learns from its
+ * InfoEvaluator pass (S/constraint_framework/src/component.rs:139-180, info.rs) — as JSON: {"relations": {name: size},
+ * "components": [{name, opcodes, n_trace_columns, n_interaction_columns, n_preprocessed_columns, n_constraints,
+ * n_cumsum_columns, n_lookups, lookups: {relation: [count, widest tuple]}}]} in claim order.  Host only (no device work).
+ * The Rust shim asserts these against its own InfoEvaluator counts before it trusts a generated kernel; tests/test_air_shapes.py
+ * checks them against the constants of P/src/components/**. buf may be NULL to query the length. */
+int cm31_air_shapes(char* buf, size_t cap, size_t* len);
+
 /* S/examples/src/wide_fibonacci/mod.rs:22-43 — the bring-up AIR (parity tests only) */
 int cm31_prove_wide_fibonacci(uint32_t log_n_rows, uint32_t n_cols, uint32_t pow_bits, uint32_t n_queries,
                               uint8_t* proof_out, size_t proof_cap, size_t* proof_len);

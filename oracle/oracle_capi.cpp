@@ -314,6 +314,56 @@ int orc_poseidon2_permutation(const u32* in16, u32* out16) {
     for (int i = 0; i < 16; i++) out16[i] = out[i];
     return 0;
 }
+// cm31::MemoryModel (csrc/cairo/vm.hpp: the host restatement of adapter::memory::Memory, crates/prover/src/adapter/memory.rs:405-537)
+// driven by a script of pushes, so the reference's own Memory::push unit tests (memory.rs:546-858) can be replayed on it.
+//   entries  : (address, value[4], clock) x n
+//   args_out : MemoryArg per push = (address, prev_clock, clock, prev_val[4], value[4]), 11 words
+//   cu_out   : clock_update_data rows (address, prev_clk, value[4]), 6 words each, in push order
+//   cells    : present cells of initial_memory then final_memory as (address, value[4], clock, multiplicity), 7 words, ascending address
+int orc_memory_push_script(const u32* initial_memory, size_t n_initial, const u32* entries, size_t n, u32* args_out, u32* cu_out,
+                           size_t cu_cap, size_t* n_cu, u32* init_cells, u32* final_cells, size_t cells_cap, size_t* n_init_cells,
+                           size_t* n_final_cells) {
+    using namespace cm31;
+    try {
+        std::vector<Word4> init(n_initial);
+        for (size_t a = 0; a < n_initial; a++)
+            for (int k = 0; k < 4; k++) init[a].v[k] = initial_memory[4 * a + k];
+        MemoryModel m(init);
+        for (size_t i = 0; i < n; i++) {
+            const u32* e = entries + 6 * i;
+            MemoryModel::Arg a = m.push(e[0], Word4{{e[1], e[2], e[3], e[4]}}, e[5]);
+            u32* o = args_out + 11 * i;
+            o[0] = a.address, o[1] = a.prev_clock, o[2] = a.clock;
+            for (int k = 0; k < 4; k++) o[3 + k] = a.prev_val.v[k], o[7 + k] = a.value.v[k];
+        }
+        *n_cu = m.clock_update_data.size();
+        if (*n_cu > cu_cap) throw std::runtime_error("clock-update capacity");
+        for (size_t i = 0; i < *n_cu; i++) {
+            const ClockUpdateRow& r = m.clock_update_data[i];
+            cu_out[6 * i] = r.address, cu_out[6 * i + 1] = r.prev_clk;
+            for (int k = 0; k < 4; k++) cu_out[6 * i + 2 + k] = r.value[k];
+        }
+        auto dump = [&](const std::vector<MemoryModel::Cell>& cells, u32* out, size_t* n_out) {
+            size_t c = 0;
+            for (size_t a = 0; a < cells.size(); a++) {
+                if (!cells[a].present) continue;
+                if (c >= cells_cap) throw std::runtime_error("cell capacity");
+                out[7 * c] = (u32)a;
+                for (int k = 0; k < 4; k++) out[7 * c + 1 + k] = cells[a].value.v[k];
+                out[7 * c + 5] = cells[a].clock, out[7 * c + 6] = cells[a].multiplicity;
+                c++;
+            }
+            *n_out = c;
+        };
+        dump(m.initial, init_cells, n_init_cells);
+        dump(m.final_, final_cells, n_final_cells);
+        return 0;
+    } catch (const std::exception& e) {
+        g_orc_err = e.what();
+        return 1;
+    }
+}
+
 // The scenarios of the reference's adapter/merkle.rs tests (:262-424) on build_partial_merkle_tree; 0 = all hold.
 int orc_merkle_selftest(void) {
     using namespace cm31;
