@@ -193,19 +193,19 @@ def dist_selftest(rank: int, world: int):
 def measure_adapter(cm, lib, torch, program_id, n, k_steps, vm_steps, proof_buf, cap, proof_len, tm):
     t0 = time.perf_counter()
     vt = C.c_void_p()
-    cm.check(lib.cm31_vm_trace_create(C.c_uint32(program_id), C.c_uint32(n), C.byref(vt)))
+    cm.check(lib.cm31_test_vm_trace_create(C.c_uint32(program_id), C.c_uint32(n), C.byref(vt)))
     vm_s = time.perf_counter() - t0
     t0 = time.perf_counter()
     hh = C.c_void_p()
-    cm.check(lib.cm31_program_input_create(C.c_uint32(program_id), C.c_uint32(n), C.byref(hh)))  # VM + host adapter
+    cm.check(lib.cm31_test_program_input_create(C.c_uint32(program_id), C.c_uint32(n), C.byref(hh)))  # VM + host adapter
     host_adapter_ms = max(0.0, (time.perf_counter() - t0) - vm_s) * 1e3
     cm.check(lib.cm31_input_destroy(hh))
     info = (C.c_uint64 * 4)()
-    cm.check(lib.cm31_vm_trace_info(vt, info))
+    cm.check(lib.cm31_test_vm_trace_info(vt, info))
     n_trace, n_mem, n_init = int(info[0]), int(info[1]), int(info[2])
     pt, pm, pi = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
     ranges = (C.c_uint32 * 6)()
-    cm.check(lib.cm31_vm_trace_data(vt, C.byref(pt), C.byref(pm), C.byref(pi), ranges))
+    cm.check(lib.cm31_test_vm_trace_data(vt, C.byref(pt), C.byref(pm), C.byref(pi), ranges))
     import numpy as np
 
     def pinned(ptr, words):  # the logs in page-locked host memory, as a runner would hand them over
@@ -213,7 +213,7 @@ def measure_adapter(cm, lib, torch, program_id, n, k_steps, vm_steps, proof_buf,
         return torch.from_numpy(a.view(np.int32)).clone().pin_memory()
 
     trace, mem, init = pinned(pt, 2 * n_trace), pinned(pm, 5 * n_mem), pinned(pi, 4 * n_init)
-    cm.check(lib.cm31_vm_trace_destroy(vt))
+    cm.check(lib.cm31_test_vm_trace_destroy(vt))
     as_p = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_uint32))
 
     def import_logs():
@@ -295,7 +295,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     programs = {"fibonacci_loop": 0, "array_sum": 1, "u32_counter": 2, "u32_mix": 3}
     n = args.iterations if args.iterations else fib_iterations(args.log_steps)
     h = C.c_void_p()
-    cm.check(lib.cm31_program_input_create(C.c_uint32(programs[args.program]), C.c_uint32(n), C.byref(h)))
+    cm.check(lib.cm31_test_program_input_create(C.c_uint32(programs[args.program]), C.c_uint32(n), C.byref(h)))
     info = (C.c_uint64 * 5)()
     cm.check(lib.cm31_input_info(h, info))
     vm_steps, h2d_bytes = int(info[0]), int(info[4])

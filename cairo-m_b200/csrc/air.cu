@@ -37,7 +37,7 @@ template <int NREGS>
 __global__ void __launch_bounds__(128) air_program_kernel(const u32* const* __restrict__ in_cols, u32* const* __restrict__ out_cols,
                                                           u32 row_log, u32 trace_log, const uint64_t* __restrict__ code, u32 n_instr,
                                                           const u32* __restrict__ consts, const u32* __restrict__ denom_inv,
-                                                          u32* acc0, u32* acc1, u32* acc2, u32* acc3) {
+                                                          u32* acc0, u32* acc1, u32* acc2, u32* acc3, u32 hist_bins, u32* err) {
     const u32 row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (1u << row_log)) return;
     u32 regs[NREGS];
@@ -97,9 +97,7 @@ __global__ void __launch_bounds__(128) air_program_kernel(const u32* const* __re
             case OP_HIST: {
                 // lookups of a fibonacci-like trace hit a handful of bins (clock deltas, small offsets):
                 // aggregate equal values across the warp so each distinct value costs one atomic
-                const u32 v = regs[a];
-                const unsigned peers = __match_any_sync(__activemask(), v);
-                if ((threadIdx.x & 31u) == (u32)(__ffs(peers) - 1)) atomicAdd(out_cols[b] + v, (u32)__popc(peers));
+                gen_hist(out_cols[b], regs[a], hist_bins, err);  // bounds-checked (air_gen.cuh)
                 break;
             }
             case OP_INV: regs[dst] = m31_inv(regs[a]); break;
@@ -126,9 +124,23 @@ __global__ void __launch_bounds__(128) air_program_kernel(const u32* const* __re
 
 static int g_air_mode = 0;  // 0 = AOT-specialised kernel when one exists, 1 = always the bytecode interpreter
 
+// device word collecting AIR_ERR_* bits of every AIR program launched since the last cm31_air_error_check
+static u32* air_err_flag() {
+    static u32* flag[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!flag[dev & 63]) {
+        if (cudaMalloc(&flag[dev & 63], 4) != cudaSuccess) return nullptr;
+        cudaMemset(flag[dev & 63], 0, 4);
+    }
+    return flag[dev & 63];
+}
+
 static int run_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* const* out_cols, size_t n_out, u32 row_log,
                        u32 trace_log, const uint64_t* code, size_t n_instr, u32 n_regs, const u32* consts, size_t n_consts,
-                       const u32* denom_inv_host, size_t n_denom, uint32_t* const* acc4) {
+                       const u32* denom_inv_host, size_t n_denom, uint32_t* const* acc4, u32 hist_bins = 0) {
+    u32* err = air_err_flag();
+    CM_REQUIRE(err != nullptr, "air: cannot allocate the error word");
     CM_REQUIRE(row_log <= 30, "air: too many rows");
     CM_REQUIRE(n_regs <= 2048, "air: program needs more than 2048 registers");
     CM_REQUIRE(trace_log <= row_log, "air: trace domain larger than the evaluation domain");
@@ -139,7 +151,7 @@ static int run_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* co
             CM_REQUIRE(n_denom == ((size_t)1 << (row_log - trace_log)), "air: wrong number of denominator inverses");
             if (int e = ddenom_gen.upload(denom_inv_host, n_denom * 4)) return e;
         }
-        GenLaunch gl{in_cols, n_in, out_cols, n_out, row_log, trace_log, consts, n_consts, (const u32*)ddenom_gen.d, acc4};
+        GenLaunch gl{in_cols, n_in, out_cols, n_out, row_log, trace_log, consts, n_consts, (const u32*)ddenom_gen.d, acc4, hist_bins, err};
         size_t rows = (size_t)1 << row_log;
         ProfScope prof(acc4 ? "constraint_eval" : "air_program", acc4 ? 4ull * rows * n_in + 32ull * rows : 4ull * rows * (n_in + n_out));
         if (int e = gen->launch(gl)) return e;
@@ -163,7 +175,7 @@ static int run_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* co
 #define CM_AIR_LAUNCH(NR)                                                                                              \
     air_program_kernel<NR><<<blocks, threads, 0, stream()>>>((const u32* const*)din.d, (u32* const*)dout.d, row_log,   \
                                                              trace_log, (const uint64_t*)dcode.d, (u32)n_instr,        \
-                                                             (const u32*)dconsts.d, (const u32*)ddenom.d, a0, a1, a2, a3)
+                                                             (const u32*)dconsts.d, (const u32*)ddenom.d, a0, a1, a2, a3, hist_bins, err)
     if (n_regs <= 64) CM_AIR_LAUNCH(64);
     else if (n_regs <= 128) CM_AIR_LAUNCH(128);
     else if (n_regs <= 256) CM_AIR_LAUNCH(256);
@@ -417,8 +429,37 @@ int cm31_constraint_eval(const uint32_t* const* cols, size_t n_cols, uint32_t tr
 int cm31_air_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* const* out_cols, size_t n_out,
                      uint32_t log_size, const uint64_t* code, size_t n_instr, uint32_t n_regs, const uint32_t* consts,
                      size_t n_consts) {
+    for (size_t i = 0; i < n_instr; i++)
+        CM_REQUIRE((code[i] & 0xff) != OP_HIST, "air_program: histogram programs go through cm31_air_lookups (the bin count bounds OP_HIST)");
     return run_program(in_cols, n_in, out_cols, n_out, log_size, log_size, code, n_instr, n_regs, consts, n_consts,
                        nullptr, 0, nullptr);
+}
+
+int cm31_air_lookups(const uint32_t* const* in_cols, size_t n_in, uint32_t* bins, uint32_t log_bins, uint32_t log_size,
+                     const uint64_t* code, size_t n_instr, uint32_t n_regs, const uint32_t* consts, size_t n_consts) {
+    CM_REQUIRE(bins != nullptr && log_bins <= 30, "air_lookups: bad bin column");
+    for (size_t i = 0; i < n_instr; i++) {
+        const u32 op = (u32)(code[i] & 0xff), b = (u32)((code[i] >> 44) & 0xfffff);
+        CM_REQUIRE(op != OP_STORE_E && op != OP_STORE_F, "air_lookups: a lookup program only counts");
+        CM_REQUIRE(op != OP_HIST || b == 0, "air_lookups: one bin column per call");
+    }
+    uint32_t* out[1] = {bins};
+    return run_program(in_cols, n_in, out, 1, log_size, log_size, code, n_instr, n_regs, consts, n_consts, nullptr, 0, nullptr,
+                       1u << log_bins);
+}
+
+int cm31_air_error_check(void) {
+    u32* err = air_err_flag();
+    CM_REQUIRE(err != nullptr, "air: cannot allocate the error word");
+    u32 bits = 0;
+    CM_CUDA(cudaMemcpyAsync(&bits, err, 4, cudaMemcpyDeviceToHost, stream()));
+    CM_CUDA(cudaStreamSynchronize(stream()));
+    if (bits) {
+        CM_CUDA(cudaMemsetAsync(err, 0, 4, stream()));
+        CM_REQUIRE(!(bits & AIR_ERR_LOOKUP_OUT_OF_TABLE), "lookup outside its table");
+        CM_REQUIRE(false, "air: device error");
+    }
+    return 0;
 }
 
 // claimed_sum_dev: 4 device words receiving the claimed sum; nothing is synchronised.

@@ -21,7 +21,10 @@ struct GenLaunch {
     size_t n_consts;
     const u32* denom_inv_dev;  // device, or null
     uint32_t* const* acc4;     // host array of 4 device pointers, or null
+    u32 hist_bins;             // size of the bin column OP_HIST counts into (0 for programs without histograms)
+    u32* err_flag;             // device word: AIR_ERR_* bits (cm31_air_error_check)
 };
+enum : u32 { AIR_ERR_LOOKUP_OUT_OF_TABLE = 1 };
 
 struct GenEntry {
     uint64_t hash;
@@ -43,7 +46,14 @@ __device__ __forceinline__ u32 gen_offset_row(u32 row, u32 trace_log, u32 eval_l
     return bit_reverse(idx, eval_log);
 }
 
-__device__ __forceinline__ void gen_hist(u32* bins, u32 v) {
+__device__ __forceinline__ void gen_hist(u32* bins, u32 v, u32 n_bins, u32* err) {
+    // A looked-up value comes from witness data (clock deltas, u32 limbs, bitwise tuples): outside the table it must not
+    // index the bin column -- the reference panics on the slice index (range_check_macro.rs:72-84), here the proof fails
+    // with "lookup outside its table" (cm31_air_error_check).
+    if (v >= n_bins) {
+        atomicOr(err, AIR_ERR_LOOKUP_OUT_OF_TABLE);
+        return;
+    }
     // equal values across the warp cost one atomic (lookups of a loop-shaped trace hit few bins)
     const unsigned peers = __match_any_sync(__activemask(), v);
     if ((threadIdx.x & 31u) == (u32)(__ffs(peers) - 1)) atomicAdd(bins + v, (u32)__popc(peers));
@@ -100,4 +110,4 @@ using cm31::g_qm_mul;
         a.out[(slot) + 2][row] = (e).c; \
         a.out[(slot) + 3][row] = (e).d; \
     } while (0)
-#define hist(slot, f) cm31::gen_hist(a.out[slot], (f))
+#define hist(slot, f) cm31::gen_hist(a.out[slot], (f), a.hist_bins, a.err)

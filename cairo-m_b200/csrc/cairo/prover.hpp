@@ -493,6 +493,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
             shape.for_each(emit);
         }
         B::lanes_join();
+        Impl::check_lookups();  // "lookup outside its table": a witness value that no range-check / bitwise table holds
         for (size_t ti = 0; ti < tables.size(); ti++) {
             auto& tb = tables[ti];
             log_sizes.push_back(tb.second);

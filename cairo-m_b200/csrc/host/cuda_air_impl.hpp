@@ -11,15 +11,6 @@
 #include "cuda_backend.hpp"
 #include "framework.hpp"
 
-extern "C" {
-int cm31_bitwise_table_col(int k, uint32_t* col);
-int cm31_unpack_bundles(const uint32_t* bundles_dev, size_t n_real, uint32_t log_size, const uint32_t* accesses_dev,
-                        size_t n_accesses, uint32_t* const* out_cols);
-int cm31_unpack_bundles_slots(const uint32_t* bundles_dev, size_t n_real, uint32_t log_size, const uint32_t* accesses_dev,
-                              size_t n_accesses, uint32_t* const* out_cols, uint32_t n_access_slots);
-int cm31_unpack_rows(const uint32_t* rows_dev, size_t n_real, uint32_t n_fields, uint32_t log_size, uint32_t* const* out_cols);
-int cm31_iota(uint32_t* col, size_t n);
-}
 
 namespace cm31 {
 
@@ -157,6 +148,8 @@ struct CudaAirImpl {
     static void emit_lookups(Comp& comp, int relation, const std::vector<const Col*>& trace_cols, Col& bins) {
         comp.emit_lookups(relation, trace_cols, bins);
     }
+    // a looked-up value outside its table raised the device error word instead of being counted (cm31_air_lookups)
+    static void check_lookups() { CudaBackend::check_air_errors(); }
 };
 
 }  // namespace cm31

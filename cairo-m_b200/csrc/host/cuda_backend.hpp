@@ -287,6 +287,16 @@ struct CudaBackend {
         cm_check(cm31_air_program(s.data(), s.size(), d.data(), d.size(), log_size, prog.code.data(), prog.code.size(), prog.n_regs,
                                   prog.consts.data(), prog.consts.size()));
     }
+    // multiplicity histogram: `bins` is the whole bin column, so its length bounds every looked-up value
+    static void air_lookups(const std::vector<const Col*>& in, Col& bins, u32 log_size, const AirProgram& prog) {
+        auto s = cptrs(in);
+        u32 log_bins = 0;
+        while (((size_t)1 << log_bins) < bins.size()) log_bins++;
+        if (((size_t)1 << log_bins) != bins.size()) throw std::logic_error("air_lookups: the bin column is not a power of two");
+        cm_check(cm31_air_lookups(s.data(), s.size(), bins.ptr(), log_bins, log_size, prog.code.data(), prog.code.size(), prog.n_regs,
+                                  prog.consts.data(), prog.consts.size()));
+    }
+    static void check_air_errors() { cm_check(cm31_air_error_check()); }
     // Claimed sums of one interaction phase: finalize_last is stream-ordered and writes into a device
     // arena; collect_sums() reads every pending sum with ONE copy.
     struct SumArena {

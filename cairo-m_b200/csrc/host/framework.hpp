@@ -325,8 +325,7 @@ class FrameworkComponent : public ComponentProver<B> {
             it = captured->lookup_programs.emplace(relation, build_lookup_program(ev, relation, cairo_table_index_weights(relation))).first;
         const AirProgram& prog = it->second;
         if (prog.code.empty()) return;
-        std::vector<Col*> outp = {&bins};
-        B::air_program(trace_cols, outp, log_size(), prog);
+        B::air_lookups(trace_cols, bins, log_size(), prog);
     }
 
     const AirProgram& constraint_program() const { return captured->constraint_program; }

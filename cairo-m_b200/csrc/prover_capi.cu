@@ -17,7 +17,7 @@ static int write_out(const std::vector<uint8_t>& bytes, uint8_t* out, size_t cap
 
 extern "C" {
 
-int cm31_prove_wide_fibonacci(uint32_t log_n_rows, uint32_t n_cols, uint32_t pow_bits, uint32_t n_queries,
+int cm31_test_prove_wide_fibonacci(uint32_t log_n_rows, uint32_t n_cols, uint32_t pow_bits, uint32_t n_queries,
                               uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
     try {
         PcsConfig cfg;
@@ -68,10 +68,10 @@ static void pin_range(cm31_prover_input* h, const void* p, size_t bytes) {
 extern "C" {
 
 // Runs the (host) VM + adapter for fibonacci_loop(n): the prover input of crates/prover/src/adapter.
-int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out);
-int cm31_fib_input_create(uint32_t n, cm31_prover_input** out) { return cm31_program_input_create(PROGRAM_FIBONACCI_LOOP, n, out); }
+int cm31_test_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out);
+int cm31_test_fib_input_create(uint32_t n, cm31_prover_input** out) { return cm31_test_program_input_create(PROGRAM_FIBONACCI_LOOP, n, out); }
 // program_id: 0 = fibonacci_loop(n), 1 = array_sum(n) (call / frame-pointer / double-deref / assert / le opcodes), 2 = u32_counter(n), 3 = u32_mix(n) (u32 mul / divrem / eq / lt and the two-word *_fp_imm u32 instructions)
-int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out) {
+int cm31_test_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out) {
     try {
         CM_REQUIRE(out != nullptr, "program_input_create: null out");
         VmTrace vm = run_program(program_by_id(program_id), n);
@@ -92,7 +92,7 @@ int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input
 // (ConstraintsNotSatisfied, stwo prover/mod.rs:76-82).  A corruption that only unbalances a lookup would
 // still prove — as in the reference — and be caught by the verifier's logup-sum check instead.
 //   kind 0: the value written by the middle StoreAddFpFp step;  kind 1: the second operand read by the middle StoreSubFpFp step
-int cm31_input_tamper(cm31_prover_input* h, uint32_t kind) {
+int cm31_test_input_tamper(cm31_prover_input* h, uint32_t kind) {
     CM_REQUIRE(h != nullptr, "input_tamper: null handle");
     CM_REQUIRE(!h->device_adapted, "input_tamper: not available on a device-adapted input");
     h->staged.reset();
@@ -256,25 +256,19 @@ int cm31_input_describe(cm31_prover_input* h, cm31_prover_input_desc* d) {
 
 // ------------------------------------------------------------------ runner logs + device adapter
 }  // extern "C"
-struct cm31_vm_trace {
+struct cm31_test_vm_trace {
     cm31::VmTrace vm;
     std::vector<uint32_t> trace_words;  // IoTraceEntry {fp, pc} per entry (crates/prover/src/adapter/io.rs:38-43)
 };
 static_assert(sizeof(std::pair<cm31::u32, cm31::Word4>) == 20, "memory-trace entries must be IoMemoryEntry-shaped (5 words)");
 extern "C" {
-int cm31_adapter_stage_logs(const uint32_t* trace_host, size_t n_trace, const uint32_t* mem_host, size_t n_mem, const uint32_t* init_host,
-                            size_t n_init, int background, void** plan_out);
-int cm31_adapter_scan_staged(void* plan, uint64_t counts_out[67]);
-int cm31_adapter_emit(void* plan, uint32_t* const opcode_rows_dev[64], const uint64_t counts[67], uint32_t* accesses_dev,
-                      uint32_t* clock_update_dev, uint32_t* cells_host);
-int cm31_adapter_free(void* plan);
 
 // The runner's output for one of the built-in programs (what cairo-m-runner hands to import_from_runner_output):
 // execution trace, memory-access log, preloaded memory, public address ranges.
-int cm31_vm_trace_create(uint32_t program_id, uint32_t n, cm31_vm_trace** out) {
+int cm31_test_vm_trace_create(uint32_t program_id, uint32_t n, cm31_test_vm_trace** out) {
     try {
         CM_REQUIRE(out != nullptr, "vm_trace_create: null out");
-        std::unique_ptr<cm31_vm_trace> h(new cm31_vm_trace());
+        std::unique_ptr<cm31_test_vm_trace> h(new cm31_test_vm_trace());
         h->vm = run_program(program_by_id(program_id), n);
         h->trace_words.reserve(h->vm.trace.size() * 2);
         for (const Registers& r : h->vm.trace) {
@@ -289,7 +283,7 @@ int cm31_vm_trace_create(uint32_t program_id, uint32_t n, cm31_vm_trace** out) {
     }
 }
 // info[0] = trace entries (steps + 1), [1] = memory-log entries, [2] = preloaded cells, [3] = return value
-int cm31_vm_trace_info(const cm31_vm_trace* h, uint64_t info[4]) {
+int cm31_test_vm_trace_info(const cm31_test_vm_trace* h, uint64_t info[4]) {
     CM_REQUIRE(h != nullptr && info != nullptr, "vm_trace_info: null argument");
     info[0] = h->vm.trace.size();
     info[1] = h->vm.memory_trace.size();
@@ -297,7 +291,7 @@ int cm31_vm_trace_info(const cm31_vm_trace* h, uint64_t info[4]) {
     info[3] = h->vm.return_value;
     return 0;
 }
-int cm31_vm_trace_data(const cm31_vm_trace* h, const uint32_t** trace, const uint32_t** memory_trace, const uint32_t** initial_memory,
+int cm31_test_vm_trace_data(const cm31_test_vm_trace* h, const uint32_t** trace, const uint32_t** memory_trace, const uint32_t** initial_memory,
                        uint32_t public_ranges[6]) {
     CM_REQUIRE(h != nullptr, "vm_trace_data: null handle");
     if (trace) *trace = h->trace_words.data();
@@ -310,7 +304,7 @@ int cm31_vm_trace_data(const cm31_vm_trace* h, const uint32_t** trace, const uin
     }
     return 0;
 }
-int cm31_vm_trace_destroy(cm31_vm_trace* h) {
+int cm31_test_vm_trace_destroy(cm31_test_vm_trace* h) {
     delete h;
     return 0;
 }

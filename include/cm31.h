@@ -209,6 +209,14 @@ int cm31_set_air_mode(int mode);
 int cm31_air_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* const* out_cols, size_t n_out,
                      uint32_t log_size, const uint64_t* code, size_t n_instr, uint32_t n_regs,
                      const uint32_t* consts, size_t n_consts);
+/* Lookup multiplicities (P/src/preprocessed/range_check/range_check_macro.rs:72-84, P/src/preprocessed/bitwise.rs:86-109): a
+ * program whose OP_HIST instructions count looked-up values into `bins` (2^log_bins words).  A value >= 2^log_bins is NOT
+ * counted (no out-of-bounds write) and raises the device error word: the next cm31_air_error_check returns non-zero with
+ * "lookup outside its table" (the reference panics on the slice index).  cm31_air_program refuses programs with OP_HIST. */
+int cm31_air_lookups(const uint32_t* const* in_cols, size_t n_in, uint32_t* bins, uint32_t log_bins, uint32_t log_size,
+                     const uint64_t* code, size_t n_instr, uint32_t n_regs, const uint32_t* consts, size_t n_consts);
+/* reads (one 4-byte copy, synchronises the current lane) and clears the error bits AIR programs raised since the last call */
+int cm31_air_error_check(void);
 /* finalize_last (logup.rs:211-251): claimed_sum = sum(last col); last col -= claimed_sum/n;
  * inclusive prefix sum in coset order (simd/prefix_sum.rs:19, index map core/utils.rs:121-143). */
 int cm31_logup_finalize_last(uint32_t* const last4[4], uint32_t log_size, uint32_t claimed_sum_out[4]);
@@ -217,23 +225,34 @@ int cm31_logup_finalize_last(uint32_t* const last4[4], uint32_t log_size, uint32
 int cm31_logup_finalize_last_async(uint32_t* const last4[4], uint32_t log_size, uint32_t* claimed_sum_dev);
 /* multiplicity histograms (P/src/preprocessed/range_check/range_check_macro.rs:72-84) */
 int cm31_histogram(const uint32_t* values, size_t n, uint32_t* bins, uint32_t log_bins);
+/* Pack::pack for ExecutionBundle + get_access_field (P/src/utils/execution_bundle.rs:31-75, P/src/utils/data_accesses.rs:10-28):
+ * AoS bundles (12 words: pc, fp, clock, inst_prev_clock, inst[6], span start, span len) + the global access log (4 words per
+ * access) -> the SoA input columns of a component's trace program, padded to 2^log_size rows with ExecutionBundle::default()
+ * (P/src/adapter/memory.rs:112-124).  out_cols: 10 bundle columns, then 4 columns (address, prev_clock, prev_value, value) per
+ * access slot; the _slots form writes only the first n_access_slots slots (the ones the component's program reads). */
+int cm31_unpack_bundles(const uint32_t* bundles_dev, size_t n_real, uint32_t log_size, const uint32_t* accesses_dev,
+                        size_t n_accesses, uint32_t* const* out_cols);
+int cm31_unpack_bundles_slots(const uint32_t* bundles_dev, size_t n_real, uint32_t log_size, const uint32_t* accesses_dev,
+                              size_t n_accesses, uint32_t* const* out_cols, uint32_t n_access_slots);
+/* AoS rows of n_fields words (memory / merkle / clock_update / poseidon2 inputs: P/src/components/memory.rs:105-140,
+ * merkle.rs:103-130, clock_update.rs:87-102, poseidon2.rs:180-200) -> n_fields columns of 2^log_size rows, zero padded */
+int cm31_unpack_rows(const uint32_t* rows_dev, size_t n_real, uint32_t n_fields, uint32_t log_size, uint32_t* const* out_cols);
+/* col[i] = i: the range-check preprocessed columns (P/src/preprocessed/range_check/mod.rs: RangeCheck::gen_column_simd) */
+int cm31_iota(uint32_t* col, size_t n);
+/* column k (0: op id, 1: a, 2: b, 3: result) of the stacked and/or/xor table (P/src/preprocessed/bitwise.rs:253-290), 2^18 rows */
+int cm31_bitwise_table_col(int k, uint32_t* col);
 
 /* ------------------------------------------------------------------ whole proofs
  * prove_cairo_m::<Blake2sMerkleChannel> (P/src/prover.rs:23-147) over the ops above.  The input
  * handle owns the reference's ProverInput (P/src/adapter/mod.rs:97-193): per-opcode ExecutionBundles,
- * the data-access log, boundary memory, clock-update rows.  Only the fibonacci_loop input producer
- * (host VM + adapter, the serial step BEFORE the hot path) is built in this round. */
+ * the data-access log, boundary memory, clock-update rows, Merkle nodes.  A handle comes from cm31_input_create (a caller
+ * that ran its own adapter) or from cm31_adapter_import (the runner's logs, adapted on the device). */
 typedef struct cm31_prover_input cm31_prover_input;
-int cm31_fib_input_create(uint32_t n, cm31_prover_input** out);
 /* Starts the host->device copy of this handle's prover input on the background stream and returns at once; the next
  * cm31_prove_cairo_m on the handle consumes it (oldest first) instead of copying itself: the upload of segment i+1 overlaps
  * the proof of segment i. */
 int cm31_input_prefetch(cm31_prover_input* h);
-/* program_id 0 = fibonacci_loop(n); 1 = array_sum(n): call/ret, frame pointer, double-deref, assert, le; 2 = u32_counter(n): u32 limb ops; 3 = u32_mix(n): u32 mul/divrem/eq/lt + two-word *_fp_imm u32 instructions */
-int cm31_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out);
 int cm31_input_destroy(cm31_prover_input* h);
-/* test hook: corrupt the adapter output so a store_fp_fp constraint fails (kind 0: a written value, 1: an operand read) */
-int cm31_input_tamper(cm31_prover_input* h, uint32_t kind);
 /* info[0] VM steps, [1] data accesses, [2] boundary-memory rows, [3] return value, [4] input bytes staged per proof */
 int cm31_input_info(const cm31_prover_input* h, uint64_t info[5]);
 /* stage the input in HBM once (later proofs on this handle skip the host->device copy) / drop that copy */
@@ -302,19 +321,27 @@ int cm31_adapter_prefetch(const uint32_t* trace, size_t n_trace, const uint32_t*
                           cm31_adapter_logs** out);
 int cm31_adapter_import_prefetched(cm31_adapter_logs* logs, cm31_prover_input** out);
 int cm31_adapter_logs_destroy(cm31_adapter_logs* logs); /* only for logs that were never imported */
+/* The three phases cm31_adapter_import is made of, for a caller that owns the output buffers (the Rust shim allocates the
+ * per-opcode row buffers itself once phase 1 has told it their sizes).  `plan` is an opaque device-side work area.
+ *   stage_logs  : device buffers + upload of the logs; background != 0 issues the copies on the background copy stream
+ *   scan(_staged): everything whose size is data dependent -> counts[0..63] steps per opcode, [64] data accesses,
+ *                 [65] clock-update rows, [66] distinct cells touched (cm31_adapter_scan = stage_logs + scan_staged)
+ *   emit        : opcode_rows_dev[op] = device buffer for the bundles of opcode op (12 words per step, NULL iff no steps),
+ *                 accesses_dev 4 words per access, clock_update_dev 6 words per row, cells_host 10 words per distinct cell
+ *                 {address, first value[4], last value[4], last clock} in ascending address order (HOST pointer)
+ *   free        : releases the plan (after emit, or on any error path) */
+int cm31_adapter_stage_logs(const uint32_t* trace_host, size_t n_trace, const uint32_t* mem_host, size_t n_mem,
+                            const uint32_t* init_host, size_t n_init, int background, void** plan_out);
+int cm31_adapter_scan_staged(void* plan, uint64_t counts_out[67]);
+int cm31_adapter_scan(const uint32_t* trace_host, size_t n_trace, const uint32_t* mem_host, size_t n_mem,
+                      const uint32_t* init_host, size_t n_init, void** plan_out, uint64_t counts_out[67]);
+int cm31_adapter_emit(void* plan, uint32_t* const opcode_rows_dev[64], const uint64_t counts[67], uint32_t* accesses_dev,
+                      uint32_t* clock_update_dev, uint32_t* cells_host);
+int cm31_adapter_free(void* plan);
 /* One table of a resident input read back to the host (parity tests): table 0 = data-access log (4 words per access),
  * 1..26 = opcode components in claim order (12 words per step), 100 = memory rows (8), 101 = merkle rows (9),
  * 102 = clock-update rows (6), 103 = poseidon2 states (16).  out may be NULL to query the size. */
 int cm31_input_staged_words(const cm31_prover_input* h, uint32_t table, uint32_t* out, size_t cap_words, size_t* n_words_out);
-/* The runner's output for a built-in program (program_id as in cm31_program_input_create): the host VM only, no adapter. */
-typedef struct cm31_vm_trace cm31_vm_trace;
-int cm31_vm_trace_create(uint32_t program_id, uint32_t n, cm31_vm_trace** out);
-/* info[0] trace entries (steps + 1), [1] memory-log entries, [2] preloaded cells, [3] return value */
-int cm31_vm_trace_info(const cm31_vm_trace* h, uint64_t info[4]);
-/* pointers into the handle, laid out as cm31_adapter_import takes them */
-int cm31_vm_trace_data(const cm31_vm_trace* h, const uint32_t** trace, const uint32_t** memory_trace,
-                       const uint32_t** initial_memory, uint32_t public_ranges[6]);
-int cm31_vm_trace_destroy(cm31_vm_trace* h);
 
 /* The AIR shapes of the 34 components as captured from their `evaluate` bodies — what FrameworkComponent::new learns from its
  * InfoEvaluator pass (S/constraint_framework/src/component.rs:139-180, info.rs) — as JSON: {"relations": {name: size},
@@ -324,9 +351,29 @@ int cm31_vm_trace_destroy(cm31_vm_trace* h);
  * checks them against the constants of P/src/components/**. buf may be NULL to query the length. */
 int cm31_air_shapes(char* buf, size_t cap, size_t* len);
 
+
+/* ------------------------------------------------------------------ test conveniences (cm31_test_*)
+ * NOT part of the drop-in surface: built-in hand-assembled programs run on the host VM + host adapter of csrc/cairo/vm.hpp
+ * (the serial steps BEFORE the hot path), a tamper hook, and the bring-up AIR.  Tests, bench.py and smoke() use them to have
+ * inputs; a cairo-m-prover integration never calls them. */
+/* program_id 0 = fibonacci_loop(n); 1 = array_sum(n): call/ret, frame pointer, double-deref, assert, le; 2 = u32_counter(n):
+ * u32 limb ops; 3 = u32_mix(n): u32 mul/divrem/eq/lt + two-word *_fp_imm u32 instructions; 4 = sha256 compression rounds */
+int cm31_test_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out);
+int cm31_test_fib_input_create(uint32_t n, cm31_prover_input** out);
+/* corrupt the adapter output so a store_fp_fp constraint fails (kind 0: a written value, 1: an operand read) */
+int cm31_test_input_tamper(cm31_prover_input* h, uint32_t kind);
+/* The runner's output for a built-in program: the host VM only, no adapter. */
+typedef struct cm31_test_vm_trace cm31_test_vm_trace;
+int cm31_test_vm_trace_create(uint32_t program_id, uint32_t n, cm31_test_vm_trace** out);
+/* info[0] trace entries (steps + 1), [1] memory-log entries, [2] preloaded cells, [3] return value */
+int cm31_test_vm_trace_info(const cm31_test_vm_trace* h, uint64_t info[4]);
+/* pointers into the handle, laid out as cm31_adapter_import takes them */
+int cm31_test_vm_trace_data(const cm31_test_vm_trace* h, const uint32_t** trace, const uint32_t** memory_trace,
+                            const uint32_t** initial_memory, uint32_t public_ranges[6]);
+int cm31_test_vm_trace_destroy(cm31_test_vm_trace* h);
 /* S/examples/src/wide_fibonacci/mod.rs:22-43 — the bring-up AIR (parity tests only) */
-int cm31_prove_wide_fibonacci(uint32_t log_n_rows, uint32_t n_cols, uint32_t pow_bits, uint32_t n_queries,
-                              uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+int cm31_test_prove_wide_fibonacci(uint32_t log_n_rows, uint32_t n_cols, uint32_t pow_bits, uint32_t n_queries,
+                                   uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
 
 /* ------------------------------------------------------------------ per-kernel device timing
  * (the reference's tracing spans, S/prover/src/tracing/mod.rs:22-50).  When enabled every kernel

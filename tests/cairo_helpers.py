@@ -41,7 +41,7 @@ class GpuFibInput:
     def __init__(self, cm, n, program=FIB):
         self.cm = cm
         self.h = C.c_void_p()
-        cm.check(cm.lib().cm31_program_input_create(C.c_uint32(program), C.c_uint32(n), C.byref(self.h)))
+        cm.check(cm.lib().cm31_test_program_input_create(C.c_uint32(program), C.c_uint32(n), C.byref(self.h)))
         info = (C.c_uint64 * 5)()
         cm.check(cm.lib().cm31_input_info(self.h, info))
         self.steps, self.accesses, self.memory_rows, self.return_value, self.h2d_bytes = list(info)
@@ -120,9 +120,9 @@ class VmTrace:
     def __init__(self, cm, program, n):
         self.cm = cm
         self.h = C.c_void_p()
-        cm.check(cm.lib().cm31_vm_trace_create(C.c_uint32(program), C.c_uint32(n), C.byref(self.h)))
+        cm.check(cm.lib().cm31_test_vm_trace_create(C.c_uint32(program), C.c_uint32(n), C.byref(self.h)))
         info = (C.c_uint64 * 4)()
-        cm.check(cm.lib().cm31_vm_trace_info(self.h, info))
+        cm.check(cm.lib().cm31_test_vm_trace_info(self.h, info))
         self.n_trace, self.n_mem, self.n_init, self.return_value = list(info)
 
     def arrays(self):
@@ -130,7 +130,7 @@ class VmTrace:
         import numpy as np
         pt, pm, pi = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
         ranges = (C.c_uint32 * 6)()
-        self.cm.check(self.cm.lib().cm31_vm_trace_data(self.h, C.byref(pt), C.byref(pm), C.byref(pi), ranges))
+        self.cm.check(self.cm.lib().cm31_test_vm_trace_data(self.h, C.byref(pt), C.byref(pm), C.byref(pi), ranges))
         trace = np.ctypeslib.as_array(pt, shape=(2 * self.n_trace,)).copy()
         mem = np.ctypeslib.as_array(pm, shape=(5 * self.n_mem,)).copy()
         init = np.ctypeslib.as_array(pi, shape=(4 * self.n_init,)).copy()
@@ -138,7 +138,7 @@ class VmTrace:
 
     def close(self):
         if self.h:
-            self.cm.lib().cm31_vm_trace_destroy(self.h)
+            self.cm.lib().cm31_test_vm_trace_destroy(self.h)
             self.h = C.c_void_p()
 
 

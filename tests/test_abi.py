@@ -1,4 +1,5 @@
-"""CPU-side checks of the drop-in boundary: libcm31.so loads and exports every symbol include/cm31.h declares."""
+"""CPU-side checks of the drop-in boundary: libcm31.so loads, exports every symbol include/cm31.h declares, and exports NO
+cm31_* symbol the header does not declare (nothing the product's own host path calls is hidden from an integrator)."""
 import ctypes
 import re
 from pathlib import Path
@@ -24,6 +25,26 @@ def test_library_exports_every_declared_symbol(cm):
     lib = cm.lib()
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, f"declared in include/cm31.h but not exported: {missing}"
+
+
+def exported_symbols():
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", str(ROOT / "cairo-m_b200" / "libcm31.so")], capture_output=True, text=True, check=True).stdout
+    return sorted({line.split()[-1] for line in out.splitlines() if line.split() and line.split()[-1].startswith("cm31_")})
+
+
+def test_every_exported_symbol_is_declared(cm):
+    cm.lib()
+    undeclared = sorted(set(exported_symbols()) - set(declared_symbols()))
+    assert not undeclared, f"exported by libcm31.so but not declared in include/cm31.h: {undeclared}"
+
+
+def test_test_conveniences_are_prefixed():
+    # built-in programs, the tamper hook and the bring-up AIR are not part of the drop-in surface
+    syms = declared_symbols()
+    for s in syms:
+        if any(k in s for k in ("fib_input", "program_input", "tamper", "vm_trace", "wide_fibonacci")):
+            assert s.startswith("cm31_test_"), s
 
 
 def test_errors_are_reported_not_swallowed(cm):

@@ -1,4 +1,4 @@
-"""CPU: the runner-log interface of the device adapter (cm31_vm_trace_*, cm31_adapter_import): log layout as
+"""CPU: the runner-log interface of the device adapter (cm31_test_vm_trace_*, cm31_adapter_import): log layout as
 crates/prover/src/adapter/io.rs:38-60 defines it, and no silent CPU fallback when there is no device."""
 import ctypes as C
 

@@ -170,7 +170,7 @@ def test_invalid_trace_is_refused(cm, kind):
     import ctypes as C
     inp = ch.GpuFibInput(cm, 50)
     try:
-        cm.check(cm.lib().cm31_input_tamper(inp.h, C.c_uint32(kind)))
+        cm.check(cm.lib().cm31_test_input_tamper(inp.h, C.c_uint32(kind)))
         with pytest.raises(Exception) as err:
             inp.prove()
         assert "ConstraintsNotSatisfied" in str(err.value) or "onstraint" in str(err.value)
@@ -193,3 +193,38 @@ def test_fib_2_22_steps_headline_size_verifies(cm, extra):
     assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
     residual, _ = ch.oracle_logup_residual(n, got)
     assert residual == (0, 0, 0, 0)
+
+
+@pytest.mark.parametrize("what", ["clock_delta", "after_valid_proof"])
+def test_lookup_outside_its_table_is_refused_not_written_out_of_bounds(cm, what):
+    # OP_HIST / gen_hist index the bin column with witness data.  A data access whose prev_clock is NOT below its
+    # clock gives a range_check_20 lookup of clock - prev_clock - 1 = P - k: the value must not be used as a bin index
+    # (the reference panics on the slice index, range_check_macro.rs:72-84; the oracle throws "lookup outside its table").
+    import ctypes as C
+    import numpy as np
+    src = ch.GpuFibInput(cm, 30)
+    try:
+        scalars, tables = ch.describe_input(cm, src.h)
+        good, _ = src.prove()
+    finally:
+        src.close()
+    bad = dict(tables, data_accesses=tables["data_accesses"].copy())
+    acc = bad["data_accesses"].reshape(-1, 4)
+    acc[7, 1] = acc[7, 1] + 1000  # prev_clock far above the clock of the step that makes the access
+    h = C.c_void_p()
+    cm.check(ch.create_input(cm, scalars, bad, h))
+    buf = (C.c_uint8 * ch.CAP)()
+    ln = C.c_size_t()
+    try:
+        rc = cm.lib().cm31_prove_cairo_m(h, 16, 80, buf, C.c_size_t(ch.CAP), C.byref(ln), None)
+        assert rc != 0
+        assert "lookup outside its table" in cm.lib().cm31_last_error().decode()
+    finally:
+        cm.lib().cm31_input_destroy(h)
+    if what == "after_valid_proof":
+        # the error word is cleared by the failed proof: the next proof of a valid input is unaffected and unchanged
+        again = ch.GpuFibInput(cm, 30)
+        try:
+            assert again.prove()[0] == good
+        finally:
+            again.close()

@@ -14,7 +14,7 @@ def gpu_prove_wide_fib(cm, log_n, n_cols, pow_bits=5, n_queries=3):
     cap = 1 << 26
     buf = (C.c_uint8 * cap)()
     n = C.c_size_t()
-    cm.check(lib.cm31_prove_wide_fibonacci(log_n, n_cols, pow_bits, n_queries, buf, C.c_size_t(cap), C.byref(n)))
+    cm.check(lib.cm31_test_prove_wide_fibonacci(log_n, n_cols, pow_bits, n_queries, buf, C.c_size_t(cap), C.byref(n)))
     return bytes(buf[: n.value])
 
 

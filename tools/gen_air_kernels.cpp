@@ -50,7 +50,7 @@ static void emit_kernel(std::ostream& os, const Kernel& k, std::vector<std::pair
     os << "// " << k.prog.code.size() << " bytecode instructions, " << k.prog.n_mul_m31 << " M31 multiplications per row, " << k.n_in
        << " input / " << k.n_out << " output columns\n";
     os << "struct A_" << n << " {\n    u32 row_log, trace_log;\n    const u32* denom_inv;\n    u32* acc[4];\n    const u32* in[" << nin
-       << "];\n    u32* out[" << nout << "];\n    u32 c[" << nc << "];\n};\n";
+       << "];\n    u32* out[" << nout << "];\n    u32 c[" << nc << "];\n    u32 hist_bins;\n    u32* err;\n};\n";
     // CTA size: the programs are thousands of straight-line instructions executed once per row, so instruction fetch is
     // shared only between warps that run the same code at the same time; the warps of one CTA start together and stay
     // close, warps of different CTAs do not (ncu r01b: no_inst 30 % with one warp per scheduler and CTA).
@@ -72,6 +72,7 @@ static void emit_kernel(std::ostream& os, const Kernel& k, std::vector<std::pair
     os << "    CM_REQUIRE(" << (k.constraint ? "g.acc4 != nullptr && g.denom_inv_dev != nullptr" : "g.acc4 == nullptr")
        << ", \"generated AIR kernel " << n << ": accumulator mismatch\");\n";
     os << "    A_" << n << " a;\n    a.row_log = g.row_log;\n    a.trace_log = g.trace_log;\n    a.denom_inv = g.denom_inv_dev;\n";
+    os << "    a.hist_bins = g.hist_bins;\n    a.err = g.err_flag;\n";
     os << "    for (int k = 0; k < 4; k++) a.acc[k] = g.acc4 ? g.acc4[k] : nullptr;\n";
     os << "    for (size_t k = 0; k < " << k.n_in << "; k++) a.in[k] = g.in_cols[k];\n";
     os << "    for (size_t k = 0; k < " << k.n_out << "; k++) a.out[k] = g.out_cols[k];\n";

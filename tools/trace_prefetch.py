@@ -17,7 +17,7 @@ log = int(sys.argv[1]) if len(sys.argv) > 1 else 22
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 lib = cm.lib()
 h = C.c_void_p()
-cm.check(lib.cm31_fib_input_create(C.c_uint32(bench.fib_iterations(log)), C.byref(h)))
+cm.check(lib.cm31_test_fib_input_create(C.c_uint32(bench.fib_iterations(log)), C.byref(h)))
 cap = 1 << 26
 buf = (C.c_uint8 * cap)()
 ln = C.c_size_t()

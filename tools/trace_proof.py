@@ -13,7 +13,7 @@ import bench
 log = int(sys.argv[1]) if len(sys.argv) > 1 else 22
 lib = cm.lib()
 h = C.c_void_p()
-cm.check(lib.cm31_fib_input_create(C.c_uint32(bench.fib_iterations(log)), C.byref(h)))
+cm.check(lib.cm31_test_fib_input_create(C.c_uint32(bench.fib_iterations(log)), C.byref(h)))
 cm.check(lib.cm31_input_upload(h))
 cap = 1 << 26
 buf = (C.c_uint8 * cap)()
