@@ -117,33 +117,46 @@ def cpu_cores() -> int:
         return os.cpu_count() or 1
 
 
+def cpu_sample_text(log_steps: int, seconds: float | None = None) -> str:
+    t = f"; {seconds:.1f} s" if seconds is not None else ""
+    return (f"one whole proof of fibonacci_loop 2^{log_steps} VM steps (all 34 components, REGULAR_96_BITS) on oracle/ "
+            f"(C++ port of stwo CpuBackend + the same protocol driver, OpenMP){t}")
+
+
 def run_reference(args, rank: int, world: int):
+    """The CPU arm proves THE SAME workload the CUDA arm names (2^log_steps VM steps per proof, same pcs config).  One oracle
+    proof of 2^22 steps takes about a minute, so the number of timed proofs is capped (min(steps, 2)) and the warm-up is one
+    small proof (page faults, OpenMP pool): both are stated in the line."""
     if rank != 0:
         return
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core
     os.environ["OMP_NUM_THREADS"] = str(cpu_cores())
-    sample_log = args.cpu_sample_log
-    for _ in range(min(args.warmup, 1)):  # the CPU path has no warm-up effects beyond page faults: one is enough
-        oracle_prove_timed(sample_log)
+    log_steps = args.log_steps
+    timed = max(1, min(args.steps, 2))
+    if args.warmup > 0:
+        oracle_prove_timed(min(log_steps, 14))
     total_steps, total_s = 0, 0.0
-    for _ in range(args.steps):
-        s, dt = oracle_prove_timed(sample_log)
+    for _ in range(timed):
+        s, dt = oracle_prove_timed(log_steps)
         total_steps += s
         total_s += dt
     value = total_steps / total_s
     cores = cpu_cores()
-    sample = (f"fibonacci_loop 2^{sample_log} VM steps per proof (bounded sample of the 2^{args.log_steps} workload; the "
-              f"2^20-row range-check tables are a fixed floor, so CPU steps/s grows with segment length)")
+    sample = cpu_sample_text(log_steps, total_s / timed) + f" per proof, {timed} proof(s) timed"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": timed,
+        "steps_requested": args.steps, "warmup": 1 if args.warmup > 0 else 0, "warmup_requested": args.warmup,
+        "warmup_note": "one small (2^14-step) proof: the CPU path has no warm-up effect beyond page faults and the OpenMP pool",
+        "ms_per_step": 1e3 * total_s / timed, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 (M31/QM31 modular integer)", "data": "synthetic",
-        "config": {"workload": workload_name(args.log_steps), "cpu_sample": sample},
+        "config": {"workload": workload_name(log_steps), "vm_steps_per_proof": total_steps // timed,
+                   "parallelism": "host cores (OpenMP)", "pcs": {"pow_bits": 16, "log_blowup": 1, "n_queries": 80}},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "the Rust reference cannot be built in this image (no cargo/rustc, crates not vendored): this arm times "
-                "oracle/ (C++ restatement of stwo CpuBackend + the same protocol driver), OpenMP on all host cores",
+                "oracle/ (scalar C++ restatement of stwo CpuBackend + the same protocol driver, OpenMP on all host cores), "
+                "not the Rust SimdBackend",
     }
     print(json.dumps(line), flush=True)
 
@@ -348,8 +361,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     cm.check(lib.cm31_input_upload(h))
     for _ in range(args.warmup):
         prove()
-    ms, clocks, launches, report, phases = timed_region(args.steps, True)
+    # `value`: K proofs, per-kernel event timers OFF (they cost two event records per launch, ~460 launches per proof)
+    ms, clocks, launches, _, phases = timed_region(args.steps, False)
     value = aggregate_value(world, vm_steps, args.steps, ms)
+    # second pass over the same K steps with every launch bracketed by CUDA events on its launch stream: the per-kernel table
+    # and the roofline come from here; its own ms/step is reported next to the unprofiled one
+    prof_ms, _, _, report, _ = timed_region(args.steps, True)
 
     # ---- end to end: host (pinned) input copied in, proof bytes copied out, every step
     cm.check(lib.cm31_input_release_device(h))
@@ -416,19 +433,22 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "int_issue": int_issue, "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches_per_step": top["launches"] / args.steps,
         "share_of_kernel_time": top["ms"] / kern_total if kern_total else None,
-        "kernel_time_share_of_step": kern_total / ms,
+        "kernel_time_share_of_step": kern_total / prof_ms,
+        "profiled_pass_ms_per_step": prof_ms / args.steps,
+        "note": "value / ms_per_step are measured with the per-kernel timers off; this table is a second pass over the same K steps "
+                "with every launch bracketed by CUDA events (kernel_time_share_of_step is relative to that pass)",
         "kernels": [{"kernel": r["kernel"], "ms_per_step": r["ms"] / args.steps, "launches_per_step": r["launches"] / args.steps,
-                     "alg_GBps": (r["alg_bytes"] / (r["ms"] * 1e-3) / 1e9) if r["ms"] > 0 else None} for r in report],
+                     "alg_GBps": (r["alg_bytes"] / (r["ms"] * 1e-3) / 1e9) if r["ms"] > 0 else None,
+                     "m31_Gops": (r.get("m31_ops", 0) / (r["ms"] * 1e-3) / 1e9) if r["ms"] > 0 and r.get("m31_ops") else None} for r in report],
+        "m31_ops_per_step": sum(r.get("m31_ops", 0) for r in report) / args.steps,
+        "m31_Gops_whole_step": sum(r.get("m31_ops", 0) for r in report) / (ms * 1e-3) / 1e9,
     }
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
+        os.environ["OMP_NUM_THREADS"] = str(cpu_cores())
         s, dt = oracle_prove_timed(args.cpu_sample_log)
-        cpu_baseline = {
-            "value": s / dt, "unit": UNIT, "cores": cpu_cores(), "kind": "port",
-            "sample": f"one proof of fibonacci_loop 2^{args.cpu_sample_log} VM steps on oracle/ (C++ port of stwo CpuBackend + same "
-                      f"protocol, OpenMP); {dt:.1f} s",
-        }
+        cpu_baseline = {"value": s / dt, "unit": UNIT, "cores": cpu_cores(), "kind": "port", "sample": cpu_sample_text(args.cpu_sample_log, dt)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -464,7 +484,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-steps", type=int, default=22, help="log2 of VM steps per proof (BASELINE metric: 2^22)")
-    ap.add_argument("--cpu-sample-log", type=int, default=17, help="log2 VM steps of the bounded CPU sample")
+    ap.add_argument("--cpu-sample-log", type=int, default=0,
+                    help="log2 VM steps of the cpu_baseline proof (default: the workload's own size, one whole proof)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-adapter", action="store_true", help="skip the adapter side measurement")
     ap.add_argument("--program", default="fibonacci_loop", choices=["fibonacci_loop", "array_sum", "u32_counter", "u32_mix"],
@@ -475,6 +496,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not args.cpu_sample_log:
+        args.cpu_sample_log = args.log_steps
     if args.dist_selftest:
         dist_selftest(rank, world)
         return

@@ -8,6 +8,8 @@
 // One thread per row; every column access is a coalesced 4-byte-per-lane load; the program and
 // its constants are warp-uniform reads.  The register file lives in per-thread local memory
 // (hardware-interleaved, L1 resident), sized by the program's register allocation.
+#include <unordered_map>
+
 #include "air_gen.cuh"
 #include "common.cuh"
 #include "host/air_expr.hpp"
@@ -136,6 +138,31 @@ static u32* air_err_flag() {
     return flag[dev & 63];
 }
 
+// ALGORITHMIC M31 operations of one row of a bytecode program (S/constraint_framework/src/info.rs arithmetic counts, in M31
+// units: QM31 mul = 16 mul + 15 add, QM31 x M31 = 4, QM31 add = 4, QM31 inverse ~ 60 + an M31 inverse of 37 mul)
+static uint64_t program_m31_ops(const uint64_t* code, size_t n_instr, uint64_t hash) {
+    static std::unordered_map<uint64_t, uint64_t> cache;  // programs are few and immutable: count once per program
+    auto it = cache.find(hash);
+    if (it != cache.end()) return it->second;
+    uint64_t ops = 0;
+    for (size_t i = 0; i < n_instr; i++) {
+        switch ((u32)(code[i] & 0xff)) {
+            case OP_ADD: case OP_SUB: case OP_MUL: case OP_NEG: ops += 1; break;
+            case OP_EADD: case OP_ESUB: case OP_ENEG: ops += 4; break;
+            case OP_EMUL: ops += 31; break;
+            case OP_EMULF: ops += 4; break;
+            case OP_EADDF: case OP_ESUBF: ops += 1; break;
+            case OP_EINV: ops += 97; break;
+            case OP_INV: ops += 37; break;
+            case OP_CONSTRAINT_E: ops += 35; break;
+            case OP_CONSTRAINT_F: ops += 8; break;
+            default: break;
+        }
+    }
+    cache[hash] = ops;
+    return ops;
+}
+
 static int run_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* const* out_cols, size_t n_out, u32 row_log,
                        u32 trace_log, const uint64_t* code, size_t n_instr, u32 n_regs, const u32* consts, size_t n_consts,
                        const u32* denom_inv_host, size_t n_denom, uint32_t* const* acc4, u32 hist_bins = 0) {
@@ -144,7 +171,8 @@ static int run_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* co
     CM_REQUIRE(row_log <= 30, "air: too many rows");
     CM_REQUIRE(n_regs <= 2048, "air: program needs more than 2048 registers");
     CM_REQUIRE(trace_log <= row_log, "air: trace domain larger than the evaluation domain");
-    const GenEntry* gen = g_air_mode == 0 ? air_gen_lookup(air_code_hash(code, n_instr)) : nullptr;
+    const uint64_t code_hash = air_code_hash(code, n_instr);
+    const GenEntry* gen = g_air_mode == 0 ? air_gen_lookup(code_hash) : nullptr;
     if (gen) {
         DeviceTable ddenom_gen;
         if (acc4) {
@@ -154,6 +182,7 @@ static int run_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* co
         GenLaunch gl{in_cols, n_in, out_cols, n_out, row_log, trace_log, consts, n_consts, (const u32*)ddenom_gen.d, acc4, hist_bins, err};
         size_t rows = (size_t)1 << row_log;
         ProfScope prof(acc4 ? "constraint_eval" : "air_program", acc4 ? 4ull * rows * n_in + 32ull * rows : 4ull * rows * (n_in + n_out));
+        if (prof_enabled()) prof_ops(rows * (program_m31_ops(code, n_instr, code_hash) + (acc4 ? 8 : 0)));
         if (int e = gen->launch(gl)) return e;
         CM_LAUNCH_CHECK();
         return 0;
@@ -172,6 +201,7 @@ static int run_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* co
     u32 *a0 = acc4 ? acc4[0] : nullptr, *a1 = acc4 ? acc4[1] : nullptr, *a2 = acc4 ? acc4[2] : nullptr,
         *a3 = acc4 ? acc4[3] : nullptr;
     ProfScope prof(acc4 ? "constraint_eval" : "air_program", acc4 ? 4ull * n * n_in + 32ull * n : 4ull * n * (n_in + n_out));
+    if (prof_enabled()) prof_ops(n * (program_m31_ops(code, n_instr, code_hash) + (acc4 ? 8 : 0)));
 #define CM_AIR_LAUNCH(NR)                                                                                              \
     air_program_kernel<NR><<<blocks, threads, 0, stream()>>>((const u32* const*)din.d, (u32* const*)dout.d, row_log,   \
                                                              trace_log, (const uint64_t*)dcode.d, (u32)n_instr,        \

@@ -493,7 +493,6 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
             shape.for_each(emit);
         }
         B::lanes_join();
-        Impl::check_lookups();  // "lookup outside its table": a witness value that no range-check / bitwise table holds
         for (size_t ti = 0; ti < tables.size(); ti++) {
             auto& tb = tables[ti];
             log_sizes.push_back(tb.second);
@@ -515,6 +514,9 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
             for (auto& e : comp) all.push_back(&e);
         commitment_scheme.commit_evals_keep(all, channel);
     }
+    // "lookup outside its table": a witness value that no range-check / bitwise table holds raised the device error word
+    // in the histogram kernels above; it is read here, where the root of tree 1 has just synchronised the host anyway
+    Impl::check_lookups();
     auto t2 = Impl::now_ms();
 
     // ---- interaction: PoW, relations, logup columns (prover.rs:84-102)

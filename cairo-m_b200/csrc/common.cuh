@@ -38,6 +38,10 @@ cudaStream_t stream();
 // to the kernel's name.  Disabled (default) it costs one branch.
 void prof_begin(const char* name, uint64_t alg_bytes, unsigned n_kernels);
 void prof_end();
+// books ALGORITHMIC M31 operations (SURVEY.md §8d "ALGORITHMIC ops": butterfly = 3, QM31 mul = 31, QM31 x M31 = 4, ...) to the
+// launch bracketed by the innermost open ProfScope; a no-op when timing is off
+void prof_ops(uint64_t m31_ops);
+bool prof_enabled();
 struct ProfScope {
     ProfScope(const char* name, uint64_t alg_bytes, unsigned n_kernels = 1) { prof_begin(name, alg_bytes, n_kernels); }
     ~ProfScope() { prof_end(); }

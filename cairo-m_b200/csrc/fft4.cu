@@ -216,6 +216,7 @@ static int launch_fft4(const u32* const* src, u32* const* dst, u32 L, u32 log_in
     const size_t n_blocks = n_quads * (((size_t)1 << L) >> TL);
     CM_REQUIRE(n_blocks < (1ull << 31), "fft: batch too large for one launch");
     ProfScope prof(INV ? "ifft_pass" : "rfft_pass", 4ull * n_cols * ((1ull << L) + (1ull << log_in)) / n_passes);
+    prof_ops(n_cols * (3ull * NL * (1ull << (L - 1)) + ((INV && scale != 1) ? (1ull << L) : 0)));  // NL layers of 2^(L-1) butterflies (mul + add + sub)
     kern<<<(unsigned)n_blocks, THREADS, smem, stream()>>>(src, dst, L, log_in, lo, tree, M, scale, (u32)n_cols);
     CM_LAUNCH_CHECK();
     return 0;

@@ -277,6 +277,7 @@ int cm31_fold_line(const uint32_t* const src4[4], uint32_t log_size, const uint3
     size_t n_out = (size_t)1 << (log_size - 1);
     const u32* itw = tree_level_for_line_coset(tw, true, log_size);
     ProfScope prof("fold_line", 24ull * (n_out * 2));
+    prof_ops(n_out * (4 + 4 + 4 + 31 + 4));  // per output: ibutterfly on QM31 (add, sub, x M31) + alpha * f1 (QM31 mul) + add
     fold_line_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, stream()>>>(s, d, n_out, qm_from_arr(alpha), itw);
     CM_LAUNCH_CHECK();
     return 0;
@@ -295,6 +296,7 @@ int cm31_fold_circle_into_line(uint32_t* const dst4[4], const uint32_t* const sr
     QM31 a = qm_from_arr(alpha);
     QM31 a2 = qm_sqr(a);
     ProfScope prof("fold_circle_into_line", 32ull * (n_out * 2));
+    prof_ops(n_out * (4 + 4 + 4 + 31 + 4 + 31 + 4));  // as fold_line + dst * alpha^2 + f'
     if (log_size <= 2) {
         CircleDomain dom = CanonicCoset(log_size).circle_domain();
         u32 iy0 = m31_inv(dom.at(bit_reverse(0, log_size)).y);
@@ -318,6 +320,7 @@ int cm31_accumulate(uint32_t* const dst4[4], const uint32_t* const src4[4], size
     }
     if (n == 0) return 0;
     ProfScope prof("accumulate", 48ull * n);
+    prof_ops(4ull * n);
     accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(d, s, n);
     CM_LAUNCH_CHECK();
     return 0;
@@ -444,6 +447,9 @@ int cm31_accumulate_quotients(uint32_t log_size, const uint32_t* const* cols, si
         CirclePointM31* dq = nullptr;
         CM_CUDA(cudaMallocAsync(&dq, (n / 256) * sizeof(CirclePointM31), stream()));
         ProfScope prof("accumulate_quotients", (4ull * n_cols + 16ull) * n, 2);
+        // per row: every column term c * f(row) is QM31 x M31 + QM31 add (8); per batch: line value (8), acc * alpha^k (31),
+        // CM31 denominator + inverse share (~12), numerator x 1/den (QM31 x CM31 = 8 mul + 4 add)
+        prof_ops(n * (8ull * entries.size() + (8 + 31 + 12 + 12) * (uint64_t)n_batches));
         quotients_block_points_kernel<<<(unsigned)((n / 256 + 127) / 128), 128, 0, stream()>>>(log_size, half.initial_index, half.step_size,
                                                                                              (const CirclePointM31*)dgen.d, dq);
         quotients_fast_kernel<<<(unsigned)(n / 256), 256, 0, stream()>>>(log_size, (const QuotEntry*)dent.d, (const QuotBatch*)dqb.d,

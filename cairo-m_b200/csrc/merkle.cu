@@ -7,6 +7,9 @@
 // One thread per Merkle node: consecutive threads read consecutive words of every column
 // (coalesced 128 B per warp per column) and write 32 contiguous bytes each.  The message block
 // lives in 16 registers and is refilled 16 columns at a time.
+#include <algorithm>
+#include <cstdlib>
+
 #include "blake2s.cuh"
 #include "common.cuh"
 
@@ -63,6 +66,118 @@ __global__ void __launch_bounds__(256) merkle_layer_kernel(u32 log_size, const u
     hash_node(i, prev, cols, n_cols, out);
 }
 
+// ---- one node hashed by FOUR lanes.  The layers near the root that receive the columns of the 16-row padding components
+// (~500 trace / ~1000 interaction columns land in the 32-node layer) are one Merkle-Damgard chain of 30-65 dependent
+// compressions per node: with a thread per node a single warp issues ~1300 dependent-ish instructions per compression
+// (profiles/full_merkle_top_kernel_r01h.md: 219-264 us, one warp active).  Here lane q of a quad holds column q of the 4x4
+// Blake2s state (v[q], v[4+q], v[8+q], v[12+q]): the four column G's of a round run in parallel across the quad, three
+// shuffles rotate b, c, d into the diagonals and back, the message block sits in shared memory (16 words per node) and the
+// next block's column words are loaded while the current one is compressed.
+__constant__ uint8_t CM_SIGMA[10][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}};
+__constant__ u32 CM_BLAKE_IV[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+
+// Lane q's four message indices of round r, packed 4 bits each (column G: x, y; diagonal G: x, y).  The table is built once
+// per CTA in shared memory (a constant-memory table indexed by q serialises the quad's lanes on every access).
+__device__ __forceinline__ void quad_sigma_init(u32 (*tab)[10]) {  // first 40 threads of the CTA; followed by __syncthreads
+    if (threadIdx.x < 40) {
+        const u32 q = threadIdx.x / 10, r = threadIdx.x % 10;
+        const uint8_t* sg = CM_SIGMA[r];
+        tab[q][r] = (u32)sg[2 * q] | ((u32)sg[2 * q + 1] << 4) | ((u32)sg[8 + 2 * q] << 8) | ((u32)sg[9 + 2 * q] << 12);
+    }
+}
+__device__ __forceinline__ void quad_compress(u32& h_lo, u32& h_hi, const u32* msg, u32 q, const u32* sig, u64 t, bool last, u32 mask) {
+    u32 a = h_lo, b = h_hi, c = CM_BLAKE_IV[q], d = CM_BLAKE_IV[4 + q];
+    if (q == 0) d ^= (u32)t;
+    else if (q == 1) d ^= (u32)(t >> 32);
+    else if (q == 2 && last) d = ~d;
+    const u32 l1 = (q + 1) & 3, l2 = (q + 2) & 3, l3 = (q + 3) & 3;
+    // the round's four message words are read from shared memory one round ahead (volatile: the compiler must not hoist all
+    // forty reads to the top and spill them -- the kernel is capped at 64 registers by its 1024-thread launch bound)
+    const volatile u32* vm = msg;
+    u32 sg = sig[0];
+    u32 x0 = vm[sg & 15u], y0 = vm[(sg >> 4) & 15u], x1 = vm[(sg >> 8) & 15u], y1 = vm[(sg >> 12) & 15u];
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        u32 nx0 = 0, ny0 = 0, nx1 = 0, ny1 = 0;
+        if (r < 9) {
+            sg = sig[r + 1];
+            nx0 = vm[sg & 15u], ny0 = vm[(sg >> 4) & 15u], nx1 = vm[(sg >> 8) & 15u], ny1 = vm[(sg >> 12) & 15u];
+        }
+        CM_G(a, b, c, d, x0, y0)
+        b = __shfl_sync(mask, b, l1, 4);
+        c = __shfl_sync(mask, c, l2, 4);
+        d = __shfl_sync(mask, d, l3, 4);
+        CM_G(a, b, c, d, x1, y1)
+        b = __shfl_sync(mask, b, l3, 4);
+        c = __shfl_sync(mask, c, l2, 4);
+        d = __shfl_sync(mask, d, l1, 4);
+        x0 = nx0, y0 = ny0, x1 = nx1, y1 = ny1;
+    }
+    h_lo ^= a ^ c;
+    h_hi ^= b ^ d;
+}
+// node `i` by the quad of lanes (q = lane & 3); `mask` = the lanes of this warp that take part (whole quads).
+// msg = this node's 16 shared-memory words.  Column words are prefetched one block ahead and the column POINTERS two
+// blocks ahead, so neither of the two dependent global loads is ever waited for between compressions.
+__device__ __noinline__ void hash_node_quad(size_t i, const u32* prev, const u32* const* __restrict__ cols, u32 n_cols, u32* out,
+                                            u32* msg, u32 q, const u32 (*sigtab)[10], u32 mask) {
+    const u32* sig = sigtab[q];  // shared memory, read one round ahead
+    u32 h_lo = CM_BLAKE_IV[q] ^ (q == 0 ? 0x01010020u : 0u), h_hi = CM_BLAKE_IV[4 + q];
+    const u64 total = (prev ? 64ull : 0ull) + 4ull * n_cols;
+    u64 done = 0;
+    u32 nxt[4];
+    const u32* nptr[4];  // pointers of the columns of the block after the one in `nxt`
+    auto load_ptrs = [&](u32 c0) {
+#pragma unroll
+        for (u32 k = 0; k < 4; k++) {
+            const u32 col = c0 + 4 * q + k;
+            nptr[k] = col < n_cols ? cols[col] : nullptr;
+        }
+    };
+    auto load_words = [&]() {
+#pragma unroll
+        for (u32 k = 0; k < 4; k++) nxt[k] = nptr[k] ? __ldg(nptr[k] + i) : 0u;
+    };
+    u32 c0;    // first column of the block whose pointers sit in nptr
+    u32 held;  // bytes of the block in nxt
+    if (prev) {
+        const uint4 w = __ldcg(reinterpret_cast<const uint4*>(prev + i * 16) + q);
+        nxt[0] = w.x, nxt[1] = w.y, nxt[2] = w.z, nxt[3] = w.w;
+        held = 64;
+        c0 = 0;
+        load_ptrs(0);
+    } else {
+        load_ptrs(0);
+        load_words();
+        held = 4u * min(16u, n_cols);
+        c0 = 16;
+        load_ptrs(16);
+    }
+    while (true) {
+        __syncwarp(mask);  // the quad has finished reading the previous block
+#pragma unroll
+        for (u32 k = 0; k < 4; k++) msg[4 * q + k] = nxt[k];
+        __syncwarp(mask);
+        done += held;
+        const bool last = done == total;
+        if (!last) {  // words of the next block, pointers of the one after: both in flight while this block is compressed
+            load_words();
+            held = 4u * min(16u, n_cols - c0);
+            c0 += 16;
+            load_ptrs(c0);
+        }
+        quad_compress(h_lo, h_hi, msg, q, sig, done, last, mask);
+        if (last) break;
+    }
+    out[i * 8 + q] = h_lo;
+    out[i * 8 + 4 + q] = h_hi;
+}
+
 // The top of a tree (layers top_log .. 0, at most 2^10 nodes wide) in ONE single-CTA launch:
 // these layers are pure latency (<= 1024 hashes each), a launch per layer costs more than the work.
 // layer_out[l] = output of layer l; cols of layer l = cols[col_start[l] .. col_start[l+1]).
@@ -70,11 +185,23 @@ struct MerkleTopArgs {
     u32* layer_out[11];
     u32 col_start[12];
 };
-__global__ void __launch_bounds__(1024) merkle_top_kernel(u32 top_log, const u32* prev, const u32* const* cols, MerkleTopArgs args) {
+constexpr u32 QUAD_MAX_LOG = 8;  // 4 lanes per node, <= 1024 threads
+__global__ void __launch_bounds__(1024) merkle_top_kernel(u32 top_log, const u32* prev, const u32* const* cols, MerkleTopArgs args, int use_quads) {
+    __shared__ u32 quad_msg[(1u << QUAD_MAX_LOG) * 16];
+    __shared__ u32 quad_sig[4][10];
+    quad_sigma_init(quad_sig);
+    __syncthreads();
     for (int l = (int)top_log; l >= 0; l--) {
-        if (threadIdx.x < (1u << l)) {
-            if (l == (int)top_log) hash_node<false>(threadIdx.x, prev, cols + args.col_start[l], args.col_start[l + 1] - args.col_start[l], args.layer_out[l]);
-            else hash_node<true>(threadIdx.x, prev, cols + args.col_start[l], args.col_start[l + 1] - args.col_start[l], args.layer_out[l]);
+        const u32 n_cols = args.col_start[l + 1] - args.col_start[l];
+        if (use_quads && l <= (int)QUAD_MAX_LOG && (4u << l) <= blockDim.x && (prev != nullptr || n_cols != 0)) {
+            if (threadIdx.x < (4u << l)) {
+                const u32 mask = (4u << l) >= 32u ? 0xffffffffu : ((1u << (4u << l)) - 1u);  // partial warp near the root
+                hash_node_quad(threadIdx.x >> 2, prev, cols + args.col_start[l], n_cols, args.layer_out[l], quad_msg + (threadIdx.x >> 2) * 16,
+                               threadIdx.x & 3u, quad_sig, mask);
+            }
+        } else if (threadIdx.x < (1u << l)) {
+            if (l == (int)top_log) hash_node<false>(threadIdx.x, prev, cols + args.col_start[l], n_cols, args.layer_out[l]);
+            else hash_node<true>(threadIdx.x, prev, cols + args.col_start[l], n_cols, args.layer_out[l]);
         }
         prev = args.layer_out[l];
         __syncthreads();  // block-scope visibility of the layer just written
@@ -95,6 +222,31 @@ __global__ void __launch_bounds__(256) merkle_multi_kernel(u32 log_size, const u
         __syncthreads();  // the children written by this CTA are visible to it
         const u32 cnt = 256u >> lvl;
         if (threadIdx.x < cnt) hash_node<true>(blockIdx.x * (size_t)cnt + threadIdx.x, args.layer_out[lvl - 1], nullptr, 0, args.layer_out[lvl]);
+    }
+}
+
+// The same fusion for LARGE first layers (>= 2^19 nodes), without block barriers: a WARP owns 32 * PER_LANE consecutive nodes of
+// the first layer and the whole subtree above them that keeps all 32 lanes busy (PER_LANE = 8: 256 -> 128 -> 64 -> 32 nodes,
+// 15 full-warp compressions for 480 nodes).  Lanes exchange children through the layer buffers themselves (they are
+// outputs anyway): __syncwarp orders the stores, the re-reads bypass L1.  ncu r01d on the CTA-wide form: 55 % of the
+// stall samples were `barrier` -- after the first level 128, 64, 32, .. of 256 threads hash while the CTA waits; here no
+// warp ever waits for another, so the schedulers always find an eligible warp among the resident ones.
+template <int PER_LANE>
+__global__ void __launch_bounds__(256) merkle_warp_kernel(u32 log_size, const u32* prev, const u32* const* cols, u32 n_cols, u32 n_levels,
+                                                          MerkleMultiArgs args) {
+    const u32 lane = threadIdx.x & 31u;
+    size_t base = ((blockIdx.x * (size_t)256 + threadIdx.x) >> 5) * (32u * PER_LANE);
+    if (base >= ((size_t)1 << log_size)) return;  // whole warps only: 2^log_size is a multiple of 32 * PER_LANE
+#pragma unroll 1
+    for (u32 j = 0; j < (u32)PER_LANE; j++) hash_node<false>(base + j * 32u + lane, prev, cols, n_cols, args.layer_out[0]);
+    u32 cnt = 32u * PER_LANE;
+#pragma unroll 1
+    for (u32 lvl = 1; lvl < n_levels; lvl++) {
+        __syncwarp();  // the children this warp wrote are visible to all of its lanes
+        cnt >>= 1;
+        base >>= 1;
+#pragma unroll 1
+        for (u32 k = lane; k < cnt; k += 32u) hash_node<true>(base + k, args.layer_out[lvl - 1], nullptr, 0, args.layer_out[lvl]);
     }
 }
 
@@ -155,6 +307,23 @@ int cm31_blake2s_commit_multi(uint32_t log_size, const uint32_t* prev_layer, con
     size_t n = (size_t)1 << log_size;
     uint64_t bytes = (4ull * n_cols + 32ull + (prev_layer ? 64ull : 0ull)) * n;
     for (u32 l = 1; l < n_levels; l++) bytes += 96ull * (n >> l);
+    if (log_size >= 19 && n_levels >= 2 && !getenv("CM31_MERKLE_CTA_FUSION")) {
+        // large layers: barrier-free warp subtrees, 4 (3) levels per launch, the remaining levels by further launches
+        const u32 per_lane = log_size >= 21 ? 8 : 4;
+        const u32 lv = std::min<u32>(n_levels, per_lane == 8 ? 4 : 3);
+        uint64_t b0 = (4ull * n_cols + 32ull + (prev_layer ? 64ull : 0ull)) * n;
+        for (u32 l = 1; l < lv; l++) b0 += 96ull * (n >> l);
+        {
+            ProfScope prof(n_cols ? "merkle_leaf_layer" : "merkle_inner_layer", b0);
+            const unsigned blocks = (unsigned)((n / (32 * per_lane) * 32 + 255) / 256);
+            if (per_lane == 8) merkle_warp_kernel<8><<<blocks, 256, 0, stream()>>>(log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, lv, args);
+            else merkle_warp_kernel<4><<<blocks, 256, 0, stream()>>>(log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, lv, args);
+            CM_LAUNCH_CHECK();
+        }
+        if (lv == n_levels) return 0;
+        if (n_levels - lv == 1) return cm31_blake2s_commit_layer(log_size - lv, out_layers[lv - 1], nullptr, 0, out_layers[lv]);
+        return cm31_blake2s_commit_multi(log_size - lv, out_layers[lv - 1], nullptr, 0, n_levels - lv, out_layers + lv);
+    }
     ProfScope prof(n_cols ? "merkle_leaf_layer" : "merkle_inner_layer", bytes);
     merkle_multi_kernel<<<(unsigned)(n / 256), 256, 0, stream()>>>(log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, n_levels, args);
     CM_LAUNCH_CHECK();
@@ -174,7 +343,11 @@ int cm31_blake2s_commit_top(uint32_t top_log_size, const uint32_t* prev_layer, c
     uint64_t bytes = 0;
     for (u32 l = 0; l <= top_log_size; l++) bytes += (4ull * (args.col_start[l + 1] - args.col_start[l]) + 96ull) << l;
     ProfScope prof("merkle_top_layers", bytes);
-    merkle_top_kernel<<<1, 1u << top_log_size < 32 ? 32 : 1u << top_log_size, 0, stream()>>>(top_log_size, prev_layer, (const u32* const*)dcols.d, args);
+    static const int use_quads = getenv("CM31_MERKLE_NO_QUADS") ? 0 : 1;
+    unsigned threads = 1u << top_log_size < 32 ? 32 : 1u << top_log_size;
+    if (use_quads) threads = std::max(threads, std::min(1024u, 4u << std::min(top_log_size, QUAD_MAX_LOG)));
+    if (threads < 64) threads = 64;  // the sigma table is built by the first 40 threads
+    merkle_top_kernel<<<1, threads, 0, stream()>>>(top_log_size, prev_layer, (const u32* const*)dcols.d, args, use_quads);
     CM_LAUNCH_CHECK();
     return 0;
 }

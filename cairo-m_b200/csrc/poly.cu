@@ -509,6 +509,7 @@ static int run_fft(const u32* const* src_host, u32* const* dst_host, size_t n_co
         CM_REQUIRE(n_blocks < (1ull << 31), "fft: batch too large for one launch");
         // algorithmic bytes of the whole transform (read 2^log_in, write 2^L words per column) split evenly over its passes
         ProfScope prof(INV ? "ifft_pass" : "rfft_pass", 4ull * n_cols * ((1ull << L) + (1ull << log_in)) / np);
+        prof_ops(n_cols * (3ull * ps.nl * (1ull << (L - 1)) + ((INV && last) ? (1ull << L) : 0)));
         kern<<<(unsigned)n_blocks, threads, smem, stream()>>>(first ? src : (const u32* const*)dst, dst, L,
                                                               first ? log_in : L, ps.lo, ps.nl, ps.b, tree,
                                                               tw->log_size, (INV && last) ? scale_last : 1u,
@@ -650,6 +651,7 @@ int cm31_eval_at_point_batch(const uint32_t* const* coeffs, const uint32_t* log_
         uint64_t coeff_bytes = 0;
         for (size_t i = 0; i < n_polys; i++) coeff_bytes += 4ull << log_sizes_host[i];
         ProfScope prof("eval_at_point", coeff_bytes, 2);
+        prof_ops(coeff_bytes / 4 * 8);  // per coefficient: QM31 x M31 (4 mul) + QM31 add (4)
         eap_stage1_kernel<<<(unsigned)chunk_job.size(), 256, 0, stream()>>>((const EapJob*)djobs.d, (const u32*)dchunk.d,
                                                                            (const u32*)dfac.d, dpart);
         eap_stage2_kernel<<<(unsigned)n_polys, 256, 0, stream()>>>((const EapJob*)djobs.d, (const u32*)dfac.d, dpart, dout);

@@ -41,6 +41,7 @@ struct ProfRec {
     const char* name;
     uint64_t bytes;
     cudaEvent_t a, b;
+    uint64_t ops = 0;
 };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
@@ -64,6 +65,10 @@ void prof_begin(const char* name, uint64_t alg_bytes, unsigned n_kernels) {
     cudaEventRecord(r.a, stream());
     g_prof.push_back(r);
 }
+void prof_ops(uint64_t m31_ops) {
+    if (g_prof_on && !g_prof.empty()) g_prof.back().ops += m31_ops;
+}
+bool prof_enabled() { return g_prof_on; }
 void prof_end() {
     if (!g_prof_on) return;
     cudaEventRecord(g_prof.back().b, stream());
@@ -236,7 +241,7 @@ int cm31_profile_report(char* buf, size_t cap, size_t* len) {
     struct Agg {
         const char* name;
         double ms = 0;
-        uint64_t launches = 0, bytes = 0;
+        uint64_t launches = 0, bytes = 0, ops = 0;
     };
     std::vector<Agg> aggs;
     for (ProfRec& r : g_prof) {
@@ -253,12 +258,14 @@ int cm31_profile_report(char* buf, size_t cap, size_t* len) {
         a->ms += ms;
         a->launches++;
         a->bytes += r.bytes;
+        a->ops += r.ops;
     }
     std::string s = "[";
     for (size_t i = 0; i < aggs.size(); i++) {
         char line[256];
-        snprintf(line, sizeof line, "%s{\"kernel\": \"%s\", \"ms\": %.6f, \"launches\": %llu, \"alg_bytes\": %llu}", i ? ", " : "",
-                 aggs[i].name, aggs[i].ms, (unsigned long long)aggs[i].launches, (unsigned long long)aggs[i].bytes);
+        snprintf(line, sizeof line, "%s{\"kernel\": \"%s\", \"ms\": %.6f, \"launches\": %llu, \"alg_bytes\": %llu, \"m31_ops\": %llu}",
+                 i ? ", " : "", aggs[i].name, aggs[i].ms, (unsigned long long)aggs[i].launches, (unsigned long long)aggs[i].bytes,
+                 (unsigned long long)aggs[i].ops);
         s += line;
     }
     s += "]";

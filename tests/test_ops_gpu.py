@@ -311,7 +311,11 @@ def test_commit_top_layers_matches_layer_by_layer_oracle(cm, top, with_prev, col
 
 
 @pytest.mark.parametrize("log_size,n_cols,with_prev,n_levels", [(8, 4, False, 9), (11, 4, False, 1), (13, 0, True, 3), (12, 21, True, 2),
-                                                               (16, 4, False, 6), (17, 17, True, 9)])
+                                                               (16, 4, False, 6), (17, 17, True, 9),
+                                                               # >= 2^19 nodes: barrier-free warp subtrees (4 nodes per lane: 3
+                                                               # levels per launch; 8 per lane from 2^21: 4 levels), then the rest
+                                                               (19, 4, False, 2), (19, 0, True, 3), (20, 5, True, 9), (21, 4, False, 4),
+                                                               (21, 18, True, 6), (22, 4, False, 9)])
 def test_commit_multi_matches_layer_by_layer_oracle(cm, log_size, n_cols, with_prev, n_levels):
     # fused consecutive layers (first with columns / a previous layer, the rest column-free) == one commit_on_layer per layer
     mat = orc.splitmix64(0x51 + log_size, n_cols << log_size).reshape(n_cols, 1 << log_size) if n_cols else None
