@@ -39,6 +39,7 @@ int cm31_test_prove_wide_fibonacci(uint32_t log_n_rows, uint32_t n_cols, uint32_
 #include <deque>
 
 #include "cairo/prover.hpp"
+#include "cairo/proof_json.hpp"
 #include "host/cuda_air_impl.hpp"
 
 struct cm31_prover_input {
@@ -568,6 +569,43 @@ int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n
         set_error(e.what());
         return -2;
     }
+}
+
+// ---- the reference's wire format (serde JSON of Proof<Blake2sMerkleHasher>, crates/prover/src/lib.rs:61-73)
+int cm31_proof_to_json(const uint8_t* proof, size_t proof_len, char* json_out, size_t cap, size_t* json_len) {
+    try {
+        CM_REQUIRE(proof != nullptr, "proof_to_json: null proof");
+        std::string js = cairo_proof_to_json(CairoProof::from_bytes(proof, proof_len, cairo_component_names()));
+        if (json_len) *json_len = js.size();
+        CM_REQUIRE(json_out == nullptr || js.size() < cap, "proof_to_json: buffer too small");
+        if (json_out) memcpy(json_out, js.c_str(), js.size() + 1);
+        return 0;
+    } catch (const std::exception& e) {
+        set_error(e.what());
+        return -2;
+    }
+}
+int cm31_proof_from_json(const char* json, size_t json_len, uint8_t* proof_out, size_t cap, size_t* proof_len) {
+    try {
+        CM_REQUIRE(json != nullptr, "proof_from_json: null text");
+        return write_out(cairo_proof_from_json(json, json_len).to_bytes(), proof_out, cap, proof_len);
+    } catch (const std::exception& e) {
+        set_error(e.what());
+        return -2;
+    }
+}
+int cm31_prove_cairo_m_json(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, char* json_out, size_t cap, size_t* json_len) {
+    // proofs are deterministic: a NULL json_out proves once to learn the length, like the other size queries of this ABI;
+    // callers that care pass a buffer of 8x the blob size (the JSON is ~3.4x the blob)
+    std::vector<uint8_t> blob((size_t)1 << 24);
+    size_t n = 0;
+    int rc = cm31_prove_cairo_m(h, pow_bits, n_queries, blob.data(), blob.size(), &n, nullptr);
+    if (rc == -1 && n > blob.size()) {
+        blob.resize(n);
+        rc = cm31_prove_cairo_m(h, pow_bits, n_queries, blob.data(), blob.size(), &n, nullptr);
+    }
+    if (rc) return rc;
+    return cm31_proof_to_json(blob.data(), n, json_out, cap, json_len);
 }
 
 }  // extern "C"

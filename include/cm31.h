@@ -263,6 +263,15 @@ int cm31_input_release_device(cm31_prover_input* h);
  * "ConstraintsNotSatisfied" (S/prover/src/core/prover/mod.rs:76-82) if the OODS check fails. */
 int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out,
                        size_t proof_cap, size_t* proof_len, double* timings_ms);
+/* The reference's proof wire format: serde JSON of Proof<Blake2sMerkleHasher> (P/src/lib.rs:61-73; CommitmentSchemeProof
+ * S/prover/src/core/pcs/prover.rs:156-165, FriProof S/prover/src/core/fri.rs:675-699, MerkleDecommitment
+ * S/prover/src/core/vcs/prover.rs:163-173), as `cairo-m-prover --output` writes it with sonic_rs (P/src/main.rs:88) and
+ * `verify_cairo_m` reads it.  The blob of cm31_prove_cairo_m and the JSON carry the same proof: to_json / from_json are
+ * inverse of each other (host only, no device work).  json_out may be NULL to query the length (without the final NUL). */
+int cm31_proof_to_json(const uint8_t* proof, size_t proof_len, char* json_out, size_t cap, size_t* json_len);
+int cm31_proof_from_json(const char* json, size_t json_len, uint8_t* proof_out, size_t cap, size_t* proof_len);
+int cm31_prove_cairo_m_json(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, char* json_out, size_t cap,
+                            size_t* json_len);
 /* The reference's ProverInput (P/src/adapter/mod.rs:40-95: Instructions {initial/final registers, states_by_opcodes,
  * data_accesses}, Memory {initial_memory, final_memory, clock_update_data}, MerkleTrees, public_address_ranges) as flat
  * u32 tables — what a Rust caller that ran its own adapter hands over.  Record layouts (words):
