@@ -305,8 +305,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    programs = {"fibonacci_loop": 0, "array_sum": 1, "u32_counter": 2, "u32_mix": 3}
+    programs = {"fibonacci_loop": 0, "array_sum": 1, "u32_counter": 2, "u32_mix": 3, "sha256": 4}
     n = args.iterations if args.iterations else fib_iterations(args.log_steps)
+    if args.program == "sha256" and not args.iterations:
+        n = (1 << args.log_steps) // 3490  # ~3 490 VM steps per compression: BASELINE config 3 (~2^22 rows of u32 / bitwise work)
     h = C.c_void_p()
     cm.check(lib.cm31_test_program_input_create(C.c_uint32(programs[args.program]), C.c_uint32(n), C.byref(h)))
     info = (C.c_uint64 * 5)()
@@ -455,7 +457,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 (M31/QM31 modular integer)", "data": "synthetic",
         "config": {"workload": workload_name(args.log_steps) if args.program == "fibonacci_loop" and not args.iterations
-                   else f"{args.program}({n}) [side measurement, not the BASELINE workload]", "vm_steps_per_proof": vm_steps,
+                   else (f"sha256({n} compressions of a padded block, examples/sha256-cairo-m style: u32 / bitwise / range-check components) "
+                         f"[BASELINE config 3, not the headline workload]" if args.program == "sha256"
+                         else f"{args.program}({n}) [side measurement, not the BASELINE workload]"), "vm_steps_per_proof": vm_steps,
                    "parallelism": "one independent segment proof per GPU" if world > 1 else "single GPU",
                    "l2": "working set per proof (GBs of trace/LDE columns) >> 126 MB L2; no flush between steps",
                    "pcs": {"pow_bits": 16, "log_blowup": 1, "n_queries": 80}},
@@ -488,7 +492,7 @@ def main():
                     help="log2 VM steps of the cpu_baseline proof (default: the workload's own size, one whole proof)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-adapter", action="store_true", help="skip the adapter side measurement")
-    ap.add_argument("--program", default="fibonacci_loop", choices=["fibonacci_loop", "array_sum", "u32_counter", "u32_mix"],
+    ap.add_argument("--program", default="fibonacci_loop", choices=["fibonacci_loop", "array_sum", "u32_counter", "u32_mix", "sha256"],
                     help="side measurements on the other hand-assembled programs (the headline is fibonacci_loop)")
     ap.add_argument("--iterations", type=int, default=0, help="program argument n (default: 2^log_steps / 8 for fibonacci_loop)")
     ap.add_argument("--dist-selftest", action="store_true", help=argparse.SUPPRESS)

@@ -216,13 +216,129 @@ inline std::vector<Word4> u32_mix_program() {
     return p;
 }
 
-enum CairoProgramId : u32 { PROGRAM_FIBONACCI_LOOP = 0, PROGRAM_ARRAY_SUM = 1, PROGRAM_U32_COUNTER = 2, PROGRAM_U32_MIX = 3 };
+// SHA-256 (FIPS 180-4) the way examples/sha256-cairo-m/src/sha256.cm writes it -- BASELINE config 3, the u32 / bitwise /
+// range-check heavy workload: rotr(x, n) = (x * 2^(32-n)) | (x / 2^n) through U32StoreMulFpImm + U32StoreDivRemFpImm +
+// U32StoreOrFpFp (sha256.cm:17-28), Sigma / sigma / Ch / Maj through the byte-wise bitwise table (and, or, xor), the additions
+// through the u32 limb adders.  n compressions of the padded block of "abc" chained through H (n = 1 gives sha256("abc"),
+// the vector of the reference's own prover test, crates/prover/tests/prover.rs:247); one compression is straight-line code
+// (48 schedule steps + 64 rounds, the working variables a..h renamed at assembly time instead of copied), ~3 490 VM steps.
+// Returns the sum of the sixteen 16-bit limbs of H.  No instruction reads and writes the same cell.
+inline std::vector<Word4> sha256_program() {
+    static const u32 K[64] = {
+        0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+        0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+        0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+        0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+        0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+        0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    static const u32 IV[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    const u32 M3 = P - 3, M4 = P - 4;
+    std::vector<Word4> p;
+    auto one_word = [&](u32 op, u32 a, u32 b, u32 c) { p.push_back(Word4{{op, a, b, c}}); };
+    auto two_words = [&](u32 op, u32 a, u32 b, u32 c, u32 d, u32 e = 0) {
+        p.push_back(Word4{{op, a, b, c}});
+        p.push_back(Word4{{d, e, 0, 0}});
+    };
+    const u32 I = 0, I_NEXT = 1, CMP = 2, T0 = 200;  // frame: felts 0..2, H 10.., working variables 30.., W 50.., temporaries 200..
+    auto H = [](u32 k) { return 10 + 2 * k; };
+    auto S = [](u32 k) { return 30 + 2 * (k & 7); };
+    auto W = [](u32 t) { return 50 + 2 * t; };
+    u32 tnext = T0;
+    auto T = [&]() {
+        u32 t = tnext;
+        tnext += 2;
+        return t;
+    };
+    auto lo = [](u32 v) { return v & 0xffffu; };
+    auto hi = [](u32 v) { return v >> 16; };
+    auto imm = [&](u32 v, u32 dst) { one_word(OP_U32_STORE_IMM, lo(v), hi(v), dst); };
+    auto bin_to = [&](u32 op, u32 a, u32 b, u32 dst) { one_word(op, a, b, dst); };
+    auto bin = [&](u32 op, u32 a, u32 b) {
+        u32 d = T();
+        one_word(op, a, b, d);
+        return d;
+    };
+    auto add = [&](u32 a, u32 b) { return bin(OP_U32_STORE_ADD_FP_FP, a, b); };
+    auto band = [&](u32 a, u32 b) { return bin(OP_U32_STORE_AND_FP_FP, a, b); };
+    auto bor = [&](u32 a, u32 b) { return bin(OP_U32_STORE_OR_FP_FP, a, b); };
+    auto bxor = [&](u32 a, u32 b) { return bin(OP_U32_STORE_XOR_FP_FP, a, b); };
+    auto addi = [&](u32 a, u32 v) {
+        u32 d = T();
+        two_words(OP_U32_STORE_ADD_FP_IMM, a, lo(v), hi(v), d);
+        return d;
+    };
+    auto xori = [&](u32 a, u32 v) {
+        u32 d = T();
+        two_words(OP_U32_STORE_XOR_FP_IMM, a, lo(v), hi(v), d);
+        return d;
+    };
+    auto copy = [&](u32 a, u32 dst) { two_words(OP_U32_STORE_ADD_FP_IMM, a, 0, 0, dst); };
+    auto shr = [&](u32 a, u32 n) {  // x / 2^n (sha256.cm:40,45)
+        u32 q = T(), r = T();
+        two_words(OP_U32_STORE_DIV_REM_FP_IMM, a, lo(1u << n), hi(1u << n), q, r);
+        return q;
+    };
+    auto rotr = [&](u32 a, u32 n) {  // sha256.cm:17-28
+        u32 q = T(), r = T(), sh = T();
+        two_words(OP_U32_STORE_DIV_REM_FP_IMM, a, lo(1u << n), hi(1u << n), q, r);
+        two_words(OP_U32_STORE_MUL_FP_IMM, a, lo(1u << (32 - n)), hi(1u << (32 - n)), sh);
+        return bor(sh, q);
+    };
+    for (u32 k = 0; k < 8; k++) imm(IV[k], H(k));
+    one_word(OP_STORE_IMM, 0, I, 0);
+    const u32 loop = (u32)p.size();
+    one_word(OP_STORE_SUB_FP_FP, I, M4, CMP);  // i - n
+    one_word(OP_JNZ_FP_IMM, CMP, 2, 0);
+    const u32 exit_jmp = (u32)p.size();
+    one_word(OP_JMP_REL_IMM, 0, 0, 0);  // -> exit (patched below)
+    for (u32 k = 0; k < 8; k++) copy(H(k), S(k));
+    imm(0x61626380u, W(0));  // "abc" + the 1 bit
+    for (u32 t = 1; t < 15; t++) imm(0, W(t));
+    imm(0x18, W(15));  // message length in bits
+    for (u32 t = 16; t < 64; t++) {  // message schedule (sha256.cm:73-77)
+        tnext = T0;
+        u32 s0 = bxor(bxor(rotr(W(t - 15), 7), rotr(W(t - 15), 18)), shr(W(t - 15), 3));
+        u32 s1 = bxor(bxor(rotr(W(t - 2), 17), rotr(W(t - 2), 19)), shr(W(t - 2), 10));
+        bin_to(OP_U32_STORE_ADD_FP_FP, add(add(W(t - 16), s0), W(t - 7)), s1, W(t));
+    }
+    for (u32 t = 0; t < 64; t++) {  // compression rounds (sha256.cm:86-97); role r of round t lives in slot (r - t) mod 8
+        tnext = T0;
+        const u32 a = S(0 - t), b = S(1 - t), c = S(2 - t), d = S(3 - t), e = S(4 - t), f = S(5 - t), g = S(6 - t), h = S(7 - t);
+        u32 s1 = bxor(bxor(rotr(e, 6), rotr(e, 11)), rotr(e, 25));
+        u32 ch = bxor(band(e, f), band(xori(e, 0xffffffffu), g));
+        u32 t1 = add(addi(add(add(h, s1), ch), K[t]), W(t));
+        u32 s0 = bxor(bxor(rotr(a, 2), rotr(a, 13)), rotr(a, 22));
+        u32 maj = bxor(bxor(band(a, b), band(a, c)), band(b, c));
+        u32 t2 = add(s0, maj);
+        copy(add(d, t1), d);                                  // e' = d + temp1, in d's slot (= role e of round t + 1)
+        bin_to(OP_U32_STORE_ADD_FP_FP, t1, t2, h);            // a' = temp1 + temp2, in h's slot (= role a of round t + 1)
+    }
+    tnext = T0;
+    for (u32 k = 0; k < 8; k++) copy(add(H(k), S(k)), H(k));  // after 64 rounds role k is back in slot k
+    one_word(OP_STORE_ADD_FP_IMM, I, 1, I_NEXT);
+    one_word(OP_STORE_ADD_FP_IMM, I_NEXT, 0, I);
+    const u32 back = (u32)p.size();
+    one_word(OP_JMP_REL_IMM, m31_sub(loop, back), 0, 0);
+    p[exit_jmp].v[1] = (u32)p.size() - exit_jmp;
+    u32 acc = H(0);  // felt sum of the sixteen limbs
+    for (u32 k = 1; k < 16; k++) {
+        u32 dst = T0 + (k & 1);
+        one_word(OP_STORE_ADD_FP_FP, acc, H(0) + k, dst);
+        acc = dst;
+    }
+    one_word(OP_STORE_ADD_FP_IMM, acc, 0, M3);
+    one_word(OP_RET, 0, 0, 0);
+    return p;
+}
+
+enum CairoProgramId : u32 { PROGRAM_FIBONACCI_LOOP = 0, PROGRAM_ARRAY_SUM = 1, PROGRAM_U32_COUNTER = 2, PROGRAM_U32_MIX = 3, PROGRAM_SHA256 = 4 };
 inline std::vector<Word4> program_by_id(u32 id) {
     switch (id) {
         case PROGRAM_FIBONACCI_LOOP: return fibonacci_loop_program();
         case PROGRAM_ARRAY_SUM: return array_sum_program();
         case PROGRAM_U32_COUNTER: return u32_counter_program();
         case PROGRAM_U32_MIX: return u32_mix_program();
+        case PROGRAM_SHA256: return sha256_program();
         default: throw std::runtime_error("unknown program id");
     }
 }

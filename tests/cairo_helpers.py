@@ -6,7 +6,7 @@ from tests import oracle_lib as orc
 CAP = 1 << 27
 
 
-FIB, ARRAY_SUM, U32_COUNTER, U32_MIX = 0, 1, 2, 3
+FIB, ARRAY_SUM, U32_COUNTER, U32_MIX, SHA256 = 0, 1, 2, 3, 4
 
 
 def oracle_fib_prove(n, pow_bits=16, n_queries=80):
@@ -208,6 +208,39 @@ def u32_mix_expected(n):
         x = (b + r) & M
         y = (y + 2) & M
     return x & 0xFFFF
+
+
+_SHA_K = [0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+          0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+          0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+          0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+          0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+          0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2]
+
+
+def sha256_state_after(n):
+    """H after n compressions of the padded block of b"abc", chained (the sha256 program of csrc/cairo/vm.hpp); plain FIPS 180-4."""
+    M = 0xFFFFFFFF
+    rotr = lambda x, k: ((x >> k) | (x << (32 - k))) & M
+    H = [0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19]
+    for _ in range(n):
+        w = [0x61626380] + [0] * 14 + [0x18]
+        for t in range(16, 64):
+            s0 = rotr(w[t - 15], 7) ^ rotr(w[t - 15], 18) ^ (w[t - 15] >> 3)
+            s1 = rotr(w[t - 2], 17) ^ rotr(w[t - 2], 19) ^ (w[t - 2] >> 10)
+            w.append((w[t - 16] + s0 + w[t - 7] + s1) & M)
+        a, b, c, d, e, f, g, h = H
+        for t in range(64):
+            t1 = (h + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & M & g)) + _SHA_K[t] + w[t]) & M
+            t2 = ((rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c))) & M
+            a, b, c, d, e, f, g, h = (t1 + t2) & M, a, b, c, (d + t1) & M, e, f, g
+        H = [(x + y) & M for x, y in zip(H, [a, b, c, d, e, f, g, h])]
+    return H
+
+
+def sha256_expected(n):
+    """The program's return value: the sum of the sixteen 16-bit limbs of H."""
+    return sum((x & 0xFFFF) + (x >> 16) for x in sha256_state_after(n))
 
 
 def corrupt_first_claimed_sum(proof: bytes) -> bytes:

@@ -38,7 +38,7 @@ def assert_same_tables(cm, host_handle, dev_handle):
 
 
 @pytest.mark.parametrize("program,n", [(ch.FIB, 0), (ch.FIB, 1), (ch.FIB, 1000), (ch.ARRAY_SUM, 200), (ch.U32_COUNTER, 150),
-                                       (ch.U32_MIX, 60)])
+                                       (ch.U32_MIX, 60), (ch.SHA256, 2)])
 def test_device_adapter_tables_match_host_adapter(cm, program, n):
     host = ch.GpuFibInput(cm, n, program)
     dev = ch.GpuAdaptedInput(cm, n, program)

@@ -228,3 +228,38 @@ def test_lookup_outside_its_table_is_refused_not_written_out_of_bounds(cm, what)
             assert again.prove()[0] == good
         finally:
             again.close()
+
+
+@pytest.mark.parametrize("n", [1, 5])
+def test_sha256_proof_bit_exact(cm, n):
+    # BASELINE config 3: SHA-256 as examples/sha256-cairo-m/src/sha256.cm computes it (rotr = mul | div, byte-wise and / or / xor
+    # through the bitwise table, u32 limb adders): n = 1 is sha256("abc"), the vector of crates/prover/tests/prover.rs:247
+    inp = ch.GpuFibInput(cm, n, program=ch.SHA256)
+    try:
+        assert inp.return_value == ch.sha256_expected(n)
+        got, _ = inp.prove()
+    finally:
+        inp.close()
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+    residual, _ = ch.oracle_logup_residual(n, got, program=ch.SHA256)
+    assert residual == (0, 0, 0, 0)
+    want, _ = ch.oracle_program_prove(ch.SHA256, n)
+    assert got == want
+
+
+def test_sha256_2_20_steps_verifies_from_device_adapted_logs(cm):
+    # 300 chained compressions = 1.05 M VM steps, u32 / bitwise / range-check components at 2^17..2^19 rows, input produced by
+    # the DEVICE adapter from the runner's logs; the JSON wire form of the proof round-trips to the same bytes
+    import ctypes as C
+    n = 300
+    dev = ch.GpuAdaptedInput(cm, n, ch.SHA256)
+    try:
+        assert dev.steps > 1 << 20 and dev.return_value == ch.sha256_expected(n)
+        got, _ = dev.prove()
+    finally:
+        dev.close()
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+    residual, _ = ch.oracle_logup_residual(n, got, program=ch.SHA256)
+    assert residual == (0, 0, 0, 0)
+    from tests.test_proof_json import from_json, to_json
+    assert from_json(cm, to_json(cm, got)) == got

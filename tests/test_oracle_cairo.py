@@ -114,3 +114,24 @@ def test_poseidon2_permutation_structure():
     orc.lib().orc_poseidon2_permutation((C.c_uint32 * 16)(*range(16)), a)
     orc.lib().orc_poseidon2_permutation((C.c_uint32 * 16)(*([1] + list(range(1, 16)))), b)
     assert all(x != y for x, y in zip(a, b)) and all(x < orc.P for x in a)
+
+
+# ---- BASELINE config 3: SHA-256 (examples/sha256-cairo-m/src/sha256.cm) on the u32 / bitwise / range-check components
+def test_sha256_reference_state_is_fips_180_4():
+    import hashlib
+    assert b"".join(x.to_bytes(4, "big") for x in ch.sha256_state_after(1)) == hashlib.sha256(b"abc").digest()
+
+
+def test_sha256_program_proves_and_returns_the_digest_of_abc():
+    # the vector of the reference's own prover test (crates/prover/tests/prover.rs:247: sha256 of "abc")
+    proof = ch.oracle_program_prove(ch.SHA256, 1)[0]
+    assert ch.oracle_cairo_verify(proof) == 0, orc.last_error()
+    residual, info = ch.oracle_logup_residual(1, proof, program=ch.SHA256)
+    assert residual == (0, 0, 0, 0)
+    assert info["fib"] == ch.sha256_expected(1)
+    assert 3000 < info["steps"] < 4000
+
+
+def test_sha256_program_chains_compressions():
+    residual, info = ch.oracle_logup_residual(3, ch.oracle_program_prove(ch.SHA256, 3)[0], program=ch.SHA256)
+    assert residual == (0, 0, 0, 0) and info["fib"] == ch.sha256_expected(3)
