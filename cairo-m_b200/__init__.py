@@ -42,6 +42,35 @@ def check(status: int) -> None:
         raise Cm31Error(lib().cm31_last_error().decode() or f"cm31 status {status}")
 
 
+def shard_init(arena_gib: float = 24.0) -> tuple[int, int]:
+    """Single-proof sharding over the ranks of torch.distributed (one process per GPU, NCCL): rank 0 creates the NCCL id of
+    libcm31's own communicator, torch.distributed hands it to the others, every rank maps every other rank's arena.
+    Returns (rank, world).  After this call every cm31_prove_cairo_m of this process is one share of a sharded proof: all
+    ranks must call it in lockstep with the same input."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(), dist.get_world_size()
+    else:
+        rank, world = 0, 1
+    uid = (C.c_uint8 * 128)()
+    if rank == 0:
+        check(lib().cm31_shard_unique_id(uid))
+    if world > 1:
+        t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        uid = (C.c_uint8 * 128)(*t.cpu().tolist())
+    check(lib().cm31_shard_init(C.c_int(rank), C.c_int(world), uid, C.c_size_t(int(arena_gib * (1 << 30)))))
+    return rank, world
+
+
+def shard_stats() -> dict:
+    rank, world, st = C.c_int(), C.c_int(), (C.c_uint64 * 4)()
+    check(lib().cm31_shard_info(C.byref(rank), C.byref(world), st))
+    return {"rank": rank.value, "world": world.value, "arena_peak_bytes": int(st[0]), "bytes_all_gathered": int(st[1]),
+            "bytes_all_reduced": int(st[2]), "collectives": int(st[3])}
+
+
 def _ptr_array(tensors):
     arr = (C.c_void_p * len(tensors))()
     for i, t in enumerate(tensors):

@@ -91,7 +91,7 @@ def build_lib(force: bool = False) -> Path:
         list(ex.map(compile_one, jobs))
     if force or jobs or not _newer(LIB, objs):
         _run([NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
-              "-Xcompiler", "-fopenmp", "-lcudart", "-lgomp"])
+              "-Xcompiler", "-fopenmp", "-lcudart", "-lgomp", "-lnccl"])
     return LIB
 
 

@@ -364,13 +364,53 @@ StagedInput<Impl> stage_input(const ProverInput& input, StagedInput<Impl>* recyc
     return st;
 }
 
+// Longest-processing-time-first assignment of components to `world` ranks (deterministic: ties go to the lower index / rank).
+inline std::vector<int> assign_component_owners(const std::vector<double>& cost, int world) {
+    std::vector<int> owner(cost.size(), 0);
+    if (world <= 1) return owner;
+    std::vector<size_t> order(cost.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cost[a] > cost[b]; });
+    std::vector<double> load((size_t)world, 0.0);
+    for (size_t i : order) {
+        int best = 0;
+        for (int r = 1; r < world; r++)
+            if (load[(size_t)r] < load[(size_t)best]) best = r;
+        owner[i] = best;
+        load[(size_t)best] += cost[i];
+    }
+    return owner;
+}
+
 template <class Impl>
 CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& staged, PcsConfig pcs_config, ProveTimings* timings = nullptr) {
     typedef typename Impl::B B;
     typedef typename B::Col Col;
     auto t0 = Impl::now_ms();
+    B::shard_begin_proof();  // single-proof sharding: arena reset + barrier; a no-op otherwise
+    struct ShardEnd {
+        ~ShardEnd() { B::shard_end_proof(); }
+    } shard_end;
     Blake2sChannel channel;
     pcs_config.mix_into(channel);
+
+    // Component ownership when the proof is sharded over the GPUs of a node: all columns of a component stay on one rank
+    // (its constraint evaluation and logup generation are local); components are dealt out longest-processing-time first
+    // by padded rows x trace columns.  Every rank computes the same assignment.
+    {
+        std::vector<double> cost;
+        size_t oi = 0;
+#define CM31_X(E) cost.push_back((double)((size_t)1 << padded_log_size(staged.opcode.at(oi++).n_real)) * (double)E::N_TRACE_COLUMNS);
+        CM31_OPCODE_EVALS(CM31_X)
+#undef CM31_X
+        cost.push_back((double)((size_t)1 << padded_log_size(staged.memory.n_real)) * MemoryEval::N_TRACE_COLUMNS);
+        cost.push_back((double)((size_t)1 << padded_log_size(staged.merkle.n_real)) * MerkleEval::N_TRACE_COLUMNS);
+        cost.push_back((double)((size_t)1 << padded_log_size(staged.clock_update.n_real)) * ClockUpdateEval::N_TRACE_COLUMNS);
+        cost.push_back((double)((size_t)1 << padded_log_size(staged.poseidon2.n_real)) * Poseidon2Eval::N_TRACE_COLUMNS);
+        for (u32 bits : {8u, 16u, 20u, (u32)BITWISE_STACKED_LOG_SIZE}) cost.push_back((double)((size_t)1 << bits) * 2.0);
+        B::set_component_owners(assign_component_owners(cost, B::shard_world()));
+    }
+    size_t scope_index = 0;  // claim-order index of the component whose trace is being written
 
     // trace_log_size (prover.rs:38-53)
     size_t max_rows = 1;
@@ -416,6 +456,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         typedef decltype(eval_tag) Eval;
         const auto& rows = staged.opcode.at(opcode_index++);
         u32 ls = padded_log_size(rows.n_real);
+        B::component_scope_index(scope_index++);  // sharded proof: only the owner fills this component's trace
         B::lane(ls);  // small components go to the side lane; every temporary below dies on the lane that used it
         Impl::staging_wait(rows.mark);
         std::vector<Col> inputs = Impl::unpack_bundles(rows.words, rows.n_real, staged.accesses, staged.n_accesses, ls);
@@ -430,6 +471,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
 #undef CM31_X
     {
         u32 ls = padded_log_size(staged.memory.n_real);
+        B::component_scope_index(scope_index++);
         B::lane(ls);
         std::vector<Col> inputs = Impl::unpack_rows(staged.memory.words, staged.memory.n_real, 8, ls);
         MemoryEval eval;
@@ -439,6 +481,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     }
     {
         u32 ls = padded_log_size(staged.merkle.n_real);
+        B::component_scope_index(scope_index++);
         B::lane(ls);
         std::vector<Col> inputs = Impl::unpack_rows(staged.merkle.words, staged.merkle.n_real, 9, ls);
         MerkleEval eval;
@@ -448,6 +491,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     }
     {
         u32 ls = padded_log_size(staged.clock_update.n_real);
+        B::component_scope_index(scope_index++);
         B::lane(ls);
         std::vector<Col> inputs = Impl::unpack_rows(staged.clock_update.words, staged.clock_update.n_real, 6, ls);
         ClockUpdateEval eval;
@@ -457,6 +501,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     }
     {
         u32 ls = padded_log_size(staged.poseidon2.n_real);
+        B::component_scope_index(scope_index++);
         B::lane(ls);
         std::vector<Col> inputs = Impl::unpack_rows(staged.poseidon2.words, staged.poseidon2.n_real, POSEIDON2_T, ls);
         Poseidon2Eval eval;
@@ -464,6 +509,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         log_sizes.push_back(ls);
         traces.push_back(Impl::template write_trace<Poseidon2Eval>(eval, inputs, (u32)staged.poseidon2.n_real));
     }
+    B::component_scope(-1);
     B::lanes_join();
     // range-check multiplicities: histogram of every value the opcode components look up
     // (opcodes/mod.rs:83-105 providers; range_check_macro.rs:72-84).  The AIR graphs drive it.
@@ -485,6 +531,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
                 if (ci < n_opcode_components()) {  // opcode components only
                     std::vector<const Col*> tc;
                     for (auto& e : traces[ci]) tc.push_back(&e.values);
+                    B::component_scope_index(ci);  // sharded proof: the owner counts its component's lookups
                     B::lane(log_sizes[ci]);
                     Impl::emit_lookups(comp, tb.first, tc, bins);
                 }
@@ -492,7 +539,9 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
             };
             shape.for_each(emit);
         }
+        B::component_scope(-1);
         B::lanes_join();
+        for (auto& bins : all_bins) B::allreduce_bins(bins);  // sharded proof: multiplicities are sums over the ranks' components
         for (size_t ti = 0; ti < tables.size(); ti++) {
             auto& tb = tables[ti];
             log_sizes.push_back(tb.second);
@@ -537,11 +586,13 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         components.for_each([&](auto& comp) {
             std::vector<const Col*> tc;
             for (auto& e : traces[ci]) tc.push_back(&e.values);
+            B::component_scope_index(ci);  // sharded proof: the owner generates this component's logup columns
             B::lane(comp.log_size());
             auto cols = comp.gen_interaction_trace(tc, pre_lookup);
             for (auto& e : cols) interaction.push_back(std::move(e));
             ci++;
         });
+        B::component_scope(-1);
         B::lanes_join();
         Impl::collect_claimed_sums(components);
         components.for_each([&](auto& comp) { proof.interaction_claim.claimed_sums.push_back(comp.claimed_sum); });

@@ -13,6 +13,9 @@ namespace cm31 {
 
 void set_error(const std::string& msg);
 cudaStream_t stream();
+// shard.cu: while a sharded proof is being made cm31_malloc bump-allocates from the peer-mapped arena
+bool shard_arena_alloc(void** out, size_t bytes, int* status);
+bool shard_arena_owns(const void* p);
 
 #define CM_CUDA(expr)                                                                          \
     do {                                                                                       \

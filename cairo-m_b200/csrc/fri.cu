@@ -185,11 +185,12 @@ constexpr u32 QUOT_TILE = 256;  // (batch, column) terms staged in shared memory
 __global__ void __launch_bounds__(256) quotients_fast_kernel(u32 log_size, const QuotEntry* __restrict__ entries,
                                                              const QuotBatch* __restrict__ batches, u32 n_batches,
                                                              const CirclePointM31* __restrict__ q_blk,
-                                                             const __grid_constant__ QuotPointTable table, Ptr4 out) {
+                                                             const __grid_constant__ QuotPointTable table, Ptr4 out, u32 blk0) {
     __shared__ uint4 sh_entries[QUOT_TILE * 2];
     const u32 t = threadIdx.x;
-    const size_t row = blockIdx.x * (size_t)256 + t;
-    CirclePointM31 p = cp_add(q_blk[blockIdx.x], table.r[t >> 1]);
+    const u32 blk = blockIdx.x + blk0;  // blk0: first 256-row block of this launch (a rank's row range when a proof is sharded)
+    const size_t row = blk * (size_t)256 + t;
+    CirclePointM31 p = cp_add(q_blk[blk], table.r[t >> 1]);
     if (t & 1) p.y = m31_neg(p.y);
     QM31 acc = qm_zero();
     for (u32 b = 0; b < n_batches; b++) {
@@ -381,7 +382,18 @@ int cm31_accumulate_quotients(uint32_t log_size, const uint32_t* const* cols, si
                               const uint32_t random_coeff[4], size_t n_batches, const uint32_t* batch_points_host,
                               const uint32_t* batch_start_host, const uint32_t* col_idx_host,
                               const uint32_t* values_host, uint32_t* const out4[4]) {
+    return cm31_accumulate_quotients_range(log_size, cols, n_cols, random_coeff, n_batches, batch_points_host, batch_start_host, col_idx_host,
+                                           values_host, out4, 0, (size_t)1 << log_size);
+}
+
+int cm31_accumulate_quotients_range(uint32_t log_size, const uint32_t* const* cols, size_t n_cols,
+                                    const uint32_t random_coeff[4], size_t n_batches, const uint32_t* batch_points_host,
+                                    const uint32_t* batch_start_host, const uint32_t* col_idx_host,
+                                    const uint32_t* values_host, uint32_t* const out4[4], size_t first_row, size_t n_rows) {
     CM_REQUIRE(log_size >= 1 && log_size <= 30, "accumulate_quotients: bad log_size");
+    const bool whole = first_row == 0 && n_rows == ((size_t)1 << log_size);
+    CM_REQUIRE(whole || (log_size >= 9 && first_row % 256 == 0 && n_rows % 256 == 0 && first_row + n_rows <= ((size_t)1 << log_size)),
+               "accumulate_quotients: a row range must be made of whole 256-row blocks of a domain of at least 2^9 rows");
     QM31 alpha = qm_from_arr(random_coeff);
     size_t n_entries = batch_start_host[n_batches];
     std::vector<QuotBatch> qb(n_batches);
@@ -446,14 +458,14 @@ int cm31_accumulate_quotients(uint32_t log_size, const uint32_t* const* cols, si
         if (int e = dent.upload(entries.data(), entries.size() * sizeof(QuotEntry))) return e;
         CirclePointM31* dq = nullptr;
         CM_CUDA(cudaMallocAsync(&dq, (n / 256) * sizeof(CirclePointM31), stream()));
-        ProfScope prof("accumulate_quotients", (4ull * n_cols + 16ull) * n, 2);
+        ProfScope prof("accumulate_quotients", (4ull * n_cols + 16ull) * n_rows, 2);
         // per row: every column term c * f(row) is QM31 x M31 + QM31 add (8); per batch: line value (8), acc * alpha^k (31),
         // CM31 denominator + inverse share (~12), numerator x 1/den (QM31 x CM31 = 8 mul + 4 add)
-        prof_ops(n * (8ull * entries.size() + (8 + 31 + 12 + 12) * (uint64_t)n_batches));
+        prof_ops(n_rows * (8ull * entries.size() + (8 + 31 + 12 + 12) * (uint64_t)n_batches));
         quotients_block_points_kernel<<<(unsigned)((n / 256 + 127) / 128), 128, 0, stream()>>>(log_size, half.initial_index, half.step_size,
                                                                                              (const CirclePointM31*)dgen.d, dq);
-        quotients_fast_kernel<<<(unsigned)(n / 256), 256, 0, stream()>>>(log_size, (const QuotEntry*)dent.d, (const QuotBatch*)dqb.d,
-                                                                       (u32)n_batches, dq, table, o);
+        quotients_fast_kernel<<<(unsigned)(n_rows / 256), 256, 0, stream()>>>(log_size, (const QuotEntry*)dent.d, (const QuotBatch*)dqb.d,
+                                                                            (u32)n_batches, dq, table, o, (u32)(first_row / 256));
         CM_LAUNCH_CHECK();
         CM_CUDA(cudaFreeAsync(dq, stream()));
         return 0;

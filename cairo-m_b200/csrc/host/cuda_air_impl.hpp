@@ -98,7 +98,7 @@ struct CudaAirImpl {
         std::vector<Col> cols = Col::many(n_fields, (size_t)1 << log_size);
         std::vector<u32*> p;
         for (auto& c : cols) p.push_back(c.ptr());
-        cm_check(cm31_unpack_rows(rows.ptr(), n_real, n_fields, log_size, p.data()));
+        if (!Shard::get().skip()) cm_check(cm31_unpack_rows(rows.ptr(), n_real, n_fields, log_size, p.data()));
         return cols;
     }
     template <class Eval>
@@ -118,7 +118,8 @@ struct CudaAirImpl {
         if (pu.active) {  // an opcode component: its inputs are unpacked here, only as wide as the program reads
             if (inputs.empty() || pu.out.empty() || inputs[0].ptr() != pu.out[0]) throw std::logic_error("write_trace: pending unpack belongs to other inputs");
             pu.active = false;
-            cm_check(cm31_unpack_bundles_slots(pu.rows, pu.n_real, pu.log_size, pu.accesses, pu.n_accesses, pu.out.data(), access_slots_read(prog)));
+            if (!Shard::get().skip())
+                cm_check(cm31_unpack_bundles_slots(pu.rows, pu.n_real, pu.log_size, pu.accesses, pu.n_accesses, pu.out.data(), access_slots_read(prog)));
         }
         std::vector<CircleEvaluation<B>> out(Eval::N_TRACE_COLUMNS);
         std::vector<Col> slab = Col::many(Eval::N_TRACE_COLUMNS, (size_t)1 << eval.log_size());

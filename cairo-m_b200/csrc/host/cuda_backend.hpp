@@ -3,9 +3,13 @@
 // `cm31_*` entry points, exactly what the shim's trait impls would bind
 // (Backend: external/stwo/crates/prover/src/core/backend/mod.rs:19-65).
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
+#include <unordered_set>
 
 #include "../../../include/cm31.h"
 #include "air_expr.hpp"
@@ -20,11 +24,62 @@ inline void cm_check(int status) {
     if (status != 0) throw CudaError(std::string("libcm31: ") + cm31_last_error());
 }
 
+// Single-proof sharding (csrc/shard.cu): host-side view.  Every rank runs the same driver; a column is either
+// replicated (owner -1: every rank computes and holds it) or owned by one rank (the others hold an untouched buffer at
+// the same arena offset and read the owner's copy through the peer mapping).  `scope_owner` is the owner of the component
+// whose per-component work (trace fill, lookups, logup columns, constraint evaluation) is being issued: columns allocated
+// inside the scope are tagged with it, and on the other ranks the kernel launches of that scope are skipped.
+struct Shard {
+    bool on = false;
+    int rank = 0, world = 1;
+    int scope_owner = -1;
+    std::unordered_map<const u32*, int> owner;   // column base pointer -> owning rank (absent = replicated)
+    std::unordered_set<const u32*> striped;      // hash layers of which every rank holds only its node range
+    std::vector<int> component_owner;            // by component index (claim order)
+    static Shard& get() {
+        static Shard s;
+        return s;
+    }
+    bool skip() const { return on && scope_owner >= 0 && scope_owner != rank; }
+    int owner_of(const u32* p) const {
+        if (!on) return -1;
+        auto it = owner.find(p);
+        return it == owner.end() ? -1 : it->second;
+    }
+    bool mine(const u32* p) const {
+        int o = owner_of(p);
+        return o < 0 || o == rank;
+    }
+    void tag(const u32* p, int o) {
+        if (!on) return;
+        if (o < 0) owner.erase(p);
+        else owner[p] = o;
+    }
+    void on_alloc(const u32* p) {
+        if (on && scope_owner >= 0) owner[p] = scope_owner;
+    }
+    const u32* peer(const u32* p, int r) const {
+        if (!on || r < 0 || r == rank) return p;
+        const void* q = nullptr;
+        if (cm31_shard_peer(p, r, &q) != 0) throw std::runtime_error(std::string("libcm31: ") + cm31_last_error());
+        return (const u32*)q;
+    }
+    const u32* resolve(const u32* p) const { return on ? peer(p, owner_of(p)) : p; }
+    u32 stripe_log() const {  // layers / domains of at least 2^stripe_log rows are split into per-rank row ranges
+        u32 l = 10;
+        for (int w = world; w > 1; w >>= 1) l++;
+        return l;
+    }
+};
+
 // Owning device column (the reference `BaseColumn`, simd/column.rs:26-30).
 class DeviceCol {
    public:
     DeviceCol() {}
-    explicit DeviceCol(size_t n) : n_(n) { cm_check(cm31_malloc((void**)&p_, n * 4)); }
+    explicit DeviceCol(size_t n) : n_(n) {
+        cm_check(cm31_malloc((void**)&p_, n * 4));
+        Shard::get().on_alloc(p_);
+    }
     DeviceCol(DeviceCol&& o) noexcept : p_(o.p_), n_(o.n_), slab_(std::move(o.slab_)) {
         o.p_ = nullptr;
         o.n_ = 0;
@@ -60,6 +115,7 @@ class DeviceCol {
             out[i].p_ = base + i * stride;
             out[i].n_ = n;
             out[i].slab_ = slab;
+            Shard::get().on_alloc(out[i].p_);
         }
         return out;
     }
@@ -92,9 +148,116 @@ struct CudaBackend {
 
     // components / size groups of at most 2^LANE_SPLIT_LOG rows are issued on the side lane (cm31_lane)
     static constexpr u32 LANE_SPLIT_LOG = 12;
-    static void lane(u32 log_size) { cm_check(cm31_lane(log_size <= LANE_SPLIT_LOG ? 1 : 0)); }
+    static void lane(u32 log_size) {
+        if (Shard::get().on) return;  // a sharded proof keeps one stream: its NCCL calls must be issued in one order on every rank
+        cm_check(cm31_lane(log_size <= LANE_SPLIT_LOG ? 1 : 0));
+    }
     static void lanes_join() { cm_check(cm31_lanes_join()); }
     static size_t len(const Col& c) { return c.size(); }
+    // ---- single-proof sharding hooks (no-ops when sharding is off)
+    static int shard_world() { return Shard::get().on ? Shard::get().world : 1; }
+    static int shard_rank() { return Shard::get().rank; }
+    static u32 shard_stripe_log() { return Shard::get().stripe_log(); }
+    static void shard_begin_proof() {
+        Shard& sh = Shard::get();
+        int rank = 0, world = 0;
+        cm_check(cm31_shard_info(&rank, &world, nullptr));
+        sh.on = world > 0;
+        sh.rank = rank;
+        sh.world = world > 0 ? world : 1;
+        sh.scope_owner = -1;
+        sh.owner.clear();
+        sh.striped.clear();
+        sh.component_owner.clear();
+        if (!sh.on) return;
+        cm_check(cm31_shard_arena_reset());  // also switches cm31_malloc to the arena until shard_end_proof
+        sums().buf = DeviceCol(4 * 256);  // the persistent claimed-sum buffer lived in the arena that was just reset
+        sums().used = 0;
+        sums().owned.clear();
+    }
+    static void shard_end_proof() {
+        Shard& sh = Shard::get();
+        if (!sh.on) return;
+        sh.scope_owner = -1;
+        cm31_shard_arena_suspend();  // buffers allocated between proofs (staged inputs) come from the ordinary pool
+    }
+    static void component_scope(int owner) { Shard::get().scope_owner = Shard::get().on ? owner : -1; }
+    static void component_scope_index(size_t component) {
+        Shard& sh = Shard::get();
+        sh.scope_owner = sh.on && component < sh.component_owner.size() ? sh.component_owner[component] : -1;
+    }
+    static void set_component_owners(const std::vector<int>& owners) { Shard::get().component_owner = owners; }
+    static void set_owner(const Col& c, int owner) { Shard::get().tag(c.ptr(), owner); }
+    static void shard_barrier() {
+        if (Shard::get().on && Shard::get().world > 1) cm_check(cm31_shard_barrier());
+    }
+    static void debug_checksum(const char* what, const Col& c) {
+        if (!getenv("CM31_SHARD_DEBUG")) return;
+        std::vector<u32> h(c.size());
+        cm_check(cm31_d2h(h.data(), c.ptr(), c.size() * 4));
+        cm_check(cm31_sync());
+        u64 sum = 0, mix = 0;
+        for (size_t i = 0; i < h.size(); i++) sum += h[i], mix = mix * 1000003u + h[i];
+        fprintf(stderr, "[shard debug rank %d] %s: n=%zu sum=%llu mix=%016llx ptr_off=%p\n", Shard::get().rank, what, h.size(), (unsigned long long)sum,
+                (unsigned long long)mix, (void*)c.ptr());
+    }
+    static void allreduce_bins(Col& bins) {
+        debug_checksum("bins before allreduce", bins);
+        if (Shard::get().on) cm_check(cm31_shard_allreduce_u32(bins.ptr(), bins.size()));
+        debug_checksum("bins after allreduce", bins);
+    }
+    // values: one entry per item, valid on the rank that computed it; keep[i] = this rank contributes entry i
+    static void exchange_qm31(std::vector<QM31>& values, const std::vector<char>& keep) {
+        Shard& sh = Shard::get();
+        if (!sh.on || sh.world == 1) return;
+        std::vector<u32> w(4 * values.size() + 4, 0);
+        for (size_t i = 0; i < values.size(); i++)
+            if (keep[i]) {
+                w[4 * i] = values[i].a, w[4 * i + 1] = values[i].b, w[4 * i + 2] = values[i].c, w[4 * i + 3] = values[i].d;
+            }
+        cm_check(cm31_shard_allreduce_host_u32(w.data(), 4 * values.size()));
+        for (size_t i = 0; i < values.size(); i++) values[i] = qm_make(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    }
+    // mod-P sum over ranks of an accumulator (4 coordinate columns): returns the reduced copy, complete on every rank
+    static void allreduce_m31(std::array<Col, 4>& acc) {
+        Shard& sh = Shard::get();
+        if (!sh.on || sh.world == 1) return;
+        std::array<Col, 4> out;
+        u32* d4[4];
+        const u32* s4[4];
+        for (int k = 0; k < 4; k++) {
+            out[k] = Col(acc[k].size());
+            sh.tag(out[k].ptr(), -1);
+            d4[k] = out[k].ptr();
+            s4[k] = acc[k].ptr();
+        }
+        cm_check(cm31_shard_reduce_m31(d4, s4, acc[0].size()));
+        for (int k = 0; k < 4; k++) acc[k] = std::move(out[k]);
+    }
+    // hash layer of which this rank holds nodes [rank * n / world, (rank + 1) * n / world)
+    static HashCol commit_on_layer_striped(u32 log_size, const HashCol* prev, const std::vector<const Col*>& cols) {
+        Shard& sh = Shard::get();
+        HashCol out(((size_t)1 << log_size) * 8);
+        sh.tag(out.ptr(), -1);
+        auto s = cptrs(cols);
+        const size_t count = ((size_t)1 << log_size) / (size_t)sh.world, first = count * (size_t)sh.rank;
+        cm_check(cm31_blake2s_commit_layer_range(log_size, prev ? prev->ptr() : nullptr, s.data(), s.size(), out.ptr(), first, count));
+        sh.striped.insert(out.ptr());
+        return out;
+    }
+    // the last striped layer becomes complete on every rank (the all-gather at the Merkle root of the north star)
+    static void join_striped_layer(HashCol& layer) {
+        Shard& sh = Shard::get();
+        cm_check(cm31_shard_allgather(layer.ptr(), layer.size() * 4 / (size_t)sh.world));
+        sh.striped.erase(layer.ptr());
+    }
+    // where node `node` of a hash layer can be read from: the owner's copy for a striped layer
+    static const u32* hash_node_source(const HashCol& layer, size_t node) {
+        Shard& sh = Shard::get();
+        if (!sh.on || !sh.striped.count(layer.ptr())) return layer.ptr();
+        const size_t per = (layer.size() / 8) / (size_t)sh.world;
+        return sh.peer(layer.ptr(), (int)(node / per));
+    }
     static Col zeros(size_t n) {
         Col c(n);
         cm_check(cm31_memset0(c.ptr(), n * 4));
@@ -112,9 +275,10 @@ struct CudaBackend {
         cm_check(cm31_twiddles_create(log_size, &out.h));
         out.log_size = log_size;
     }
-    static std::vector<const u32*> cptrs(const std::vector<const Col*>& cols) {
+    static std::vector<const u32*> cptrs(const std::vector<const Col*>& cols) {  // columns another rank owns: its copy
         std::vector<const u32*> p;
-        for (auto* c : cols) p.push_back(c->ptr());
+        const Shard& sh = Shard::get();
+        for (auto* c : cols) p.push_back(sh.resolve(c->ptr()));
         return p;
     }
     static std::vector<u32*> ptrs(const std::vector<Col*>& cols) {
@@ -122,31 +286,67 @@ struct CudaBackend {
         for (auto* c : cols) p.push_back(c->ptr());
         return p;
     }
+    // Column-wise transforms: a rank only transforms the columns it owns (and the replicated ones); outputs inherit the owner.
     static void interpolate_columns(const std::vector<Col*>& cols, u32 log_size, const Twiddles& tw) {
-        auto p = ptrs(cols);
-        cm_check(cm31_interpolate_batch(p.data(), p.size(), log_size, tw.h));
+        const Shard& sh = Shard::get();
+        std::vector<u32*> p;
+        for (auto* c : cols)
+            if (sh.mine(c->ptr())) p.push_back(c->ptr());
+        if (!p.empty()) cm_check(cm31_interpolate_batch(p.data(), p.size(), log_size, tw.h));
     }
     static void interpolate_columns_to(const std::vector<const Col*>& evals, const std::vector<Col*>& outs, u32 log_size, const Twiddles& tw) {
-        auto s = cptrs(evals);
-        auto d = ptrs(outs);
-        cm_check(cm31_interpolate_batch_to(s.data(), d.data(), s.size(), log_size, tw.h));
+        Shard& sh = Shard::get();
+        std::vector<const u32*> s;
+        std::vector<u32*> d;
+        for (size_t i = 0; i < evals.size(); i++) {
+            sh.tag(outs[i]->ptr(), sh.owner_of(evals[i]->ptr()));
+            if (!sh.mine(evals[i]->ptr())) continue;
+            s.push_back(evals[i]->ptr());
+            d.push_back(outs[i]->ptr());
+        }
+        if (!s.empty()) cm_check(cm31_interpolate_batch_to(s.data(), d.data(), s.size(), log_size, tw.h));
     }
     static void evaluate_polynomials(const std::vector<const Col*>& polys, const std::vector<Col*>& outs, u32 log_size, u32 log_eval,
                                      const Twiddles& tw) {
-        auto s = cptrs(polys);
-        auto d = ptrs(outs);
-        cm_check(cm31_evaluate_batch(s.data(), d.data(), s.size(), log_size, log_eval, tw.h));
+        Shard& sh = Shard::get();
+        std::vector<const u32*> s;
+        std::vector<u32*> d;
+        for (size_t i = 0; i < polys.size(); i++) {
+            sh.tag(outs[i]->ptr(), sh.owner_of(polys[i]->ptr()));
+            if (!sh.mine(polys[i]->ptr())) continue;
+            s.push_back(polys[i]->ptr());
+            d.push_back(outs[i]->ptr());
+        }
+        if (!s.empty()) cm_check(cm31_evaluate_batch(s.data(), d.data(), s.size(), log_size, log_eval, tw.h));
     }
     static void eval_at_points(const std::vector<const Col*>& polys, const std::vector<u32>& log_sizes, const std::vector<SecurePoint>& points,
                                const std::vector<u32>& point_idx, std::vector<QM31>& out) {
-        auto s = cptrs(polys);
+        const Shard& sh = Shard::get();
         std::vector<u32> pts;
         for (auto& p : points)
             for (u32 w : {p.x.a, p.x.b, p.x.c, p.x.d, p.y.a, p.y.b, p.y.c, p.y.d}) pts.push_back(w);
-        std::vector<u32> res(4 * polys.size());
-        cm_check(cm31_eval_at_point_batch(s.data(), log_sizes.data(), s.size(), pts.data(), points.size(), point_idx.data(), res.data()));
-        out.resize(polys.size());
-        for (size_t i = 0; i < polys.size(); i++) out[i] = qm_make(res[4 * i], res[4 * i + 1], res[4 * i + 2], res[4 * i + 3]);
+        // a rank evaluates the polynomials it owns; replicated ones are spread round-robin; the values are then exchanged
+        std::vector<size_t> sel;
+        std::vector<char> keep(polys.size(), 0);
+        for (size_t i = 0; i < polys.size(); i++) {
+            int o = sh.owner_of(polys[i]->ptr());
+            if (!sh.on || o == sh.rank || (o < 0 && (int)(i % (size_t)sh.world) == sh.rank)) {
+                sel.push_back(i);
+                keep[i] = 1;
+            }
+        }
+        std::vector<const u32*> s;
+        std::vector<u32> ls, pi;
+        for (size_t i : sel) {
+            s.push_back(polys[i]->ptr());
+            ls.push_back(log_sizes[i]);
+            pi.push_back(point_idx[i]);
+        }
+        std::vector<u32> res(4 * sel.size() + 4);
+        if (!sel.empty()) cm_check(cm31_eval_at_point_batch(s.data(), ls.data(), s.size(), pts.data(), points.size(), pi.data(), res.data()));
+        out.assign(polys.size(), qm_make(0, 0, 0, 0));
+        for (size_t k = 0; k < sel.size(); k++) out[sel[k]] = qm_make(res[4 * k], res[4 * k + 1], res[4 * k + 2], res[4 * k + 3]);
+        exchange_qm31(out, keep);
     }
     static HashCol commit_on_layer(u32 log_size, const HashCol* prev, const std::vector<const Col*>& cols) {
         HashCol out(((size_t)1 << log_size) * 8);
@@ -183,13 +383,28 @@ struct CudaBackend {
             out.emplace_back(((size_t)1 << l) * 8);
             outp.push_back(out.back().ptr());
             start.push_back((u32)cols.size());
-            for (auto* c : cols_by_layer[l]) cols.push_back(c->ptr());
+            for (auto* c : cols_by_layer[l]) cols.push_back(Shard::get().resolve(c->ptr()));  // the owner's copy
         }
         start.push_back((u32)cols.size());
+        if (getenv("CM31_SHARD_DEBUG")) {  // what this rank sees through the (possibly peer) pointers
+            u64 mix = 0;
+            size_t n_peer = 0;
+            for (u32 l = 0; l <= top_log; l++)
+                for (auto* c : cols_by_layer[l]) {
+                    const u32* q = Shard::get().resolve(c->ptr());
+                    n_peer += q != c->ptr();
+                    std::vector<u32> h(c->size());
+                    cm_check(cm31_d2h(h.data(), q, h.size() * 4));
+                    cm_check(cm31_sync());
+                    for (u32 w : h) mix = mix * 1000003u + w;
+                }
+            fprintf(stderr, "[shard debug rank %d] commit_top top_log=%u cols=%zu peer=%zu mix=%016llx\n", Shard::get().rank, top_log, cols.size(), n_peer,
+                    (unsigned long long)mix);
+        }
         cm_check(cm31_blake2s_commit_top(top_log, prev ? prev->ptr() : nullptr, cols.data(), start.data(), outp.data()));
         return out;
     }
-    static const u32* col_words(const Col& c) { return c.ptr(); }
+    static const u32* col_words(const Col& c) { return Shard::get().resolve(c.ptr()); }  // decommitment reads go to the owner's copy
     static const u32* hash_words(const HashCol& c) { return c.ptr(); }
     static void gather_runs(const std::vector<const u32*>& srcs, const std::vector<u32>& src_id, const std::vector<u32>& word,
                             const std::vector<u32>& out_off, const std::vector<u32>& cnt, const std::vector<u32>& grid_desc,
@@ -201,6 +416,10 @@ struct CudaBackend {
     static Hash32 read_root(const HashCol& root_layer) {
         Hash32 h;
         cm_check(cm31_d2h(h.b, root_layer.ptr(), 32));
+        if (getenv("CM31_SHARD_DEBUG")) {
+            cm_check(cm31_sync());
+            fprintf(stderr, "[shard debug rank %d] root %02x%02x%02x%02x at %p\n", Shard::get().rank, h.b[0], h.b[1], h.b[2], h.b[3], (void*)root_layer.ptr());
+        }
         return h;
     }
     static void gather_hashes(const HashCol& layer, const std::vector<u32>& idx, std::vector<Hash32>& out) {
@@ -226,7 +445,19 @@ struct CudaBackend {
         }
         auto s = cptrs(cols);
         u32 rc[4] = {random_coeff.a, random_coeff.b, random_coeff.c, random_coeff.d};
-        cm_check(cm31_accumulate_quotients(log_size, s.data(), s.size(), rc, batches.size(), pts.data(), starts.data(), idx.data(), vals.data(), o4));
+        const Shard& sh = Shard::get();
+        if (sh.on && sh.world > 1 && log_size >= sh.stripe_log()) {
+            // every rank accumulates ITS row range (remote columns are read through the peer mapping), then the four
+            // coordinate columns are completed with one grouped in-place all-gather
+            const size_t count = ((size_t)1 << log_size) / (size_t)sh.world, first = count * (size_t)sh.rank;
+            cm_check(cm31_accumulate_quotients_range(log_size, s.data(), s.size(), rc, batches.size(), pts.data(), starts.data(), idx.data(),
+                                                     vals.data(), o4, first, count));
+            void* bufs[4] = {o4[0], o4[1], o4[2], o4[3]};
+            size_t per[4] = {4 * count, 4 * count, 4 * count, 4 * count};
+            cm_check(cm31_shard_allgather_many(bufs, per, 4));
+        } else {
+            cm_check(cm31_accumulate_quotients(log_size, s.data(), s.size(), rc, batches.size(), pts.data(), starts.data(), idx.data(), vals.data(), o4));
+        }
         return out;
     }
     static std::array<Col, 4> fold_line(const std::array<Col, 4>& src, u32 log_size, QM31 alpha, const Twiddles& tw) {
@@ -276,12 +507,14 @@ struct CudaBackend {
     }
     static void constraint_eval(const std::vector<const Col*>& cols, u32 trace_log, u32 eval_log, const AirProgram& prog,
                                 const std::vector<u32>& denom_inv, std::array<Col, 4>& acc) {
+        if (Shard::get().skip()) return;  // another rank owns this component
         auto s = cptrs(cols);
         u32* a4[4] = {acc[0].ptr(), acc[1].ptr(), acc[2].ptr(), acc[3].ptr()};
         cm_check(cm31_constraint_eval(s.data(), s.size(), trace_log, eval_log, prog.code.data(), prog.code.size(), prog.n_regs,
                                       prog.consts.data(), prog.consts.size(), denom_inv.data(), a4));
     }
     static void air_program(const std::vector<const Col*>& in, const std::vector<Col*>& out, u32 log_size, const AirProgram& prog) {
+        if (Shard::get().skip()) return;
         auto s = cptrs(in);
         auto d = ptrs(out);
         cm_check(cm31_air_program(s.data(), s.size(), d.data(), d.size(), log_size, prog.code.data(), prog.code.size(), prog.n_regs,
@@ -289,6 +522,7 @@ struct CudaBackend {
     }
     // multiplicity histogram: `bins` is the whole bin column, so its length bounds every looked-up value
     static void air_lookups(const std::vector<const Col*>& in, Col& bins, u32 log_size, const AirProgram& prog) {
+        if (Shard::get().skip()) return;  // the owner counts this component's lookups; the bins are summed over ranks afterwards
         auto s = cptrs(in);
         u32 log_bins = 0;
         while (((size_t)1 << log_bins) < bins.size()) log_bins++;
@@ -302,6 +536,7 @@ struct CudaBackend {
     struct SumArena {
         DeviceCol buf;
         size_t used = 0;
+        std::vector<char> owned;  // per pending slot: this rank computed it (single-proof sharding)
     };
     static SumArena& sums() {
         static SumArena a;
@@ -316,7 +551,8 @@ struct CudaBackend {
         if (a.buf.size() == 0) a.buf = DeviceCol(4 * 256);
         if (a.used >= 256) throw CudaError("too many pending claimed sums");
         u32* l4[4] = {last[0]->ptr(), last[1]->ptr(), last[2]->ptr(), last[3]->ptr()};
-        cm_check(cm31_logup_finalize_last_async(l4, log_size, a.buf.ptr() + 4 * a.used));
+        a.owned.push_back(Shard::get().skip() ? 0 : 1);
+        if (a.owned.back()) cm_check(cm31_logup_finalize_last_async(l4, log_size, a.buf.ptr() + 4 * a.used));
         return a.used++;
     }
     static std::vector<QM31> collect_sums() {
@@ -325,10 +561,13 @@ struct CudaBackend {
         if (a.used) cm_check(cm31_d2h(h.data(), a.buf.ptr(), a.used * 16));
         std::vector<QM31> out;
         for (size_t i = 0; i < a.used; i++) out.push_back(qm_make(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]));
+        exchange_qm31(out, a.owned);  // sharded: every claimed sum was computed by the rank that owns the component
         a.used = 0;
+        a.owned.clear();
         return out;
     }
     static QM31 logup_finalize_last(const std::array<Col*, 4>& last, u32 log_size) {
+        if (Shard::get().on) throw CudaError("logup_finalize_last: the synchronous form is not used by the sharded prover");
         u32* l4[4] = {last[0]->ptr(), last[1]->ptr(), last[2]->ptr(), last[3]->ptr()};
         u32 cs[4];
         cm_check(cm31_logup_finalize_last(l4, log_size, cs));

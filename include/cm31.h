@@ -95,6 +95,41 @@ int cm31_ipc_free(void* dptr);
 int cm31_ipc_open(const uint8_t handle[64], void** out);
 int cm31_ipc_close(void* dptr);
 
+/* ------------------------------------------------------------------ single-proof sharding
+ * One process per GPU, every rank runs the same protocol driver and owns a subset of the components; see csrc/shard.cu.
+ * While sharding is on, cm31_malloc bump-allocates from a per-rank arena that every peer has mapped (cudaIpc): the same
+ * allocation sequence on every rank puts a buffer at the same offset everywhere, so cm31_shard_peer translates any arena
+ * pointer into rank `owner`'s copy and kernels read remote columns over NVLink/NVSwitch directly.  Collectives are NCCL
+ * (all stream-ordered on the current lane): barrier, in-place all-gather(s), u32 sum.  cm31_shard_reduce_m31 is the mod-P
+ * all-reduce of the four composition accumulator columns (S/prover/src/core/air/accumulation.rs:49-58) as reduce-scatter
+ * by peer loads + all-gather.  Rank 0 creates the 128-byte NCCL id (cm31_shard_unique_id) and hands it to the others
+ * (torch.distributed broadcast in bench.py). */
+int cm31_shard_unique_id(uint8_t out[128]);
+int cm31_shard_init(int rank, int world, const uint8_t unique_id[128], size_t arena_bytes);
+int cm31_shard_finalize(void);
+/* world = 0 when sharding is off; stats: arena high-water mark, bytes received by all-gathers, bytes all-reduced, collectives */
+int cm31_shard_info(int* rank, int* world, uint64_t stats[4]);
+int cm31_shard_barrier(void);
+int cm31_shard_arena_reset(void);   /* new proof: barrier, arena back to offset 0, cm31_malloc draws from it */
+int cm31_shard_arena_suspend(void); /* end of proof: cm31_malloc goes back to the ordinary pool (the arena keeps its contents) */
+int cm31_shard_allgather(void* buf, size_t bytes_per_rank);
+int cm31_shard_allgather_many(void* const* bufs, const size_t* bytes_per_rank, size_t n);
+int cm31_shard_allreduce_u32(uint32_t* buf, size_t n);
+int cm31_shard_allreduce_host_u32(uint32_t* host, size_t n);
+int cm31_shard_peer(const void* p, int owner, const void** out);
+int cm31_shard_reduce_m31(uint32_t* const dst4[4], const uint32_t* const src4[4], size_t n);
+/* the component -> rank assignment every rank computes for itself (longest-processing-time first over per-component costs,
+ * claim order); host only */
+int cm31_shard_plan(const double* cost, size_t n_components, int world, int* owners_out);
+/* MerkleOps::commit_on_layer restricted to nodes [first_node, first_node + n_nodes) of the layer (a rank's row range;
+ * prev_layer / out_layer are full-size buffers of which only that range is read / written) */
+int cm31_blake2s_commit_layer_range(uint32_t log_size, const uint32_t* prev_layer, const uint32_t* const* cols, size_t n_cols,
+                                    uint32_t* out_layer, size_t first_node, size_t n_nodes);
+/* QuotientOps::accumulate_quotients restricted to rows [first_row, first_row + n_rows) (multiples of 256) */
+int cm31_accumulate_quotients_range(uint32_t log_size, const uint32_t* const* cols, size_t n_cols, const uint32_t random_coeff[4],
+                                    size_t n_batches, const uint32_t* points, const uint32_t* batch_start, const uint32_t* col_idx,
+                                    const uint32_t* values, uint32_t* const out4[4], size_t first_row, size_t n_rows);
+
 /* ------------------------------------------------------------------ PolyOps
  * S/prover/src/core/poly/circle/ops.rs:13-69, CPU definition S/prover/src/core/backend/cpu/circle.rs */
 typedef struct cm31_twiddles cm31_twiddles;

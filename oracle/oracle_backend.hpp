@@ -81,6 +81,22 @@ struct OracleBackend {
         }
         return out;
     }
+    // single-proof sharding is a property of the CUDA data plane: the oracle is always one "rank" holding everything
+    static int shard_world() { return 1; }
+    static int shard_rank() { return 0; }
+    static u32 shard_stripe_log() { return 31; }
+    static void shard_begin_proof() {}
+    static void shard_end_proof() {}
+    static void shard_barrier() {}
+    static void component_scope(int) {}
+    static void component_scope_index(size_t) {}
+    static void set_component_owners(const std::vector<int>&) {}
+    static void set_owner(const Col&, int) {}
+    static void allreduce_m31(std::array<Col, 4>&) {}
+    static void allreduce_bins(Col&) {}
+    static HashCol commit_on_layer_striped(u32 log_size, const HashCol* prev, const std::vector<const Col*>& cols) { return commit_on_layer(log_size, prev, cols); }
+    static void join_striped_layer(HashCol&) {}
+    static const u32* hash_node_source(const HashCol& layer, size_t) { return (const u32*)layer.data(); }
     static void lane(u32) {}  // the CUDA backend's stream lanes have no CPU counterpart
     static void lanes_join() {}
     static void prepare() {}

@@ -15,6 +15,11 @@ lib = cm.lib()
 h = C.c_void_p()
 cm.check(lib.cm31_test_fib_input_create(C.c_uint32(bench.fib_iterations(log)), C.byref(h)))
 cm.check(lib.cm31_input_upload(h))
+import os
+if os.environ.get("CM31_TRACE_SHARDED"):  # the same proof as one share of a (world size 1) sharded proof
+    import torch
+    torch.cuda.set_device(0)
+    cm.shard_init(arena_gib=16)
 cap = 1 << 26
 buf = (C.c_uint8 * cap)()
 ln = C.c_size_t()
