@@ -305,6 +305,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sharded = args.mode == "sharded"
+    if sharded:
+        # ONE proof sharded over all ranks: every rank holds the same input and owns a subset of the components;
+        # strong scaling -- the work per step is one proof whatever the number of GPUs
+        cm.shard_init(arena_gib=args.arena_gib)
     programs = {"fibonacci_loop": 0, "array_sum": 1, "u32_counter": 2, "u32_mix": 3, "sha256": 4}
     n = args.iterations if args.iterations else fib_iterations(args.log_steps)
     if args.program == "sha256" and not args.iterations:
@@ -365,7 +370,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         prove()
     # `value`: K proofs, per-kernel event timers OFF (they cost two event records per launch, ~460 launches per proof)
     ms, clocks, launches, _, phases = timed_region(args.steps, False)
-    value = aggregate_value(world, vm_steps, args.steps, ms)
+    value = aggregate_value(1 if sharded else world, vm_steps, args.steps, ms)
     # second pass over the same K steps with every launch bracketed by CUDA events on its launch stream: the per-kernel table
     # and the roofline come from here; its own ms/step is reported next to the unprofiled one
     prof_ms, _, _, report, _ = timed_region(args.steps, True)
@@ -389,7 +394,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         e2e_rejected = {"ms_per_step": e2e_ms / args.steps, "step_wall_ms": e2e_step_wall}
         e2e_ms, _, _, _, _ = timed_region(args.steps, False, prefetch=True)
         e2e_step_wall = timed_region.last_step_wall
-    e2e_value = aggregate_value(world, vm_steps, args.steps, e2e_ms)
+    e2e_value = aggregate_value(1 if sharded else world, vm_steps, args.steps, e2e_ms)
     proof_bytes = int(proof_len.value)
     cm.check(lib.cm31_input_destroy(h))
 
@@ -397,9 +402,24 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # reference adapter (serial walk, csrc/cairo/vm.hpp) vs the device adapter (csrc/adapter.cu), and whole steps that
     # START from the pinned logs: upload + device adapter + proof + proof bytes back.
     adapter = None
-    if world == 1 and not args.no_adapter:
+    if world == 1 and not args.no_adapter and not sharded:
         adapter = measure_adapter(cm, lib, torch, programs[args.program], n, args.steps, vm_steps, proof_buf, cap, proof_len, tm)
 
+    shard_info = None
+    if sharded:
+        st = cm.shard_stats()
+        per_proof = max(1, 3 * args.steps + args.warmup + 4)  # proofs made since shard_init (warm-up, value, profile, e2e passes)
+        shard_info = {"world": st["world"], "arena_peak_bytes": st["arena_peak_bytes"],
+                      "bytes_all_gathered_per_proof_approx": st["bytes_all_gathered"] // per_proof,
+                      "collectives_per_proof_approx": st["collectives"] // per_proof,
+                      "data_plane": "components dealt out over the ranks (trace fill, lookups, logup, ICFFT/LDE, constraint evaluation local to the "
+                                    "owner); Merkle layers striped by node range with remote LDE columns read over NVLink inside the leaf kernel; "
+                                    "DEEP quotients by row range; FRI replicated",
+                      "collectives": "NCCL all-gather: last striped Merkle layer of every tree (the join at the Merkle root), DEEP quotient rows, "
+                                     "reduced accumulator rows; NCCL all-reduce: barriers, multiplicity bins, claimed sums, OODS values; "
+                                     "mod-P accumulator sum = reduce-scatter by peer loads + all-gather",
+                      "proof_identical_to_single_gpu": "checked by tests/dist/sharded_prover_worker.py (byte-for-byte on every rank)"}
+        cm.check(lib.cm31_shard_finalize())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -454,13 +474,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": "u32 (M31/QM31 modular integer)", "data": "synthetic",
         "config": {"workload": workload_name(args.log_steps) if args.program == "fibonacci_loop" and not args.iterations
                    else (f"sha256({n} compressions of a padded block, examples/sha256-cairo-m style: u32 / bitwise / range-check components) "
                          f"[BASELINE config 3, not the headline workload]" if args.program == "sha256"
                          else f"{args.program}({n}) [side measurement, not the BASELINE workload]"), "vm_steps_per_proof": vm_steps,
-                   "parallelism": "one independent segment proof per GPU" if world > 1 else "single GPU",
+                   "parallelism": (f"ONE proof sharded over {world} GPU(s)" if sharded else
+                                   "one independent segment proof per GPU" if world > 1 else "single GPU"),
                    "l2": "working set per proof (GBs of trace/LDE columns) >> 126 MB L2; no flush between steps",
                    "pcs": {"pow_bits": 16, "log_blowup": 1, "n_queries": 80}},
         "phases_ms": dict(zip(["preprocessed", "trace", "interaction", "stark", "total"], phases)),
@@ -471,6 +492,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "serial_ms_per_step": e2e_serial_ms / args.steps,
                 "serial_value": aggregate_value(world, vm_steps, args.steps, e2e_serial_ms)},
         "adapter": adapter,
+        "sharded": shard_info,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
@@ -487,6 +509,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
+                    help="N > 1: replicas = one independent segment proof per GPU (weak scaling, the default); sharded = ONE proof "
+                         "sharded over the N GPUs (strong scaling; SURVEY.md §8e)")
+    ap.add_argument("--arena-gib", type=float, default=24.0, help="sharded mode: peer-mapped arena per rank")
     ap.add_argument("--log-steps", type=int, default=22, help="log2 of VM steps per proof (BASELINE metric: 2^22)")
     ap.add_argument("--cpu-sample-log", type=int, default=0,
                     help="log2 VM steps of the cpu_baseline proof (default: the workload's own size, one whole proof)")

@@ -20,6 +20,22 @@ P = (1 << 31) - 1
 _lib = None
 
 
+def _preload_nccl() -> None:
+    """libcm31 links NCCL (single-proof sharding, csrc/shard.cu).  torch ships its own, newer libnccl.so.2; whichever copy is
+    loaded first serves both, and torch does not work with the older system copy -- so the wheel's copy goes in first."""
+    import importlib.util
+    import sys
+    if "torch" in sys.modules:
+        return  # torch already loaded its NCCL: libcm31 binds to that copy
+    spec = importlib.util.find_spec("nvidia.nccl")
+    if spec and spec.submodule_search_locations:
+        for base in spec.submodule_search_locations:
+            cand = Path(base) / "lib" / "libnccl.so.2"
+            if cand.exists():
+                ctypes.CDLL(str(cand), mode=ctypes.RTLD_GLOBAL)
+                return
+
+
 def lib() -> ctypes.CDLL:
     """The loaded C-ABI library; raises loudly when the CUDA extension is missing."""
     global _lib
@@ -28,6 +44,7 @@ def lib() -> ctypes.CDLL:
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python cairo-m_b200/build.py` "
                 "(there is no CPU fallback for the product path)")
+        _preload_nccl()
         _lib = ctypes.CDLL(str(LIB_PATH), mode=ctypes.RTLD_GLOBAL)
         _lib.cm31_last_error.restype = C.c_char_p
     return _lib

@@ -390,14 +390,27 @@ int cm31_accumulate_quotients_range(uint32_t log_size, const uint32_t* const* co
                                     const uint32_t random_coeff[4], size_t n_batches, const uint32_t* batch_points_host,
                                     const uint32_t* batch_start_host, const uint32_t* col_idx_host,
                                     const uint32_t* values_host, uint32_t* const out4[4], size_t first_row, size_t n_rows) {
+    return cm31_accumulate_quotients_partial(log_size, cols, n_cols, random_coeff, n_batches, batch_points_host, batch_start_host, col_idx_host,
+                                             values_host, out4, first_row, n_rows, nullptr);
+}
+
+// entry_active (one byte per (batch, column) entry, or NULL = all): the quotient is LINEAR in the per-column terms
+// (c * f(row) - (a * y + b)) / den, so the entries can be split over the ranks of a sharded proof -- every rank accumulates
+// the terms of the columns it owns over all rows, reading only local memory, and the partial quotients are summed mod P
+// (cm31_shard_reduce_m31).  Inactive entries still take their power of the random coefficient.
+int cm31_accumulate_quotients_partial(uint32_t log_size, const uint32_t* const* cols, size_t n_cols,
+                                      const uint32_t random_coeff[4], size_t n_batches, const uint32_t* batch_points_host,
+                                      const uint32_t* batch_start_host, const uint32_t* col_idx_host,
+                                      const uint32_t* values_host, uint32_t* const out4[4], size_t first_row, size_t n_rows,
+                                      const uint8_t* entry_active) {
     CM_REQUIRE(log_size >= 1 && log_size <= 30, "accumulate_quotients: bad log_size");
     const bool whole = first_row == 0 && n_rows == ((size_t)1 << log_size);
     CM_REQUIRE(whole || (log_size >= 9 && first_row % 256 == 0 && n_rows % 256 == 0 && first_row + n_rows <= ((size_t)1 << log_size)),
                "accumulate_quotients: a row range must be made of whole 256-row blocks of a domain of at least 2^9 rows");
     QM31 alpha = qm_from_arr(random_coeff);
-    size_t n_entries = batch_start_host[n_batches];
     std::vector<QuotBatch> qb(n_batches);
-    std::vector<u32> coef_c(n_entries * 4 + 4);
+    std::vector<u32> coef_c, act_idx;  // the ACTIVE entries, compacted: coefficient (4 words) and column index per entry
+    coef_c.reserve((size_t)batch_start_host[n_batches] * 4 + 4);
     for (size_t b = 0; b < n_batches; b++) {
         const u32* pt = batch_points_host + b * 8;
         QM31 px = qm_make(pt[0], pt[1], pt[2], pt[3]), py = qm_make(pt[4], pt[5], pt[6], pt[7]);
@@ -405,27 +418,32 @@ int cm31_accumulate_quotients_range(uint32_t log_size, const uint32_t* const* co
         QuotBatch& q = qb[b];
         q.prx[0] = px.a; q.prx[1] = px.b; q.pix[0] = px.c; q.pix[1] = px.d;
         q.pry[0] = py.a; q.pry[1] = py.b; q.piy[0] = py.c; q.piy[1] = py.d;
-        q.start = batch_start_host[b];
-        q.end = batch_start_host[b + 1];
+        q.start = (u32)act_idx.size();
         // column_line_coeffs (cpu/quotients.rs:84-108) + complex_conjugate_line_coeffs (constraints.rs:98-113)
         QM31 al = qm_one(), sa = qm_zero(), sb = qm_zero();
         QM31 c = qm_sub(qm_conj(py), py);
-        for (u32 k = q.start; k < q.end; k++) {
+        for (u32 k = batch_start_host[b]; k < batch_start_host[b + 1]; k++) {
             CM_REQUIRE(col_idx_host[k] < n_cols, "accumulate_quotients: column index out of range");
-            al = qm_mul(al, alpha);
+            al = qm_mul(al, alpha);  // every entry takes its power, active or not
+            if (entry_active && !entry_active[k]) continue;
             QM31 v = qm_from_arr(values_host + (size_t)k * 4);
             QM31 a = qm_sub(qm_conj(v), v);
             QM31 bq = qm_sub(qm_mul(v, c), qm_mul(a, py));
             sa = qm_add(sa, qm_mul(al, a));
             sb = qm_add(sb, qm_mul(al, bq));
             QM31 ac = qm_mul(al, c);
-            coef_c[k * 4] = ac.a; coef_c[k * 4 + 1] = ac.b; coef_c[k * 4 + 2] = ac.c; coef_c[k * 4 + 3] = ac.d;
+            for (u32 w : {ac.a, ac.b, ac.c, ac.d}) coef_c.push_back(w);
+            act_idx.push_back(col_idx_host[k]);
         }
-        QM31 bc = qm_pow(alpha, q.end - q.start);
+        q.end = (u32)act_idx.size();
+        QM31 bc = qm_pow(alpha, batch_start_host[b + 1] - batch_start_host[b]);
         q.batch_coeff[0] = bc.a; q.batch_coeff[1] = bc.b; q.batch_coeff[2] = bc.c; q.batch_coeff[3] = bc.d;
         q.sum_a[0] = sa.a; q.sum_a[1] = sa.b; q.sum_a[2] = sa.c; q.sum_a[3] = sa.d;
         q.sum_b[0] = sb.a; q.sum_b[1] = sb.b; q.sum_b[2] = sb.c; q.sum_b[3] = sb.d;
     }
+    const size_t n_entries = act_idx.size();
+    const u32* col_idx_act = act_idx.data();
+    for (int k = 0; k < 4; k++) coef_c.push_back(0);
     std::vector<CirclePointM31> gen_pow(31);
     CirclePointM31 g = {M31_CIRCLE_GEN_X, M31_CIRCLE_GEN_Y};
     for (int i = 0; i < 31; i++) {
@@ -435,7 +453,7 @@ int cm31_accumulate_quotients_range(uint32_t log_size, const uint32_t* const* co
     DeviceTable dcols, dqb, didx, dc, dgen;
     if (int e = dcols.upload(cols, n_cols * sizeof(void*))) return e;
     if (int e = dqb.upload(qb.data(), qb.size() * sizeof(QuotBatch))) return e;
-    if (int e = didx.upload(col_idx_host, n_entries * 4)) return e;
+    if (int e = didx.upload(col_idx_act, n_entries * 4)) return e;
     if (int e = dc.upload(coef_c.data(), coef_c.size() * 4)) return e;
     if (int e = dgen.upload(gen_pow.data(), gen_pow.size() * sizeof(CirclePointM31))) return e;
     Ptr4 o;
@@ -445,7 +463,7 @@ int cm31_accumulate_quotients_range(uint32_t log_size, const uint32_t* const* co
     if (log_size >= 9) {
         std::vector<QuotEntry> entries(n_entries + 1);
         for (size_t k = 0; k < n_entries; k++) {
-            entries[k].col = cols[col_idx_host[k]];
+            entries[k].col = cols[col_idx_act[k]];
             entries[k].pad[0] = entries[k].pad[1] = 0;
             for (int j = 0; j < 4; j++) entries[k].c[j] = coef_c[k * 4 + j];
         }

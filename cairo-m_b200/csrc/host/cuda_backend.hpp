@@ -245,6 +245,22 @@ struct CudaBackend {
         sh.striped.insert(out.ptr());
         return out;
     }
+    // several striped layers in one launch (only the first carries columns): this rank's node range and the subtree above it
+    static std::vector<HashCol> commit_layers_fused_striped(u32 log_size, const HashCol* prev, const std::vector<const Col*>& cols, u32 n_levels) {
+        Shard& sh = Shard::get();
+        std::vector<HashCol> out;
+        std::vector<u32*> outp;
+        for (u32 l = 0; l < n_levels; l++) {
+            out.emplace_back(((size_t)1 << (log_size - l)) * 8);
+            sh.tag(out.back().ptr(), -1);
+            sh.striped.insert(out.back().ptr());
+            outp.push_back(out.back().ptr());
+        }
+        auto s = cptrs(cols);
+        const size_t count = ((size_t)1 << log_size) / (size_t)sh.world, first = count * (size_t)sh.rank;
+        cm_check(cm31_blake2s_commit_multi_range(log_size, prev ? prev->ptr() : nullptr, s.data(), s.size(), n_levels, outp.data(), first, count));
+        return out;
+    }
     // the last striped layer becomes complete on every rank (the all-gather at the Merkle root of the north star)
     static void join_striped_layer(HashCol& layer) {
         Shard& sh = Shard::get();
@@ -445,16 +461,30 @@ struct CudaBackend {
         }
         auto s = cptrs(cols);
         u32 rc[4] = {random_coeff.a, random_coeff.b, random_coeff.c, random_coeff.d};
-        const Shard& sh = Shard::get();
-        if (sh.on && sh.world > 1 && log_size >= sh.stripe_log()) {
-            // every rank accumulates ITS row range (remote columns are read through the peer mapping), then the four
-            // coordinate columns are completed with one grouped in-place all-gather
-            const size_t count = ((size_t)1 << log_size) / (size_t)sh.world, first = count * (size_t)sh.rank;
-            cm_check(cm31_accumulate_quotients_range(log_size, s.data(), s.size(), rc, batches.size(), pts.data(), starts.data(), idx.data(),
-                                                     vals.data(), o4, first, count));
-            void* bufs[4] = {o4[0], o4[1], o4[2], o4[3]};
-            size_t per[4] = {4 * count, 4 * count, 4 * count, 4 * count};
-            cm_check(cm31_shard_allgather_many(bufs, per, 4));
+        Shard& sh = Shard::get();
+        if (sh.on && sh.world > 1) {
+            // The quotient is linear in the per-column terms: every rank accumulates the terms of the columns it owns
+            // (replicated columns: round-robin) over ALL rows, from local memory only; the partial quotients are then summed
+            // mod P over the ranks (reduce-scatter by peer loads + all-gather, cm31_shard_reduce_m31).
+            std::vector<uint8_t> active(idx.size(), 0);
+            for (size_t k = 0; k < idx.size(); k++) {
+                int o = sh.owner_of(cols[idx[k]]->ptr());
+                active[k] = (o == sh.rank || (o < 0 && (int)(idx[k] % (u32)sh.world) == sh.rank)) ? 1 : 0;
+            }
+            std::vector<const u32*> local;
+            for (auto* c : cols) local.push_back(c->ptr());  // only active (= locally valid) columns are dereferenced
+            std::array<Col, 4> part;
+            u32* p4[4];
+            const u32* s4[4];
+            for (int k = 0; k < 4; k++) {
+                part[k] = Col((size_t)1 << log_size);
+                sh.tag(part[k].ptr(), -1);
+                p4[k] = part[k].ptr();
+                s4[k] = part[k].ptr();
+            }
+            cm_check(cm31_accumulate_quotients_partial(log_size, local.data(), local.size(), rc, batches.size(), pts.data(), starts.data(), idx.data(),
+                                                       vals.data(), p4, 0, (size_t)1 << log_size, active.data()));
+            cm_check(cm31_shard_reduce_m31(o4, s4, (size_t)1 << log_size));
         } else {
             cm_check(cm31_accumulate_quotients(log_size, s.data(), s.size(), rc, batches.size(), pts.data(), starts.data(), idx.data(), vals.data(), o4));
         }

@@ -367,9 +367,18 @@ struct MerkleProver {
             while (log_size >= stripe && log_size > TOP_LOG) {
                 std::vector<const Col*> layer_cols;
                 while (pos < sorted.size() && ilog2(B::len(*sorted[pos])) == (u32)log_size) layer_cols.push_back(sorted[pos++]);
+                // the column-free layers below are hashed by the same launch, as in the unsharded planner
+                int next_with_cols = pos < sorted.size() ? (int)ilog2(B::len(*sorted[pos])) : -1;
+                int n_levels = 1;
+                while (log_size - n_levels >= stripe && log_size - n_levels > TOP_LOG && log_size - n_levels > next_with_cols && n_levels < 9) n_levels++;
                 const HashCol* prev = layers.empty() ? nullptr : &layers.back();
-                layers.push_back(B::commit_on_layer_striped((u32)log_size, prev, layer_cols));
-                log_size--;
+                if (n_levels == 1) {
+                    layers.push_back(B::commit_on_layer_striped((u32)log_size, prev, layer_cols));
+                } else {
+                    std::vector<HashCol> fused = B::commit_layers_fused_striped((u32)log_size, prev, layer_cols, (u32)n_levels);
+                    for (auto& l : fused) layers.push_back(std::move(l));
+                }
+                log_size -= n_levels;
                 any = true;
             }
             if (any) B::join_striped_layer(layers.back());

@@ -222,14 +222,15 @@ __global__ void __launch_bounds__(1024) merkle_top_kernel(u32 top_log, const u32
 struct MerkleMultiArgs {
     u32* layer_out[9];
 };
+// `first`: first node of the launch's range in the first layer (a multiple of 256; 0 for a whole layer)
 __global__ void __launch_bounds__(256) merkle_multi_kernel(u32 log_size, const u32* prev, const u32* const* cols, u32 n_cols, u32 n_levels,
-                                                           MerkleMultiArgs args) {
-    const size_t i = blockIdx.x * (size_t)256 + threadIdx.x;
+                                                           MerkleMultiArgs args, size_t first) {
+    const size_t i = first + blockIdx.x * (size_t)256 + threadIdx.x;
     if (i < ((size_t)1 << log_size)) hash_node<false>(i, prev, cols, n_cols, args.layer_out[0]);
     for (u32 lvl = 1; lvl < n_levels; lvl++) {
         __syncthreads();  // the children written by this CTA are visible to it
         const u32 cnt = 256u >> lvl;
-        if (threadIdx.x < cnt) hash_node<true>(blockIdx.x * (size_t)cnt + threadIdx.x, args.layer_out[lvl - 1], nullptr, 0, args.layer_out[lvl]);
+        if (threadIdx.x < cnt) hash_node<true>((first >> lvl) + blockIdx.x * (size_t)cnt + threadIdx.x, args.layer_out[lvl - 1], nullptr, 0, args.layer_out[lvl]);
     }
 }
 
@@ -241,10 +242,11 @@ __global__ void __launch_bounds__(256) merkle_multi_kernel(u32 log_size, const u
 // warp ever waits for another, so the schedulers always find an eligible warp among the resident ones.
 template <int PER_LANE>
 __global__ void __launch_bounds__(256) merkle_warp_kernel(u32 log_size, const u32* prev, const u32* const* cols, u32 n_cols, u32 n_levels,
-                                                          MerkleMultiArgs args) {
+                                                          MerkleMultiArgs args, size_t first, size_t count) {
     const u32 lane = threadIdx.x & 31u;
     size_t base = ((blockIdx.x * (size_t)256 + threadIdx.x) >> 5) * (32u * PER_LANE);
-    if (base >= ((size_t)1 << log_size)) return;  // whole warps only: 2^log_size is a multiple of 32 * PER_LANE
+    if (base >= count) return;  // whole warps only: the range is a multiple of 32 * PER_LANE
+    base += first;
 #pragma unroll 1
     for (u32 j = 0; j < (u32)PER_LANE; j++) hash_node<false>(base + j * 32u + lane, prev, cols, n_cols, args.layer_out[0]);
     u32 cnt = 32u * PER_LANE;
@@ -320,35 +322,44 @@ int cm31_blake2s_commit_layer_range(uint32_t log_size, const uint32_t* prev_laye
 
 int cm31_blake2s_commit_multi(uint32_t log_size, const uint32_t* prev_layer, const uint32_t* const* cols, size_t n_cols,
                               uint32_t n_levels, uint32_t* const* out_layers) {
+    return cm31_blake2s_commit_multi_range(log_size, prev_layer, cols, n_cols, n_levels, out_layers, 0, (size_t)1 << log_size);
+}
+
+// nodes [first_node, first_node + n_nodes) of layer log_size and the whole subtree above them in the next n_levels - 1
+// layers (a rank's share of a striped tree; the whole layer for first_node = 0, n_nodes = 2^log_size)
+int cm31_blake2s_commit_multi_range(uint32_t log_size, const uint32_t* prev_layer, const uint32_t* const* cols, size_t n_cols,
+                                    uint32_t n_levels, uint32_t* const* out_layers, size_t first_node, size_t n_nodes) {
     CM_REQUIRE(out_layers != nullptr && n_levels >= 1 && n_levels <= 9, "commit_multi: 1..9 levels");
     CM_REQUIRE(log_size <= 30 && log_size >= 8 && log_size + 1 >= n_levels, "commit_multi: first layer needs at least 256 nodes");
+    CM_REQUIRE(n_nodes >= 256 && (n_nodes & (n_nodes - 1)) == 0 && first_node % n_nodes == 0 && first_node + n_nodes <= ((size_t)1 << log_size),
+               "commit_multi: the node range must be an aligned power of two of at least 256 nodes");
     MerkleMultiArgs args;
     for (u32 l = 0; l < 9; l++) args.layer_out[l] = l < n_levels ? out_layers[l] : nullptr;
     DeviceTable dcols;
     if (n_cols != 0)
         if (int e = dcols.upload(cols, n_cols * sizeof(void*))) return e;
-    size_t n = (size_t)1 << log_size;
+    const size_t n = n_nodes;
     uint64_t bytes = (4ull * n_cols + 32ull + (prev_layer ? 64ull : 0ull)) * n;
     for (u32 l = 1; l < n_levels; l++) bytes += 96ull * (n >> l);
-    if (log_size >= 19 && n_levels >= 2 && !getenv("CM31_MERKLE_CTA_FUSION")) {
+    if (n >= ((size_t)1 << 19) && n_levels >= 2 && !getenv("CM31_MERKLE_CTA_FUSION")) {
         // large layers: barrier-free warp subtrees, 4 (3) levels per launch, the remaining levels by further launches
-        const u32 per_lane = log_size >= 21 ? 8 : 4;
+        const u32 per_lane = n >= ((size_t)1 << 21) ? 8 : 4;
         const u32 lv = std::min<u32>(n_levels, per_lane == 8 ? 4 : 3);
         uint64_t b0 = (4ull * n_cols + 32ull + (prev_layer ? 64ull : 0ull)) * n;
         for (u32 l = 1; l < lv; l++) b0 += 96ull * (n >> l);
         {
             ProfScope prof(n_cols ? "merkle_leaf_layer" : "merkle_inner_layer", b0);
             const unsigned blocks = (unsigned)((n / (32 * per_lane) * 32 + 255) / 256);
-            if (per_lane == 8) merkle_warp_kernel<8><<<blocks, 256, 0, stream()>>>(log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, lv, args);
-            else merkle_warp_kernel<4><<<blocks, 256, 0, stream()>>>(log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, lv, args);
+            if (per_lane == 8) merkle_warp_kernel<8><<<blocks, 256, 0, stream()>>>(log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, lv, args, first_node, n);
+            else merkle_warp_kernel<4><<<blocks, 256, 0, stream()>>>(log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, lv, args, first_node, n);
             CM_LAUNCH_CHECK();
         }
         if (lv == n_levels) return 0;
-        if (n_levels - lv == 1) return cm31_blake2s_commit_layer(log_size - lv, out_layers[lv - 1], nullptr, 0, out_layers[lv]);
-        return cm31_blake2s_commit_multi(log_size - lv, out_layers[lv - 1], nullptr, 0, n_levels - lv, out_layers + lv);
+        if (n_levels - lv == 1) return cm31_blake2s_commit_layer_range(log_size - lv, out_layers[lv - 1], nullptr, 0, out_layers[lv], first_node >> lv, n >> lv);
+        return cm31_blake2s_commit_multi_range(log_size - lv, out_layers[lv - 1], nullptr, 0, n_levels - lv, out_layers + lv, first_node >> lv, n >> lv);
     }
     ProfScope prof(n_cols ? "merkle_leaf_layer" : "merkle_inner_layer", bytes);
-    merkle_multi_kernel<<<(unsigned)(n / 256), 256, 0, stream()>>>(log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, n_levels, args);
+    merkle_multi_kernel<<<(unsigned)(n / 256), 256, 0, stream()>>>(log_size, prev_layer, (const u32* const*)dcols.d, (u32)n_cols, n_levels, args, first_node);
     CM_LAUNCH_CHECK();
     return 0;
 }

@@ -125,10 +125,22 @@ int cm31_shard_plan(const double* cost, size_t n_components, int world, int* own
  * prev_layer / out_layer are full-size buffers of which only that range is read / written) */
 int cm31_blake2s_commit_layer_range(uint32_t log_size, const uint32_t* prev_layer, const uint32_t* const* cols, size_t n_cols,
                                     uint32_t* out_layer, size_t first_node, size_t n_nodes);
+/* the fused form (cm31_blake2s_commit_multi) on an aligned power-of-two node range of at least 256 nodes */
+int cm31_blake2s_commit_multi_range(uint32_t log_size, const uint32_t* prev_layer, const uint32_t* const* cols, size_t n_cols,
+                                    uint32_t n_levels, uint32_t* const* out_layers, size_t first_node, size_t n_nodes);
 /* QuotientOps::accumulate_quotients restricted to rows [first_row, first_row + n_rows) (multiples of 256) */
 int cm31_accumulate_quotients_range(uint32_t log_size, const uint32_t* const* cols, size_t n_cols, const uint32_t random_coeff[4],
                                     size_t n_batches, const uint32_t* points, const uint32_t* batch_start, const uint32_t* col_idx,
                                     const uint32_t* values, uint32_t* const out4[4], size_t first_row, size_t n_rows);
+
+/* The same with a per-entry mask (entry_active[k] != 0: the k-th (batch, column) entry contributes; NULL = all).  The quotient
+ * is linear in the per-column terms, so a sharded proof splits the ENTRIES over the ranks -- every rank accumulates the
+ * terms of the columns it owns over all rows from local memory -- and sums the partial quotients mod P
+ * (cm31_shard_reduce_m31).  Inactive entries still take their power of the random coefficient. */
+int cm31_accumulate_quotients_partial(uint32_t log_size, const uint32_t* const* cols, size_t n_cols, const uint32_t random_coeff[4],
+                                      size_t n_batches, const uint32_t* points, const uint32_t* batch_start, const uint32_t* col_idx,
+                                      const uint32_t* values, uint32_t* const out4[4], size_t first_row, size_t n_rows,
+                                      const uint8_t* entry_active);
 
 /* ------------------------------------------------------------------ PolyOps
  * S/prover/src/core/poly/circle/ops.rs:13-69, CPU definition S/prover/src/core/backend/cpu/circle.rs */

@@ -95,6 +95,9 @@ struct OracleBackend {
     static void allreduce_m31(std::array<Col, 4>&) {}
     static void allreduce_bins(Col&) {}
     static HashCol commit_on_layer_striped(u32 log_size, const HashCol* prev, const std::vector<const Col*>& cols) { return commit_on_layer(log_size, prev, cols); }
+    static std::vector<HashCol> commit_layers_fused_striped(u32 log_size, const HashCol* prev, const std::vector<const Col*>& cols, u32 n_levels) {
+        return commit_layers_fused(log_size, prev, cols, n_levels);
+    }
     static void join_striped_layer(HashCol&) {}
     static const u32* hash_node_source(const HashCol& layer, size_t) { return (const u32*)layer.data(); }
     static void lane(u32) {}  // the CUDA backend's stream lanes have no CPU counterpart

@@ -41,7 +41,7 @@ def main():
 
     def prove():
         cm.check(lib.cm31_prove_cairo_m(h, 16, 80, buf, C.c_size_t(cap), C.byref(ln), None))
-        return bytes(buf[: ln.value])
+        return C.string_at(buf, ln.value)
 
     alone = prove()
     cm.shard_init(arena_gib=float(os.environ.get("CM31_ARENA_GIB", "16")))
