@@ -36,6 +36,19 @@ struct Shard {
     std::unordered_map<const u32*, int> owner;   // column base pointer -> owning rank (absent = replicated)
     std::unordered_set<const u32*> striped;      // hash layers of which every rank holds only its node range
     std::vector<int> component_owner;            // by component index (claim order)
+    std::vector<double> fft_load;                // per rank: column-transform work dealt out so far in this proof
+    // Column-wise work (ICFFT + LDE + OODS evaluation + the column's DEEP quotient terms) is balanced per COLUMN, not per
+    // component: one component can hold half of a proof's cells (store_fp_imm in fibonacci_loop).  The rank that gets a
+    // column reads its trace-domain values from the component's owner through the peer mapping (a streaming read) and
+    // owns the coefficients and the LDE from then on.
+    int next_fft_rank(double weight) {
+        if ((int)fft_load.size() != world) fft_load.assign((size_t)world, 0.0);
+        int best = 0;
+        for (int r = 1; r < world; r++)
+            if (fft_load[(size_t)r] < fft_load[(size_t)best]) best = r;
+        fft_load[(size_t)best] += weight;
+        return best;
+    }
     static Shard& get() {
         static Shard s;
         return s;
@@ -169,6 +182,7 @@ struct CudaBackend {
         sh.owner.clear();
         sh.striped.clear();
         sh.component_owner.clear();
+        sh.fft_load.clear();
         if (!sh.on) return;
         cm_check(cm31_shard_arena_reset());  // also switches cm31_malloc to the arena until shard_end_proof
         sums().buf = DeviceCol(4 * 256);  // the persistent claimed-sum buffer lived in the arena that was just reset
@@ -315,9 +329,13 @@ struct CudaBackend {
         std::vector<const u32*> s;
         std::vector<u32*> d;
         for (size_t i = 0; i < evals.size(); i++) {
-            sh.tag(outs[i]->ptr(), sh.owner_of(evals[i]->ptr()));
-            if (!sh.mine(evals[i]->ptr())) continue;
-            s.push_back(evals[i]->ptr());
+            int o = sh.owner_of(evals[i]->ptr());
+            // sharded: an owned column's transform goes to the least loaded rank (it reads the values from the owner);
+            // replicated columns stay replicated
+            if (sh.on && sh.world > 1 && o >= 0) o = sh.next_fft_rank((double)log_size * (double)((size_t)1 << log_size));
+            sh.tag(outs[i]->ptr(), o);
+            if (o >= 0 && o != sh.rank) continue;
+            s.push_back(sh.resolve(evals[i]->ptr()));
             d.push_back(outs[i]->ptr());
         }
         if (!s.empty()) cm_check(cm31_interpolate_batch_to(s.data(), d.data(), s.size(), log_size, tw.h));

@@ -589,6 +589,12 @@ struct CommitmentSchemeProver {
 
     // TreeBuilder::extend_evals + commit (pcs/prover.rs:173-203): columns are consumed.
     void commit_evals(std::vector<CircleEvaluation<B>> columns, Blake2sChannel& channel) {
+        if (B::shard_world() > 1) {  // sharded proof: out-of-place, so the column transforms can be dealt out over the ranks
+            std::vector<const CircleEvaluation<B>*> refs;
+            for (auto& c : columns) refs.push_back(&c);
+            commit_evals_keep(refs, channel);
+            return;
+        }
         std::map<u32, std::vector<typename B::Col*>> by_size;
         for (auto& c : columns) by_size[c.log_size].push_back(&c.values);
         for (auto& kv : by_size) {
@@ -602,6 +608,7 @@ struct CommitmentSchemeProver {
     }
     // Same commitment, but the evaluations are only borrowed: coefficients go to fresh columns.
     void commit_evals_keep(const std::vector<const CircleEvaluation<B>*>& columns, Blake2sChannel& channel) {
+        B::shard_barrier();  // sharded proof: the values are complete on their owners before other ranks transform them
         std::vector<CirclePoly<B>> polys(columns.size());
         std::map<u32, std::vector<size_t>> idx_by_size;
         for (size_t i = 0; i < columns.size(); i++) idx_by_size[columns[i]->log_size].push_back(i);
