@@ -281,6 +281,7 @@ struct CudaBackend {
         cm_check(cm31_shard_allgather(layer.ptr(), layer.size() * 4 / (size_t)sh.world));
         sh.striped.erase(layer.ptr());
     }
+    static bool is_striped(const HashCol& layer) { return Shard::get().on && Shard::get().striped.count(layer.ptr()) != 0; }
     // where node `node` of a hash layer can be read from: the owner's copy for a striped layer
     static const u32* hash_node_source(const HashCol& layer, size_t node) {
         Shard& sh = Shard::get();
@@ -332,7 +333,8 @@ struct CudaBackend {
             int o = sh.owner_of(evals[i]->ptr());
             // sharded: an owned column's transform goes to the least loaded rank (it reads the values from the owner);
             // replicated columns stay replicated
-            if (sh.on && sh.world > 1 && o >= 0) o = sh.next_fft_rank((double)log_size * (double)((size_t)1 << log_size));
+            // (from 4 ranks on: with 2 ranks the remote reads cost more than the better balance gains, measured on 2^22 / 2^24)
+            if (sh.on && sh.world >= 4 && o >= 0) o = sh.next_fft_rank((double)log_size * (double)((size_t)1 << log_size));
             sh.tag(outs[i]->ptr(), o);
             if (o >= 0 && o != sh.rank) continue;
             s.push_back(sh.resolve(evals[i]->ptr()));

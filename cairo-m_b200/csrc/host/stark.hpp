@@ -451,7 +451,11 @@ struct MerkleProver {
             std::vector<u32> col_ids;
             for (const Col* c : layer_columns) col_ids.push_back(queue.source(B::col_words(*c)));
             // (a striped layer of a sharded proof is read from the rank that holds the node: hash_node_source)
-            auto prev_id_of = [&](size_t node) { return queue.source(B::hash_node_source(*previous_layer_hashes, node)); };
+            const bool prev_striped = previous_layer_hashes && B::is_striped(*previous_layer_hashes);
+            const u32 prev_id_whole = previous_layer_hashes && !prev_striped ? queue.source(B::hash_words(*previous_layer_hashes)) : 0;
+            auto prev_id_of = [&](size_t node) {
+                return prev_striped ? queue.source(B::hash_node_source(*previous_layer_hashes, node)) : prev_id_whole;
+            };
             while (pi < last_layer_queries.size() || ci < layer_column_queries.size()) {
                 size_t node_index;
                 bool has_p = pi < last_layer_queries.size(), has_c = ci < layer_column_queries.size();

@@ -99,6 +99,7 @@ struct OracleBackend {
         return commit_layers_fused(log_size, prev, cols, n_levels);
     }
     static void join_striped_layer(HashCol&) {}
+    static bool is_striped(const HashCol&) { return false; }
     static const u32* hash_node_source(const HashCol& layer, size_t) { return (const u32*)layer.data(); }
     static void lane(u32) {}  // the CUDA backend's stream lanes have no CPU counterpart
     static void lanes_join() {}
