@@ -8,6 +8,7 @@
 // One thread per row; every column access is a coalesced 4-byte-per-lane load; the program and
 // its constants are warp-uniform reads.  The register file lives in per-thread local memory
 // (hardware-interleaved, L1 resident), sized by the program's register allocation.
+#include <cstdlib>
 #include <unordered_map>
 
 #include "air_gen.cuh"
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(128) air_program_kernel(const u32* const* __re
     }
 }
 
+static int g_gen_sync = getenv("CM31_GEN_SYNC") ? atoi(getenv("CM31_GEN_SYNC")) : 1;  // CTA barriers in the generated bodies (air_gen.cuh GEN_SYNC)
 static int g_air_mode = 0;  // 0 = AOT-specialised kernel when one exists, 1 = always the bytecode interpreter
 
 // device word collecting AIR_ERR_* bits of every AIR program launched since the last cm31_air_error_check
@@ -179,7 +181,7 @@ static int run_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* co
             CM_REQUIRE(n_denom == ((size_t)1 << (row_log - trace_log)), "air: wrong number of denominator inverses");
             if (int e = ddenom_gen.upload(denom_inv_host, n_denom * 4)) return e;
         }
-        GenLaunch gl{in_cols, n_in, out_cols, n_out, row_log, trace_log, consts, n_consts, (const u32*)ddenom_gen.d, acc4, hist_bins, err};
+        GenLaunch gl{in_cols, n_in, out_cols, n_out, row_log, trace_log, consts, n_consts, (const u32*)ddenom_gen.d, acc4, g_gen_sync, hist_bins, err};
         size_t rows = (size_t)1 << row_log;
         ProfScope prof(acc4 ? "constraint_eval" : "air_program", acc4 ? 4ull * rows * n_in + 32ull * rows : 4ull * rows * (n_in + n_out));
         if (prof_enabled()) prof_ops(rows * (program_m31_ops(code, n_instr, code_hash) + (acc4 ? 8 : 0)));

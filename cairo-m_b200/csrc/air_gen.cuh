@@ -21,6 +21,7 @@ struct GenLaunch {
     size_t n_consts;
     const u32* denom_inv_dev;  // device, or null
     uint32_t* const* acc4;     // host array of 4 device pointers, or null
+    int sync;                  // CTA-wide barriers inside the generated bodies (instruction-fetch sharing), see GEN_SYNC
     u32 hist_bins;             // size of the bin column OP_HIST counts into (0 for programs without histograms)
     u32* err_flag;             // device word: AIR_ERR_* bits (cm31_air_error_check)
 };
@@ -102,12 +103,36 @@ using cm31::g_qm_mul;
 #define ldcol_off(i, off) __ldg(a.in[i] + cm31::gen_offset_row(row, a.trace_log, a.row_log, (off)))
 #define cw(s) (a.c[s])
 #define cq(s) cm31::qm_make(a.c[s], a.c[(s) + 1], a.c[(s) + 2], a.c[(s) + 3])
-#define st1(slot, f) a.out[slot][row] = (f)
-#define st4(slot, e)                 \
-    do {                             \
-        a.out[slot][row] = (e).a;    \
-        a.out[(slot) + 1][row] = (e).b; \
-        a.out[(slot) + 2][row] = (e).c; \
-        a.out[(slot) + 3][row] = (e).d; \
+// `live`: the thread's row exists (every thread of a CTA runs the whole body so the CTA-wide barriers of GEN_SYNC are legal;
+// rows past the end compute on row 0 and store nothing)
+#define st1(slot, f)                      \
+    do {                                  \
+        if (live) a.out[slot][row] = (f); \
     } while (0)
-#define hist(slot, f) cm31::gen_hist(a.out[slot], (f), a.hist_bins, a.err)
+#define st4(slot, e)                        \
+    do {                                    \
+        if (live) {                         \
+            a.out[slot][row] = (e).a;       \
+            a.out[(slot) + 1][row] = (e).b; \
+            a.out[(slot) + 2][row] = (e).c; \
+            a.out[(slot) + 3][row] = (e).d; \
+        }                                   \
+    } while (0)
+#define hist(slot, f)                                                     \
+    do {                                                                  \
+        if (live) cm31::gen_hist(a.out[slot], (f), a.hist_bins, a.err);   \
+    } while (0)
+// Instruction fetch is what these 2-7k-instruction straight-line bodies are short of (ncu r01b: `no_inst` 29-32 % of the
+// stall samples): every warp streams the whole body from L2 unless another warp of its SM fetched the same lines a moment
+// ago.  A CTA-wide barrier every few dozen statements keeps the warps of a CTA within the 32 KB L1.5 instruction cache of
+// each other, so a line is fetched once per CTA instead of once per warp.  a.sync is uniform (kernel argument).
+#define GEN_SYNC()                    \
+    do {                              \
+        if (a.sync) __syncthreads();  \
+    } while (0)
+// lazily reduced accumulation of  coeff (QM31) x f  over the base-field constraints of a component
+#define CACC(e, f)                                  \
+    do {                                            \
+        dot_term(ca0, ca1, ca2, ca3, (e), (f));     \
+        if ((++ca_n & 3) == 0) dot_fold(ca0, ca1, ca2, ca3); \
+    } while (0)

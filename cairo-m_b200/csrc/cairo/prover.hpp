@@ -89,6 +89,10 @@ struct CairoProof {  // crates/prover/src/lib.rs:61-73
 
     std::vector<uint8_t> to_bytes() const {
         ProofWriter w;
+        write(w);
+        return w.bytes;
+    }
+    void write(ProofWriter& w) const {
         w.u64v(claim.log_sizes.size());
         for (auto& kv : claim.log_sizes) w.u32v(kv.second);
         w.u64v(interaction_claim.claimed_sums.size());
@@ -108,7 +112,6 @@ struct CairoProof {  // crates/prover/src/lib.rs:61-73
         }
         w.u64v(interaction_pow);
         w.proof(stark_proof);
-        return w.bytes;
     }
     static CairoProof from_bytes(const uint8_t* data, size_t len, const std::vector<std::string>& component_names) {
         ProofReader r(data, len);

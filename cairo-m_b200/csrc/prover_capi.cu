@@ -560,7 +560,10 @@ int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n
         int rc;
         {
             HostTimer ht("proof_to_bytes");
-            rc = write_out(proof.to_bytes(), proof_out, proof_cap, proof_len);
+            static thread_local ProofWriter writer;  // reused across proofs: a fresh megabyte costs ~250 page faults per proof
+            writer.bytes.clear();
+            proof.write(writer);
+            rc = write_out(writer.bytes, proof_out, proof_cap, proof_len);
         }
         HostTimer::report();
         return rc;

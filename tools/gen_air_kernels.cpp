@@ -40,6 +40,9 @@ static std::set<uint64_t> g_seen;
 #ifndef GEN_BLOCK
 #define GEN_BLOCK 256
 #endif
+#ifndef GEN_SYNC_EVERY
+#define GEN_SYNC_EVERY 48
+#endif
 
 static void emit_kernel(std::ostream& os, const Kernel& k, std::vector<std::pair<uint64_t, std::string>>& table) {
     uint64_t h = air_code_hash(k.prog.code.data(), k.prog.code.size());
@@ -50,20 +53,32 @@ static void emit_kernel(std::ostream& os, const Kernel& k, std::vector<std::pair
     os << "// " << k.prog.code.size() << " bytecode instructions, " << k.prog.n_mul_m31 << " M31 multiplications per row, " << k.n_in
        << " input / " << k.n_out << " output columns\n";
     os << "struct A_" << n << " {\n    u32 row_log, trace_log;\n    const u32* denom_inv;\n    u32* acc[4];\n    const u32* in[" << nin
-       << "];\n    u32* out[" << nout << "];\n    u32 c[" << nc << "];\n    u32 hist_bins;\n    u32* err;\n};\n";
+       << "];\n    u32* out[" << nout << "];\n    u32 c[" << nc << "];\n    u32 hist_bins;\n    u32* err;\n    int sync;\n};\n";
     // CTA size: the programs are thousands of straight-line instructions executed once per row, so instruction fetch is
     // shared only between warps that run the same code at the same time; the warps of one CTA start together and stay
     // close, warps of different CTAs do not (ncu r01b: no_inst 30 % with one warp per scheduler and CTA).
     const unsigned block = GEN_BLOCK;
     os << "__global__ void __launch_bounds__(" << block << ") k_" << n << "(const __grid_constant__ A_" << n << " a) {\n";
-    os << "    const u32 row = blockIdx.x * " << block << "u + threadIdx.x;\n    if (row >= (1u << a.row_log)) return;\n";
-    if (k.constraint) os << "    QM31 acc = qm_zero();\n";
-    os << k.prog.cuda_body;
+    os << "    const u32 row_raw = blockIdx.x * " << block << "u + threadIdx.x;\n    const bool live = row_raw < (1u << a.row_log);\n"
+       << "    const u32 row = live ? row_raw : 0u;\n";
+    if (k.constraint) os << "    QM31 acc = qm_zero();\n    u64 ca0 = 0, ca1 = 0, ca2 = 0, ca3 = 0;\n    u32 ca_n = 0;\n";
+    {  // the body, with a (run-time switchable) CTA barrier every GEN_SYNC_EVERY statements
+        std::istringstream body(k.prog.cuda_body);
+        std::string line;
+        size_t n_lines = 0;
+        while (std::getline(body, line)) {
+            os << line << "\n";
+            if (++n_lines % GEN_SYNC_EVERY == 0) os << "    GEN_SYNC();\n";
+        }
+    }
     if (k.constraint) {
         // component.rs:413-421: col[row] += row_res * denom_inv[row >> trace_log]
+        os << "    acc = qm_add(acc, dot_done(ca0, ca1, ca2, ca3));\n";
         os << "    const QM31 res = qm_mul_m31(acc, __ldg(a.denom_inv + (row >> a.trace_log)));\n";
-        os << "    a.acc[0][row] = m31_add(a.acc[0][row], res.a);\n    a.acc[1][row] = m31_add(a.acc[1][row], res.b);\n";
-        os << "    a.acc[2][row] = m31_add(a.acc[2][row], res.c);\n    a.acc[3][row] = m31_add(a.acc[3][row], res.d);\n";
+        os << "    if (live) {\n";
+        os << "        a.acc[0][row] = m31_add(a.acc[0][row], res.a);\n        a.acc[1][row] = m31_add(a.acc[1][row], res.b);\n";
+        os << "        a.acc[2][row] = m31_add(a.acc[2][row], res.c);\n        a.acc[3][row] = m31_add(a.acc[3][row], res.d);\n";
+        os << "    }\n";
     }
     os << "}\n";
     os << "static int l_" << n << "(const GenLaunch& g) {\n";
@@ -72,7 +87,7 @@ static void emit_kernel(std::ostream& os, const Kernel& k, std::vector<std::pair
     os << "    CM_REQUIRE(" << (k.constraint ? "g.acc4 != nullptr && g.denom_inv_dev != nullptr" : "g.acc4 == nullptr")
        << ", \"generated AIR kernel " << n << ": accumulator mismatch\");\n";
     os << "    A_" << n << " a;\n    a.row_log = g.row_log;\n    a.trace_log = g.trace_log;\n    a.denom_inv = g.denom_inv_dev;\n";
-    os << "    a.hist_bins = g.hist_bins;\n    a.err = g.err_flag;\n";
+    os << "    a.hist_bins = g.hist_bins;\n    a.err = g.err_flag;\n    a.sync = g.sync;\n";
     os << "    for (int k = 0; k < 4; k++) a.acc[k] = g.acc4 ? g.acc4[k] : nullptr;\n";
     os << "    for (size_t k = 0; k < " << k.n_in << "; k++) a.in[k] = g.in_cols[k];\n";
     os << "    for (size_t k = 0; k < " << k.n_out << "; k++) a.out[k] = g.out_cols[k];\n";
