@@ -310,8 +310,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         # ONE proof sharded over all ranks: every rank holds the same input and owns a subset of the components;
         # strong scaling -- the work per step is one proof whatever the number of GPUs
         cm.shard_init(arena_gib=args.arena_gib)
-    programs = {"fibonacci_loop": 0, "array_sum": 1, "u32_counter": 2, "u32_mix": 3, "sha256": 4}
+    programs = {"fibonacci_loop": 0, "array_sum": 1, "u32_counter": 2, "u32_mix": 3, "sha256": 4, "all_opcodes": 5}
     n = args.iterations if args.iterations else fib_iterations(args.log_steps)
+    if args.program == "all_opcodes" and not args.iterations:
+        n = (1 << args.log_steps) // 45  # 45 VM steps per iteration: BASELINE config 4 (synthetic trace, every opcode component live)
     if args.program == "sha256" and not args.iterations:
         n = (1 << args.log_steps) // 3490  # ~3 490 VM steps per compression: BASELINE config 3 (~2^22 rows of u32 / bitwise work)
     h = C.c_void_p()
@@ -479,6 +481,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "config": {"workload": workload_name(args.log_steps) if args.program == "fibonacci_loop" and not args.iterations
                    else (f"sha256({n} compressions of a padded block, examples/sha256-cairo-m style: u32 / bitwise / range-check components) "
                          f"[BASELINE config 3, not the headline workload]" if args.program == "sha256"
+                         else f"all_opcodes({n} iterations x 45 steps: synthetic trace with every opcode component live, memory / merkle / "
+                              f"clock_update / poseidon2 / range-check / bitwise components included) [BASELINE config 4]" if args.program == "all_opcodes"
                          else f"{args.program}({n}) [side measurement, not the BASELINE workload]"), "vm_steps_per_proof": vm_steps,
                    "parallelism": (f"ONE proof sharded over {world} GPU(s)" if sharded else
                                    "one independent segment proof per GPU" if world > 1 else "single GPU"),
@@ -518,7 +522,7 @@ def main():
                     help="log2 VM steps of the cpu_baseline proof (default: the workload's own size, one whole proof)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-adapter", action="store_true", help="skip the adapter side measurement")
-    ap.add_argument("--program", default="fibonacci_loop", choices=["fibonacci_loop", "array_sum", "u32_counter", "u32_mix", "sha256"],
+    ap.add_argument("--program", default="fibonacci_loop", choices=["fibonacci_loop", "array_sum", "u32_counter", "u32_mix", "sha256", "all_opcodes"],
                     help="side measurements on the other hand-assembled programs (the headline is fibonacci_loop)")
     ap.add_argument("--iterations", type=int, default=0, help="program argument n (default: 2^log_steps / 8 for fibonacci_loop)")
     ap.add_argument("--dist-selftest", action="store_true", help=argparse.SUPPRESS)

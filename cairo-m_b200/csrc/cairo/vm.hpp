@@ -331,7 +331,98 @@ inline std::vector<Word4> sha256_program() {
     return p;
 }
 
-enum CairoProgramId : u32 { PROGRAM_FIBONACCI_LOOP = 0, PROGRAM_ARRAY_SUM = 1, PROGRAM_U32_COUNTER = 2, PROGRAM_U32_MIX = 3, PROGRAM_SHA256 = 4 };
+// ------------------------------------------------------------------ program: all_opcodes (BASELINE config 4)
+// The synthetic "all components" workload: every loop iteration executes every opcode family once or more, so after n
+// iterations 25 of the 26 opcode components hold n .. 4n live rows each (u32_store_eq_fp_imm can only prove padding: see
+// U32StoreEqFpImmEval).  One iteration = a felt block (store / add / sub / mul / div, le, assert), a pointer block (frame
+// pointer, the four double-deref forms), a call / ret pair, an absolute jump, the u32_mix round (u32 mul / divrem / eq / lt and
+// every two-word *_fp_imm instruction) and the u32_counter round (u32 add / sub / and / or / xor / lt on registers): 45 VM
+// steps.  Returns the low limb of u32_mix's x (same recurrence as u32_mix_program).
+inline std::vector<Word4> all_opcodes_program() {
+    const u32 M3 = P - 3, M4 = P - 4;
+    std::vector<Word4> p;
+    auto one_word = [&](u32 op, u32 a, u32 b, u32 c) { p.push_back(Word4{{op, a, b, c}}); };
+    auto two_words = [&](u32 op, u32 a, u32 b, u32 c, u32 d, u32 e = 0) {
+        p.push_back(Word4{{op, a, b, c}});
+        p.push_back(Word4{{d, e, 0, 0}});
+    };
+    // felt slots
+    const u32 EQ = 0, I = 1, I_NEXT = 2, CMP = 3, A = 4, B = 5, T = 6, U = 7, V = 8, W = 9, D = 10, LE = 11, PTR = 12, IDX = 13, LD1 = 14, LD2 = 15;
+    const u32 ARRAY = 80, CALLEE = 90;  // ptr = fp + 80; the callee's frame starts at fp + 90 (its fp = fp + 92)
+    const u32 MX = 100, CN = 140;       // u32 registers of the u32_mix / u32_counter rounds
+    one_word(OP_U32_STORE_IMM, 0x1234, 0x5678, MX + 30);  // mix: x = 0x56781234
+    one_word(OP_U32_STORE_IMM, 0x00f1, 0x0000, MX + 2);   // mix: y = 0xf1
+    one_word(OP_U32_STORE_IMM, 0xfff0, 0x0001, CN + 0);   // counter: x
+    one_word(OP_U32_STORE_IMM, 0x0011, 0x0000, CN + 2);   // counter: y
+    one_word(OP_U32_STORE_IMM, 0, 0, CN + 8);             // counter: zero
+    one_word(OP_U32_STORE_IMM, 1, 0, CN + 10);            // counter: one
+    one_word(OP_STORE_IMM, 0, I, 0);
+    const u32 loop = (u32)p.size();
+    one_word(OP_STORE_SUB_FP_FP, I, M4, CMP);  // i - n
+    one_word(OP_JNZ_FP_IMM, CMP, 2, 0);
+    const u32 exit_jmp = (u32)p.size();
+    one_word(OP_JMP_REL_IMM, 0, 0, 0);  // -> exit (patched)
+    // ---- felt block
+    one_word(OP_STORE_IMM, 7, A, 0);               // a = 7
+    one_word(OP_STORE_ADD_FP_IMM, A, 3, B);        // b = a + 3
+    one_word(OP_STORE_MUL_FP_IMM, B, 5, T);        // t = b * 5
+    one_word(OP_STORE_ADD_FP_FP, A, B, U);         // u = a + b
+    one_word(OP_STORE_SUB_FP_FP, T, U, V);         // v = t - u
+    one_word(OP_STORE_MUL_FP_FP, V, U, W);         // w = v * u
+    one_word(OP_STORE_DIV_FP_FP, W, B, D);         // d = w / b
+    one_word(OP_STORE_LE_FP_IMM, A, 9, LE);        // le = (a <= 9)
+    one_word(OP_ASSERT_EQ_FP_IMM, A, 7, 0);        // assert a == 7
+    // ---- pointer block
+    one_word(OP_STORE_FRAME_POINTER, ARRAY, PTR, 0);           // ptr = fp + 80
+    one_word(OP_STORE_IMM, 2, IDX, 0);                         // idx = 2
+    one_word(OP_STORE_TO_DOUBLE_DEREF_FP_IMM, PTR, 1, A);      // ptr[1] = a
+    one_word(OP_STORE_TO_DOUBLE_DEREF_FP_FP, PTR, IDX, B);     // ptr[idx] = b
+    one_word(OP_STORE_DOUBLE_DEREF_FP, PTR, 1, LD1);           // ld1 = ptr[1]
+    one_word(OP_STORE_DOUBLE_DEREF_FP_FP, PTR, IDX, LD2);      // ld2 = ptr[idx]
+    // ---- call / ret, absolute jump
+    const u32 call_at = (u32)p.size();
+    one_word(OP_CALL_ABS_IMM, CALLEE, 0, 0);                   // target patched below
+    one_word(OP_JMP_ABS_IMM, (u32)p.size() + 1, 0, 0);         // jmp abs -> the next instruction
+    // ---- the u32_mix round (registers at fp + 100 ..; the equality lands in [fp+0], see U32StoreEqFpFpEval)
+    one_word(OP_U32_STORE_MUL_FP_FP, MX + 30, MX + 2, MX + 8);                  // t = x * y
+    two_words(OP_U32_STORE_ADD_FP_IMM, MX + 8, 0x79b9, 0x9e37, MX + 10);        // u = t + 0x9e3779b9
+    two_words(OP_U32_STORE_DIV_REM_FP_FP, MX + 10, MX + 2, MX + 12, MX + 14);   // q = u / y, r = u % y
+    two_words(OP_U32_STORE_MUL_FP_IMM, MX + 12, 0x0065, 0x0001, MX + 16);       // v = q * 0x10065
+    two_words(OP_U32_STORE_XOR_FP_IMM, MX + 16, 0xa5a5, 0x5a5a, MX + 18);       // w = v ^ 0x5a5aa5a5
+    two_words(OP_U32_STORE_AND_FP_IMM, MX + 18, 0xffff, 0x0fff, MX + 20);       // a = w & 0x0fffffff
+    two_words(OP_U32_STORE_OR_FP_IMM, MX + 20, 0x0001, 0x0000, MX + 22);        // b = a | 1
+    two_words(OP_U32_STORE_DIV_REM_FP_IMM, MX + 22, 7, 0, MX + 24, MX + 26);    // c = b / 7, d = b % 7
+    two_words(OP_U32_STORE_LT_FP_IMM, MX + 26, 3, 0, MX + 28);                  // (d < 3)
+    one_word(OP_U32_STORE_EQ_FP_FP, MX + 24, MX + 12, EQ);                      // [fp+0] = (c == q)
+    one_word(OP_U32_STORE_ADD_FP_FP, MX + 22, MX + 14, MX + 30);                // x = b + r
+    two_words(OP_U32_STORE_ADD_FP_IMM, MX + 2, 2, 0, MX + 32);                  // y2 = y + 2
+    two_words(OP_U32_STORE_ADD_FP_IMM, MX + 32, 0, 0, MX + 2);                  // y = y2
+    // ---- the u32_counter round (registers at fp + 140 ..)
+    one_word(OP_U32_STORE_ADD_FP_FP, CN + 0, CN + 2, CN + 4);                   // t = x + y
+    one_word(OP_U32_STORE_XOR_FP_FP, CN + 4, CN + 2, CN + 14);                  // a = t ^ y
+    one_word(OP_U32_STORE_AND_FP_FP, CN + 14, CN + 4, CN + 16);                 // b = a & t
+    one_word(OP_U32_STORE_OR_FP_FP, CN + 16, CN + 2, CN + 18);                  // c = b | y
+    one_word(OP_U32_STORE_ADD_FP_FP, CN + 18, CN + 8, CN + 0);                  // x = c + 0
+    one_word(OP_U32_STORE_SUB_FP_FP, CN + 2, CN + 10, CN + 12);                 // t2 = y - 1
+    one_word(OP_U32_STORE_ADD_FP_FP, CN + 12, CN + 8, CN + 2);                  // y = t2 + 0
+    one_word(OP_U32_STORE_LT_FP_FP, CN + 2, CN + 0, CN + 20);                   // (y < x)
+    // ---- loop control
+    one_word(OP_STORE_ADD_FP_IMM, I, 1, I_NEXT);
+    one_word(OP_STORE_ADD_FP_IMM, I_NEXT, 0, I);
+    const u32 back = (u32)p.size();
+    one_word(OP_JMP_REL_IMM, m31_sub(loop, back), 0, 0);
+    p[exit_jmp].v[1] = (u32)p.size() - exit_jmp;
+    one_word(OP_STORE_ADD_FP_IMM, MX + 30, 0, M3);  // return mix x.lo
+    one_word(OP_RET, 0, 0, 0);
+    p[call_at].v[2] = (u32)p.size();                // callee: one store, ret
+    one_word(OP_STORE_IMM, 5, 0, 0);
+    one_word(OP_RET, 0, 0, 0);
+    return p;
+}
+
+enum CairoProgramId : u32 {
+    PROGRAM_FIBONACCI_LOOP = 0, PROGRAM_ARRAY_SUM = 1, PROGRAM_U32_COUNTER = 2, PROGRAM_U32_MIX = 3, PROGRAM_SHA256 = 4, PROGRAM_ALL_OPCODES = 5
+};
 inline std::vector<Word4> program_by_id(u32 id) {
     switch (id) {
         case PROGRAM_FIBONACCI_LOOP: return fibonacci_loop_program();
@@ -339,6 +430,7 @@ inline std::vector<Word4> program_by_id(u32 id) {
         case PROGRAM_U32_COUNTER: return u32_counter_program();
         case PROGRAM_U32_MIX: return u32_mix_program();
         case PROGRAM_SHA256: return sha256_program();
+        case PROGRAM_ALL_OPCODES: return all_opcodes_program();
         default: throw std::runtime_error("unknown program id");
     }
 }

@@ -413,7 +413,7 @@ int cm31_air_shapes(char* buf, size_t cap, size_t* len);
  * (the serial steps BEFORE the hot path), a tamper hook, and the bring-up AIR.  Tests, bench.py and smoke() use them to have
  * inputs; a cairo-m-prover integration never calls them. */
 /* program_id 0 = fibonacci_loop(n); 1 = array_sum(n): call/ret, frame pointer, double-deref, assert, le; 2 = u32_counter(n):
- * u32 limb ops; 3 = u32_mix(n): u32 mul/divrem/eq/lt + two-word *_fp_imm u32 instructions; 4 = sha256 compression rounds */
+ * u32 limb ops; 3 = u32_mix(n): u32 mul/divrem/eq/lt + two-word *_fp_imm u32 instructions; 4 = sha256 (n chained compressions of the padded block of "abc"); 5 = all_opcodes (n iterations, every opcode family) */
 int cm31_test_program_input_create(uint32_t program_id, uint32_t n, cm31_prover_input** out);
 int cm31_test_fib_input_create(uint32_t n, cm31_prover_input** out);
 /* corrupt the adapter output so a store_fp_fp constraint fails (kind 0: a written value, 1: an operand read) */

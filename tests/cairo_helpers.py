@@ -6,7 +6,7 @@ from tests import oracle_lib as orc
 CAP = 1 << 27
 
 
-FIB, ARRAY_SUM, U32_COUNTER, U32_MIX, SHA256 = 0, 1, 2, 3, 4
+FIB, ARRAY_SUM, U32_COUNTER, U32_MIX, SHA256, ALL_OPCODES = 0, 1, 2, 3, 4, 5
 
 
 def oracle_fib_prove(n, pow_bits=16, n_queries=80):

@@ -263,3 +263,29 @@ def test_sha256_2_20_steps_verifies_from_device_adapted_logs(cm):
     assert residual == (0, 0, 0, 0)
     from tests.test_proof_json import from_json, to_json
     assert from_json(cm, to_json(cm, got)) == got
+
+
+@pytest.mark.parametrize("n", [1, 50])
+def test_all_opcodes_proof_bit_exact(cm, n):
+    # BASELINE config 4: the synthetic all-components workload -- every opcode family live in one proof
+    inp = ch.GpuFibInput(cm, n, program=ch.ALL_OPCODES)
+    try:
+        assert inp.return_value == ch.u32_mix_expected(n) and inp.steps == 45 * n + 12
+        got, _ = inp.prove()
+    finally:
+        inp.close()
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+    want, _ = ch.oracle_program_prove(ch.ALL_OPCODES, n)
+    assert got == want
+
+
+def test_all_opcodes_2_20_steps_from_device_adapted_logs(cm):
+    n = 23500  # 1.06 M steps, 25 opcode components of 2^15 .. 2^17 rows
+    dev = ch.GpuAdaptedInput(cm, n, ch.ALL_OPCODES)
+    try:
+        got, _ = dev.prove()
+    finally:
+        dev.close()
+    assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
+    residual, _ = ch.oracle_logup_residual(n, got, program=ch.ALL_OPCODES)
+    assert residual == (0, 0, 0, 0)

@@ -135,3 +135,23 @@ def test_sha256_program_proves_and_returns_the_digest_of_abc():
 def test_sha256_program_chains_compressions():
     residual, info = ch.oracle_logup_residual(3, ch.oracle_program_prove(ch.SHA256, 3)[0], program=ch.SHA256)
     assert residual == (0, 0, 0, 0) and info["fib"] == ch.sha256_expected(3)
+
+
+# ---- BASELINE config 4: the synthetic all-components workload (every opcode family in every loop iteration)
+def test_all_opcodes_program_fills_25_of_26_opcode_components():
+    n = 20
+    proof = ch.oracle_program_prove(ch.ALL_OPCODES, n)[0]
+    assert ch.oracle_cairo_verify(proof) == 0, orc.last_error()
+    residual, info = ch.oracle_logup_residual(n, proof, program=ch.ALL_OPCODES)
+    assert residual == (0, 0, 0, 0)
+    assert info["fib"] == ch.u32_mix_expected(n)        # the u32_mix recurrence runs inside the loop
+    assert info["steps"] == 45 * n + 12
+    k = int.from_bytes(proof[:8], "little")
+    log_sizes = [int.from_bytes(proof[8 + 4 * i:12 + 4 * i], "little") for i in range(k)]
+    import json
+    from pathlib import Path
+    names = [c["name"] for c in json.loads((Path(__file__).parent / "golden" / "air_shapes_reference.json").read_text())["components"]]
+    live = {nm: ls for nm, ls in zip(names[:26], log_sizes[:26])}
+    # n = 20 rows or more in every opcode component (padded to 2^5 .. 2^7) except the one that can only prove padding
+    assert all(ls >= 5 for nm, ls in live.items() if nm != "u32_store_eq_fp_imm"), live
+    assert live["u32_store_eq_fp_imm"] == 4
