@@ -313,7 +313,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     programs = {"fibonacci_loop": 0, "array_sum": 1, "u32_counter": 2, "u32_mix": 3, "sha256": 4, "all_opcodes": 5}
     n = args.iterations if args.iterations else fib_iterations(args.log_steps)
     if args.program == "all_opcodes" and not args.iterations:
-        n = (1 << args.log_steps) // 45  # 45 VM steps per iteration: BASELINE config 4 (synthetic trace, every opcode component live)
+        n = (1 << args.log_steps) // 46  # 46 VM steps per iteration: BASELINE config 4 (synthetic trace, every opcode component live)
     if args.program == "sha256" and not args.iterations:
         n = (1 << args.log_steps) // 3490  # ~3 490 VM steps per compression: BASELINE config 3 (~2^22 rows of u32 / bitwise work)
     h = C.c_void_p()
@@ -481,7 +481,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "config": {"workload": workload_name(args.log_steps) if args.program == "fibonacci_loop" and not args.iterations
                    else (f"sha256({n} compressions of a padded block, examples/sha256-cairo-m style: u32 / bitwise / range-check components) "
                          f"[BASELINE config 3, not the headline workload]" if args.program == "sha256"
-                         else f"all_opcodes({n} iterations x 45 steps: synthetic trace with every opcode component live, memory / merkle / "
+                         else f"all_opcodes({n} iterations x 46 steps: synthetic trace with every opcode component live, memory / merkle / "
                               f"clock_update / poseidon2 / range-check / bitwise components included) [BASELINE config 4]" if args.program == "all_opcodes"
                          else f"{args.program}({n}) [side measurement, not the BASELINE workload]"), "vm_steps_per_proof": vm_steps,
                    "parallelism": (f"ONE proof sharded over {world} GPU(s)" if sharded else

@@ -336,7 +336,7 @@ inline std::vector<Word4> sha256_program() {
 // iterations 25 of the 26 opcode components hold n .. 4n live rows each (u32_store_eq_fp_imm can only prove padding: see
 // U32StoreEqFpImmEval).  One iteration = a felt block (store / add / sub / mul / div, le, assert), a pointer block (frame
 // pointer, the four double-deref forms), a call / ret pair, an absolute jump, the u32_mix round (u32 mul / divrem / eq / lt and
-// every two-word *_fp_imm instruction) and the u32_counter round (u32 add / sub / and / or / xor / lt on registers): 45 VM
+// every two-word *_fp_imm instruction) and the u32_counter round (u32 add / sub / and / or / xor / lt on registers, one u32 constant): 46 VM
 // steps.  Returns the low limb of u32_mix's x (same recurrence as u32_mix_program).
 inline std::vector<Word4> all_opcodes_program() {
     const u32 M3 = P - 3, M4 = P - 4;
@@ -406,6 +406,7 @@ inline std::vector<Word4> all_opcodes_program() {
     one_word(OP_U32_STORE_SUB_FP_FP, CN + 2, CN + 10, CN + 12);                 // t2 = y - 1
     one_word(OP_U32_STORE_ADD_FP_FP, CN + 12, CN + 8, CN + 2);                  // y = t2 + 0
     one_word(OP_U32_STORE_LT_FP_FP, CN + 2, CN + 0, CN + 20);                   // (y < x)
+    one_word(OP_U32_STORE_IMM, 0x00ff, 0x0000, CN + 22);                        // a scratch u32 constant (u32_store_imm live)
     // ---- loop control
     one_word(OP_STORE_ADD_FP_IMM, I, 1, I_NEXT);
     one_word(OP_STORE_ADD_FP_IMM, I_NEXT, 0, I);

@@ -270,7 +270,7 @@ def test_all_opcodes_proof_bit_exact(cm, n):
     # BASELINE config 4: the synthetic all-components workload -- every opcode family live in one proof
     inp = ch.GpuFibInput(cm, n, program=ch.ALL_OPCODES)
     try:
-        assert inp.return_value == ch.u32_mix_expected(n) and inp.steps == 45 * n + 12
+        assert inp.return_value == ch.u32_mix_expected(n) and inp.steps == 46 * n + 12
         got, _ = inp.prove()
     finally:
         inp.close()
@@ -280,7 +280,7 @@ def test_all_opcodes_proof_bit_exact(cm, n):
 
 
 def test_all_opcodes_2_20_steps_from_device_adapted_logs(cm):
-    n = 23500  # 1.06 M steps, 25 opcode components of 2^15 .. 2^17 rows
+    n = 23000  # 1.06 M steps, 25 opcode components of 2^15 .. 2^17 rows
     dev = ch.GpuAdaptedInput(cm, n, ch.ALL_OPCODES)
     try:
         got, _ = dev.prove()

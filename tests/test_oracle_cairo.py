@@ -145,7 +145,7 @@ def test_all_opcodes_program_fills_25_of_26_opcode_components():
     residual, info = ch.oracle_logup_residual(n, proof, program=ch.ALL_OPCODES)
     assert residual == (0, 0, 0, 0)
     assert info["fib"] == ch.u32_mix_expected(n)        # the u32_mix recurrence runs inside the loop
-    assert info["steps"] == 45 * n + 12
+    assert info["steps"] == 46 * n + 12
     k = int.from_bytes(proof[:8], "little")
     log_sizes = [int.from_bytes(proof[8 + 4 * i:12 + 4 * i], "little") for i in range(k)]
     import json
