@@ -342,8 +342,11 @@ int cm31_adapter_stage_logs(const uint32_t* trace_host, size_t n_trace, const ui
 
     if (background) {
         if ((e = cm31_bg_begin()) || (e = cm31_h2d_bg_ordered(P_.trace, trace_host, n_trace * 8)) || (e = cm31_h2d_bg_ordered(P_.init, init_host, n_init * 16)) ||
-            (e = cm31_h2d_bg_ordered(P_.mem, mem_host, n_mem * 20)) || (e = cm31_bg_mark(&P_.upload_mark)))
+            (e = cm31_h2d_bg_ordered(P_.mem, mem_host, n_mem * 20)) || (e = cm31_bg_mark(&P_.upload_mark))) {
+            cm31_bg_fence();  // copies already issued on the background stream still target these buffers: the plan's destructor
+                              // frees them on the main stream, which must be ordered after those copies
             return e;
+        }
         P_.wait_upload = true;
     } else {
         CM_CUDA(cudaMemcpyAsync(P_.trace, trace_host, n_trace * 8, cudaMemcpyHostToDevice, stream()));

@@ -745,6 +745,7 @@ class MemoryModel {  // adapter::memory::Memory with dense address-indexed stora
         Word4 prev_val, value;
     };
     Arg push(u32 address, Word4 value, u32 clock) {
+        if (address >= (1u << 28)) throw std::runtime_error("adapter: memory address outside the 2^28-cell address space");  // TREE_HEIGHT 30, 4 words per cell
         if (address >= final_.size()) {
             final_.resize(address + 1);
             initial.resize(address + 1);

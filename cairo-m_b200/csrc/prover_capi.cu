@@ -389,6 +389,13 @@ static int adapter_finish(cm31_adapter_logs& logs, cm31_prover_input** out) {
         std::vector<Word4> preloaded(n_initial);
         memcpy(preloaded.data(), logs.initial_memory, n_initial * 16);
         MemoryModel memory(preloaded);
+        // the memory commitment is a depth-30 tree over 4 words per cell: addresses live below 2^28 (adapter/merkle.rs
+        // TREE_HEIGHT).  The cells come back in ascending address order, so the last one is the largest: a stray address in
+        // the runner's log is refused here instead of sizing the dense cell tables by it (2 x 2^31 x 28 bytes).
+        if (counts[66] != 0 && cells[10 * (counts[66] - 1)] >= (1u << 28)) {
+            set_error("cm31: adapter: memory address outside the 2^28-cell address space (VmImportError)");
+            return -1;
+        }
         for (size_t c = 0; c < counts[66]; c++) {
             const uint32_t* w = &cells[10 * c];
             uint32_t a = w[0];

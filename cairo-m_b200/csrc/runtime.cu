@@ -169,8 +169,16 @@ int cm31_device_count(int* out) {
     CM_CUDA(cudaGetDeviceCount(out));
     return 0;
 }
+// The runtime state of this library (streams, staging rings, lane events, the sharding arena) belongs to ONE device and ONE
+// host thread per process -- the deployment model is one process per GPU (SURVEY.md §8b "Threading", §8e).  The device is
+// fixed by the first call that touches it; asking for another one afterwards is refused instead of leaving kernel-argument
+// tables in the first device's memory.
+static int g_bound_device = -1;
 int cm31_set_device(int ordinal) {
+    CM_REQUIRE(g_bound_device < 0 || g_bound_device == ordinal || g_stage == nullptr,
+               "set_device: this process already runs on another device (one process per GPU; the staging rings live on the first device)");
     CM_CUDA(cudaSetDevice(ordinal));
+    g_bound_device = ordinal;
     return 0;
 }
 int cm31_set_stream(void* s) {

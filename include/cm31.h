@@ -33,6 +33,9 @@ extern "C" {
 /* ------------------------------------------------------------------ runtime / buffers */
 const char* cm31_last_error(void);
 int cm31_device_count(int* out);
+/* One process drives ONE device from ONE host thread (the reference calls its backend ops sequentially from one thread,
+ * SURVEY.md §8b): the library's streams, staging rings and arenas are process-wide.  The device is bound by the first call
+ * that uses it; cm31_set_device with another ordinal afterwards returns an error. */
 int cm31_set_device(int ordinal);
 int cm31_set_stream(void* cuda_stream); /* cudaStream_t; NULL = legacy default stream */
 int cm31_sync(void);

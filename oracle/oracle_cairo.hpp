@@ -143,7 +143,7 @@ struct OracleAirImpl {
     static void check_lookups() {}  // emit_lookups throws on the spot
 };
 
-inline QM31 logup_residual(const cm31::CairoProof& proof, const cm31::ProverInput& input);
+inline QM31 logup_residual(const cm31::CairoProof& proof, const cm31::ProverInput& input, const cm31::PcsConfig* verifier_config = nullptr);
 
 // verify_cairo_m (verifier.rs:17-95), closing logup-sum check included (verifier.rs:84-92: InvalidLogupSum).
 inline void verify_cairo_m(const cm31::CairoProof& proof, cm31::PcsConfig pcs_config) {
@@ -217,17 +217,26 @@ inline void verify_cairo_m(const cm31::CairoProof& proof, cm31::PcsConfig pcs_co
     cm31::TraceLocationAllocator alloc(cm31::cairo_preprocessed_ids());
     components.allocate(alloc);
     verify(components.provers(), channel, cs, proof.stark_proof);
-    if (!(logup_residual(proof, cm31::ProverInput()) == QM31::zero())) throw VerificationError("InvalidLogupSum");
+    // the closing logup check replays the transcript: it must run under the VERIFIER's parameters, never under the ones the
+    // (attacker-supplied) proof carries -- a proof whose embedded config differs from the expected one is rejected outright
+    {
+        const cm31::PcsConfig& pc = proof.stark_proof.config;
+        if (pc.pow_bits != pcs_config.pow_bits || pc.fri_config.log_blowup_factor != pcs_config.fri_config.log_blowup_factor ||
+            pc.fri_config.n_queries != pcs_config.fri_config.n_queries ||
+            pc.fri_config.log_last_layer_degree_bound != pcs_config.fri_config.log_last_layer_degree_bound)
+            throw VerificationError("proof was made under a different PcsConfig");
+    }
+    if (!(logup_residual(proof, cm31::ProverInput(), &pcs_config) == QM31::zero())) throw VerificationError("InvalidLogupSum");
 }
 
 // Logup balance (InteractionClaim::claimed_sum, components/mod.rs:288-302 + public_data.rs:287-399):
 //   Σ claimed sums + public-data sum == 0.
 // Every relation must balance exactly (the Merkle / Poseidon2 relations through the merkle and poseidon2 components,
 // under the Poseidon2 tables of csrc/cairo/poseidon2_constants.hpp, pinned by the reference KAT).
-inline QM31 logup_residual(const cm31::CairoProof& proof, const cm31::ProverInput& input) {
-    // replay the transcript up to Relations::draw
+inline QM31 logup_residual(const cm31::CairoProof& proof, const cm31::ProverInput& input, const cm31::PcsConfig* verifier_config) {
+    // replay the transcript up to Relations::draw (under the verifier's config when one is given)
     OChannel channel;
-    cm31::PcsConfig cfg = proof.stark_proof.config;
+    cm31::PcsConfig cfg = verifier_config ? *verifier_config : proof.stark_proof.config;
     channel.mix_u64(cfg.pow_bits);
     channel.mix_u64(cfg.fri_config.log_blowup_factor);
     channel.mix_u64(cfg.fri_config.n_queries);
