@@ -7,7 +7,7 @@ LOG=${2:-22}
 shift 2
 KERNELS=${@:-fft4_pass_kernel merkle_layer_kernel merkle_multi_kernel quotients_fast_kernel k_store_fp_imm_constraints k_store_fp_imm_logup}
 mkdir -p gpurun_out
-BENCH="python bench.py --log-steps $LOG --steps 1 --warmup 0 --no-cpu-baseline"
+BENCH="python bench.py --log-steps $LOG --steps 1 --warmup 0 --no-cpu-baseline --no-adapter"
 SKIP=${SKIP:-12}    # launches of the kernel skipped before the full capture (warm-up proofs); low-launch kernels: SKIP=1
 COUNT=${COUNT:-8}
 if [ -z "$NOLIST" ]; then
