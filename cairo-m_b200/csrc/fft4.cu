@@ -65,11 +65,13 @@ __device__ __forceinline__ void bfly4(uint4& a, uint4& b, u32 t) {
 // K layers (layer0 .. layer0+K-1) on the 2^K uint4 values of one group.  Layer l pairs values
 // (j, j + 2^l); its twiddle index is (H << (K-1-l)) | (j >> (l+1)), H = index of the group in the
 // top layer of the round.
-template <bool INV, int K>
+// ZT (forward only): the round's top layer pairs a value with a coefficient that is zero by construction (the upper half of
+// a zero-padded low-degree extension), so its butterfly v0 +- t*0 is a copy: no twiddle, no multiply.
+template <bool INV, int K, bool ZT = false>
 __device__ __forceinline__ void radix_round(uint4 (&v)[1 << K], const u32* __restrict__ tree, u32 M, u32 L, u32 layer0, u32 H) {
     u32 tw[(1 << K) - 1];
 #pragma unroll
-    for (int l = 0; l < K; l++)
+    for (int l = 0; l < (ZT ? K - 1 : K); l++)
 #pragma unroll
         for (int m = 0; m < (1 << (K - 1 - l)); m++)
             tw[((1 << K) - (1 << (K - l))) + m] = fft4_twiddle(tree, M, L, layer0 + l, (H << (K - 1 - l)) | m) << 1;  // doubled
@@ -78,11 +80,16 @@ __device__ __forceinline__ void radix_round(uint4 (&v)[1 << K], const u32* __res
         const int l = INV ? ll : K - 1 - ll;
 #pragma unroll
         for (int j = 0; j < (1 << K); j++)
-            if (!(j & (1 << l))) bfly4<INV>(v[j], v[j | (1 << l)], tw[((1 << K) - (1 << (K - l))) + (j >> (l + 1))]);
+            if (!(j & (1 << l))) {
+                if (ZT && l == K - 1)
+                    v[j | (1 << l)] = v[j];
+                else
+                    bfly4<INV>(v[j], v[j | (1 << l)], tw[((1 << K) - (1 << (K - l))) + (j >> (l + 1))]);
+            }
     }
 }
 
-template <bool INV, int NL, int B, int THREADS>
+template <bool INV, int NL, int B, int THREADS, bool ZTOP = false>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) fft4_pass_kernel(const u32* const* __restrict__ src_cols, u32* const* __restrict__ dst_cols,
                                                             u32 L, u32 log_in, u32 lo, const u32* __restrict__ tree, u32 M, u32 scale,
                                                             u32 n_cols) {
@@ -151,21 +158,30 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) fft4_pass_k
                 uint4 v[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) v[j] = sm4[fft4_pad(base + (j << p))];
-                radix_round<INV, 3>(v, tree, M, L, layer0, H);
+                if (ZTOP && rr == 0)
+                    radix_round<INV, 3, true>(v, tree, M, L, layer0, H);
+                else
+                    radix_round<INV, 3, false>(v, tree, M, L, layer0, H);
 #pragma unroll
                 for (int j = 0; j < 8; j++) sm4[fft4_pad(base + (j << p))] = v[j];
             } else if (k == 2) {
                 uint4 v[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) v[j] = sm4[fft4_pad(base + (j << p))];
-                radix_round<INV, 2>(v, tree, M, L, layer0, H);
+                if (ZTOP && rr == 0)
+                    radix_round<INV, 2, true>(v, tree, M, L, layer0, H);
+                else
+                    radix_round<INV, 2, false>(v, tree, M, L, layer0, H);
 #pragma unroll
                 for (int j = 0; j < 4; j++) sm4[fft4_pad(base + (j << p))] = v[j];
             } else {
                 uint4 v[2];
 #pragma unroll
                 for (int j = 0; j < 2; j++) v[j] = sm4[fft4_pad(base + (j << p))];
-                radix_round<INV, 1>(v, tree, M, L, layer0, H);
+                if (ZTOP && rr == 0)
+                    radix_round<INV, 1, true>(v, tree, M, L, layer0, H);
+                else
+                    radix_round<INV, 1, false>(v, tree, M, L, layer0, H);
 #pragma unroll
                 for (int j = 0; j < 2; j++) sm4[fft4_pad(base + (j << p))] = v[j];
             }
@@ -210,13 +226,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) fft4_pass_k
     }
 }
 
-template <bool INV, int NL, int B, int THREADS>
+template <bool INV, int NL, int B, int THREADS, bool ZTOP = false>
 static int launch_fft4(const u32* const* src, u32* const* dst, u32 L, u32 log_in, u32 lo, const u32* tree, u32 M, u32 scale,
                        size_t n_cols, size_t n_passes) {
     constexpr u32 TL = NL + B;
     constexpr size_t TILE = (size_t)1 << TL;
     const size_t smem = (TILE + (TILE >> 3) + 1) * 16;
-    auto kern = fft4_pass_kernel<INV, NL, B, THREADS>;
+    auto kern = fft4_pass_kernel<INV, NL, B, THREADS, ZTOP>;
     static bool attr_set = false;  // one per template instantiation
     if (!attr_set) {
         CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -233,12 +249,12 @@ static int launch_fft4(const u32* const* src, u32* const* dst, u32 L, u32 log_in
 }
 
 // pass 2 of a two-pass transform: NL2 = L - NL1 layers starting at lo = NL1, tile 2^TL points
-template <bool INV, int TL, int THREADS>
+template <bool INV, int TL, int THREADS, bool ZTOP = false>
 static int launch_second(u32 nl2, const u32* const* src, u32* const* dst, u32 L, u32 log_in, u32 lo, const u32* tree, u32 M,
                          u32 scale, size_t n_cols) {
 #define CM_F4(N)                                                                                                          \
     case N:                                                                                                               \
-        if constexpr (N >= 1 && (TL == 12 ? N <= 9 : (N >= 9 && N <= 11))) return launch_fft4<INV, N, TL - N, THREADS>(src, dst, L, log_in, lo, tree, M, scale, n_cols, 2); \
+        if constexpr (N >= 1 && (TL == 12 ? N <= 9 : (N >= 9 && N <= 11))) return launch_fft4<INV, N, TL - N, THREADS, ZTOP>(src, dst, L, log_in, lo, tree, M, scale, n_cols, 2); \
         break;
     switch (nl2) {
         CM_F4(1) CM_F4(2) CM_F4(3) CM_F4(4) CM_F4(5) CM_F4(6) CM_F4(7) CM_F4(8) CM_F4(9) CM_F4(10) CM_F4(11)
@@ -261,7 +277,11 @@ int run_fft4(const u32* const* src, u32* const* dst, size_t n_cols, u32 L, u32 l
             return nl2 == 6 ? launch_fft4<INV, 6, 7, 1024>(s_, dst, L, lin, 13, tree, M, scale, n_cols, 3)
                             : launch_fft4<INV, 7, 6, 1024>(s_, dst, L, lin, 13, tree, M, scale, n_cols, 3);
         };
-        auto p3 = [&](const u32* const* s_, u32 lin, u32 scale) { return launch_fft4<INV, 6, 7, 1024>(s_, dst, L, lin, 13 + nl2, tree, M, scale, n_cols, 3); };
+        auto p3 = [&](const u32* const* s_, u32 lin, u32 scale) {
+            if constexpr (!INV)
+                if (lin < L) return launch_fft4<INV, 6, 7, 1024, true>(s_, dst, L, lin, 13 + nl2, tree, M, scale, n_cols, 3);
+            return launch_fft4<INV, 6, 7, 1024>(s_, dst, L, lin, 13 + nl2, tree, M, scale, n_cols, 3);
+        };
         const u32* const* d = (const u32* const*)dst;
         if (INV) {
             if (int e = p1(src, log_in, 1)) return e;
@@ -272,7 +292,11 @@ int run_fft4(const u32* const* src, u32* const* dst, size_t n_cols, u32 L, u32 l
         if (int e = p2(d, L, 1)) return e;
         return p1(d, L, 1);
     }
-    if (L == 12) return launch_fft4<INV, 12, 0, 512>(src, dst, L, log_in, 0, tree, M, scale_last, n_cols, 1);
+    if (L == 12) {
+        if constexpr (!INV)
+            if (log_in < L) return launch_fft4<INV, 12, 0, 512, true>(src, dst, L, log_in, 0, tree, M, scale_last, n_cols, 1);
+        return launch_fft4<INV, 12, 0, 512>(src, dst, L, log_in, 0, tree, M, scale_last, n_cols, 1);
+    }
     // two passes: the contiguous one covers layers [0, NL1), the strided one [NL1, L)
     const bool big = L > 21;  // second pass would fall below 32-byte runs with 2^12-point tiles
     const u32 nl1 = big ? 13 : 12;
@@ -284,6 +308,10 @@ int run_fft4(const u32* const* src, u32* const* dst, size_t n_cols, u32 L, u32 l
                    : launch_fft4<INV, 12, 0, 512>(s, dst, L, lin, 0, tree, M, scale, n_cols, 2);
     };
     auto second = [&](const u32* const* s, u32 lin, u32 scale) {
+        if constexpr (!INV)
+            if (lin < L)  // low-degree extension: the upper half of the coefficients is zero padding, the top layer is a copy
+                return big ? launch_second<INV, 13, 1024, true>(nl2, s, dst, L, lin, nl1, tree, M, scale, n_cols)
+                           : launch_second<INV, 12, 512, true>(nl2, s, dst, L, lin, nl1, tree, M, scale, n_cols);
         return big ? launch_second<INV, 13, 1024>(nl2, s, dst, L, lin, nl1, tree, M, scale, n_cols)
                    : launch_second<INV, 12, 512>(nl2, s, dst, L, lin, nl1, tree, M, scale, n_cols);
     };

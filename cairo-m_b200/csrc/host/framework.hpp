@@ -207,12 +207,26 @@ class FrameworkComponent : public ComponentProver<B> {
     MaskPoints mask_points(SecurePoint point) const override {
         CirclePointM31 trace_step = CanonicCoset(log_size()).step();
         MaskPoints out(3);
-        for (int t = 1; t < 3; t++)
+        // offset 0 is the point itself; the few other offsets (-1 for the logup cumulative sums) are shifted once per
+        // component, not once per column (this runs on the critical path between the composition root and the OODS launch)
+        std::vector<std::pair<int, SecurePoint>> shifted;
+        auto at = [&](int off) -> const SecurePoint& {
+            if (off == 0) return point;
+            for (auto& kv : shifted)
+                if (kv.first == off) return kv.second;
+            shifted.emplace_back(off, secure_point_add_m31(point, cp_mul_signed(trace_step, off)));
+            return shifted.back().second;
+        };
+        shifted.reserve(8);
+        for (int t = 1; t < 3; t++) {
+            out[t].reserve(ev.mask_offsets[t].size());
             for (auto& offsets : ev.mask_offsets[t]) {
-                std::vector<SecurePoint> pts;
-                for (int off : offsets) pts.push_back(secure_point_add_m31(point, cp_mul_signed(trace_step, off)));
-                out[t].push_back(pts);
+                out[t].emplace_back();
+                std::vector<SecurePoint>& pts = out[t].back();
+                pts.reserve(offsets.size());
+                for (int off : offsets) pts.push_back(at(off));
             }
+        }
         return out;
     }
     std::vector<size_t> preprocessed_column_indices() const override { return preprocessed_indices; }

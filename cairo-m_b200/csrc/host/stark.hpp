@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <array>
 #include <functional>
+#include <iterator>
 #include <map>
 #include <memory>
 #include <numeric>
@@ -286,6 +287,11 @@ struct GatherQueue {
     std::vector<u32> src_id, word, out_off, cnt;  // per run request: cnt[k] words land at results[out_off[k]..]
     std::vector<u32> results;
     size_t n_words = 0;
+    GatherQueue() {  // a proof records ~50k run requests: no regrowth on the critical path after the proof-of-work nonce
+        for (auto* v : {&src_id, &word, &out_off, &cnt}) v->reserve(1u << 16);
+        srcs.reserve(8192);
+        src_index.reserve(8192);
+    }
     u32 source(const u32* base) {
         auto it = src_index.find(base);
         if (it != src_index.end()) return it->second;
@@ -930,19 +936,24 @@ CommitmentSchemeProof CommitmentSchemeProver<B>::prove_values(const std::vector<
     std::vector<std::vector<PointSample>> samples_flat;
     std::vector<QM31> sampled_flat;
     size_t vi = 0;
+    size_t n_cols_total = 0;
+    for (auto& t : trees) n_cols_total += t.polynomials.size();
+    samples_flat.reserve(n_cols_total);
+    sampled_flat.reserve(values.size());
     for (size_t t = 0; t < trees.size(); t++) {
         proof.sampled_values.emplace_back();
+        proof.sampled_values.back().reserve(trees[t].polynomials.size());
         for (size_t c = 0; c < trees[t].polynomials.size(); c++) {
-            std::vector<QM31> col_vals;
-            std::vector<PointSample> col_samples;
+            const size_t k = sampled_points[t][c].size();
+            proof.sampled_values.back().emplace_back(values.begin() + vi, values.begin() + vi + k);
+            samples_flat.emplace_back();
+            std::vector<PointSample>& col_samples = samples_flat.back();
+            col_samples.reserve(k);
             for (const SecurePoint& p : sampled_points[t][c]) {
-                col_vals.push_back(values[vi]);
                 col_samples.push_back(PointSample{p, values[vi]});
                 sampled_flat.push_back(values[vi]);
                 vi++;
             }
-            proof.sampled_values.back().push_back(col_vals);
-            samples_flat.push_back(col_samples);
         }
     }
     channel.mix_felts(sampled_flat);
@@ -1089,7 +1100,8 @@ struct ComponentProvers {  // air/components.rs
         for (auto* c : components) {
             MaskPoints mp = c->mask_points(point);
             if (out.size() < mp.size()) out.resize(mp.size());
-            for (size_t t = 0; t < mp.size(); t++) out[t].insert(out[t].end(), mp[t].begin(), mp[t].end());
+            for (size_t t = 0; t < mp.size(); t++)
+                out[t].insert(out[t].end(), std::make_move_iterator(mp[t].begin()), std::make_move_iterator(mp[t].end()));
         }
         out[PREPROCESSED_TRACE_IDX_()].assign(n_preprocessed_columns, {});
         for (auto* c : components)

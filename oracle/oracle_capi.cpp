@@ -262,6 +262,7 @@ int orc_program_prove(u32 program_id, u32 n, u32 pow_bits, u32 n_queries, uint8_
             timings_ms[3] = t.stark_ms;
             timings_ms[4] = t.total_ms;
         }
+        cm31::HostTimer::report();  // CM31_HOST_TIMING=1: host-side sections of the shared protocol driver
         return copy_out(proof.to_bytes(), out, cap, out_len);
     } catch (const std::exception& e) {
         g_orc_err = e.what();

@@ -193,6 +193,11 @@ def test_fib_2_22_steps_headline_size_verifies(cm, extra):
     assert ch.oracle_cairo_verify(got) == 0, ch.orc.last_error()
     residual, _ = ch.oracle_logup_residual(n, got)
     assert residual == (0, 0, 0, 0)
+    if extra == 0:
+        # ... and BYTE-IDENTICAL to the oracle prover's proof at the headline size itself (the OpenMP oracle needs ~20 s
+        # of host time for 2^22 steps -- the same proof `bench.py --impl reference` times)
+        want, _ = ch.oracle_fib_prove(n)
+        assert got == want
 
 
 @pytest.mark.parametrize("what", ["clock_delta", "after_valid_proof"])
