@@ -447,7 +447,12 @@ struct VmTrace {
 };
 
 // Runs `program` with one felt argument: frame = [arg, ret slot, old fp, return pc], fp after it.
-inline VmTrace run_program(const std::vector<Word4>& program, u32 arg, size_t max_steps = (size_t)1 << 30) {
+// `segments` + `segment_steps`: continuation segments as the reference runner cuts them (crates/runner/src/vm/mod.rs:158-285,
+// RunnerOptions::max_steps): a segment ends once its trace holds `segment_steps` states, gets the current state appended as
+// its final entry, and the next segment starts from that state with the whole memory image as its initial memory (clocks
+// restart).  The segments before the last one are appended to *segments; the last one is the return value.
+inline VmTrace run_program(const std::vector<Word4>& program, u32 arg, size_t max_steps = (size_t)1 << 30,
+                           std::vector<VmTrace>* segments = nullptr, size_t segment_steps = 0) {
     VmTrace out;
     u32 prog_len = (u32)program.size();
     std::vector<Word4> mem(program);
@@ -482,6 +487,14 @@ inline VmTrace run_program(const std::vector<Word4>& program, u32 arg, size_t ma
     size_t steps = 0;
     while (pc != prog_len) {
         if (steps++ >= max_steps) throw std::runtime_error("vm: step limit reached");
+        if (segments && segment_steps && out.trace.size() >= segment_steps) {  // ExecutionStatus::Ongoing -> finalize_segment(false)
+            out.trace.push_back(Registers{pc, fp});
+            VmTrace next;
+            next.public_ranges = out.public_ranges;
+            next.initial_memory = mem;
+            segments->push_back(std::move(out));
+            out = std::move(next);
+        }
         out.trace.push_back(Registers{pc, fp});
         if (pc >= prog_len) throw std::runtime_error("vm: pc outside the program");
         Word4 ins = mem[pc];

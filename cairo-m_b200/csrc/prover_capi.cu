@@ -309,6 +309,49 @@ int cm31_test_vm_trace_destroy(cm31_test_vm_trace* h) {
     delete h;
     return 0;
 }
+// Continuation segments (crates/runner/src/vm/mod.rs:158-285): the run of a built-in program cut every `segment_steps` steps,
+// as RunnerOptions::max_steps cuts it; returns segment `index` (its own trace, memory log and initial-memory image) and the
+// number of segments.  The reference chains the proofs of consecutive segments by their memory roots
+// (crates/prover/tests/prover.rs:204-243).
+int cm31_test_vm_segment_create(uint32_t program_id, uint32_t n, uint64_t segment_steps, uint32_t index, uint32_t* n_segments,
+                                cm31_test_vm_trace** out) {
+    try {
+        CM_REQUIRE(out != nullptr && segment_steps > 0, "vm_segment_create: bad arguments");
+        std::vector<VmTrace> segs;
+        VmTrace last = run_program(program_by_id(program_id), n, (size_t)1 << 30, &segs, (size_t)segment_steps);
+        segs.push_back(std::move(last));
+        if (n_segments) *n_segments = (uint32_t)segs.size();
+        CM_REQUIRE(index < segs.size(), "vm_segment_create: no such segment");
+        std::unique_ptr<cm31_test_vm_trace> h(new cm31_test_vm_trace());
+        h->vm = std::move(segs[index]);
+        h->trace_words.reserve(h->vm.trace.size() * 2);
+        for (const Registers& r : h->vm.trace) {
+            h->trace_words.push_back(r.fp);
+            h->trace_words.push_back(r.pc);
+        }
+        *out = h.release();
+        return 0;
+    } catch (const std::exception& e) {
+        set_error(e.what());
+        return -2;
+    }
+}
+// The host adapter (csrc/cairo/vm.hpp::import_from_vm, the restatement of import_from_runner_output) on a given runner output.
+int cm31_test_vm_trace_to_input(const cm31_test_vm_trace* t, cm31_prover_input** out) {
+    try {
+        CM_REQUIRE(t != nullptr && out != nullptr, "vm_trace_to_input: null argument");
+        cm31_prover_input* h = new cm31_prover_input();
+        h->input = import_from_vm(t->vm);
+        h->return_value = t->vm.return_value;
+        pin_range(h, h->input.data_accesses.data(), h->input.data_accesses.size() * sizeof(DataAccess));
+        for (auto& kv : h->input.states_by_opcodes) pin_range(h, kv.second.data(), kv.second.size() * sizeof(Bundle));
+        *out = h;
+        return 0;
+    } catch (const std::exception& e) {
+        set_error(e.what());
+        return -2;
+    }
+}
 
 // Reads one table of the input resident in HBM back to the host (parity tests compare the host adapter's upload with the
 // device adapter's output word for word).  table 0 = data-access log, 1..26 = opcode components (CM31_OPCODE_EVALS order),

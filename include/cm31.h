@@ -430,6 +430,13 @@ int cm31_test_vm_trace_info(const cm31_test_vm_trace* h, uint64_t info[4]);
 int cm31_test_vm_trace_data(const cm31_test_vm_trace* h, const uint32_t** trace, const uint32_t** memory_trace,
                             const uint32_t** initial_memory, uint32_t public_ranges[6]);
 int cm31_test_vm_trace_destroy(cm31_test_vm_trace* h);
+/* Continuation segments: the same run cut every `segment_steps` steps as RunnerOptions::max_steps cuts it
+ * (R/crates/runner/src/vm/mod.rs:158-285); segment `index` as a runner output of its own, *n_segments = how many there are.
+ * The reference chains consecutive segment proofs by their memory roots (P/tests/prover.rs:204-243). */
+int cm31_test_vm_segment_create(uint32_t program_id, uint32_t n, uint64_t segment_steps, uint32_t index, uint32_t* n_segments,
+                                cm31_test_vm_trace** out);
+/* the host restatement of import_from_runner_output (csrc/cairo/vm.hpp) on a given runner output */
+int cm31_test_vm_trace_to_input(const cm31_test_vm_trace* t, cm31_prover_input** out);
 /* S/examples/src/wide_fibonacci/mod.rs:22-43 — the bring-up AIR (parity tests only) */
 int cm31_test_prove_wide_fibonacci(uint32_t log_n_rows, uint32_t n_cols, uint32_t pow_bits, uint32_t n_queries,
                                    uint8_t* proof_out, size_t proof_cap, size_t* proof_len);

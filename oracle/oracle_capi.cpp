@@ -270,6 +270,27 @@ int orc_program_prove(u32 program_id, u32 n, u32 pow_bits, u32 n_queries, uint8_
     }
 }
 
+// One continuation segment (crates/runner/src/vm/mod.rs:158-285) proven on the oracle backend; *n_segments = segments of the run.
+int orc_segment_prove(u32 program_id, u32 n, u64 segment_steps, u32 index, u32* n_segments, u32 pow_bits, u32 n_queries, uint8_t* out,
+                      size_t cap, size_t* out_len) {
+    try {
+        std::vector<cm31::VmTrace> segs;
+        cm31::VmTrace last = cm31::run_program(cm31::program_by_id(program_id), n, (size_t)1 << 30, &segs, (size_t)segment_steps);
+        segs.push_back(std::move(last));
+        if (n_segments) *n_segments = (u32)segs.size();
+        if (index >= segs.size()) throw std::runtime_error("no such segment");
+        cm31::ProverInput input = cm31::import_from_vm(segs[index]);
+        cm31::PcsConfig cfg = cm31::PcsConfig::regular_96_bits();
+        cfg.pow_bits = pow_bits;
+        cfg.fri_config.n_queries = n_queries;
+        cm31::CairoProof proof = cm31::prove_cairo_m<OracleAirImpl>(input, cfg, nullptr);
+        return copy_out(proof.to_bytes(), out, cap, out_len);
+    } catch (const std::exception& e) {
+        g_orc_err = e.what();
+        return -2;
+    }
+}
+
 int orc_cairo_verify(const uint8_t* proof_bytes, size_t len, u32 pow_bits, u32 n_queries) {
     try {
         cm31::CairoProof proof = cm31::CairoProof::from_bytes(proof_bytes, len, cm31::cairo_component_names());
