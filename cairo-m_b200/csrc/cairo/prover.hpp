@@ -274,6 +274,7 @@ struct StagedInput {
     std::vector<Rows> opcode;  // one per opcode component, CM31_OPCODE_EVALS order
     Rows memory, merkle, clock_update, poseidon2;
     size_t bytes = 0;  // total bytes staged
+    uint64_t bg_ticket = 0;  // deferred staging (cm31_bg_defer): the copies are issued by cm31_bg_release(bg_ticket) at the latest
 };
 
 // The O(memory footprint) tables of a prover input: boundary-memory rows, Merkle nodes and the Poseidon2 states derived from
@@ -394,6 +395,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     struct ShardEnd {
         ~ShardEnd() { B::shard_end_proof(); }
     } shard_end;
+    Impl::staging_release_point(0);  // a prefetch recorded for the NEXT segment starts to travel (throttled) under this proof
     Blake2sChannel channel;
     pcs_config.mix_into(channel);
 
@@ -560,6 +562,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     }
     // Tree 1 borrows the trace columns (out-of-place interpolation): the interaction trace needs the
     // trace-domain values again for the logup programs.
+    Impl::staging_release_point(1);  // the next segment's input may start to travel now: long FFT / Merkle kernels follow
     {
         std::vector<const CircleEvaluation<B>*> all;
         for (auto& comp : traces)
@@ -601,6 +604,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         components.for_each([&](auto& comp) { proof.interaction_claim.claimed_sums.push_back(comp.claimed_sum); });
         for (auto& s : proof.interaction_claim.claimed_sums) channel.mix_felts({s});  // InteractionClaim::mix_into
         traces.clear();
+        Impl::staging_release_point(2);
         commitment_scheme.commit_evals(std::move(interaction), channel);
     }
     auto t3 = Impl::now_ms();
@@ -608,6 +612,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     // ---- STARK (prover.rs:104-131)
     TraceLocationAllocator alloc(cairo_preprocessed_ids());
     components.allocate(alloc);
+    Impl::staging_release_point(3);
     proof.stark_proof = prove<B>(components.provers(), channel, commitment_scheme);
     auto t4 = Impl::now_ms();
     if (timings) {

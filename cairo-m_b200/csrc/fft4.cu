@@ -65,16 +65,30 @@ __device__ __forceinline__ void bfly4(uint4& a, uint4& b, u32 t) {
 // K layers (layer0 .. layer0+K-1) on the 2^K uint4 values of one group.  Layer l pairs values
 // (j, j + 2^l); its twiddle index is (H << (K-1-l)) | (j >> (l+1)), H = index of the group in the
 // top layer of the round.
+// The doubled twiddles of the whole tile are staged in shared memory once, next to the tile (tws): layer li of the pass
+// (li = 0 .. NL-1) owns 2^(NL-1-li) entries at offset 2^NL - 2^(NL-li), indexed by the tile-local group number.  A radix-8
+// round then reads its 4 + 2 + 1 twiddles as one LDS.128, one LDS.64 and one LDS.32 (shared-memory latency, broadcast inside a
+// warp) instead of 7 global loads whose L2 latency every warp of the CTA paid right after each barrier.
 // ZT (forward only): the round's top layer pairs a value with a coefficient that is zero by construction (the upper half of
 // a zero-padded low-degree extension), so its butterfly v0 +- t*0 is a copy: no twiddle, no multiply.
 template <bool INV, int K, bool ZT = false>
-__device__ __forceinline__ void radix_round(uint4 (&v)[1 << K], const u32* __restrict__ tree, u32 M, u32 L, u32 layer0, u32 H) {
+__device__ __forceinline__ void radix_round(uint4 (&v)[1 << K], const u32* __restrict__ tws, u32 NLr, u32 high) {
+    // tws: first entry of the round's lowest layer; NLr = layers of the pass at and above it (NL - 3r): layer l of the round
+    // starts 2^NLr - 2^(NLr-l) entries further
     u32 tw[(1 << K) - 1];
-#pragma unroll
-    for (int l = 0; l < (ZT ? K - 1 : K); l++)
-#pragma unroll
-        for (int m = 0; m < (1 << (K - 1 - l)); m++)
-            tw[((1 << K) - (1 << (K - l))) + m] = fft4_twiddle(tree, M, L, layer0 + l, (H << (K - 1 - l)) | m) << 1;  // doubled
+    if (K == 3) {
+        const uint4 t0 = *reinterpret_cast<const uint4*>(tws + 4 * high);
+        tw[0] = t0.x; tw[1] = t0.y; tw[2] = t0.z; tw[3] = t0.w;
+        const uint2 t1 = *reinterpret_cast<const uint2*>(tws + ((1u << NLr) - (1u << (NLr - 1))) + 2 * high);
+        tw[4] = t1.x; tw[5] = t1.y;
+        if (!ZT) tw[6] = tws[((1u << NLr) - (1u << (NLr - 2))) + high];
+    } else if (K == 2) {
+        const uint2 t0 = *reinterpret_cast<const uint2*>(tws + 2 * high);
+        tw[0] = t0.x; tw[1] = t0.y;
+        if (!ZT) tw[2] = tws[((1u << NLr) - (1u << (NLr - 1))) + high];
+    } else {
+        if (!ZT) tw[0] = tws[high];
+    }
 #pragma unroll
     for (int ll = 0; ll < K; ll++) {
         const int l = INV ? ll : K - 1 - ll;
@@ -117,6 +131,15 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) fft4_pass_k
     const u32 n_in = 1u << log_in;
     const size_t gbase = ((size_t)hi << (lo + NL)) | ((size_t)lo_hi << B);
 
+    // ---- twiddles of the tile (all NL layers), doubled: entry e of layer li = tree twiddle (hi << (NL-1-li)) | e
+    u32* tws = reinterpret_cast<u32*>(sm4 + (TILE + (TILE >> 3) + 1));
+    for (u32 e = tid; e < (1u << NL) - 1; e += THREADS) {
+        const u32 hb = 31 - __clz((1u << NL) - 1 - e);  // = NL - 1 - li
+        const u32 li = NL - 1 - hb;
+        const u32 idx = e - ((1u << NL) - (2u << hb));
+        tws[e] = fft4_twiddle(tree, M, L, lo + li, (hi << hb) | idx) << 1;
+    }
+
     // ---- load: tile point s of the 4 columns -> one uint4
     if (B == 0) {
         // contiguous tile: 128-bit loads along each column, 4x4 transpose in registers
@@ -147,21 +170,19 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) fft4_pass_k
         const int p = B + 3 * r;
         const int k = (NL - 3 * r) < 3 ? (NL - 3 * r) : 3;
         const u32 groups = TILE >> k;
-        const u32 hshift = NL - 3 * r - k;
-        const u32 layer0 = lo + 3 * r;
+        const u32* tws_r = tws + ((1u << NL) - (1u << (NL - 3 * r)));  // first twiddle of layer 3r of the pass
         for (u32 q = tid; q < groups; q += THREADS) {
             const u32 low = q & ((1u << p) - 1);
             const u32 high = q >> p;
             const u32 base = (high << (p + k)) | low;
-            const u32 H = (hi << hshift) | high;
             if (k == 3) {
                 uint4 v[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) v[j] = sm4[fft4_pad(base + (j << p))];
                 if (ZTOP && rr == 0)
-                    radix_round<INV, 3, true>(v, tree, M, L, layer0, H);
+                    radix_round<INV, 3, true>(v, tws_r, NL - 3 * r, high);
                 else
-                    radix_round<INV, 3, false>(v, tree, M, L, layer0, H);
+                    radix_round<INV, 3, false>(v, tws_r, NL - 3 * r, high);
 #pragma unroll
                 for (int j = 0; j < 8; j++) sm4[fft4_pad(base + (j << p))] = v[j];
             } else if (k == 2) {
@@ -169,9 +190,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) fft4_pass_k
 #pragma unroll
                 for (int j = 0; j < 4; j++) v[j] = sm4[fft4_pad(base + (j << p))];
                 if (ZTOP && rr == 0)
-                    radix_round<INV, 2, true>(v, tree, M, L, layer0, H);
+                    radix_round<INV, 2, true>(v, tws_r, NL - 3 * r, high);
                 else
-                    radix_round<INV, 2, false>(v, tree, M, L, layer0, H);
+                    radix_round<INV, 2, false>(v, tws_r, NL - 3 * r, high);
 #pragma unroll
                 for (int j = 0; j < 4; j++) sm4[fft4_pad(base + (j << p))] = v[j];
             } else {
@@ -179,9 +200,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) fft4_pass_k
 #pragma unroll
                 for (int j = 0; j < 2; j++) v[j] = sm4[fft4_pad(base + (j << p))];
                 if (ZTOP && rr == 0)
-                    radix_round<INV, 1, true>(v, tree, M, L, layer0, H);
+                    radix_round<INV, 1, true>(v, tws_r, NL - 3 * r, high);
                 else
-                    radix_round<INV, 1, false>(v, tree, M, L, layer0, H);
+                    radix_round<INV, 1, false>(v, tws_r, NL - 3 * r, high);
 #pragma unroll
                 for (int j = 0; j < 2; j++) sm4[fft4_pad(base + (j << p))] = v[j];
             }
@@ -231,7 +252,7 @@ static int launch_fft4(const u32* const* src, u32* const* dst, u32 L, u32 log_in
                        size_t n_cols, size_t n_passes) {
     constexpr u32 TL = NL + B;
     constexpr size_t TILE = (size_t)1 << TL;
-    const size_t smem = (TILE + (TILE >> 3) + 1) * 16;
+    const size_t smem = (TILE + (TILE >> 3) + 1) * 16 + ((size_t)4 << NL);  // tile (padded) + the tile's twiddles
     auto kern = fft4_pass_kernel<INV, NL, B, THREADS, ZTOP>;
     static bool attr_set = false;  // one per template instantiation
     if (!attr_set) {

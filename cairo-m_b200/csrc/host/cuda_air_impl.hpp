@@ -58,6 +58,23 @@ struct CudaAirImpl {
         return m;
     }
     static void staging_wait(u32 mark) { cm_check(cm31_bg_wait(mark)); }
+    // Where a running proof lets the deferred bulk copy of the NEXT input start (cm31_bg_defer / cm31_bg_release), and how:
+    // point 0 = at its own start, 1 = before the commitment of the execution traces, 2 = before the commitment of the
+    // interaction traces, 3 = before the STARK phase (default), -1 = copies are never deferred (cm31_input_prefetch issues
+    // them); CM31_PREFETCH_CTAS = CTAs of the throttled copy kernel (default 16, 0 = copy-engine DMA).
+    // Same-box A/B, 2^22-step proofs, device-resident step 22.3 ms: DMA at prefetch time 25.9 ms per end-to-end step, DMA
+    // deferred to the STARK phase 25.3, 16-CTA copy from the proof's start 24.5, 12-CTA 24.3, 16-CTA from the STARK phase 24.1.
+    static int prefetch_point() {
+        static const int at = getenv("CM31_PREFETCH_AT") ? atoi(getenv("CM31_PREFETCH_AT")) : 3;
+        return at;
+    }
+    static int prefetch_ctas() {
+        static const int n = getenv("CM31_PREFETCH_CTAS") ? atoi(getenv("CM31_PREFETCH_CTAS")) : 16;
+        return n;
+    }
+    static void staging_release_point(int point) {
+        if (point == prefetch_point()) cm_check(cm31_bg_release_throttled(0, prefetch_ctas()));
+    }
     // The AoS -> SoA unpack of a component's bundles is issued by write_trace, which knows the component's trace program and
     // therefore how many of the 8 access slots it reads: the columns of the other slots are allocated (fixed column indices)
     // but never written — for store_fp_imm (2 accesses) 18 columns instead of 42.

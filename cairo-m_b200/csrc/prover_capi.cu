@@ -53,7 +53,14 @@ struct cm31_prover_input {
     std::vector<uint64_t> desc_start;
     bool device_adapted = false;  // cm31_adapter_import: the per-step tables exist in HBM only (`staged`), not in `input`
     uint64_t adapted_info[2] = {0, 0};  // data accesses, bytes of runner logs uploaded
+    // prefetches that were recorded but never released (deferred staging) must not be issued into freed buffers
+    void drop_prefetched() {
+        for (auto& st : prefetched)
+            if (st && st->bg_ticket) cm31_bg_cancel(st->bg_ticket);
+        prefetched.clear();
+    }
     ~cm31_prover_input() {
+        drop_prefetched();
         for (void* p : pinned) cudaHostUnregister(p);
     }
 };
@@ -97,7 +104,7 @@ int cm31_test_input_tamper(cm31_prover_input* h, uint32_t kind) {
     CM_REQUIRE(h != nullptr, "input_tamper: null handle");
     CM_REQUIRE(!h->device_adapted, "input_tamper: not available on a device-adapted input");
     h->staged.reset();
-    h->prefetched.clear();
+    h->drop_prefetched();
     auto it = h->input.states_by_opcodes.find(kind == 0 ? OP_STORE_ADD_FP_FP : OP_STORE_SUB_FP_FP);
     CM_REQUIRE(it != h->input.states_by_opcodes.end() && !it->second.empty(), "input_tamper: the program has no such step");
     const Bundle& b = it->second[it->second.size() / 2];
@@ -127,7 +134,7 @@ int cm31_input_release_device(cm31_prover_input* h) {
     CM_REQUIRE(h != nullptr, "input_release_device: null handle");
     CM_REQUIRE(!h->device_adapted, "input_release_device: a device-adapted input has no host copy to fall back to");
     h->staged.reset();
-    h->prefetched.clear();
+    h->drop_prefetched();
     h->spare.reset();
     return 0;
 }
@@ -138,7 +145,19 @@ int cm31_input_prefetch(cm31_prover_input* h) {
         CM_REQUIRE(h->prefetched.size() < 4, "input_prefetch: too many uploads in flight");
         static const bool slots = getenv("CM31_NO_INPUT_SLOTS") == nullptr;
         std::unique_ptr<StagedInput<CudaAirImpl>> spare = std::move(h->spare);
-        h->prefetched.emplace_back(new StagedInput<CudaAirImpl>(stage_input<CudaAirImpl>(h->input, slots ? spare.get() : nullptr)));
+        // The bulk copies are recorded, not issued: a proof that is running (or about to run) releases them where it is not
+        // launch-bound (CudaAirImpl::staging_release_point), the consumer releases them at the latest.
+        uint64_t ticket = 0;
+        const bool defer = CudaAirImpl::prefetch_point() >= 0;
+        if (defer) cm_check(cm31_bg_defer(1, &ticket));
+        try {
+            h->prefetched.emplace_back(new StagedInput<CudaAirImpl>(stage_input<CudaAirImpl>(h->input, slots ? spare.get() : nullptr)));
+        } catch (...) {
+            if (defer) cm31_bg_defer(0, nullptr);
+            throw;
+        }
+        h->prefetched.back()->bg_ticket = ticket;
+        if (defer) cm_check(cm31_bg_defer(0, nullptr));
         return 0;
     } catch (const std::exception& e) {
         set_error(e.what());
@@ -595,6 +614,7 @@ int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n
         if (!h->staged && !h->prefetched.empty()) {
             pre = std::move(const_cast<cm31_prover_input*>(h)->prefetched.front());
             const_cast<cm31_prover_input*>(h)->prefetched.pop_front();
+            if (pre->bg_ticket) cm_check(cm31_bg_release(pre->bg_ticket));  // its own copies, if no earlier proof released them
         }
         CairoProof proof = h->staged ? prove_cairo_m<CudaAirImpl>(h->input, *h->staged, cfg, &t)
                            : pre     ? prove_cairo_m<CudaAirImpl>(h->input, *pre, cfg, &t)

@@ -1,6 +1,7 @@
 // libcm31 runtime: errors, stream, stream-ordered device memory, gathers.
 // Replaces Column<T> storage management of the reference backends
 // (external/stwo/crates/prover/src/core/backend/mod.rs:46-65).
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 
@@ -348,7 +349,30 @@ int cm31_h2d_bg(void* dst, const void* src_host, size_t bytes) {
 }
 // Bracketed form: cm31_bg_begin orders the copy stream after the main stream ONCE (all destinations allocated before it),
 // cm31_h2d_bg_ordered then only enqueues the copy (2 driver calls fewer per copy).
+// Deferred form (cm31_bg_defer / cm31_bg_release): a prefetch of the NEXT segment's input is usually issued right before the
+// proof of the current one, and a 327 MB DMA that runs during the launch-bound start of that proof (preprocessed tree, trace
+// fill: hundreds of short kernels and small tables) delays it -- measured: preprocessed + trace phases 4.7 -> 7.7 ms while the
+// copy is in flight, the long-kernel phases unaffected.  While deferral is on, background copies and their marks are only
+// RECORDED (tagged with a ticket); the prover releases them at a point of its own choosing (before a commitment: seconds of
+// FFT / Merkle kernels, few launches), or at the latest when the input they belong to is about to be consumed.
+struct DeferredBg {
+    uint64_t ticket;
+    void* dst;
+    const void* src;
+    size_t bytes;
+    uint32_t mark;
+    bool is_mark;
+};
+static std::vector<DeferredBg> g_bg_deferred;
+static uint64_t g_bg_ticket = 0;  // 0 = not deferring
+static uint64_t g_bg_next_ticket = 1;
+int cm31_bg_defer(int on, uint64_t* ticket_out) {
+    g_bg_ticket = on ? g_bg_next_ticket++ : 0;
+    if (ticket_out) *ticket_out = g_bg_ticket;
+    return 0;
+}
 int cm31_bg_begin(void) {
+    if (g_bg_ticket) return 0;
     if (int e = ensure_copy_stream()) return e;
     CM_CUDA(cudaEventRecord(g_main_event, stream()));
     CM_CUDA(cudaStreamWaitEvent(g_copy_stream, g_main_event, 0));
@@ -356,6 +380,10 @@ int cm31_bg_begin(void) {
 }
 int cm31_h2d_bg_ordered(void* dst, const void* src_host, size_t bytes) {
     if (int e = ensure_copy_stream()) return e;
+    if (g_bg_ticket) {
+        g_bg_deferred.push_back(DeferredBg{g_bg_ticket, dst, src_host, bytes, 0, false});
+        return 0;
+    }
     CM_CUDA(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, g_copy_stream));
     return 0;
 }
@@ -369,8 +397,58 @@ int cm31_bg_mark(uint32_t* mark_out) {
     if (int e = ensure_copy_stream()) return e;
     uint32_t m = g_next_mark++ % 256;
     if (!g_marks[m]) CM_CUDA(cudaEventCreateWithFlags(&g_marks[m], cudaEventDisableTiming));
-    CM_CUDA(cudaEventRecord(g_marks[m], g_copy_stream));
     *mark_out = m;
+    if (g_bg_ticket) {
+        g_bg_deferred.push_back(DeferredBg{g_bg_ticket, nullptr, nullptr, 0, m, true});
+        return 0;
+    }
+    CM_CUDA(cudaEventRecord(g_marks[m], g_copy_stream));
+    return 0;
+}
+// Issues the recorded copies with a ticket <= upto (0 = all), oldest first, ordered after the CURRENT point of the main stream.
+// A mark must be released before anything waits on it: cm31_prove_cairo_m releases the tickets of the input it is about to
+// consume before its first cm31_bg_wait.
+int cm31_bg_cancel(uint64_t ticket) {  // the destination buffers are about to be freed: forget the recorded copies
+    g_bg_deferred.erase(std::remove_if(g_bg_deferred.begin(), g_bg_deferred.end(), [&](const DeferredBg& d) { return d.ticket == ticket; }),
+                        g_bg_deferred.end());
+    return 0;
+}
+// Throttled form of a released copy: a few CTAs read the page-locked host buffer through the unified address space, so the
+// PCIe reads in flight are bounded (16 CTAs x 256 threads x 16 B = 64 KB, ~25-30 GB/s) and the link is never saturated.  Measured
+// on a 2^22-step proof with the next segment's 327 MB travelling meanwhile: copy-engine DMA (55 GB/s for 6 ms) stretches the
+// phases it overlaps by 3.0 ms whichever phases they are; the throttled kernel copy (~13 ms long) by about 1 ms in total.
+__global__ void bg_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+static int bg_copy(void* dst, const void* src, size_t bytes, int throttle_ctas) {
+    if (throttle_ctas > 0 && bytes >= (1u << 20) && (((uintptr_t)dst | bytes) & 15) == 0) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, src) == cudaSuccess && at.devicePointer != nullptr && ((uintptr_t)at.devicePointer & 15) == 0 &&
+            (at.type == cudaMemoryTypeHost)) {
+            bg_copy_kernel<<<throttle_ctas, 256, 0, g_copy_stream>>>((uint4*)dst, (const uint4*)at.devicePointer, bytes / 16);
+            CM_LAUNCH_CHECK();
+            return 0;
+        }
+        cudaGetLastError();
+    }
+    CM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_copy_stream));
+    return 0;
+}
+int cm31_bg_release_throttled(uint64_t upto, int throttle_ctas);
+int cm31_bg_release(uint64_t upto) { return cm31_bg_release_throttled(upto, 0); }
+int cm31_bg_release_throttled(uint64_t upto, int throttle_ctas) {
+    size_t n = 0;
+    while (n < g_bg_deferred.size() && (upto == 0 || g_bg_deferred[n].ticket <= upto)) n++;
+    if (n == 0) return 0;
+    if (int e = ensure_copy_stream()) return e;
+    CM_CUDA(cudaEventRecord(g_main_event, g_main));
+    CM_CUDA(cudaStreamWaitEvent(g_copy_stream, g_main_event, 0));
+    for (size_t i = 0; i < n; i++) {
+        const DeferredBg& d = g_bg_deferred[i];
+        if (d.is_mark) CM_CUDA(cudaEventRecord(g_marks[d.mark], g_copy_stream));
+        else if (int e = bg_copy(d.dst, d.src, d.bytes, throttle_ctas)) return e;
+    }
+    g_bg_deferred.erase(g_bg_deferred.begin(), g_bg_deferred.begin() + n);
     return 0;
 }
 int cm31_bg_wait(uint32_t mark) {

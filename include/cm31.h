@@ -62,6 +62,16 @@ int cm31_bg_fence(void);
 int cm31_bg_begin(void); /* order the background stream after the current one, once, then: */
 int cm31_h2d_bg_ordered(void* dst, const void* src_host, size_t bytes);
 int cm31_bg_mark(uint32_t* mark_out);
+/* Deferred background copies: between cm31_bg_defer(1, &ticket) and cm31_bg_defer(0, NULL) the calls above are only recorded;
+ * cm31_bg_release(upto) issues the recorded ones with ticket <= upto (0 = all), ordered after the current point of the main
+ * stream.  cm31_input_prefetch uses it so that the prover itself places the bulk DMA of the next segment's input where the
+ * running proof is not launch-bound (CM31_PREFETCH_AT). */
+int cm31_bg_defer(int on, uint64_t* ticket_out);
+int cm31_bg_release(uint64_t upto);
+/* the same with the copies >= 1 MB issued as a `throttle_ctas`-CTA copy kernel over the unified address space (bounded PCIe
+ * reads in flight) when the source is page-locked; 0 = copy engine */
+int cm31_bg_release_throttled(uint64_t upto, int throttle_ctas);
+int cm31_bg_cancel(uint64_t ticket); /* forget the recorded copies of a ticket (their destinations are being freed) */
 int cm31_bg_wait(uint32_t mark);
 int cm31_d2d(void* dst, const void* src, size_t bytes);
 /* Column::at for many (column,row) pairs at once (decommit):
