@@ -562,6 +562,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     }
     // Tree 1 borrows the trace columns (out-of-place interpolation): the interaction trace needs the
     // trace-domain values again for the logup programs.
+    Impl::idle_gate_open();  // a previous proof's deferred tail (host work) runs while this commitment's kernels execute
     Impl::staging_release_point(1);  // the next segment's input may start to travel now: long FFT / Merkle kernels follow
     {
         std::vector<const CircleEvaluation<B>*> all;

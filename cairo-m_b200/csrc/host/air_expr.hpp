@@ -73,16 +73,29 @@ struct AirProgram {
     std::string cuda_body;
 };
 
-// FNV-1a over the instruction words: identifies a program independently of its parameter values
-// (all constants are read from the `consts` table at run time).
+// Hash of the instruction words: identifies a program independently of its parameter values (all constants are read from the
+// `consts` table at run time).  It is recomputed on EVERY program launch (the C ABI takes the bytecode, not a handle), on the
+// thread that issues the launches, so it must be cheap: four independent multiply-xorshift lanes over the 64-bit words
+// (~2 cycles per instruction; the byte-wise FNV-1a it replaces cost ~32, 0.25 ms per proof in the launch-bound phases).
 inline uint64_t air_code_hash(const uint64_t* code, size_t n_instr) {
-    uint64_t h = 1469598103934665603ull;
-    for (size_t i = 0; i < n_instr; i++)
-        for (int b = 0; b < 8; b++) {
-            h ^= (code[i] >> (8 * b)) & 0xff;
-            h *= 1099511628211ull;
+    const uint64_t K = 0x9E3779B97F4A7C15ull;
+    uint64_t h[4] = {0x243F6A8885A308D3ull, 0x13198A2E03707344ull, 0xA4093822299F31D0ull, 0x082EFA98EC4E6C89ull};
+    size_t i = 0;
+    for (; i + 4 <= n_instr; i += 4)
+        for (int k = 0; k < 4; k++) {
+            h[k] = (h[k] ^ code[i + k]) * K;
+            h[k] ^= h[k] >> 29;
         }
-    return h ^ (uint64_t)n_instr;
+    for (int k = 0; i < n_instr; i++, k++) {
+        h[k] = (h[k] ^ code[i]) * K;
+        h[k] ^= h[k] >> 29;
+    }
+    uint64_t r = (uint64_t)n_instr;
+    for (int k = 0; k < 4; k++) {
+        r = (r ^ h[k]) * K;
+        r ^= r >> 32;
+    }
+    return r;
 }
 
 // ------------------------------------------------------------------ graph

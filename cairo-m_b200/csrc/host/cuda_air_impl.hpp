@@ -72,6 +72,7 @@ struct CudaAirImpl {
         static const int n = getenv("CM31_PREFETCH_CTAS") ? atoi(getenv("CM31_PREFETCH_CTAS")) : 16;
         return n;
     }
+    static void idle_gate_open() { B::idle_gate_open(); }
     static void staging_release_point(int point) {
         if (point == prefetch_point()) cm_check(cm31_bg_release_throttled(0, prefetch_ctas()));
     }

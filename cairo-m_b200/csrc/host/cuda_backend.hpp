@@ -442,14 +442,45 @@ struct CudaBackend {
     }
     static const u32* col_words(const Col& c) { return Shard::get().resolve(c.ptr()); }  // decommitment reads go to the owner's copy
     static const u32* hash_words(const HashCol& c) { return c.ptr(); }
-    static void gather_runs(const std::vector<const u32*>& srcs, const std::vector<u32>& src_id, const std::vector<u32>& word,
-                            const std::vector<u32>& out_off, const std::vector<u32>& cnt, const std::vector<u32>& grid_desc,
-                            const std::vector<u32>& grid_cols, const std::vector<u32>& grid_rows, std::vector<u32>& out) {
-        cm_check(cm31_gather_batch(srcs.data(), srcs.size(), src_id.data(), word.data(), out_off.data(), cnt.data(), src_id.size(), grid_desc.data(),
-                                   grid_desc.size() / 5, grid_cols.data(), grid_cols.size(), grid_rows.data(), grid_rows.size(), out.size(),
-                                   out.data()));
+    // the gathered words land in a page-locked buffer of the library; gather_wait() blocks until they have
+    static const u32* gather_runs_async(const std::vector<const u32*>& srcs, const std::vector<u32>& src_id, const std::vector<u32>& word,
+                                        const std::vector<u32>& out_off, const std::vector<u32>& cnt, const std::vector<u32>& grid_desc,
+                                        const std::vector<u32>& grid_cols, const std::vector<u32>& grid_rows, size_t n_words,
+                                        std::vector<u32>& /*store*/) {
+        const u32* res = nullptr;
+        cm_check(cm31_gather_batch_async(srcs.data(), srcs.size(), src_id.data(), word.data(), out_off.data(), cnt.data(), src_id.size(),
+                                         grid_desc.data(), grid_desc.size() / 5, grid_cols.data(), grid_cols.size(), grid_rows.data(),
+                                         grid_rows.size(), n_words, &res));
+        return res;
     }
+    static void gather_wait() { cm_check(cm31_gather_wait()); }
+    // Deferred proof tails (cm31_prove_cairo_m_async): while `defer` is set, prove_values leaves the host-side assembly of the
+    // decommitments to a closure; the owner of the pending proof registers `hook`, which runs it (and serialises the proof).
+    // The hook fires at the first Merkle-root read after idle_gate_open() -- the prover opens the gate before the commitment
+    // of the execution traces, where milliseconds of FFT / Merkle kernels are queued and the host would only wait -- or at the
+    // latest before the next gather (finish_deferred_tails).
+    struct TailState {
+        bool defer = false;
+        bool gate = false;
+        std::function<void()> hook;
+    };
+    static TailState& tail_state() {
+        static TailState t;
+        return t;
+    }
+    static bool defer_proof_tail() { return tail_state().defer; }
+    static void finish_deferred_tails() {
+        TailState& t = tail_state();
+        t.gate = false;
+        if (t.hook) {
+            std::function<void()> h = std::move(t.hook);
+            t.hook = nullptr;
+            h();
+        }
+    }
+    static void idle_gate_open() { tail_state().gate = true; }
     static Hash32 read_root(const HashCol& root_layer) {
+        if (tail_state().gate) finish_deferred_tails();  // the kernels of this tree are queued: host time is free until its root arrives
         Hash32 h;
         cm_check(cm31_d2h(h.b, root_layer.ptr(), 32));
         if (getenv("CM31_SHARD_DEBUG")) {

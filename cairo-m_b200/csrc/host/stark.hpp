@@ -112,6 +112,16 @@ struct CommitmentSchemeProof {
     std::vector<std::vector<u32>> queried_values;
     u64 proof_of_work = 0;
     FriProof fri_proof;
+    // Deferred tail (B::defer_proof_tail()): the decommitment values of this proof are still travelling device->host; the
+    // closure waits for them and fills queried_values / decommitments / fri_proof.  resolve() must run before the proof is
+    // read; the CUDA prover runs it while the NEXT proof keeps the GPU busy (cm31_prove_cairo_m_async).
+    std::shared_ptr<std::function<void(CommitmentSchemeProof&)>> pending_tail;
+    void resolve() {
+        if (!pending_tail) return;
+        auto f = std::move(pending_tail);
+        pending_tail.reset();
+        (*f)(*this);
+    }
 };
 typedef CommitmentSchemeProof StarkProof;
 
@@ -285,7 +295,8 @@ struct GatherQueue {
     std::vector<const u32*> srcs;
     std::unordered_map<const u32*, u32> src_index;
     std::vector<u32> src_id, word, out_off, cnt;  // per run request: cnt[k] words land at results[out_off[k]..]
-    std::vector<u32> results;
+    const u32* results = nullptr;  // n_words gathered words (a page-locked buffer of the backend, or `store`)
+    std::vector<u32> store;
     size_t n_words = 0;
     GatherQueue() {  // a proof records ~50k run requests: no regrowth on the critical path after the proof-of-work nonce
         for (auto* v : {&src_id, &word, &out_off, &cnt}) v->reserve(1u << 16);
@@ -324,13 +335,20 @@ struct GatherQueue {
         n_words += col_ids.size() * rows.size();
         return base;
     }
+    // flush = flush_async (the reads are enqueued) + wait (their results are in `results`)
+    void flush_async() {
+        if (n_words) results = B::gather_runs_async(srcs, src_id, word, out_off, cnt, grid_desc, grid_cols, grid_rows, n_words, store);
+    }
+    void wait() {
+        if (n_words) B::gather_wait();
+    }
     void flush() {
-        results.resize(n_words);
-        if (n_words) B::gather_runs(srcs, src_id, word, out_off, cnt, grid_desc, grid_cols, grid_rows, results);
+        flush_async();
+        wait();
     }
     Hash32 hash_at(size_t slot) const {
         Hash32 h;
-        memcpy(h.b, &results[slot], 32);
+        memcpy(h.b, results + slot, 32);
         return h;
     }
 };
@@ -420,7 +438,15 @@ struct MerkleProver {
         return mp;
     }
 
-    Hash32 root() const { return B::read_root(layers[0]); }  // one 32-byte device->host copy
+    Hash32 root() const {  // one 32-byte device->host copy, once
+        if (!root_read_) {
+            root_ = B::read_root(layers[0]);
+            root_read_ = true;
+        }
+        return root_;
+    }
+    mutable Hash32 root_;
+    mutable bool root_read_ = false;
 
     // vcs/prover.rs:82-156 in two phases: `plan` walks the layers exactly like the reference and
     // records every read in the gather queue; `finish` (after queue.flush()) assembles the values.
@@ -430,9 +456,9 @@ struct MerkleProver {
         std::pair<std::vector<u32>, MerkleDecommitment> finish(const GatherQueue<B>& q) const {
             std::vector<u32> queried_values;
             MerkleDecommitment d;
-            for (auto& r : queried_runs) queried_values.insert(queried_values.end(), q.results.begin() + r.first, q.results.begin() + r.first + r.second);
+            for (auto& r : queried_runs) queried_values.insert(queried_values.end(), q.results + r.first, q.results + r.first + r.second);
             for (auto& r : column_witness_runs)
-                d.column_witness.insert(d.column_witness.end(), q.results.begin() + r.first, q.results.begin() + r.first + r.second);
+                d.column_witness.insert(d.column_witness.end(), q.results + r.first, q.results + r.first + r.second);
             for (size_t s : hash_witness_slots) d.hash_witness.push_back(q.hash_at(s));
             return {queried_values, d};
         }
@@ -985,16 +1011,33 @@ CommitmentSchemeProof CommitmentSchemeProver<B>::prove_values(const std::vector<
     ht.reset(new HostTimer("pv_decommit_plan_trees"));
     for (auto& t : trees) pending.push_back(t.plan_decommit(queue, query_positions_per_log_size));
     ht.reset(new HostTimer("pv_decommit_flush"));
-    queue.flush();
-    ht.reset(new HostTimer("pv_decommit_finish"));
-    proof.fri_proof = fri_res.first.finish(queue);
-    ht.reset(new HostTimer("pv_decommit_finish_trees"));
-    for (auto& pd : pending) {
-        auto res = pd.finish(queue);
-        proof.queried_values.push_back(std::move(res.first));
-        proof.decommitments.push_back(std::move(res.second));
-    }
-    proof.commitments = roots();
+    B::finish_deferred_tails();  // a previous proof's tail reads the landing buffer this gather is about to take over
+    queue.flush_async();
+    proof.commitments = roots();  // (cached at commit time: no device read)
+    struct Tail {
+        typename FriProver<B>::PendingFriProof fri;
+        std::vector<typename MerkleProver<B>::PendingDecommit> pending;
+        GatherQueue<B> queue;
+    };
+    auto st = std::make_shared<Tail>();
+    st->fri = std::move(fri_res.first);
+    st->pending = std::move(pending);
+    st->queue = std::move(queue);
+    auto tail = [st](CommitmentSchemeProof& p) {
+        HostTimer ht2("pv_decommit_finish");
+        st->queue.wait();
+        p.fri_proof = st->fri.finish(st->queue);
+        for (auto& pd : st->pending) {
+            auto res = pd.finish(st->queue);
+            p.queried_values.push_back(std::move(res.first));
+            p.decommitments.push_back(std::move(res.second));
+        }
+    };
+    ht.reset();
+    if (B::defer_proof_tail())
+        proof.pending_tail = std::make_shared<std::function<void(CommitmentSchemeProof&)>>(tail);
+    else
+        tail(proof);
     return proof;
 }
 

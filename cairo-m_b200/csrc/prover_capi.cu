@@ -602,9 +602,72 @@ int cm31_air_shapes(char* buf, size_t cap, size_t* len) {
     }
 }
 
+// ---- asynchronous proofs: the tail of proof i (assembly of the decommitments from the gathered words, serialisation: host
+// work with the GPU idle, ~1.4 ms of a 22 ms proof) runs while proof i+1 executes.  One proof may be pending at a time.
+struct PendingProofOut {
+    std::unique_ptr<CairoProof> proof;
+    uint8_t* out = nullptr;
+    size_t cap = 0;
+    size_t* len = nullptr;
+    int rc = 0;
+    std::string err;
+};
+static PendingProofOut g_pending_out;
+static void finish_pending_proof() {
+    PendingProofOut& p = g_pending_out;
+    if (!p.proof) return;
+    std::unique_ptr<CairoProof> proof = std::move(p.proof);
+    try {
+        proof->stark_proof.resolve();
+        HostTimer ht("proof_to_bytes");
+        static thread_local ProofWriter writer;
+        writer.bytes.clear();
+        proof->write(writer);
+        p.rc = write_out(writer.bytes, p.out, p.cap, p.len);
+        if (p.rc) p.err = cm31_last_error();
+    } catch (const std::exception& e) {
+        p.rc = -2;
+        p.err = e.what();
+    }
+}
+static int prove_impl(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out, size_t proof_cap,
+                      size_t* proof_len, double* timings_ms, bool async);
+// Returns once the proof's kernels and the device->host copy of its decommitment values are enqueued; proof_out / proof_len
+// are written later -- during the next cm31_prove_cairo_m[_async] call on this thread or by cm31_prove_wait(), whichever
+// comes first -- and must stay valid until then.  A failure of the deferred part is reported by the call that ran it
+// (cm31_prove_wait, or the next cm31_prove_cairo_m_async, returns it).
+int cm31_prove_cairo_m_async(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out,
+                             size_t proof_cap, size_t* proof_len, double* timings_ms) {
+    return prove_impl(h, pow_bits, n_queries, proof_out, proof_cap, proof_len, timings_ms, true);
+}
+int cm31_prove_wait(void) {
+    CudaBackend::finish_deferred_tails();
+    finish_pending_proof();  // (no hook registered: e.g. the proof failed before its tail was deferred)
+    PendingProofOut& p = g_pending_out;
+    int rc = p.rc;
+    if (rc) set_error(p.err);
+    p.rc = 0;
+    p.err.clear();
+    return rc;
+}
 int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out,
                        size_t proof_cap, size_t* proof_len, double* timings_ms) {
+    if (int e = cm31_prove_wait()) return e;  // a pending asynchronous proof is completed first
+    return prove_impl(h, pow_bits, n_queries, proof_out, proof_cap, proof_len, timings_ms, false);
+}
+static int prove_impl(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out, size_t proof_cap,
+                      size_t* proof_len, double* timings_ms, bool async) {
+    struct DeferGuard {  // prove_values defers its tail only inside an asynchronous proof
+        ~DeferGuard() { CudaBackend::tail_state().defer = false; }
+    } defer_guard;
     try {
+        if (g_pending_out.rc) {  // the deferred part of the previous asynchronous proof failed: report it now
+            int rc = g_pending_out.rc;
+            set_error(g_pending_out.err);
+            g_pending_out.rc = 0;
+            return rc;
+        }
+        CudaBackend::tail_state().defer = async;
         CM_REQUIRE(h != nullptr, "prove_cairo_m: null input");
         PcsConfig cfg = PcsConfig::regular_96_bits();
         cfg.pow_bits = pow_bits;
@@ -627,6 +690,19 @@ int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n
             timings_ms[4] = t.total_ms;
         }
         if (pre) const_cast<cm31_prover_input*>(h)->spare = std::move(pre);  // keep the slot for the next prefetch
+        if (async && proof.stark_proof.pending_tail) {
+            // (the previous pending proof was completed inside this proof at the latest: prove_values runs
+            // finish_deferred_tails before it takes over the gather landing buffer)
+            finish_pending_proof();
+            g_pending_out.proof.reset(new CairoProof(std::move(proof)));
+            g_pending_out.out = proof_out;
+            g_pending_out.cap = proof_cap;
+            g_pending_out.len = proof_len;
+            CudaBackend::tail_state().hook = finish_pending_proof;
+            HostTimer::report();
+            return 0;
+        }
+        proof.stark_proof.resolve();
         int rc;
         {
             HostTimer ht("proof_to_bytes");

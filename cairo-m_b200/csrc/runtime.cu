@@ -565,10 +565,16 @@ int cm31_gather_runs(const uint32_t* const* srcs, size_t n_srcs, const uint32_t*
     return 0;
 }
 
-int cm31_gather_batch(const uint32_t* const* srcs, size_t n_srcs, const uint32_t* src_id_host, const uint32_t* word_idx_host,
-                      const uint32_t* out_off_host, const uint32_t* cnt_host, size_t n_runs, const uint32_t* grid_desc_host,
-                      size_t n_grids, const uint32_t* grid_cols_host, size_t n_grid_cols, const uint32_t* grid_rows_host,
-                      size_t n_grid_rows, size_t total_words, uint32_t* out_host) {
+// Asynchronous form: the gather kernels and the device->host copy of the result are enqueued, *result_out names the page-locked
+// buffer the words land in, and cm31_gather_wait() blocks until they have.  The prover uses it to leave the assembly and the
+// serialisation of a proof (host work, ~1.4 ms) for a moment when the NEXT proof has the GPU busy (cm31_prove_cairo_m_async).
+static cudaEvent_t g_gather_event = nullptr;
+int cm31_gather_batch_async(const uint32_t* const* srcs, size_t n_srcs, const uint32_t* src_id_host, const uint32_t* word_idx_host,
+                            const uint32_t* out_off_host, const uint32_t* cnt_host, size_t n_runs, const uint32_t* grid_desc_host,
+                            size_t n_grids, const uint32_t* grid_cols_host, size_t n_grid_cols, const uint32_t* grid_rows_host,
+                            size_t n_grid_rows, size_t total_words, const uint32_t** result_out) {
+    CM_REQUIRE(result_out != nullptr, "gather_batch_async: null result pointer");
+    *result_out = nullptr;
     if (total_words == 0) return 0;
     for (size_t k = 0; k < n_runs; k++)
         CM_REQUIRE(src_id_host[k] < n_srcs && (size_t)out_off_host[k] + cnt_host[k] <= total_words, "gather_batch: bad run request");
@@ -580,13 +586,16 @@ int cm31_gather_batch(const uint32_t* const* srcs, size_t n_srcs, const uint32_t
         max_work = std::max(max_work, (size_t)d[1] * d[3]);
     }
     for (size_t c = 0; c < n_grid_cols; c++) CM_REQUIRE(grid_cols_host[c] < n_srcs, "gather_batch: bad grid column");
-    // page-locked landing buffer (grow-only): the result copy is a true DMA instead of a driver-staged pageable copy
-    static u32* pinned = nullptr;
-    static size_t pinned_words = 0;
-    if (pinned_words < total_words) {
-        if (pinned) cudaFreeHost(pinned);
-        pinned_words = std::max<size_t>(total_words * 2, (size_t)1 << 18);
-        CM_CUDA(cudaHostAlloc((void**)&pinned, pinned_words * 4, cudaHostAllocDefault));
+    // page-locked landing buffers (grow-only, two of them alternate): the result copy is a true DMA, and the caller may read
+    // the result of one gather while the next proof is already running (cm31_gather_batch_async / cm31_gather_wait)
+    static u32* pinned[2] = {nullptr, nullptr};
+    static size_t pinned_words[2] = {0, 0};
+    static int which = 0;
+    which ^= 1;
+    if (pinned_words[which] < total_words) {
+        if (pinned[which]) cudaFreeHost(pinned[which]);
+        pinned_words[which] = std::max<size_t>(total_words * 2, (size_t)1 << 18);
+        CM_CUDA(cudaHostAlloc((void**)&pinned[which], pinned_words[which] * 4, cudaHostAllocDefault));
     }
     DeviceTable dsrcs, dsid, dword, doff, dcnt, ddesc, dcols, drows;
     if (int e = dsrcs.upload(srcs, n_srcs * sizeof(void*))) return e;
@@ -610,10 +619,29 @@ int cm31_gather_batch(const uint32_t* const* srcs, size_t n_srcs, const uint32_t
         gather_grid_kernel<<<grid, 256, 0, stream()>>>((const u32* const*)dsrcs.d, (const u32*)ddesc.d, (const u32*)dcols.d, (const u32*)drows.d, dout);
         CM_LAUNCH_CHECK();
     }
-    CM_CUDA(cudaMemcpyAsync(pinned, dout, total_words * 4, cudaMemcpyDeviceToHost, stream()));
+    CM_CUDA(cudaMemcpyAsync(pinned[which], dout, total_words * 4, cudaMemcpyDeviceToHost, stream()));
     CM_CUDA(cudaFreeAsync(dout, stream()));
-    CM_CUDA(cudaStreamSynchronize(stream()));
-    memcpy(out_host, pinned, total_words * 4);
+    if (!g_gather_event) CM_CUDA(cudaEventCreateWithFlags(&g_gather_event, cudaEventDisableTiming));
+    CM_CUDA(cudaEventRecord(g_gather_event, stream()));
+    *result_out = pinned[which];
+    return 0;
+}
+// the words requested by the last cm31_gather_batch_async have landed in its result buffer
+int cm31_gather_wait(void) {
+    if (g_gather_event) CM_CUDA(cudaEventSynchronize(g_gather_event));
+    return 0;
+}
+int cm31_gather_batch(const uint32_t* const* srcs, size_t n_srcs, const uint32_t* src_id_host, const uint32_t* word_idx_host,
+                      const uint32_t* out_off_host, const uint32_t* cnt_host, size_t n_runs, const uint32_t* grid_desc_host,
+                      size_t n_grids, const uint32_t* grid_cols_host, size_t n_grid_cols, const uint32_t* grid_rows_host,
+                      size_t n_grid_rows, size_t total_words, uint32_t* out_host) {
+    if (total_words == 0) return 0;
+    const uint32_t* res = nullptr;
+    if (int e = cm31_gather_batch_async(srcs, n_srcs, src_id_host, word_idx_host, out_off_host, cnt_host, n_runs, grid_desc_host, n_grids,
+                                        grid_cols_host, n_grid_cols, grid_rows_host, n_grid_rows, total_words, &res))
+        return e;
+    if (int e = cm31_gather_wait()) return e;
+    memcpy(out_host, res, total_words * 4);
     return 0;
 }
 

@@ -15,9 +15,15 @@
 
 namespace cm31 {
 
+// the output column pointers travel as a kernel parameter (no table upload: this kernel runs once per opcode component, most of
+// them 16-row paddings whose cost is the host's launch path)
+struct UnpackOut {
+    u32* p[N_BUNDLE_INPUTS];
+};
 __global__ void __launch_bounds__(256) unpack_bundles_kernel(const uint4* __restrict__ bundles, u32 n_real, u32 log_size,
                                                              const uint4* __restrict__ accesses, u32 n_accesses,
-                                                             u32* const* __restrict__ out, u32 n_slots) {
+                                                             const __grid_constant__ UnpackOut outs, u32 n_slots) {
+    u32* const* out = outs.p;
     u32 row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (1u << log_size)) return;
     u32 w[12];
@@ -84,13 +90,12 @@ int cm31_unpack_bundles_slots(const uint32_t* bundles_dev, size_t n_real, uint32
     CM_REQUIRE(n_access_slots <= (uint32_t)MAX_ACCESSES, "unpack_bundles: at most 8 access slots");
     static const bool full = getenv("CM31_FULL_UNPACK") != nullptr;  // A/B runs: write all 8 slots as the first version did
     if (full) n_access_slots = MAX_ACCESSES;
-    DeviceTable dout;
-    if (int e = dout.upload(out_cols, N_BUNDLE_INPUTS * sizeof(void*))) return e;
+    UnpackOut outs;
+    for (int k = 0; k < N_BUNDLE_INPUTS; k++) outs.p[k] = out_cols[k];
     size_t n = (size_t)1 << log_size;
     ProfScope prof("unpack_bundles", 48ull * n_real + 4ull * (IN_ACC_BASE + 4ull * n_access_slots) * n);
     unpack_bundles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>((const uint4*)bundles_dev, (u32)n_real, log_size,
-                                                                            (const uint4*)accesses_dev, (u32)n_accesses,
-                                                                            (u32* const*)dout.d, n_access_slots);
+                                                                            (const uint4*)accesses_dev, (u32)n_accesses, outs, n_access_slots);
     CM_LAUNCH_CHECK();
     return 0;
 }

@@ -96,6 +96,13 @@ int cm31_gather_batch(const uint32_t* const* srcs, size_t n_srcs, const uint32_t
                       const uint32_t* out_off_host, const uint32_t* cnt_host, size_t n_runs, const uint32_t* grid_desc_host,
                       size_t n_grids, const uint32_t* grid_cols_host, size_t n_grid_cols, const uint32_t* grid_rows_host,
                       size_t n_grid_rows, size_t total_words, uint32_t* out_host);
+/* The same without the final synchronisation: *result_out = the page-locked buffer the total_words words land in (valid until
+ * the second next call), cm31_gather_wait() returns once they have.  Lets a prover assemble proof i while proof i+1 runs. */
+int cm31_gather_batch_async(const uint32_t* const* srcs, size_t n_srcs, const uint32_t* src_id_host, const uint32_t* word_idx_host,
+                            const uint32_t* out_off_host, const uint32_t* cnt_host, size_t n_runs, const uint32_t* grid_desc_host,
+                            size_t n_grids, const uint32_t* grid_cols_host, size_t n_grid_cols, const uint32_t* grid_rows_host,
+                            size_t n_grid_rows, size_t total_words, const uint32_t** result_out);
+int cm31_gather_wait(void);
 /* same for hash columns: out_host[q*8..] = layer[idx[q]] */
 int cm31_gather_hash(const uint32_t* layer, const uint32_t* idx_host, size_t n_idx, uint32_t* out_host);
 
@@ -323,6 +330,13 @@ int cm31_input_release_device(cm31_prover_input* h);
  * "ConstraintsNotSatisfied" (S/prover/src/core/prover/mod.rs:76-82) if the OODS check fails. */
 int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out,
                        size_t proof_cap, size_t* proof_len, double* timings_ms);
+/* Asynchronous form for a prover fed with a stream of segments: returns once the proof's kernels and the device->host copy of
+ * its decommitment values are enqueued.  proof_out / proof_len are written later -- while the NEXT proof of this thread keeps
+ * the GPU busy, or by cm31_prove_wait() -- and must stay valid until then; one proof may be pending at a time.  The bytes are
+ * identical to cm31_prove_cairo_m's.  cm31_prove_wait() completes the pending proof and returns its status. */
+int cm31_prove_cairo_m_async(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out,
+                             size_t proof_cap, size_t* proof_len, double* timings_ms);
+int cm31_prove_wait(void);
 /* The reference's proof wire format: serde JSON of Proof<Blake2sMerkleHasher> (P/src/lib.rs:61-73; CommitmentSchemeProof
  * S/prover/src/core/pcs/prover.rs:156-165, FriProof S/prover/src/core/fri.rs:675-699, MerkleDecommitment
  * S/prover/src/core/vcs/prover.rs:163-173), as `cairo-m-prover --output` writes it with sonic_rs (P/src/main.rs:88) and

@@ -117,6 +117,18 @@ struct OracleBackend {
                 for (u32 c = 0; c < n_cols; c++) out[base + (size_t)k * n_cols + c] = srcs[grid_cols[col_off + c]][grid_rows[row_off + k]];
         }
     }
+    // the CPU backend gathers synchronously: the "asynchronous" form fills `store` at once
+    static const u32* gather_runs_async(const std::vector<const u32*>& srcs, const std::vector<u32>& src_id, const std::vector<u32>& word,
+                                        const std::vector<u32>& out_off, const std::vector<u32>& cnt, const std::vector<u32>& grid_desc,
+                                        const std::vector<u32>& grid_cols, const std::vector<u32>& grid_rows, size_t n_words,
+                                        std::vector<u32>& store) {
+        store.assign(n_words, 0);
+        gather_runs(srcs, src_id, word, out_off, cnt, grid_desc, grid_cols, grid_rows, store);
+        return store.data();
+    }
+    static void gather_wait() {}
+    static bool defer_proof_tail() { return false; }
+    static void finish_deferred_tails() {}
     static cm31::Hash32 read_root(const HashCol& root_layer) {
         cm31::Hash32 h;
         memcpy(h.b, root_layer[0].b, 32);

@@ -163,6 +163,41 @@ def test_prefetched_input_gives_the_same_proof(cm):
     assert plain == want
 
 
+def test_async_proofs_are_the_same_bytes(cm):
+    # cm31_prove_cairo_m_async: the tail of proof i (decommitment assembly + serialisation) runs inside proof i+1 or in
+    # cm31_prove_wait; the bytes must be exactly those of the synchronous call, in every interleaving
+    import ctypes as C
+    lib = cm.lib()
+    a, b = ch.GpuFibInput(cm, 1000), ch.GpuFibInput(cm, 300, program=ch.U32_COUNTER)
+    try:
+        want_a, _ = a.prove()
+        want_b, _ = b.prove()
+        bufs = [(C.c_uint8 * ch.CAP)() for _ in range(4)]
+        lens = [C.c_size_t() for _ in range(4)]
+        tm = (C.c_double * 5)()
+
+        def submit(inp, k):
+            cm.check(lib.cm31_prove_cairo_m_async(inp.h, 16, 80, bufs[k], C.c_size_t(ch.CAP), C.byref(lens[k]), tm))
+
+        def got(k):
+            return bytes(bufs[k][: lens[k].value])
+
+        submit(a, 0)
+        submit(b, 1)  # completes proof 0 on its way
+        assert got(0) == want_a
+        submit(a, 2)
+        assert got(1) == want_b
+        cm.check(lib.cm31_prove_wait())
+        assert got(2) == want_a
+        cm.check(lib.cm31_prove_wait())  # nothing pending: a no-op
+        submit(b, 3)
+        again, _ = a.prove()  # a synchronous proof first completes the pending one
+        assert got(3) == want_b and again == want_a
+    finally:
+        a.close()
+        b.close()
+
+
 @pytest.mark.parametrize("kind", [0, 1])
 def test_invalid_trace_is_refused(cm, kind):
     # an execution trace that does not satisfy the AIR must not yield a proof: the composition OODS
