@@ -21,8 +21,11 @@ def run_worker(world, program, n, port):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                "--master-port", str(port), str(WORKER), str(program), str(n)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=str(ROOT))
-    lines = [l for l in (res.stdout + res.stderr).splitlines() if "SHARDED_" in l]
-    assert res.returncode == 0 and len(lines) == world and all("SHARDED_OK" in l for l in lines), (res.stdout + res.stderr)[-3000:]
+    # one record per rank; the ranks share a pipe, so two records can end up on one line (no newline in between): match
+    # the records themselves, not lines
+    import re
+    lines = re.findall(r"SHARDED_(?:OK|MISMATCH) rank=\d+ world=\d+ sha256=[0-9a-f]+ .*?collectives=\d+", res.stdout + res.stderr)
+    assert res.returncode == 0 and len(lines) == world and all(l.startswith("SHARDED_OK") for l in lines), (res.stdout + res.stderr)[-3000:]
     return lines
 
 
