@@ -36,13 +36,11 @@ __device__ __forceinline__ void wr4(u32* r, u32 i, QM31 v) {
     r[i + 3] = v.d;
 }
 
+// one row of a bytecode program; returns the row's constraint accumulator
 template <int NREGS>
-__global__ void __launch_bounds__(128) air_program_kernel(const u32* const* __restrict__ in_cols, u32* const* __restrict__ out_cols,
-                                                          u32 row_log, u32 trace_log, const uint64_t* __restrict__ code, u32 n_instr,
-                                                          const u32* __restrict__ consts, const u32* __restrict__ denom_inv,
-                                                          u32* acc0, u32* acc1, u32* acc2, u32* acc3, u32 hist_bins, u32* err) {
-    const u32 row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= (1u << row_log)) return;
+__device__ __forceinline__ QM31 air_interpret_row(const u32* const* __restrict__ in_cols, u32* const* __restrict__ out_cols, u32 row,
+                                                  u32 row_log, u32 trace_log, const uint64_t* __restrict__ code, u32 n_instr,
+                                                  const u32* __restrict__ consts, u32 hist_bins, u32* err) {
     u32 regs[NREGS];
     QM31 acc = qm_zero();
     for (u32 pc = 0; pc < n_instr; pc++) {
@@ -114,6 +112,17 @@ __global__ void __launch_bounds__(128) air_program_kernel(const u32* const* __re
             default: break;
         }
     }
+    return acc;
+}
+
+template <int NREGS>
+__global__ void __launch_bounds__(128) air_program_kernel(const u32* const* __restrict__ in_cols, u32* const* __restrict__ out_cols,
+                                                          u32 row_log, u32 trace_log, const uint64_t* __restrict__ code, u32 n_instr,
+                                                          const u32* __restrict__ consts, const u32* __restrict__ denom_inv,
+                                                          u32* acc0, u32* acc1, u32* acc2, u32* acc3, u32 hist_bins, u32* err) {
+    const u32 row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= (1u << row_log)) return;
+    const QM31 acc = air_interpret_row<NREGS>(in_cols, out_cols, row, row_log, trace_log, code, n_instr, consts, hist_bins, err);
     if (acc0 != nullptr) {
         // component.rs:413-421: col[row] += row_res * denom_inv[row >> trace_log]
         u32 di = __ldg(denom_inv + (row >> trace_log));
@@ -123,6 +132,25 @@ __global__ void __launch_bounds__(128) air_program_kernel(const u32* const* __re
         acc2[row] = m31_add(acc2[row], v.c);
         acc3[row] = m31_add(acc3[row], v.d);
     }
+}
+
+// MANY small programs in one launch (blockIdx.y = program): the trace-fill, lookup and logup programs of the components that
+// only prove their 16 padding rows -- 21 of the 26 opcode components of a fibonacci_loop proof -- are pure launch latency when
+// issued one by one (~7 us of host time each, ~135 launches per proof).  The descriptors, pointer arrays, bytecode and constants
+// of the whole batch travel in one table.  No constraint programs here: those accumulate into shared per-size columns.
+struct AirBatchDesc {
+    const u32* const* in;
+    u32* const* out;
+    const uint64_t* code;
+    const u32* consts;
+    u32 row_log, n_instr, hist_bins, pad;
+};
+template <int NREGS>
+__global__ void __launch_bounds__(128) air_program_batch_kernel(const AirBatchDesc* __restrict__ descs, u32* err) {
+    const AirBatchDesc d = descs[blockIdx.y];
+    const u32 row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= (1u << d.row_log)) return;
+    air_interpret_row<NREGS>(d.in, d.out, row, d.row_log, d.row_log, d.code, d.n_instr, d.consts, d.hist_bins, err);
 }
 
 static int g_gen_sync = getenv("CM31_GEN_SYNC") ? atoi(getenv("CM31_GEN_SYNC")) : 1;  // CTA barriers in the generated bodies (air_gen.cuh GEN_SYNC)
@@ -392,7 +420,7 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(Col4 c, u32 L, const u3
 // whole finalize_last — sums, claimed sum, shift, coset-order scan of the 4 coordinates — in ONE
 // single-CTA launch.  64 threads per coordinate, each scanning a contiguous run.
 constexpr u32 FINALIZE_SMALL_LOG = 11;
-__global__ void __launch_bounds__(256) logup_finalize_small_kernel(Col4 c, u32 L, u32 n_inv, u32* claimed_out) {
+__device__ __forceinline__ void logup_finalize_small_body(const Col4& c, u32 L, u32 n_inv, u32* claimed_out) {
     __shared__ u32 vals[4][1u << FINALIZE_SMALL_LOG];
     __shared__ u32 tot[4][64];
     __shared__ u32 shift[4];
@@ -429,6 +457,18 @@ __global__ void __launch_bounds__(256) logup_finalize_small_kernel(Col4 c, u32 L
         running = m31_add(running, m31_sub(vals[k][j], sh));
         col[coset_pos_to_row(j, L)] = running;
     }
+}
+__global__ void __launch_bounds__(256) logup_finalize_small_kernel(Col4 c, u32 L, u32 n_inv, u32* claimed_out) {
+    logup_finalize_small_body(c, L, n_inv, claimed_out);
+}
+struct LogupSmallItem {
+    Col4 c;
+    u32 L, n_inv;
+    u32* claimed;
+};
+__global__ void __launch_bounds__(256) logup_finalize_small_batch_kernel(const LogupSmallItem* __restrict__ items) {
+    const LogupSmallItem it = items[blockIdx.x];
+    logup_finalize_small_body(it.c, it.L, it.n_inv, it.claimed);
 }
 
 __global__ void histogram_kernel(const u32* values, size_t n, u32* bins, u32 n_bins) {
@@ -478,6 +518,77 @@ int cm31_air_lookups(const uint32_t* const* in_cols, size_t n_in, uint32_t* bins
     uint32_t* out[1] = {bins};
     return run_program(in_cols, n_in, out, 1, log_size, log_size, code, n_instr, n_regs, consts, n_consts, nullptr, 0, nullptr,
                        1u << log_bins);
+}
+
+// see air_program_batch_kernel.  Every item is a cm31_air_program call (hist_bins == 0) or a cm31_air_lookups call
+// (hist_bins = bin count of out_cols[0]); items must be independent of each other (they run concurrently).
+int cm31_air_program_batch(const cm31_air_batch_item* items, size_t n_items) {
+    if (n_items == 0) return 0;
+    u32* err = air_err_flag();
+    CM_REQUIRE(err != nullptr, "air: cannot allocate the error word");
+    CM_REQUIRE(items != nullptr && n_items <= 65535, "air_program_batch: bad batch");
+    // blob = [descriptors][pointer arrays][bytecode][constants], 8-byte aligned sections
+    size_t n_ptrs = 0, n_code = 0, n_consts = 0;
+    u32 max_regs = 0, max_log = 0;
+    for (size_t i = 0; i < n_items; i++) {
+        const cm31_air_batch_item& it = items[i];
+        CM_REQUIRE(it.log_size <= 12, "air_program_batch: small programs only");
+        CM_REQUIRE(it.n_regs <= 2048, "air: program needs more than 2048 registers");
+        for (size_t k = 0; k < it.n_instr; k++) {
+            const u32 op = (u32)(it.code[k] & 0xff);
+            CM_REQUIRE(op != OP_HIST || it.hist_bins != 0, "air_program_batch: a histogram program needs its bin count");
+            CM_REQUIRE(it.hist_bins == 0 || (op != OP_STORE_E && op != OP_STORE_F), "air_program_batch: a lookup program only counts");
+        }
+        n_ptrs += it.n_in + it.n_out;
+        n_code += it.n_instr;
+        n_consts += it.n_consts + (it.n_consts & 1);
+        max_regs = std::max(max_regs, it.n_regs);
+        max_log = std::max(max_log, it.log_size);
+    }
+    const size_t off_ptrs = n_items * sizeof(AirBatchDesc), off_code = off_ptrs + n_ptrs * 8, off_consts = off_code + n_code * 8;
+    const size_t bytes = off_consts + n_consts * 4;
+    static thread_local std::vector<uint8_t> blob;
+    blob.resize(bytes);
+    // the device address of the table is known only after the upload slot is taken: stage with offsets, patch after
+    DeviceTable table;
+    if (int e = table.reserve(bytes)) return e;  // fixes the device address; the bytes follow (fill)
+    uint8_t* dbase = (uint8_t*)table.d;
+    AirBatchDesc* descs = (AirBatchDesc*)blob.data();
+    size_t at_ptr = off_ptrs, at_code = off_code, at_consts = off_consts;
+    uint64_t ops = 0;
+    for (size_t i = 0; i < n_items; i++) {
+        const cm31_air_batch_item& it = items[i];
+        descs[i].in = (const u32* const*)(dbase + at_ptr);
+        memcpy(blob.data() + at_ptr, it.in_cols, it.n_in * 8);
+        at_ptr += it.n_in * 8;
+        descs[i].out = (u32* const*)(dbase + at_ptr);
+        memcpy(blob.data() + at_ptr, it.out_cols, it.n_out * 8);
+        at_ptr += it.n_out * 8;
+        descs[i].code = (const uint64_t*)(dbase + at_code);
+        memcpy(blob.data() + at_code, it.code, it.n_instr * 8);
+        at_code += it.n_instr * 8;
+        descs[i].consts = (const u32*)(dbase + at_consts);
+        if (it.n_consts) memcpy(blob.data() + at_consts, it.consts, it.n_consts * 4);
+        at_consts += (it.n_consts + (it.n_consts & 1)) * 4;
+        descs[i].row_log = it.log_size;
+        descs[i].n_instr = (u32)it.n_instr;
+        descs[i].hist_bins = it.hist_bins;
+        descs[i].pad = 0;
+        ops += ((uint64_t)1 << it.log_size) * (it.n_in + it.n_out) * 4;
+    }
+    if (int e = table.fill(blob.data(), bytes)) return e;
+    ProfScope prof("air_program_batch", ops);
+    dim3 grid((unsigned)((((size_t)1 << max_log) + 127) / 128), (unsigned)n_items);
+#define CM_AIR_BATCH(NR) air_program_batch_kernel<NR><<<grid, 128, 0, stream()>>>((const AirBatchDesc*)table.d, err)
+    if (max_regs <= 64) CM_AIR_BATCH(64);
+    else if (max_regs <= 128) CM_AIR_BATCH(128);
+    else if (max_regs <= 256) CM_AIR_BATCH(256);
+    else if (max_regs <= 512) CM_AIR_BATCH(512);
+    else if (max_regs <= 1024) CM_AIR_BATCH(1024);
+    else CM_AIR_BATCH(2048);
+#undef CM_AIR_BATCH
+    CM_LAUNCH_CHECK();
+    return 0;
 }
 
 int cm31_air_error_check(void) {
@@ -543,6 +654,30 @@ int cm31_logup_finalize_last_async(uint32_t* const last4[4], uint32_t log_size, 
     CM_CUDA(cudaFreeAsync(dchunks, stream()));
     CM_CUDA(cudaFreeAsync(dshift, stream()));
     CM_CUDA(cudaFreeAsync(dsums, stream()));
+    return 0;
+}
+
+// the single-CTA finalize_last of MANY small components in one launch (blockIdx.x = component)
+int cm31_logup_finalize_small_batch(const cm31_logup_finalize_item* items, size_t n_items) {
+    if (n_items == 0) return 0;
+    CM_REQUIRE(items != nullptr, "logup_finalize_small_batch: null items");
+    static thread_local std::vector<LogupSmallItem> host;
+    host.resize(n_items);
+    uint64_t bytes = 0;
+    for (size_t i = 0; i < n_items; i++) {
+        CM_REQUIRE(items[i].log_size >= 1 && items[i].log_size <= FINALIZE_SMALL_LOG && items[i].claimed_sum_dev != nullptr,
+                   "logup_finalize_small_batch: bad item");
+        for (int k = 0; k < 4; k++) host[i].c.p[k] = items[i].last4[k];
+        host[i].L = items[i].log_size;
+        host[i].n_inv = m31_inv((u32)(((size_t)1 << items[i].log_size) % P));
+        host[i].claimed = items[i].claimed_sum_dev;
+        bytes += 32ull << items[i].log_size;
+    }
+    DeviceTable table;
+    if (int e = table.upload(host.data(), n_items * sizeof(LogupSmallItem))) return e;
+    ProfScope prof("logup_finalize_small", bytes);
+    logup_finalize_small_batch_kernel<<<(unsigned)n_items, 256, 0, stream()>>>((const LogupSmallItem*)table.d);
+    CM_LAUNCH_CHECK();
     return 0;
 }
 

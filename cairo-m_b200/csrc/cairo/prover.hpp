@@ -457,17 +457,28 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     std::vector<u32> log_sizes;
     std::vector<std::vector<CircleEvaluation<B>>> traces;  // per component (kept until tree 2 is built)
     size_t opcode_index = 0;
+    std::vector<Col> padding_inputs;  // shared by the components without real rows; alive until their batch has been issued
     auto opcode_trace = [&](auto eval_tag) {
         typedef decltype(eval_tag) Eval;
         const auto& rows = staged.opcode.at(opcode_index++);
         u32 ls = padded_log_size(rows.n_real);
         B::component_scope_index(scope_index++);  // sharded proof: only the owner fills this component's trace
-        B::lane(ls);  // small components go to the side lane; every temporary below dies on the lane that used it
-        Impl::staging_wait(rows.mark);
-        std::vector<Col> inputs = Impl::unpack_bundles(rows.words, rows.n_real, staged.accesses, staged.n_accesses, ls);
         Eval eval;
         eval.log_size_ = ls;
         log_sizes.push_back(ls);
+        if (rows.n_real == 0 && Impl::batch_small_components()) {
+            // an unused opcode component: 16 rows of ExecutionBundle::default().  Its inputs are the same columns for every
+            // such component and its trace program is recorded, not launched (one batched launch for all of them below)
+            B::lane(ls);  // the side lane: recorded programs are issued there too, so their columns are allocated, written and
+                          // (for the shared inputs) read in one stream order
+            if (padding_inputs.empty()) padding_inputs = Impl::unpack_padding(staged.accesses, staged.n_accesses, ls);
+            typename Impl::BatchScope batch(true);
+            traces.push_back(Impl::template write_trace<Eval>(eval, padding_inputs, 0));
+            return;
+        }
+        B::lane(ls);  // small components go to the side lane; every temporary below dies on the lane that used it
+        Impl::staging_wait(rows.mark);
+        std::vector<Col> inputs = Impl::unpack_bundles(rows.words, rows.n_real, staged.accesses, staged.n_accesses, ls);
         traces.push_back(Impl::template write_trace<Eval>(eval, inputs, (u32)rows.n_real));
     };
     B::prepare();
@@ -515,7 +526,9 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         traces.push_back(Impl::template write_trace<Poseidon2Eval>(eval, inputs, (u32)staged.poseidon2.n_real));
     }
     B::component_scope(-1);
+    Impl::air_batch_flush();  // the trace programs of the unused components: one launch
     B::lanes_join();
+    padding_inputs.clear();
     // range-check multiplicities: histogram of every value the opcode components look up
     // (opcodes/mod.rs:83-105 providers; range_check_macro.rs:72-84).  The AIR graphs drive it.
     RelationSet dummy_relations;
@@ -528,6 +541,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         // different components only meet in atomicAdds
         std::vector<Col> all_bins;
         for (auto& tb : tables) all_bins.push_back(B::zeros((size_t)1 << tb.second));
+        typename Impl::BatchScope lookup_batch(true);  // lookups of the 16-row components: recorded, one launch below
         for (size_t ti = 0; ti < tables.size(); ti++) {
             auto& tb = tables[ti];
             Col& bins = all_bins[ti];
@@ -545,6 +559,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
             shape.for_each(emit);
         }
         B::component_scope(-1);
+        Impl::air_batch_flush();
         B::lanes_join();
         for (auto& bins : all_bins) B::allreduce_bins(bins);  // sharded proof: multiplicities are sums over the ranks' components
         for (size_t ti = 0; ti < tables.size(); ti++) {
@@ -590,16 +605,20 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
             throw std::logic_error("unknown preprocessed column " + id);
         };
         size_t ci = 0;
-        components.for_each([&](auto& comp) {
-            std::vector<const Col*> tc;
-            for (auto& e : traces[ci]) tc.push_back(&e.values);
-            B::component_scope_index(ci);  // sharded proof: the owner generates this component's logup columns
-            B::lane(comp.log_size());
-            auto cols = comp.gen_interaction_trace(tc, pre_lookup);
-            for (auto& e : cols) interaction.push_back(std::move(e));
-            ci++;
-        });
+        {
+            typename Impl::BatchScope logup_batch(true);  // logup programs + finalisations of the 16-row components: two launches
+            components.for_each([&](auto& comp) {
+                std::vector<const Col*> tc;
+                for (auto& e : traces[ci]) tc.push_back(&e.values);
+                B::component_scope_index(ci);  // sharded proof: the owner generates this component's logup columns
+                B::lane(comp.log_size());
+                auto cols = comp.gen_interaction_trace(tc, pre_lookup);
+                for (auto& e : cols) interaction.push_back(std::move(e));
+                ci++;
+            });
+        }
         B::component_scope(-1);
+        Impl::air_batch_flush();
         B::lanes_join();
         Impl::collect_claimed_sums(components);
         components.for_each([&](auto& comp) { proof.interaction_claim.claimed_sums.push_back(comp.claimed_sum); });

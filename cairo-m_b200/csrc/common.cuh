@@ -57,6 +57,10 @@ struct DeviceTable {
     void* d = nullptr;
     bool owned = false;
     int upload(const void* host, size_t bytes);
+    // two-step form for tables that embed their own device address: reserve() fixes `d`, fill() copies the bytes
+    int reserve(size_t bytes);
+    int fill(const void* host, size_t bytes);
+    size_t ring_at = 0;
     void release();
     ~DeviceTable() { release(); }
 };

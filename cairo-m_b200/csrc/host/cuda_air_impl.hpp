@@ -73,6 +73,19 @@ struct CudaAirImpl {
         return n;
     }
     static void idle_gate_open() { B::idle_gate_open(); }
+    // batched small programs (CudaBackend::AirBatch)
+    typedef typename B::BatchScope BatchScope;
+    static bool batch_small_components() { return B::batch_small_components(); }
+    static void air_batch_flush() { B::air_batch_flush(); }
+    // the input columns of a component WITHOUT real rows: every row is ExecutionBundle::default() (witness.cu), whatever the
+    // component -- unpacked once per proof and shared by all such components (their trace programs run as one batch)
+    static std::vector<Col> unpack_padding(const Words& accesses, size_t n_accesses, u32 log_size) {
+        std::vector<Col> cols = Col::many(N_BUNDLE_INPUTS, (size_t)1 << log_size);
+        std::vector<u32*> out;
+        for (auto& c : cols) out.push_back(c.ptr());
+        cm_check(cm31_unpack_bundles_slots(accesses.ptr(), 0, log_size, accesses.ptr(), n_accesses, out.data(), MAX_ACCESSES));
+        return cols;
+    }
     static void staging_release_point(int point) {
         if (point == prefetch_point()) cm_check(cm31_bg_release_throttled(0, prefetch_ctas()));
     }

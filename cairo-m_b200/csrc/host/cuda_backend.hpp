@@ -165,7 +165,70 @@ struct CudaBackend {
         if (Shard::get().on) return;  // a sharded proof keeps one stream: its NCCL calls must be issued in one order on every rank
         cm_check(cm31_lane(log_size <= LANE_SPLIT_LOG ? 1 : 0));
     }
-    static void lanes_join() { cm_check(cm31_lanes_join()); }
+    static void lanes_join() {
+        air_batch_flush();  // (defensive: the phases flush explicitly before they join)
+        cm_check(cm31_lanes_join());
+    }
+    // ---- batched small programs (cm31_air_program_batch).  cairo-m proves all 34 components for every segment; the opcode
+    // components a program does not use are 16 padding rows each (21 of 26 for fibonacci_loop), and their trace-fill, lookup
+    // and logup programs cost ~7 us of launch path each when issued one by one.  Inside a BatchScope, programs over at most
+    // 2^SMALL_BATCH_LOG rows are recorded instead of launched; air_batch_flush() issues them as ONE interpreter launch (plus
+    // one launch for the recorded logup finalisations).  The caller guarantees that a recorded program's input and output
+    // columns stay alive until the flush and that recorded programs are independent of each other.
+    static constexpr u32 SMALL_BATCH_LOG = 6;
+    struct AirBatch {
+        struct Item {
+            std::vector<const u32*> in;
+            std::vector<u32*> out;
+            std::vector<uint64_t> code;
+            std::vector<u32> consts;
+            u32 log_size, n_regs, hist_bins;
+        };
+        std::vector<Item> items;
+        std::vector<cm31_logup_finalize_item> finals;
+        int depth = 0;
+    };
+    static AirBatch& air_batch() {
+        static AirBatch b;
+        return b;
+    }
+    static bool batch_small_components() {
+        static const bool off = getenv("CM31_NO_BATCH") != nullptr;
+        return !off && !Shard::get().on;
+    }
+    struct BatchScope {
+        bool on;
+        explicit BatchScope(bool enable) : on(enable && batch_small_components()) {
+            if (on) air_batch().depth++;
+        }
+        ~BatchScope() {
+            if (on) air_batch().depth--;
+        }
+        BatchScope(const BatchScope&) = delete;
+        BatchScope& operator=(const BatchScope&) = delete;
+    };
+    static bool batching(u32 log_size) { return air_batch().depth > 0 && log_size <= SMALL_BATCH_LOG; }
+    static void air_batch_flush() {
+        AirBatch& b = air_batch();
+        if (b.items.empty() && b.finals.empty()) return;
+        // on the SIDE lane: the columns of the recorded programs were allocated there (lane(small size)), so allocation,
+        // writes and reads follow one stream order; what they read from lane 0 was issued before the fork
+        cm_check(cm31_lane(1));
+        if (!b.items.empty()) {
+            std::vector<cm31_air_batch_item> v(b.items.size());
+            for (size_t i = 0; i < v.size(); i++) {
+                const AirBatch::Item& it = b.items[i];
+                v[i] = cm31_air_batch_item{it.in.data(), it.in.size(), it.out.data(), it.out.size(), it.log_size, it.code.data(), it.code.size(),
+                                           it.n_regs, it.consts.data(), it.consts.size(), it.hist_bins};
+            }
+            cm_check(cm31_air_program_batch(v.data(), v.size()));
+            b.items.clear();
+        }
+        if (!b.finals.empty()) {
+            cm_check(cm31_logup_finalize_small_batch(b.finals.data(), b.finals.size()));
+            b.finals.clear();
+        }
+    }
     static size_t len(const Col& c) { return c.size(); }
     // ---- single-proof sharding hooks (no-ops when sharding is off)
     static int shard_world() { return Shard::get().on ? Shard::get().world : 1; }
@@ -598,6 +661,10 @@ struct CudaBackend {
         if (Shard::get().skip()) return;
         auto s = cptrs(in);
         auto d = ptrs(out);
+        if (batching(log_size)) {
+            air_batch().items.push_back(AirBatch::Item{std::move(s), std::move(d), prog.code, prog.consts, log_size, prog.n_regs, 0});
+            return;
+        }
         cm_check(cm31_air_program(s.data(), s.size(), d.data(), d.size(), log_size, prog.code.data(), prog.code.size(), prog.n_regs,
                                   prog.consts.data(), prog.consts.size()));
     }
@@ -608,6 +675,10 @@ struct CudaBackend {
         u32 log_bins = 0;
         while (((size_t)1 << log_bins) < bins.size()) log_bins++;
         if (((size_t)1 << log_bins) != bins.size()) throw std::logic_error("air_lookups: the bin column is not a power of two");
+        if (batching(log_size)) {
+            air_batch().items.push_back(AirBatch::Item{std::move(s), std::vector<u32*>{bins.ptr()}, prog.code, prog.consts, log_size, prog.n_regs, 1u << log_bins});
+            return;
+        }
         cm_check(cm31_air_lookups(s.data(), s.size(), bins.ptr(), log_bins, log_size, prog.code.data(), prog.code.size(), prog.n_regs,
                                   prog.consts.data(), prog.consts.size()));
     }
@@ -633,7 +704,10 @@ struct CudaBackend {
         if (a.used >= 256) throw CudaError("too many pending claimed sums");
         u32* l4[4] = {last[0]->ptr(), last[1]->ptr(), last[2]->ptr(), last[3]->ptr()};
         a.owned.push_back(Shard::get().skip() ? 0 : 1);
-        if (a.owned.back()) cm_check(cm31_logup_finalize_last_async(l4, log_size, a.buf.ptr() + 4 * a.used));
+        if (a.owned.back() && batching(log_size))  // after the recorded logup program that writes these columns
+            air_batch().finals.push_back(cm31_logup_finalize_item{{l4[0], l4[1], l4[2], l4[3]}, log_size, a.buf.ptr() + 4 * a.used});
+        else if (a.owned.back())
+            cm_check(cm31_logup_finalize_last_async(l4, log_size, a.buf.ptr() + 4 * a.used));
         return a.used++;
     }
     static std::vector<QM31> collect_sums() {

@@ -714,6 +714,12 @@ static int prove_impl(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_
         HostTimer::report();
         return rc;
     } catch (const std::exception& e) {
+        {  // programs recorded for a batch that will never be issued point into columns that are gone
+            CudaBackend::AirBatch& b = CudaBackend::air_batch();
+            b.items.clear();
+            b.finals.clear();
+            b.depth = 0;
+        }
         cm31_lanes_join();  // an error may have been raised while the side lane was current
         set_error(e.what());
         return -2;

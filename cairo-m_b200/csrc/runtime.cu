@@ -85,13 +85,16 @@ static size_t g_stage_pos = 0;
 constexpr size_t STAGE_BYTES = 16u << 20;
 
 int DeviceTable::upload(const void* host, size_t bytes) {
+    if (int e = reserve(bytes)) return e;
+    return fill(host, bytes == 0 ? 0 : bytes);
+}
+int DeviceTable::reserve(size_t bytes) {
     release();
     if (bytes == 0) bytes = 4;
     if (bytes > STAGE_BYTES / 4) {  // large: own allocation, plain copy (the runtime stages pageable sources itself)
         if (int e = ensure_pool()) return e;
         CM_CUDA(cudaMallocAsync(&d, bytes, stream()));
         owned = true;
-        CM_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, stream()));
         return 0;
     }
     if (!g_stage) {
@@ -105,11 +108,20 @@ int DeviceTable::upload(const void* host, size_t bytes) {
         if (g_side) CM_CUDA(cudaStreamSynchronize(g_side));
         g_stage_pos = 0;
     }
-    if (host) memcpy(g_stage + g_stage_pos, host, bytes);
     d = g_stage_dev + g_stage_pos;
+    ring_at = g_stage_pos;
     owned = false;
-    CM_CUDA(cudaMemcpyAsync(d, g_stage + g_stage_pos, bytes, cudaMemcpyHostToDevice, stream()));
     g_stage_pos += need;
+    return 0;
+}
+int DeviceTable::fill(const void* host, size_t bytes) {
+    if (!host || bytes == 0) return 0;
+    if (owned) {
+        CM_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, stream()));
+        return 0;
+    }
+    memcpy(g_stage + ring_at, host, bytes);
+    CM_CUDA(cudaMemcpyAsync(d, g_stage + ring_at, bytes, cudaMemcpyHostToDevice, stream()));
     return 0;
 }
 void DeviceTable::release() {

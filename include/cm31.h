@@ -282,6 +282,24 @@ int cm31_air_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* cons
  * "lookup outside its table" (the reference panics on the slice index).  cm31_air_program refuses programs with OP_HIST. */
 int cm31_air_lookups(const uint32_t* const* in_cols, size_t n_in, uint32_t* bins, uint32_t log_bins, uint32_t log_size,
                      const uint64_t* code, size_t n_instr, uint32_t n_regs, const uint32_t* consts, size_t n_consts);
+/* MANY small programs (log_size <= 12) in ONE launch: every item is a cm31_air_program call (hist_bins == 0) or a
+ * cm31_air_lookups call (hist_bins = 2^log_bins, out_cols[0] = the bin column).  Items must be independent of each other.
+ * cairo-m proves 34 components per segment whatever the program; the ones a program does not use are 16 padding rows each,
+ * and their trace-fill (Claim::write_trace), lookup and logup programs are pure launch latency one by one. */
+typedef struct cm31_air_batch_item {
+    const uint32_t* const* in_cols; /* host array of n_in device pointers */
+    size_t n_in;
+    uint32_t* const* out_cols;
+    size_t n_out;
+    uint32_t log_size;
+    const uint64_t* code;
+    size_t n_instr;
+    uint32_t n_regs;
+    const uint32_t* consts;
+    size_t n_consts;
+    uint32_t hist_bins;
+} cm31_air_batch_item;
+int cm31_air_program_batch(const cm31_air_batch_item* items, size_t n_items);
 /* reads (one 4-byte copy, synchronises the current lane) and clears the error bits AIR programs raised since the last call */
 int cm31_air_error_check(void);
 /* finalize_last (logup.rs:211-251): claimed_sum = sum(last col); last col -= claimed_sum/n;
@@ -290,6 +308,13 @@ int cm31_logup_finalize_last(uint32_t* const last4[4], uint32_t log_size, uint32
 /* same, stream-ordered: the claimed sum lands in 4 DEVICE words; the prover reads the sums of all
  * components with one copy after the interaction trace is generated */
 int cm31_logup_finalize_last_async(uint32_t* const last4[4], uint32_t log_size, uint32_t* claimed_sum_dev);
+/* the same for many small columns (log_size <= 11) in one launch */
+typedef struct cm31_logup_finalize_item {
+    uint32_t* last4[4];
+    uint32_t log_size;
+    uint32_t* claimed_sum_dev;
+} cm31_logup_finalize_item;
+int cm31_logup_finalize_small_batch(const cm31_logup_finalize_item* items, size_t n_items);
 /* multiplicity histograms (P/src/preprocessed/range_check/range_check_macro.rs:72-84) */
 int cm31_histogram(const uint32_t* values, size_t n, uint32_t* bins, uint32_t log_bins);
 /* Pack::pack for ExecutionBundle + get_access_field (P/src/utils/execution_bundle.rs:31-75, P/src/utils/data_accesses.rs:10-28):

@@ -66,6 +66,12 @@ struct OracleAirImpl {
     static void staging_wait(u32) {}
     static void staging_release_point(int) {}
     static void idle_gate_open() {}
+    struct BatchScope {
+        explicit BatchScope(bool) {}
+    };
+    static bool batch_small_components() { return false; }
+    static void air_batch_flush() {}
+    static std::vector<Col> unpack_padding(const Words&, size_t, u32) { throw std::logic_error("the oracle does not batch"); }
     static void copy_words(Words& dst, size_t at, const u32* src, size_t n_words) { std::copy(src, src + n_words, dst.begin() + at); }
     static std::vector<Col> unpack_bundles(const Words& row_words, size_t n_real, const Words& access_words, size_t n_accesses, u32 log_size) {
         const cm31::Bundle* rows = (const cm31::Bundle*)row_words.data();
