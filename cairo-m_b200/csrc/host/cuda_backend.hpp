@@ -133,6 +133,26 @@ class DeviceCol {
         return out;
     }
 
+    // columns of DIFFERENT sizes carved out of one allocation (the levels of a small Merkle tree)
+    static std::vector<DeviceCol> carve(const std::vector<size_t>& sizes) {
+        std::vector<DeviceCol> out(sizes.size());
+        size_t total = 0;
+        for (size_t n : sizes) total += (n + 3) & ~(size_t)3;
+        if (total == 0) return out;
+        u32* base = nullptr;
+        cm_check(cm31_malloc((void**)&base, total * 4));
+        std::shared_ptr<void> slab(base, [](void* p) { cm31_free(p); });
+        size_t at = 0;
+        for (size_t i = 0; i < sizes.size(); i++) {
+            out[i].p_ = base + at;
+            out[i].n_ = sizes[i];
+            out[i].slab_ = slab;
+            Shard::get().on_alloc(out[i].p_);
+            at += (sizes[i] + 3) & ~(size_t)3;
+        }
+        return out;
+    }
+
    private:
     void release() {
         if (slab_) slab_.reset();
@@ -635,6 +655,62 @@ struct CudaBackend {
             d4[k] = dst[k].ptr();
         }
         cm_check(cm31_accumulate(d4, s4, dst[0].size()));
+    }
+    // The inner FRI layers of at most 2^fri_tail_log() points: one launch for the whole chain (cm31_fri_tail), the channel
+    // replayed on the host from the roots.  Appends the layers to `inner_layers`, leaves the last evaluation in layer_eval.
+    static u32 fri_tail_log() {
+        static const u32 l = getenv("CM31_FRI_TAIL_LOG") ? (u32)atoi(getenv("CM31_FRI_TAIL_LOG")) : 12;
+        return Shard::get().on ? 0 : std::min<u32>(l, 14);
+    }
+    template <class InnerLayer, class SecureEval>
+    static void fri_tail(Blake2sChannel& channel, std::array<Col, 4>& layer_eval, u32& layer_log, u32 last_log,
+                         const std::vector<SecureEval>& columns, size_t& next_col, const Twiddles& tw, std::vector<InnerLayer>& inner_layers) {
+        const size_t n_layers = layer_log - last_log;
+        std::vector<cm31_fri_tail_layer> desc(n_layers);
+        std::vector<std::vector<u32*>> level_ptrs(n_layers);
+        std::vector<std::vector<HashCol>> trees(n_layers);
+        std::vector<std::array<Col, 4>> evals(n_layers + 1);
+        evals[0] = std::move(layer_eval);
+        for (size_t i = 0; i < n_layers; i++) {
+            const u32 k = layer_log - (u32)i;
+            std::vector<Col> nxt = Col::many(4, (size_t)1 << (k - 1));
+            for (int c = 0; c < 4; c++) evals[i + 1][c] = std::move(nxt[c]);
+            std::vector<size_t> sizes;
+            for (u32 j = 0; j <= k; j++) sizes.push_back(((size_t)1 << j) * 8);
+            trees[i] = DeviceCol::carve(sizes);
+            for (u32 j = 0; j <= k; j++) level_ptrs[i].push_back(trees[i][j].ptr());
+            cm31_fri_tail_layer& d = desc[i];
+            for (int c = 0; c < 4; c++) {
+                d.ev_in[c] = evals[i][c].ptr();
+                d.ev_out[c] = evals[i + 1][c].ptr();
+                d.circle[c] = nullptr;
+            }
+            d.tree_levels = level_ptrs[i].data();
+            d.log_size = k;
+            if (next_col < columns.size() && columns[next_col].log_size == k) {  // joins the line of 2^(k-1) points (fri.rs:255-262)
+                for (int c = 0; c < 4; c++) d.circle[c] = columns[next_col].columns[c].ptr();
+                next_col++;
+            }
+        }
+        const Hash32 digest = channel.digest();
+        u32 din[8];
+        memcpy(din, digest.b, 32);
+        std::vector<u32> roots(8 * n_layers);
+        cm_check(cm31_fri_tail(din, desc.data(), n_layers, tw.h, roots.data()));
+        for (size_t i = 0; i < n_layers; i++) {
+            InnerLayer layer;
+            memcpy(layer.root.b, &roots[8 * i], 32);
+            channel.mix_root(layer.root);
+            (void)channel.draw_secure_felt();  // the folding alpha the kernel derived from the same digest
+            layer.log_size = layer_log - (u32)i;
+            layer.evaluation = std::move(evals[i]);
+            layer.merkle_tree.layers = std::move(trees[i]);  // [0] = root layer .. [k] = leaves
+            layer.merkle_tree.root_ = layer.root;
+            layer.merkle_tree.root_read_ = true;
+            inner_layers.push_back(std::move(layer));
+        }
+        layer_eval = std::move(evals[n_layers]);
+        layer_log = last_log;
     }
     static std::vector<QM31> generate_secure_powers(QM31 felt, size_t n) {
         std::vector<u32> out(4 * n + 4);

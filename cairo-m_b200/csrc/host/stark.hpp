@@ -729,6 +729,13 @@ struct FriProver {
         B::fold_circle_into_line(layer_eval, columns[next_col].columns, columns[next_col].log_size, folding_alpha, twiddles);
         next_col++;
         while (((size_t)1 << layer_log) > config.last_layer_domain_size()) {
+            if (layer_log <= B::fri_tail_log()) {
+                // the remaining (small) layers: one launch for the whole chain, Fiat-Shamir included; the roots come back and
+                // the channel is replayed from them (same transcript)
+                B::template fri_tail<InnerLayer>(channel, layer_eval, layer_log, ilog2(config.last_layer_domain_size()), columns, next_col,
+                                                 twiddles, fp.inner_layers);
+                break;
+            }
             InnerLayer layer;
             std::vector<const Col*> cc;
             for (auto& c : layer_eval) cc.push_back(&c);

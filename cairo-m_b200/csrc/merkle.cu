@@ -9,8 +9,10 @@
 // lives in 16 registers and is refilled 16 columns at a time.
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "blake2s.cuh"
+#include "circle.hpp"
 #include "common.cuh"
 
 namespace cm31 {
@@ -216,6 +218,120 @@ __global__ void __launch_bounds__(1024) merkle_top_kernel(u32 top_log, const u32
     }
 }
 
+// ------------------------------------------------------------------ FRI tail: the small inner layers in ONE launch
+// FriProver::commit_inner_layers (fri.rs:226-266) below 2^FRI_TAIL_LOG points is a chain of tiny, strictly dependent steps:
+// Merkle tree of the layer (blake2_merkle.rs), root -> channel.mix_root, channel.draw_secure_felt -> alpha (channel/blake2s.rs),
+// fold_line (fri.rs:1132-1157) [+ fold_circle_into_line of a column that joins at this size, fri.rs:1159-1189].  Issued from the
+// host that is 3-4 launches and one device->host round trip PER LAYER (~60-85 us each, ~1 ms per proof for the last dozen
+// layers).  Here a single CTA runs the whole chain, Fiat-Shamir included: the Blake2s channel lives in shared memory, the host
+// gets the roots back and replays mix_root / draw on its own channel (microseconds) so both transcripts stay identical.
+struct FriTailLayerDev {
+    const u32* in[4];
+    u32* out[4];
+    u32* lvl[16];         // lvl[j] = hash layer with 2^j nodes of this layer's tree
+    const u32* circ[4];   // circle evaluation (log = this layer's log) folded into `out`, or null
+    const u32* itw_line;  // 1/x twiddles of the line domain
+    const u32* itw_circ;  // first line layer pairs the 1/y twiddles are derived from (circle log > 2)
+    u32 log, has_circ, iy0, iy1;
+};
+__device__ __forceinline__ QM31 ldcg4(const u32* const* c, size_t i) { return qm_make(__ldcg(c[0] + i), __ldcg(c[1] + i), __ldcg(c[2] + i), __ldcg(c[3] + i)); }
+
+__global__ void __launch_bounds__(1024) fri_tail_kernel(const FriTailLayerDev* __restrict__ layers, u32 n_layers, const u32* __restrict__ digest_in,
+                                                        u32* __restrict__ roots_out) {
+    __shared__ u32 sh_digest[8];
+    __shared__ u32 sh_alpha[4];
+    const u32 tid = threadIdx.x;
+    if (tid < 8) sh_digest[tid] = digest_in[tid];
+    __syncthreads();
+    for (u32 li = 0; li < n_layers; li++) {
+        const FriTailLayerDev& L = layers[li];
+        const u32 k = L.log;
+        // ---- leaves: Blake2s of the 4 coordinate words (one 16-byte block)
+        for (u32 n = tid; n < (1u << k); n += blockDim.x) {
+            Blake2sState st;
+            blake2s_init(st);
+            u32 m[16];
+#pragma unroll
+            for (int c = 0; c < 4; c++) m[c] = __ldcg(L.in[c] + n);
+#pragma unroll
+            for (int c = 4; c < 16; c++) m[c] = 0;
+            blake2s_compress(st, m, 16, true);
+            uint4* o = reinterpret_cast<uint4*>(L.lvl[k] + (size_t)n * 8);
+            o[0] = make_uint4(st.h[0], st.h[1], st.h[2], st.h[3]);
+            o[1] = make_uint4(st.h[4], st.h[5], st.h[6], st.h[7]);
+        }
+        __syncthreads();
+        // ---- inner levels
+        for (int j = (int)k - 1; j >= 0; j--) {
+            for (u32 n = tid; n < (1u << j); n += blockDim.x) hash_node<true>(n, L.lvl[j + 1], nullptr, 0, L.lvl[j]);
+            __syncthreads();
+        }
+        // ---- Fiat-Shamir: mix_root, draw_secure_felt (channel/blake2s.rs:60-116)
+        if (tid == 0) {
+            u32 m[16];
+            Blake2sState st;
+            blake2s_init(st);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                m[i] = sh_digest[i];
+                const u32 r = __ldcg(L.lvl[0] + i);
+                m[8 + i] = r;
+                roots_out[li * 8 + i] = r;
+            }
+            blake2s_compress(st, m, 64, true);
+#pragma unroll
+            for (int i = 0; i < 8; i++) sh_digest[i] = st.h[i];
+            for (u32 n_sent = 0;; n_sent++) {  // draw_base_felts: retry until all 8 words are below 2P
+                Blake2sState d;
+                blake2s_init(d);
+#pragma unroll
+                for (int i = 0; i < 8; i++) m[i] = sh_digest[i];
+                m[8] = n_sent;
+#pragma unroll
+                for (int i = 9; i < 16; i++) m[i] = 0;
+                blake2s_compress(d, m, 36, true);
+                bool ok = true;
+#pragma unroll
+                for (int i = 0; i < 8; i++) ok = ok && d.h[i] < 2 * P;
+                if (ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) sh_alpha[i] = d.h[i] >= P ? d.h[i] - P : d.h[i];
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- fold_line (+ fold_circle_into_line with the same alpha)
+        const QM31 alpha = qm_make(sh_alpha[0], sh_alpha[1], sh_alpha[2], sh_alpha[3]);
+        const QM31 alpha_sq = qm_sqr(alpha);
+        for (u32 n = tid; n < (1u << (k - 1)); n += blockDim.x) {
+            const QM31 f0 = ldcg4(L.in, 2 * (size_t)n), f1 = ldcg4(L.in, 2 * (size_t)n + 1);
+            const u32 it = __ldg(L.itw_line + n);
+            QM31 v = qm_add(qm_add(f0, f1), qm_mul(alpha, qm_mul_m31(qm_sub(f0, f1), it)));
+            if (L.has_circ) {
+                const QM31 c0 = qm_make(__ldg(L.circ[0] + 2 * n), __ldg(L.circ[1] + 2 * n), __ldg(L.circ[2] + 2 * n), __ldg(L.circ[3] + 2 * n));
+                const QM31 c1 = qm_make(__ldg(L.circ[0] + 2 * n + 1), __ldg(L.circ[1] + 2 * n + 1), __ldg(L.circ[2] + 2 * n + 1), __ldg(L.circ[3] + 2 * n + 1));
+                u32 ity;
+                if (k <= 2) {
+                    ity = n == 0 ? L.iy0 : L.iy1;
+                } else {
+                    const u32 x = __ldg(L.itw_circ + 2 * (n >> 2)), y = __ldg(L.itw_circ + 2 * (n >> 2) + 1);
+                    const u32 sel = n & 3;
+                    const u32 w = sel < 2 ? y : x;
+                    ity = (sel == 1 || sel == 2) ? m31_neg(w) : w;
+                }
+                const QM31 fp = qm_add(qm_mul(alpha, qm_mul_m31(qm_sub(c0, c1), ity)), qm_add(c0, c1));
+                v = qm_add(qm_mul(v, alpha_sq), fp);
+            }
+            L.out[0][n] = v.a;
+            L.out[1][n] = v.b;
+            L.out[2][n] = v.c;
+            L.out[3][n] = v.d;
+        }
+        __syncthreads();
+    }
+}
+
 // Layers log_size, log_size-1, .., log_size-n_levels+1 in ONE launch, when only the first of them carries columns (FRI
 // layer trees, the composition tree, the gaps between column sizes of a trace tree): a CTA hashes 256 nodes of the
 // first layer and keeps halving inside the block, so a tree costs a few launches instead of one per layer.
@@ -383,6 +499,59 @@ int cm31_blake2s_commit_top(uint32_t top_log_size, const uint32_t* prev_layer, c
     if (threads < 64) threads = 64;  // the sigma table is built by the first 40 threads
     merkle_top_kernel<<<1, threads, 0, stream()>>>(top_log_size, prev_layer, (const u32* const*)dcols.d, args, use_quads);
     CM_LAUNCH_CHECK();
+    return 0;
+}
+
+int cm31_fri_tail(const uint32_t digest_in[8], const cm31_fri_tail_layer* layers, size_t n_layers, const cm31_twiddles* tw,
+                  uint32_t* roots_out_host) {
+    if (n_layers == 0) return 0;
+    CM_REQUIRE(digest_in != nullptr && layers != nullptr && tw != nullptr && roots_out_host != nullptr, "fri_tail: null argument");
+    CM_REQUIRE(n_layers <= 16, "fri_tail: too many layers");
+    static thread_local std::vector<FriTailLayerDev> host;
+    host.assign(n_layers, FriTailLayerDev());
+    uint64_t bytes = 0;
+    for (size_t i = 0; i < n_layers; i++) {
+        const cm31_fri_tail_layer& l = layers[i];
+        CM_REQUIRE(l.log_size >= 1 && l.log_size <= 15 && l.log_size + 1 <= tw->log_size, "fri_tail: bad layer size");
+        CM_REQUIRE(i == 0 || l.log_size + 1 == layers[i - 1].log_size, "fri_tail: layers must halve");
+        FriTailLayerDev& d = host[i];
+        for (int k = 0; k < 4; k++) {
+            d.in[k] = l.ev_in[k];
+            d.out[k] = l.ev_out[k];
+            d.circ[k] = l.circle[k];
+        }
+        for (u32 j = 0; j <= l.log_size; j++) d.lvl[j] = l.tree_levels[j];
+        d.log = l.log_size;
+        d.has_circ = l.circle[0] != nullptr;
+        // twiddle tree levels as in cm31_fold_line / cm31_fold_circle_into_line (fri.cu): the inverse-twiddle level whose coset
+        // is half_odds(c) starts at 2^(M-1) - 2^c
+        d.itw_line = tw->itw + (((size_t)1 << (tw->log_size - 1)) - ((size_t)1 << l.log_size));
+        d.itw_circ = nullptr;
+        d.iy0 = d.iy1 = 0;
+        if (d.has_circ) {  // the circle evaluation has log size l.log_size and folds into 2^(log_size-1) line points
+            if (l.log_size <= 2) {
+                CircleDomain dom = CanonicCoset(l.log_size).circle_domain();
+                d.iy0 = m31_inv(dom.at(bit_reverse(0, l.log_size)).y);
+                d.iy1 = l.log_size == 2 ? m31_inv(dom.at(bit_reverse(2, l.log_size)).y) : 0;
+            } else {
+                d.itw_circ = tw->itw + (((size_t)1 << (tw->log_size - 1)) - ((size_t)1 << (l.log_size - 1)));
+            }
+        }
+        bytes += (16ull + 96ull + 24ull) << l.log_size;
+    }
+    DeviceTable dl, dd;
+    if (int e = dl.upload(host.data(), n_layers * sizeof(FriTailLayerDev))) return e;
+    if (int e = dd.upload(digest_in, 32)) return e;
+    u32* droots = nullptr;
+    CM_CUDA(cudaMallocAsync(&droots, n_layers * 32, stream()));
+    {
+        ProfScope prof("fri_tail", bytes);
+        fri_tail_kernel<<<1, 1024, 0, stream()>>>((const FriTailLayerDev*)dl.d, (u32)n_layers, (const u32*)dd.d, droots);
+        CM_LAUNCH_CHECK();
+    }
+    CM_CUDA(cudaMemcpyAsync(roots_out_host, droots, n_layers * 32, cudaMemcpyDeviceToHost, stream()));
+    CM_CUDA(cudaFreeAsync(droots, stream()));
+    CM_CUDA(cudaStreamSynchronize(stream()));
     return 0;
 }
 

@@ -235,6 +235,21 @@ int cm31_fold_line(const uint32_t* const src4[4], uint32_t log_size, const uint3
  * dst[i] = dst[i]*alpha^2 + fold(src)[i], dst has 2^(log_size-1) values */
 int cm31_fold_circle_into_line(uint32_t* const dst4[4], const uint32_t* const src4[4], uint32_t log_size,
                                const uint32_t alpha[4], const cm31_twiddles* tw);
+/* The small inner layers of FriProver::commit_inner_layers (S/prover/src/core/fri.rs:226-266) in ONE launch, Fiat-Shamir
+ * included: per layer the Blake2s Merkle tree of the 4 coordinate columns, root -> mix_root, draw_secure_felt -> alpha
+ * (S/prover/src/core/channel/blake2s.rs:60-116), fold_line and -- where a column joins at that size -- fold_circle_into_line
+ * with the same alpha.  digest_in = the channel digest before the first mix_root; roots_out_host receives the n_layers roots
+ * (8 words each): the caller replays mix_root / draw_secure_felt on its own channel, which keeps both transcripts identical.
+ * layers[i].log_size halves from layer to layer; tree_levels[j] = hash layer with 2^j nodes (j = 0 .. log_size). */
+typedef struct cm31_fri_tail_layer {
+    const uint32_t* ev_in[4];
+    uint32_t* ev_out[4];
+    uint32_t* const* tree_levels;
+    const uint32_t* circle[4]; /* all NULL when no column joins after this fold */
+    uint32_t log_size;
+} cm31_fri_tail_layer;
+int cm31_fri_tail(const uint32_t digest_in[8], const cm31_fri_tail_layer* layers, size_t n_layers, const cm31_twiddles* tw,
+                  uint32_t* roots_out_host);
 int cm31_decompose(const uint32_t* const src4[4], uint32_t log_size, uint32_t* const dst4[4],
                    uint32_t lambda_out[4]);
 

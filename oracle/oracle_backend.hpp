@@ -127,6 +127,12 @@ struct OracleBackend {
         return store.data();
     }
     static void gather_wait() {}
+    static u32 fri_tail_log() { return 0; }  // the CPU backend folds layer by layer
+    template <class InnerLayer, class SecureEval, class Tw>
+    static void fri_tail(cm31::Blake2sChannel&, std::array<Col, 4>&, u32&, u32, const std::vector<SecureEval>&, size_t&, const Tw&,
+                         std::vector<InnerLayer>&) {
+        throw std::logic_error("fri_tail: not available on the CPU backend");
+    }
     static bool defer_proof_tail() { return false; }
     static void finish_deferred_tails() {}
     static cm31::Hash32 read_root(const HashCol& root_layer) {
