@@ -96,3 +96,29 @@ def test_malformed_json_is_refused(cm, blob):
         n = C.c_size_t()
         assert cm.lib().cm31_proof_from_json(raw, C.c_size_t(len(raw)), None, C.c_size_t(0), C.byref(n)) != 0
         assert b"proof json" in cm.lib().cm31_last_error()
+
+
+def test_fibonacci_public_memory_contents(cm):
+    # crates/prover/tests/prover.rs:373-449: the proof's public memory holds (1) the return value in the output range,
+    # (2) the input argument in the input range, (3) the program, word for word, in the program range
+    n = 5
+    blob, _ = ch.oracle_program_prove(ch.FIB, n)
+    pm = json.loads(to_json(cm, blob))["public_data"]["public_memory"]
+    values = lambda entries: [e[1] for e in entries if e is not None]
+    assert values(pm["output"]) == [[[ch.fib_mod_p(n), 0], [0, 0]]], "the return value of fibonacci_loop(n)"
+    assert values(pm["input"]) == [[[n, 0], [0, 0]]], "the input argument"
+    # the program as the runner preloaded it (the VM's initial memory below the input cell)
+    lib = cm.lib()
+    h = C.c_void_p()
+    cm.check(lib.cm31_test_vm_trace_create(C.c_uint32(ch.FIB), C.c_uint32(n), C.byref(h)))
+    try:
+        init = C.POINTER(C.c_uint32)()
+        ranges = (C.c_uint32 * 6)()
+        cm.check(lib.cm31_test_vm_trace_data(h, None, None, C.byref(init), ranges))
+        program_start, program_end = ranges[0], ranges[1]
+        words = [[[init[4 * a], init[4 * a + 1]], [init[4 * a + 2], init[4 * a + 3]]] for a in range(program_start, program_end)]
+    finally:
+        lib.cm31_test_vm_trace_destroy(h)
+    got = values(pm["program"])
+    assert len(got) == len(words) == program_end - program_start and got == words, "program in public memory == program loaded by the runner"
+    assert [e[0] for e in pm["program"] if e is not None] == list(range(program_start, program_end))
