@@ -624,6 +624,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         components.for_each([&](auto& comp) { proof.interaction_claim.claimed_sums.push_back(comp.claimed_sum); });
         for (auto& s : proof.interaction_claim.claimed_sums) channel.mix_felts({s});  // InteractionClaim::mix_into
         traces.clear();
+        Impl::idle_gate_open();  // second stage of a previous proof's deferred tail (assembly + serialisation)
         Impl::staging_release_point(2);
         commitment_scheme.commit_evals(std::move(interaction), channel);
     }

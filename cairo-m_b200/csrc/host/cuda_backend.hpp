@@ -539,31 +539,37 @@ struct CudaBackend {
     static void gather_wait() { cm_check(cm31_gather_wait()); }
     // Deferred proof tails (cm31_prove_cairo_m_async): while `defer` is set, prove_values leaves the host-side assembly of the
     // decommitments to a closure; the owner of the pending proof registers `hook`, which runs it (and serialises the proof).
-    // The hook fires at the first Merkle-root read after idle_gate_open() -- the prover opens the gate before the commitment
-    // of the execution traces, where milliseconds of FFT / Merkle kernels are queued and the host would only wait -- or at the
-    // latest before the next gather (finish_deferred_tails).
+    // One stage of the hook runs at the first Merkle-root read after each idle_gate_open() -- the prover opens the gate before
+    // the commitments of the execution traces (stage: queries, decommitment plan, gather) and of the interaction traces
+    // (stage: assembly, serialisation), where milliseconds of FFT / Merkle kernels are queued and the host would only wait --
+    // and whatever is left runs before the next proof defers its own tail (finish_deferred_tails).
     struct TailState {
         bool defer = false;
         bool gate = false;
-        std::function<void()> hook;
+        std::function<bool()> hook;  // runs ONE stage of the pending proof's tail; true after the last
     };
     static TailState& tail_state() {
         static TailState t;
         return t;
     }
-    static bool defer_proof_tail() { return tail_state().defer; }
+    static bool defer_proof_tail() { return tail_state().defer && !Shard::get().on; }
+    static void run_tail_stage() {
+        TailState& t = tail_state();
+        if (!t.hook) return;
+        std::function<bool()> h = t.hook;  // (the stage may register nothing new; keep the hook until it reports completion)
+        if (h()) t.hook = nullptr;
+    }
     static void finish_deferred_tails() {
         TailState& t = tail_state();
         t.gate = false;
-        if (t.hook) {
-            std::function<void()> h = std::move(t.hook);
-            t.hook = nullptr;
-            h();
-        }
+        while (t.hook) run_tail_stage();
     }
     static void idle_gate_open() { tail_state().gate = true; }
     static Hash32 read_root(const HashCol& root_layer) {
-        if (tail_state().gate) finish_deferred_tails();  // the kernels of this tree are queued: host time is free until its root arrives
+        if (tail_state().gate) {  // the kernels of this tree are queued: host time is free until its root arrives
+            tail_state().gate = false;
+            run_tail_stage();
+        }
         Hash32 h;
         cm_check(cm31_d2h(h.b, root_layer.ptr(), 32));
         if (getenv("CM31_SHARD_DEBUG")) {

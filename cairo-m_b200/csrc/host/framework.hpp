@@ -229,6 +229,23 @@ class FrameworkComponent : public ComponentProver<B> {
         }
         return out;
     }
+    void fill_mask_points(SecurePoint point, MaskPoints& out, std::vector<size_t>& at) const override {
+        CirclePointM31 trace_step = CanonicCoset(log_size()).step();
+        std::vector<std::pair<int, SecurePoint>> shifted;
+        shifted.reserve(8);
+        auto at_off = [&](int off) -> const SecurePoint& {
+            if (off == 0) return point;
+            for (auto& kv : shifted)
+                if (kv.first == off) return kv.second;
+            shifted.emplace_back(off, secure_point_add_m31(point, cp_mul_signed(trace_step, off)));
+            return shifted.back().second;
+        };
+        for (int t = 1; t < 3; t++)
+            for (auto& offsets : ev.mask_offsets[t]) {
+                std::vector<SecurePoint>& pts = out[(size_t)t][at[(size_t)t]++];
+                for (size_t k = 0; k < offsets.size(); k++) pts[k] = at_off(offsets[k]);
+            }
+    }
     std::vector<size_t> preprocessed_column_indices() const override { return preprocessed_indices; }
 
     std::vector<QM31> eval_params() const {

@@ -112,15 +112,21 @@ struct CommitmentSchemeProof {
     std::vector<std::vector<u32>> queried_values;
     u64 proof_of_work = 0;
     FriProof fri_proof;
-    // Deferred tail (B::defer_proof_tail()): the decommitment values of this proof are still travelling device->host; the
-    // closure waits for them and fills queried_values / decommitments / fri_proof.  resolve() must run before the proof is
-    // read; the CUDA prover runs it while the NEXT proof keeps the GPU busy (cm31_prove_cairo_m_async).
-    std::shared_ptr<std::function<void(CommitmentSchemeProof&)>> pending_tail;
+    // Deferred tail (B::defer_proof_tail()): everything after the proof-of-work nonce -- query generation, decommitment
+    // planning, the gather of the queried values and the assembly of queried_values / decommitments / fri_proof -- is left to
+    // a closure that owns the trees and FRI layers.  resolve() must run before the proof is read; the CUDA prover runs the
+    // stages while the NEXT proof keeps the GPU busy (cm31_prove_cairo_m_async).
+    // The tail runs in STAGES (each call does one and returns true after the last): planning + gather, then assembly, so that
+    // each can be placed behind a different commitment of the next proof.
+    std::shared_ptr<std::function<bool(CommitmentSchemeProof&)>> pending_tail;
+    bool step() {  // one stage; true once nothing is pending
+        if (!pending_tail) return true;
+        if ((*pending_tail)(*this)) pending_tail.reset();
+        return !pending_tail;
+    }
     void resolve() {
-        if (!pending_tail) return;
-        auto f = std::move(pending_tail);
-        pending_tail.reset();
-        (*f)(*this);
+        while (!step()) {
+        }
     }
 };
 typedef CommitmentSchemeProof StarkProof;
@@ -974,14 +980,10 @@ CommitmentSchemeProof CommitmentSchemeProver<B>::prove_values(const std::vector<
     samples_flat.reserve(n_cols_total);
     sampled_flat.reserve(values.size());
     for (size_t t = 0; t < trees.size(); t++) {
-        proof.sampled_values.emplace_back();
-        proof.sampled_values.back().reserve(trees[t].polynomials.size());
         for (size_t c = 0; c < trees[t].polynomials.size(); c++) {
-            const size_t k = sampled_points[t][c].size();
-            proof.sampled_values.back().emplace_back(values.begin() + vi, values.begin() + vi + k);
             samples_flat.emplace_back();
             std::vector<PointSample>& col_samples = samples_flat.back();
-            col_samples.reserve(k);
+            col_samples.reserve(sampled_points[t][c].size());
             for (const SecurePoint& p : sampled_points[t][c]) {
                 col_samples.push_back(PointSample{p, values[vi]});
                 sampled_flat.push_back(values[vi]);
@@ -997,6 +999,18 @@ CommitmentSchemeProof CommitmentSchemeProver<B>::prove_values(const std::vector<
     QM31 random_coeff = channel.draw_secure_felt();
     ht.reset(new HostTimer("pv_quotients"));
     std::vector<SecureEvaluation<B>> quotients = compute_fri_quotients<B>(columns, samples_flat, random_coeff, config.fri_config.log_blowup_factor);
+    {  // proof.sampled_values ([tree][column][sample]): assembled while the quotient kernels run
+        size_t v2 = 0;
+        for (size_t t = 0; t < trees.size(); t++) {
+            proof.sampled_values.emplace_back();
+            proof.sampled_values.back().reserve(trees[t].polynomials.size());
+            for (size_t c = 0; c < trees[t].polynomials.size(); c++) {
+                const size_t k = sampled_points[t][c].size();
+                proof.sampled_values.back().emplace_back(values.begin() + v2, values.begin() + v2 + k);
+                v2 += k;
+            }
+        }
+    }
 
     if (after_sampling) {
         ht.reset(new HostTimer("pv_after_sampling_hook"));
@@ -1008,43 +1022,66 @@ CommitmentSchemeProof CommitmentSchemeProver<B>::prove_values(const std::vector<
     ht.reset(new HostTimer("pv_grind"));
     proof.proof_of_work = B::grind(channel.digest(), config.pow_bits);
     channel.mix_u64(proof.proof_of_work);
-    ht.reset(new HostTimer("pv_decommit_plan"));
+    proof.commitments = roots();  // (cached at commit time: no device read)
 
     // FRI + the 4 trees decommit through one batched device gather
-    GatherQueue<B> queue;
-    auto fri_res = fri_prover.plan_decommit(channel, queue);
-    const std::map<u32, std::vector<size_t>>& query_positions_per_log_size = fri_res.second;
-    std::vector<typename MerkleProver<B>::PendingDecommit> pending;
-    ht.reset(new HostTimer("pv_decommit_plan_trees"));
-    for (auto& t : trees) pending.push_back(t.plan_decommit(queue, query_positions_per_log_size));
-    ht.reset(new HostTimer("pv_decommit_flush"));
-    B::finish_deferred_tails();  // a previous proof's tail reads the landing buffer this gather is about to take over
-    queue.flush_async();
-    proof.commitments = roots();  // (cached at commit time: no device read)
     struct Tail {
-        typename FriProver<B>::PendingFriProof fri;
+        // deferred form only: the prover state the decommitment reads, moved out of this call
+        std::vector<CommitmentTreeProver<B>> trees;
+        std::vector<SecureEvaluation<B>> quotients;
+        std::unique_ptr<FriProver<B>> fri;
+        Blake2sChannel channel;
+        // both forms
+        typename FriProver<B>::PendingFriProof fri_pending;
         std::vector<typename MerkleProver<B>::PendingDecommit> pending;
         GatherQueue<B> queue;
+        int stage = 0;
     };
-    auto st = std::make_shared<Tail>();
-    st->fri = std::move(fri_res.first);
-    st->pending = std::move(pending);
-    st->queue = std::move(queue);
-    auto tail = [st](CommitmentSchemeProof& p) {
+    auto plan_and_gather = [](std::vector<CommitmentTreeProver<B>>& tr, FriProver<B>& fp, Blake2sChannel& ch, Tail& st) {
+        std::unique_ptr<HostTimer> h(new HostTimer("pv_decommit_plan"));
+        auto fri_res = fp.plan_decommit(ch, st.queue);
+        st.fri_pending = std::move(fri_res.first);
+        h.reset(new HostTimer("pv_decommit_plan_trees"));
+        for (auto& t : tr) st.pending.push_back(t.plan_decommit(st.queue, fri_res.second));
+        h.reset(new HostTimer("pv_decommit_flush"));
+        st.queue.flush_async();
+    };
+    auto finish = [](CommitmentSchemeProof& p, Tail& st) {
         HostTimer ht2("pv_decommit_finish");
-        st->queue.wait();
-        p.fri_proof = st->fri.finish(st->queue);
-        for (auto& pd : st->pending) {
-            auto res = pd.finish(st->queue);
+        st.queue.wait();
+        p.fri_proof = st.fri_pending.finish(st.queue);
+        for (auto& pd : st.pending) {
+            auto res = pd.finish(st.queue);
             p.queried_values.push_back(std::move(res.first));
             p.decommitments.push_back(std::move(res.second));
         }
     };
     ht.reset();
-    if (B::defer_proof_tail())
-        proof.pending_tail = std::make_shared<std::function<void(CommitmentSchemeProof&)>>(tail);
-    else
-        tail(proof);
+    B::finish_deferred_tails();  // a previous proof's tail must be complete before this one takes over the landing buffer / the hook
+    auto st = std::make_shared<Tail>();
+    if (B::defer_proof_tail()) {
+        st->trees = std::move(trees);
+        st->quotients = std::move(quotients);
+        st->fri.reset(new FriProver<B>(std::move(fri_prover)));
+        st->fri->columns = &st->quotients;
+        st->channel = channel;
+        proof.pending_tail = std::make_shared<std::function<bool(CommitmentSchemeProof&)>>([st, plan_and_gather, finish](CommitmentSchemeProof& p) {
+            if (st->stage == 0) {
+                plan_and_gather(st->trees, *st->fri, st->channel, *st);
+                // the gather is enqueued: the device buffers of the proof go back to the pool (stream-ordered after it)
+                st->fri.reset();
+                st->quotients.clear();
+                st->trees.clear();
+                st->stage = 1;
+                return false;
+            }
+            finish(p, *st);
+            return true;
+        });
+    } else {
+        plan_and_gather(trees, fri_prover, channel, *st);
+        finish(proof, *st);
+    }
     return proof;
 }
 
@@ -1130,6 +1167,13 @@ struct ComponentProver {
     virtual u32 max_constraint_log_degree_bound() const = 0;
     virtual std::vector<std::vector<u32>> trace_log_degree_bounds() const = 0;
     virtual MaskPoints mask_points(SecurePoint point) const = 0;
+    // Overwrites the points of this component's columns inside an already SHAPED MaskPoints (trees 1.., `at[t]` = its first
+    // column in tree t, advanced past its columns): same values as mask_points(point), no allocation.
+    virtual void fill_mask_points(SecurePoint point, MaskPoints& out, std::vector<size_t>& at) const {
+        MaskPoints mp = mask_points(point);
+        for (size_t t = 1; t < mp.size(); t++)
+            for (auto& col : mp[t]) out[t][at[t]++] = col;
+    }
     virtual std::vector<size_t> preprocessed_column_indices() const = 0;
     virtual void evaluate_constraint_quotients_at_point(SecurePoint point, const MaskValues& mask, PointEvaluationAccumulator& acc) const = 0;
     virtual void evaluate_constraint_quotients_on_domain(const Trace<B>& trace, DomainEvaluationAccumulator<B>& acc) const = 0;
@@ -1157,6 +1201,14 @@ struct ComponentProvers {  // air/components.rs
         for (auto* c : components)
             for (size_t idx : c->preprocessed_column_indices()) out[PREPROCESSED_TRACE_IDX_()][idx] = {point};
         return out;
+    }
+    // the same result written into `out`, which has the shape of an earlier mask_points(..) call (made with any point while
+    // the GPU was busy): on the critical path between the composition root and the OODS launch only values are written
+    void fill_mask_points(SecurePoint point, MaskPoints& out) const {
+        std::vector<size_t> at(out.size(), 0);
+        for (auto* c : components) c->fill_mask_points(point, out, at);
+        for (auto* c : components)
+            for (size_t idx : c->preprocessed_column_indices()) out[PREPROCESSED_TRACE_IDX_()][idx][0] = point;
     }
     QM31 eval_composition_polynomial_at_point(SecurePoint point, const MaskValues& mask_values, QM31 random_coeff) const {
         PointEvaluationAccumulator acc(random_coeff);
@@ -1197,12 +1249,18 @@ StarkProof prove(const std::vector<const ComponentProver<B>*>& components, Blake
     ht0.reset(new HostTimer("composition_commit"));
     std::vector<CirclePoly<B>> comp_polys;
     for (auto& p : composition) comp_polys.push_back(std::move(p));
+    // the SHAPE of the sample points (which column is opened at how many points) does not depend on the OODS point: built now,
+    // while the composition kernels are still running; the values are filled in once the point is known
+    SecurePoint shape_point;
+    shape_point.x = qm_one();
+    shape_point.y = qm_zero();
+    MaskPoints sample_points = provers.mask_points(shape_point);
     commitment_scheme.commit_polys(std::move(comp_polys), channel);
     ht0.reset();
 
     SecurePoint oods_point = get_random_point(channel);
     std::unique_ptr<HostTimer> ht(new HostTimer("mask_points"));
-    MaskPoints sample_points = provers.mask_points(oods_point);
+    provers.fill_mask_points(oods_point, sample_points);
     // a component set without interaction columns commits fewer trees (TreeVec is sized by use)
     size_t n_trace_trees = commitment_scheme.trees.size() - 1;
     while (sample_points.size() > n_trace_trees && sample_points.back().empty()) sample_points.pop_back();

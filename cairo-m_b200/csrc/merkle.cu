@@ -240,8 +240,11 @@ __global__ void __launch_bounds__(1024) fri_tail_kernel(const FriTailLayerDev* _
                                                         u32* __restrict__ roots_out) {
     __shared__ u32 sh_digest[8];
     __shared__ u32 sh_alpha[4];
+    __shared__ u32 quad_msg[(1u << QUAD_MAX_LOG) * 16];
+    __shared__ u32 quad_sig[4][10];
     const u32 tid = threadIdx.x;
     if (tid < 8) sh_digest[tid] = digest_in[tid];
+    quad_sigma_init(quad_sig);
     __syncthreads();
     for (u32 li = 0; li < n_layers; li++) {
         const FriTailLayerDev& L = layers[li];
@@ -263,7 +266,14 @@ __global__ void __launch_bounds__(1024) fri_tail_kernel(const FriTailLayerDev* _
         __syncthreads();
         // ---- inner levels
         for (int j = (int)k - 1; j >= 0; j--) {
-            for (u32 n = tid; n < (1u << j); n += blockDim.x) hash_node<true>(n, L.lvl[j + 1], nullptr, 0, L.lvl[j]);
+            if (j <= (int)QUAD_MAX_LOG) {  // few nodes: 4 lanes per node (latency of one compression / ~3), as in merkle_top_kernel
+                if (tid < (4u << j)) {
+                    const u32 mask = (4u << j) >= 32u ? 0xffffffffu : ((1u << (4u << j)) - 1u);
+                    hash_node_quad(tid >> 2, L.lvl[j + 1], nullptr, 0, L.lvl[j], quad_msg + (tid >> 2) * 16, tid & 3u, quad_sig, mask);
+                }
+            } else {
+                for (u32 n = tid; n < (1u << j); n += blockDim.x) hash_node<true>(n, L.lvl[j + 1], nullptr, 0, L.lvl[j]);
+            }
             __syncthreads();
         }
         // ---- Fiat-Shamir: mix_root, draw_secure_felt (channel/blake2s.rs:60-116)

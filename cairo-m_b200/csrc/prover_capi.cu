@@ -613,21 +613,26 @@ struct PendingProofOut {
     std::string err;
 };
 static PendingProofOut g_pending_out;
-static void finish_pending_proof() {
+static bool finish_pending_stage() {  // one stage of the pending proof's tail; true once nothing is pending
     PendingProofOut& p = g_pending_out;
-    if (!p.proof) return;
-    std::unique_ptr<CairoProof> proof = std::move(p.proof);
+    if (!p.proof) return true;
     try {
-        proof->stark_proof.resolve();
+        if (!p.proof->stark_proof.step()) return false;
         HostTimer ht("proof_to_bytes");
         static thread_local ProofWriter writer;
         writer.bytes.clear();
-        proof->write(writer);
+        p.proof->write(writer);
         p.rc = write_out(writer.bytes, p.out, p.cap, p.len);
         if (p.rc) p.err = cm31_last_error();
     } catch (const std::exception& e) {
         p.rc = -2;
         p.err = e.what();
+    }
+    p.proof.reset();
+    return true;
+}
+static void finish_pending_proof() {
+    while (!finish_pending_stage()) {
     }
 }
 static int prove_impl(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out, size_t proof_cap,
@@ -698,7 +703,7 @@ static int prove_impl(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_
             g_pending_out.out = proof_out;
             g_pending_out.cap = proof_cap;
             g_pending_out.len = proof_len;
-            CudaBackend::tail_state().hook = finish_pending_proof;
+            CudaBackend::tail_state().hook = finish_pending_stage;
             HostTimer::report();
             return 0;
         }
