@@ -202,6 +202,29 @@ __global__ void __launch_bounds__(256) quotients_fast_kernel(u32 log_size, const
             for (u32 i = t; i < cnt * 2; i += 256) sh_entries[i] = __ldg(reinterpret_cast<const uint4*>(entries + k0) + i);
             __syncthreads();
             u32 k = 0;
+            for (; k + 8 <= cnt; k += 8) {  // 8 independent column reads in flight (ncu r02: long_scoreboard 31 % with 4)
+                u32 f[8];
+#pragma unroll
+                for (u32 j = 0; j < 8; j++) {
+                    const uint4 e0 = sh_entries[2 * (k + j)];
+                    f[j] = __ldg(reinterpret_cast<const u32*>(((u64)e0.y << 32) | e0.x) + row);
+                }
+#pragma unroll
+                for (u32 h = 0; h < 2; h++) {  // 4 products of < 2^62 fit a u64 on top of a folded carry
+#pragma unroll
+                    for (u32 j = 4 * h; j < 4 * h + 4; j++) {
+                        const uint4 c = sh_entries[2 * (k + j) + 1];
+                        n0 += (u64)f[j] * c.x;
+                        n1 += (u64)f[j] * c.y;
+                        n2 += (u64)f[j] * c.z;
+                        n3 += (u64)f[j] * c.w;
+                    }
+                    n0 = fold64(n0);
+                    n1 = fold64(n1);
+                    n2 = fold64(n2);
+                    n3 = fold64(n3);
+                }
+            }
             for (; k + 4 <= cnt; k += 4) {
                 u32 f[4];
 #pragma unroll
