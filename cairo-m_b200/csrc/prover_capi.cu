@@ -609,10 +609,17 @@ struct PendingProofOut {
     uint8_t* out = nullptr;
     size_t cap = 0;
     size_t* len = nullptr;
-    int rc = 0;
-    std::string err;
 };
 static PendingProofOut g_pending_out;
+static int g_tail_rc = 0;  // status of the last deferred tail that ran; reported (and cleared) by take_tail_status()
+static std::string g_tail_err;
+static int take_tail_status() {
+    int rc = g_tail_rc;
+    if (rc) set_error("deferred tail of an asynchronous proof: " + g_tail_err);
+    g_tail_rc = 0;
+    g_tail_err.clear();
+    return rc;
+}
 static bool finish_pending_stage() {  // one stage of the pending proof's tail; true once nothing is pending
     PendingProofOut& p = g_pending_out;
     if (!p.proof) return true;
@@ -622,11 +629,14 @@ static bool finish_pending_stage() {  // one stage of the pending proof's tail; 
         static thread_local ProofWriter writer;
         writer.bytes.clear();
         p.proof->write(writer);
-        p.rc = write_out(writer.bytes, p.out, p.cap, p.len);
-        if (p.rc) p.err = cm31_last_error();
+        int rc = write_out(writer.bytes, p.out, p.cap, p.len);
+        if (rc) {
+            g_tail_rc = rc;
+            g_tail_err = cm31_last_error();
+        }
     } catch (const std::exception& e) {
-        p.rc = -2;
-        p.err = e.what();
+        g_tail_rc = -2;
+        g_tail_err = e.what();
     }
     p.proof.reset();
     return true;
@@ -637,10 +647,10 @@ static void finish_pending_proof() {
 }
 static int prove_impl(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out, size_t proof_cap,
                       size_t* proof_len, double* timings_ms, bool async);
-// Returns once the proof's kernels and the device->host copy of its decommitment values are enqueued; proof_out / proof_len
-// are written later -- during the next cm31_prove_cairo_m[_async] call on this thread or by cm31_prove_wait(), whichever
-// comes first -- and must stay valid until then.  A failure of the deferred part is reported by the call that ran it
-// (cm31_prove_wait, or the next cm31_prove_cairo_m_async, returns it).
+// Returns once the proof-of-work nonce of the proof is known; proof_out / proof_len are written later -- during the next
+// cm31_prove_cairo_m[_async] call on this thread or by cm31_prove_wait(), whichever comes first -- and must stay valid until
+// then.  When call i+1 returns 0, proof i is complete and its bytes are valid; a failure of a deferred part is reported by
+// the call that ran it ("deferred tail of an asynchronous proof: ..").
 int cm31_prove_cairo_m_async(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out,
                              size_t proof_cap, size_t* proof_len, double* timings_ms) {
     return prove_impl(h, pow_bits, n_queries, proof_out, proof_cap, proof_len, timings_ms, true);
@@ -648,12 +658,7 @@ int cm31_prove_cairo_m_async(const cm31_prover_input* h, uint32_t pow_bits, uint
 int cm31_prove_wait(void) {
     CudaBackend::finish_deferred_tails();
     finish_pending_proof();  // (no hook registered: e.g. the proof failed before its tail was deferred)
-    PendingProofOut& p = g_pending_out;
-    int rc = p.rc;
-    if (rc) set_error(p.err);
-    p.rc = 0;
-    p.err.clear();
-    return rc;
+    return take_tail_status();
 }
 int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out,
                        size_t proof_cap, size_t* proof_len, double* timings_ms) {
@@ -666,12 +671,7 @@ static int prove_impl(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_
         ~DeferGuard() { CudaBackend::tail_state().defer = false; }
     } defer_guard;
     try {
-        if (g_pending_out.rc) {  // the deferred part of the previous asynchronous proof failed: report it now
-            int rc = g_pending_out.rc;
-            set_error(g_pending_out.err);
-            g_pending_out.rc = 0;
-            return rc;
-        }
+        if (int rc = take_tail_status()) return rc;  // a deferred tail failed since the last call: report it now
         CudaBackend::tail_state().defer = async;
         CM_REQUIRE(h != nullptr, "prove_cairo_m: null input");
         PcsConfig cfg = PcsConfig::regular_96_bits();
@@ -705,7 +705,8 @@ static int prove_impl(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_
             g_pending_out.len = proof_len;
             CudaBackend::tail_state().hook = finish_pending_stage;
             HostTimer::report();
-            return 0;
+            // the previous asynchronous proof was completed inside this call: a zero return also vouches for ITS bytes
+            return take_tail_status();
         }
         proof.stark_proof.resolve();
         int rc;

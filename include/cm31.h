@@ -373,7 +373,8 @@ int cm31_prove_cairo_m(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n
 /* Asynchronous form for a prover fed with a stream of segments: returns once the proof's kernels and the device->host copy of
  * its decommitment values are enqueued.  proof_out / proof_len are written later -- while the NEXT proof of this thread keeps
  * the GPU busy, or by cm31_prove_wait() -- and must stay valid until then; one proof may be pending at a time.  The bytes are
- * identical to cm31_prove_cairo_m's.  cm31_prove_wait() completes the pending proof and returns its status. */
+ * identical to cm31_prove_cairo_m's.  When the NEXT call returns 0 the previous proof is complete and its bytes are valid;
+ * cm31_prove_wait() completes the pending proof and returns its status. */
 int cm31_prove_cairo_m_async(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_queries, uint8_t* proof_out,
                              size_t proof_cap, size_t* proof_len, double* timings_ms);
 int cm31_prove_wait(void);

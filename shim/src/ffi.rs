@@ -97,6 +97,10 @@ extern "C" {
     pub fn cm31_adapter_prefetch(trace: *const u32, n_trace: usize, memory_trace: *const u32, n_mem: usize, initial_memory: *const u32, n_initial: usize, public_ranges: *const u32, out: *mut *mut Cm31AdapterLogs) -> c_int;
     pub fn cm31_adapter_import_prefetched(logs: *mut Cm31AdapterLogs, out: *mut *mut Cm31ProverInput) -> c_int;
     pub fn cm31_prove_cairo_m(h: *const Cm31ProverInput, pow_bits: u32, n_queries: u32, proof_out: *mut u8, cap: usize, proof_len: *mut usize, timings_ms: *mut f64) -> c_int;
+    // a stream of segments: the tail of proof i runs under proof i+1
+    pub fn cm31_prove_cairo_m_async(h: *const Cm31ProverInput, pow_bits: u32, n_queries: u32, proof_out: *mut u8, cap: usize, proof_len: *mut usize, timings_ms: *mut f64) -> c_int;
+    pub fn cm31_prove_wait() -> c_int;
+    pub fn cm31_proof_to_json(proof: *const u8, proof_len: usize, json_out: *mut c_char, cap: usize, json_len: *mut usize) -> c_int;
     pub fn cm31_prove_cairo_m_json(h: *const Cm31ProverInput, pow_bits: u32, n_queries: u32, json_out: *mut c_char, cap: usize, json_len: *mut usize) -> c_int;
 }
 

@@ -216,3 +216,50 @@ pub fn emit_component_lookups(program: &AirProgram, trace: &[DeviceColumn], bins
 pub fn check_lookups() {
     check(unsafe { cm31_air_error_check() });
 }
+
+/// One proof per continuation segment (`crates/prover/tests/prover.rs:204-243`), pipelined: while segment i is being proven the
+/// input of segment i+1 travels to the device (`cm31_input_prefetch`: the running proof releases the copy as a throttled copy
+/// kernel at its STARK phase), and the host-side tail of proof i -- query generation, decommitment planning, the gather of the
+/// queried values, assembly and serialisation -- runs under the trace / interaction commitments of proof i+1
+/// (`cm31_prove_cairo_m_async`).  The proofs are byte-identical to `prove_cairo_m_cuda`'s.
+pub fn prove_segments_cuda(inputs: &[CudaProverInput], pcs_config: Option<PcsConfig>) -> Result<Vec<Proof<Blake2sMerkleHasher>>, ProvingError> {
+    let cfg = pcs_config.unwrap_or_else(PcsConfig::default);
+    const CAP: usize = 1 << 26;
+    let mut bufs = [vec![0u8; CAP], vec![0u8; CAP]];
+    let mut lens = [0usize; 2];
+    let mut proofs = Vec::with_capacity(inputs.len());
+    let mut collect = |buf: &[u8], len: usize, proofs: &mut Vec<Proof<Blake2sMerkleHasher>>| -> Result<(), ProvingError> {
+        // blob -> the reference's serde JSON -> Proof (cm31_proof_to_json, crates/prover/src/lib.rs:61-73)
+        let mut n = 0usize;
+        check(unsafe { cm31_proof_to_json(buf.as_ptr(), len, std::ptr::null_mut(), 0, &mut n) });
+        let mut js = vec![0u8; n + 1];
+        check(unsafe { cm31_proof_to_json(buf.as_ptr(), len, js.as_mut_ptr() as *mut c_char, js.len(), &mut n) });
+        proofs.push(sonic_rs::from_slice(&js[..n]).map_err(|_| ProvingError::ConstraintsNotSatisfied)?);
+        Ok(())
+    };
+    if let Some(first) = inputs.first() {
+        check(unsafe { cm31_input_prefetch(first.0) });
+    }
+    for (i, input) in inputs.iter().enumerate() {
+        if let Some(next) = inputs.get(i + 1) {
+            check(unsafe { cm31_input_prefetch(next.0) });
+        }
+        // submitting proof i completes proof i-1 at the latest: its bytes are in the other buffer
+        let rc = unsafe {
+            cm31_prove_cairo_m_async(input.0, cfg.pow_bits, cfg.fri_config.n_queries as u32, bufs[i & 1].as_mut_ptr(), CAP, &mut lens[i & 1], std::ptr::null_mut())
+        };
+        if rc != 0 {
+            return Err(ProvingError::ConstraintsNotSatisfied);
+        }
+        if i > 0 {
+            // (a zero return of call i also vouches for proof i-1, which was completed inside it)
+            collect(&bufs[(i - 1) & 1], lens[(i - 1) & 1], &mut proofs)?;
+        }
+    }
+    if !inputs.is_empty() {
+        check(unsafe { cm31_prove_wait() });
+        let i = inputs.len() - 1;
+        collect(&bufs[i & 1], lens[i & 1], &mut proofs)?;
+    }
+    Ok(proofs)
+}
