@@ -54,6 +54,9 @@ class ClockSampler(threading.Thread):
         self.max_mhz = None
         self._stop_evt = threading.Event()
         self.ok = False
+        self.period = float(os.environ.get("CM31_CLOCK_SAMPLE_PERIOD", "0.01"))
+        if os.environ.get("CM31_NO_SAMPLER"):
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -89,7 +92,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(self.period)
 
     def stop(self):
         self._stop_evt.set()

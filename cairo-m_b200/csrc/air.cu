@@ -533,7 +533,7 @@ int cm31_air_program_batch(const cm31_air_batch_item* items, size_t n_items) {
     for (size_t i = 0; i < n_items; i++) {
         const cm31_air_batch_item& it = items[i];
         CM_REQUIRE(it.log_size <= 12, "air_program_batch: small programs only");
-        CM_REQUIRE(it.n_regs <= 2048, "air: program needs more than 2048 registers");
+        CM_REQUIRE(it.n_regs <= 512, "air_program_batch: programs of at most 512 registers (larger register files live in local memory: see CudaBackend::BATCH_MAX_REGS)");
         for (size_t k = 0; k < it.n_instr; k++) {
             const u32 op = (u32)(it.code[k] & 0xff);
             CM_REQUIRE(op != OP_HIST || it.hist_bins != 0, "air_program_batch: a histogram program needs its bin count");
@@ -583,9 +583,7 @@ int cm31_air_program_batch(const cm31_air_batch_item* items, size_t n_items) {
     if (max_regs <= 64) CM_AIR_BATCH(64);
     else if (max_regs <= 128) CM_AIR_BATCH(128);
     else if (max_regs <= 256) CM_AIR_BATCH(256);
-    else if (max_regs <= 512) CM_AIR_BATCH(512);
-    else if (max_regs <= 1024) CM_AIR_BATCH(1024);
-    else CM_AIR_BATCH(2048);
+    else CM_AIR_BATCH(512);
 #undef CM_AIR_BATCH
     CM_LAUNCH_CHECK();
     return 0;

@@ -482,7 +482,15 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         traces.push_back(Impl::template write_trace<Eval>(eval, inputs, (u32)rows.n_real));
     };
     B::prepare();
-#define CM31_X(E) opcode_trace(E{});
+    static const bool phase_debug = getenv("CM31_PHASE_DEBUG") != nullptr;
+    double dbg_t = Impl::now_ms();
+    auto dbg = [&](const char* what) {
+        if (!phase_debug) return;
+        double now = Impl::now_ms();
+        fprintf(stderr, "[phase] %-28s %8.3f ms\n", what, now - dbg_t);
+        dbg_t = now;
+    };
+#define CM31_X(E) opcode_trace(E{}); dbg(#E);
     CM31_OPCODE_EVALS(CM31_X)
 #undef CM31_X
     {
@@ -526,9 +534,12 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
         traces.push_back(Impl::template write_trace<Poseidon2Eval>(eval, inputs, (u32)staged.poseidon2.n_real));
     }
     B::component_scope(-1);
+    dbg("memory..poseidon2 traces");
     Impl::air_batch_flush();  // the trace programs of the unused components: one launch
+    dbg("trace batch flush");
     B::lanes_join();
     padding_inputs.clear();
+    dbg("join");
     // range-check multiplicities: histogram of every value the opcode components look up
     // (opcodes/mod.rs:83-105 providers; range_check_macro.rs:72-84).  The AIR graphs drive it.
     RelationSet dummy_relations;
@@ -559,8 +570,10 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
             shape.for_each(emit);
         }
         B::component_scope(-1);
+        dbg("lookups issued");
         Impl::air_batch_flush();
         B::lanes_join();
+        dbg("lookups flush+join");
         for (auto& bins : all_bins) B::allreduce_bins(bins);  // sharded proof: multiplicities are sums over the ranks' components
         for (size_t ti = 0; ti < tables.size(); ti++) {
             auto& tb = tables[ti];
@@ -587,6 +600,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     }
     // "lookup outside its table": a witness value that no range-check / bitwise table holds raised the device error word
     // in the histogram kernels above; it is read here, where the root of tree 1 has just synchronised the host anyway
+    dbg("tree 1 commit");
     Impl::check_lookups();
     auto t2 = Impl::now_ms();
 

@@ -227,7 +227,12 @@ struct CudaBackend {
         BatchScope(const BatchScope&) = delete;
         BatchScope& operator=(const BatchScope&) = delete;
     };
-    static bool batching(u32 log_size) { return air_batch().depth > 0 && log_size <= SMALL_BATCH_LOG; }
+    // Programs that need more than 512 interpreter registers stay on their own (generated) kernels: the interpreter keeps its
+    // register file in local memory, and a launch that needs more local memory per thread than any kernel before makes the
+    // driver re-size its local-memory arena -- a device-wide synchronisation, and a shrink afterwards (measured on the sha256
+    // workload, whose unused components include 1024-register programs: trace phase 10 -> 95 ms).
+    static constexpr u32 BATCH_MAX_REGS = 512;
+    static bool batching(u32 log_size, u32 n_regs) { return air_batch().depth > 0 && log_size <= SMALL_BATCH_LOG && n_regs <= BATCH_MAX_REGS; }
     static void air_batch_flush() {
         AirBatch& b = air_batch();
         if (b.items.empty() && b.finals.empty()) return;
@@ -743,7 +748,7 @@ struct CudaBackend {
         if (Shard::get().skip()) return;
         auto s = cptrs(in);
         auto d = ptrs(out);
-        if (batching(log_size)) {
+        if (batching(log_size, prog.n_regs)) {
             air_batch().items.push_back(AirBatch::Item{std::move(s), std::move(d), prog.code, prog.consts, log_size, prog.n_regs, 0});
             return;
         }
@@ -757,7 +762,7 @@ struct CudaBackend {
         u32 log_bins = 0;
         while (((size_t)1 << log_bins) < bins.size()) log_bins++;
         if (((size_t)1 << log_bins) != bins.size()) throw std::logic_error("air_lookups: the bin column is not a power of two");
-        if (batching(log_size)) {
+        if (batching(log_size, prog.n_regs)) {
             air_batch().items.push_back(AirBatch::Item{std::move(s), std::vector<u32*>{bins.ptr()}, prog.code, prog.consts, log_size, prog.n_regs, 1u << log_bins});
             return;
         }
@@ -786,7 +791,7 @@ struct CudaBackend {
         if (a.used >= 256) throw CudaError("too many pending claimed sums");
         u32* l4[4] = {last[0]->ptr(), last[1]->ptr(), last[2]->ptr(), last[3]->ptr()};
         a.owned.push_back(Shard::get().skip() ? 0 : 1);
-        if (a.owned.back() && batching(log_size))  // after the recorded logup program that writes these columns
+        if (a.owned.back() && batching(log_size, 0))  // after the logup program that writes these columns, recorded or already issued on the side lane
             air_batch().finals.push_back(cm31_logup_finalize_item{{l4[0], l4[1], l4[2], l4[3]}, log_size, a.buf.ptr() + 4 * a.used});
         else if (a.owned.back())
             cm_check(cm31_logup_finalize_last_async(l4, log_size, a.buf.ptr() + 4 * a.used));

@@ -672,6 +672,27 @@ static int prove_impl(const cm31_prover_input* h, uint32_t pow_bits, uint32_t n_
     } defer_guard;
     try {
         if (int rc = take_tail_status()) return rc;  // a deferred tail failed since the last call: report it now
+        {  // pool head-room (cm31_pool_reserve_headroom) from the high-water mark of the proofs made so far: before the second
+           // and the third proof of the process -- i.e. inside any warm-up -- and again only if a later proof at least doubles
+           // the mark (a much larger input)
+            static uint64_t n_proofs = 0, seen_high = 0;
+            static const bool off = getenv("CM31_NO_POOL_HEADROOM") != nullptr;
+            if (!off && n_proofs > 0) {
+                int dev = 0;
+                cudaMemPool_t pool;
+                uint64_t high = 0;
+                if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess &&
+                    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &high) == cudaSuccess) {
+                    if (n_proofs <= 2 || high >= 2 * seen_high) {
+                        seen_high = std::max(seen_high, high);
+                        cm31_pool_reserve_headroom(n_proofs == 1 ? 2.5 : 1.5);
+                    }
+                } else {
+                    cudaGetLastError();
+                }
+            }
+            n_proofs++;
+        }
         CudaBackend::tail_state().defer = async;
         CM_REQUIRE(h != nullptr, "prove_cairo_m: null input");
         PcsConfig cfg = PcsConfig::regular_96_bits();

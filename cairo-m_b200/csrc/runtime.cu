@@ -315,6 +315,38 @@ int cm31_profile_trace(char* buf, size_t cap, size_t* len) {
     return 0;
 }
 
+// Head-room for the stream-ordered pool.  Growing the pool (cuMemCreate + map) while kernels are running stalls the caller for
+// 30-240 ms on some boxes (round 1: the first step with two prover inputs in flight; round 2: proofs whose buffers outlive the
+// call -- cm31_prove_cairo_m_async keeps the trees of proof i until proof i+1 has gathered from them -- make the free list
+// differ from proof to proof, so a request occasionally fits no cached block).  cm31_pool_reserve_headroom(factor) makes the pool
+// hold factor x its high-water mark of bytes in use: one allocation + free while the GPU is idle, after which later requests
+// are served from cached memory.  Best effort: failures (not enough free memory) are ignored.
+int cm31_pool_reserve_headroom(double factor) {
+    int dev = 0;
+    CM_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    CM_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t used_high = 0, reserved = 0;
+    CM_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &used_high));
+    CM_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved));
+    const uint64_t want = (uint64_t)((double)used_high * factor);
+    if (want <= reserved) return 0;
+    size_t free_b = 0, total_b = 0;
+    CM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t extra = want - reserved;
+    if (extra + (8ull << 30) > free_b) return 0;  // keep 8 GB clear of the pool
+    CM_CUDA(cudaStreamSynchronize(g_main));
+    if (g_side) CM_CUDA(cudaStreamSynchronize(g_side));
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, extra, g_main) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    CM_CUDA(cudaFreeAsync(p, g_main));
+    CM_CUDA(cudaStreamSynchronize(g_main));
+    return 0;
+}
+
 int cm31_malloc(void** out, size_t bytes) {
     CM_REQUIRE(out != nullptr, "malloc: null out");
     if (bytes == 0) bytes = 4;

@@ -49,6 +49,10 @@ int cm31_lane(int lane);
 int cm31_lanes_join(void);
 /* Column<T>::zeros / uninitialized / to_cpu / from_iter  (S/prover/src/core/backend/mod.rs:46-65) */
 int cm31_malloc(void** out, size_t bytes);
+/* Makes the stream-ordered pool hold `factor` x its high-water mark of bytes in use (one allocation + free with the GPU idle):
+ * growing the pool while kernels run stalls the caller for 30-240 ms on some systems.  cm31_prove_cairo_m[_async] calls it
+ * after the first proofs of a process (factor 2.5); best effort, no error when memory is short. */
+int cm31_pool_reserve_headroom(double factor);
 int cm31_free(void* dptr);
 int cm31_memset0(void* dptr, size_t bytes);
 int cm31_h2d(void* dst, const void* src_host, size_t bytes);
@@ -297,7 +301,7 @@ int cm31_air_program(const uint32_t* const* in_cols, size_t n_in, uint32_t* cons
  * "lookup outside its table" (the reference panics on the slice index).  cm31_air_program refuses programs with OP_HIST. */
 int cm31_air_lookups(const uint32_t* const* in_cols, size_t n_in, uint32_t* bins, uint32_t log_bins, uint32_t log_size,
                      const uint64_t* code, size_t n_instr, uint32_t n_regs, const uint32_t* consts, size_t n_consts);
-/* MANY small programs (log_size <= 12) in ONE launch: every item is a cm31_air_program call (hist_bins == 0) or a
+/* MANY small programs (log_size <= 12, n_regs <= 512) in ONE launch: every item is a cm31_air_program call (hist_bins == 0) or a
  * cm31_air_lookups call (hist_bins = 2^log_bins, out_cols[0] = the bin column).  Items must be independent of each other.
  * cairo-m proves 34 components per segment whatever the program; the ones a program does not use are 16 padding rows each,
  * and their trace-fill (Claim::write_trace), lookup and logup programs are pure launch latency one by one. */
