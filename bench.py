@@ -262,6 +262,9 @@ def measure_adapter(cm, lib, torch, program_id, n, k_steps, vm_steps, proof_buf,
                                            ranges, C.byref(lg)))
         return lg
 
+    pbufs = [proof_buf, (C.c_uint8 * cap)()]
+    plens = [proof_len, C.c_size_t()]
+
     def pipelined(k):  # K uploads + K adapter runs + K proofs; the upload of segment i+1 is issued before segment i is adapted and proven
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,9 +274,10 @@ def measure_adapter(cm, lib, torch, program_id, n, k_steps, vm_steps, proof_buf,
             nxt = prefetch_logs() if step + 1 < k else None
             h = C.c_void_p()
             cm.check(lib.cm31_adapter_import_prefetched(lg, C.byref(h)))
-            cm.check(lib.cm31_prove_cairo_m(h, 16, 80, proof_buf, C.c_size_t(cap), C.byref(proof_len), tm))
+            cm.check(lib.cm31_prove_cairo_m_async(h, 16, 80, pbufs[step & 1], C.c_size_t(cap), C.byref(plens[step & 1]), tm))
             cm.check(lib.cm31_input_destroy(h))
             lg = nxt
+        cm.check(lib.cm31_prove_wait())
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / k

@@ -404,6 +404,7 @@ struct cm31_adapter_logs {  // cm31_adapter_prefetch: the logs on their way to H
     const uint32_t *trace = nullptr, *initial_memory = nullptr;
     size_t n_trace = 0, n_mem = 0, n_initial = 0;
     uint32_t ranges[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t bg_ticket = 0;  // deferred upload (cm31_bg_defer): released by a running proof or by cm31_adapter_import_prefetched
     ~cm31_adapter_logs() {
         if (plan) cm31_adapter_free(plan);
     }
@@ -524,7 +525,18 @@ int cm31_adapter_prefetch(const uint32_t* trace, size_t n_trace, const uint32_t*
                           size_t n_initial, const uint32_t public_ranges[6], cm31_adapter_logs** out) {
     CM_REQUIRE(out != nullptr, "adapter_prefetch: null argument");
     std::unique_ptr<cm31_adapter_logs> logs(new cm31_adapter_logs());
-    if (int e = adapter_stage(trace, n_trace, memory_trace, n_mem, initial_memory, n_initial, public_ranges, 1, *logs)) return e;
+    // like cm31_input_prefetch: the bulk copies are recorded; a running proof releases them (throttled) at its release point,
+    // cm31_adapter_import_prefetched at the latest
+    uint64_t ticket = 0;
+    const bool defer = CudaAirImpl::prefetch_point() >= 0;
+    if (defer) cm31_bg_defer(1, &ticket);
+    int e = adapter_stage(trace, n_trace, memory_trace, n_mem, initial_memory, n_initial, public_ranges, 1, *logs);
+    if (defer) cm31_bg_defer(0, nullptr);
+    if (e) {
+        if (ticket) cm31_bg_cancel(ticket);
+        return e;
+    }
+    logs->bg_ticket = ticket;
     *out = logs.release();
     return 0;
 }
@@ -533,9 +545,14 @@ int cm31_adapter_import_prefetched(cm31_adapter_logs* logs, cm31_prover_input** 
     CM_REQUIRE(logs != nullptr && out != nullptr, "adapter_import_prefetched: null argument");
     std::unique_ptr<cm31_adapter_logs> own(logs);
     CM_REQUIRE(own->plan != nullptr, "adapter_import_prefetched: the logs were already consumed");
+    if (own->bg_ticket) {
+        if (int e = cm31_bg_release(own->bg_ticket)) return e;  // (no-op when a proof released them already)
+        own->bg_ticket = 0;
+    }
     return adapter_finish(*own, out);
 }
 int cm31_adapter_logs_destroy(cm31_adapter_logs* logs) {
+    if (logs && logs->bg_ticket) cm31_bg_cancel(logs->bg_ticket);  // recorded, never issued
     if (logs && logs->plan) cm31_bg_fence();  // the upload may still be in flight: order the (stream-ordered) frees after it
     delete logs;
     return 0;

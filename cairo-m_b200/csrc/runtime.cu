@@ -465,12 +465,15 @@ __global__ void bg_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict_
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 static int bg_copy(void* dst, const void* src, size_t bytes, int throttle_ctas) {
-    if (throttle_ctas > 0 && bytes >= (1u << 20) && (((uintptr_t)dst | bytes) & 15) == 0) {
+    if (throttle_ctas > 0 && bytes >= (1u << 20) && ((uintptr_t)dst & 15) == 0) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, src) == cudaSuccess && at.devicePointer != nullptr && ((uintptr_t)at.devicePointer & 15) == 0 &&
             (at.type == cudaMemoryTypeHost)) {
-            bg_copy_kernel<<<throttle_ctas, 256, 0, g_copy_stream>>>((uint4*)dst, (const uint4*)at.devicePointer, bytes / 16);
+            const size_t body = bytes & ~(size_t)15;  // 16-byte words by the kernel, the last <= 15 bytes by a plain copy
+            bg_copy_kernel<<<throttle_ctas, 256, 0, g_copy_stream>>>((uint4*)dst, (const uint4*)at.devicePointer, body / 16);
             CM_LAUNCH_CHECK();
+            if (body < bytes)
+                CM_CUDA(cudaMemcpyAsync((uint8_t*)dst + body, (const uint8_t*)src + body, bytes - body, cudaMemcpyHostToDevice, g_copy_stream));
             return 0;
         }
         cudaGetLastError();
