@@ -391,6 +391,7 @@ CairoProof prove_cairo_m(const ProverInput& input, const StagedInput<Impl>& stag
     typedef typename Impl::B B;
     typedef typename B::Col Col;
     auto t0 = Impl::now_ms();
+    Span<B> whole_span("prove_cairo_m");  // P/src/prover.rs:30
     B::shard_begin_proof();  // single-proof sharding: arena reset + barrier; a no-op otherwise
     struct ShardEnd {
         ~ShardEnd() { B::shard_end_proof(); }

@@ -181,6 +181,8 @@ struct CudaBackend {
 
     // components / size groups of at most 2^LANE_SPLIT_LOG rows are issued on the side lane (cm31_lane)
     static constexpr u32 LANE_SPLIT_LOG = 12;
+    static void range_push(const char* name) { cm31_range_push(name); }
+    static void range_pop() { cm31_range_pop(); }
     static void lane(u32 log_size) {
         if (Shard::get().on) return;  // a sharded proof keeps one stream: its NCCL calls must be issued in one order on every rank
         cm_check(cm31_lane(log_size <= LANE_SPLIT_LOG ? 1 : 0));

@@ -61,6 +61,18 @@ struct HostTimer {
 };
 
 
+// A named range on the profiler timeline (NVTX on the CUDA backend, nothing on the CPU oracle), with the span names and
+// `class` fields of the reference's `tracing` spans (S/prover/src/core/pcs/prover.rs:41,89,127,177,219,223,
+// prover/mod.rs:45-51, air/accumulation.rs:111, pcs/quotients.rs:83; P/src/prover.rs:30), so an nsys / ncu timeline of this
+// prover reads like the reference's SpanAccumulator CSV.
+template <class B>
+struct Span {
+    explicit Span(const char* name) { B::range_push(name); }
+    ~Span() { B::range_pop(); }
+    Span(const Span&) = delete;
+    Span& operator=(const Span&) = delete;
+};
+
 struct FriConfig {
     u32 log_blowup_factor = 1;
     u32 log_last_layer_degree_bound = 0;
@@ -583,6 +595,8 @@ struct CommitmentTreeProver {
         // B::evaluate_polynomials, batched per log size (ops.rs:51-65)
         std::map<u32, std::vector<size_t>> by_size;
         for (size_t i = 0; i < t.polynomials.size(); i++) by_size[t.polynomials[i].log_size].push_back(i);
+        Span<B> commitment_span("Commitment");
+        std::unique_ptr<Span<B>> phase(new Span<B>("Extension"));
         for (auto& kv : by_size) {
             u32 log_size = kv.first, log_eval = log_size + log_blowup_factor;
             B::lane(log_size);  // size groups are independent until the Merkle tree reads them all
@@ -602,6 +616,8 @@ struct CommitmentTreeProver {
         B::shard_barrier();  // sharded proof: every rank's LDE columns are complete before any rank hashes rows across them
         std::vector<const typename B::Col*> cols;
         for (auto& e : t.evaluations) cols.push_back(&e.values);
+        phase.reset();
+        phase.reset(new Span<B>("Merkle"));
         t.commitment = MerkleProver<B>::commit(cols);
         channel.mix_root(t.commitment.root());
         return t;
@@ -639,9 +655,12 @@ struct CommitmentSchemeProver {
         }
         std::map<u32, std::vector<typename B::Col*>> by_size;
         for (auto& c : columns) by_size[c.log_size].push_back(&c.values);
-        for (auto& kv : by_size) {
-            B::lane(kv.first);
-            B::interpolate_columns(kv.second, kv.first, *twiddles);
+        {
+            Span<B> span("Interpolation for commitment");
+            for (auto& kv : by_size) {
+                B::lane(kv.first);
+                B::interpolate_columns(kv.second, kv.first, *twiddles);
+            }
         }
         B::lane(0xffffffffu);  // back to lane 0 (no join: each size stays on its lane through the LDE)
         std::vector<CirclePoly<B>> polys;
@@ -665,9 +684,12 @@ struct CommitmentSchemeProver {
                 by_size[kv.first].second.push_back(&polys[i].coeffs);
             }
         }
-        for (auto& kv : by_size) {
-            B::lane(kv.first);
-            B::interpolate_columns_to(kv.second.first, kv.second.second, kv.first, *twiddles);
+        {
+            Span<B> span("Interpolation for commitment");
+            for (auto& kv : by_size) {
+                B::lane(kv.first);
+                B::interpolate_columns_to(kv.second.first, kv.second.second, kv.first, *twiddles);
+            }
         }
         B::lane(0xffffffffu);
         commit_polys(std::move(polys), channel);
@@ -968,7 +990,10 @@ CommitmentSchemeProof CommitmentSchemeProver<B>::prove_values(const std::vector<
     }
     std::vector<QM31> values;
     ht.reset(new HostTimer("pv_eval_at_points"));
-    B::eval_at_points(polys, log_sizes, points, point_idx, values);
+    {
+        Span<B> span("Evaluate columns out of domain");
+        B::eval_at_points(polys, log_sizes, points, point_idx, values);
+    }
     ht.reset(new HostTimer("pv_assemble"));
     CommitmentSchemeProof proof;
     proof.config = config;
@@ -998,7 +1023,9 @@ CommitmentSchemeProof CommitmentSchemeProver<B>::prove_values(const std::vector<
         for (auto& e : t.evaluations) columns.push_back(&e);
     QM31 random_coeff = channel.draw_secure_felt();
     ht.reset(new HostTimer("pv_quotients"));
+    std::unique_ptr<Span<B>> qspan(new Span<B>("Compute FRI quotients"));
     std::vector<SecureEvaluation<B>> quotients = compute_fri_quotients<B>(columns, samples_flat, random_coeff, config.fri_config.log_blowup_factor);
+    qspan.reset();
     {  // proof.sampled_values ([tree][column][sample]): assembled while the quotient kernels run
         size_t v2 = 0;
         for (size_t t = 0; t < trees.size(); t++) {
@@ -1017,10 +1044,15 @@ CommitmentSchemeProof CommitmentSchemeProver<B>::prove_values(const std::vector<
         after_sampling(proof.sampled_values);
     }
     ht.reset(new HostTimer("pv_fri_commit"));
+    std::unique_ptr<Span<B>> fspan(new Span<B>("FRI commitment"));
     FriProver<B> fri_prover = FriProver<B>::commit(channel, config.fri_config, quotients, *twiddles);
+    fspan.reset();
 
     ht.reset(new HostTimer("pv_grind"));
-    proof.proof_of_work = B::grind(channel.digest(), config.pow_bits);
+    {
+        Span<B> span("Grind");
+        proof.proof_of_work = B::grind(channel.digest(), config.pow_bits);
+    }
     channel.mix_u64(proof.proof_of_work);
     proof.commitments = roots();  // (cached at commit time: no device read)
 
@@ -1233,6 +1265,7 @@ struct ComponentProvers {  // air/components.rs
         if (B::shard_world() > 1)
             for (auto& slot : acc.sub_accumulations)
                 if (slot) B::allreduce_m31(*slot);
+        Span<B> span("Constraints interpolation");
         return acc.finalize(tw);
     }
     static size_t PREPROCESSED_TRACE_IDX_() { return 0; }
@@ -1245,7 +1278,9 @@ StarkProof prove(const std::vector<const ComponentProver<B>*>& components, Blake
     Trace<B> trace{&commitment_scheme.trees};
     QM31 random_coeff = channel.draw_secure_felt();
     std::unique_ptr<HostTimer> ht0(new HostTimer("composition"));
+    std::unique_ptr<Span<B>> cspan(new Span<B>("Composition"));
     std::array<CirclePoly<B>, 4> composition = provers.compute_composition_polynomial(random_coeff, trace, *commitment_scheme.twiddles);
+    cspan.reset();
     ht0.reset(new HostTimer("composition_commit"));
     std::vector<CirclePoly<B>> comp_polys;
     for (auto& p : composition) comp_polys.push_back(std::move(p));

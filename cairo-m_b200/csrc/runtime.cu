@@ -5,6 +5,8 @@
 #include <cstring>
 #include <mutex>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace cm31 {
@@ -234,6 +236,17 @@ int cm31_lanes_join(void) {
         CM_CUDA(cudaStreamWaitEvent(g_main, g_ev_join, 0));
         g_forked = false;
     }
+    return 0;
+}
+// NVTX ranges (no-ops unless a profiler is attached): the prover marks its phases with the span names of the reference's
+// `tracing` instrumentation (stark.hpp Span<B>)
+static const bool g_nvtx_on = getenv("CM31_NO_NVTX") == nullptr;
+int cm31_range_push(const char* name) {
+    if (g_nvtx_on) nvtxRangePushA(name ? name : "");
+    return 0;
+}
+int cm31_range_pop(void) {
+    if (g_nvtx_on) nvtxRangePop();
     return 0;
 }
 int cm31_sync(void) {

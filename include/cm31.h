@@ -47,6 +47,10 @@ int cm31_sync(void);
  * used it.  Calls that return host-readable values must be made on lane 0 after a join. */
 int cm31_lane(int lane);
 int cm31_lanes_join(void);
+/* NVTX range on the profiler timeline (a no-op without a profiler): the host driver marks the proof's phases with the span
+ * names of the reference's `tracing` spans ("Interpolation for commitment", "Extension", "Merkle", "Composition", ..) */
+int cm31_range_push(const char* name);
+int cm31_range_pop(void);
 /* Column<T>::zeros / uninitialized / to_cpu / from_iter  (S/prover/src/core/backend/mod.rs:46-65) */
 int cm31_malloc(void** out, size_t bytes);
 /* Makes the stream-ordered pool hold `factor` x its high-water mark of bytes in use (one allocation + free with the GPU idle):

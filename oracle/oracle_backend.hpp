@@ -127,6 +127,8 @@ struct OracleBackend {
         return store.data();
     }
     static void gather_wait() {}
+    static void range_push(const char*) {}
+    static void range_pop() {}
     static u32 fri_tail_log() { return 0; }  // the CPU backend folds layer by layer
     template <class InnerLayer, class SecureEval, class Tw>
     static void fri_tail(cm31::Blake2sChannel&, std::array<Col, 4>&, u32&, u32, const std::vector<SecureEval>&, size_t&, const Tw&,
