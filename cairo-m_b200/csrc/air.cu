@@ -533,6 +533,10 @@ int cm31_air_program_batch(const cm31_air_batch_item* items, size_t n_items) {
     for (size_t i = 0; i < n_items; i++) {
         const cm31_air_batch_item& it = items[i];
         CM_REQUIRE(it.log_size <= 12, "air_program_batch: small programs only");
+        CM_REQUIRE((it.n_in == 0 || it.in_cols != nullptr) && (it.n_out == 0 || it.out_cols != nullptr) && it.code != nullptr &&
+                       (it.n_consts == 0 || it.consts != nullptr),
+                   "air_program_batch: null table in an item");
+        CM_REQUIRE(it.hist_bins == 0 || it.n_out >= 1, "air_program_batch: a lookup item needs its bin column");
         CM_REQUIRE(it.n_regs <= 512, "air_program_batch: programs of at most 512 registers (larger register files live in local memory: see CudaBackend::BATCH_MAX_REGS)");
         for (size_t k = 0; k < it.n_instr; k++) {
             const u32 op = (u32)(it.code[k] & 0xff);

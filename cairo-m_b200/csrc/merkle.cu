@@ -524,6 +524,12 @@ int cm31_fri_tail(const uint32_t digest_in[8], const cm31_fri_tail_layer* layers
         const cm31_fri_tail_layer& l = layers[i];
         CM_REQUIRE(l.log_size >= 1 && l.log_size <= 15 && l.log_size + 1 <= tw->log_size, "fri_tail: bad layer size");
         CM_REQUIRE(i == 0 || l.log_size + 1 == layers[i - 1].log_size, "fri_tail: layers must halve");
+        CM_REQUIRE(l.tree_levels != nullptr, "fri_tail: null tree level table");
+        for (int k = 0; k < 4; k++) CM_REQUIRE(l.ev_in[k] != nullptr && l.ev_out[k] != nullptr, "fri_tail: null evaluation column");
+        for (u32 j = 0; j <= l.log_size; j++) CM_REQUIRE(l.tree_levels[j] != nullptr, "fri_tail: null tree level");
+        CM_REQUIRE((l.circle[0] == nullptr) == (l.circle[1] == nullptr) && (l.circle[0] == nullptr) == (l.circle[2] == nullptr) &&
+                       (l.circle[0] == nullptr) == (l.circle[3] == nullptr),
+                   "fri_tail: a joining circle evaluation has 4 coordinate columns");
         FriTailLayerDev& d = host[i];
         for (int k = 0; k < 4; k++) {
             d.in[k] = l.ev_in[k];
