@@ -363,9 +363,10 @@ int cm31_bitwise_table_col(int k, uint32_t* col);
  * the data-access log, boundary memory, clock-update rows, Merkle nodes.  A handle comes from cm31_input_create (a caller
  * that ran its own adapter) or from cm31_adapter_import (the runner's logs, adapted on the device). */
 typedef struct cm31_prover_input cm31_prover_input;
-/* Starts the host->device copy of this handle's prover input on the background stream and returns at once; the next
- * cm31_prove_cairo_m on the handle consumes it (oldest first) instead of copying itself: the upload of segment i+1 overlaps
- * the proof of segment i. */
+/* Allocates the device buffers of this handle's prover input and RECORDS its host->device copies (cm31_bg_defer); returns at
+ * once.  A proof that is running, or the next one, releases them at its STARK phase as a throttled copy kernel (DESIGN.md
+ * section 5); the next cm31_prove_cairo_m[_async] on the handle consumes the staged input (oldest first) instead of copying
+ * itself, releasing the copies by plain DMA if no proof did: the upload of segment i+1 overlaps the proof of segment i. */
 int cm31_input_prefetch(cm31_prover_input* h);
 int cm31_input_destroy(cm31_prover_input* h);
 /* info[0] VM steps, [1] data accesses, [2] boundary-memory rows, [3] return value, [4] input bytes staged per proof */
@@ -444,9 +445,11 @@ int cm31_input_describe(cm31_prover_input* h, cm31_prover_input_desc* out);
 int cm31_adapter_import(const uint32_t* trace, size_t n_trace, const uint32_t* memory_trace, size_t n_mem,
                         const uint32_t* initial_memory, size_t n_initial, const uint32_t public_ranges[6],
                         cm31_prover_input** out);
-/* Pipelined form (continuation segments): cm31_adapter_prefetch starts the upload of a segment's logs on the background copy
- * stream and returns at once — the logs must stay valid (and should be page-locked) until cm31_adapter_import_prefetched, which
- * consumes the handle, returns; the adapter kernels and the proof of the previous segment run while the next logs arrive. */
+/* Pipelined form (continuation segments): cm31_adapter_prefetch allocates the device buffers and RECORDS the upload of a
+ * segment's logs; a proof that is running (or runs next) releases it at its STARK phase as a throttled copy kernel,
+ * cm31_adapter_import_prefetched at the latest (plain DMA).  The logs must stay valid (and should be page-locked) until
+ * cm31_adapter_import_prefetched, which consumes the handle, returns; the proof of the previous segment runs while the next
+ * logs arrive. */
 typedef struct cm31_adapter_logs cm31_adapter_logs;
 int cm31_adapter_prefetch(const uint32_t* trace, size_t n_trace, const uint32_t* memory_trace, size_t n_mem,
                           const uint32_t* initial_memory, size_t n_initial, const uint32_t public_ranges[6],
