@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <fstream>
+#include <map>
 #include <set>
 #include <sstream>
 
@@ -37,6 +38,7 @@ static void shape_of(Kernel& k) {
 }
 
 static std::set<uint64_t> g_seen;
+static std::map<uint64_t, std::vector<uint64_t>> g_code_of;  // collision check
 #ifndef GEN_BLOCK
 #define GEN_BLOCK 256
 #endif
@@ -46,7 +48,16 @@ static std::set<uint64_t> g_seen;
 
 static void emit_kernel(std::ostream& os, const Kernel& k, std::vector<std::pair<uint64_t, std::string>>& table) {
     uint64_t h = air_code_hash(k.prog.code.data(), k.prog.code.size());
-    if (!g_seen.insert(h).second) return;
+    if (!g_seen.insert(h).second) {
+        // the same hash must mean the same program (one kernel serves both); a collision between different programs would
+        // make the second one run the first one's kernel
+        if (g_code_of[h] != k.prog.code) {
+            fprintf(stderr, "gen_air_kernels: air_code_hash collision between two different programs (%s)\n", k.name.c_str());
+            exit(1);
+        }
+        return;
+    }
+    g_code_of[h] = k.prog.code;
     const std::string& n = k.name;
     size_t nin = std::max<size_t>(1, k.n_in), nout = std::max<size_t>(1, k.n_out), nc = std::max<size_t>(1, k.n_consts);
     os << "// ---------------------------------------------------------------- " << n << "\n";
