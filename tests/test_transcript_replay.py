@@ -1,0 +1,184 @@
+"""An INDEPENDENT replay of the Fiat-Shamir transcript of a proof, written from the reference's Rust source only -- no C++ of this
+repo is involved beyond producing the proof and printing it in the reference's serde JSON layout.
+
+The oracle prover and the CUDA prover share one protocol driver, so their byte-identity says nothing about
+the ORDER and ENCODING of what is mixed into the channel.  This test re-walks the verifier's side of the transcript exactly as
+
+    crates/prover/src/verifier.rs:17-95                     verify_cairo_m
+    external/stwo/.../core/pcs/mod.rs:42-49, fri.rs:80-89   PcsConfig / FriConfig ::mix_into
+    crates/prover/src/public_data.rs:132-189, 401-412       PublicMemory / PublicData ::mix_into
+    crates/prover/src/components/mod.rs:94-104, 298-308     Claim / InteractionClaim ::mix_into (opcodes in define_opcodes! order)
+    crates/prover/src/components/mod.rs:311-323 + constraint_framework/src/logup.rs:82-95   Relations::draw
+    external/stwo/.../core/prover/mod.rs:87-140             verify: random coefficient, composition root, OODS point
+    external/stwo/.../core/pcs/verifier.rs:55-84            verify_values: sampled values, random coefficient, FRI commit, PoW
+    external/stwo/.../core/fri.rs:370-432                   FriVerifier::commit: layer roots / folding alphas / last layer
+    external/stwo/.../core/channel/blake2s.rs:15-116        Blake2sChannel;  vcs/blake2_merkle.rs:36-46  mix_root
+
+prescribe it (Python + hashlib), and checks the two places where the transcript state is observable in the proof: the
+interaction proof of work (relations.rs:47, 2 bits) after the execution-trace commitment, and the FRI proof of work (16 bits)
+after the last FRI layer.  A prover that mixed anything in another order, width or endianness than the reference passes the
+second check with probability 2^-16.  The query positions drawn afterwards (queries.rs:21-50) are checked for count and range."""
+import ctypes as C
+import hashlib
+import json
+
+import pytest
+
+from tests import cairo_helpers as ch
+from tests.test_proof_json import to_json
+
+P = (1 << 31) - 1
+INTERACTION_POW_BITS = 2  # crates/prover/src/relations.rs:47
+N_RELATIONS = 8           # components/mod.rs:311-323: registers, memory, merkle, poseidon2, range_check_8/16/20, bitwise
+
+
+class Blake2sChannel:  # channel/blake2s.rs:15-116
+    def __init__(self):
+        self.digest = bytes(32)
+        self.n_sent = 0
+
+    def _update(self, data: bytes):
+        self.digest = hashlib.blake2s(self.digest + data, digest_size=32).digest()
+        self.n_sent = 0  # ChannelTime::inc_challenges
+
+    def mix_u32s(self, words):
+        self._update(b"".join(int(w).to_bytes(4, "little") for w in words))
+
+    def mix_u64(self, v):
+        self.mix_u32s([v & 0xFFFFFFFF, v >> 32])
+
+    def mix_felts(self, felts):  # QM31 as [[a, b], [c, d]] (serde of SecureField)
+        self.mix_u32s([x for f in felts for half in f for x in half])
+
+    def mix_root(self, root_bytes):  # Blake2sMerkleChannel::mix_root = concat_and_hash(digest, root)
+        self._update(bytes(root_bytes))
+
+    def draw_random_bytes(self):
+        out = hashlib.blake2s(self.digest + self.n_sent.to_bytes(4, "little"), digest_size=32).digest()
+        self.n_sent += 1
+        return out
+
+    def draw_base_felts(self):
+        while True:
+            b = self.draw_random_bytes()
+            words = [int.from_bytes(b[4 * i:4 * i + 4], "little") for i in range(8)]
+            if all(w < 2 * P for w in words):
+                return [w % P for w in words]
+
+    def draw_secure_felt(self):
+        return self.draw_base_felts()[:4]
+
+    def draw_secure_felts(self, n):
+        out, pool = [], []
+        while len(out) < n:
+            if len(pool) < 4:
+                pool += self.draw_base_felts()
+            out.append(pool[:4])
+            pool = pool[4:]
+        return out
+
+    def trailing_zeros(self):
+        v = int.from_bytes(self.digest[:16], "little")
+        return 128 if v == 0 else (v & -v).bit_length() - 1
+
+
+def replay(proof):
+    """verify_cairo_m's transcript; returns (trailing zeros after interaction_pow, trailing zeros after proof_of_work, channel)."""
+    sp = proof["stark_proof"]
+    ch_ = Blake2sChannel()
+    cfg = sp["config"]
+    ch_.mix_u64(cfg["pow_bits"])                                        # PcsConfig::mix_into
+    ch_.mix_u64(cfg["fri_config"]["log_blowup_factor"])                 # FriConfig::mix_into: blowup, n_queries, last layer bound
+    ch_.mix_u64(cfg["fri_config"]["n_queries"])
+    ch_.mix_u64(cfg["fri_config"]["log_last_layer_degree_bound"])
+    pd = proof["public_data"]                                           # PublicData::mix_into
+    ch_.mix_u32s([pd["initial_registers"]["pc"], pd["initial_registers"]["fp"], pd["final_registers"]["pc"], pd["final_registers"]["fp"],
+                  pd["clock"], pd["initial_root"], pd["final_root"]])
+    pm = pd["public_memory"]
+    ch_.mix_u32s([len(pm["program"]), len(pm["input"]), len(pm["output"])])
+    for part in ("program", "input", "output"):                        # iter().flatten(): None entries are skipped
+        ch_.mix_u32s([w for e in pm[part] if e is not None for w in (e[0], e[1][0][0], e[1][0][1], e[1][1][0], e[1][1][1], e[2])])
+    ch_.mix_root(sp["commitments"][0])                                  # preprocessed trace
+    claim = proof["claim"]                                              # Claim::mix_into
+    for comp in claim["opcodes"].values():
+        ch_.mix_u64(comp["log_size"])
+    for name in ("memory", "merkle", "clock_update", "poseidon2", "range_check_8", "range_check_16", "range_check_20", "bitwise"):
+        ch_.mix_u64(claim[name]["log_size"])
+    ch_.mix_root(sp["commitments"][1])                                  # execution traces
+    ch_.mix_u64(proof["interaction_pow"])
+    tz_interaction = ch_.trailing_zeros()
+    for _ in range(N_RELATIONS):                                        # Relations::draw: [z, alpha] = draw_secure_felts(2) each
+        ch_.draw_secure_felts(2)
+    ic = proof["interaction_claim"]                                     # InteractionClaim::mix_into
+    for comp in ic["opcodes"].values():
+        ch_.mix_felts([comp["claimed_sum"]])
+    for name in ("memory", "merkle", "clock_update", "poseidon2", "range_check_8", "range_check_16", "range_check_20", "bitwise"):
+        ch_.mix_felts([ic[name]["claimed_sum"]])
+    ch_.mix_root(sp["commitments"][2])                                  # interaction traces
+    ch_.draw_secure_felt()                                              # verify(): random_coeff
+    ch_.mix_root(sp["commitments"][3])                                  # composition polynomial
+    ch_.draw_secure_felt()                                              # get_random_point: t
+    ch_.mix_felts([v for tree in sp["sampled_values"] for col in tree for v in col])  # verify_values: flatten_cols
+    ch_.draw_secure_felt()                                              # random_coeff of the quotients
+    fri = sp["fri_proof"]                                               # FriVerifier::commit
+    ch_.mix_root(fri["first_layer"]["commitment"])
+    ch_.draw_secure_felt()
+    for layer in fri["inner_layers"]:
+        ch_.mix_root(layer["commitment"])
+        ch_.draw_secure_felt()
+    ch_.mix_felts(fri["last_layer_poly"]["coeffs"])
+    ch_.mix_u64(sp["proof_of_work"])
+    return tz_interaction, ch_.trailing_zeros(), ch_
+
+
+def check(cm, blob):
+    proof = json.loads(to_json(cm, blob))
+    tz_i, tz_pow, channel = replay(proof)
+    assert tz_i >= INTERACTION_POW_BITS, "interaction proof of work: the transcript up to the execution-trace commitment differs"
+    assert tz_pow >= proof["stark_proof"]["config"]["pow_bits"], "proof of work: the transcript up to the last FRI layer differs"
+    # Queries::generate (queries.rs:21-50): n_queries draws of log_domain_size bits; the distinct sorted positions index the
+    # first FRI layer, whose witness + queried values must cover them: fri_witness holds one value per position's sibling
+    sp = proof["stark_proof"]
+    n_queries = sp["config"]["fri_config"]["n_queries"]
+    max_log = max(c["log_size"] for c in list(proof["claim"]["opcodes"].values()) + [proof["claim"][k] for k in proof["claim"] if k != "opcodes"]) + 1
+    positions, cnt = set(), 0
+    while cnt < n_queries:
+        b = channel.draw_random_bytes()
+        for i in range(8):
+            positions.add(int.from_bytes(b[4 * i:4 * i + 4], "little") & ((1 << max_log) - 1))
+            cnt += 1
+            if cnt == n_queries:
+                break
+    assert 1 <= len(positions) <= n_queries and all(0 <= q < (1 << max_log) for q in positions)
+    return tz_i, tz_pow
+
+
+@pytest.mark.parametrize("program,n", [(ch.FIB, 10), (ch.U32_MIX, 3), (ch.ARRAY_SUM, 7)])
+def test_oracle_proof_transcript_replays_as_the_reference_verifier_prescribes(cm, program, n):
+    blob, _ = ch.oracle_program_prove(program, n)
+    tz_i, tz_pow = check(cm, blob)
+    assert tz_pow >= 16
+
+
+def test_a_reordered_transcript_fails_the_replay(cm):
+    # sensitivity: swap two roots in the proof (what a prover mixing them in the wrong order would produce): the FRI proof
+    # of work no longer verifies
+    blob, _ = ch.oracle_program_prove(ch.FIB, 10)
+    proof = json.loads(to_json(cm, blob))
+    c = proof["stark_proof"]["commitments"]
+    c[2], c[3] = c[3], c[2]
+    assert replay(proof)[1] < 16
+    proof = json.loads(to_json(cm, blob))
+    proof["claim"]["memory"]["log_size"] += 1
+    tz_i, tz_pow, _ = replay(proof)
+    assert tz_pow < 16
+
+
+@pytest.mark.gpu
+def test_gpu_proof_transcript_replays(cm):
+    inp = ch.GpuFibInput(cm, 1000)
+    try:
+        blob, _ = inp.prove()
+    finally:
+        inp.close()
+    check(cm, blob)
