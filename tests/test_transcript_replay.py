@@ -17,10 +17,16 @@ the ORDER and ENCODING of what is mixed into the channel.  This test re-walks th
 prescribe it (Python + hashlib), and checks the two places where the transcript state is observable in the proof: the
 interaction proof of work (relations.rs:47, 2 bits) after the execution-trace commitment, and the FRI proof of work (16 bits)
 after the last FRI layer.  A prover that mixed anything in another order, width or endianness than the reference passes the
-second check with probability 2^-16.  The query positions drawn afterwards (queries.rs:21-50) are checked for count and range."""
+second check with probability 2^-16.  From that channel state the FRI query positions are drawn (queries.rs:21-50,
+fri.rs:560-603) and the Merkle decommitments of all four commitment trees are verified against the committed roots by a Python
+restatement of MerkleVerifier::verify (vcs/verifier.rs:53-171, hasher vcs/blake2_merkle.rs:14-30), with the per-tree column counts
+taken from the reference SOURCE (N_TRACE_COLUMNS / N_*_LOOKUPS constants, tests/golden/air_shapes_reference.json): this pins the
+query derivation, the leaf / node hashing, the column order by size inside a tree and the number of columns every component
+commits, independently of the oracle."""
 import ctypes as C
 import hashlib
 import json
+from pathlib import Path
 
 import pytest
 
@@ -131,16 +137,95 @@ def replay(proof):
     return tz_interaction, ch_.trailing_zeros(), ch_
 
 
-def check(cm, blob):
-    proof = json.loads(to_json(cm, blob))
-    tz_i, tz_pow, channel = replay(proof)
-    assert tz_i >= INTERACTION_POW_BITS, "interaction proof of work: the transcript up to the execution-trace commitment differs"
-    assert tz_pow >= proof["stark_proof"]["config"]["pow_bits"], "proof of work: the transcript up to the last FRI layer differs"
-    # Queries::generate (queries.rs:21-50): n_queries draws of log_domain_size bits; the distinct sorted positions index the
-    # first FRI layer, whose witness + queried values must cover them: fri_witness holds one value per position's sibling
+# ---------------------------------------------------------------- Merkle decommitments (vcs/verifier.rs:53-171)
+def hash_node(children, values):  # Blake2sMerkleHasher::hash_node (vcs/blake2_merkle.rs:14-30)
+    h = hashlib.blake2s(digest_size=32)
+    if children is not None:
+        h.update(children[0])
+        h.update(children[1])
+    for v in values:
+        h.update(int(v).to_bytes(4, "little"))
+    return h.digest()
+
+
+def merkle_verify(root, n_columns_per_log_size, queries_per_log_size, queried_values, decommitment):
+    """MerkleVerifier::verify, statement for statement; returns None or the name of the reference's error."""
+    qv, hw, cw = iter(queried_values), iter(decommitment["hash_witness"]), iter(decommitment["column_witness"])
+    last = None
+    for layer_log_size in range(max(n_columns_per_log_size), -1, -1):
+        n_cols = n_columns_per_log_size.get(layer_log_size, 0)
+        prev_q = [q for q, _ in last] if last is not None else []
+        prev_h, ph = last, 0
+        col_q = list(queries_per_log_size.get(layer_log_size, []))
+        pi = ci = 0
+        total = []
+        while pi < len(prev_q) or ci < len(col_q):
+            node = min(([prev_q[pi] // 2] if pi < len(prev_q) else []) + ([col_q[ci]] if ci < len(col_q) else []))  # next_decommitment_node
+            while pi < len(prev_q) and prev_q[pi] // 2 == node:
+                pi += 1
+            children = None
+            if prev_h is not None:
+                pair = []
+                for child in (2 * node, 2 * node + 1):
+                    if ph < len(prev_h) and prev_h[ph][0] == child:
+                        pair.append(prev_h[ph][1])
+                        ph += 1
+                    else:
+                        w = next(hw, None)
+                        if w is None:
+                            return "WitnessTooShort"
+                        pair.append(bytes(w))
+                children = tuple(pair)
+            if ci < len(col_q) and col_q[ci] == node:
+                ci += 1
+                src, err = qv, "TooFewQueriedValues"
+            else:
+                src, err = cw, "WitnessTooShort"
+            values = [v for v in (next(src, None) for _ in range(n_cols)) if v is not None]
+            if len(values) != n_cols:
+                return err
+            total.append((node, hash_node(children, values)))
+        last = total
+    if next(hw, None) is not None or next(cw, None) is not None:
+        return "WitnessTooLong"
+    if next(qv, None) is not None:
+        return "TooManyQueriedValues"
+    if len(last) != 1 or last[0][1] != bytes(root):
+        return "RootMismatch"
+    return None
+
+
+def tree_column_counts(proof, shapes):
+    """n_columns_per_log_size of the 4 commitment trees (extended sizes: log_size + log_blowup_factor), from the claim and the
+    column counts the reference SOURCE declares (tests/golden/air_shapes_reference.json: N_TRACE_COLUMNS, N_*_LOOKUPS;
+    interaction columns = SECURE_EXTENSION_DEGREE * ceil(lookups / 2), e.g. opcodes/store_fp_imm.rs:96-101, memory.rs:56-59)."""
+    blowup = proof["stark_proof"]["config"]["fri_config"]["log_blowup_factor"]
+    claim = proof["claim"]
+    log_size = dict((name, c["log_size"]) for name, c in claim["opcodes"].items())
+    log_size.update((k, v["log_size"]) for k, v in claim.items() if k != "opcodes")
+    trees = [{}, {}, {}, {}]
+
+    def add(tree, ls, n):
+        trees[tree][ls + blowup] = trees[tree].get(ls + blowup, 0) + n
+    # PreProcessedTraceBuilder::default() (preprocessed/mod.rs:75-83): bitwise(8) = 4 columns of 2*8+2 bits, range checks 8/16/20
+    add(0, 18, 4)
+    for bits in (8, 16, 20):
+        add(0, bits, 1)
+    for comp in shapes["components"]:
+        ls = log_size[comp["name"]]
+        add(1, ls, comp["n_trace_columns"])
+        add(2, ls, 4 * ((sum(comp["lookups"].values()) + 1) // 2))
+    add(3, max(log_size.values()) + 1, 4)  # composition_log_degree_bound = max(log_size + 1), 4 coordinate columns
+    return trees
+
+
+def check_decommitments(proof, channel, shapes):
     sp = proof["stark_proof"]
+    trees = tree_column_counts(proof, shapes)
+    column_log_sizes = sorted({ls for t in trees for ls in t})
+    max_log = column_log_sizes[-1]
+    # Queries::generate (queries.rs:21-40) + get_query_positions_by_log_size (fri.rs:592-603)
     n_queries = sp["config"]["fri_config"]["n_queries"]
-    max_log = max(c["log_size"] for c in list(proof["claim"]["opcodes"].values()) + [proof["claim"][k] for k in proof["claim"] if k != "opcodes"]) + 1
     positions, cnt = set(), 0
     while cnt < n_queries:
         b = channel.draw_random_bytes()
@@ -149,7 +234,30 @@ def check(cm, blob):
             cnt += 1
             if cnt == n_queries:
                 break
-    assert 1 <= len(positions) <= n_queries and all(0 <= q < (1 << max_log) for q in positions)
+    positions = sorted(positions)
+    per_log = {}
+    for ls in column_log_sizes:
+        folded = []
+        for q in positions:
+            f = q >> (max_log - ls)
+            if not folded or folded[-1] != f:
+                folded.append(f)
+        per_log[ls] = folded
+    for t in range(4):
+        err = merkle_verify(sp["commitments"][t], trees[t], per_log, sp["queried_values"][t], sp["decommitments"][t])
+        assert err is None, f"tree {t}: {err}"
+    return trees, per_log
+
+
+def check(cm, blob):
+    proof = json.loads(to_json(cm, blob))
+    tz_i, tz_pow, channel = replay(proof)
+    assert tz_i >= INTERACTION_POW_BITS, "interaction proof of work: the transcript up to the execution-trace commitment differs"
+    assert tz_pow >= proof["stark_proof"]["config"]["pow_bits"], "proof of work: the transcript up to the last FRI layer differs"
+    # the channel now stands where the reference verifier draws the FRI queries: the 4 trees' decommitments must verify at
+    # exactly those positions, against the committed roots, with the column counts the reference source declares
+    shapes = json.loads((Path(__file__).resolve().parent / "golden" / "air_shapes_reference.json").read_text())
+    check_decommitments(proof, channel, shapes)
     return tz_i, tz_pow
 
 
@@ -172,6 +280,18 @@ def test_a_reordered_transcript_fails_the_replay(cm):
     proof["claim"]["memory"]["log_size"] += 1
     tz_i, tz_pow, _ = replay(proof)
     assert tz_pow < 16
+    # ... and the decommitment check is not vacuous: one flipped queried value, or one column too many, is caught
+    shapes = json.loads((Path(__file__).resolve().parent / "golden" / "air_shapes_reference.json").read_text())
+    proof = json.loads(to_json(cm, blob))
+    _, _, channel = replay(proof)
+    proof["stark_proof"]["queried_values"][1][5] ^= 1
+    with pytest.raises(AssertionError, match="tree 1: RootMismatch"):
+        check_decommitments(proof, channel, shapes)
+    proof = json.loads(to_json(cm, blob))
+    _, _, channel = replay(proof)
+    shapes["components"][0]["n_trace_columns"] += 1
+    with pytest.raises(AssertionError, match="tree 1"):
+        check_decommitments(proof, channel, shapes)
 
 
 @pytest.mark.gpu
