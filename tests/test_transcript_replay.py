@@ -22,7 +22,10 @@ fri.rs:560-603) and the Merkle decommitments of all four commitment trees are ve
 restatement of MerkleVerifier::verify (vcs/verifier.rs:53-171, hasher vcs/blake2_merkle.rs:14-30), with the per-tree column counts
 taken from the reference SOURCE (N_TRACE_COLUMNS / N_*_LOOKUPS constants, tests/golden/air_shapes_reference.json): this pins the
 query derivation, the leaf / node hashing, the column order by size inside a tree and the number of columns every component
-commits, independently of the oracle."""
+commits, independently of the oracle.  Between the two, the closing sum of the lookup argument (verifier.rs:64-72:
+InteractionClaim::claimed_sum with PublicData::initial_logup_sum, public_data.rs:287-399) is recomputed with a Python QM31 and
+the relation elements in Relations::draw order: it is zero only if the relations are drawn in the reference's order and
+`combine`, the register / Merkle-root / public-memory terms and every component's claimed sum are the reference's."""
 import ctypes as C
 import hashlib
 import json
@@ -113,8 +116,11 @@ def replay(proof):
     ch_.mix_root(sp["commitments"][1])                                  # execution traces
     ch_.mix_u64(proof["interaction_pow"])
     tz_interaction = ch_.trailing_zeros()
+    rels = []
     for _ in range(N_RELATIONS):                                        # Relations::draw: [z, alpha] = draw_secure_felts(2) each
-        ch_.draw_secure_felts(2)
+        z, alpha = ch_.draw_secure_felts(2)
+        rels.append((q_from(z), q_from(alpha)))
+    ch_.relations = rels
     ic = proof["interaction_claim"]                                     # InteractionClaim::mix_into
     for comp in ic["opcodes"].values():
         ch_.mix_felts([comp["claimed_sum"]])
@@ -135,6 +141,96 @@ def replay(proof):
     ch_.mix_felts(fri["last_layer_poly"]["coeffs"])
     ch_.mix_u64(sp["proof_of_work"])
     return tz_interaction, ch_.trailing_zeros(), ch_
+
+
+# ---------------------------------------------------------------- the lookup argument's closing sum (verifier.rs:64-72)
+# QM31 = CM31[u] / (u^2 - 2 - i), CM31 = M31[i] / (i^2 + 1)  (core/fields/cm31.rs, qm31.rs:14-129); values as [[a, b], [c, d]]
+def m_inv(x):
+    return pow(x, P - 2, P)
+
+
+def c_mul(x, y):
+    return [(x[0] * y[0] - x[1] * y[1]) % P, (x[0] * y[1] + x[1] * y[0]) % P]
+
+
+def c_add(x, y):
+    return [(x[0] + y[0]) % P, (x[1] + y[1]) % P]
+
+
+def c_sub(x, y):
+    return [(x[0] - y[0]) % P, (x[1] - y[1]) % P]
+
+
+def c_inv(x):
+    n = m_inv((x[0] * x[0] + x[1] * x[1]) % P)
+    return [x[0] * n % P, (-x[1]) * n % P]
+
+
+R = [2, 1]  # qm31.rs:14
+
+
+def q_mul(x, y):  # (a + bu)(c + du) = (ac + R bd) + (ad + bc) u   (qm31.rs:78-88)
+    return [c_add(c_mul(x[0], y[0]), c_mul(R, c_mul(x[1], y[1]))), c_add(c_mul(x[0], y[1]), c_mul(x[1], y[0]))]
+
+
+def q_add(x, y):
+    return [c_add(x[0], y[0]), c_add(x[1], y[1])]
+
+
+def q_neg(x):
+    return [[(-x[0][0]) % P, (-x[0][1]) % P], [(-x[1][0]) % P, (-x[1][1]) % P]]
+
+
+def q_inv(x):  # (a + bu)^-1 = (a - bu) / (a^2 - R b^2)   (qm31.rs:119-129)
+    d = c_inv(c_sub(c_mul(x[0], x[0]), c_mul(R, c_mul(x[1], x[1]))))
+    return [c_mul(x[0], d), c_mul([(-x[1][0]) % P, (-x[1][1]) % P], d)]
+
+
+def q_from(felts4):
+    return [[felts4[0], felts4[1]], [felts4[2], felts4[3]]]
+
+
+def combine(rel, values):  # LookupElements::combine (constraint_framework/src/logup.rs:96-111): sum alpha^i v_i - z
+    z, alpha = rel
+    acc, power = [[0, 0], [0, 0]], [[1, 0], [0, 0]]
+    for v in values:
+        acc = q_add(acc, q_mul(power, [[v % P, 0], [0, 0]]))
+        power = q_mul(power, alpha)
+    return q_add(acc, q_neg(z))
+
+
+TREE_HEIGHT = 30  # adapter/merkle.rs:62: MAX_MEMORY_LOG_SIZE (28) + QM31_LOG_SIZE (2)
+
+
+def logup_total(proof, rels):
+    """InteractionClaim::claimed_sum (components/mod.rs:283-296) with PublicData::initial_logup_sum (public_data.rs:287-399);
+    rels = the 8 [z, alpha] pairs in Relations::draw order: registers, memory, merkle, poseidon2, rc8, rc16, rc20, bitwise."""
+    registers, memory, merkle = rels[0], rels[1], rels[2]
+    pd = proof["public_data"]
+    one = [[1, 0], [0, 0]]
+    terms = [
+        combine(registers, [pd["initial_registers"]["pc"], pd["initial_registers"]["fp"], 1]),
+        q_neg(combine(registers, [pd["final_registers"]["pc"], pd["final_registers"]["fp"], pd["clock"] + 1])),
+        combine(merkle, [0, 0, pd["initial_root"], pd["initial_root"]]),
+        combine(merkle, [0, 0, pd["final_root"], pd["final_root"]]),
+    ]
+    for part, mult, root in (("program", one, pd["initial_root"]), ("input", one, pd["initial_root"]), ("output", q_neg(one), pd["final_root"])):
+        for e in pd["public_memory"][part]:
+            if e is None:
+                continue
+            addr, value, clock = e[0], [value for half in e[1] for value in half], e[2]
+            terms.append(q_mul(mult, combine(memory, [addr, clock] + value)))
+            for k in range(4):
+                terms.append(q_neg(combine(merkle, [4 * addr + k, TREE_HEIGHT, value[k], root])))
+    total = [[0, 0], [0, 0]]
+    for t in terms:
+        total = q_add(total, q_inv(t))
+    ic = proof["interaction_claim"]
+    for comp in ic["opcodes"].values():
+        total = q_add(total, comp["claimed_sum"])
+    for name in ("memory", "merkle", "clock_update", "poseidon2", "range_check_8", "range_check_16", "range_check_20", "bitwise"):
+        total = q_add(total, ic[name]["claimed_sum"])
+    return total
 
 
 # ---------------------------------------------------------------- Merkle decommitments (vcs/verifier.rs:53-171)
@@ -254,6 +350,8 @@ def check(cm, blob):
     tz_i, tz_pow, channel = replay(proof)
     assert tz_i >= INTERACTION_POW_BITS, "interaction proof of work: the transcript up to the execution-trace commitment differs"
     assert tz_pow >= proof["stark_proof"]["config"]["pow_bits"], "proof of work: the transcript up to the last FRI layer differs"
+    # InvalidLogupSum (verifier.rs:64-72): the claimed sums plus the public data's terms cancel under the relations drawn above
+    assert logup_total(proof, channel.relations) == [[0, 0], [0, 0]], "the lookup argument does not close"
     # the channel now stands where the reference verifier draws the FRI queries: the 4 trees' decommitments must verify at
     # exactly those positions, against the committed roots, with the column counts the reference source declares
     shapes = json.loads((Path(__file__).resolve().parent / "golden" / "air_shapes_reference.json").read_text())
@@ -280,6 +378,15 @@ def test_a_reordered_transcript_fails_the_replay(cm):
     proof["claim"]["memory"]["log_size"] += 1
     tz_i, tz_pow, _ = replay(proof)
     assert tz_pow < 16
+    # the closing sum is zero only under the reference's relation order and public-data terms
+    proof = json.loads(to_json(cm, blob))
+    _, _, channel = replay(proof)
+    rels = list(channel.relations)
+    assert logup_total(proof, rels) == [[0, 0], [0, 0]]
+    rels[1], rels[2] = rels[2], rels[1]  # memory <-> merkle
+    assert logup_total(proof, rels) != [[0, 0], [0, 0]]
+    proof["public_data"]["clock"] += 1
+    assert logup_total(proof, channel.relations) != [[0, 0], [0, 0]]
     # ... and the decommitment check is not vacuous: one flipped queried value, or one column too many, is caught
     shapes = json.loads((Path(__file__).resolve().parent / "golden" / "air_shapes_reference.json").read_text())
     proof = json.loads(to_json(cm, blob))
